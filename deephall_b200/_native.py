@@ -1,0 +1,268 @@
+"""ctypes binding of libdeephall_b200.so (the C ABI in include/deephall_b200.h).
+
+There is no fallback: if the shared library is missing or CUDA is unavailable every compute
+call raises.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdeephall_b200.so")
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class dh_config(C.Structure):
+    _fields_ = [
+        ("n_up", C.c_int32),
+        ("n_dn", C.c_int32),
+        ("flux", C.c_int32),
+        ("ndets", C.c_int32),
+        ("num_heads", C.c_int32),
+        ("heads_dim", C.c_int32),
+        ("num_layers", C.c_int32),
+        ("interaction_type", C.c_int32),
+        ("interaction_strength", C.c_float),
+        ("radius", C.c_float),
+        ("chunk_walkers", C.c_int32),
+    ]
+
+
+class dh_param_entry(C.Structure):
+    _fields_ = [("name", C.c_char * 96), ("offset", C.c_int64), ("ndim", C.c_int32), ("shape", C.c_int32 * 4)]
+
+
+OP_LOGPSI, OP_LOCAL_ENERGY, OP_MCMC, OP_VJP = 0, 1, 2, 3
+
+# symbol -> (restype, argtypes); must list every function include/deephall_b200.h declares
+_vp, _i64, _i32, _u64, _f = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_float
+SIGNATURES = OrderedDict(
+    dh_plan_create=(C.c_int, [C.POINTER(dh_config), C.POINTER(_vp)]),
+    dh_plan_destroy=(C.c_int, [_vp]),
+    dh_version=(C.c_char_p, []),
+    dh_param_count=(_i64, [_vp]),
+    dh_param_layout=(C.c_int, [_vp, C.POINTER(dh_param_entry), C.POINTER(_i32)]),
+    dh_workspace_bytes=(C.c_int, [_vp, C.c_int, _i64, C.POINTER(C.c_size_t)]),
+    dh_logpsi=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
+    dh_local_energy=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    dh_potential=(C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    dh_mcmc_sweep=(C.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _u64, _u64, _u64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    dh_mcmc_propose=(C.c_int, [_vp, _vp, _i64, _f, _u64, _u64, _u64, _vp, _vp, _vp]),
+    dh_mcmc_accept=(C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _u64, _vp, _vp, _vp]),
+    dh_init_walkers=(C.c_int, [_vp, _vp, _i64, _u64, _u64, _vp]),
+    dh_logpsi_vjp=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    dh_slogdet=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    dh_debug_buffer=(C.c_int, [_vp, C.c_int, _i64, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+)
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (raises NativeError if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise NativeError(
+            f"{_LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C deephall_b200/csrc).  There is no CPU fallback."
+        )
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        if rc > 0:
+            raise NativeError(f"{what}: CUDA error {rc}")
+        raise NativeError(f"{what}: error {rc} ({ {-1: 'bad argument', -2: 'unsupported', -3: 'workspace too small'}.get(rc, '?')})")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device, contiguous tensors only"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda():
+    if not torch.cuda.is_available():
+        raise NativeError("deephall_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+class Plan:
+    """One plan per (device, configuration).  Thin, stream-ordered wrappers over the C ABI."""
+
+    def __init__(self, nspins=(3, 0), flux=2, ndets=1, num_heads=4, heads_dim=64, num_layers=2,
+                 interaction_type="coulomb", interaction_strength=1.0, radius=None, chunk_walkers=0):
+        _need_cuda()
+        self.lib = load()
+        self.cfg = dh_config(
+            int(nspins[0]), int(nspins[1]), int(flux), int(ndets), int(num_heads), int(heads_dim), int(num_layers),
+            0 if str(interaction_type) == "coulomb" else 1, float(interaction_strength),
+            float(radius) if radius else 0.0, int(chunk_walkers),
+        )
+        self.N = int(nspins[0]) + int(nspins[1])
+        self.R = 2 * self.N + 8
+        h = C.c_void_p()
+        _check(self.lib.dh_plan_create(C.byref(self.cfg), C.byref(h)), "dh_plan_create")
+        self.handle = h
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.dh_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- parameters
+    @property
+    def num_params(self) -> int:
+        return int(self.lib.dh_param_count(self.handle))
+
+    def param_layout(self):
+        n = C.c_int32(0)
+        _check(self.lib.dh_param_layout(self.handle, None, C.byref(n)), "dh_param_layout")
+        arr = (dh_param_entry * n.value)()
+        _check(self.lib.dh_param_layout(self.handle, arr, C.byref(n)), "dh_param_layout")
+        out = OrderedDict()
+        for e in arr:
+            out[e.name.decode()] = (int(e.offset), tuple(int(e.shape[i]) for i in range(e.ndim)))
+        return out
+
+    # ---- workspace
+    def workspace(self, op: int, B: int):
+        nbytes = C.c_size_t(0)
+        _check(self.lib.dh_workspace_bytes(self.handle, op, B, C.byref(nbytes)), "dh_workspace_bytes")
+        if self._ws is None or self._ws.numel() < nbytes.value:
+            self._ws = None
+            self._ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+        return self._ws
+
+    def debug_buffer(self, op: int, B: int, name: str):
+        off, cnt = C.c_int64(0), C.c_int64(0)
+        _check(self.lib.dh_debug_buffer(self.handle, op, B, name.encode(), C.byref(off), C.byref(cnt)), "dh_debug_buffer")
+        base = (self._ws.data_ptr() + 255) // 256 * 256 - self._ws.data_ptr()
+        fl = self._ws[base:].view(torch.float32) if (self._ws.numel() - base) % 4 == 0 else self._ws[base : base + (self._ws.numel() - base) // 4 * 4].view(torch.float32)
+        return fl[off.value : off.value + cnt.value]
+
+    # ---- ops
+    def logpsi(self, params, x):
+        B = x.shape[0]
+        out = torch.empty((B, 2), dtype=torch.float32, device=x.device)
+        ws = self.workspace(OP_LOGPSI, B)
+        _check(self.lib.dh_logpsi(self.handle, _ptr(params), _ptr(x), B, _ptr(out), _ptr(ws), ws.numel(), _stream()), "dh_logpsi")
+        return torch.view_as_complex(out)
+
+    def local_energy(self, params, x):
+        B = x.shape[0]
+        dev = x.device
+        el = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        kin = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        pot, lz, lz2, l2 = (torch.empty((B,), dtype=torch.float32, device=dev) for _ in range(4))
+        lpsi = torch.empty((B, 2), dtype=torch.float32, device=dev)
+        ws = self.workspace(OP_LOCAL_ENERGY, B)
+        _check(
+            self.lib.dh_local_energy(self.handle, _ptr(params), _ptr(x), B, _ptr(el), _ptr(kin), _ptr(pot), _ptr(lz),
+                                     _ptr(lz2), _ptr(l2), _ptr(lpsi), _ptr(ws), ws.numel(), _stream()),
+            "dh_local_energy",
+        )
+        return {
+            "energy": torch.view_as_complex(el),
+            "kinetic": torch.view_as_complex(kin),
+            "potential": pot,
+            "angular_momentum_z": lz,
+            "angular_momentum_z_square": lz2,
+            "angular_momentum_square": l2,
+            "logpsi": torch.view_as_complex(lpsi),
+        }
+
+    def potential(self, x):
+        out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+        _check(self.lib.dh_potential(self.handle, _ptr(x), x.shape[0], _ptr(out), _stream()), "dh_potential")
+        return out
+
+    def mcmc_sweep(self, params, x, steps, width, seed=0, offset=0, subsequence0=0, randoms=None, want_lp=False):
+        """In-place on x.  Returns (naccept device int64 tensor, lp or None)."""
+        B = x.shape[0]
+        nacc = torch.zeros((1,), dtype=torch.int64, device=x.device)
+        lp = torch.empty((B,), dtype=torch.float32, device=x.device) if want_lp else None
+        ws = self.workspace(OP_MCMC, B)
+        _check(
+            self.lib.dh_mcmc_sweep(self.handle, _ptr(params), _ptr(x), B, int(steps), float(width), int(seed), int(offset),
+                                   int(subsequence0), _ptr(randoms), _ptr(nacc), _ptr(lp), _ptr(ws), ws.numel(), _stream()),
+            "dh_mcmc_sweep",
+        )
+        return nacc, lp
+
+    def mcmc_propose(self, x1, width, seed=0, offset=0, subsequence0=0, randoms=None):
+        x2 = torch.empty_like(x1)
+        _check(self.lib.dh_mcmc_propose(self.handle, _ptr(x1), x1.shape[0], float(width), int(seed), int(offset),
+                                        int(subsequence0), _ptr(randoms), _ptr(x2), _stream()), "dh_mcmc_propose")
+        return x2
+
+    def mcmc_accept(self, x1, x2, lp1, lp2, seed=0, offset=0, subsequence0=0, randoms=None):
+        nacc = torch.zeros((1,), dtype=torch.int64, device=x1.device)
+        _check(self.lib.dh_mcmc_accept(self.handle, _ptr(x1), _ptr(x2), _ptr(lp1), _ptr(lp2), x1.shape[0], int(seed),
+                                       int(offset), int(subsequence0), _ptr(randoms), _ptr(nacc), _stream()), "dh_mcmc_accept")
+        return nacc
+
+    def init_walkers(self, B, seed=0, subsequence0=0, device="cuda"):
+        x = torch.empty((B, self.N, 2), dtype=torch.float32, device=device)
+        _check(self.lib.dh_init_walkers(self.handle, _ptr(x), B, int(seed), int(subsequence0), _stream()), "dh_init_walkers")
+        return x
+
+    def logpsi_vjp(self, params, x, cot, want_logpsi=False):
+        B = x.shape[0]
+        grad = torch.empty_like(params)
+        lpsi = torch.empty((B, 2), dtype=torch.float32, device=x.device) if want_logpsi else None
+        ws = self.workspace(OP_VJP, B)
+        _check(self.lib.dh_logpsi_vjp(self.handle, _ptr(params), _ptr(x), B, _ptr(cot), _ptr(grad), _ptr(lpsi), _ptr(ws),
+                                      ws.numel(), _stream()), "dh_logpsi_vjp")
+        return (grad, torch.view_as_complex(lpsi)) if want_logpsi else grad
+
+
+def slogdet(mats):
+    """mats: (B, K, n, n) complex64 cuda -> (sign (B,K) c64, logabs (B,K) f32, logpsi (B,) c64)."""
+    _need_cuda()
+    lib = load()
+    B, K, n, _ = mats.shape
+    m = torch.view_as_real(mats.contiguous())
+    sign = torch.empty((B, K, 2), dtype=torch.float32, device=mats.device)
+    logabs = torch.empty((B, K), dtype=torch.float32, device=mats.device)
+    lpsi = torch.empty((B, 2), dtype=torch.float32, device=mats.device)
+    _check(lib.dh_slogdet(_ptr(m), B, K, n, _ptr(sign), _ptr(logabs), _ptr(lpsi), _stream()), "dh_slogdet")
+    return torch.view_as_complex(sign), logabs, torch.view_as_complex(lpsi)
+
+
+def gemm(A, W, bias=None, rows_per_group=1, out=None, accumulate=False, impl=0):
+    _need_cuda()
+    lib = load()
+    M, K = A.shape
+    N = W.shape[1]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    _check(lib.dh_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, rows_per_group, int(accumulate), impl, _stream()), "dh_gemm")
+    return out

@@ -1,0 +1,412 @@
+// C ABI (include/deephall_b200.h): plan, parameter layout, workspace carving and the launch
+// sequences of the four hot-path operations.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/deephall_b200.h"
+#include "kernels.h"
+
+using namespace dh;
+
+struct LayerOff {
+  int64_t q_k, q_b, k_k, k_b, v_k, v_b, o_k, o_b, d1_k, ln0_s, ln0_b, d2_k, d2_b, ln1_s, ln1_b;
+};
+
+struct dh_plan {
+  dh_config cfg;
+  int N, L, K, D, H, hd, nl, twoQ, LNK;
+  float Q, radius;
+  std::vector<dh_param_entry> entries;
+  int64_t nparams;
+  int64_t off_W0;
+  std::vector<LayerOff> layer;
+  int64_t orb_re_k, orb_re_b, orb_im_k, orb_im_b, ee_par;
+  double* d_normfac;
+  int gemm_impl;  // 0 = SIMT, 1 = tcgen05 3xTF32
+  // prepared (pre-split, transposed) weights for the tcgen05 path
+  float* prep;            // device buffer owned by the plan
+  size_t prep_floats;
+  const float* prep_src;  // params pointer the preparation was made from
+};
+
+static void add_entry(dh_plan* p, const std::string& name, std::vector<int> shape, int64_t* off_out) {
+  dh_param_entry e;
+  memset(&e, 0, sizeof(e));
+  snprintf(e.name, sizeof(e.name), "%s", name.c_str());
+  e.offset = p->nparams;
+  e.ndim = (int)shape.size();
+  int64_t n = 1;
+  for (size_t i = 0; i < shape.size(); ++i) { e.shape[i] = shape[i]; n *= shape[i]; }
+  p->entries.push_back(e);
+  if (off_out) *off_out = p->nparams;
+  p->nparams += n;
+}
+
+static double binom(int n, int k) {
+  double r = 1.0;
+  for (int i = 1; i <= k; ++i) r = r * (double)(n - k + i) / (double)i;
+  return r;
+}
+
+extern "C" const char* dh_version(void) { return "deephall_b200 0.1 (sm_100a)"; }
+
+extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
+  if (!cfg || !out) return DH_E_BADARG;
+  if (cfg->n_up < 1 || cfg->flux < 0 || cfg->ndets < 1 || cfg->num_heads < 1 || cfg->heads_dim < 1 ||
+      cfg->num_layers < 0)
+    return DH_E_BADARG;
+  if (cfg->n_dn != 0) return DH_E_UNSUPPORTED;  // spin-unpolarised systems: SURVEY 8f N4 (next)
+  dh_plan* p = new dh_plan();
+  p->cfg = *cfg;
+  p->N = cfg->n_up + cfg->n_dn;
+  p->twoQ = cfg->flux;
+  p->L = cfg->flux + 1;
+  p->K = cfg->ndets;
+  p->H = cfg->num_heads;
+  p->hd = cfg->heads_dim;
+  p->D = p->H * p->hd;
+  p->nl = cfg->num_layers;
+  p->Q = 0.5f * cfg->flux;
+  p->radius = cfg->radius > 0.f ? cfg->radius : sqrtf(p->Q);
+  p->LNK = p->L * p->N * p->K;
+  p->nparams = 0;
+  p->prep = nullptr;
+  p->prep_floats = 0;
+  p->prep_src = nullptr;
+  p->gemm_impl = 0;
+  if (p->N > 16 || p->D % 32 != 0 || p->D > 256 || p->hd % 4 != 0) { delete p; return DH_E_UNSUPPORTED; }
+  const int D = p->D, H = p->H, hd = p->hd, N = p->N, L = p->L, K = p->K;
+  const std::string pl = "PsiformerLayers_0/";
+  add_entry(p, pl + "Dense_0/kernel", {4, D}, &p->off_W0);
+  p->layer.resize(p->nl);
+  for (int l = 0; l < p->nl; ++l) {
+    LayerOff& o = p->layer[l];
+    const std::string a = pl + "MultiHeadAttention_" + std::to_string(l) + "/";
+    add_entry(p, a + "query/kernel", {D, H, hd}, &o.q_k);
+    add_entry(p, a + "query/bias", {H, hd}, &o.q_b);
+    add_entry(p, a + "key/kernel", {D, H, hd}, &o.k_k);
+    add_entry(p, a + "key/bias", {H, hd}, &o.k_b);
+    add_entry(p, a + "value/kernel", {D, H, hd}, &o.v_k);
+    add_entry(p, a + "value/bias", {H, hd}, &o.v_b);
+    add_entry(p, a + "out/kernel", {H, hd, D}, &o.o_k);
+    add_entry(p, a + "out/bias", {D}, &o.o_b);
+    add_entry(p, pl + "Dense_" + std::to_string(1 + 2 * l) + "/kernel", {D, D}, &o.d1_k);
+    add_entry(p, pl + "LayerNorm_" + std::to_string(2 * l) + "/scale", {D}, &o.ln0_s);
+    add_entry(p, pl + "LayerNorm_" + std::to_string(2 * l) + "/bias", {D}, &o.ln0_b);
+    add_entry(p, pl + "Dense_" + std::to_string(2 + 2 * l) + "/kernel", {D, D}, &o.d2_k);
+    add_entry(p, pl + "Dense_" + std::to_string(2 + 2 * l) + "/bias", {D}, &o.d2_b);
+    add_entry(p, pl + "LayerNorm_" + std::to_string(2 * l + 1) + "/scale", {D}, &o.ln1_s);
+    add_entry(p, pl + "LayerNorm_" + std::to_string(2 * l + 1) + "/bias", {D}, &o.ln1_b);
+  }
+  const std::string ob = "Orbitals_0/featured_orbitals/";
+  add_entry(p, ob + "DenseGeneral_0/kernel", {D, L, N, K}, &p->orb_re_k);
+  add_entry(p, ob + "DenseGeneral_0/bias", {L, N, K}, &p->orb_re_b);
+  add_entry(p, ob + "DenseGeneral_1/kernel", {D, L, N, K}, &p->orb_im_k);
+  add_entry(p, ob + "DenseGeneral_1/bias", {L, N, K}, &p->orb_im_b);
+  p->ee_par = -1;
+  if (cfg->n_up >= 2) add_entry(p, "Jastrow_0/ee_par", {1}, &p->ee_par);
+
+  // sqrt(C(2Q, Q-m)) for m = -Q..Q  (blocks.py:45-46); index a = Q+m -> C(2Q, 2Q-a) = C(2Q, a)
+  std::vector<double> nf(L);
+  for (int a = 0; a < L; ++a) nf[a] = sqrt(binom(p->twoQ, a));
+  cudaError_t e = cudaMalloc(&p->d_normfac, L * sizeof(double));
+  if (e != cudaSuccess) { delete p; return (int)e; }
+  e = cudaMemcpy(p->d_normfac, nf.data(), L * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(p->d_normfac); delete p; return (int)e; }
+  *out = p;
+  return 0;
+}
+
+extern "C" int dh_plan_destroy(dh_plan* p) {
+  if (!p) return DH_E_BADARG;
+  if (p->d_normfac) cudaFree(p->d_normfac);
+  if (p->prep) cudaFree(p->prep);
+  delete p;
+  return 0;
+}
+
+extern "C" int64_t dh_param_count(const dh_plan* p) { return p ? p->nparams : -1; }
+
+extern "C" int dh_param_layout(const dh_plan* p, dh_param_entry* entries, int32_t* n) {
+  if (!p || !n) return DH_E_BADARG;
+  if (entries) {
+    if (*n < (int32_t)p->entries.size()) return DH_E_BADARG;
+    memcpy(entries, p->entries.data(), p->entries.size() * sizeof(dh_param_entry));
+  }
+  *n = (int32_t)p->entries.size();
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- workspace
+struct FwdWs {
+  float *h, *t1, *t2, *qkv, *att, *cbuf, *Mj, *ld, *lpjet, *Minv;
+  size_t floats;
+};
+
+static inline size_t al(size_t n) { return (n + 63) / 64 * 64; }  // 256-byte granules
+
+static int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
+  int64_t c = p->cfg.chunk_walkers > 0 ? p->cfg.chunk_walkers : (jets ? 1024 : 16384);
+  return B < c ? B : c;
+}
+
+static FwdWs carve_fwd(const dh_plan* p, float* base, int64_t Bc, bool jets, bool keep_inverse) {
+  const int R = jets ? 2 * p->N + 8 : 1;
+  const size_t rows = (size_t)Bc * p->N * R;
+  FwdWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
+  w.h = take(rows * p->D);
+  w.t1 = take(rows * p->D);
+  w.t2 = take(rows * p->D);
+  w.qkv = take(rows * 3 * p->D);
+  w.att = take(rows * p->D);
+  w.cbuf = take(rows * 2 * (size_t)p->LNK);
+  w.Mj = take((size_t)Bc * p->K * R * p->N * p->N * 2);
+  w.ld = take((size_t)Bc * p->K * R * 2);
+  w.lpjet = take((size_t)Bc * R * 2);
+  w.Minv = keep_inverse ? take((size_t)Bc * p->K * p->N * p->N * 2) : nullptr;
+  w.floats = off;
+  return w;
+}
+
+struct McmcWs {
+  float *x2, *lp1, *logpsi2;
+  size_t floats;
+};
+static McmcWs carve_mcmc(const dh_plan* p, float* base, int64_t B) {
+  McmcWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
+  w.x2 = take((size_t)B * p->N * 2);
+  w.lp1 = take((size_t)B);
+  w.logpsi2 = take((size_t)B * 2);
+  w.floats = off;
+  return w;
+}
+
+size_t vjp_ws_floats(const dh_plan* p, int64_t Bc);  // api_vjp.cu
+
+extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* bytes) {
+  if (!p || !bytes || B < 0) return DH_E_BADARG;
+  size_t fl = 0;
+  switch (op) {
+    case DH_OP_LOGPSI: fl = carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats; break;
+    case DH_OP_LOCAL_ENERGY: fl = carve_fwd(p, nullptr, pick_chunk(p, true, B), true, false).floats; break;
+    case DH_OP_MCMC:
+      fl = carve_mcmc(p, nullptr, B).floats + carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats;
+      break;
+    case DH_OP_VJP: fl = vjp_ws_floats(p, pick_chunk(p, false, B)); break;
+    default: return DH_E_BADARG;
+  }
+  *bytes = fl * sizeof(float) + 256;
+  return 0;
+}
+
+static inline float* align_ws(void* ws) {
+  uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+  return reinterpret_cast<float*>(a);
+}
+
+// --------------------------------------------------------------------------------- forward
+// C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
+static int dense(const dh_plan* p, const float* A, const float* W, const float* bias, float* C, int64_t rows,
+                 int Nout, int64_t ldc, int R, cudaStream_t s) {
+  return gemm_simt(A, W, bias, C, rows, Nout, p->D, p->D, 1, Nout, 1, ldc, R, 0, 1, s);
+}
+
+// Runs the network body + tail for Bc walkers whose coordinates are x; fills w.ld / outputs.
+int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, bool jets, const FwdWs& w,
+                  FinalizeArgs fa, cudaStream_t s) {
+  const int N = p->N, D = p->D;
+  const int R = jets ? 2 * N + 8 : 1;
+  const int64_t rows = Bc * N * R;
+  NetDims nd{N, R, D, p->H, p->hd, p->cfg.n_up};
+  TailDims td{N, R, p->L, p->K, p->twoQ, p->cfg.n_up};
+  int rc;
+  if ((rc = features_dense0(x, P + p->off_W0, w.h, Bc, nd, s))) return rc;
+  for (int l = 0; l < p->nl; ++l) {
+    const LayerOff& o = p->layer[l];
+    if ((rc = dense(p, w.h, P + o.q_k, P + o.q_b, w.qkv, rows, D, 3 * D, R, s))) return rc;
+    if ((rc = dense(p, w.h, P + o.k_k, P + o.k_b, w.qkv + D, rows, D, 3 * D, R, s))) return rc;
+    if ((rc = dense(p, w.h, P + o.v_k, P + o.v_b, w.qkv + 2 * D, rows, D, 3 * D, R, s))) return rc;
+    if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, s);
+    else rc = attention_value(w.qkv, w.att, Bc, nd, s);
+    if (rc) return rc;
+    if ((rc = dense(p, w.att, P + o.o_k, P + o.o_b, w.t1, rows, D, D, R, s))) return rc;
+    if ((rc = dense(p, w.t1, P + o.d1_k, nullptr, w.t2, rows, D, D, R, s))) return rc;
+    if ((rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s))) return rc;
+    if ((rc = dense(p, w.h, P + o.d2_k, P + o.d2_b, w.t1, rows, D, D, R, s))) return rc;
+    if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc;
+  }
+  if ((rc = dense(p, w.h, P + p->orb_re_k, P + p->orb_re_b, w.cbuf, rows, p->LNK, 2 * (int64_t)p->LNK, R, s))) return rc;
+  if ((rc = dense(p, w.h, P + p->orb_im_k, P + p->orb_im_b, w.cbuf + p->LNK, rows, p->LNK, 2 * (int64_t)p->LNK, R, s))) return rc;
+  if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
+  if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;
+  fa.ld = w.ld;
+  fa.x = x;
+  fa.ee_par = p->ee_par >= 0 ? P + p->ee_par : nullptr;
+  fa.Q = p->Q;
+  fa.radius = p->radius;
+  fa.interaction_strength = p->cfg.interaction_strength;
+  fa.interaction_type = p->cfg.interaction_type;
+  fa.lpjet = jets ? w.lpjet : nullptr;
+  return finalize(fa, Bc, td, s);
+}
+
+static int run_forward(dh_plan* p, const float* params, const float* x, int64_t B, bool jets, float* out_el,
+                       float* out_kin, float* out_pot, float* out_lz, float* out_lz2, float* out_l2,
+                       float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (!p || !params || !x || B < 0) return DH_E_BADARG;
+  if (B == 0) return 0;
+  const int64_t chunk = pick_chunk(p, jets, B);
+  float* base = align_ws(ws);
+  FwdWs w = carve_fwd(p, base, chunk, jets, false);
+  if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t Bc = (B - b0) < chunk ? (B - b0) : chunk;
+    FinalizeArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.out_logpsi = out_logpsi ? out_logpsi + b0 * 2 : nullptr;
+    fa.out_el = out_el ? out_el + b0 * 2 : nullptr;
+    fa.out_kin = out_kin ? out_kin + b0 * 2 : nullptr;
+    fa.out_pot = out_pot ? out_pot + b0 : nullptr;
+    fa.out_lz = out_lz ? out_lz + b0 : nullptr;
+    fa.out_lz2 = out_lz2 ? out_lz2 + b0 : nullptr;
+    fa.out_l2 = out_l2 ? out_l2 + b0 : nullptr;
+    int rc = forward_chunk(p, params, x + b0 * p->N * 2, Bc, jets, w, fa, s);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int dh_logpsi(dh_plan* p, const float* params, const float* x, int64_t B, float* out_logpsi,
+                         void* ws, size_t ws_bytes, void* stream) {
+  if (!out_logpsi) return DH_E_BADARG;
+  return run_forward(p, params, x, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_logpsi, ws,
+                     ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dh_local_energy(dh_plan* p, const float* params, const float* x, int64_t B, float* out_el,
+                               float* out_kinetic, float* out_potential, float* out_lz, float* out_lz2,
+                               float* out_l2, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
+  return run_forward(p, params, x, B, true, out_el, out_kinetic, out_potential, out_lz, out_lz2, out_l2,
+                     out_logpsi, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dh_potential(dh_plan* p, const float* x, int64_t B, float* out, void* stream) {
+  if (!p || !x || !out) return DH_E_BADARG;
+  if (B == 0) return 0;
+  return potential(x, out, B, p->N, p->Q, p->radius, p->cfg.interaction_type, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------------- MCMC
+extern "C" int dh_mcmc_propose(dh_plan* p, const float* x1, int64_t B, float width, uint64_t seed,
+                               uint64_t offset, uint64_t subsequence0, const float* randoms, float* x2,
+                               void* stream) {
+  if (!p || !x1 || !x2) return DH_E_BADARG;
+  if (B == 0) return 0;
+  return mcmc_propose(x1, x2, B, p->N, width, seed, offset, subsequence0, randoms, (cudaStream_t)stream);
+}
+
+extern "C" int dh_mcmc_accept(dh_plan* p, float* x1, const float* x2, float* lp1, const float* lp2, int64_t B,
+                              uint64_t seed, uint64_t offset, uint64_t subsequence0, const float* randoms,
+                              long long* naccept, void* stream) {
+  if (!p || !x1 || !x2 || !lp1 || !lp2 || !naccept) return DH_E_BADARG;
+  if (B == 0) return 0;
+  return mcmc_accept(x1, x2, lp1, lp2, 1, B, p->N, seed, offset, subsequence0, randoms,
+                     reinterpret_cast<unsigned long long*>(naccept), (cudaStream_t)stream);
+}
+
+extern "C" int dh_init_walkers(dh_plan* p, float* x, int64_t B, uint64_t seed, uint64_t subsequence0,
+                               void* stream) {
+  if (!p || !x) return DH_E_BADARG;
+  if (B == 0) return 0;
+  return init_walkers(x, B, p->N, seed, subsequence0, (cudaStream_t)stream);
+}
+
+extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t B, int32_t steps, float width,
+                             uint64_t seed, uint64_t offset, uint64_t subsequence0, const float* randoms,
+                             long long* out_naccept, float* out_lp, void* ws, size_t ws_bytes, void* stream) {
+  if (!p || !params || !x || !out_naccept || steps < 0) return DH_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B == 0) return (int)cudaMemsetAsync(out_naccept, 0, sizeof(long long), s);
+  float* base = align_ws(ws);
+  McmcWs mw = carve_mcmc(p, base, B);
+  float* fbase = base + mw.floats;
+  const int64_t chunk = pick_chunk(p, false, B);
+  FwdWs fw = carve_fwd(p, fbase, chunk, false, false);
+  if (!ws || (size_t)((char*)(fbase + fw.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
+  size_t fwd_bytes = ws_bytes - (size_t)((char*)fbase - (char*)ws);
+  int rc;
+  DH_CHECK(cudaMemsetAsync(out_naccept, 0, sizeof(long long), s));
+  // mcmc.py:142 -- log-probability of the incoming configurations
+  if ((rc = dh_logpsi(p, params, x, B, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
+  if ((rc = lp_from_logpsi(mw.logpsi2, mw.lp1, B, s))) return rc;
+  const int64_t rstride = B * (2 * (int64_t)p->N + 1);
+  for (int st = 0; st < steps; ++st) {
+    const float* rnd = randoms ? randoms + st * rstride : nullptr;
+    if ((rc = mcmc_propose(x, mw.x2, B, p->N, width, seed, offset + st, subsequence0, rnd, s))) return rc;
+    if ((rc = dh_logpsi(p, params, mw.x2, B, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
+    if ((rc = mcmc_accept(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, seed, offset + st, subsequence0, rnd,
+                          reinterpret_cast<unsigned long long*>(out_naccept), s)))
+      return rc;
+  }
+  if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" int dh_slogdet(const float* mats, int64_t B, int32_t K, int32_t n, float* out_sign,
+                          float* out_logabs, float* out_logpsi, void* stream) {
+  if (!mats) return DH_E_BADARG;
+  if (B == 0) return 0;
+  return slogdet_batched(mats, B, K, n, out_sign, out_logabs, out_logpsi, (cudaStream_t)stream);
+}
+
+extern "C" int dh_gemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
+                       int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* stream) {
+  if (!A || !W || !C) return DH_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (impl == 0) return gemm_simt(A, W, bias, C, M, N, K, K, 1, N, 1, N, rows_per_group, accumulate, 1, s);
+  if (!gemm_tc_supported(N, K)) return DH_E_UNSUPPORTED;
+  // test/bench entry point: the split weights are made on the fly (the plan ops keep them cached)
+  float* wt = nullptr;
+  DH_CHECK(cudaMalloc(&wt, 2 * (size_t)N * K * sizeof(float)));
+  int rc = split_weight_tc(W, N, K, N, wt, wt + (size_t)N * K, s);
+  if (!rc) rc = gemm_tc(A, wt, wt + (size_t)N * K, bias, C, M, N, K, N, rows_per_group, accumulate, s);
+  cudaStreamSynchronize(s);
+  cudaFree(wt);
+  return rc;
+}
+
+extern "C" int dh_debug_buffer(const dh_plan* p, int op, int64_t B, const char* name, int64_t* offset,
+                               int64_t* count) {
+  if (!p || !name || !offset || !count) return DH_E_BADARG;
+  const bool jets = op == DH_OP_LOCAL_ENERGY;
+  if (op != DH_OP_LOCAL_ENERGY && op != DH_OP_LOGPSI) return DH_E_BADARG;
+  const int64_t Bc = pick_chunk(p, jets, B);
+  float* zero = reinterpret_cast<float*>(uintptr_t(256));
+  FwdWs w = carve_fwd(p, zero, Bc, jets, false);
+  const int R = jets ? 2 * p->N + 8 : 1;
+  const int64_t rows = Bc * p->N * R;
+  const std::string n(name);
+  const float* ptr = nullptr;
+  int64_t cnt = 0;
+  if (n == "h") { ptr = w.h; cnt = rows * p->D; }
+  else if (n == "qkv") { ptr = w.qkv; cnt = rows * 3 * p->D; }
+  else if (n == "attn") { ptr = w.att; cnt = rows * p->D; }
+  else if (n == "t1") { ptr = w.t1; cnt = rows * p->D; }
+  else if (n == "t2") { ptr = w.t2; cnt = rows * p->D; }
+  else if (n == "c") { ptr = w.cbuf; cnt = rows * 2 * (int64_t)p->LNK; }
+  else if (n == "orb") { ptr = w.Mj; cnt = Bc * p->K * R * p->N * p->N * 2; }
+  else if (n == "ld") { ptr = w.ld; cnt = Bc * p->K * R * 2; }
+  else if (n == "lpjet") { ptr = w.lpjet; cnt = Bc * R * 2; }
+  else return DH_E_BADARG;
+  *offset = ptr - zero;  // floats from the 256-byte-aligned workspace base
+  *count = cnt;
+  return 0;
+}

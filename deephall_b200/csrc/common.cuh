@@ -1,0 +1,91 @@
+// Shared device helpers for the deephall_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DH_CHECK(expr)                         \
+  do {                                         \
+    cudaError_t _e = (expr);                   \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+#define DH_LAUNCH_CHECK()                      \
+  do {                                         \
+    cudaError_t _e = cudaGetLastError();       \
+    if (_e != cudaSuccess) return (int)_e;     \
+  } while (0)
+
+namespace dh {
+
+// Row layout of a jet group (see oracle/jets.py): R = 2N + 8 rows per electron.
+//   0: value | 1..2N: J_k | 2N+1: S | 2N+2..4: D_a | 2N+5..7: T_a
+struct Rows {
+  int N, R;
+  __host__ __device__ explicit Rows(int n, bool jets) : N(n), R(jets ? 2 * n + 8 : 1) {}
+  __host__ __device__ int J(int k) const { return 1 + k; }
+  __host__ __device__ int S() const { return 2 * N + 1; }
+  __host__ __device__ int D(int a) const { return 2 * N + 2 + a; }
+  __host__ __device__ int T(int a) const { return 2 * N + 5 + a; }
+};
+
+typedef float2 cplx;
+__host__ __device__ inline cplx cmake(float re, float im) { return make_float2(re, im); }
+__host__ __device__ inline cplx cadd(cplx a, cplx b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ inline cplx csub(cplx a, cplx b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ inline cplx cmul(cplx a, cplx b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ inline cplx cscale(cplx a, float s) { return make_float2(a.x * s, a.y * s); }
+__host__ __device__ inline cplx cconj(cplx a) { return make_float2(a.x, -a.y); }
+__device__ inline cplx cfma(cplx a, cplx b, cplx c) {  // a*b + c
+  return make_float2(fmaf(a.x, b.x, fmaf(-a.y, b.y, c.x)), fmaf(a.x, b.y, fmaf(a.y, b.x, c.y)));
+}
+__device__ inline float cabs2(cplx a) { return a.x * a.x + a.y * a.y; }
+__device__ inline cplx cinv(cplx a) {
+  float d = 1.0f / (a.x * a.x + a.y * a.y);
+  return make_float2(a.x * d, -a.y * d);
+}
+
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ inline float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (offset_lo, offset_hi, subseq_lo, subseq_hi).
+struct Philox {
+  uint32_t k0, k1;
+  __host__ __device__ explicit Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+  }
+  __host__ __device__ inline uint4 operator()(uint64_t offset, uint64_t subseq) const {
+    uint32_t c0 = (uint32_t)offset, c1 = (uint32_t)(offset >> 32);
+    uint32_t c2 = (uint32_t)subseq, c3 = (uint32_t)(subseq >> 32);
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      uint32_t hi0, lo0, hi1, lo1;
+      mulhilo(0xD2511F53u, c0, hi0, lo0);
+      mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+      uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+// 24-bit mantissa uniform in [0, 1)
+__host__ __device__ inline float u01(uint32_t r) { return (r >> 8) * (1.0f / 16777216.0f); }
+// uniform in (0, 1] for Box-Muller
+__host__ __device__ inline float u01_open0(uint32_t r) { return ((r >> 8) + 1) * (1.0f / 16777216.0f); }
+
+}  // namespace dh

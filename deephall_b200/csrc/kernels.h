@@ -1,0 +1,89 @@
+// Internal launch interface between api.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace dh {
+
+// ---- gemm_simt.cu
+int gemm_simt(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int64_t K,
+              int64_t a_sm, int64_t a_sk, int64_t b_sk, int64_t b_sn, int64_t ldc, int rpg, int accumulate,
+              int split_k, cudaStream_t stream);
+
+// ---- gemm_tc.cu (tcgen05 3xTF32): C[M,N] = A[M,K] @ W[K,N] (+bias on value rows) (+C)
+//      Wt_hi / Wt_lo are the pre-split, K-major (transposed, [N][K]) copies of W.
+int gemm_tc_supported(int N, int K);
+int gemm_tc(const float* A, const float* Wt_hi, const float* Wt_lo, const float* bias, float* C, int64_t M,
+            int N, int K, int64_t ldc, int rpg, int accumulate, cudaStream_t stream);
+int split_weight_tc(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
+
+// ---- net_kernels.cu
+struct NetDims {
+  int N;       // electrons
+  int R;       // rows per electron (1 or 2N+8)
+  int D;       // model width = H*hd
+  int H, hd;
+  int n_up;    // spin-up count (for the spin feature)
+};
+int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDims d, cudaStream_t s);
+// out = LN(a + (tanh_mode ? tanh(b) : b)) with jets; a/b/out are [B*N*R, D]
+int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
+                       int64_t B, NetDims d, int tanh_mode, cudaStream_t s);
+int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
+size_t attention_jets_smem(NetDims d);
+
+// ---- tail_kernels.cu
+struct TailDims {
+  int N, R, L, K;   // electrons, rows, orbitals (2Q+1), determinants
+  int twoQ;
+  int n_up;
+};
+// c: [B*N*R, 2*L*N*K] (re block | im block) -> M jets [B][K][R][N][N] complex
+int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
+                     cudaStream_t s);
+// M jets -> per-det logdet jets ld [B][K][R] complex
+int logdet_jets(const float* Mj, float* ld, int64_t B, TailDims d, cudaStream_t s);
+// same, also writing the inverse of the value matrix ([b][kd][N][N] complex) when Minv != nullptr
+int logdet_jets_impl(const float* Mj, float* ld, float* Minv, int64_t B, TailDims d, cudaStream_t s);
+struct FinalizeArgs {
+  const float* ld;       // [B][K][R] complex
+  const float* x;        // [B][N][2]
+  const float* ee_par;   // jastrow parameter (device scalar) or nullptr when N < 2
+  float Q, radius, interaction_strength;
+  int interaction_type;
+  float* out_logpsi;     // [B] complex
+  float* out_el;         // [B] complex   (jets only)
+  float* out_kin;        // [B] complex
+  float* out_pot, *out_lz, *out_lz2, *out_l2;  // [B]
+  float* lpjet;          // optional [B][R] complex debug copy of the log psi jets
+};
+int finalize(FinalizeArgs a, int64_t B, TailDims d, cudaStream_t s);
+int potential(const float* x, float* out, int64_t B, int N, float Q, float radius, int interaction_type,
+              cudaStream_t s);
+int slogdet_batched(const float* mats, int64_t B, int K, int n, float* out_sign, float* out_logabs,
+                    float* out_logpsi, cudaStream_t s);
+
+// ---- mcmc_kernels.cu
+int mcmc_propose(const float* x1, float* x2, int64_t B, int N, float width, uint64_t seed, uint64_t offset,
+                 uint64_t subseq0, const float* randoms, cudaStream_t s);
+int mcmc_accept(float* x1, const float* x2, float* lp1, const float* lp2c, int lp2_stride, int64_t B, int N,
+                uint64_t seed, uint64_t offset, uint64_t subseq0, const float* randoms,
+                unsigned long long* naccept, cudaStream_t s);
+int init_walkers(float* x, int64_t B, int N, uint64_t seed, uint64_t subseq0, cudaStream_t s);
+int lp_from_logpsi(const float* logpsi_c, float* lp, int64_t B, cudaStream_t s);
+
+// ---- vjp_kernels.cu
+int finalize_bwd(const float* cot, const float* x, const float* ee_par, const float* ld0, const float* logpsi,
+                 float* g_ld, float* g_eepar, int64_t B, TailDims d, cudaStream_t s);
+int logdet_bwd(const float* M0, const float* g_ld, float* g_M, int64_t B, TailDims d, cudaStream_t s);
+int orbital_contract_bwd(const float* g_M, const float* x, const float* normfac, float* g_c, int64_t B,
+                         TailDims d, cudaStream_t s);
+int residual_layernorm_bwd(const float* a, const float* b, const float* scale, const float* g_out, float* g_a,
+                           float* g_b, float* g_scale, float* g_bias, int64_t B, NetDims d, int tanh_mode,
+                           cudaStream_t s);
+int attention_value_bwd(const float* qkv, const float* g_o, float* g_qkv, int64_t B, NetDims d, cudaStream_t s);
+int features_dense0_bwd(const float* x, const float* g_h, float* g_W0, int64_t B, NetDims d, cudaStream_t s);
+int colsum_add(const float* g, float* out, int64_t M, int N, int64_t ld, cudaStream_t s);
+int add_inplace(float* dst, const float* src, int64_t n, cudaStream_t s);
+
+}  // namespace dh

@@ -1,0 +1,127 @@
+// Metropolis-Hastings walker update: on-sphere rotation proposal (mcmc.py:67-102), accept /
+// select (mcmc.py:56-62), uniform initial walkers (train.py:40-54).  Random numbers come from an
+// in-kernel Philox4x32-10 stream or, for bit-exact parity tests, from an injected array.
+//
+// Philox addressing: key = seed; counter = (offset * 64 + slot, subsequence0 + walker) where
+// slot = electron index for the proposal draws and 63 for the accept draw; `offset` advances by
+// one per MH move.
+#include "kernels.h"
+
+namespace dh {
+
+constexpr float kTwoPi = 6.283185307179586f;
+
+__global__ void mcmc_propose_kernel(const float* __restrict__ x1, float* __restrict__ x2, int64_t total, int N,
+                                    float width, uint64_t seed, uint64_t offset, uint64_t subseq0,
+                                    const float* __restrict__ randoms) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t b = t / N;
+  const int i = (int)(t % N);
+  float nrm, uph;
+  if (randoms != nullptr) {
+    nrm = randoms[b * (2 * N + 1) + i];
+    uph = randoms[b * (2 * N + 1) + N + i];
+  } else {
+    Philox ph(seed);
+    uint4 r = ph(offset * 64 + (uint64_t)i, subseq0 + (uint64_t)b);
+    float u1 = u01_open0(r.x), u2 = u01(r.y);
+    float s_, c_;
+    sincosf(kTwoPi * u2, &s_, &c_);
+    nrm = sqrtf(-2.f * logf(u1)) * c_;
+    uph = u01(r.z);
+  }
+  const float theta = x1[t * 2], phi = x1[t * 2 + 1];
+  const float theta_p = atanf(nrm * width);
+  const float phi_p = uph * kTwoPi;
+  float stp, ctp, spp, cpp, st, ct, sp, cp;
+  sincosf(theta_p, &stp, &ctp);
+  sincosf(phi_p, &spp, &cpp);
+  sincosf(theta, &st, &ct);
+  sincosf(phi, &sp, &cp);
+  const float xp = stp * cpp, yp = stp * spp, zp = ctp;
+  // R_z(phi) R_y(theta) (xp, yp, zp)
+  const float X = ct * xp + st * zp;
+  const float Y = yp;
+  const float Z = -st * xp + ct * zp;
+  const float x2v = cp * X - sp * Y;
+  const float y2v = sp * X + cp * Y;
+  const float z2v = Z;
+  const float th2 = acosf(fminf(fmaxf(z2v, -1.f), 1.f));
+  const float sgn = (y2v > 0.f) ? 1.f : ((y2v < 0.f) ? -1.f : 0.f);
+  const float ph2 = sgn * acosf(fminf(fmaxf(x2v / sinf(th2), -1.f), 1.f));
+  x2[t * 2] = th2;
+  x2[t * 2 + 1] = ph2;
+}
+
+int mcmc_propose(const float* x1, float* x2, int64_t B, int N, float width, uint64_t seed, uint64_t offset,
+                 uint64_t subseq0, const float* randoms, cudaStream_t s) {
+  const int64_t total = B * N;
+  mcmc_propose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x1, x2, total, N, width, seed, offset,
+                                                                      subseq0, randoms);
+  return (int)cudaGetLastError();
+}
+
+// lp2c: pointer to 2 Re log psi source; if lp2_stride == 2 it is the complex log psi array
+// (lp = 2 * re), if 1 it is already lp.
+__global__ void mcmc_accept_kernel(float* __restrict__ x1, const float* __restrict__ x2, float* __restrict__ lp1,
+                                   const float* __restrict__ lp2c, int lp2_stride, int64_t B, int N, uint64_t seed,
+                                   uint64_t offset, uint64_t subseq0, const float* __restrict__ randoms,
+                                   unsigned long long* __restrict__ naccept) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool acc = false;
+  if (b < B) {
+    float u;
+    if (randoms != nullptr) u = randoms[b * (2 * N + 1) + 2 * N];
+    else {
+      Philox ph(seed);
+      u = u01(ph(offset * 64 + 63, subseq0 + (uint64_t)b).x);
+    }
+    const float logu = (float)log((double)u);  // one rounding, same convention as oracle.mcmc.log_uniform
+    const float l2 = lp2_stride == 2 ? 2.0f * lp2c[b * 2] : lp2c[b];
+    const float l1 = lp1[b];
+    acc = (l2 - l1) > logu;  // NaN -> false (mcmc.py:59)
+    if (acc) {
+      lp1[b] = l2;
+      for (int t = 0; t < 2 * N; ++t) x1[b * 2 * N + t] = x2[b * 2 * N + t];
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, acc);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(naccept, (unsigned long long)__popc(m));
+}
+
+int mcmc_accept(float* x1, const float* x2, float* lp1, const float* lp2c, int lp2_stride, int64_t B, int N,
+                uint64_t seed, uint64_t offset, uint64_t subseq0, const float* randoms,
+                unsigned long long* naccept, cudaStream_t s) {
+  mcmc_accept_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(x1, x2, lp1, lp2c, lp2_stride, B, N, seed, offset,
+                                                                subseq0, randoms, naccept);
+  return (int)cudaGetLastError();
+}
+
+__global__ void init_walkers_kernel(float* __restrict__ x, int64_t total, int N, uint64_t seed, uint64_t subseq0) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int64_t b = t / N;
+  const int i = (int)(t % N);
+  Philox ph(seed);
+  uint4 r = ph((uint64_t)i, subseq0 + (uint64_t)b);
+  x[t * 2] = acosf(2.f * u01(r.x) - 1.f);
+  x[t * 2 + 1] = (2.f * u01(r.y) - 1.f) * 3.14159265358979f;
+}
+
+int init_walkers(float* x, int64_t B, int N, uint64_t seed, uint64_t subseq0, cudaStream_t s) {
+  const int64_t total = B * N;
+  init_walkers_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, total, N, seed, subseq0);
+  return (int)cudaGetLastError();
+}
+
+__global__ void lp_from_logpsi_kernel(const float* __restrict__ lc, float* __restrict__ lp, int64_t B) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) lp[b] = 2.0f * lc[b * 2];
+}
+int lp_from_logpsi(const float* logpsi_c, float* lp, int64_t B, cudaStream_t s) {
+  lp_from_logpsi_kernel<<<(unsigned)((B + 255) / 256), 256, 0, s>>>(logpsi_c, lp, B);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dh

@@ -1,0 +1,155 @@
+/*
+ * deephall_b200 -- C ABI of the B200-native walker-evaluation engine for DeepHall.
+ *
+ * The reference (peterzjx/DeepHall) is pure Python on JAX and has no FFI of its own; its
+ * seams are Python factories returning closures.  Each entry point below is what a
+ * `jax.ffi` / ctypes binding for that seam would call (INTEGRATION.md shows the stubs):
+ *
+ *   dh_logpsi          <- model.apply(params, x)            networks/psiformer.py:72-76
+ *                         (vmapped: train.py:69)             types.py:68-70
+ *   dh_local_energy    <- local_energy(f, system)._e_l      hamiltonian.py:175-212
+ *                         (vmapped: loss.py:51,67)           types.py:49-65
+ *   dh_potential       <- make_potential(...).potential     hamiltonian.py:63-80
+ *   dh_mcmc_sweep      <- make_mcmc_step(...).mcmc_step     mcmc.py:105-150
+ *   dh_mcmc_propose    <- sph_sampling                      mcmc.py:67-102
+ *   dh_mcmc_accept     <- mh_update (accept/select part)    mcmc.py:56-62
+ *   dh_logpsi_vjp      <- df_real/df_imag + loss_prod       loss.py:53-64,96-106
+ *   dh_slogdet         <- jnp.linalg.slogdet + tail         psiformer.py:74-76
+ *   dh_param_layout    <- the flax parameter tree           psiformer.py, blocks.py
+ *   dh_init_walkers    <- init_guess                        train.py:40-54
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all floating-point data is fp32; complex data is interleaved (re, im) fp32;
+ *   - walkers `x` are (B, N, 2) = (theta, phi), exactly the reference layout (mcmc.py:68);
+ *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), performs
+ *     no allocation and no host synchronisation; the caller owns every buffer including
+ *     the workspace (size from dh_workspace_bytes);
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = DH_E_* argument error.  Numerical
+ *     pathologies follow the reference: NaN/-inf propagate into the outputs
+ *     (singular determinant -> log|psi| = -inf, NaN proposal -> rejected, mcmc.py:59).
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef DEEPHALL_B200_H
+#define DEEPHALL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DH_E_BADARG (-1)
+#define DH_E_UNSUPPORTED (-2)
+#define DH_E_WORKSPACE (-3)
+
+/* System + network hyper-parameters: config.py:56-104 (System, PsiformerNetwork). */
+typedef struct dh_config {
+  int32_t n_up, n_dn;       /* system.nspins (n_dn must be 0 in this round)           */
+  int32_t flux;             /* system.flux = 2Q                                        */
+  int32_t ndets;            /* network.psiformer.determinants                         */
+  int32_t num_heads;        /* network.psiformer.num_heads                            */
+  int32_t heads_dim;        /* network.psiformer.heads_dim                            */
+  int32_t num_layers;       /* network.psiformer.num_layers                           */
+  int32_t interaction_type; /* 0 = coulomb, 1 = harmonic (config.py:51-53)            */
+  float interaction_strength; /* system.interaction_strength                          */
+  float radius;             /* system.radius; <= 0 means sqrt(Q) (hamiltonian.py:189) */
+  int32_t chunk_walkers;    /* walkers per internal pass (0 = library default)        */
+} dh_config;
+
+typedef struct dh_plan dh_plan;
+
+/* One entry of the flat parameter layout (mirrors the flax tree path). */
+typedef struct dh_param_entry {
+  char name[96];    /* e.g. "PsiformerLayers_0/MultiHeadAttention_0/query/kernel" */
+  int64_t offset;   /* in floats, into the flat parameter vector                  */
+  int32_t ndim;
+  int32_t shape[4];
+} dh_param_entry;
+
+enum dh_op { DH_OP_LOGPSI = 0, DH_OP_LOCAL_ENERGY = 1, DH_OP_MCMC = 2, DH_OP_VJP = 3 };
+
+int dh_plan_create(const dh_config* cfg, dh_plan** out);
+int dh_plan_destroy(dh_plan* plan);
+const char* dh_version(void);
+
+/* Flat parameter vector: number of floats, and the name/offset/shape table. */
+int64_t dh_param_count(const dh_plan* plan);
+int dh_param_layout(const dh_plan* plan, dh_param_entry* entries_host, int32_t* n_entries_host);
+
+/* Bytes of device workspace an op needs for a batch of B walkers. */
+int dh_workspace_bytes(const dh_plan* plan, int op, int64_t B, size_t* bytes_host);
+
+/* log psi of B walkers.  out_logpsi: (B) complex64 = (log|psi|, phase). */
+int dh_logpsi(dh_plan* plan, const float* params, const float* x, int64_t B, float* out_logpsi,
+              void* ws, size_t ws_bytes, void* stream);
+
+/* Local energy + observables (hamiltonian.py:207-210).  Any output may be NULL.
+ *   out_el, out_kinetic: (B) complex64;  out_potential, out_lz, out_lz2, out_l2: (B) f32;
+ *   out_logpsi: (B) complex64 (free by-product). */
+int dh_local_energy(dh_plan* plan, const float* params, const float* x, int64_t B, float* out_el,
+                    float* out_kinetic, float* out_potential, float* out_lz, float* out_lz2,
+                    float* out_l2, float* out_logpsi, void* ws, size_t ws_bytes, void* stream);
+
+/* interaction_strength is NOT applied here (hamiltonian.py:78 vs :205). */
+int dh_potential(dh_plan* plan, const float* x, int64_t B, float* out, void* stream);
+
+/* `steps` Metropolis-Hastings all-electron moves (mcmc.py:122-148).
+ *   x_inout (B,N,2) is updated in place (the reference donates it, train.py:75);
+ *   randoms: NULL -> in-kernel Philox4x32-10 keyed by (seed, offset); walker b uses
+ *            subsequence `subsequence0 + b`.  Otherwise "injected randoms":
+ *            (steps, B, 2N+1) f32 = [N normals | N uniforms (phi') | 1 uniform (accept)].
+ *   out_naccept: one int64 on the device, overwritten with the number of accepted moves
+ *            (pmove = naccept / (steps * B), mcmc.py:146).
+ *   out_lp: optional (B) f32, 2 Re log psi of the final configurations. */
+int dh_mcmc_sweep(dh_plan* plan, const float* params, float* x_inout, int64_t B, int32_t steps,
+                  float width, uint64_t seed, uint64_t offset, uint64_t subsequence0,
+                  const float* randoms, long long* out_naccept, float* out_lp, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* One proposal (mcmc.py:67-102) and one accept/select (mcmc.py:56-62), exposed for parity
+ * tests.  `randoms` as above with steps = 1 (NULL -> Philox). */
+int dh_mcmc_propose(dh_plan* plan, const float* x1, int64_t B, float width, uint64_t seed,
+                    uint64_t offset, uint64_t subsequence0, const float* randoms, float* x2,
+                    void* stream);
+int dh_mcmc_accept(dh_plan* plan, float* x1_inout, const float* x2, float* lp1_inout,
+                   const float* lp2, int64_t B, uint64_t seed, uint64_t offset,
+                   uint64_t subsequence0, const float* randoms, long long* naccept_inout,
+                   void* stream);
+
+/* Uniform points on the sphere (train.py:40-54) from Philox. */
+int dh_init_walkers(dh_plan* plan, float* x, int64_t B, uint64_t seed, uint64_t subsequence0,
+                    void* stream);
+
+/* grad_flat (P floats) = sum_b [ cot[b,0] * d Re logpsi_b / d params
+ *                              + cot[b,1] * d Im logpsi_b / d params ]        (loss.py:99-106:
+ * the caller passes cot = (2/B) * (Re diff, Im diff)).  grad_flat is overwritten.
+ * out_logpsi optional. */
+int dh_logpsi_vjp(dh_plan* plan, const float* params, const float* x, int64_t B,
+                  const float* cot, float* grad_flat, float* out_logpsi, void* ws,
+                  size_t ws_bytes, void* stream);
+
+/* Batched complex slogdet with the reference's multi-determinant tail (psiformer.py:74-76).
+ *   mats: (B, K, n, n) complex64, row-major.
+ *   out_sign (B,K) complex64 and out_logabs (B,K) f32 may be NULL;
+ *   out_logpsi (B) complex64 = log sum_k sign_k exp(logabs_k) may be NULL. */
+int dh_slogdet(const float* mats, int64_t B, int32_t K, int32_t n, float* out_sign,
+               float* out_logabs, float* out_logpsi, void* stream);
+
+/* fp32 GEMM used by the network (exposed for parity tests and the roofline bench):
+ *   C[M,N] = A[M,K] @ W[K,N] (+ bias[N] on rows r with r % rows_per_group == 0) (+ C if accumulate)
+ *   impl: 0 = SIMT fp32 FMA, 1 = tcgen05 3xTF32. */
+int dh_gemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
+            int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* stream);
+
+/* Debug: after dh_logpsi / dh_local_energy with B <= chunk, intermediate buffers live in
+ * the workspace.  Returns the float offset and count of a named buffer ("h", "qkv", "attn",
+ * "orb", "ld", "lpjet"); <0 if unknown. */
+int dh_debug_buffer(const dh_plan* plan, int op, int64_t B, const char* name, int64_t* offset,
+                    int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPHALL_B200_H */
