@@ -61,7 +61,12 @@ SIGNATURES = OrderedDict(
     dh_slogdet=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     dh_debug_buffer=(C.c_int, [_vp, C.c_int, _i64, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
+    dh_launch_count=(C.c_longlong, [_vp]),
+    dh_profile_begin=(C.c_int, [_vp, _i32]),
+    dh_profile_end=(C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i32), C.POINTER(C.c_double)]),
 )
+
+PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "tail", "mcmc", "other")
 
 
 def lib_path() -> str:
@@ -167,6 +172,21 @@ class Plan:
         base = (self._ws.data_ptr() + 255) // 256 * 256 - self._ws.data_ptr()
         fl = self._ws[base:].view(torch.float32) if (self._ws.numel() - base) % 4 == 0 else self._ws[base : base + (self._ws.numel() - base) // 4 * 4].view(torch.float32)
         return fl[off.value : off.value + cnt.value]
+
+    # ---- instrumentation
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.dh_launch_count(self.handle))
+
+    def profile_begin(self, max_launches=8192):
+        _check(self.lib.dh_profile_begin(self.handle, max_launches), "dh_profile_begin")
+
+    def profile_end(self):
+        ms = (C.c_double * 6)()
+        cnt = (_i32 * 6)()
+        fl = (C.c_double * 6)()
+        _check(self.lib.dh_profile_end(self.handle, ms, cnt, fl), "dh_profile_end")
+        return {c: {"ms": ms[i], "count": cnt[i], "flops": fl[i]} for i, c in enumerate(PROFILE_CATEGORIES)}
 
     # ---- ops
     def logpsi(self, params, x):

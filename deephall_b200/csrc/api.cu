@@ -8,30 +8,9 @@
 #include <vector>
 
 #include "../../include/deephall_b200.h"
-#include "kernels.h"
+#include "plan.h"
 
 using namespace dh;
-
-struct LayerOff {
-  int64_t q_k, q_b, k_k, k_b, v_k, v_b, o_k, o_b, d1_k, ln0_s, ln0_b, d2_k, d2_b, ln1_s, ln1_b;
-};
-
-struct dh_plan {
-  dh_config cfg;
-  int N, L, K, D, H, hd, nl, twoQ, LNK;
-  float Q, radius;
-  std::vector<dh_param_entry> entries;
-  int64_t nparams;
-  int64_t off_W0;
-  std::vector<LayerOff> layer;
-  int64_t orb_re_k, orb_re_b, orb_im_k, orb_im_b, ee_par;
-  double* d_normfac;
-  int gemm_impl;  // 0 = SIMT, 1 = tcgen05 3xTF32
-  // prepared (pre-split, transposed) weights for the tcgen05 path
-  float* prep;            // device buffer owned by the plan
-  size_t prep_floats;
-  const float* prep_src;  // params pointer the preparation was made from
-};
 
 static void add_entry(dh_plan* p, const std::string& name, std::vector<int> shape, int64_t* off_out) {
   dh_param_entry e;
@@ -78,6 +57,9 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->prep_floats = 0;
   p->prep_src = nullptr;
   p->gemm_impl = 0;
+  p->prof_on = false;
+  p->prof_used = 0;
+  p->launches = 0;
   if (p->N > 16 || p->D % 32 != 0 || p->D > 256 || p->hd % 4 != 0) { delete p; return DH_E_UNSUPPORTED; }
   const int D = p->D, H = p->H, hd = p->hd, N = p->N, L = p->L, K = p->K;
   const std::string pl = "PsiformerLayers_0/";
@@ -125,6 +107,7 @@ extern "C" int dh_plan_destroy(dh_plan* p) {
   if (!p) return DH_E_BADARG;
   if (p->d_normfac) cudaFree(p->d_normfac);
   if (p->prep) cudaFree(p->prep);
+  for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
   delete p;
   return 0;
 }
@@ -139,54 +122,6 @@ extern "C" int dh_param_layout(const dh_plan* p, dh_param_entry* entries, int32_
   }
   *n = (int32_t)p->entries.size();
   return 0;
-}
-
-// --------------------------------------------------------------------------------- workspace
-struct FwdWs {
-  float *h, *t1, *t2, *qkv, *att, *cbuf, *Mj, *ld, *lpjet, *Minv;
-  size_t floats;
-};
-
-static inline size_t al(size_t n) { return (n + 63) / 64 * 64; }  // 256-byte granules
-
-static int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
-  int64_t c = p->cfg.chunk_walkers > 0 ? p->cfg.chunk_walkers : (jets ? 1024 : 16384);
-  return B < c ? B : c;
-}
-
-static FwdWs carve_fwd(const dh_plan* p, float* base, int64_t Bc, bool jets, bool keep_inverse) {
-  const int R = jets ? 2 * p->N + 8 : 1;
-  const size_t rows = (size_t)Bc * p->N * R;
-  FwdWs w;
-  size_t off = 0;
-  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
-  w.h = take(rows * p->D);
-  w.t1 = take(rows * p->D);
-  w.t2 = take(rows * p->D);
-  w.qkv = take(rows * 3 * p->D);
-  w.att = take(rows * p->D);
-  w.cbuf = take(rows * 2 * (size_t)p->LNK);
-  w.Mj = take((size_t)Bc * p->K * R * p->N * p->N * 2);
-  w.ld = take((size_t)Bc * p->K * R * 2);
-  w.lpjet = take((size_t)Bc * R * 2);
-  w.Minv = keep_inverse ? take((size_t)Bc * p->K * p->N * p->N * 2) : nullptr;
-  w.floats = off;
-  return w;
-}
-
-struct McmcWs {
-  float *x2, *lp1, *logpsi2;
-  size_t floats;
-};
-static McmcWs carve_mcmc(const dh_plan* p, float* base, int64_t B) {
-  McmcWs w;
-  size_t off = 0;
-  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
-  w.x2 = take((size_t)B * p->N * 2);
-  w.lp1 = take((size_t)B);
-  w.logpsi2 = take((size_t)B * 2);
-  w.floats = off;
-  return w;
 }
 
 size_t vjp_ws_floats(const dh_plan* p, int64_t Bc);  // api_vjp.cu
@@ -207,18 +142,6 @@ extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* b
   return 0;
 }
 
-static inline float* align_ws(void* ws) {
-  uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
-  return reinterpret_cast<float*>(a);
-}
-
-// --------------------------------------------------------------------------------- forward
-// C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
-static int dense(const dh_plan* p, const float* A, const float* W, const float* bias, float* C, int64_t rows,
-                 int Nout, int64_t ldc, int R, cudaStream_t s) {
-  return gemm_simt(A, W, bias, C, rows, Nout, p->D, p->D, 1, Nout, 1, ldc, R, 0, 1, s);
-}
-
 // Runs the network body + tail for Bc walkers whose coordinates are x; fills w.ld / outputs.
 int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, bool jets, const FwdWs& w,
                   FinalizeArgs fa, cudaStream_t s) {
@@ -228,23 +151,25 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   NetDims nd{N, R, D, p->H, p->hd, p->cfg.n_up};
   TailDims td{N, R, p->L, p->K, p->twoQ, p->cfg.n_up};
   int rc;
-  if ((rc = features_dense0(x, P + p->off_W0, w.h, Bc, nd, s))) return rc;
+  { ProfScope ps(p, PC_OTHER, 0, s); if ((rc = features_dense0(x, P + p->off_W0, w.h, Bc, nd, s))) return rc; }
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
     if ((rc = dense(p, w.h, P + o.q_k, P + o.q_b, w.qkv, rows, D, 3 * D, R, s))) return rc;
     if ((rc = dense(p, w.h, P + o.k_k, P + o.k_b, w.qkv + D, rows, D, 3 * D, R, s))) return rc;
     if ((rc = dense(p, w.h, P + o.v_k, P + o.v_b, w.qkv + 2 * D, rows, D, 3 * D, R, s))) return rc;
-    if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, s);
-    else rc = attention_value(w.qkv, w.att, Bc, nd, s);
-    if (rc) return rc;
+    { ProfScope ps(p, PC_ATTENTION, 0, s);
+      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, s);
+      else rc = attention_value(w.qkv, w.att, Bc, nd, s);
+      if (rc) return rc; }
     if ((rc = dense(p, w.att, P + o.o_k, P + o.o_b, w.t1, rows, D, D, R, s))) return rc;
     if ((rc = dense(p, w.t1, P + o.d1_k, nullptr, w.t2, rows, D, D, R, s))) return rc;
-    if ((rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s))) return rc;
+    { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s))) return rc; }
     if ((rc = dense(p, w.h, P + o.d2_k, P + o.d2_b, w.t1, rows, D, D, R, s))) return rc;
-    if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc;
+    { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc; }
   }
   if ((rc = dense(p, w.h, P + p->orb_re_k, P + p->orb_re_b, w.cbuf, rows, p->LNK, 2 * (int64_t)p->LNK, R, s))) return rc;
   if ((rc = dense(p, w.h, P + p->orb_im_k, P + p->orb_im_b, w.cbuf + p->LNK, rows, p->LNK, 2 * (int64_t)p->LNK, R, s))) return rc;
+  ProfScope pst(p, PC_TAIL, 0, s, 3);
   if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
   if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;
   fa.ld = w.ld;
@@ -350,11 +275,12 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
   const int64_t rstride = B * (2 * (int64_t)p->N + 1);
   for (int st = 0; st < steps; ++st) {
     const float* rnd = randoms ? randoms + st * rstride : nullptr;
-    if ((rc = mcmc_propose(x, mw.x2, B, p->N, width, seed, offset + st, subsequence0, rnd, s))) return rc;
+    { ProfScope ps(p, PC_MCMC, 0, s); if ((rc = mcmc_propose(x, mw.x2, B, p->N, width, seed, offset + st, subsequence0, rnd, s))) return rc; }
     if ((rc = dh_logpsi(p, params, mw.x2, B, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
-    if ((rc = mcmc_accept(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, seed, offset + st, subsequence0, rnd,
-                          reinterpret_cast<unsigned long long*>(out_naccept), s)))
-      return rc;
+    { ProfScope ps(p, PC_MCMC, 0, s);
+      if ((rc = mcmc_accept(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, seed, offset + st, subsequence0, rnd,
+                            reinterpret_cast<unsigned long long*>(out_naccept), s)))
+        return rc; }
   }
   if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
@@ -408,5 +334,40 @@ extern "C" int dh_debug_buffer(const dh_plan* p, int op, int64_t B, const char* 
   else return DH_E_BADARG;
   *offset = ptr - zero;  // floats from the 256-byte-aligned workspace base
   *count = cnt;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------- instrumentation
+extern "C" long long dh_launch_count(const dh_plan* p) { return p ? p->launches : -1; }
+
+extern "C" int dh_profile_begin(dh_plan* p, int32_t max_launches) {
+  if (!p || max_launches < 1) return DH_E_BADARG;
+  while (p->prof_ev.size() < (size_t)max_launches * 2) {
+    cudaEvent_t e;
+    DH_CHECK(cudaEventCreate(&e));
+    p->prof_ev.push_back(e);
+  }
+  p->prof_cat.assign(p->prof_ev.size() / 2, 0);
+  p->prof_flops.assign(p->prof_ev.size() / 2, 0.0);
+  p->prof_used = 0;
+  p->prof_on = true;
+  return 0;
+}
+
+// Synchronises the device, then reports per category: total ms, number of timed scopes, flops.
+extern "C" int dh_profile_end(dh_plan* p, double* ms_host, int32_t* count_host, double* flops_host) {
+  if (!p || !ms_host || !count_host || !flops_host) return DH_E_BADARG;
+  p->prof_on = false;
+  DH_CHECK(cudaDeviceSynchronize());
+  for (int c = 0; c < PC_COUNT; ++c) { ms_host[c] = 0; count_host[c] = 0; flops_host[c] = 0; }
+  for (size_t i = 0; i + 1 < p->prof_used; i += 2) {
+    float ms = 0.f;
+    DH_CHECK(cudaEventElapsedTime(&ms, p->prof_ev[i], p->prof_ev[i + 1]));
+    const int c = p->prof_cat[i / 2];
+    ms_host[c] += ms;
+    count_host[c] += 1;
+    flops_host[c] += p->prof_flops[i / 2];
+  }
+  p->prof_used = 0;
   return 0;
 }

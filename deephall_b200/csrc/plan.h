@@ -1,0 +1,121 @@
+// Internal: plan object, workspace carving and profiling hooks shared by api.cu / api_vjp.cu.
+#pragma once
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/deephall_b200.h"
+#include "kernels.h"
+
+using namespace dh;
+
+struct LayerOff {
+  int64_t q_k, q_b, k_k, k_b, v_k, v_b, o_k, o_b, d1_k, ln0_s, ln0_b, d2_k, d2_b, ln1_s, ln1_b;
+};
+
+struct dh_plan {
+  dh_config cfg;
+  int N, L, K, D, H, hd, nl, twoQ, LNK;
+  float Q, radius;
+  std::vector<dh_param_entry> entries;
+  int64_t nparams;
+  int64_t off_W0;
+  std::vector<LayerOff> layer;
+  int64_t orb_re_k, orb_re_b, orb_im_k, orb_im_b, ee_par;
+  double* d_normfac;
+  int gemm_impl;  // 0 = SIMT, 1 = tcgen05 3xTF32
+  // prepared (pre-split, transposed) weights for the tcgen05 path
+  float* prep;            // device buffer owned by the plan
+  size_t prep_floats;
+  const float* prep_src;  // params pointer the preparation was made from
+  // ---- instrumentation (dh_profile_*): CUDA-event timing of kernel categories, launch count
+  bool prof_on;
+  std::vector<cudaEvent_t> prof_ev;   // pool, pairs (start, stop)
+  std::vector<int> prof_cat;          // category of pair i
+  std::vector<double> prof_flops;     // algorithmic flops of pair i
+  size_t prof_used;
+  long long launches;
+};
+
+enum ProfCat { PC_GEMM = 0, PC_ATTENTION = 1, PC_LAYERNORM = 2, PC_TAIL = 3, PC_MCMC = 4, PC_OTHER = 5, PC_COUNT = 6 };
+
+// Wraps one kernel launch: counts it and, when profiling, brackets it with events.
+struct ProfScope {
+  dh_plan* p; cudaStream_t s; bool active;
+  ProfScope(const dh_plan* plan, int cat, double flops, cudaStream_t st, int nlaunch = 1)
+      : p(const_cast<dh_plan*>(plan)), s(st), active(false) {
+    p->launches += nlaunch;
+    if (p->prof_on && p->prof_used + 2 <= p->prof_ev.size()) {
+      active = true;
+      p->prof_cat[p->prof_used / 2] = cat;
+      p->prof_flops[p->prof_used / 2] = flops;
+      cudaEventRecord(p->prof_ev[p->prof_used], s);
+    }
+  }
+  ~ProfScope() {
+    if (active) { cudaEventRecord(p->prof_ev[p->prof_used + 1], s); p->prof_used += 2; }
+  }
+};
+
+// --------------------------------------------------------------------------------- workspace
+struct FwdWs {
+  float *h, *t1, *t2, *qkv, *att, *cbuf, *Mj, *ld, *lpjet, *Minv;
+  size_t floats;
+};
+
+static inline size_t al(size_t n) { return (n + 63) / 64 * 64; }  // 256-byte granules
+
+static inline int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
+  int64_t c = p->cfg.chunk_walkers > 0 ? p->cfg.chunk_walkers : (jets ? 1024 : 16384);
+  return B < c ? B : c;
+}
+
+static inline FwdWs carve_fwd(const dh_plan* p, float* base, int64_t Bc, bool jets, bool keep_inverse) {
+  const int R = jets ? 2 * p->N + 8 : 1;
+  const size_t rows = (size_t)Bc * p->N * R;
+  FwdWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
+  w.h = take(rows * p->D);
+  w.t1 = take(rows * p->D);
+  w.t2 = take(rows * p->D);
+  w.qkv = take(rows * 3 * p->D);
+  w.att = take(rows * p->D);
+  w.cbuf = take(rows * 2 * (size_t)p->LNK);
+  w.Mj = take((size_t)Bc * p->K * R * p->N * p->N * 2);
+  w.ld = take((size_t)Bc * p->K * R * 2);
+  w.lpjet = take((size_t)Bc * R * 2);
+  w.Minv = keep_inverse ? take((size_t)Bc * p->K * p->N * p->N * 2) : nullptr;
+  w.floats = off;
+  return w;
+}
+
+struct McmcWs {
+  float *x2, *lp1, *logpsi2;
+  size_t floats;
+};
+static inline McmcWs carve_mcmc(const dh_plan* p, float* base, int64_t B) {
+  McmcWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
+  w.x2 = take((size_t)B * p->N * 2);
+  w.lp1 = take((size_t)B);
+  w.logpsi2 = take((size_t)B * 2);
+  w.floats = off;
+  return w;
+}
+
+static inline float* align_ws(void* ws) {
+  uintptr_t a = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+  return reinterpret_cast<float*>(a);
+}
+
+// --------------------------------------------------------------------------------- forward
+// C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
+static inline int dense(const dh_plan* p, const float* A, const float* W, const float* bias, float* C, int64_t rows,
+                 int Nout, int64_t ldc, int R, cudaStream_t s) {
+  ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * Nout * p->D, s);
+  return gemm_simt(A, W, bias, C, rows, Nout, p->D, p->D, 1, Nout, 1, ldc, R, 0, 1, s);
+}
+

@@ -149,6 +149,15 @@ int dh_gemm(const float* A, const float* W, const float* bias, float* C, int64_t
 int dh_debug_buffer(const dh_plan* plan, int op, int64_t B, const char* name, int64_t* offset,
                     int64_t* count);
 
+/* Instrumentation used by bench.py.  dh_launch_count: kernels launched through this plan so
+ * far.  dh_profile_begin/end: bracket every kernel launch of the following calls with CUDA
+ * events on the launching stream; dh_profile_end synchronises and returns, per category
+ * (0 dense contractions, 1 attention, 2 layernorm, 3 envelope+logdet+assembly, 4 mcmc, 5 other),
+ * the summed milliseconds, the number of timed scopes and the algorithmic flops. Arrays of 6. */
+long long dh_launch_count(const dh_plan* plan);
+int dh_profile_begin(dh_plan* plan, int32_t max_launches);
+int dh_profile_end(dh_plan* plan, double* ms_host, int32_t* count_host, double* flops_host);
+
 #ifdef __cplusplus
 }
 #endif
