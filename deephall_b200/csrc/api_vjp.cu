@@ -1,5 +1,166 @@
-#include "../../include/deephall_b200.h"
-#include "kernels.h"
-struct dh_plan;
-size_t vjp_ws_floats(const dh_plan*, int64_t) { return 0; }
-extern "C" int dh_logpsi_vjp(dh_plan*, const float*, const float*, int64_t, const float*, float*, float*, void*, size_t, void*) { return DH_E_UNSUPPORTED; }
+// dh_logpsi_vjp: one reverse pass through the value-only network for a batch of walkers,
+// contracting d(Re, Im log psi_b)/d params with per-walker cotangents (loss.py:53-64,96-106).
+#include <vector>
+
+#include "plan.h"
+
+namespace {
+
+struct VjpWs {
+  std::vector<float*> hs, qkv, att, t1, t2, hA, z;
+  float *cbuf, *Mj, *ld, *Minv, *logpsi, *lpjet;
+  float *gH, *gA, *gB, *gC, *gQKV, *gCb;
+  size_t floats;
+};
+
+VjpWs carve_vjp(const dh_plan* p, float* base, int64_t Bc) {
+  const size_t rows = (size_t)Bc * p->N;
+  const int D = p->D, nl = p->nl;
+  VjpWs w;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };
+  w.hs.resize(nl + 1);
+  w.qkv.resize(nl); w.att.resize(nl); w.t1.resize(nl); w.t2.resize(nl); w.hA.resize(nl); w.z.resize(nl);
+  for (int l = 0; l <= nl; ++l) w.hs[l] = take(rows * D);
+  for (int l = 0; l < nl; ++l) {
+    w.qkv[l] = take(rows * 3 * D);
+    w.att[l] = take(rows * D);
+    w.t1[l] = take(rows * D);
+    w.t2[l] = take(rows * D);
+    w.hA[l] = take(rows * D);
+    w.z[l] = take(rows * D);
+  }
+  w.cbuf = take(rows * 2 * (size_t)p->LNK);
+  w.Mj = take((size_t)Bc * p->K * p->N * p->N * 2);
+  w.ld = take((size_t)Bc * p->K * 2);
+  w.Minv = take((size_t)Bc * p->K * p->N * p->N * 2);
+  w.logpsi = take((size_t)Bc * 2);
+  w.lpjet = take((size_t)Bc * 2);
+  w.gH = take(rows * D);
+  w.gA = take(rows * D);
+  w.gB = take(rows * D);
+  w.gC = take(rows * D);
+  w.gQKV = take(rows * 3 * D);
+  w.gCb = take(rows * 2 * (size_t)p->LNK);
+  w.floats = off;
+  return w;
+}
+
+// C[rows, Din] (=|+=) G[rows, Nout] (ldg) @ W[Din, Nout]^T
+int dense_bwd_x(const dh_plan* p, const float* G, int64_t ldg, const float* W, int Nout, float* C, int64_t rows,
+                int Din, int accumulate, cudaStream_t s) {
+  ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * Nout * Din, s);
+  return gemm_simt(G, W, nullptr, C, rows, Din, Nout, ldg, 1, 1, Nout, Din, 1, accumulate, 1, s);
+}
+
+// dW[Din, Nout] += X[rows, Din]^T @ G[rows, Nout] (ldg)
+int dense_bwd_w(const dh_plan* p, const float* X, int Din, const float* G, int64_t ldg, int Nout, float* dW,
+                int64_t rows, cudaStream_t s) {
+  ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * Nout * Din, s);
+  const int tiles = ((Din + 127) / 128) * ((Nout + 127) / 128);
+  int split = 296 / tiles;
+  if (split < 1) split = 1;
+  const int64_t max_split = (rows + 127) / 128;
+  if (split > max_split) split = (int)max_split;
+  return gemm_simt(X, G, nullptr, dW, Din, Nout, rows, 1, Din, ldg, 1, Nout, 1, 1, split, s);
+}
+
+}  // namespace
+
+size_t vjp_ws_floats(const dh_plan* p, int64_t Bc) { return carve_vjp(p, nullptr, Bc).floats; }
+
+extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot,
+                             float* grad, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
+  if (!p || !P || !x || !cot || !grad || B < 0) return DH_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
+  if (B == 0) return 0;
+  const int64_t chunk = pick_chunk(p, false, B);
+  float* base = align_ws(ws);
+  VjpWs w = carve_vjp(p, base, chunk);
+  if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
+  const int N = p->N, D = p->D, nl = p->nl, LNK = p->LNK;
+  NetDims nd{N, 1, D, p->H, p->hd, p->cfg.n_up};
+  TailDims td{N, 1, p->L, p->K, p->twoQ, p->cfg.n_up};
+  int rc;
+#define RUN(cat, call)                          \
+  do {                                          \
+    ProfScope _ps(p, cat, 0, s);                \
+    if ((rc = (call))) return rc;               \
+  } while (0)
+
+  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+    const int64_t Bc = (B - b0) < chunk ? (B - b0) : chunk;
+    const int64_t rows = Bc * N;
+    const float* xc = x + b0 * N * 2;
+    const float* cotc = cot + b0 * 2;
+    // ------------------------------------------------------------ forward, keeping activations
+    RUN(PC_OTHER, features_dense0(xc, P + p->off_W0, w.hs[0], Bc, nd, s));
+    for (int l = 0; l < nl; ++l) {
+      const LayerOff& o = p->layer[l];
+      if ((rc = dense(p, w.hs[l], P + o.q_k, P + o.q_b, w.qkv[l], rows, D, 3 * D, 1, s))) return rc;
+      if ((rc = dense(p, w.hs[l], P + o.k_k, P + o.k_b, w.qkv[l] + D, rows, D, 3 * D, 1, s))) return rc;
+      if ((rc = dense(p, w.hs[l], P + o.v_k, P + o.v_b, w.qkv[l] + 2 * D, rows, D, 3 * D, 1, s))) return rc;
+      RUN(PC_ATTENTION, attention_value(w.qkv[l], w.att[l], Bc, nd, s));
+      if ((rc = dense(p, w.att[l], P + o.o_k, P + o.o_b, w.t1[l], rows, D, D, 1, s))) return rc;
+      if ((rc = dense(p, w.t1[l], P + o.d1_k, nullptr, w.t2[l], rows, D, D, 1, s))) return rc;
+      RUN(PC_LAYERNORM, residual_layernorm(w.hs[l], w.t2[l], P + o.ln0_s, P + o.ln0_b, w.hA[l], Bc, nd, 0, s));
+      if ((rc = dense(p, w.hA[l], P + o.d2_k, P + o.d2_b, w.z[l], rows, D, D, 1, s))) return rc;
+      RUN(PC_LAYERNORM, residual_layernorm(w.hA[l], w.z[l], P + o.ln1_s, P + o.ln1_b, w.hs[l + 1], Bc, nd, 1, s));
+    }
+    const float* hf = w.hs[nl];
+    if ((rc = dense(p, hf, P + p->orb_re_k, P + p->orb_re_b, w.cbuf, rows, LNK, 2 * (int64_t)LNK, 1, s))) return rc;
+    if ((rc = dense(p, hf, P + p->orb_im_k, P + p->orb_im_b, w.cbuf + LNK, rows, LNK, 2 * (int64_t)LNK, 1, s))) return rc;
+    RUN(PC_TAIL, orbital_contract(w.cbuf, xc, p->d_normfac, w.Mj, Bc, td, s));
+    RUN(PC_TAIL, logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s));
+    if (out_logpsi) {
+      FinalizeArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.ld = w.ld; fa.x = xc;
+      fa.ee_par = p->ee_par >= 0 ? P + p->ee_par : nullptr;
+      fa.Q = p->Q; fa.radius = p->radius;
+      fa.interaction_strength = p->cfg.interaction_strength;
+      fa.interaction_type = p->cfg.interaction_type;
+      fa.out_logpsi = out_logpsi + b0 * 2;
+      RUN(PC_TAIL, finalize(fa, Bc, td, s));
+    }
+    // ------------------------------------------------------------ backward
+    RUN(PC_TAIL, tail_bwd(cotc, w.ld, w.Minv, xc, p->d_normfac, w.gCb, Bc, td, s));
+    if (p->ee_par >= 0) RUN(PC_TAIL, jastrow_bwd(cotc, xc, P + p->ee_par, grad + p->ee_par, Bc, N, s));
+    // orbital projections
+    if ((rc = dense_bwd_w(p, hf, D, w.gCb, 2 * (int64_t)LNK, LNK, grad + p->orb_re_k, rows, s))) return rc;
+    if ((rc = dense_bwd_w(p, hf, D, w.gCb + LNK, 2 * (int64_t)LNK, LNK, grad + p->orb_im_k, rows, s))) return rc;
+    RUN(PC_OTHER, colsum_add(w.gCb, grad + p->orb_re_b, rows, LNK, 2 * (int64_t)LNK, s));
+    RUN(PC_OTHER, colsum_add(w.gCb + LNK, grad + p->orb_im_b, rows, LNK, 2 * (int64_t)LNK, s));
+    if ((rc = dense_bwd_x(p, w.gCb, 2 * (int64_t)LNK, P + p->orb_re_k, LNK, w.gH, rows, D, 0, s))) return rc;
+    if ((rc = dense_bwd_x(p, w.gCb + LNK, 2 * (int64_t)LNK, P + p->orb_im_k, LNK, w.gH, rows, D, 1, s))) return rc;
+    for (int l = nl - 1; l >= 0; --l) {
+      const LayerOff& o = p->layer[l];
+      // h_out = LN1(hA + tanh(z)) : gH -> (gA = d/d hA, gB = d/d z)
+      RUN(PC_LAYERNORM, residual_layernorm_bwd(w.hA[l], w.z[l], P + o.ln1_s, w.gH, w.gA, w.gB, grad + o.ln1_s,
+                                               grad + o.ln1_b, rows, D, 1, s));
+      if ((rc = dense_bwd_w(p, w.hA[l], D, w.gB, D, D, grad + o.d2_k, rows, s))) return rc;
+      RUN(PC_OTHER, colsum_add(w.gB, grad + o.d2_b, rows, D, D, s));
+      if ((rc = dense_bwd_x(p, w.gB, D, P + o.d2_k, D, w.gA, rows, D, 1, s))) return rc;
+      // hA = LN0(h_in + t2) : gA -> (gH = d/d h_in, gB = d/d t2)
+      RUN(PC_LAYERNORM, residual_layernorm_bwd(w.hs[l], w.t2[l], P + o.ln0_s, w.gA, w.gH, w.gB, grad + o.ln0_s,
+                                               grad + o.ln0_b, rows, D, 0, s));
+      if ((rc = dense_bwd_w(p, w.t1[l], D, w.gB, D, D, grad + o.d1_k, rows, s))) return rc;
+      if ((rc = dense_bwd_x(p, w.gB, D, P + o.d1_k, D, w.gC, rows, D, 0, s))) return rc;   // gC = d/d t1
+      if ((rc = dense_bwd_w(p, w.att[l], D, w.gC, D, D, grad + o.o_k, rows, s))) return rc;
+      RUN(PC_OTHER, colsum_add(w.gC, grad + o.o_b, rows, D, D, s));
+      if ((rc = dense_bwd_x(p, w.gC, D, P + o.o_k, D, w.gB, rows, D, 0, s))) return rc;    // gB = d/d att
+      RUN(PC_ATTENTION, attention_value_bwd(w.qkv[l], w.gB, w.gQKV, Bc, nd, s));
+      const int64_t qk[3] = {o.q_k, o.k_k, o.v_k};
+      const int64_t qb[3] = {o.q_b, o.k_b, o.v_b};
+      for (int t = 0; t < 3; ++t) {
+        if ((rc = dense_bwd_w(p, w.hs[l], D, w.gQKV + t * D, 3 * D, D, grad + qk[t], rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.gQKV + t * D, grad + qb[t], rows, D, 3 * D, s));
+        if ((rc = dense_bwd_x(p, w.gQKV + t * D, 3 * D, P + qk[t], D, w.gH, rows, D, 1, s))) return rc;
+      }
+    }
+    RUN(PC_OTHER, features_dense0_bwd(xc, w.gH, grad + p->off_W0, Bc, nd, s));
+  }
+#undef RUN
+  return 0;
+}

@@ -73,13 +73,12 @@ int init_walkers(float* x, int64_t B, int N, uint64_t seed, uint64_t subseq0, cu
 int lp_from_logpsi(const float* logpsi_c, float* lp, int64_t B, cudaStream_t s);
 
 // ---- vjp_kernels.cu
-int finalize_bwd(const float* cot, const float* x, const float* ee_par, const float* ld0, const float* logpsi,
-                 float* g_ld, float* g_eepar, int64_t B, TailDims d, cudaStream_t s);
-int logdet_bwd(const float* M0, const float* g_ld, float* g_M, int64_t B, TailDims d, cudaStream_t s);
-int orbital_contract_bwd(const float* g_M, const float* x, const float* normfac, float* g_c, int64_t B,
-                         TailDims d, cudaStream_t s);
+int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* x, const double* normfac,
+             float* g_c, int64_t B, TailDims d, cudaStream_t s);
+int jastrow_bwd(const float* cot, const float* x, const float* ee_par, float* g_eepar, int64_t B, int N,
+                cudaStream_t s);
 int residual_layernorm_bwd(const float* a, const float* b, const float* scale, const float* g_out, float* g_a,
-                           float* g_b, float* g_scale, float* g_bias, int64_t B, NetDims d, int tanh_mode,
+                           float* g_b, float* g_scale, float* g_bias, int64_t rows, int D, int tanh_mode,
                            cudaStream_t s);
 int attention_value_bwd(const float* qkv, const float* g_o, float* g_qkv, int64_t B, NetDims d, cudaStream_t s);
 int features_dense0_bwd(const float* x, const float* g_h, float* g_W0, int64_t B, NetDims d, cudaStream_t s);

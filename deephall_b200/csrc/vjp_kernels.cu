@@ -1,1 +1,356 @@
+// Reverse-mode kernels for d(Re, Im log psi)/d params contracted with per-walker cotangents
+// (loss.py:53-64,96-106 computes the same number from materialised per-walker gradients).
+// Value-only activations (R = 1).  Convention: for a complex intermediate z the "gradient"
+// G_z satisfies dL = Re(G_z dz); for log psi, G = cot_re - i cot_im.
 #include "kernels.h"
+
+namespace dh {
+
+typedef double2 dcplx;
+
+// =============================================================================================
+// tail backward: (cot, ld, Minv, x) -> g_c [rows, 2*L*N*K].  One block per (walker, electron).
+//   w_k = softmax_k(ld_k) (complex), G_k = G w_k, G^M_ij = G_k (M_k^-1)_ji,
+//   dL/dc_re[i,m,j,k] = Re(G^M_ij env_im), dL/dc_im = -Im(G^M_ij env_im).
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+tail_bwd_kernel(const float* __restrict__ cot, const float* __restrict__ ld, const float* __restrict__ Minv,
+                const float* __restrict__ x, const double* __restrict__ normfac, float* __restrict__ g_c,
+                TailDims dm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = dm.N, L = dm.L, K = dm.K, twoQ = dm.twoQ;
+  dcplx* upow = reinterpret_cast<dcplx*>(smraw);
+  dcplx* vpow = upow + L;
+  cplx* env = reinterpret_cast<cplx*>(vpow + L);  // [L]
+  cplx* gm = env + L;                             // [N*K]  G^M_{i j} for this electron i, per (j,k)
+  const int64_t bi = blockIdx.x;
+  const int64_t b = bi / N;
+  const int i = (int)(bi % N);
+  const int tid = threadIdx.x;
+  // envelope values (double powers, as in the forward)
+  {
+    double sh, ch, sph, cph;
+    sincos(0.5 * (double)x[bi * 2], &sh, &ch);
+    sincos(0.5 * (double)x[bi * 2 + 1], &sph, &cph);
+    const dcplx u = make_double2(ch * cph, ch * sph);
+    const dcplx v = make_double2(sh * cph, -sh * sph);
+    if (tid < 2) {
+      dcplx z = tid == 0 ? u : v;
+      dcplx* tab = tid == 0 ? upow : vpow;
+      dcplx p = make_double2(1.0, 0.0);
+      for (int e = 0; e <= twoQ; ++e) {
+        tab[e] = p;
+        p = make_double2(p.x * z.x - p.y * z.y, p.x * z.y + p.y * z.x);
+      }
+    }
+    __syncthreads();
+    for (int m = tid; m < L; m += blockDim.x) {
+      dcplx a = upow[m], c = vpow[twoQ - m];
+      const double nf = normfac[m];
+      env[m] = make_float2((float)(nf * (a.x * c.x - a.y * c.y)), (float)(nf * (a.x * c.y + a.y * c.x)));
+    }
+  }
+  // determinant weights and G^M
+  const cplx* ldb = reinterpret_cast<const cplx*>(ld) + b * K;
+  float mx = -INFINITY;
+  for (int k = 0; k < K; ++k) mx = fmaxf(mx, ldb[k].x);
+  float sr = 0.f, si = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float e = expf(ldb[k].x - mx), s_, c_;
+    sincosf(ldb[k].y, &s_, &c_);
+    sr += e * c_; si += e * s_;
+  }
+  const cplx sinv = cinv(cmake(sr, si));
+  const cplx G = cmake(cot[b * 2], -cot[b * 2 + 1]);
+  for (int t = tid; t < N * K; t += blockDim.x) {
+    const int j = t / K, k = t % K;
+    float e = expf(ldb[k].x - mx), s_, c_;
+    sincosf(ldb[k].y, &s_, &c_);
+    const cplx wk = cmul(cmake(e * c_, e * s_), sinv);
+    const cplx mi = reinterpret_cast<const cplx*>(Minv)[((b * K + k) * N + j) * N + i];  // (M^-1)_{j i}
+    gm[t] = cmul(cmul(G, wk), mi);
+  }
+  __syncthreads();
+  const int NK = N * K, LNK = L * NK;
+  float* row = g_c + bi * 2 * (int64_t)LNK;
+  for (int t = tid; t < LNK; t += blockDim.x) {
+    const int m = t / NK, jk = t % NK;
+    const cplx val = cmul(gm[jk], env[m]);
+    row[t] = val.x;
+    row[LNK + t] = -val.y;
+  }
+}
+
+int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* x, const double* normfac,
+             float* g_c, int64_t B, TailDims d, cudaStream_t s) {
+  size_t smem = 2 * d.L * sizeof(dcplx) + (size_t)(d.L + d.N * d.K) * sizeof(cplx);
+  tail_bwd_kernel<<<(unsigned)(B * d.N), 128, smem, s>>>(cot, ld, Minv, x, normfac, g_c, d);
+  return (int)cudaGetLastError();
+}
+
+// d Jastrow / d ee_par summed over walkers with weight cot_re (the Jastrow is real).
+__global__ void jastrow_bwd_kernel(const float* __restrict__ cot, const float* __restrict__ x,
+                                   const float* __restrict__ ee_par, float* __restrict__ g_eepar, int64_t B, int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+  float acc = 0.f;
+  if (b < B && lane < N) {
+    const float a = ee_par[0];
+    const float* xw = x + b * N * 2;
+    float st, ct, sp, cp;
+    sincosf(xw[lane * 2], &st, &ct);
+    sincosf(xw[lane * 2 + 1], &sp, &cp);
+    const float rx = st * cp, ry = st * sp, rz = ct;
+    for (int j = lane + 1; j < N; ++j) {
+      float sj, cj, spj, cpj;
+      sincosf(xw[j * 2], &sj, &cj);
+      sincosf(xw[j * 2 + 1], &spj, &cpj);
+      const float dx = rx - sj * cpj, dy = ry - sj * spj, dz = rz - cj;
+      const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+      const float ar = a + r;
+      acc += -0.25f * (a * a + 2.f * a * r) / (ar * ar);  // d/da [-a^2/4/(a+r)]
+    }
+    acc *= cot[b * 2];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && b < B) atomicAdd(g_eepar, acc);
+}
+
+int jastrow_bwd(const float* cot, const float* x, const float* ee_par, float* g_eepar, int64_t B, int N,
+                cudaStream_t s) {
+  const int wpb = 4;
+  jastrow_bwd_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, s>>>(cot, x, ee_par, g_eepar, B, N);
+  return (int)cudaGetLastError();
+}
+
+// =============================================================================================
+// LayerNorm backward: u = a + (TANH ? tanh(b) : b); y = LN(u).  One warp per row, grid-stride.
+// g_a = dL/du ; g_b = g_a or g_a * (1 - tanh^2 b) ; g_scale/g_bias accumulated with atomics.
+// =============================================================================================
+constexpr int LNB_VPL = 8;
+
+template <bool TANH>
+__global__ void __launch_bounds__(256)
+residual_layernorm_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                              const float* __restrict__ scale, const float* __restrict__ g_out,
+                              float* __restrict__ g_a, float* __restrict__ g_b, float* __restrict__ g_scale,
+                              float* __restrict__ g_bias, int64_t rows, int D) {
+  __shared__ float red[2][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int vpl = D >> 5;
+  const float invD = 1.f / (float)D;
+  float gam[LNB_VPL], gs[LNB_VPL], gb[LNB_VPL];
+#pragma unroll
+  for (int v = 0; v < LNB_VPL; ++v) {
+    gam[v] = v < vpl ? scale[lane + 32 * v] : 0.f;
+    gs[v] = 0.f; gb[v] = 0.f;
+  }
+  for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
+    float u[LNB_VPL], tp[LNB_VPL], gy[LNB_VPL];
+    float sum = 0.f;
+#pragma unroll
+    for (int v = 0; v < LNB_VPL; ++v) {
+      u[v] = 0.f; tp[v] = 1.f; gy[v] = 0.f;
+      if (v < vpl) {
+        const int64_t idx = row * D + lane + 32 * v;
+        float bv = b[idx];
+        if (TANH) { float t = tanhf(bv); tp[v] = 1.f - t * t; bv = t; }
+        u[v] = a[idx] + bv;
+        gy[v] = g_out[idx];
+        sum += u[v];
+      }
+    }
+    const float mu = warp_sum(sum) * invD;
+    float sq = 0.f;
+#pragma unroll
+    for (int v = 0; v < LNB_VPL; ++v) { u[v] = v < vpl ? u[v] - mu : 0.f; sq += u[v] * u[v]; }
+    const float rho = rsqrtf(warp_sum(sq) * invD + 1e-5f);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < LNB_VPL; ++v) {
+      u[v] *= rho;  // x_hat
+      const float gx = gy[v] * gam[v];
+      m1 += gx; m2 += gx * u[v];
+      gs[v] += gy[v] * u[v];
+      gb[v] += gy[v];
+    }
+    m1 = warp_sum(m1) * invD;
+    m2 = warp_sum(m2) * invD;
+#pragma unroll
+    for (int v = 0; v < LNB_VPL; ++v) {
+      if (v < vpl) {
+        const int64_t idx = row * D + lane + 32 * v;
+        const float gu = rho * (gy[v] * gam[v] - m1 - u[v] * m2);
+        g_a[idx] = gu;
+        g_b[idx] = TANH ? gu * tp[v] : gu;
+      }
+    }
+  }
+  // block reduction of g_scale / g_bias partials, then one atomic per column per block
+  for (int v = 0; v < vpl; ++v) {
+    __syncthreads();
+    red[0][threadIdx.x] = gs[v];
+    red[1][threadIdx.x] = gb[v];
+    __syncthreads();
+    if (warp == 0) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int w = 0; w < nwarp; ++w) { s0 += red[0][w * 32 + lane]; s1 += red[1][w * 32 + lane]; }
+      atomicAdd(g_scale + lane + 32 * v, s0);
+      atomicAdd(g_bias + lane + 32 * v, s1);
+    }
+  }
+}
+
+int residual_layernorm_bwd(const float* a, const float* b, const float* scale, const float* g_out, float* g_a,
+                           float* g_b, float* g_scale, float* g_bias, int64_t rows, int D, int tanh_mode,
+                           cudaStream_t s) {
+  if (D % 32 != 0 || D > 32 * LNB_VPL) return -2;
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (tanh_mode)
+    residual_layernorm_bwd_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(a, b, scale, g_out, g_a, g_b, g_scale, g_bias, rows, D);
+  else
+    residual_layernorm_bwd_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(a, b, scale, g_out, g_a, g_b, g_scale, g_bias, rows, D);
+  return (int)cudaGetLastError();
+}
+
+// =============================================================================================
+// attention backward (value-only): one block per walker.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+attention_value_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g_o,
+                           float* __restrict__ g_qkv, NetDims dm) {
+  extern __shared__ float sm[];
+  const int N = dm.N, D = dm.D, H = dm.H, hd = dm.hd;
+  float* sq = sm;                   // [N][3D]
+  float* sgo = sq + N * 3 * D;      // [N][D]
+  float* sp = sgo + N * D;          // [H][N][N] probabilities
+  float* sgs = sp + H * N * N;      // [H][N][N] dL/ds
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  for (int t = tid; t < N * 3 * D; t += blockDim.x) sq[t] = qkv[b * N * 3 * D + t];
+  for (int t = tid; t < N * D; t += blockDim.x) sgo[t] = g_o[b * N * D + t];
+  __syncthreads();
+  const float scl = rsqrtf((float)hd);
+  // scores + softmax + dL/dp -> dL/ds ; one warp per (h, i)
+  for (int w = warp; w < H * N; w += nwarp) {
+    const int hh = w / N, i = w % N;
+    const float* q = sq + i * 3 * D + hh * hd;
+    const float* go = sgo + i * D + hh * hd;
+    float sc[32], gp[32];
+    float mx = -INFINITY;
+    for (int j = 0; j < N; ++j) {
+      const float* k = sq + j * 3 * D + D + hh * hd;
+      const float* v = sq + j * 3 * D + 2 * D + hh * hd;
+      float p = 0.f, g = 0.f;
+      for (int d = lane; d < hd; d += 32) { p = fmaf(q[d], k[d], p); g = fmaf(go[d], v[d], g); }
+      sc[j] = warp_sum(p) * scl;
+      gp[j] = warp_sum(g);
+      mx = fmaxf(mx, sc[j]);
+    }
+    float Z = 0.f;
+    for (int j = 0; j < N; ++j) { sc[j] = expf(sc[j] - mx); Z += sc[j]; }
+    const float iz = 1.f / Z;
+    float dot = 0.f;
+    for (int j = 0; j < N; ++j) { sc[j] *= iz; dot = fmaf(sc[j], gp[j], dot); }
+    if (lane == 0) {
+      for (int j = 0; j < N; ++j) {
+        sp[(hh * N + i) * N + j] = sc[j];
+        sgs[(hh * N + i) * N + j] = sc[j] * (gp[j] - dot) * scl;
+      }
+    }
+  }
+  __syncthreads();
+  // g_q_i = sum_j gs_ij k_j ; g_k_j = sum_i gs_ij q_i ; g_v_j = sum_i p_ij go_i
+  float* out = g_qkv + b * N * 3 * D;
+  for (int t = tid; t < N * D; t += blockDim.x) {
+    const int n = t / D, c = t % D, hh = c / hd;
+    float gq = 0.f, gk = 0.f, gv = 0.f;
+    for (int m = 0; m < N; ++m) {
+      gq = fmaf(sgs[(hh * N + n) * N + m], sq[m * 3 * D + D + c], gq);
+      gk = fmaf(sgs[(hh * N + m) * N + n], sq[m * 3 * D + c], gk);
+      gv = fmaf(sp[(hh * N + m) * N + n], sgo[m * D + c], gv);
+    }
+    out[n * 3 * D + c] = gq;
+    out[n * 3 * D + D + c] = gk;
+    out[n * 3 * D + 2 * D + c] = gv;
+  }
+}
+
+int attention_value_bwd(const float* qkv, const float* g_o, float* g_qkv, int64_t B, NetDims d, cudaStream_t s) {
+  if (d.N > 32) return -2;
+  size_t smem = ((size_t)d.N * 4 * d.D + 2 * (size_t)d.H * d.N * d.N) * sizeof(float);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(attention_value_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  attention_value_bwd_kernel<<<(unsigned)B, 256, smem, s>>>(qkv, g_o, g_qkv, d);
+  return (int)cudaGetLastError();
+}
+
+// =============================================================================================
+// Dense_0 backward: g_W0[c, d] += sum_rows feat[row, c] g_h[row, d]   (features recomputed)
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+features_dense0_bwd_kernel(const float* __restrict__ x, const float* __restrict__ g_h, float* __restrict__ g_W0,
+                           int64_t rows, NetDims dm, int rows_per_block) {
+  const int D = dm.D, N = dm.N;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      float st, ct, sp, cp;
+      sincosf(x[r * 2], &st, &ct);
+      sincosf(x[r * 2 + 1], &sp, &cp);
+      const float g = g_h[r * D + d];
+      a0 = fmaf(ct, g, a0);
+      a1 = fmaf(st * cp, g, a1);
+      a2 = fmaf(st * sp, g, a2);
+      a3 = fmaf((int)(r % N) < dm.n_up ? 1.f : -1.f, g, a3);
+    }
+    atomicAdd(g_W0 + d, a0);
+    atomicAdd(g_W0 + D + d, a1);
+    atomicAdd(g_W0 + 2 * D + d, a2);
+    atomicAdd(g_W0 + 3 * D + d, a3);
+  }
+}
+
+int features_dense0_bwd(const float* x, const float* g_h, float* g_W0, int64_t B, NetDims d, cudaStream_t s) {
+  const int64_t rows = B * d.N;
+  const int rpb = 64;
+  int threads = d.D >= 256 ? 256 : ((d.D + 31) / 32 * 32);
+  features_dense0_bwd_kernel<<<(unsigned)((rows + rpb - 1) / rpb), threads, 0, s>>>(x, g_h, g_W0, rows, d, rpb);
+  return (int)cudaGetLastError();
+}
+
+// out[n] += sum_m g[m*ld + n]
+__global__ void __launch_bounds__(256)
+colsum_add_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t M, int N, int64_t ld,
+                  int rows_per_block) {
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) acc += g[r * ld + n];
+  atomicAdd(out + n, acc);
+}
+
+int colsum_add(const float* g, float* out, int64_t M, int N, int64_t ld, cudaStream_t s) {
+  const int rpb = 256;
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)((M + rpb - 1) / rpb));
+  colsum_add_kernel<<<grid, 256, 0, s>>>(g, out, M, N, ld, rpb);
+  return (int)cudaGetLastError();
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+int add_inplace(float* dst, const float* src, int64_t n, cudaStream_t s) {
+  add_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(dst, src, n);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dh

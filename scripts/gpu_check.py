@@ -129,6 +129,66 @@ def check_mcmc(cfgkw, B=64):
     print(f"mcmc philox: pmove {nacc2.item() / (10 * B):.3f}")
 
 
+def check_vjp(cfgkw, B=16):
+    cfg, p64, x = make(cfgkw, B)
+    plan = nat.Plan(nspins=cfg.nspins, flux=cfg.flux, ndets=cfg.ndets, num_heads=cfg.num_heads,
+                    heads_dim=cfg.heads_dim, num_layers=cfg.num_layers)
+    flat64 = OP.flatten_params(p64)
+    flat = flat64.float().to(dev)
+    cot = torch.randn(B, 2)
+    g = plan.logpsi_vjp(flat, x.to(dev), cot.to(dev))
+    p = flat64.clone().requires_grad_(True)
+    lp = OP.logpsi(OP.unflatten_params(p, cfg), x.double(), cfg)
+    obj = (lp.real * cot[:, 0].double() + lp.imag * cot[:, 1].double()).sum()
+    (gref,) = torch.autograd.grad(obj, p)
+    gd = g.double().cpu()
+    print(f"{cfgkw}: vjp rel err (global) {(gd - gref).norm() / gref.norm():.2e}")
+    off = 0
+    for name, shape in OP.param_shapes(cfg).items():
+        n = 1
+        for q in shape:
+            n *= q
+        a, b = gd[off:off + n], gref[off:off + n]
+        e = (a - b).norm() / (b.norm() + 1e-30)
+        if e > 1e-4:
+            print(f"     {name}: rel {e:.2e} |ref| {b.norm():.3e}")
+        off += n
+
+
+def timing(cfgkw, B):
+    cfg, p64, x = make(cfgkw, 64)
+    plan = nat.Plan(nspins=cfg.nspins, flux=cfg.flux, ndets=cfg.ndets, num_heads=cfg.num_heads,
+                    heads_dim=cfg.heads_dim, num_layers=cfg.num_layers)
+    flat = OP.flatten_params(p64).float().to(dev)
+    xd = plan.init_walkers(B, seed=1)
+    plan.mcmc_sweep(flat, xd, 10, 0.1, seed=3)
+    def t(fn, n=3):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    ms = t(lambda: plan.logpsi(flat, xd))
+    print(f"{cfgkw} B={B}: logpsi {ms:.2f} ms -> {B / ms * 1e3:.3e} evals/s")
+    ms = t(lambda: plan.mcmc_sweep(flat, xd, 10, 0.1, seed=5))
+    print(f"   mcmc 10 moves {ms:.2f} ms -> {B * 10 / ms * 1e3:.3e} walker-steps/s")
+    ms = t(lambda: plan.local_energy(flat, xd), n=2)
+    print(f"   local_energy {ms:.2f} ms -> {B / ms * 1e3:.3e} evals/s")
+    plan.profile_begin()
+    plan.local_energy(flat, xd)
+    pr = plan.profile_end()
+    print("   LE profile:", {k: (round(v['ms'], 2), v['count'], round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 1)) for k, v in pr.items()})
+    cot = torch.randn(B, 2, device=dev) / B
+    ms = t(lambda: plan.logpsi_vjp(flat, xd, cot), n=2)
+    print(f"   vjp {ms:.2f} ms")
+    plan.profile_begin()
+    plan.logpsi_vjp(flat, xd, cot)
+    pr = plan.profile_end()
+    print("   VJP profile:", {k: (round(v['ms'], 2), v['count'], round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 1)) for k, v in pr.items()})
+
+
 if __name__ == "__main__":
     print(nat.load().dh_version().decode())
     check_gemm()
@@ -139,3 +199,7 @@ if __name__ == "__main__":
     check_forward(dict(nspins=(12, 0), flux=33), B=8, detail=True)
     check_forward(dict(nspins=(16, 0), flux=45, ndets=4), B=4)
     check_mcmc(dict(nspins=(6, 0), flux=15))
+    check_vjp(dict(nspins=(3, 0), flux=2))
+    check_vjp(dict(nspins=(5, 0), flux=11, ndets=2))
+    check_vjp(dict(nspins=(12, 0), flux=33), B=8)
+    timing(dict(nspins=(12, 0), flux=33), 8192)
