@@ -1,0 +1,307 @@
+"""Benchmark of the walker-evaluation hot path (BASELINE.json metric: walker local-energy
+evals/sec and VMC steps/sec at N=12).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host CPUs
+
+A "step" is one `local_energy` pass (E_L + the five observables, hamiltonian.py:207-210) over
+the batch.  Workload = BASELINE.json configs[2] (the configuration the metric is quoted on):
+nspins=[12,0], flux=33, default Psiformer (4x64, 2 layers, 1 det), batch 8192 walkers per GPU,
+interaction_strength 1.  Walkers are sharded over GPUs with no data-path collective (weak
+scaling); one JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(nspins=(12, 0), flux=33, num_heads=4, heads_dim=64, num_layers=2, determinants=1,
+                batch_per_gpu=8192, interaction_strength=1.0, mcmc_steps=10, mcmc_width=0.1)
+WORKLOAD_NAME = "c3: nspins=[12,0] flux=33 (1/3 filling), default Psiformer, batch 8192 per GPU"
+METRIC = "local_energy_evals_per_sec"
+UNIT = "walker local-energy evals/s"
+
+
+def flops_local_energy_per_walker(N, L, K, D=256, nl=2):
+    """Algorithmic flops of the dense contractions as executed (R = 2N+8 rows, no block-diagonal
+    shortcut): 2*R*N*D*(nl*6*D + 2*L*N*K).  DESIGN.md 'Measurement'."""
+    R = 2 * N + 8
+    return 2.0 * R * N * D * (nl * 6 * D + 2 * L * N * K)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.th.join(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# --------------------------------------------------------------------------------- CPU reference leg
+def cpu_reference_local_energy(nwalkers, steps=1, warmup=0):
+    """Times the reference's algorithm (complex gradient + full Hessian of log psi,
+    hamiltonian.py:105-133) restated in torch on the host cores, fp32, on `nwalkers` walkers."""
+    from oracle import hamiltonian as OH
+    from oracle import mcmc as OM
+    from oracle import psiformer as OP
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = OP.NetCfg(nspins=WORKLOAD["nspins"], flux=WORKLOAD["flux"], ndets=WORKLOAD["determinants"],
+                    num_heads=WORKLOAD["num_heads"], heads_dim=WORKLOAD["heads_dim"], num_layers=WORKLOAD["num_layers"])
+    params = OP.init_params(cfg, 0, torch.float32)
+    x = OM.init_guess(torch.Generator().manual_seed(42), nwalkers, cfg.nelec, torch.float32)
+
+    def f(xx):
+        return OP.logpsi(params, xx, cfg)
+
+    def one():
+        return OH.batch_local_energy(f, x, cfg.Q, interaction_strength=WORKLOAD["interaction_strength"], chunk=32)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = one()
+    dt = time.perf_counter() - t0
+    assert torch.isfinite(out["energy"].real).any()
+    return nwalkers * steps / dt, dt / steps, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 32
+    val, spstep, cores = cpu_reference_local_energy(sample, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (uniform walkers on the sphere, random-init parameters)",
+        "config": {"workload": WORKLOAD_NAME, "sample": f"{sample} walkers per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} walkers/step x {args.steps} steps; torch-CPU restatement of the reference algorithm "
+                                   "(jax/flax are not installable here, so the reference itself cannot run)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------- CUDA arm
+def run_ours(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from deephall_b200 import hamiltonian, mcmc, networks
+    from deephall_b200.config import Config, MCMC, Network, Optim, PsiformerNetwork, System
+    from deephall_b200.train import VMC
+
+    W = WORKLOAD
+    B = W["batch_per_gpu"]
+    N = sum(W["nspins"])
+    system = System(flux=W["flux"], nspins=W["nspins"], interaction_strength=W["interaction_strength"])
+    network = Network(psiformer=PsiformerNetwork(W["num_heads"], W["heads_dim"], W["num_layers"], W["determinants"]))
+    cfg = Config(batch_size=B * world, seed=42, system=system, network=network,
+                 mcmc=MCMC(steps=W["mcmc_steps"], width=W["mcmc_width"]), optim=Optim(optimizer="adam"))
+    vmc = VMC(cfg)
+    model, params = vmc.model, vmc.state.params
+    vmc.burn_in(20)  # synthetic walkers: short equilibration, not timed
+    data = vmc.state.data
+    plan = model.plan(system)
+    e_l = hamiltonian.local_energy(model.apply, system)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    # ---- headline: device-resident local-energy passes
+    result = {}
+
+    def le_step():
+        result["el"] = plan.local_energy(params, data)
+
+    for _ in range(args.warmup):
+        le_step()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = plan.launch_count
+    ms_total = timed(le_step, args.steps, 0)
+    launches = plan.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = B * world * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host walkers -> public API -> host energies, every step
+    x_host = data.cpu().pin_memory()
+    el_host = torch.empty((B,), dtype=torch.complex64).pin_memory()
+    x_dev = torch.empty_like(data)
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        el, _obs = e_l(params, x_dev)
+        el_host.copy_(el, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms_e2e = timed(e2e_step, args.steps, 1)
+    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+
+    # ---- the other two metrics of BASELINE.json (same hygiene, fewer steps)
+    k2 = max(1, min(args.steps, 3))
+    ms_mcmc = timed(lambda: vmc.mcmc_step(params, data, mcmc.PhiloxKey(7), W["mcmc_width"]), k2, 1) / k2
+    ms_vmc = timed(lambda: vmc.step(sync_stats=False), k2, 1) / k2
+
+    # ---- roofline of the dominant kernel (dense contractions), CUDA-event timed per launch
+    barrier()
+    plan.profile_begin()
+    plan.local_energy(params, data)
+    prof = plan.profile_end()
+    peaks = measured_peaks()
+    g = prof["gemm"]
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = {
+        "bound": "tensor", "kernel": "dense contraction (dh::gemm_*)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak, "traffic": None,
+        "launches": g["count"], "avg_launch_ms": g["ms"] / max(g["count"], 1),
+        "share_of_step": g["ms"] / sum(v["ms"] for v in prof.values()),
+        "peak_source": peaks["source"] + ", dense bf16 sustained; fp32-accurate 3xTF32 can reach at most 1/6 of it",
+        "per_category_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+    }
+
+    if rank == 0:
+        cpu = None
+        if world == 1:
+            sample = 64
+            v, sps, cores = cpu_reference_local_energy(sample, steps=1, warmup=0)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{sample} walkers of the same workload, one pass ({sps:.1f} s); torch-CPU restatement of the reference "
+                             "algorithm (grad + full Hessian), eager fp32; the JAX reference is not installable here"}
+        el = result["el"]["energy"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (Philox uniform walkers + 20 burn-in sweeps, random-init parameters)",
+            "config": {"workload": WORKLOAD_NAME, "global_batch": B * world, "parallelism": f"walkers sharded x{world}",
+                       "l2": "per-pass working set (GBs of jet activations) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world,
+                    "d2h_bytes_per_step": el_host.numel() * 8 * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "extra": {
+                "walker_steps_per_sec": B * world * W["mcmc_steps"] / (ms_mcmc * 1e-3),
+                "mcmc_step_ms": ms_mcmc,
+                "vmc_steps_per_sec": 1.0 / (ms_vmc * 1e-3),
+                "vmc_step_ms": ms_vmc,
+                "mean_energy": float(torch.nanmean(el.real)),
+                "algorithmic_flops_per_walker": flops_local_energy_per_walker(N, W["flux"] + 1, W["determinants"]),
+            },
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

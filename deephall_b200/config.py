@@ -101,18 +101,18 @@ class Config:  # config.py:201-214
 
 def from_dict(cls, dikt: dict[str, Any]):
     """Nested dict -> dataclass; unknown keys are ignored (config.py:23-48 tolerates them)."""
-    kwargs = {}
-    for f in dc.fields(cls):
-        if f.name not in dikt:
-            continue
-        v = dikt[f.name]
-        sub = _DATACLASS_FIELDS.get((cls.__name__, f.name))
-        if sub is not None and isinstance(v, dict):
-            v = from_dict(sub, v)
-        elif f.name == "nspins":
-            v = tuple(int(s) for s in v)
-        kwargs[f.name] = v
     try:
+        kwargs = {}
+        for f in dc.fields(cls):
+            if f.name not in dikt:
+                continue
+            v = dikt[f.name]
+            sub = _DATACLASS_FIELDS.get((cls.__name__, f.name))
+            if sub is not None and isinstance(v, dict):
+                v = from_dict(sub, v)
+            elif f.name == "nspins":
+                v = tuple(int(s) for s in v)
+            kwargs[f.name] = v
         return cls(**kwargs)
     except Exception as e:  # same error type as the reference
         raise ValueError(f"Error converting dictionary to {cls.__name__}: {e}")

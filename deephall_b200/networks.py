@@ -100,7 +100,10 @@ class Psiformer:
             node = root
             for p in name.split("/"):
                 node = node[p]
-            arr = torch.as_tensor(np.asarray(node), dtype=torch.float32)
+            if isinstance(node, torch.Tensor):
+                arr = node.detach().to("cpu", torch.float32)
+            else:
+                arr = torch.as_tensor(np.asarray(node), dtype=torch.float32)
             if tuple(arr.shape) != tuple(shape):
                 raise ValueError(f"{name}: expected shape {shape}, got {tuple(arr.shape)}")
             flat[off : off + arr.numel()] = arr.reshape(-1)

@@ -1,0 +1,386 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped facade) with the CPU oracle.
+
+Bars (BASELINE.json north_star): per-walker log psi and E_L within 1e-5 relative in
+fp32 -- reported as a distribution against the fp64 oracle because 1e-5 is the rounding floor
+of the reference's own fp32 arithmetic: median <= 1e-5, batch mean <= 1e-5, and
+the tail bounded; Metropolis decisions bit-exact on identical inputs; integer results exact.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import hamiltonian as OH  # noqa: E402
+from oracle import jets as OJ  # noqa: E402
+from oracle import loss as OLoss  # noqa: E402
+from oracle import mcmc as OM  # noqa: E402
+from oracle import psiformer as OP  # noqa: E402
+
+DEV = "cuda"
+TOL_MEDIAN = 1e-5  # north_star tolerance, fp32
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from deephall_b200 import _native
+
+    _native.load()
+    assert torch.cuda.is_available()
+    return _native
+
+
+def make_plan(nat, cfg, **kw):
+    return nat.Plan(nspins=cfg.nspins, flux=cfg.flux, ndets=cfg.ndets, num_heads=cfg.num_heads, heads_dim=cfg.heads_dim,
+                    num_layers=cfg.num_layers, **kw)
+
+
+def setup_case(nat, kw, B, seed=0, burn=3, **plan_kw):
+    cfg = OP.NetCfg(**kw)
+    p64 = OP.init_params(cfg, seed, torch.float64, 0.1)
+    flat32 = OP.flatten_params(p64).float()
+    p64 = OP.unflatten_params(flat32.double(), cfg)  # the oracle sees exactly the fp32 parameter values
+    plan = make_plan(nat, cfg, **plan_kw)
+    x = plan.init_walkers(B, seed=100 + seed)
+    flat = flat32.to(DEV)
+    if burn:
+        plan.mcmc_sweep(flat, x, burn * 10, 0.2, seed=seed)  # leave the node-dense uniform start
+    return cfg, p64, plan, flat, x
+
+
+def phase_diff(a, b):
+    return (a - b + math.pi) % (2 * math.pi) - math.pi
+
+
+CONFIGS = {
+    "c1": dict(nspins=(3, 0), flux=2),
+    "c2": dict(nspins=(6, 0), flux=15),
+    "c3": dict(nspins=(12, 0), flux=33),
+    "c4": dict(nspins=(10, 0), flux=21),
+    "c5k4": dict(nspins=(16, 0), flux=45, ndets=4),
+    "odd": dict(nspins=(5, 0), flux=11, ndets=3, num_heads=2, heads_dim=48, num_layers=1),
+}
+SIZES = {"c1": 64, "c2": 48, "c3": 24, "c4": 24, "c5k4": 8, "odd": 33}
+
+
+def test_param_layout_is_the_flax_tree(nat):
+    for kw in CONFIGS.values():
+        cfg = OP.NetCfg(**kw)
+        plan = make_plan(nat, cfg)
+        lay = plan.param_layout()
+        shapes = OP.param_shapes(cfg)
+        assert list(lay.keys()) == list(shapes.keys())
+        assert [v[1] for v in lay.values()] == [tuple(s) for s in shapes.values()]
+        assert plan.num_params == OP.num_params(cfg)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_logpsi_parity(nat, name):
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS[name], SIZES[name])
+    lp = plan.logpsi(flat, x).cpu()
+    ref = OP.logpsi(p64, x.double().cpu(), cfg)
+    err_re = (lp.real.double() - ref.real).abs() / ref.real.abs().clamp(min=1.0)
+    err_im = phase_diff(lp.imag.double(), ref.imag).abs()
+    assert err_re.median() < TOL_MEDIAN and err_im.median() < TOL_MEDIAN
+    assert err_re.max() < 2e-4 and err_im.max() < 2e-4, (err_re.max(), err_im.max())
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_local_energy_parity(nat, name):
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS[name], SIZES[name])
+    out = plan.local_energy(flat, x)
+    ref = OJ.local_energy(p64, x.double().cpu(), cfg)
+    e, er = out["energy"].cpu().to(torch.complex128), ref["energy"]
+    rel = (e - er).abs() / er.abs()
+    assert rel.median() < TOL_MEDIAN, rel.median()
+    assert torch.quantile(rel, 0.9) < 1e-4 and rel.max() < 5e-3, (torch.quantile(rel, 0.9), rel.max())
+    assert abs(e.real.mean() - er.real.mean()) / abs(er.real.mean()) < TOL_MEDIAN  # batch-mean energy
+    for k in ("kinetic", "potential", "angular_momentum_z", "angular_momentum_z_square", "angular_momentum_square"):
+        a = out[k].cpu()
+        a = a.to(torch.complex128) if a.is_complex() else a.double()
+        r = (a - ref[k]).abs() / ref[k].abs().clamp(min=1.0)
+        assert r.median() < TOL_MEDIAN, (k, r.median())
+        assert r.max() < 5e-3, (k, r.max())
+    lp = out["logpsi"].cpu()
+    assert (lp.real.double() - ref["logpsi"].real).abs().median() < TOL_MEDIAN
+
+
+def test_local_energy_vs_reference_algorithm_yardstick(nat):
+    """Our fp32 error tail is no worse than that of the reference's own arithmetic run in fp32
+    (grad + Hessian in (theta, phi)), both measured against fp64."""
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c2"], 32)
+    xc = x.cpu()
+    ref64 = OH.batch_local_energy(lambda xx: OP.logpsi(p64, xx, cfg), xc.double(), cfg.Q)["energy"]
+    p32 = OP.cast_params(p64, torch.float32)
+    ref32 = OH.batch_local_energy(lambda xx: OP.logpsi(p32, xx, cfg), xc, cfg.Q)["energy"].to(torch.complex128)
+    ours = plan.local_energy(flat, x)["energy"].cpu().to(torch.complex128)
+    err_ours = ((ours - ref64).abs() / ref64.abs())
+    err_ref32 = ((ref32 - ref64).abs() / ref64.abs())
+    assert err_ours.median() <= max(2 * err_ref32.median().item(), TOL_MEDIAN)
+    assert torch.quantile(err_ours, 0.9) <= max(2 * torch.quantile(err_ref32, 0.9).item(), 2e-5)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_golden_vectors(nat, golden, tag):
+    """Committed fixture made by the fp64 reference-algorithm oracle (tests/golden/make_golden.py)."""
+    c = [int(v) for v in golden[f"{tag}_cfg"]]
+    cfg = OP.NetCfg(nspins=(c[0], c[1]), flux=c[2], ndets=c[3], num_heads=c[4], heads_dim=c[5], num_layers=c[6])
+    plan = make_plan(nat, cfg)
+    flat = torch.tensor(golden[f"{tag}_params"]).to(DEV)
+    x = torch.tensor(golden[f"{tag}_x"]).to(DEV)
+    out = plan.local_energy(flat, x)
+    lp = torch.tensor(golden[f"{tag}_logpsi"])
+    got = out["logpsi"].cpu()
+    assert (got.real.double() - lp.real).abs().max() < 5e-5
+    assert phase_diff(got.imag.double(), lp.imag).abs().max() < 5e-5
+    for k in ("energy", "kinetic", "potential", "angular_momentum_z", "angular_momentum_z_square", "angular_momentum_square"):
+        ref = torch.tensor(golden[f"{tag}_{k}"])
+        a = out[k].cpu()
+        a = a.to(torch.complex128) if a.is_complex() else a.double()
+        r = (a - ref).abs() / ref.abs().clamp(min=1.0)
+        assert r.median() < TOL_MEDIAN and r.max() < 2e-4, (k, r.median(), r.max())
+    g = plan.logpsi_vjp(flat, x, torch.tensor(golden[f"{tag}_cot"]).float().to(DEV)).cpu().double()
+    gref = torch.tensor(golden[f"{tag}_grad"]).double()
+    assert (g - gref).norm() / gref.norm() < 5e-5
+
+
+def test_known_answer_lll_floor(nat):
+    """Constant orbital coefficients -> lowest-Landau-level determinant: KE = N/2; for the filled
+    shell N = 2Q+1 also L^2 = 0 and L_z = 0 (tests/hamiltonian_test.py:65-76 (3,1,0);
+    train_test.py:46-48 energy 1.5)."""
+    for kw, ke in ((dict(nspins=(3, 0), flux=2), 1.5), (dict(nspins=(12, 0), flux=33), 6.0)):
+        cfg = OP.NetCfg(**kw)
+        p = OP.init_params(cfg, 4, torch.float64, 0.3)
+        for k in list(p.keys()):
+            if "DenseGeneral" in k and k.endswith("/kernel"):
+                p[k] = torch.zeros_like(p[k])
+        p["Jastrow_0/ee_par"] = torch.zeros(1, dtype=torch.float64)
+        plan = make_plan(nat, cfg, interaction_strength=0.0)
+        x = plan.init_walkers(64, seed=3)
+        out = plan.local_energy(OP.flatten_params(p).float().to(DEV), x)
+        kin = out["kinetic"].cpu()
+        assert (kin.real - ke).abs().median() < 1e-4 and (kin.real - ke).abs().max() < 5e-3
+        assert (out["energy"].cpu() - kin).abs().max() == 0  # interaction_strength = 0
+        if cfg.nelec == cfg.norb:
+            assert out["angular_momentum_square"].abs().median() < 1e-3
+            assert out["angular_momentum_z"].abs().median() < 1e-4
+
+
+def test_exchange_antisymmetry_full_batch(nat):
+    """Size-independent property at the BASELINE size (c3, 8192 walkers): swapping two electrons
+    leaves log|psi| and E_L unchanged and shifts the phase by pi."""
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c3"], 8192, burn=1)
+    perm = list(range(12))
+    perm[2], perm[7] = perm[7], perm[2]
+    xs = x[:, perm].contiguous()
+    a, b = plan.logpsi(flat, x), plan.logpsi(flat, xs)
+    assert torch.isfinite(a.real).all()
+    assert (a.real - b.real).abs().max() < 2e-3 and (a.real - b.real).abs().median() < 2e-5
+    d = phase_diff(a.imag.double() - b.imag.double(), torch.full_like(a.imag, math.pi, dtype=torch.float64)).abs()
+    assert d.median() < 2e-5
+    ea = plan.local_energy(flat, x[:2048].contiguous())["energy"]
+    eb = plan.local_energy(flat, xs[:2048].contiguous())["energy"]
+    rel = (ea - eb).abs() / ea.abs()
+    assert rel.median() < 2e-5
+
+
+def test_chunking_is_invisible(nat):
+    cfg = OP.NetCfg(**CONFIGS["c2"])
+    flat = OP.flatten_params(OP.init_params(cfg, 0, torch.float64, 0.1)).float().to(DEV)
+    p_big, p_small = make_plan(nat, cfg), make_plan(nat, cfg, chunk_walkers=7)
+    x = p_big.init_walkers(50, seed=9)
+    a, b = p_big.local_energy(flat, x), p_small.local_energy(flat, x)
+    for k in a:
+        assert torch.equal(torch.view_as_real(a[k]) if a[k].is_complex() else a[k],
+                           torch.view_as_real(b[k]) if b[k].is_complex() else b[k]), k
+    assert torch.equal(torch.view_as_real(p_big.logpsi(flat, x)), torch.view_as_real(p_small.logpsi(flat, x)))
+    cot = torch.randn(50, 2, device=DEV)
+    ga, gb = p_big.logpsi_vjp(flat, x, cot), p_small.logpsi_vjp(flat, x, cot)
+    assert (ga - gb).norm() / ga.norm() < 1e-5  # split-K atomics reorder the sum
+    assert p_big.local_energy(flat, x[:0].contiguous())["energy"].numel() == 0  # empty batch
+
+
+def test_potential(nat):
+    for itype in ("coulomb", "harmonic"):
+        cfg = OP.NetCfg(**CONFIGS["c4"])
+        plan = make_plan(nat, cfg, interaction_type=itype)
+        x = plan.init_walkers(257, seed=1)
+        got = plan.potential(x).cpu().double()
+        ref = OH.potential(x.cpu().double(), cfg.Q, math.sqrt(cfg.Q), itype)
+        assert ((got - ref).abs() / ref.abs()).max() < 5e-6
+
+
+def test_slogdet(nat):
+    for n, K in [(1, 1), (3, 1), (6, 2), (12, 4), (16, 16), (32, 2)]:
+        m = torch.randn(40, K, n, n, dtype=torch.complex64, device=DEV)
+        sign, logabs, lpsi = nat.slogdet(m)
+        s_ref, l_ref = torch.linalg.slogdet(m.cpu().to(torch.complex128))
+        assert (logabs.cpu().double() - l_ref).abs().max() < 1e-4
+        assert (sign.cpu().to(torch.complex128) - s_ref).abs().max() < 1e-4
+        mx = l_ref.max(-1, keepdim=True).values
+        ref = torch.log((s_ref * torch.exp(l_ref - mx)).sum(-1)) + mx[..., 0]
+        assert (lpsi.real.cpu().double() - ref.real).abs().max() < 2e-4
+        assert phase_diff(lpsi.imag.cpu().double(), ref.imag).abs().max() < 2e-4
+    sing = torch.ones(2, 1, 4, 4, dtype=torch.complex64, device=DEV)  # singular: jax slogdet -> (0, -inf)
+    sign, logabs, _ = nat.slogdet(sing)
+    assert torch.isinf(logabs).all() and (logabs < 0).all() and (sign.abs() == 0).all()
+
+
+def test_gemm_simt(nat):
+    for (M, N, K, rpg) in [(300, 256, 256, 1), (1000, 408, 256, 4), (77, 9, 256, 3), (129, 768, 256, 32), (1, 256, 4, 1)]:
+        A, W, b = torch.randn(M, K, device=DEV), torch.randn(K, N, device=DEV), torch.randn(N, device=DEV)
+        out = nat.gemm(A, W, b, rpg).cpu().double()
+        ref = A.cpu().double() @ W.cpu().double()
+        ref[::rpg] += b.cpu().double()
+        assert (out - ref).abs().max() / ref.abs().max() < 2e-6
+
+
+# --------------------------------------------------------------------------------- MCMC
+def test_mcmc_proposal_and_decisions(nat):
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c2"], 256, burn=0)
+    N, B, steps = cfg.nelec, 256, 4
+    rnd = OM.draw_randoms(torch.Generator().manual_seed(7), steps, B, N)
+    packed = torch.stack([torch.cat([n_, u_, a_[:, None]], dim=1) for (n_, u_, a_) in rnd]).contiguous().to(DEV)
+    x2 = plan.mcmc_propose(x, 0.1, randoms=packed[0]).cpu()
+    x2_ref = OM.sph_sampling(x.cpu(), rnd[0][0], rnd[0][1], 0.1)
+    assert (x2 - x2_ref).abs().max() < 1e-4
+    assert (x2[..., 0] >= 0).all() and (x2[..., 0] <= math.pi).all() and (x2[..., 1].abs() <= math.pi + 1e-6).all()
+    # accept/select: bit-exact given identical (lp_1, lp_2, u), including NaN -> reject and u = 0 -> accept
+    lp1 = torch.randn(B)
+    lp2 = lp1 + torch.randn(B)
+    lp2[5] = float("nan")
+    u = rnd[0][2].clone()
+    u[6] = 0.0
+    pk = packed[0].clone()
+    pk[:, 2 * N] = u.to(DEV)
+    x1d, lp1d = x.clone(), lp1.to(DEV).clone()
+    nacc = plan.mcmc_accept(x1d, x2.to(DEV), lp1d, lp2.to(DEV), randoms=pk)
+    cond = OM.mh_accept(lp1, lp2, u)
+    assert not cond[5] and cond[6]
+    assert int(nacc.item()) == int(cond.sum())
+    assert torch.equal(lp1d.cpu(), torch.where(cond, lp2, lp1))
+    assert torch.equal(x1d.cpu(), torch.where(cond[:, None, None], x2, x.cpu()))
+    # a whole sweep with injected randoms follows the fp32 oracle chain decision by decision
+    xs = x.clone()
+    nacc, lp = plan.mcmc_sweep(flat, xs, steps, 0.1, randoms=packed, want_lp=True)
+    p32 = OP.cast_params(p64, torch.float32)
+    xr, pm = OM.mcmc_step(lambda xx: OP.logpsi(p32, xx, cfg), x.cpu(), rnd, 0.1)
+    flips = (xs.cpu() - xr).abs().amax((1, 2)).gt(1e-3).sum().item()
+    assert flips <= 2, flips  # a flip needs |lp2 - lp1 - log u| below fp32 noise
+    assert abs(int(nacc.item()) - round(pm * steps * B)) <= 2
+
+
+def test_mcmc_philox_stream(nat):
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c1"], 4096, burn=0)
+    a, b, c = x.clone(), x.clone(), x.clone()
+    na, _ = plan.mcmc_sweep(flat, a, 10, 0.1, seed=11, offset=0)
+    nb, _ = plan.mcmc_sweep(flat, b, 10, 0.1, seed=11, offset=0)
+    nc, _ = plan.mcmc_sweep(flat, c, 10, 0.1, seed=11, offset=1 << 20)
+    assert torch.equal(a, b) and int(na) == int(nb)  # same key -> same chain
+    assert not torch.equal(a, c)
+    pm = int(na) / (10 * 4096)
+    assert 0.3 < pm < 0.98
+    # sharding: walkers [2048:] with subsequence0 = 2048 reproduce the second half of the full run
+    d = x[2048:].clone()
+    plan.mcmc_sweep(flat, d, 10, 0.1, seed=11, offset=0, subsequence0=2048)
+    assert torch.equal(d, a[2048:])
+    # init_guess distribution: cos(theta) and phi uniform (train.py:51-53)
+    w = plan.init_walkers(200000, seed=5).cpu()
+    ct = torch.cos(w[..., 0]).flatten()
+    assert abs(ct.mean()) < 5e-3 and abs(ct.var() - 1 / 3) < 5e-3
+    assert abs(w[..., 1].mean()) < 1e-2 and abs(w[..., 1].var() - math.pi**2 / 3) < 2e-2
+
+
+def test_mcmc_samples_psi_squared(nat):
+    """Filled-LLL N=3 state: <KE> = 1.5 exactly for every walker, and the sampled Coulomb energy of
+    the chain is stationary -- the chain equilibrates to a distribution with E = 1.5 + <V>."""
+    cfg = OP.NetCfg(nspins=(3, 0), flux=2)
+    plan = make_plan(nat, cfg)
+    flat = OP.flatten_params(OP.init_params(cfg, 0, torch.float64)).float().to(DEV)
+    x = plan.init_walkers(4096, seed=2)
+    for it in range(5):
+        plan.mcmc_sweep(flat, x, 20, 0.3, seed=it)
+    e1 = plan.local_energy(flat, x)["energy"].real.mean().item()
+    for it in range(5, 8):
+        plan.mcmc_sweep(flat, x, 20, 0.3, seed=it)
+    e2 = plan.local_energy(flat, x)["energy"].real.mean().item()
+    assert abs(e1 - e2) < 0.08 and 1.5 < e1 < 4.0
+
+
+# --------------------------------------------------------------------------------- gradient + facade
+@pytest.mark.parametrize("name", ["c1", "odd", "c3"])
+def test_vjp_parity(nat, name):
+    B = 12
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS[name], B)
+    cot = torch.randn(B, 2, generator=torch.Generator().manual_seed(1))
+    g = plan.logpsi_vjp(flat, x, cot.to(DEV)).cpu().double()
+    p = OP.flatten_params(p64).clone().requires_grad_(True)
+    lp = OP.logpsi(OP.unflatten_params(p, cfg), x.cpu().double(), cfg)
+    (gref,) = torch.autograd.grad((lp.real * cot[:, 0].double() + lp.imag * cot[:, 1].double()).sum(), p)
+    assert (g - gref).norm() / gref.norm() < 5e-5
+    off = 0
+    for nm, shape in OP.param_shapes(cfg).items():
+        n = int(np.prod(shape))
+        a, b = g[off:off + n], gref[off:off + n]
+        if b.norm() > 1e-6 * gref.norm():
+            assert (a - b).norm() / b.norm() < 5e-4, nm
+        off += n
+
+
+def test_vjp_linearity_full_batch(nat):
+    """Size-independent property at the BASELINE size: the VJP is linear in the cotangent."""
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c3"], 8192, burn=1)
+    c1, c2 = torch.randn(8192, 2, device=DEV) / 8192, torch.randn(8192, 2, device=DEV) / 8192
+    g1, g2 = plan.logpsi_vjp(flat, x, c1), plan.logpsi_vjp(flat, x, c2)
+    g12 = plan.logpsi_vjp(flat, x, (c1 + 2 * c2).contiguous())
+    assert torch.isfinite(g12).all()
+    assert (g12 - (g1 + 2 * g2)).norm() / g12.norm() < 1e-4
+
+
+def test_facade_matches_reference_api(nat):
+    """make_network / model.apply / local_energy / make_mcmc_step / make_loss_fn keep the reference's
+    call shapes (networks/__init__.py:22, hamiltonian.py:175, mcmc.py:105, loss.py:47)."""
+    from deephall_b200 import hamiltonian, loss, mcmc, networks
+    from deephall_b200.config import Config, Network, Optim, PsiformerNetwork, System
+    from deephall_b200.train import VMC
+
+    system = System(flux=6, nspins=(3, 0))
+    net = Network(psiformer=PsiformerNetwork(num_heads=2, heads_dim=16, num_layers=1, determinants=2))
+    model = networks.make_network(system, net)
+    params = model.init(0)
+    tree = model.param_tree(params)
+    assert tree["params"]["PsiformerLayers_0"]["Dense_0"]["kernel"].shape == (4, 32)
+    assert torch.equal(model.from_tree({"params": {k: {kk: vv for kk, vv in v.items()} for k, v in tree["params"].items()}}), params)
+    B = 512
+    data = mcmc.init_guess(0, B, 3, model)
+    one = model.apply(params, data[0])
+    many = model.apply(params, data)
+    assert one.shape == () and many.shape == (B,) and many.dtype == torch.complex64 and torch.equal(one, many[0])
+    e_l = hamiltonian.local_energy(model.apply, system)
+    el, obs = e_l(params, data)
+    assert set(obs) == {"angular_momentum_z", "angular_momentum_z_square", "angular_momentum_square", "potential", "kinetic"}
+    el1, obs1 = e_l(params, data[1])
+    assert el1.shape == () and torch.equal(el1, el[1])
+    step = mcmc.make_mcmc_step(model.apply, B, steps=10)
+    d2, pmove = step(params, data.clone(), mcmc.PhiloxKey(3), 0.1)
+    assert d2.shape == data.shape and 0 < float(pmove) <= 1
+    # loss statistics and gradient vs the oracle on the same walkers (loss.py:66-106)
+    stats, grads = loss.make_loss_fn(model.apply, system)(params, d2)
+    cfg = OP.NetCfg(nspins=(3, 0), flux=6, ndets=2, num_heads=2, heads_dim=16, num_layers=1)
+    p64 = OP.unflatten_params(params.double().cpu(), cfg)
+    el_d, obs_d = e_l(params, d2)
+    o_stats, o_diff = OLoss.loss_stats(el_d.cpu().to(torch.complex128), {k: (v.cpu().to(torch.complex128) if v.is_complex() else v.cpu().double()) for k, v in obs_d.items()})
+    assert abs(complex(stats["energy"]) - complex(o_stats["energy"])) < 1e-5
+    assert abs(float(stats["variance"]) - float(o_stats["variance"])) < 1e-3 * max(1.0, float(o_stats["variance"]))
+    gref = OLoss.energy_grad_vjp(lambda p, xx: OP.logpsi(OP.unflatten_params(p, cfg), xx, cfg), OP.flatten_params(p64), d2.double().cpu(), o_diff)
+    assert (grads.cpu().double() - gref).norm() / gref.norm() < 2e-4
+    # the training sequence runs and lowers nothing catastrophic
+    cfgt = Config(batch_size=256, seed=1, system=System(flux=2, nspins=(3, 0), interaction_strength=0.0), network=net,
+                  optim=Optim(iterations=3, optimizer="adam"))
+    vmc = VMC(cfgt)
+    vmc.burn_in(5)
+    for _ in range(3):
+        pm, st = vmc.step()
+    assert abs(float(st["energy"].real) - 1.5) < 0.2  # train_test.py:46-48: energy hovers around N/2

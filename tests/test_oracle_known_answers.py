@@ -1,0 +1,109 @@
+"""Pins the CPU oracle on every known answer the reference's own tests hold for this path
+(SURVEY 8c): tests/hamiltonian_test.py:42-76, tests/cli_test.py:41-42, tests/train_test.py:46-48."""
+import math
+
+import pytest
+import torch
+
+from oracle import hamiltonian as OH
+from oracle import laughlin as OL
+from oracle import loss as OLoss
+from oracle import mcmc as OM
+from oracle import psiformer as OP
+
+
+def sample(batch, nelec, seed=1898):
+    return OM.init_guess(torch.Generator().manual_seed(seed), batch, nelec, torch.float64)
+
+
+def test_free_electron():
+    # hamiltonian_test.py:42-62: Y_1m Slater determinant, Q=0, r=1 -> KE = 3, L^2 = 0
+    def log_psi(x):
+        th, ph = x[..., 0], x[..., 1]
+        orb = torch.stack([torch.sin(th) * torch.cos(ph), torch.cos(th), torch.sin(th) * torch.sin(ph)], -1).to(torch.complex128)
+        s, l = torch.linalg.slogdet(orb)
+        return l + torch.log(s)
+
+    ke = OH.make_local_kinetic_energy(log_psi, 0, 1.0)
+    for x in sample(2, 3):
+        k, am = ke(x)
+        assert abs(k - 3) < 1e-3
+        assert abs(am["angular_momentum_square"]) < 1e-3
+
+
+def make_lll(nelec, Q):
+    def log_psi(x):
+        u, v = OP.spinors(x)
+        orb = torch.stack([u**m * v ** (2 * Q - m) for m in range(nelec)], -1)
+        s, l = torch.linalg.slogdet(orb)
+        return l + torch.log(s)
+
+    return log_psi
+
+
+@pytest.mark.parametrize("nelec,Q,L_square", [(1, 1, 2), (3, 1, 0), (9, 4, 0)])
+def test_kinetic_and_angular_momentum(nelec, Q, L_square):
+    # hamiltonian_test.py:65-76
+    ke = OH.make_local_kinetic_energy(make_lll(nelec, Q), Q, math.sqrt(Q))
+    for x in sample(2, nelec):
+        k, am = ke(x)
+        assert abs(k - nelec / 2) < 1e-3
+        assert abs(am["angular_momentum_square"] - L_square) < 1e-3
+
+
+def test_laughlin_energy():
+    # cli_test.py:37-42: Laughlin N=3, flux 6, Coulomb -> energy=2.58..., L_square=0.0000
+    flux, N, B = 6, 3, 512
+    gen = torch.Generator().manual_seed(42)
+    x = OM.init_guess(gen, B, N, torch.float64)
+
+    def f(xx):
+        return OL.logpsi(xx, flux)
+
+    for _ in range(30):  # burn-in
+        x, _ = OM.mcmc_step(f, x, OM.draw_randoms(gen, 10, B, N, torch.float64), 0.4)
+    energies, l2s = [], []
+    for _ in range(6):
+        x, pmove = OM.mcmc_step(f, x, OM.draw_randoms(gen, 10, B, N, torch.float64), 0.4)
+        res = OH.batch_local_energy(f, x, flux / 2, chunk=512)
+        stats, _ = OLoss.loss_stats(res["energy"], {k: res[k] for k in ("angular_momentum_square",)})
+        energies.append(stats["energy"].real.item())
+        l2s.append(stats["angular_momentum_square"].item())
+    e = sum(energies) / len(energies)
+    assert abs(e - 2.5866) < 0.02, e  # prints "energy=2.58" in the reference
+    assert abs(sum(l2s) / len(l2s)) < 5e-4
+    assert 0.2 < pmove < 0.9
+
+
+def test_param_counts_match_survey():
+    # closed-form parameter counts of the flax tree
+    expect = {
+        ((3, 0), 2, 1): 796_691,
+        ((6, 0), 15, 1): 841_409,
+        ((12, 0), 33, 1): 1_001_777,
+        ((10, 0), 21, 1): 905_145,
+        ((16, 0), 45, 4): 2_305_281,
+        ((16, 0), 45, 16): 6_844_929,
+    }
+    for (nspins, flux, k), n in expect.items():
+        assert OP.num_params(OP.NetCfg(nspins=nspins, flux=flux, ndets=k)) == n
+
+
+def test_psiformer_antisymmetry_and_lll_floor():
+    cfg = OP.NetCfg(nspins=(6, 0), flux=15, num_heads=2, heads_dim=16)
+    p = OP.init_params(cfg, 3, torch.float64, 0.1)
+    x = sample(3, 6, seed=2)
+    lp = OP.logpsi(p, x, cfg)
+    perm = [1, 0, 2, 3, 4, 5]
+    lp2 = OP.logpsi(p, x[:, perm], cfg)
+    assert torch.allclose(lp.real, lp2.real, atol=1e-10)
+    d = (lp.imag - lp2.imag).abs()
+    assert torch.allclose(torch.minimum(d, 2 * math.pi - d), torch.full_like(d, math.pi), atol=1e-9)
+    # zero orbital kernels + no Jastrow -> constant-coefficient LLL determinant -> KE = N/2 (train_test.py:46-48 floor)
+    for k in list(p.keys()):
+        if "DenseGeneral" in k and k.endswith("/kernel"):
+            p[k] = torch.zeros_like(p[k])
+    p["Jastrow_0/ee_par"] = torch.zeros(1, dtype=torch.float64)
+    res = OH.batch_local_energy(lambda xx: OP.logpsi(p, xx, cfg), x, cfg.Q, interaction_strength=0.0)
+    assert torch.allclose(res["kinetic"].real, torch.full((3,), 3.0, dtype=torch.float64), atol=1e-8)
+    assert res["kinetic"].imag.abs().max() < 1e-8
