@@ -2,6 +2,7 @@
 // sequences of the four hot-path operations.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -56,7 +57,6 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->prep = nullptr;
   p->prep_floats = 0;
   p->prep_src = nullptr;
-  p->gemm_impl = 0;
   p->prof_on = false;
   p->prof_used = 0;
   p->launches = 0;
@@ -91,6 +91,28 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   add_entry(p, ob + "DenseGeneral_1/bias", {L, N, K}, &p->orb_im_b);
   p->ee_par = -1;
   if (cfg->n_up >= 2) add_entry(p, "Jastrow_0/ee_par", {1}, &p->ee_par);
+
+  // prepared-weight slots for the tcgen05 path: [Npad][D] hi | lo, plus fused biases
+  {
+    const char* env = getenv("DH_GEMM_IMPL");
+    p->gemm_impl = (env && std::string(env) == "simt") ? 0 : 1;
+    size_t off = 0;
+    auto slot = [&](int Nout, bool has_bias) {
+      dh_plan::Slot sl;
+      const size_t npad = (size_t)((Nout + 15) & ~15);
+      sl.Nout = Nout;
+      sl.hi = off; off += al(npad * D);
+      sl.lo = off; off += al(npad * D);
+      sl.bias = SIZE_MAX;
+      if (has_bias) { sl.bias = off; off += al((size_t)Nout); }
+      p->slots.push_back(sl);
+    };
+    for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); }
+    slot(2 * p->LNK, true);
+    p->prep_floats = off;
+    cudaError_t e0 = cudaMalloc(&p->prep, off * sizeof(float));
+    if (e0 != cudaSuccess) { delete p; return (int)e0; }
+  }
 
   // sqrt(C(2Q, Q-m)) for m = -Q..Q  (blocks.py:45-46); index a = Q+m -> C(2Q, 2Q-a) = C(2Q, a)
   std::vector<double> nf(L);
@@ -154,21 +176,18 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   { ProfScope ps(p, PC_OTHER, 0, s); if ((rc = features_dense0(x, P + p->off_W0, w.h, Bc, nd, s))) return rc; }
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
-    if ((rc = dense(p, w.h, P + o.q_k, P + o.q_b, w.qkv, rows, D, 3 * D, R, s))) return rc;
-    if ((rc = dense(p, w.h, P + o.k_k, P + o.k_b, w.qkv + D, rows, D, 3 * D, R, s))) return rc;
-    if ((rc = dense(p, w.h, P + o.v_k, P + o.v_b, w.qkv + 2 * D, rows, D, 3 * D, R, s))) return rc;
+    if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s))) return rc;
     { ProfScope ps(p, PC_ATTENTION, 0, s);
       if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, s);
       else rc = attention_value(w.qkv, w.att, Bc, nd, s);
       if (rc) return rc; }
-    if ((rc = dense(p, w.att, P + o.o_k, P + o.o_b, w.t1, rows, D, D, R, s))) return rc;
-    if ((rc = dense(p, w.t1, P + o.d1_k, nullptr, w.t2, rows, D, D, R, s))) return rc;
+    if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
+    if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
     { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s))) return rc; }
-    if ((rc = dense(p, w.h, P + o.d2_k, P + o.d2_b, w.t1, rows, D, D, R, s))) return rc;
+    if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s))) return rc;
     { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc; }
   }
-  if ((rc = dense(p, w.h, P + p->orb_re_k, P + p->orb_re_b, w.cbuf, rows, p->LNK, 2 * (int64_t)p->LNK, R, s))) return rc;
-  if ((rc = dense(p, w.h, P + p->orb_im_k, P + p->orb_im_b, w.cbuf + p->LNK, rows, p->LNK, 2 * (int64_t)p->LNK, R, s))) return rc;
+  if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s))) return rc;
   ProfScope pst(p, PC_TAIL, 0, s, 3);
   if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
   if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;
@@ -183,10 +202,48 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   return finalize(fa, Bc, td, s);
 }
 
+int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
+  if (p->gemm_impl != 1) return 0;
+  const int D = p->D, LNK = p->LNK;
+  int rc;
+  auto cp = [&](size_t dst, int64_t src, size_t n) {
+    return (int)cudaMemcpyAsync(p->prep + dst, P + src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  };
+  for (int l = 0; l < p->nl; ++l) {
+    const LayerOff& o = p->layer[l];
+    const dh_plan::Slot& q = p->slots[l * SL_PER_LAYER + SL_QKV];
+    const int64_t wk[3] = {o.q_k, o.k_k, o.v_k}, wb[3] = {o.q_b, o.k_b, o.v_b};
+    for (int t = 0; t < 3; ++t) {
+      if ((rc = split_weight_tc(P + wk[t], D, D, D, p->prep + q.hi + (size_t)t * D * D, p->prep + q.lo + (size_t)t * D * D, s))) return rc;
+      if ((rc = cp(q.bias + (size_t)t * D, wb[t], D))) return rc;
+    }
+    const dh_plan::Slot& so = p->slots[l * SL_PER_LAYER + SL_O];
+    if ((rc = split_weight_tc(P + o.o_k, D, D, D, p->prep + so.hi, p->prep + so.lo, s))) return rc;
+    if ((rc = cp(so.bias, o.o_b, D))) return rc;
+    const dh_plan::Slot& s1 = p->slots[l * SL_PER_LAYER + SL_D1];
+    if ((rc = split_weight_tc(P + o.d1_k, D, D, D, p->prep + s1.hi, p->prep + s1.lo, s))) return rc;
+    const dh_plan::Slot& s2 = p->slots[l * SL_PER_LAYER + SL_D2];
+    if ((rc = split_weight_tc(P + o.d2_k, D, D, D, p->prep + s2.hi, p->prep + s2.lo, s))) return rc;
+    if ((rc = cp(s2.bias, o.d2_b, D))) return rc;
+  }
+  const dh_plan::Slot& sb = p->slots[p->nl * SL_PER_LAYER];
+  // rows [0, LNK) = real part, rows [LNK, 2 LNK) = imaginary part; the pad rows of the slot stay zero
+  DH_CHECK(cudaMemsetAsync(p->prep + sb.hi, 0, (size_t)((2 * LNK + 15) & ~15) * D * sizeof(float), s));
+  DH_CHECK(cudaMemsetAsync(p->prep + sb.lo, 0, (size_t)((2 * LNK + 15) & ~15) * D * sizeof(float), s));
+  if ((rc = split_weight_tc_rows(P + p->orb_re_k, LNK, D, LNK, p->prep + sb.hi, p->prep + sb.lo, s))) return rc;
+  if ((rc = split_weight_tc_rows(P + p->orb_im_k, LNK, D, LNK, p->prep + sb.hi + (size_t)LNK * D, p->prep + sb.lo + (size_t)LNK * D, s))) return rc;
+  if ((rc = cp(sb.bias, p->orb_re_b, LNK))) return rc;
+  if ((rc = cp(sb.bias + LNK, p->orb_im_b, LNK))) return rc;
+  p->launches += 4 * p->nl * 2 + 2;
+  return 0;
+}
+
 static int run_forward(dh_plan* p, const float* params, const float* x, int64_t B, bool jets, float* out_el,
                        float* out_kin, float* out_pot, float* out_lz, float* out_lz2, float* out_l2,
                        float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s) {
-  if (!p || !params || !x || B < 0) return DH_E_BADARG;
+  if (!p || B < 0) return DH_E_BADARG;
+  if (B == 0) return 0;
+  if (!params || !x) return DH_E_BADARG;
   if (B == 0) return 0;
   const int64_t chunk = pick_chunk(p, jets, B);
   float* base = align_ws(ws);
@@ -211,7 +268,8 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
 
 extern "C" int dh_logpsi(dh_plan* p, const float* params, const float* x, int64_t B, float* out_logpsi,
                          void* ws, size_t ws_bytes, void* stream) {
-  if (!out_logpsi) return DH_E_BADARG;
+  if (!out_logpsi && B > 0) return DH_E_BADARG;
+  if (p && params && B > 0) { int rc = prepare_weights(p, params, (cudaStream_t)stream); if (rc) return rc; }
   return run_forward(p, params, x, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_logpsi, ws,
                      ws_bytes, (cudaStream_t)stream);
 }
@@ -219,6 +277,7 @@ extern "C" int dh_logpsi(dh_plan* p, const float* params, const float* x, int64_
 extern "C" int dh_local_energy(dh_plan* p, const float* params, const float* x, int64_t B, float* out_el,
                                float* out_kinetic, float* out_potential, float* out_lz, float* out_lz2,
                                float* out_l2, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
+  if (p && params && B > 0) { int rc = prepare_weights(p, params, (cudaStream_t)stream); if (rc) return rc; }
   return run_forward(p, params, x, B, true, out_el, out_kinetic, out_potential, out_lz, out_lz2, out_l2,
                      out_logpsi, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -270,13 +329,18 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
   int rc;
   DH_CHECK(cudaMemsetAsync(out_naccept, 0, sizeof(long long), s));
   // mcmc.py:142 -- log-probability of the incoming configurations
-  if ((rc = dh_logpsi(p, params, x, B, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
+  if ((rc = prepare_weights(p, params, s))) return rc;
+  if ((rc = run_forward(p, params, x, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase,
+                        fwd_bytes, s)))
+    return rc;
   if ((rc = lp_from_logpsi(mw.logpsi2, mw.lp1, B, s))) return rc;
   const int64_t rstride = B * (2 * (int64_t)p->N + 1);
   for (int st = 0; st < steps; ++st) {
     const float* rnd = randoms ? randoms + st * rstride : nullptr;
     { ProfScope ps(p, PC_MCMC, 0, s); if ((rc = mcmc_propose(x, mw.x2, B, p->N, width, seed, offset + st, subsequence0, rnd, s))) return rc; }
-    if ((rc = dh_logpsi(p, params, mw.x2, B, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
+    if ((rc = run_forward(p, params, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2,
+                          fbase, fwd_bytes, s)))
+      return rc;
     { ProfScope ps(p, PC_MCMC, 0, s);
       if ((rc = mcmc_accept(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, seed, offset + st, subsequence0, rnd,
                             reinterpret_cast<unsigned long long*>(out_naccept), s)))
@@ -301,9 +365,10 @@ extern "C" int dh_gemm(const float* A, const float* W, const float* bias, float*
   if (!gemm_tc_supported(N, K)) return DH_E_UNSUPPORTED;
   // test/bench entry point: the split weights are made on the fly (the plan ops keep them cached)
   float* wt = nullptr;
-  DH_CHECK(cudaMalloc(&wt, 2 * (size_t)N * K * sizeof(float)));
-  int rc = split_weight_tc(W, N, K, N, wt, wt + (size_t)N * K, s);
-  if (!rc) rc = gemm_tc(A, wt, wt + (size_t)N * K, bias, C, M, N, K, N, rows_per_group, accumulate, s);
+  const size_t npad = (size_t)((N + 15) & ~15);
+  DH_CHECK(cudaMalloc(&wt, 2 * npad * K * sizeof(float)));
+  int rc = split_weight_tc(W, N, K, N, wt, wt + npad * K, s);
+  if (!rc) rc = gemm_tc(A, wt, wt + npad * K, bias, C, M, N, K, N, rows_per_group, accumulate, s);
   cudaStreamSynchronize(s);
   cudaFree(wt);
   return rc;

@@ -71,7 +71,7 @@ size_t vjp_ws_floats(const dh_plan* p, int64_t Bc) { return carve_vjp(p, nullptr
 
 extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot,
                              float* grad, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
-  if (!p || !P || !x || !cot || !grad || B < 0) return DH_E_BADARG;
+  if (!p || !P || !grad || B < 0 || (B > 0 && (!x || !cot))) return DH_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
   if (B == 0) return 0;
@@ -83,6 +83,7 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
   NetDims nd{N, 1, D, p->H, p->hd, p->cfg.n_up};
   TailDims td{N, 1, p->L, p->K, p->twoQ, p->cfg.n_up};
   int rc;
+  if ((rc = prepare_weights(p, P, s))) return rc;
 #define RUN(cat, call)                          \
   do {                                          \
     ProfScope _ps(p, cat, 0, s);                \
@@ -98,19 +99,16 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
     RUN(PC_OTHER, features_dense0(xc, P + p->off_W0, w.hs[0], Bc, nd, s));
     for (int l = 0; l < nl; ++l) {
       const LayerOff& o = p->layer[l];
-      if ((rc = dense(p, w.hs[l], P + o.q_k, P + o.q_b, w.qkv[l], rows, D, 3 * D, 1, s))) return rc;
-      if ((rc = dense(p, w.hs[l], P + o.k_k, P + o.k_b, w.qkv[l] + D, rows, D, 3 * D, 1, s))) return rc;
-      if ((rc = dense(p, w.hs[l], P + o.v_k, P + o.v_b, w.qkv[l] + 2 * D, rows, D, 3 * D, 1, s))) return rc;
+      if ((rc = dense_qkv(p, P, l, w.hs[l], w.qkv[l], rows, 1, s))) return rc;
       RUN(PC_ATTENTION, attention_value(w.qkv[l], w.att[l], Bc, nd, s));
-      if ((rc = dense(p, w.att[l], P + o.o_k, P + o.o_b, w.t1[l], rows, D, D, 1, s))) return rc;
-      if ((rc = dense(p, w.t1[l], P + o.d1_k, nullptr, w.t2[l], rows, D, D, 1, s))) return rc;
+      if ((rc = dense_layer(p, P, l, SL_O, w.att[l], w.t1[l], rows, 1, s))) return rc;
+      if ((rc = dense_layer(p, P, l, SL_D1, w.t1[l], w.t2[l], rows, 1, s))) return rc;
       RUN(PC_LAYERNORM, residual_layernorm(w.hs[l], w.t2[l], P + o.ln0_s, P + o.ln0_b, w.hA[l], Bc, nd, 0, s));
-      if ((rc = dense(p, w.hA[l], P + o.d2_k, P + o.d2_b, w.z[l], rows, D, D, 1, s))) return rc;
+      if ((rc = dense_layer(p, P, l, SL_D2, w.hA[l], w.z[l], rows, 1, s))) return rc;
       RUN(PC_LAYERNORM, residual_layernorm(w.hA[l], w.z[l], P + o.ln1_s, P + o.ln1_b, w.hs[l + 1], Bc, nd, 1, s));
     }
     const float* hf = w.hs[nl];
-    if ((rc = dense(p, hf, P + p->orb_re_k, P + p->orb_re_b, w.cbuf, rows, LNK, 2 * (int64_t)LNK, 1, s))) return rc;
-    if ((rc = dense(p, hf, P + p->orb_im_k, P + p->orb_im_b, w.cbuf + LNK, rows, LNK, 2 * (int64_t)LNK, 1, s))) return rc;
+    if ((rc = dense_orb(p, P, hf, w.cbuf, rows, 1, s))) return rc;
     RUN(PC_TAIL, orbital_contract(w.cbuf, xc, p->d_normfac, w.Mj, Bc, td, s));
     RUN(PC_TAIL, logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s));
     if (out_logpsi) {

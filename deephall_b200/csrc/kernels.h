@@ -15,6 +15,7 @@ int gemm_tc_supported(int N, int K);
 int gemm_tc(const float* A, const float* Wt_hi, const float* Wt_lo, const float* bias, float* C, int64_t M,
             int N, int K, int64_t ldc, int rpg, int accumulate, cudaStream_t stream);
 int split_weight_tc(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
+int split_weight_tc_rows(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
 
 // ---- net_kernels.cu
 struct NetDims {

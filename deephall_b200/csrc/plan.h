@@ -29,6 +29,8 @@ struct dh_plan {
   float* prep;            // device buffer owned by the plan
   size_t prep_floats;
   const float* prep_src;  // params pointer the preparation was made from
+  struct Slot { int Nout; size_t hi, lo, bias; };  // float offsets into prep (bias: SIZE_MAX = none)
+  std::vector<Slot> slots;  // per layer: qkv, o, d1, d2 ; last: orbitals (re | im)
   // ---- instrumentation (dh_profile_*): CUDA-event timing of kernel categories, launch count
   bool prof_on;
   std::vector<cudaEvent_t> prof_ev;   // pool, pairs (start, stop)
@@ -112,10 +114,52 @@ static inline float* align_ws(void* ws) {
 }
 
 // --------------------------------------------------------------------------------- forward
-// C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
+enum { SL_QKV = 0, SL_O = 1, SL_D1 = 2, SL_D2 = 3, SL_PER_LAYER = 4 };
+
+// tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows)
+static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C, int64_t rows, int64_t ldc, int R,
+                           cudaStream_t s) {
+  const dh_plan::Slot& sl = p->slots[slot];
+  ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * sl.Nout * p->D, s);
+  return gemm_tc(A, p->prep + sl.hi, p->prep + sl.lo, sl.bias == SIZE_MAX ? nullptr : p->prep + sl.bias, C, rows,
+                 sl.Nout, p->D, ldc, R, 0, s);
+}
+
+// SIMT path: C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
 static inline int dense(const dh_plan* p, const float* A, const float* W, const float* bias, float* C, int64_t rows,
                  int Nout, int64_t ldc, int R, cudaStream_t s) {
   ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * Nout * p->D, s);
   return gemm_simt(A, W, bias, C, rows, Nout, p->D, p->D, 1, Nout, 1, ldc, R, 0, 1, s);
 }
 
+
+// The five dense contractions of the network, on whichever implementation the plan selected.
+static inline int dense_qkv(const dh_plan* p, const float* P, int l, const float* A, float* qkv, int64_t rows, int R,
+                            cudaStream_t s) {
+  const int D = p->D;
+  if (p->gemm_impl == 1) return dense_tc(p, A, l * SL_PER_LAYER + SL_QKV, qkv, rows, 3 * D, R, s);
+  const LayerOff& o = p->layer[l];
+  int rc;
+  if ((rc = dense(p, A, P + o.q_k, P + o.q_b, qkv, rows, D, 3 * D, R, s))) return rc;
+  if ((rc = dense(p, A, P + o.k_k, P + o.k_b, qkv + D, rows, D, 3 * D, R, s))) return rc;
+  return dense(p, A, P + o.v_k, P + o.v_b, qkv + 2 * D, rows, D, 3 * D, R, s);
+}
+static inline int dense_layer(const dh_plan* p, const float* P, int l, int which, const float* A, float* C,
+                              int64_t rows, int R, cudaStream_t s) {
+  const int D = p->D;
+  if (p->gemm_impl == 1) return dense_tc(p, A, l * SL_PER_LAYER + which, C, rows, D, R, s);
+  const LayerOff& o = p->layer[l];
+  if (which == SL_O) return dense(p, A, P + o.o_k, P + o.o_b, C, rows, D, D, R, s);
+  if (which == SL_D1) return dense(p, A, P + o.d1_k, nullptr, C, rows, D, D, R, s);
+  return dense(p, A, P + o.d2_k, P + o.d2_b, C, rows, D, D, R, s);
+}
+static inline int dense_orb(const dh_plan* p, const float* P, const float* A, float* cbuf, int64_t rows, int R,
+                            cudaStream_t s) {
+  const int LNK = p->LNK;
+  if (p->gemm_impl == 1) return dense_tc(p, A, p->nl * SL_PER_LAYER, cbuf, rows, 2 * (int64_t)LNK, R, s);
+  int rc;
+  if ((rc = dense(p, A, P + p->orb_re_k, P + p->orb_re_b, cbuf, rows, LNK, 2 * (int64_t)LNK, R, s))) return rc;
+  return dense(p, A, P + p->orb_im_k, P + p->orb_im_b, cbuf + LNK, rows, LNK, 2 * (int64_t)LNK, R, s);
+}
+
+int prepare_weights(dh_plan* p, const float* P, cudaStream_t s);  // api.cu

@@ -146,6 +146,7 @@ __device__ void warp_gauss_jordan(cplx* A, int n, int ncols, int ld, float& loga
   const int lane = threadIdx.x & 31;
   float la = 0.f;
   cplx ph = cmake(1.f, 0.f);
+  bool singular = false;
   for (int p = 0; p < n; ++p) {
     // pivot search over rows p..n-1 of column p
     float best = -1.f;
@@ -172,6 +173,7 @@ __device__ void warp_gauss_jordan(cplx* A, int n, int ncols, int ld, float& loga
     const cplx d = A[p * ld + p];
     const float ad = hypotf(d.x, d.y);
     la += logf(ad);
+    if (ad == 0.f && !isnan(la)) singular = true;  // first exact-zero pivot: jax slogdet returns (0, -inf)
     ph = ad > 0.f ? cmul(ph, cmake(d.x / ad, d.y / ad)) : cmake(0.f, 0.f);
     const cplx dinv = cinv(d);
     __syncwarp();
@@ -192,6 +194,7 @@ __device__ void warp_gauss_jordan(cplx* A, int n, int ncols, int ld, float& loga
   // renormalise the phase (product of n unit numbers drifts by O(n eps))
   const float pn = hypotf(ph.x, ph.y);
   if (pn > 0.f) ph = cmake(ph.x / pn, ph.y / pn);
+  if (singular) { la = -INFINITY; ph = cmake(0.f, 0.f); }
   logabs = la;
   phase = ph;
 }
