@@ -1,0 +1,310 @@
+// Self-attention on forward-Laplacian jets (flax MultiHeadAttention semantics, networks/psiformer.py:44).
+// One block of 256 threads per (head, walker).  Rows per electron: R = 2N + 8 (common.cuh).
+//
+// Phase 1  score jets  s_ij^(r) = scale * sum_d [ q_i^(r) k_j^(0) + q_i^(0) k_j^(r) (+ 2 q_i^(r) k_j^(r) cross terms) ]
+//          register-tiled: one thread owns (row r, 3 queries, 6 keys) = 54 accumulators; q and k are
+//          staged 16 head-dim columns at a time in padded shared memory (conflict-free float4 reads).
+// Phase 2  softmax jets (log-sum-exp Hessian = diag(p) - p p^T) in shared memory.
+// Phase 3  output jets o_i^(r) = sum_j [ p^(r) v^(0) + p^(0) v^(r) (+ cross terms) ]
+//          one thread owns (row r, 4 head-dim columns, 6 queries); the S-row cross term
+//          2 sum_{j,k} p^(Jk) v^(Jk) is computed by warps whose lanes run over k and warp-reduced.
+#include "kernels.h"
+
+namespace dh {
+
+constexpr int AJ_THREADS = 256;
+constexpr int AJ_CH = 16;      // head-dim chunk staged in shared memory
+constexpr int AJ_STRIDE = 20;  // padded row stride of a staged chunk
+constexpr int AJ_IB = 3, AJ_JB = 6, AJ_OB = 6;
+
+__host__ __device__ inline int aj_np(int N) { return (N + AJ_OB - 1) / AJ_OB * AJ_OB; }  // padded query count
+__host__ __device__ inline size_t aj_smem_floats(int N, int R) {
+  const int NP = aj_np(N);
+  // qs, ks : [N*R][STRIDE] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [NP][CH]
+  return 2 * (size_t)N * R * AJ_STRIDE + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + (size_t)NP * AJ_CH;
+}
+size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R) * sizeof(float); }
+
+__device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict__ src, int64_t ld, int NR, int ch, int hd) {
+  for (int t = threadIdx.x; t < NR * 4; t += AJ_THREADS) {
+    const int row = t >> 2, f4 = t & 3;
+    const int dcol = ch * AJ_CH + f4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* pp = src + row * ld + dcol;
+    if (dcol + 3 < hd) v = *reinterpret_cast<const float4*>(pp);
+    else {
+      if (dcol < hd) v.x = pp[0];
+      if (dcol + 1 < hd) v.y = pp[1];
+      if (dcol + 2 < hd) v.z = pp[2];
+    }
+    *reinterpret_cast<float4*>(dst + row * AJ_STRIDE + f4 * 4) = v;
+  }
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+__device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
+  acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
+  acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+}
+
+__global__ void __launch_bounds__(AJ_THREADS, 2)
+attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
+  extern __shared__ __align__(16) float smem[];
+  const int N = dm.N, R = dm.R, D = dm.D, hd = dm.hd;
+  const int NP = aj_np(N);
+  const int hh = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NR = N * R;
+  Rows rw(N, true);
+  float* qs = smem;
+  float* ks = qs + (size_t)NR * AJ_STRIDE;
+  float* sj = ks + (size_t)NR * AJ_STRIDE;  // SJ(i,j,r)
+  float* cr = sj + (size_t)N * R * NP;
+  float* p0 = cr + (size_t)N * R * NP;      // [j][NP] (query index fastest)
+  float* qq = p0 + N * NP;
+  float* dd = qq + N * NP;                  // [3][j][NP]
+  float* xs = p0 + ((5 * N * NP + 3) & ~3);  // [NP][CH] S-row cross term of the current chunk (16-byte aligned)
+#define SJ(i, j, r) (((j) * R + (r)) * NP + (i))
+  const int64_t ld = 3 * (int64_t)D;
+  const float* qbase = qkv + b * NR * ld + hh * hd;
+  const float* kbase = qbase + D;
+  const float* vbase = qbase + 2 * D;
+  const float scl = rsqrtf((float)hd);
+  const int nchunk = (hd + AJ_CH - 1) / AJ_CH;
+  const int IBN = (N + AJ_IB - 1) / AJ_IB, JBN = (N + AJ_JB - 1) / AJ_JB, OBN = NP / AJ_OB;
+
+  // zero the padded query slots so that vectorised reads of sj never see garbage
+  for (int t = tid; t < 2 * N * R * NP; t += AJ_THREADS) sj[t] = 0.f;  // sj and cr are contiguous
+
+  // ------------------------------------------------------------------ phase 1: score jets
+  const int items1 = R * IBN * JBN;
+  for (int it0 = 0; it0 < items1; it0 += AJ_THREADS) {
+    const int item = it0 + tid;
+    const bool active = item < items1;
+    const int r = active ? item % R : 0;
+    const int ib = active ? (item / R) % IBN : 0;
+    const int jb = active ? item / (R * IBN) : 0;
+    const int i0 = ib * AJ_IB, j0 = jb * AJ_JB;
+    float acc[AJ_IB][AJ_JB][3];
+#pragma unroll
+    for (int a = 0; a < AJ_IB; ++a)
+#pragma unroll
+      for (int c = 0; c < AJ_JB; ++c) { acc[a][c][0] = 0.f; acc[a][c][1] = 0.f; acc[a][c][2] = 0.f; }
+    for (int ch = 0; ch < nchunk; ++ch) {
+      __syncthreads();
+      stage_chunk(qs, qbase, ld, NR, ch, hd);
+      stage_chunk(ks, kbase, ld, NR, ch, hd);
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int f = 0; f < AJ_CH; f += 4) {
+          float4 qr[AJ_IB], q0[AJ_IB];
+#pragma unroll
+          for (int a = 0; a < AJ_IB; ++a) {
+            const int i = min(i0 + a, N - 1);
+            qr[a] = *reinterpret_cast<const float4*>(qs + (i * R + r) * AJ_STRIDE + f);
+            q0[a] = *reinterpret_cast<const float4*>(qs + (i * R) * AJ_STRIDE + f);
+          }
+#pragma unroll
+          for (int c = 0; c < AJ_JB; ++c) {
+            const int j = min(j0 + c, N - 1);
+            const float4 kr = *reinterpret_cast<const float4*>(ks + (j * R + r) * AJ_STRIDE + f);
+            const float4 k0 = *reinterpret_cast<const float4*>(ks + (j * R) * AJ_STRIDE + f);
+#pragma unroll
+            for (int a = 0; a < AJ_IB; ++a) {
+              acc[a][c][0] = dot4(qr[a], k0, acc[a][c][0]);
+              acc[a][c][1] = dot4(q0[a], kr, acc[a][c][1]);
+              acc[a][c][2] = dot4(qr[a], kr, acc[a][c][2]);
+            }
+          }
+        }
+      }
+    }
+    if (active) {
+#pragma unroll
+      for (int a = 0; a < AJ_IB; ++a)
+#pragma unroll
+        for (int c = 0; c < AJ_JB; ++c) {
+          const int i = i0 + a, j = j0 + c;
+          if (i < N && j < N) {
+            sj[SJ(i, j, r)] = (r == 0) ? acc[a][c][2] * scl : (acc[a][c][0] + acc[a][c][1]) * scl;
+            cr[SJ(i, j, r)] = acc[a][c][2] * scl;
+          }
+        }
+    }
+  }
+  __syncthreads();
+  // second-order rows pick up the cross products: S += 2 sum_k qJk.kJk ; T_a += 2 qDa.kDa
+  for (int t = tid; t < N * N * 4; t += AJ_THREADS) {
+    const int w = t & 3, ij = t >> 2;
+    const int i = ij % N, j = ij / N;
+    if (w == 0) {
+      float s2 = 0.f;
+      for (int k = 0; k < 2 * N; ++k) s2 += cr[SJ(i, j, rw.J(k))];
+      sj[SJ(i, j, rw.S())] += 2.f * s2;
+    } else {
+      sj[SJ(i, j, rw.T(w - 1))] += 2.f * cr[SJ(i, j, rw.D(w - 1))];
+    }
+  }
+  __syncthreads();
+  // ------------------------------------------------------------------ phase 2: softmax jets
+  for (int i = tid; i < N; i += AJ_THREADS) {
+    float mx = -INFINITY;
+    for (int j = 0; j < N; ++j) mx = fmaxf(mx, sj[SJ(i, j, 0)]);
+    float Z = 0.f;
+    for (int j = 0; j < N; ++j) { const float e = expf(sj[SJ(i, j, 0)] - mx); p0[j * NP + i] = e; Z += e; }
+    const float iz = 1.f / Z;
+    for (int j = 0; j < N; ++j) p0[j * NP + i] *= iz;
+  }
+  __syncthreads();
+  const int nfirst = 2 * N + 3;
+  for (int t = tid; t < N * nfirst; t += AJ_THREADS) {  // first-order rows: l = s - lse
+    const int i = t % N, q = t / N;
+    const int r = q < 2 * N ? rw.J(q) : rw.D(q - 2 * N);
+    float lse = 0.f;
+    for (int j = 0; j < N; ++j) lse = fmaf(p0[j * NP + i], sj[SJ(i, j, r)], lse);
+    for (int j = 0; j < N; ++j) sj[SJ(i, j, r)] -= lse;
+  }
+  __syncthreads();
+  for (int t = tid; t < N * N; t += AJ_THREADS) {
+    const int i = t % N, j = t / N;
+    float s2 = 0.f;
+    for (int k = 0; k < 2 * N; ++k) { const float l = sj[SJ(i, j, rw.J(k))]; s2 = fmaf(l, l, s2); }
+    qq[j * NP + i] = s2;
+    for (int a3 = 0; a3 < 3; ++a3) { const float l = sj[SJ(i, j, rw.D(a3))]; dd[(a3 * N + j) * NP + i] = l * l; }
+  }
+  __syncthreads();
+  for (int t = tid; t < N * 4; t += AJ_THREADS) {  // second-order rows
+    const int i = t % N, w = t / N;
+    const int r = w == 0 ? rw.S() : rw.T(w - 1);
+    const float* extra = w == 0 ? qq : dd + (w - 1) * N * NP;
+    float lse = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float v = sj[SJ(i, j, r)] + extra[j * NP + i];
+      sj[SJ(i, j, r)] = v;
+      lse = fmaf(p0[j * NP + i], v, lse);
+    }
+    for (int j = 0; j < N; ++j) sj[SJ(i, j, r)] -= lse;
+  }
+  __syncthreads();
+  for (int t = tid; t < N * R * N; t += AJ_THREADS) {  // l -> p jets
+    const int i = t % N, jr = t / N;
+    const int r = jr % R, j = jr / R;
+    const float pv = p0[j * NP + i];
+    sj[SJ(i, j, r)] = r == 0 ? pv : pv * sj[SJ(i, j, r)];
+  }
+  // ------------------------------------------------------------------ phase 3: o = P V jets
+  float* obase = o + b * NR * (int64_t)D + hh * hd;
+  float* vs = qs;  // staged v chunk
+  const int rS = rw.S(), rT0 = rw.T(0), rD0 = rw.D(0);
+  for (int ch = 0; ch < nchunk; ++ch) {
+    __syncthreads();
+    stage_chunk(vs, vbase, ld, NR, ch, hd);
+    __syncthreads();
+    // ---- S-row cross term: xs[i][c] = 2 sum_j sum_k p_ij^(Jk) v_j^(Jk)[c] ; warp = (query block, float4), lanes = k
+    for (int wi = warp; wi < OBN * 4; wi += AJ_THREADS / 32) {
+      const int ob = wi >> 2, f4 = wi & 3;
+      float4 acc[AJ_OB];
+#pragma unroll
+      for (int a = 0; a < AJ_OB; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kk = lane; kk < 2 * N; kk += 32) {
+        const int r = rw.J(kk);
+        for (int j = 0; j < N; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(vs + (j * R + r) * AJ_STRIDE + f4 * 4);
+          const float2* pp = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
+          const float2 pa = pp[0], pb = pp[1], pc = pp[2];
+          axpy4(acc[0], pa.x, v); axpy4(acc[1], pa.y, v);
+          axpy4(acc[2], pb.x, v); axpy4(acc[3], pb.y, v);
+          axpy4(acc[4], pc.x, v); axpy4(acc[5], pc.y, v);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < AJ_OB; ++a) {
+        acc[a].x = warp_sum(acc[a].x); acc[a].y = warp_sum(acc[a].y);
+        acc[a].z = warp_sum(acc[a].z); acc[a].w = warp_sum(acc[a].w);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < AJ_OB; ++a)
+          *reinterpret_cast<float4*>(xs + (ob * AJ_OB + a) * AJ_CH + f4 * 4) =
+              make_float4(2.f * acc[a].x, 2.f * acc[a].y, 2.f * acc[a].z, 2.f * acc[a].w);
+      }
+    }
+    __syncthreads();
+    // ---- all rows: thread = (f4, r, query block)
+    for (int t = tid; t < R * 4 * OBN; t += AJ_THREADS) {
+      const int f4 = t & 3, r = (t >> 2) % R, ob = (t >> 2) / R;
+      float4 acc[AJ_OB];
+#pragma unroll
+      for (int a = 0; a < AJ_OB; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool isT = r >= rT0;
+      const int rd = isT ? rD0 + (r - rT0) : 0;
+      for (int j = 0; j < N; ++j) {
+        const float4 v0 = *reinterpret_cast<const float4*>(vs + (j * R) * AJ_STRIDE + f4 * 4);
+        const float2* pr = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
+        const float2 a0 = pr[0], a1 = pr[1], a2 = pr[2];
+        axpy4(acc[0], a0.x, v0); axpy4(acc[1], a0.y, v0);
+        axpy4(acc[2], a1.x, v0); axpy4(acc[3], a1.y, v0);
+        axpy4(acc[4], a2.x, v0); axpy4(acc[5], a2.y, v0);
+        if (r != 0) {
+          const float4 vr = *reinterpret_cast<const float4*>(vs + (j * R + r) * AJ_STRIDE + f4 * 4);
+          const float2* pz = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, 0));
+          const float2 b0 = pz[0], b1 = pz[1], b2 = pz[2];
+          axpy4(acc[0], b0.x, vr); axpy4(acc[1], b0.y, vr);
+          axpy4(acc[2], b1.x, vr); axpy4(acc[3], b1.y, vr);
+          axpy4(acc[4], b2.x, vr); axpy4(acc[5], b2.y, vr);
+          if (isT) {
+            const float4 vd = *reinterpret_cast<const float4*>(vs + (j * R + rd) * AJ_STRIDE + f4 * 4);
+            const float2* pd = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, rd));
+            const float2 c0 = pd[0], c1 = pd[1], c2 = pd[2];
+            axpy4(acc[0], 2.f * c0.x, vd); axpy4(acc[1], 2.f * c0.y, vd);
+            axpy4(acc[2], 2.f * c1.x, vd); axpy4(acc[3], 2.f * c1.y, vd);
+            axpy4(acc[4], 2.f * c2.x, vd); axpy4(acc[5], 2.f * c2.y, vd);
+          }
+        }
+      }
+      const int dcol = ch * AJ_CH + f4 * 4;
+#pragma unroll
+      for (int a = 0; a < AJ_OB; ++a) {
+        const int i = ob * AJ_OB + a;
+        if (i < N) {
+          float4 out = acc[a];
+          if (r == rS) {
+            const float4 x4 = *reinterpret_cast<const float4*>(xs + i * AJ_CH + f4 * 4);
+            out.x += x4.x; out.y += x4.y; out.z += x4.z; out.w += x4.w;
+          }
+          float* dst = obase + (int64_t)(i * R + r) * D + dcol;
+          if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = out;
+          else {
+            if (dcol < hd) dst[0] = out.x;
+            if (dcol + 1 < hd) dst[1] = out.y;
+            if (dcol + 2 < hd) dst[2] = out.z;
+          }
+        }
+      }
+    }
+  }
+#undef SJ
+}
+
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
+  if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
+  const size_t smem = attention_jets_smem(d);
+  if (smem > 227 * 1024) return -2;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_smem = smem;
+  }
+  dim3 grid((unsigned)d.H, (unsigned)B);
+  attention_jets_kernel<<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dh

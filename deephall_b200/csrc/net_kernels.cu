@@ -298,255 +298,5 @@ int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream
   return (int)cudaGetLastError();
 }
 
-// =============================================================================================
-// jet attention: one block per (head, walker).
-// =============================================================================================
-constexpr int AJ_THREADS = 256;
-constexpr int AJ_CH = 16;       // head-dim chunk staged in shared memory
-constexpr int AJ_STRIDE = 20;   // padded row stride of the staged chunk (bank-conflict-free float4)
-
-struct AJSmem {
-  float* qs;   // [N*R][AJ_STRIDE]     staged q (phase 1) / v (phase 2) chunk
-  float* sj;   // [N][N][R]            score -> log-softmax -> probability jets
-  float* cr;   // [N][N][R]            q_r . k_r cross products
-  float* p0;   // [N][N]
-  float* qq;   // [N][N]               sum_k l_Jk^2
-  float* dd;   // [3][N][N]            l_Da^2
-};
-__host__ __device__ inline size_t aj_smem_floats(int N, int R) {
-  return (size_t)N * R * AJ_STRIDE + 2 * (size_t)N * N * R + 5 * (size_t)N * N;
-}
-size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R) * sizeof(float); }
-
-template <int NMAX>
-__global__ void __launch_bounds__(AJ_THREADS)
-attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
-  extern __shared__ __align__(16) float smem[];
-  const int N = dm.N, R = dm.R, D = dm.D, hd = dm.hd;
-  const int hh = blockIdx.x;
-  const int64_t b = blockIdx.y;
-  const int tid = threadIdx.x;
-  const int NR = N * R;
-  Rows rw(N, true);
-  AJSmem S;
-  S.qs = smem;
-  S.sj = S.qs + (size_t)NR * AJ_STRIDE;
-  S.cr = S.sj + (size_t)N * N * R;
-  S.p0 = S.cr + (size_t)N * N * R;
-  S.qq = S.p0 + N * N;
-  S.dd = S.qq + N * N;
-  const int64_t ld = 3 * (int64_t)D;
-  const float* base = qkv + b * NR * ld + hh * hd;  // q columns of this head
-  const float scl = rsqrtf((float)hd);
-  const int nchunk = (hd + AJ_CH - 1) / AJ_CH;
-
-  // ------------------------------------------------------------------ phase 1: score jets
-  for (int p0i = 0; p0i < NR; p0i += AJ_THREADS) {
-    const int item = p0i + tid;
-    const bool active = item < NR;
-    const int j = active ? item / R : 0, r = active ? item % R : 0;
-    float acc[NMAX][3];
-#pragma unroll
-    for (int i = 0; i < NMAX; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; }
-    for (int ch = 0; ch < nchunk; ++ch) {
-      __syncthreads();
-      for (int t = tid; t < NR * 4; t += AJ_THREADS) {
-        const int row = t >> 2, f4 = t & 3;
-        const int dcol = ch * AJ_CH + f4 * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (dcol + 3 < hd) v = *reinterpret_cast<const float4*>(base + row * ld + dcol);
-        else {
-          const float* pp = base + row * ld + dcol;
-          if (dcol < hd) v.x = pp[0];
-          if (dcol + 1 < hd) v.y = pp[1];
-          if (dcol + 2 < hd) v.z = pp[2];
-        }
-        *reinterpret_cast<float4*>(S.qs + row * AJ_STRIDE + f4 * 4) = v;
-      }
-      __syncthreads();
-      if (active) {
-        float kr[AJ_CH], k0[AJ_CH];
-        const float* pkr = base + D + (int64_t)(j * R + r) * ld + ch * AJ_CH;
-        const float* pk0 = base + D + (int64_t)(j * R) * ld + ch * AJ_CH;
-#pragma unroll
-        for (int c = 0; c < AJ_CH; c += 4) {
-          const int dcol = ch * AJ_CH + c;
-          float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4;
-          if (dcol + 3 < hd) {
-            a4 = *reinterpret_cast<const float4*>(pkr + c);
-            b4 = *reinterpret_cast<const float4*>(pk0 + c);
-          } else {
-            if (dcol < hd) { a4.x = pkr[c]; b4.x = pk0[c]; }
-            if (dcol + 1 < hd) { a4.y = pkr[c + 1]; b4.y = pk0[c + 1]; }
-            if (dcol + 2 < hd) { a4.z = pkr[c + 2]; b4.z = pk0[c + 2]; }
-          }
-          kr[c] = a4.x; kr[c + 1] = a4.y; kr[c + 2] = a4.z; kr[c + 3] = a4.w;
-          k0[c] = b4.x; k0[c + 1] = b4.y; k0[c + 2] = b4.z; k0[c + 3] = b4.w;
-        }
-#pragma unroll
-        for (int i = 0; i < NMAX; ++i) {
-          if (i < N) {
-            const float* qr = S.qs + (i * R + r) * AJ_STRIDE;
-            const float* q0 = S.qs + (i * R) * AJ_STRIDE;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-            for (int c = 0; c < AJ_CH; c += 4) {
-              float4 x4 = *reinterpret_cast<const float4*>(qr + c);
-              float4 y4 = *reinterpret_cast<const float4*>(q0 + c);
-              a0 = fmaf(x4.x, k0[c], a0); a0 = fmaf(x4.y, k0[c + 1], a0);
-              a0 = fmaf(x4.z, k0[c + 2], a0); a0 = fmaf(x4.w, k0[c + 3], a0);
-              a1 = fmaf(y4.x, kr[c], a1); a1 = fmaf(y4.y, kr[c + 1], a1);
-              a1 = fmaf(y4.z, kr[c + 2], a1); a1 = fmaf(y4.w, kr[c + 3], a1);
-              a2 = fmaf(x4.x, kr[c], a2); a2 = fmaf(x4.y, kr[c + 1], a2);
-              a2 = fmaf(x4.z, kr[c + 2], a2); a2 = fmaf(x4.w, kr[c + 3], a2);
-            }
-            acc[i][0] += a0; acc[i][1] += a1; acc[i][2] += a2;
-          }
-        }
-      }
-    }
-    if (active) {
-#pragma unroll
-      for (int i = 0; i < NMAX; ++i) {
-        if (i < N) {
-          const int idx = (i * N + j) * R + r;
-          S.sj[idx] = (r == 0) ? acc[i][2] * scl : (acc[i][0] + acc[i][1]) * scl;
-          S.cr[idx] = acc[i][2] * scl;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  // second-order rows pick up the cross products: S += 2 sum_k qJk.kJk ; T_a += 2 qDa.kDa
-  for (int t = tid; t < N * N * 4; t += AJ_THREADS) {
-    const int ij = t >> 2, w = t & 3;
-    float* sp = S.sj + ij * R;
-    const float* cp = S.cr + ij * R;
-    if (w == 0) {
-      float s2 = 0.f;
-      for (int k = 0; k < 2 * N; ++k) s2 += cp[rw.J(k)];
-      sp[rw.S()] += 2.f * s2;
-    } else {
-      sp[rw.T(w - 1)] += 2.f * cp[rw.D(w - 1)];
-    }
-  }
-  __syncthreads();
-  // ------------------------------------------------------------------ softmax jets
-  for (int i = tid; i < N; i += AJ_THREADS) {
-    float mx = -INFINITY;
-    for (int j = 0; j < N; ++j) mx = fmaxf(mx, S.sj[(i * N + j) * R]);
-    float Z = 0.f;
-    for (int j = 0; j < N; ++j) { float e = __expf(S.sj[(i * N + j) * R] - mx); S.p0[i * N + j] = e; Z += e; }
-    const float iz = 1.f / Z;
-    for (int j = 0; j < N; ++j) S.p0[i * N + j] *= iz;
-  }
-  __syncthreads();
-  const int nfirst = 2 * N + 3;
-  for (int t = tid; t < N * nfirst; t += AJ_THREADS) {  // first-order rows: l = s - lse
-    const int i = t / nfirst, q = t % nfirst;
-    const int r = q < 2 * N ? rw.J(q) : rw.D(q - 2 * N);
-    float lse = 0.f;
-    for (int j = 0; j < N; ++j) lse = fmaf(S.p0[i * N + j], S.sj[(i * N + j) * R + r], lse);
-    for (int j = 0; j < N; ++j) S.sj[(i * N + j) * R + r] -= lse;
-  }
-  __syncthreads();
-  for (int t = tid; t < N * N; t += AJ_THREADS) {
-    const float* sp = S.sj + t * R;
-    float s2 = 0.f;
-    for (int k = 0; k < 2 * N; ++k) s2 = fmaf(sp[rw.J(k)], sp[rw.J(k)], s2);
-    S.qq[t] = s2;
-    for (int a3 = 0; a3 < 3; ++a3) S.dd[a3 * N * N + t] = sp[rw.D(a3)] * sp[rw.D(a3)];
-  }
-  __syncthreads();
-  for (int t = tid; t < N * 4; t += AJ_THREADS) {  // second-order rows
-    const int i = t >> 2, w = t & 3;
-    const int r = w == 0 ? rw.S() : rw.T(w - 1);
-    const float* extra = w == 0 ? S.qq : S.dd + (w - 1) * N * N;
-    float lse = 0.f;
-    for (int j = 0; j < N; ++j) {
-      float v = S.sj[(i * N + j) * R + r] + extra[i * N + j];
-      S.sj[(i * N + j) * R + r] = v;
-      lse = fmaf(S.p0[i * N + j], v, lse);
-    }
-    for (int j = 0; j < N; ++j) S.sj[(i * N + j) * R + r] -= lse;
-  }
-  __syncthreads();
-  for (int t = tid; t < N * N * R; t += AJ_THREADS) {  // l -> p jets
-    const int ij = t / R, r = t % R;
-    S.sj[t] = r == 0 ? S.p0[ij] : S.p0[ij] * S.sj[t];
-  }
-  // ------------------------------------------------------------------ phase 2: o = P V jets
-  const float* vbase = base + 2 * D;
-  float* obase = o + b * NR * (int64_t)D + hh * hd;
-  for (int ch = 0; ch < nchunk; ++ch) {
-    __syncthreads();
-    for (int t = tid; t < NR * 4; t += AJ_THREADS) {
-      const int row = t >> 2, f4 = t & 3;
-      const int dcol = ch * AJ_CH + f4 * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (dcol + 3 < hd) v = *reinterpret_cast<const float4*>(vbase + row * ld + dcol);
-      else {
-        const float* pp = vbase + row * ld + dcol;
-        if (dcol < hd) v.x = pp[0];
-        if (dcol + 1 < hd) v.y = pp[1];
-        if (dcol + 2 < hd) v.z = pp[2];
-      }
-      *reinterpret_cast<float4*>(S.qs + row * AJ_STRIDE + f4 * 4) = v;
-    }
-    __syncthreads();
-    for (int t = tid; t < NR * 4; t += AJ_THREADS) {
-      const int f4 = t & 3, ir = t >> 2;
-      const int i = ir / R, r = ir % R;
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto fma4 = [&](float p, const float* vrow) {
-        float4 v = *reinterpret_cast<const float4*>(vrow + f4 * 4);
-        acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
-        acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
-      };
-      for (int j = 0; j < N; ++j) {
-        const float* pj = S.sj + (i * N + j) * R;
-        const float* vj = S.qs + (size_t)(j * R) * AJ_STRIDE;
-        if (r == 0) {
-          fma4(pj[0], vj);
-        } else {
-          fma4(pj[r], vj);
-          fma4(pj[0], vj + r * AJ_STRIDE);
-          if (r == rw.S()) {
-            for (int k = 0; k < 2 * N; ++k) fma4(2.f * pj[rw.J(k)], vj + rw.J(k) * AJ_STRIDE);
-          } else if (r >= rw.T(0)) {
-            const int rd = rw.D(r - rw.T(0));
-            fma4(2.f * pj[rd], vj + rd * AJ_STRIDE);
-          }
-        }
-      }
-      const int dcol = ch * AJ_CH + f4 * 4;
-      float* dst = obase + (int64_t)ir * D + dcol;
-      if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = acc;
-      else {
-        if (dcol < hd) dst[0] = acc.x;
-        if (dcol + 1 < hd) dst[1] = acc.y;
-        if (dcol + 2 < hd) dst[2] = acc.z;
-      }
-    }
-  }
-}
-
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
-  if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
-  size_t smem = attention_jets_smem(d);
-  dim3 grid((unsigned)d.H, (unsigned)B);
-#define DH_AJ(NM)                                                                                           \
-  do {                                                                                                      \
-    cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel<NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return (int)e;                                                                    \
-    attention_jets_kernel<NM><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                                    \
-  } while (0)
-  if (d.N <= 4) DH_AJ(4);
-  else if (d.N <= 8) DH_AJ(8);
-  else if (d.N <= 12) DH_AJ(12);
-  else DH_AJ(16);
-#undef DH_AJ
-  return (int)cudaGetLastError();
-}
 
 }  // namespace dh
