@@ -107,8 +107,10 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       if (has_bias) { sl.bias = off; off += al((size_t)Nout); }
       p->slots.push_back(sl);
     };
-    for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); }
+    for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); slot(D, true); }
     slot(2 * p->LNK, true);
+    p->w0qkv = off; off += al((size_t)4 * 3 * D);
+    p->fold_tmp = off; off += al((size_t)D * D);
     p->prep_floats = off;
     cudaError_t e0 = cudaMalloc(&p->prep, off * sizeof(float));
     if (e0 != cudaSuccess) { delete p; return (int)e0; }
@@ -176,13 +178,23 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   { ProfScope ps(p, PC_OTHER, 0, s); if ((rc = features_dense0(x, P + p->off_W0, w.h, Bc, nd, s))) return rc; }
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
-    if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s))) return rc;
+    if (l == 0 && p->gemm_impl == 1) {
+      // h = feat @ W0 is linear in the features: q|k|v = feat @ (W0 Wqkv) + b, a 4-deep contraction
+      ProfScope ps(p, PC_OTHER, 0, s);
+      const dh_plan::Slot& q = p->slots[SL_QKV];
+      if ((rc = features_linear(x, p->prep + p->w0qkv, p->prep + q.bias, w.qkv, 3 * D, Bc, nd, s))) return rc;
+    } else if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s))) return rc;
     { ProfScope ps(p, PC_ATTENTION, 0, s);
       if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, s);
       else rc = attention_value(w.qkv, w.att, Bc, nd, s);
       if (rc) return rc; }
-    if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
-    if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
+    if (p->gemm_impl == 1) {
+      // MHA out-projection and the bias-free Dense that follows it are one linear map (Wo W1, bo W1)
+      if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s))) return rc;
+    } else {
+      if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
+      if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
+    }
     { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s))) return rc; }
     if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s))) return rc;
     { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc; }
@@ -222,6 +234,19 @@ int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
     if ((rc = cp(so.bias, o.o_b, D))) return rc;
     const dh_plan::Slot& s1 = p->slots[l * SL_PER_LAYER + SL_D1];
     if ((rc = split_weight_tc(P + o.d1_k, D, D, D, p->prep + s1.hi, p->prep + s1.lo, s))) return rc;
+    // folded out-projection . Dense_{1+2l}:  Wc = Wo @ W1 (fp32 FMA), bc = bo @ W1
+    const dh_plan::Slot& sod = p->slots[l * SL_PER_LAYER + SL_OD];
+    float* tmp = p->prep + p->fold_tmp;
+    if ((rc = gemm_simt(P + o.o_k, P + o.d1_k, nullptr, tmp, D, D, D, D, 1, D, 1, D, 1, 0, 1, s))) return rc;
+    if ((rc = split_weight_tc(tmp, D, D, D, p->prep + sod.hi, p->prep + sod.lo, s))) return rc;
+    if ((rc = gemm_simt(P + o.o_b, P + o.d1_k, nullptr, p->prep + sod.bias, 1, D, D, D, 1, D, 1, D, 1, 0, 1, s))) return rc;
+    if (l == 0) {
+      // W0 @ (Wq | Wk | Wv): [4][3D]
+      for (int t = 0; t < 3; ++t)
+        if ((rc = gemm_simt(P + p->off_W0, P + wk[t], nullptr, p->prep + p->w0qkv + (size_t)t * D, 4, D, D, D, 1, D, 1,
+                            3 * D, 1, 0, 1, s)))
+          return rc;
+    }
     const dh_plan::Slot& s2 = p->slots[l * SL_PER_LAYER + SL_D2];
     if ((rc = split_weight_tc(P + o.d2_k, D, D, D, p->prep + s2.hi, p->prep + s2.lo, s))) return rc;
     if ((rc = cp(s2.bias, o.d2_b, D))) return rc;
@@ -234,7 +259,7 @@ int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
   if ((rc = split_weight_tc_rows(P + p->orb_im_k, LNK, D, LNK, p->prep + sb.hi + (size_t)LNK * D, p->prep + sb.lo + (size_t)LNK * D, s))) return rc;
   if ((rc = cp(sb.bias, p->orb_re_b, LNK))) return rc;
   if ((rc = cp(sb.bias + LNK, p->orb_im_b, LNK))) return rc;
-  p->launches += 4 * p->nl * 2 + 2;
+  p->launches += p->nl * 8 + 5 + 2;
   return 0;
 }
 

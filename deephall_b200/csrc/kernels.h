@@ -26,6 +26,9 @@ struct NetDims {
   int n_up;    // spin-up count (for the spin feature)
 };
 int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDims d, cudaStream_t s);
+// out[rows, Nout] = feature jets @ W[4][Nout] (+ bias on value rows)
+int features_linear(const float* x, const float* W, const float* bias, float* out, int Nout, int64_t B, NetDims d,
+                    cudaStream_t s);
 // out = LN(a + (tanh_mode ? tanh(b) : b)) with jets; a/b/out are [B*N*R, D]
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s);

@@ -12,10 +12,13 @@ namespace dh {
 // features (psiformer.py:51-60) fused with Dense_0 (psiformer.py:42, no bias)
 // grid: B*N blocks; thread d loops over model columns.
 // =============================================================================================
+// Generalised to any linear map of the features: out[row, 0..Nout) = feat_row @ W[4][Nout]
+// (+ bias on the value row) -- also used for the FIRST layer's q|k|v, whose input h = feat @ W0
+// is linear in the features, so q|k|v = feat @ (W0 Wqkv) + b needs no 256-deep contraction.
 __global__ void features_dense0_kernel(const float* __restrict__ x, const float* __restrict__ W0,
-                                       float* __restrict__ h, NetDims dm) {
+                                       const float* __restrict__ bias, float* __restrict__ h, int Nout, NetDims dm) {
   extern __shared__ float feat[];  // [R][4]
-  const int N = dm.N, R = dm.R, D = dm.D;
+  const int N = dm.N, R = dm.R, D = Nout;
   const int64_t bi = blockIdx.x;
   const int i = (int)(bi % N);
   for (int t = threadIdx.x; t < R * 4; t += blockDim.x) feat[t] = 0.f;
@@ -52,14 +55,21 @@ __global__ void features_dense0_kernel(const float* __restrict__ x, const float*
     float w0 = W0[d], w1 = W0[D + d], w2 = W0[2 * D + d], w3 = W0[3 * D + d];
     for (int r = 0; r < R; ++r) {
       const float* f = feat + r * 4;
-      out[(int64_t)r * D + d] = fmaf(f[0], w0, fmaf(f[1], w1, fmaf(f[2], w2, f[3] * w3)));
+      float v = fmaf(f[0], w0, fmaf(f[1], w1, fmaf(f[2], w2, f[3] * w3)));
+      if (r == 0 && bias != nullptr) v += bias[d];
+      out[(int64_t)r * D + d] = v;
     }
   }
 }
 
 int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDims d, cudaStream_t s) {
-  int threads = d.D >= 256 ? 256 : ((d.D + 31) / 32 * 32);
-  features_dense0_kernel<<<(unsigned)(B * d.N), threads, d.R * 4 * sizeof(float), s>>>(x, W0, h, d);
+  return features_linear(x, W0, nullptr, h, d.D, B, d, s);
+}
+
+int features_linear(const float* x, const float* W, const float* bias, float* out, int Nout, int64_t B, NetDims d,
+                    cudaStream_t s) {
+  int threads = Nout >= 256 ? 256 : ((Nout + 31) / 32 * 32);
+  features_dense0_kernel<<<(unsigned)(B * d.N), threads, d.R * 4 * sizeof(float), s>>>(x, W, bias, out, Nout, d);
   return (int)cudaGetLastError();
 }
 

@@ -30,7 +30,9 @@ struct dh_plan {
   size_t prep_floats;
   const float* prep_src;  // params pointer the preparation was made from
   struct Slot { int Nout; size_t hi, lo, bias; };  // float offsets into prep (bias: SIZE_MAX = none)
-  std::vector<Slot> slots;  // per layer: qkv, o, d1, d2 ; last: orbitals (re | im)
+  std::vector<Slot> slots;  // per layer: qkv, o, d1, d2, od (= o folded into d1) ; last: orbitals (re | im)
+  size_t w0qkv;             // float offset into prep: [4][3D] = W0 @ (Wq|Wk|Wv) of layer 0 (fp32)
+  size_t fold_tmp;          // float offset into prep: [D][D] scratch for Wo @ W1 (fp32)
   // ---- instrumentation (dh_profile_*): CUDA-event timing of kernel categories, launch count
   bool prof_on;
   std::vector<cudaEvent_t> prof_ev;   // pool, pairs (start, stop)
@@ -114,7 +116,7 @@ static inline float* align_ws(void* ws) {
 }
 
 // --------------------------------------------------------------------------------- forward
-enum { SL_QKV = 0, SL_O = 1, SL_D1 = 2, SL_D2 = 3, SL_PER_LAYER = 4 };
+enum { SL_QKV = 0, SL_O = 1, SL_D1 = 2, SL_D2 = 3, SL_OD = 4, SL_PER_LAYER = 5 };
 
 // tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows)
 static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C, int64_t rows, int64_t ldc, int R,
