@@ -1,5 +1,6 @@
 // C ABI (include/deephall_b200.h): plan, parameter layout, workspace carving and the launch
 // sequences of the four hot-path operations.
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -96,6 +97,9 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   {
     const char* env = getenv("DH_GEMM_IMPL");
     p->gemm_impl = (env && std::string(env) == "simt") ? 0 : 1;
+    p->tc_f16 = (gemm_tc_f16_ok(D) && !(env && std::string(env) == "tf32")) ? 1 : 0;
+    const char* acc = getenv("DH_GEMM_ACC");  // "split" | "merged"; default: merged for fp16 pieces, split for tf32
+    p->tc_merged = acc ? (std::string(acc) == "merged" ? 1 : 0) : p->tc_f16;
     size_t off = 0;
     auto slot = [&](int Nout, bool has_bias) {
       dh_plan::Slot sl;
@@ -105,6 +109,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       sl.lo = off; off += al(npad * D);
       sl.bias = SIZE_MAX;
       if (has_bias) { sl.bias = off; off += al((size_t)Nout); }
+      sl.scale = off; off += al(3);
       p->slots.push_back(sl);
     };
     for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); slot(D, true); }
@@ -216,29 +221,60 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
 
 int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
   if (p->gemm_impl != 1) return 0;
-  const int D = p->D, LNK = p->LNK;
+  const int D = p->D, LNK = p->LNK, f16 = p->tc_f16;
   int rc;
   auto cp = [&](size_t dst, int64_t src, size_t n) {
     return (int)cudaMemcpyAsync(p->prep + dst, P + src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  };
+  // element `e` of a slot's hi / lo plane (fp16 planes pack two elements per float of `prep`)
+  auto plane = [&](size_t off_floats, size_t e) -> void* {
+    return f16 ? (void*)(reinterpret_cast<__half*>(p->prep + off_floats) + e) : (void*)(p->prep + off_floats + e);
+  };
+  // one slot = `nparts` blocks W_t[D][n_t] stacked along the output dimension
+  struct Part { const float* W; int64_t ldw; int n; };
+  auto fill = [&](const dh_plan::Slot& sl, const Part* parts, int nparts, bool zero_first) -> int {
+    float* slot = p->prep + sl.scale;
+    if (zero_first) {
+      const size_t bytes = (size_t)((sl.Nout + 15) & ~15) * D * (f16 ? 2 : 4);
+      DH_CHECK(cudaMemsetAsync(plane(sl.hi, 0), 0, bytes, s));
+      DH_CHECK(cudaMemsetAsync(plane(sl.lo, 0), 0, bytes, s));
+    }
+    if (f16) {
+      DH_CHECK(cudaMemsetAsync(slot, 0, 3 * sizeof(float), s));
+      for (int t = 0; t < nparts; ++t)
+        if ((rc = weight_maxabs_tc(parts[t].W, parts[t].ldw, D, parts[t].n, slot, s))) return rc;
+    }
+    size_t row = 0;
+    for (int t = 0; t < nparts; ++t) {
+      const bool last = t == nparts - 1;
+      if ((rc = split_weight_tc(parts[t].W, parts[t].ldw, D, parts[t].n, last && !zero_first ? 1 : 0,
+                                plane(sl.hi, row * D), plane(sl.lo, row * D), slot, f16, s)))
+        return rc;
+      row += parts[t].n;
+    }
+    return 0;
   };
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
     const dh_plan::Slot& q = p->slots[l * SL_PER_LAYER + SL_QKV];
     const int64_t wk[3] = {o.q_k, o.k_k, o.v_k}, wb[3] = {o.q_b, o.k_b, o.v_b};
-    for (int t = 0; t < 3; ++t) {
-      if ((rc = split_weight_tc(P + wk[t], D, D, D, p->prep + q.hi + (size_t)t * D * D, p->prep + q.lo + (size_t)t * D * D, s))) return rc;
+    const Part pq[3] = {{P + wk[0], D, D}, {P + wk[1], D, D}, {P + wk[2], D, D}};
+    if ((rc = fill(q, pq, 3, false))) return rc;
+    for (int t = 0; t < 3; ++t)
       if ((rc = cp(q.bias + (size_t)t * D, wb[t], D))) return rc;
-    }
     const dh_plan::Slot& so = p->slots[l * SL_PER_LAYER + SL_O];
-    if ((rc = split_weight_tc(P + o.o_k, D, D, D, p->prep + so.hi, p->prep + so.lo, s))) return rc;
+    const Part po = {P + o.o_k, D, D};
+    if ((rc = fill(so, &po, 1, false))) return rc;
     if ((rc = cp(so.bias, o.o_b, D))) return rc;
     const dh_plan::Slot& s1 = p->slots[l * SL_PER_LAYER + SL_D1];
-    if ((rc = split_weight_tc(P + o.d1_k, D, D, D, p->prep + s1.hi, p->prep + s1.lo, s))) return rc;
+    const Part p1 = {P + o.d1_k, D, D};
+    if ((rc = fill(s1, &p1, 1, false))) return rc;
     // folded out-projection . Dense_{1+2l}:  Wc = Wo @ W1 (fp32 FMA), bc = bo @ W1
     const dh_plan::Slot& sod = p->slots[l * SL_PER_LAYER + SL_OD];
     float* tmp = p->prep + p->fold_tmp;
     if ((rc = gemm_simt(P + o.o_k, P + o.d1_k, nullptr, tmp, D, D, D, D, 1, D, 1, D, 1, 0, 1, s))) return rc;
-    if ((rc = split_weight_tc(tmp, D, D, D, p->prep + sod.hi, p->prep + sod.lo, s))) return rc;
+    const Part pod = {tmp, D, D};
+    if ((rc = fill(sod, &pod, 1, false))) return rc;
     if ((rc = gemm_simt(P + o.o_b, P + o.d1_k, nullptr, p->prep + sod.bias, 1, D, D, D, 1, D, 1, D, 1, 0, 1, s))) return rc;
     if (l == 0) {
       // W0 @ (Wq | Wk | Wv): [4][3D]
@@ -248,18 +284,17 @@ int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
           return rc;
     }
     const dh_plan::Slot& s2 = p->slots[l * SL_PER_LAYER + SL_D2];
-    if ((rc = split_weight_tc(P + o.d2_k, D, D, D, p->prep + s2.hi, p->prep + s2.lo, s))) return rc;
+    const Part p2 = {P + o.d2_k, D, D};
+    if ((rc = fill(s2, &p2, 1, false))) return rc;
     if ((rc = cp(s2.bias, o.d2_b, D))) return rc;
   }
+  // orbital projections: rows [0, LNK) = real part, rows [LNK, 2 LNK) = imaginary part; pad rows stay zero
   const dh_plan::Slot& sb = p->slots[p->nl * SL_PER_LAYER];
-  // rows [0, LNK) = real part, rows [LNK, 2 LNK) = imaginary part; the pad rows of the slot stay zero
-  DH_CHECK(cudaMemsetAsync(p->prep + sb.hi, 0, (size_t)((2 * LNK + 15) & ~15) * D * sizeof(float), s));
-  DH_CHECK(cudaMemsetAsync(p->prep + sb.lo, 0, (size_t)((2 * LNK + 15) & ~15) * D * sizeof(float), s));
-  if ((rc = split_weight_tc_rows(P + p->orb_re_k, LNK, D, LNK, p->prep + sb.hi, p->prep + sb.lo, s))) return rc;
-  if ((rc = split_weight_tc_rows(P + p->orb_im_k, LNK, D, LNK, p->prep + sb.hi + (size_t)LNK * D, p->prep + sb.lo + (size_t)LNK * D, s))) return rc;
+  const Part pb[2] = {{P + p->orb_re_k, LNK, LNK}, {P + p->orb_im_k, LNK, LNK}};
+  if ((rc = fill(sb, pb, 2, true))) return rc;
   if ((rc = cp(sb.bias, p->orb_re_b, LNK))) return rc;
   if ((rc = cp(sb.bias + LNK, p->orb_im_b, LNK))) return rc;
-  p->launches += p->nl * 8 + 5 + 2;
+  p->launches += p->nl * (f16 ? 18 : 11) + 5 + (f16 ? 4 : 2);
   return 0;
 }
 
@@ -387,13 +422,20 @@ extern "C" int dh_gemm(const float* A, const float* W, const float* bias, float*
   if (!A || !W || !C) return DH_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (impl == 0) return gemm_simt(A, W, bias, C, M, N, K, K, 1, N, 1, N, rows_per_group, accumulate, 1, s);
-  if (!gemm_tc_supported(N, K)) return DH_E_UNSUPPORTED;
-  // test/bench entry point: the split weights are made on the fly (the plan ops keep them cached)
+  if (!gemm_tc_supported(N, K) || accumulate) return DH_E_UNSUPPORTED;
+  // test/bench entry point: the split weights are made on the fly (the plan ops keep them cached).
+  // impl 1: kind::f16 pieces when K % 64 == 0, else kind::tf32;  impl 2: kind::tf32 pieces;
+  // impl 3: kind::f16 pieces with separate main / correction accumulators.
+  const int f16 = ((impl == 1 || impl == 3) && gemm_tc_f16_ok(K)) ? 1 : 0;
+  const int merged = (impl == 1 && f16) ? 1 : 0;
   float* wt = nullptr;
   const size_t npad = (size_t)((N + 15) & ~15);
-  DH_CHECK(cudaMalloc(&wt, 2 * npad * K * sizeof(float)));
-  int rc = split_weight_tc(W, N, K, N, wt, wt + npad * K, s);
-  if (!rc) rc = gemm_tc(A, wt, wt + npad * K, bias, C, M, N, K, N, rows_per_group, accumulate, s);
+  DH_CHECK(cudaMalloc(&wt, (2 * npad * K + 64) * sizeof(float)));
+  float* slot = wt + 2 * npad * K;
+  int rc = (int)cudaMemsetAsync(slot, 0, 3 * sizeof(float), s);
+  if (!rc && f16) rc = weight_maxabs_tc(W, N, K, N, slot, s);
+  if (!rc) rc = split_weight_tc(W, N, K, N, 1, wt, wt + npad * K, slot, f16, s);
+  if (!rc) rc = gemm_tc(A, wt, wt + npad * K, bias, f16 ? slot + 1 : nullptr, C, M, N, K, N, rows_per_group, f16, merged, s);
   cudaStreamSynchronize(s);
   cudaFree(wt);
   return rc;

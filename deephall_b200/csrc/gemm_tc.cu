@@ -1,24 +1,34 @@
-// tcgen05 / TMEM / TMA dense contraction with fp32 accuracy by 3xTF32 splitting (sm_100a).
+// tcgen05 / TMEM / TMA dense contraction with fp32 accuracy from a two-piece operand split (sm_100a).
 //
 //   C[M, N] = A[M, K] @ W[K, N] (+ bias[N] on rows m with m % rpg == 0)
 //
-// A is the fp32 activation matrix (row-major, K contiguous).  W is given pre-transposed and
-// pre-split: Wt_hi / Wt_lo are [Npad][K] fp32 arrays holding tf32-exact values with
-// W = hi + lo + O(2^-22 |W|)  (split_weight_tc, once per parameter update).
-// A is split inside the kernel: TMA lands the fp32 tile in shared memory (128B swizzle), four
-// warps rewrite it in place as hi = rna_tf32(a) and write lo = rna_tf32(a - hi) to a twin buffer;
-// one elected thread then issues, per 32-float K block, 4 x 3 tcgen05.mma.kind::tf32
-// (lo*hi, hi*lo, hi*hi) accumulating in fp32 in tensor memory.
+// Every operand x is written x = hi + lo with 11-bit-significand pieces and the product is taken as
+// hi*hi + lo*hi + hi*lo on the tensor cores with fp32 accumulation in tensor memory (the dropped
+// lo*lo term is 2^-22 relative).  Two instantiations of the same kernel:
+//   * kind::tf32 ("3xTF32"):  pieces are TF32 numbers, K step 8 per MMA, 32 K-elements per stage;
+//   * kind::f16  ("3xFP16"):  pieces are fp16 numbers -- the same 11-bit significand, so inside fp16's
+//     normal range the three products are bit-identical to the TF32 ones -- K step 16 per MMA at twice
+//     the TF32 rate, 64 K-elements per stage, half the operand bytes per flop.  fp16's narrow exponent
+//     range is handled by a per-matrix power-of-two weight scale (undone exactly in the epilogue),
+//     saturating conversions, and gradual underflow of `lo` (absolute error <= 2^-25, below fp32
+//     rounding of O(1) activations; oracle emulation in DESIGN.md).  Used when K % 64 == 0.
+// W is given pre-transposed ([Npad][K], K-major) and pre-split (split_weight_tc, once per parameter
+// update).  A is split inside the kernel: TMA lands the fp32 tile in shared memory (128B swizzle),
+// four warps rewrite it in place as the hi / lo operand tiles, one elected thread issues the MMAs.
 //
-// PERSISTENT kernel, one CTA per SM, 320 threads, CTA tile 128 x (<=256) x K:
+// PERSISTENT kernel, one CTA per SM, 448 threads, CTA tile 128 x (<=256) x K:
 //   warp 0      TMA producer           (2-stage ring of 96 KB stages, runs ahead across tiles)
 //   warp 1      TMEM allocator + MMA issuer
-//   warps 2..5  splitter               (fp32 -> tf32 hi / lo, in shared memory)
-//   warps 6..9  epilogue               (tcgen05.ld -> +bias -> swizzled smem staging -> TMA store)
+//   warps 2..9   splitter              (fp32 -> hi / lo pieces, in shared memory)
+//   warps 10..13 epilogue              (tcgen05.ld -> scale, +bias -> swizzled smem staging -> TMA store)
 // so the loads and the split of tile t+1 overlap the drain and the stores of tile t.  The two
 // accumulators (main, correction) fill all 512 TMEM columns, so the first MMA of tile t+1 waits
 // until the epilogue has read tile t out of TMEM (not until its stores have landed).
 #include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_fp16.h>
 
 #include "kernels.h"
 
@@ -28,17 +38,17 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
-constexpr int BLOCK_K = 32;  // floats = one 128-byte swizzle row
-constexpr int UMMA_K = 8;    // tf32
 constexpr int STAGES = 2;
-constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;  // 16 KB
-constexpr int B_BYTES = BLOCK_N * BLOCK_K * 4;  // 32 KB
+constexpr int A_BYTES = BLOCK_M * 128;  // 16 KB: one operand tile of 128 rows x one 128-byte swizzle row
+constexpr int B_BYTES = BLOCK_N * 128;  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 96 KB
 constexpr int EPI_CHUNK = 32;                            // accumulator columns per epilogue step
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 4;        // 32 rows x 32 floats = 4 KB (one warp, one step)
 constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;         // 4 warps x 2 buffers = 32 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 320;
+constexpr int SPLIT_WARPS = 8;
+constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;  // first epilogue warp
+constexpr int THREADS = 32 * (EPI_WARP0 + 4);  // 448
 constexpr int TMEM_COLS = 512;  // [0,256): hi*hi accumulator, [256,512): correction (lo*hi + hi*lo) accumulator
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,18 +91,52 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
+template <bool F16>
 __device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  // c_format F32 (1) @4, a/b format TF32 (2) @7/@10, K-major both, N>>3 @17, M>>4 @24
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  // c_format F32 (1) @4, a/b format @7/@10 (kind::tf32: TF32 = 2; kind::f16: F16 = 0), K-major both,
+  // N>>3 @17, M>>4 @24
+  const uint32_t ab = F16 ? 0u : 2u;
+  return (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool F16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                     uint32_t accumulate) {
+  if (F16) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// fp16 piece of x with saturation to the largest finite fp16 (NaN stays NaN)
+__device__ __forceinline__ float sat_f16_range(float x) { return fabsf(x) > 65504.f ? copysignf(65504.f, x) : x; }
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(sat_f16_range(x));
+  lo = __float2half_rn(sat_f16_range(x - __half2float(hi)));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {  // a in the low half
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// two floats -> packed fp16 pair (x0 in the low half), round-to-nearest, saturating to +-65504, NaN kept
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+// (x0, x1) -> hi pair, lo pair:  hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2_sat(x0, x1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = cvt_f16x2_sat(x0 - hf.x, x1 - hf.y);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -116,26 +160,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // tma_store != 0: C is written through tmC (box 32 x 32 floats, 128B swizzle); otherwise (ldc not a
 // multiple of 4 floats, or misaligned C) by direct global stores.
+template <bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
-               const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K, int64_t ldc, int rpg,
-               int tma_store) {
+               const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
+               int N, int K, int64_t ldc, int rpg, int tma_store, int merged, unsigned long long* __restrict__ prof) {
+  constexpr int BLOCK_K = F16 ? 64 : 32;  // K elements per stage
+  constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
+  constexpr int A_TX_BYTES = BLOCK_M * BLOCK_K * 4;  // fp32 bytes TMA lands for A per stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
   // bars: [0..S) full, [S..2S) split, [2S..3S) empty, [3S] tmem_full, [3S+1] tmem_empty ; then tmem ptr
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (3 * STAGES);
-  const uint32_t tmem_empty_bar = bar_base + 8u * (3 * STAGES + 1);
+  // merged == 0: main accumulator in TMEM columns [0,256), correction accumulator in [256,512), one tile in
+  //              flight (the issuer waits for the drain of the previous tile);
+  // merged != 0: all three products of a tile go to ONE accumulator, tiles alternate between columns [0,256)
+  //              and [256,512), so tile t+1 is computed while tile t is drained -- at the price of 3x as many
+  //              truncating additions into the accumulator ("accumulator modes").
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
   auto a_hi = [&](int s) { return smem_base + s * STAGE_BYTES; };
   auto a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
   auto b_hi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_BYTES; };
@@ -154,11 +217,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(split_bar(s), 4);
+      mbar_init(split_bar(s), SPLIT_WARPS);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
-    mbar_init(tmem_empty_bar, 4);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar(b), 1);
+      mbar_init(tmem_empty_bar(b), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -170,6 +235,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+  // developer instrumentation (DH_GEMM_PROF=1): cycles each role spends blocked, summed over CTAs
+  unsigned long long pw[3] = {0, 0, 0}, pe[5] = {0, 0, 0, 0, 0};
+  const long long t_begin = prof ? clock64() : 0;
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (prof) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      pw[slot] += (unsigned long long)(clock64() - t0);
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -181,13 +258,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_arrive_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
+          timed_wait(empty_bar(s), ph ^ 1, 0);
+          mbar_arrive_expect_tx(full_bar(s), A_TX_BYTES + 2 * B_BYTES);
           tma_load_2d(a_hi(s), &tmA, full_bar(s), kb * BLOCK_K, m0);
+          if (F16) tma_load_2d(a_lo(s), &tmA, full_bar(s), kb * BLOCK_K + 32, m0);  // second 32-float half
           tma_load_2d(b_hi(s), &tmBhi, full_bar(s), kb * BLOCK_K, n0);
           tma_load_2d(b_lo(s), &tmBlo, full_bar(s), kb * BLOCK_K, n0);
         }
       }
+      if (prof) { atomicAdd(prof + 0, pw[0]); atomicAdd(prof + 10, (unsigned long long)(clock64() - t_begin)); }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -197,63 +276,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n0 = (int)(tile % n_ntiles) * BLOCK_N;
         int n_tile = N - n0 < BLOCK_N ? N - n0 : BLOCK_N;
         n_tile = (n_tile + 15) & ~15;  // Wt buffers are zero-padded to a multiple of 16 rows
-        const uint32_t idesc = make_idesc(BLOCK_M, n_tile);
-        mbar_wait(tmem_empty_bar, (tl & 1) ^ 1);  // epilogue has read the previous tile out of TMEM
+        const uint32_t idesc = make_idesc<F16>(BLOCK_M, n_tile);
+        // the epilogue has read the previous user of this accumulator out of TMEM
+        const int ab = merged ? (int)(tl & 1) : 0;
+        const uint32_t au = merged ? (tl >> 1) : tl;  // how many times this accumulator has been used before
+        const uint32_t acc = tmem_base + (uint32_t)ab * BLOCK_N;
+        timed_wait(tmem_empty_bar(ab), (au & 1) ^ 1, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
-          mbar_wait(split_bar(s), ph);
+          timed_wait(full_bar(s), ph, 1);
+          timed_wait(split_bar(s), ph, 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t dah = make_smem_desc(a_hi(s)), dal = make_smem_desc(a_lo(s));
           const uint64_t dbh = make_smem_desc(b_hi(s)), dbl = make_smem_desc(b_lo(s));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // start-address field is in 16-byte units
+            const uint64_t adv = (uint64_t)(k * 2);  // 32 operand bytes per MMA; start-address field is in 16-byte units
             // The tensor core rounds toward zero when it adds into the fp32 accumulator, a bias that
             // grows with the number of additions: keep the small correction terms in their own
             // accumulator so the main one sees K/8 additions instead of 3K/8.
-            umma_tf32(tmem_base + BLOCK_N, dal + adv, dbh + adv, idesc, (kb | k) != 0);
-            umma_tf32(tmem_base + BLOCK_N, dah + adv, dbl + adv, idesc, 1);
-            umma_tf32(tmem_base, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+            if (merged) {
+              umma<F16>(acc, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+              umma<F16>(acc, dah + adv, dbl + adv, idesc, 1);
+              umma<F16>(acc, dah + adv, dbh + adv, idesc, 1);
+            } else {
+              umma<F16>(tmem_base + BLOCK_N, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+              umma<F16>(tmem_base + BLOCK_N, dah + adv, dbl + adv, idesc, 1);
+              umma<F16>(tmem_base, dah + adv, dbh + adv, idesc, (kb | k) != 0);
+            }
           }
           umma_commit(empty_bar(s));  // arrives when the MMAs reading this stage have completed
         }
-        umma_commit(tmem_full_bar);
+        umma_commit(tmem_full_bar(ab));
       }
+      if (prof) { atomicAdd(prof + 1, pw[0]); atomicAdd(prof + 2, pw[1]); atomicAdd(prof + 3, pw[2]);
+                  atomicAdd(prof + 11, (unsigned long long)(clock64() - t_begin)); }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------ splitter
-    const int t = threadIdx.x - 64;  // 0..127
+  } else if (warp < EPI_WARP0) {
+    // ------------------------------------------------------------------ splitter (8 warps)
+    const int t = threadIdx.x - 64;  // 0..255
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar(s), ph);
-        float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+        if (t == 0) timed_wait(full_bar(s), ph, 0); else mbar_wait(full_bar(s), ph);
+        const long long ts0 = (prof && t == 0) ? clock64() : 0;
+        if (F16) {
+          // Two threads per tile row r: thread (r, h) converts the 32 floats k = 32h .. 32h+31, which TMA put
+          // in region h (16-byte piece j of row r at position j ^ (r & 7)).  The fp16 hi tile (64 halves =
+          // 128 B per row) replaces region 0 and the lo tile region 1, row r in place: only the two threads
+          // of a row touch its bytes, they sit in the same warp, and a __syncwarp separates reads from writes.
+          const int r = t >> 1, h = t & 1, sw = r & 7;
+          uint8_t* row0 = smem + s * STAGE_BYTES + r * 128;
+          uint8_t* row1 = row0 + A_BYTES;
+          const uint8_t* src = h ? row1 : row0;
+          float4 v[8];  // v[j] = 16-byte piece j ^ 4h of this thread's 32 floats: the two threads of a row
+                        // start 64 B apart, so a quarter-warp never hits a bank twice
 #pragma unroll
-        for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-          const int idx = t + i * 128;
-          float4 v = hi[idx], h, l;
-          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-          l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-          hi[idx] = h;
-          lo[idx] = l;
+          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + (((j ^ (h << 2)) ^ sw) << 4));
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {  // v[2cc], v[2cc+1] are floats 8c .. 8c+7 with c = cc ^ 2h: fp16 piece 4h + c
+            const int c = cc ^ (h << 1);
+            const float4 a = v[2 * cc], b = v[2 * cc + 1];
+            uint4 hi, lo;
+            split_f16x2(a.x, a.y, hi.x, lo.x);
+            split_f16x2(a.z, a.w, hi.y, lo.y);
+            split_f16x2(b.x, b.y, hi.z, lo.z);
+            split_f16x2(b.z, b.w, hi.w, lo.w);
+            const int pos = ((4 * h + c) ^ sw) << 4;
+            *reinterpret_cast<uint4*>(row0 + pos) = hi;
+            *reinterpret_cast<uint4*>(row1 + pos) = lo;
+          }
+        } else {
+          float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+          for (int i = 0; i < A_BYTES / 16 / (32 * SPLIT_WARPS); ++i) {
+            const int idx = t + i * 32 * SPLIT_WARPS;
+            float4 v = hi[idx], h, l;
+            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+            hi[idx] = h;
+            lo[idx] = l;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) mbar_arrive(split_bar(s));
+        if (prof && t == 0) pw[1] += (unsigned long long)(clock64() - ts0);
       }
     }
+    if (prof && t == 0) { atomicAdd(prof + 4, pw[0]); atomicAdd(prof + 5, pw[1]); }
   } else {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (4 warps)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    uint8_t* my_epi = epi_smem + (warp - 6) * 2 * EPI_BUF_BYTES;
+    const bool lead = warp == EPI_WARP0 && lane == 0;
+    uint8_t* my_epi = epi_smem + (warp - EPI_WARP0) * 2 * EPI_BUF_BYTES;
     uint32_t tl = 0, nstore = 0;
+    const float inv_scale = inv_scale_ptr ? __ldg(inv_scale_ptr) : 1.f;  // undoes the fp16 weight scale (power of two)
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
       const int64_t m0 = (tile / n_ntiles) * BLOCK_M;
       const int n0 = (int)(tile % n_ntiles) * BLOCK_N;
@@ -261,55 +386,84 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       n_tile = (n_tile + 15) & ~15;
       const int64_t m = m0 + row;
       const bool add_bias = bias != nullptr && (rpg <= 1 || (m % rpg) == 0);
-      mbar_wait(tmem_full_bar, tl & 1);
+      // first row of this warp's 32-row slice that is the value row of an electron (jet passes, rpg > 1)
+      const int first_vrow = rpg > 1 ? (int)((rpg - (m0 + q * 32) % rpg) % rpg) : 0;
+      const int ab = merged ? (int)(tl & 1) : 0;
+      const uint32_t au = merged ? (tl >> 1) : tl;
+      if (lead) timed_wait(tmem_full_bar(ab), au & 1, 0); else mbar_wait(tmem_full_bar(ab), au & 1);
+      const long long te0 = (prof && lead) ? clock64() : 0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * BLOCK_N;
       for (int c0 = 0; c0 < n_tile; c0 += EPI_CHUNK) {
         uint32_t v[32], w[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + BLOCK_N, w);
+        long long tp0 = (prof && lead) ? clock64() : 0, tp1;
+#define DH_LAP(slot) if (prof && lead) { tp1 = clock64(); pe[slot] += (unsigned long long)(tp1 - tp0); tp0 = tp1; }
+        tmem_ld32(tbase + (uint32_t)c0, v);
+        if (!merged) tmem_ld32(tbase + (uint32_t)c0 + BLOCK_N, w);
+        // lane j fetches bias column j of this step (coalesced)
+        const float bl = (bias != nullptr && n0 + c0 + lane < N) ? __ldg(bias + n0 + c0 + lane) : 0.f;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        DH_LAP(0)
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(v[j]) + (merged ? 0.f : __uint_as_float(w[j]))) * inv_scale;
         if (c0 + EPI_CHUNK >= n_tile) {
           // last read of this tile's accumulators: hand TMEM back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar);
+          if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
+          if (prof && lead) pw[1] += (unsigned long long)(clock64() - te0);
         }
+        if (bias != nullptr && (rpg <= 1 || !tma_store)) {
+          // every row takes the bias (value-only passes), or no staging buffer to patch: per-lane adds
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-        if (add_bias) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < N) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + n0 + c0 + j));
+          for (int j = 0; j < 32; ++j) {
+            const float bj = __shfl_sync(0xffffffffu, bl, j);
+            if (add_bias) o[j] += bj;
+          }
         }
+        DH_LAP(1)
         if (tma_store) {
           // staging buffer `nstore & 1` of this warp: wait until the TMA store issued two steps ago has read it
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
+          DH_LAP(2)
           uint8_t* buf = my_epi + (nstore & 1) * EPI_BUF_BYTES;
           // row `lane` of the 32 x 32 chunk; 16-byte piece j lives at piece position j ^ (lane & 7) (128B swizzle)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = o;
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          if (bias != nullptr && rpg > 1) {
+            // jet passes: only every rpg-th row (the value row of an electron) takes the bias; patch those
+            // rows in the staging buffer, lane j adding bias column j
+            __syncwarp();
+            for (int r = first_vrow; r < 32; r += rpg) {
+              float* pz = reinterpret_cast<float*>(buf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+              *pz += bl;
+            }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
+          DH_LAP(3)
           if (lane == 0) {
             tma_store_2d(&tmC, smem_u32(buf), n0 + c0, (int)(m0 + q * 32));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++nstore;
+          DH_LAP(4)
         } else if (m < M) {
           float* crow = C + m * ldc + n0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < N) crow[j] = __uint_as_float(v[j]);
+            if (n0 + c0 + j < N) crow[j] = o[j];
         }
       }
     }
     if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (prof && lead) { for (int i = 0; i < 5; ++i) atomicAdd(prof + 16 + i, pe[i]);
+                        atomicAdd(prof + 6, pw[0]); atomicAdd(prof + 7, pw[1]);
+                        atomicAdd(prof + 12, (unsigned long long)(clock64() - t_begin)); }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -319,24 +473,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// W[K][N] (row stride ldw) -> Wt_hi, Wt_lo [Npad][K]; rows n >= N are zero.
+// ---- weight preparation ---------------------------------------------------------------------
+// scale slot (3 floats): [0] max |W| over the slot (as ordered uint bits), [1] 1/scale, [2] scale.
+__global__ void weight_maxabs_kernel(const float* __restrict__ W, int64_t ldw, int K, int N, unsigned* __restrict__ slot) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)K * N; i += (int64_t)gridDim.x * blockDim.x) {
+    const float w = fabsf(W[(i / N) * ldw + (i % N)]);
+    if (w < INFINITY) m = fmaxf(m, w);  // NaN / inf weights do not define the scale
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+// power-of-two scale that brings max |W| into [2^13, 2^14): far from fp16 overflow, and the lo pieces
+// of all but the (2^-17 relative) smallest weights stay normal
+__device__ __forceinline__ float f16_weight_scale(const unsigned* slot) {
+  const float m = __uint_as_float(*slot);
+  if (!(m > 0.f)) return 1.f;
+  int e;
+  frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 14 - e);
+}
+// W[K][N] (row stride ldw) -> Wt_hi, Wt_lo [Npad][K] (K-major); rows n >= N are zero.
+template <bool F16>
 __global__ void split_weight_kernel(const float* __restrict__ W, int64_t ldw, int K, int N, int Npad,
-                                    float* __restrict__ hi, float* __restrict__ lo) {
+                                    void* __restrict__ hi_, void* __restrict__ lo_, float* __restrict__ slot) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  float scale = 1.f;
+  if (F16) {
+    scale = f16_weight_scale(reinterpret_cast<const unsigned*>(slot));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { slot[1] = 1.f / scale; slot[2] = scale; }
+  }
   for (int i = ty; i < 32; i += 8) {
     const int k = k0 + i, n = n0 + tx;
-    tile[i][tx] = (k < K && n < N) ? W[(int64_t)k * ldw + n] : 0.f;
+    tile[i][tx] = (k < K && n < N) ? W[(int64_t)k * ldw + n] * scale : 0.f;
   }
   __syncthreads();
   for (int i = ty; i < 32; i += 8) {
     const int n = n0 + i, k = k0 + tx;
     if (n < Npad && k < K) {
       const float w = tile[tx][i];
-      const float h = rna_tf32(w);
-      hi[(int64_t)n * K + k] = h;
-      lo[(int64_t)n * K + k] = rna_tf32(w - h);
+      if (F16) {
+        __half h, l;
+        split_f16(w, h, l);
+        reinterpret_cast<__half*>(hi_)[(int64_t)n * K + k] = h;
+        reinterpret_cast<__half*>(lo_)[(int64_t)n * K + k] = l;
+      } else {
+        const float h = rna_tf32(w);
+        reinterpret_cast<float*>(hi_)[(int64_t)n * K + k] = h;
+        reinterpret_cast<float*>(lo_)[(int64_t)n * K + k] = rna_tf32(w - h);
+      }
     }
   }
 }
@@ -357,17 +544,19 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows][cols] with row stride ld (floats); box = 32 floats x box_rows, 128B swizzle
-static int make_map(CUtensorMap* tm, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// 2-D tensor [rows][cols] of fp32 (or fp16) with row stride ld (elements); box = one 128-byte swizzle
+// row (32 floats / 64 halves) x box_rows
+static int make_map(CUtensorMap* tm, const void* base, bool half, uint64_t rows, uint64_t cols, uint64_t ld,
+                    uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -2;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint64_t strides[1] = {ld * (half ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(half ? 64 : 32), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
@@ -383,51 +572,81 @@ static int num_sms() {
 
 }  // namespace tc
 
-int gemm_tc_supported(int N, int K) { return N >= 1 && K >= tc::BLOCK_K && K % tc::BLOCK_K == 0; }
+int gemm_tc_supported(int N, int K) { return N >= 1 && K >= 32 && K % 32 == 0; }
+int gemm_tc_f16_ok(int K) { return K >= 64 && K % 64 == 0; }
 
-int split_weight_tc(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream) {
-  const int Npad = (N + 15) & ~15;
+int weight_maxabs_tc(const float* W, int64_t ldw, int K, int N, float* scale_slot, cudaStream_t stream) {
+  const int64_t n = (int64_t)K * N;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 296) blocks = 296;
+  tc::weight_maxabs_kernel<<<blocks, 256, 0, stream>>>(W, ldw, K, N, reinterpret_cast<unsigned*>(scale_slot));
+  return (int)cudaGetLastError();
+}
+
+// pad_rows != 0: rows N..Npad-1 (Npad = N rounded up to 16) are written as zeros; otherwise exactly N
+// rows are written so that blocks can be stacked.
+int split_weight_tc(const float* W, int64_t ldw, int K, int N, int pad_rows, void* Wt_hi, void* Wt_lo,
+                    float* scale_slot, int f16, cudaStream_t stream) {
+  const int Npad = pad_rows ? ((N + 15) & ~15) : N;
   dim3 grid((K + 31) / 32, (Npad + 31) / 32);
-  tc::split_weight_kernel<<<grid, 256, 0, stream>>>(W, ldw, K, N, Npad, Wt_hi, Wt_lo);
+  if (f16) tc::split_weight_kernel<true><<<grid, 256, 0, stream>>>(W, ldw, K, N, Npad, Wt_hi, Wt_lo, scale_slot);
+  else tc::split_weight_kernel<false><<<grid, 256, 0, stream>>>(W, ldw, K, N, Npad, Wt_hi, Wt_lo, scale_slot);
   return (int)cudaGetLastError();
 }
 
-// same, but writes exactly N rows (no zero pad rows) so that blocks can be stacked
-int split_weight_tc_rows(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream) {
-  dim3 grid((K + 31) / 32, (N + 31) / 32);
-  tc::split_weight_kernel<<<grid, 256, 0, stream>>>(W, ldw, K, N, N, Wt_hi, Wt_lo);
-  return (int)cudaGetLastError();
-}
-
-int gemm_tc(const float* A, const float* Wt_hi, const float* Wt_lo, const float* bias, float* C, int64_t M, int N,
-            int K, int64_t ldc, int rpg, int accumulate, cudaStream_t stream) {
+int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* bias, const float* inv_scale, float* C,
+            int64_t M, int N, int K, int64_t ldc, int rpg, int f16, int merged, cudaStream_t stream) {
   if (M <= 0) return 0;
-  if (!gemm_tc_supported(N, K) || accumulate || M > 0x7fffff00LL) return -2;
+  if (!gemm_tc_supported(N, K) || (f16 && !gemm_tc_f16_ok(K)) || M > 0x7fffff00LL) return -2;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wt_hi) & 15) ||
       (reinterpret_cast<uintptr_t>(Wt_lo) & 15))
     return -1;
   const int Npad = (N + 15) & ~15;
   CUtensorMap tmA, tmBh, tmBl, tmC;
   int rc;
-  if ((rc = tc::make_map(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, tc::BLOCK_M))) return rc;
-  if ((rc = tc::make_map(&tmBh, Wt_hi, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N))) return rc;
-  if ((rc = tc::make_map(&tmBl, Wt_lo, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N))) return rc;
+  if ((rc = tc::make_map(&tmA, A, false, (uint64_t)M, (uint64_t)K, (uint64_t)K, tc::BLOCK_M))) return rc;
+  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N))) return rc;
+  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N))) return rc;
   const int tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 4) == 0) ? 1 : 0;
   if (tma_store) {
-    if ((rc = tc::make_map(&tmC, C, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32))) return rc;
+    if ((rc = tc::make_map(&tmC, C, false, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32))) return rc;
   } else {
     tmC = tmA;  // unused
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((N + tc::BLOCK_N - 1) / tc::BLOCK_N);
   const int sms = tc::num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));
-  tc::gemm_tc_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBh, tmBl, tmC, bias, C, M, N, K, ldc, rpg, tma_store);
+  static const bool want_prof = getenv("DH_GEMM_PROF") != nullptr;
+  unsigned long long* prof = nullptr;
+  if (want_prof) {
+    static unsigned long long* buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 32 * sizeof(unsigned long long));
+    cudaMemsetAsync(buf, 0, 32 * sizeof(unsigned long long), stream);
+    prof = buf;
+  }
+  if (f16)
+    tc::gemm_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K, ldc, rpg, tma_store, merged, prof);
+  else
+    tc::gemm_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K, ldc, rpg, tma_store, merged, prof);
+  if (want_prof) {
+    unsigned long long h[32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    const double g = (double)grid.x, tp = (double)tiles / g;
+    fprintf(stderr, "[gemm_tc M=%lld N=%d f16=%d] per CTA: tiles %.1f | total cyc %.0f | producer wait empty %.0f | "
+            "mma wait tmem_empty %.0f full %.0f split %.0f | splitter wait full %.0f work %.0f | epi wait tmem_full %.0f drain %.0f "
+            "[tmem ld+wait %.0f, math+bias %.0f, wait_group.read %.0f, st.shared+fence %.0f, tma issue %.0f]\n",
+            (long long)M, N, f16, tp, h[11] / g, h[0] / g, h[1] / g, h[2] / g, h[3] / g, h[4] / g, h[5] / g, h[6] / g, h[7] / g,
+            h[16] / g, h[17] / g, h[18] / g, h[19] / g, h[20] / g);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -9,13 +9,20 @@ int gemm_simt(const float* A, const float* B, const float* bias, float* C, int64
               int64_t a_sm, int64_t a_sk, int64_t b_sk, int64_t b_sn, int64_t ldc, int rpg, int accumulate,
               int split_k, cudaStream_t stream);
 
-// ---- gemm_tc.cu (tcgen05 3xTF32): C[M,N] = A[M,K] @ W[K,N] (+bias on value rows) (+C)
-//      Wt_hi / Wt_lo are the pre-split, K-major (transposed, [N][K]) copies of W.
+// ---- gemm_tc.cu (tcgen05, two-piece operand split): C[M,N] = A[M,K] @ W[K,N] * (*inv_scale) (+bias on value rows)
+//      Wt_hi / Wt_lo are the pre-split, K-major (transposed, [Npad][K]) copies of W: TF32-valued fp32
+//      (f16 = 0) or fp16 with a per-slot power-of-two scale (f16 = 1; needs K % 64 == 0).
+//      merged = 1: one TMEM accumulator per tile, double-buffered (epilogue overlaps the next tile);
+//      merged = 0: separate main / correction accumulators (fewer truncating additions, no overlap).
+//      scale slot = 3 floats {max|W| bits, 1/scale, scale}; zero it, run weight_maxabs_tc over every
+//      block stacked into the slot, then split_weight_tc each block.
 int gemm_tc_supported(int N, int K);
-int gemm_tc(const float* A, const float* Wt_hi, const float* Wt_lo, const float* bias, float* C, int64_t M,
-            int N, int K, int64_t ldc, int rpg, int accumulate, cudaStream_t stream);
-int split_weight_tc(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
-int split_weight_tc_rows(const float* W, int64_t ldw, int K, int N, float* Wt_hi, float* Wt_lo, cudaStream_t stream);
+int gemm_tc_f16_ok(int K);
+int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* bias, const float* inv_scale, float* C,
+            int64_t M, int N, int K, int64_t ldc, int rpg, int f16, int merged, cudaStream_t stream);
+int weight_maxabs_tc(const float* W, int64_t ldw, int K, int N, float* scale_slot, cudaStream_t stream);
+int split_weight_tc(const float* W, int64_t ldw, int K, int N, int pad_rows, void* Wt_hi, void* Wt_lo,
+                    float* scale_slot, int f16, cudaStream_t stream);
 
 // ---- net_kernels.cu
 struct NetDims {

@@ -24,12 +24,14 @@ struct dh_plan {
   std::vector<LayerOff> layer;
   int64_t orb_re_k, orb_re_b, orb_im_k, orb_im_b, ee_par;
   double* d_normfac;
-  int gemm_impl;  // 0 = SIMT, 1 = tcgen05 3xTF32
+  int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
+  int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators
+  int tc_f16;     // tcgen05 path: 1 = kind::f16 pieces (D % 64 == 0), 0 = kind::tf32 pieces
   // prepared (pre-split, transposed) weights for the tcgen05 path
   float* prep;            // device buffer owned by the plan
   size_t prep_floats;
   const float* prep_src;  // params pointer the preparation was made from
-  struct Slot { int Nout; size_t hi, lo, bias; };  // float offsets into prep (bias: SIZE_MAX = none)
+  struct Slot { int Nout; size_t hi, lo, bias, scale; };  // float offsets into prep (bias: SIZE_MAX = none); scale: 3 floats
   std::vector<Slot> slots;  // per layer: qkv, o, d1, d2, od (= o folded into d1) ; last: orbitals (re | im)
   size_t w0qkv;             // float offset into prep: [4][3D] = W0 @ (Wq|Wk|Wv) of layer 0 (fp32)
   size_t fold_tmp;          // float offset into prep: [D][D] scratch for Wo @ W1 (fp32)
@@ -123,8 +125,8 @@ static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C,
                            cudaStream_t s) {
   const dh_plan::Slot& sl = p->slots[slot];
   ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * sl.Nout * p->D, s);
-  return gemm_tc(A, p->prep + sl.hi, p->prep + sl.lo, sl.bias == SIZE_MAX ? nullptr : p->prep + sl.bias, C, rows,
-                 sl.Nout, p->D, ldc, R, 0, s);
+  return gemm_tc(A, p->prep + sl.hi, p->prep + sl.lo, sl.bias == SIZE_MAX ? nullptr : p->prep + sl.bias,
+                 p->tc_f16 ? p->prep + sl.scale + 1 : nullptr, C, rows, sl.Nout, p->D, ldc, R, p->tc_f16, p->tc_merged, s);
 }
 
 // SIMT path: C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
