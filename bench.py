@@ -33,10 +33,21 @@ UNIT = "walker local-energy evals/s"
 
 
 def flops_local_energy_per_walker(N, L, K, D=256, nl=2):
-    """Algorithmic flops of the dense contractions as executed (R = 2N+8 rows, no block-diagonal
-    shortcut): 2*R*N*D*(nl*6*D + 2*L*N*K).  DESIGN.md 'Measurement'."""
+    """Flops of the dense contractions one local-energy evaluation executes here (R = 2N+8 jet rows;
+    MHA-out folded into the Dense that follows it: 5 D^2 per layer instead of 6; layer-0 q|k|v taken
+    straight from the 4 input features): 2*R*N*D*((5 nl - 3)*D + 2*L*N*K).  DESIGN.md section 5."""
     R = 2 * N + 8
-    return 2.0 * R * N * D * (nl * 6 * D + 2 * L * N * K)
+    return 2.0 * R * N * D * ((5 * nl - 3) * D + 2 * L * N * K)
+
+
+def gemm_traffic_per_launch():
+    """dram bytes (read + write) per launch of the dominant kernel from the committed ncu --set full
+    summary (profiles/r1_gemm_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+            return json.load(f)["avg_dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -129,7 +140,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 32
+    sample = 64
     val, spstep, cores = cpu_reference_local_energy(sample, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -242,17 +253,19 @@ def run_ours(args):
     peak = peaks["bf16_tflops_sustained"]
     roofline = {
         "bound": "tensor", "kernel": "dense contraction (dh::gemm_*)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak, "traffic": gemm_traffic_per_launch(),
         "launches": g["count"], "avg_launch_ms": g["ms"] / max(g["count"], 1),
         "share_of_step": g["ms"] / sum(v["ms"] for v in prof.values()),
-        "peak_source": peaks["source"] + ", dense bf16 sustained; fp32-accurate 3xTF32 can reach at most 1/6 of it",
+        "peak_source": peaks["source"] + ", dense bf16 sustained. fp32 accuracy costs 3 fp16-rate MMAs (hi*hi, lo*hi, hi*lo) per "
+                       "algorithmic MAC, so the attainable frac is 1/3; `achieved` counts algorithmic flops (2MNK per launch)",
+        "tensor_pipe_frac_incl_split": 3.0 * achieved / peak,
         "per_category_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
     }
 
     if rank == 0:
         cpu = None
         if world == 1:
-            sample = 64
+            sample = 256
             v, sps, cores = cpu_reference_local_energy(sample, steps=1, warmup=0)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{sample} walkers of the same workload, one pass ({sps:.1f} s); torch-CPU restatement of the reference "

@@ -238,6 +238,67 @@ def test_gemm_simt(nat):
         assert (out - ref).abs().max() / ref.abs().max() < 2e-6
 
 
+@pytest.mark.parametrize("impl,tol", [(1, 3e-6), (2, 3e-6), (3, 2e-6)])
+def test_gemm_tcgen05(nat, impl, tol):
+    """tcgen05 contraction, all three variants (1: fp16 pieces, one accumulator per tile; 2: tf32 pieces;
+    3: fp16 pieces, separate main/correction accumulators) on ragged shapes, vs fp64."""
+    torch.manual_seed(3)
+    for (M, N, K, rpg) in [(128, 256, 256, 1), (300, 256, 256, 1), (1000, 768, 256, 4), (77, 48, 256, 3), (129, 816, 256, 32),
+                           (64, 18, 32, 1), (5000, 96, 64, 1), (148 * 128 * 2 + 17, 256, 256, 32), (20000, 816, 256, 32)]:
+        A, W, b = torch.randn(M, K, device=DEV), torch.randn(K, N, device=DEV) / 16, torch.randn(N, device=DEV)
+        out = nat.gemm(A, W, b, rpg, impl=impl).double()
+        ref = A.double() @ W.double()
+        ref[::rpg] += b.double()
+        assert ((out - ref).abs().max() / ref.abs().max()).item() < tol, (M, N, K, rpg)
+
+
+def test_gemm_tcgen05_dynamic_range(nat):
+    """fp16 pieces: rows spanning 1e-4 .. 1e4 keep fp32-level accuracy relative to their own scale
+    (power-of-two weight scale, gradual underflow of the low piece); values beyond the fp16 range
+    saturate instead of overflowing; NaN propagates."""
+    torch.manual_seed(4)
+    M, K, N = 512, 256, 256
+    scale = 10.0 ** torch.linspace(-4, 4, M, device=DEV)[:, None]
+    A = torch.randn(M, K, device=DEV) * scale
+    W = torch.randn(K, N, device=DEV) * 1e-3
+    ref = A.double() @ W.double()
+    for impl in (1, 3):
+        out = nat.gemm(A, W, None, 1, impl=impl).double()
+        rowerr = (out - ref).abs().amax(1) / ref.abs().amax(1)
+        assert rowerr.max().item() < 1e-3 and rowerr.median().item() < 3e-6, (impl, rowerr.max().item(), rowerr.median().item())
+        big = rowerr[scale[:, 0] >= 1e-1]
+        assert big.max().item() < 3e-6, (impl, big.max().item())
+    A2 = torch.randn(128, K, device=DEV)
+    A2[3, 5] = 1e6      # beyond fp16: the piece saturates, the result stays finite
+    A2[7, 9] = float("nan")
+    out = nat.gemm(A2, W, None, 1, impl=1)
+    assert torch.isfinite(out[3]).all() and torch.isnan(out[7]).all() and torch.isfinite(out[:3]).all()
+
+
+def test_tcgen05_path_matches_simt_path(nat, monkeypatch):
+    """The tensor-core path (folded MHA-out . Dense, layer-0 q|k|v from the features, split operands) and
+    the plain fp32-FMA path compute the same network."""
+    cfg = OP.NetCfg(**CONFIGS["c2"])
+    p64 = OP.init_params(cfg, 5, torch.float64, 0.1)
+    flat = OP.flatten_params(p64).float().to(DEV)
+    outs = {}
+    for impl in ("simt", "tc", "tf32"):
+        if impl == "tc":
+            monkeypatch.delenv("DH_GEMM_IMPL", raising=False)
+        else:
+            monkeypatch.setenv("DH_GEMM_IMPL", impl)
+        plan = make_plan(nat, cfg)
+        x = plan.init_walkers(40, seed=9)
+        outs[impl] = plan.local_energy(flat, x)
+    for impl in ("tc", "tf32"):
+        for k in ("energy", "kinetic", "angular_momentum_square"):
+            a, b = outs[impl][k], outs["simt"][k]
+            rel = ((a - b).abs() / b.abs().clamp(min=1.0)).median().item()
+            assert rel < 5e-6, (impl, k, rel)
+        d = outs[impl]["logpsi"] - outs["simt"]["logpsi"]
+        assert d.real.abs().max().item() < 1e-4 and phase_diff(d.imag.cpu().double(), torch.zeros(40, dtype=torch.float64)).abs().max() < 1e-4
+
+
 # --------------------------------------------------------------------------------- MCMC
 def test_mcmc_proposal_and_decisions(nat):
     cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c2"], 256, burn=0)
