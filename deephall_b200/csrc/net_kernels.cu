@@ -66,8 +66,32 @@ int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDim
   return features_linear(x, W0, nullptr, h, d.D, B, d, s);
 }
 
+// value-only form (R = 1): one warp per (walker, electron), eight per block
+__global__ void __launch_bounds__(256)
+features_value_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                      float* __restrict__ out, int Nout, int64_t rows, NetDims dm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float st, ct, sp, cp;
+  sincosf(x[row * 2], &st, &ct);
+  sincosf(x[row * 2 + 1], &sp, &cp);
+  const float f0 = ct, f1 = st * cp, f2 = st * sp, f3 = ((int)(row % dm.N) < dm.n_up) ? 1.f : -1.f;  // (z, x, y, spin)
+  float* o = out + row * Nout;
+  for (int d = lane; d < Nout; d += 32) {
+    float v = fmaf(f0, W[d], fmaf(f1, W[Nout + d], fmaf(f2, W[2 * Nout + d], f3 * W[3 * Nout + d])));
+    if (bias != nullptr) v += bias[d];
+    o[d] = v;
+  }
+}
+
 int features_linear(const float* x, const float* W, const float* bias, float* out, int Nout, int64_t B, NetDims d,
                     cudaStream_t s) {
+  if (d.R == 1) {
+    const int64_t rows = B * d.N;
+    features_value_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, W, bias, out, Nout, rows, d);
+    return (int)cudaGetLastError();
+  }
   int threads = Nout >= 256 ? 256 : ((Nout + 31) / 32 * 32);
   features_dense0_kernel<<<(unsigned)(B * d.N), threads, d.R * 4 * sizeof(float), s>>>(x, W, bias, out, Nout, d);
   return (int)cudaGetLastError();
@@ -257,52 +281,78 @@ int residual_layernorm(const float* a, const float* b, const float* scale, const
 }
 
 // =============================================================================================
-// value-only attention: one block per walker, one warp per (head, query).
+// value-only attention: one block of 256 threads per walker.
 // qkv rows: [q (D) | k (D) | v (D)], head h owns columns h*hd .. (h+1)*hd of each.
+//   stage q|k|v of the walker in shared memory (row stride 3D + 4 floats: conflict-free float4 reads)
+//   scores   thread = (head, query, key): one hd-long dot product
+//   softmax  thread = (head, query)
+//   output   thread = (query, head, 4 head-dim columns)
 // =============================================================================================
 constexpr int ATT_NMAX = 32;
 
 __global__ void __launch_bounds__(256)
 attention_value_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
-  extern __shared__ float sm[];  // [N][3D]
+  extern __shared__ __align__(16) float sm[];  // [N][3D + 4] then scores [H][N][N]
   const int N = dm.N, D = dm.D, H = dm.H, hd = dm.hd;
+  const int ld = 3 * D + 4;
+  float* sc = sm + N * ld;
   const int64_t b = blockIdx.x;
-  const float* src = qkv + b * N * 3 * D;
-  for (int t = threadIdx.x; t < N * 3 * D; t += blockDim.x) sm[t] = src[t];
+  const float4* src = reinterpret_cast<const float4*>(qkv + b * N * 3 * D);
+  const int row4 = 3 * D / 4;
+  for (int t = threadIdx.x; t < N * row4; t += blockDim.x) {
+    const int r = t / row4, c = t % row4;
+    *reinterpret_cast<float4*>(sm + r * ld + 4 * c) = src[t];
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const float scl = rsqrtf((float)hd);
-  for (int w = warp; w < H * N; w += nwarp) {
-    const int hh = w / N, i = w % N;
-    const float* q = sm + i * 3 * D + hh * hd;
-    float sc[ATT_NMAX];
+  for (int t = threadIdx.x; t < H * N * N; t += blockDim.x) {
+    const int j = t % N, i = (t / N) % N, hh = t / (N * N);
+    const float4* q = reinterpret_cast<const float4*>(sm + i * ld + hh * hd);
+    const float4* k = reinterpret_cast<const float4*>(sm + j * ld + D + hh * hd);
+    float p0 = 0.f, p1 = 0.f;
+    for (int d = 0; d < hd / 4; d += 2) {
+      const float4 a0 = q[d], b0 = k[d];
+      p0 = fmaf(a0.x, b0.x, p0); p0 = fmaf(a0.y, b0.y, p0); p0 = fmaf(a0.z, b0.z, p0); p0 = fmaf(a0.w, b0.w, p0);
+      if (d + 1 < hd / 4) {
+        const float4 a1 = q[d + 1], b1 = k[d + 1];
+        p1 = fmaf(a1.x, b1.x, p1); p1 = fmaf(a1.y, b1.y, p1); p1 = fmaf(a1.z, b1.z, p1); p1 = fmaf(a1.w, b1.w, p1);
+      }
+    }
+    sc[t] = (p0 + p1) * scl;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < H * N; t += blockDim.x) {
+    float* s = sc + t * N;
     float mx = -INFINITY;
-#pragma unroll 4
-    for (int j = 0; j < N; ++j) {
-      const float* k = sm + j * 3 * D + D + hh * hd;
-      float p = 0.f;
-      for (int d = lane; d < hd; d += 32) p = fmaf(q[d], k[d], p);
-      p = warp_sum(p) * scl;
-      sc[j] = p;
-      mx = fmaxf(mx, p);
-    }
+    for (int j = 0; j < N; ++j) mx = fmaxf(mx, s[j]);
     float Z = 0.f;
-    for (int j = 0; j < N; ++j) { sc[j] = __expf(sc[j] - mx); Z += sc[j]; }
+    for (int j = 0; j < N; ++j) { const float e = expf(s[j] - mx); s[j] = e; Z += e; }
     const float iz = 1.f / Z;
-    for (int d = lane; d < hd; d += 32) {
-      float acc = 0.f;
-      for (int j = 0; j < N; ++j) acc = fmaf(sc[j] * iz, sm[j * 3 * D + 2 * D + hh * hd + d], acc);
-      o[(b * N + i) * D + hh * hd + d] = acc;
+    for (int j = 0; j < N; ++j) s[j] *= iz;
+  }
+  __syncthreads();
+  const int hd4 = hd / 4;
+  for (int t = threadIdx.x; t < N * H * hd4; t += blockDim.x) {
+    const int d4 = t % hd4, hh = (t / hd4) % H, i = t / (hd4 * H);
+    const float* p = sc + (hh * N + i) * N;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < N; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(sm + j * ld + 2 * D + hh * hd + 4 * d4);
+      const float pj = p[j];
+      acc.x = fmaf(pj, v.x, acc.x); acc.y = fmaf(pj, v.y, acc.y); acc.z = fmaf(pj, v.z, acc.z); acc.w = fmaf(pj, v.w, acc.w);
     }
+    *reinterpret_cast<float4*>(o + (b * N + i) * D + hh * hd + 4 * d4) = acc;
   }
 }
 
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
-  if (d.N > ATT_NMAX) return -2;
-  size_t smem = (size_t)d.N * 3 * d.D * sizeof(float);
-  if (smem > 48 * 1024) {
+  if (d.N > ATT_NMAX || (d.hd % 4) != 0) return -2;
+  const size_t smem = ((size_t)d.N * (3 * d.D + 4) + (size_t)d.H * d.N * d.N) * sizeof(float);
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(attention_value_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    attr_smem = smem;
   }
   attention_value_kernel<<<(unsigned)B, 256, smem, s>>>(qkv, o, d);
   return (int)cudaGetLastError();

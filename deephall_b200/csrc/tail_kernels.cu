@@ -129,8 +129,77 @@ orbital_contract_kernel(const float* __restrict__ c, const float* __restrict__ x
   }
 }
 
+// Value-only form (R = 1): one warp per (walker, electron), eight per block.
+//   env[m] = sqrt(C(2Q,m)) cos^m(theta/2) sin^(2Q-m)(theta/2) e^{i (m - Q) phi}: magnitudes by repeated squaring
+//   in double (exponents reach 2Q), phase angle reduced in double and evaluated in fp32;
+//   M[i][j,kd] = sum_m c[m][j,kd] env[m] with lanes = (m-group, column), coalesced 4-byte loads.
+__device__ inline double dpow_int(double z, int e) {
+  double r = 1.0;
+  while (e) {
+    if (e & 1) r *= z;
+    z *= z;
+    e >>= 1;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+orbital_value_kernel(const float* __restrict__ c, const float* __restrict__ x, const double* __restrict__ normfac,
+                     float* __restrict__ Mj, int64_t rows, TailDims dm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = dm.N, L = dm.L, K = dm.K, twoQ = dm.twoQ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cplx* env = reinterpret_cast<cplx*>(smraw) + warp * L;
+  const int64_t bi = (int64_t)blockIdx.x * 8 + warp;
+  if (bi >= rows) return;  // whole warps leave; only __syncwarp is used below
+  const int64_t b = bi / N;
+  const int i = (int)(bi % N);
+  const double phi = (double)x[bi * 2 + 1];
+  double sh = 0.0, ch = 0.0;
+  if (lane == 0) sincos(0.5 * (double)x[bi * 2], &sh, &ch);
+  sh = __shfl_sync(0xffffffffu, sh, 0);
+  ch = __shfl_sync(0xffffffffu, ch, 0);
+  for (int m = lane; m < L; m += 32) {
+    const double mag = normfac[m] * dpow_int(ch, m) * dpow_int(sh, twoQ - m);
+    double psi = (double)(2 * m - twoQ) * 0.5 * phi;
+    psi -= 6.283185307179586476925287 * rint(psi * 0.15915494309189533576888);
+    float sp, cp;
+    sincosf((float)psi, &sp, &cp);
+    env[m] = make_float2((float)(mag * (double)cp), (float)(mag * (double)sp));
+  }
+  __syncwarp();
+  const int NK = N * K, LNK = L * NK;
+  const float* cr = c + bi * 2 * (int64_t)LNK;
+  for (int jk0 = 0; jk0 < NK; jk0 += 32) {
+    const int width = NK - jk0 < 32 ? NK - jk0 : 32;
+    int NKp = 1;
+    while (NKp < width) NKp <<= 1;
+    const int G = 32 / NKp, g = lane / NKp, jl = lane % NKp;
+    cplx acc = cmake(0.f, 0.f);
+    if (jl < width) {
+      const float* p = cr + jk0 + jl;
+      for (int m = g; m < L; m += G) acc = cfma(cmake(p[m * NK], p[LNK + m * NK]), env[m], acc);
+    }
+    for (int off = NKp; off < 32; off <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    }
+    if (lane < width) {
+      const int jk = jk0 + lane, j = jk / K, kd = jk % K;
+      float* dst = Mj + ((((b * K + kd)) * N + i) * N + j) * 2;
+      dst[0] = acc.x;
+      dst[1] = acc.y;
+    }
+  }
+}
+
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s) {
+  if (d.R == 1) {
+    const int64_t rows = B * d.N;
+    orbital_value_kernel<<<(unsigned)((rows + 7) / 8), 256, 8 * d.L * sizeof(cplx), s>>>(c, x, normfac, Mj, rows, d);
+    return (int)cudaGetLastError();
+  }
   size_t smem = 2 * d.L * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
   orbital_contract_kernel<<<(unsigned)(B * d.N), 128, smem, s>>>(c, x, normfac, Mj, d);
   return (int)cudaGetLastError();

@@ -172,6 +172,10 @@ def timing(cfgkw, B):
         return e0.elapsed_time(e1) / n
     ms = t(lambda: plan.logpsi(flat, xd))
     print(f"{cfgkw} B={B}: logpsi {ms:.2f} ms -> {B / ms * 1e3:.3e} evals/s")
+    plan.profile_begin()
+    plan.logpsi(flat, xd)
+    pr = plan.profile_end()
+    print("   logpsi profile:", {k: (round(v['ms'], 3), v['count'], round(v['flops'] / max(v['ms'], 1e-9) / 1e9, 1)) for k, v in pr.items()})
     ms = t(lambda: plan.mcmc_sweep(flat, xd, 10, 0.1, seed=5))
     print(f"   mcmc 10 moves {ms:.2f} ms -> {B * 10 / ms * 1e3:.3e} walker-steps/s")
     ms = t(lambda: plan.local_energy(flat, xd), n=2)
