@@ -2,8 +2,10 @@
 // One block of 256 threads per (head, walker).  Rows per electron: R = 2N + 8 (common.cuh).
 //
 // Phase 1  score jets  s_ij^(r) = scale * sum_d [ q_i^(r) k_j^(0) + q_i^(0) k_j^(r) (+ 2 q_i^(r) k_j^(r) cross terms) ]
-//          register-tiled: one thread owns (row r, 3 queries, 6 keys) = 54 accumulators; q and k are
-//          staged 16 head-dim columns at a time in padded shared memory (conflict-free float4 reads).
+//          register-tiled: one thread owns (row r, 3 queries, 6 keys) = 54 accumulators; q and k stream
+//          through shared memory 8 head-dim columns at a time, double-buffered with cp.async so that the
+//          global-load latency of sub-chunk s+1 hides behind the FMAs of sub-chunk s (rows of 32 B, the
+//          16-byte half h of row n stored at half h ^ ((n >> 2) & 1): conflict-free float4 reads).
 // Phase 2  softmax jets (log-sum-exp Hessian = diag(p) - p p^T) in shared memory.
 // Phase 3  output jets o_i^(r) = sum_j [ p^(r) v^(0) + p^(0) v^(r) (+ cross terms) ]
 //          one thread owns (row r, 4 head-dim columns, 6 queries); the S-row cross term
@@ -13,32 +15,38 @@
 namespace dh {
 
 constexpr int AJ_THREADS = 256;
-constexpr int AJ_CH = 16;      // head-dim chunk staged in shared memory
-constexpr int AJ_STRIDE = 20;  // padded row stride of a staged chunk
+constexpr int AJ_CH = 16;      // head-dim columns per phase-3 step (two staged sub-chunks)
+constexpr int AJ_SUB = 8;      // head-dim columns per staged sub-chunk (one 32-byte row)
 constexpr int AJ_IB = 3, AJ_JB = 6, AJ_OB = 6;
 
 __host__ __device__ inline int aj_np(int N) { return (N + AJ_OB - 1) / AJ_OB * AJ_OB; }  // padded query count
 __host__ __device__ inline size_t aj_smem_floats(int N, int R) {
   const int NP = aj_np(N);
-  // qs, ks : [N*R][STRIDE] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [NP][CH]
-  return 2 * (size_t)N * R * AJ_STRIDE + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + (size_t)NP * AJ_CH;
+  // four staging regions [N*R][SUB] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [NP][CH]
+  return 4 * (size_t)N * R * AJ_SUB + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + (size_t)NP * AJ_CH;
 }
 size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R) * sizeof(float); }
 
-__device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict__ src, int64_t ld, int NR, int ch, int hd) {
-  for (int t = threadIdx.x; t < NR * 4; t += AJ_THREADS) {
-    const int row = t >> 2, f4 = t & 3;
-    const int dcol = ch * AJ_CH + f4 * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float* pp = src + row * ld + dcol;
-    if (dcol + 3 < hd) v = *reinterpret_cast<const float4*>(pp);
-    else {
-      if (dcol < hd) v.x = pp[0];
-      if (dcol + 1 < hd) v.y = pp[1];
-      if (dcol + 2 < hd) v.z = pp[2];
+// asynchronous copy of head-dim columns [sub*8, sub*8+8) of NR rows into a staging region
+__device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int64_t ld, int NR, int sub, int hd) {
+  for (int t = threadIdx.x; t < NR * 2; t += AJ_THREADS) {
+    const int row = t >> 1, h = t & 1;
+    const int dcol = sub * AJ_SUB + h * 4;
+    float* d = dst + row * AJ_SUB + ((h ^ ((row >> 2) & 1)) << 2);
+    if (dcol < hd) {  // hd % 4 == 0: a 16-byte piece is entirely inside or entirely outside the head
+      const unsigned da = (unsigned)__cvta_generic_to_shared(d);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + row * ld + dcol) : "memory");
+    } else {
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    *reinterpret_cast<float4*>(dst + row * AJ_STRIDE + f4 * 4) = v;
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void stage_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void stage_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// float4 number f (0 or 1) of staged row `row`
+__device__ __forceinline__ float4 staged(const float* buf, int row, int f) {
+  return *reinterpret_cast<const float4*>(buf + row * AJ_SUB + ((f ^ ((row >> 2) & 1)) << 2));
 }
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
@@ -61,9 +69,9 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NR = N * R;
   Rows rw(N, true);
-  float* qs = smem;
-  float* ks = qs + (size_t)NR * AJ_STRIDE;
-  float* sj = ks + (size_t)NR * AJ_STRIDE;  // SJ(i,j,r)
+  // four staging regions: phase 1 uses (q, k) x 2 buffers, phase 3 two 16-column steps of v
+  auto stg = [&](int u) { return smem + (size_t)u * NR * AJ_SUB; };
+  float* sj = smem + (size_t)4 * NR * AJ_SUB;  // SJ(i,j,r)
   float* cr = sj + (size_t)N * R * NP;
   float* p0 = cr + (size_t)N * R * NP;      // [j][NP] (query index fastest)
   float* qq = p0 + N * NP;
@@ -76,6 +84,7 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   const float* vbase = qbase + 2 * D;
   const float scl = rsqrtf((float)hd);
   const int nchunk = (hd + AJ_CH - 1) / AJ_CH;
+  const int nsub = (hd + AJ_SUB - 1) / AJ_SUB;
   const int IBN = (N + AJ_IB - 1) / AJ_IB, JBN = (N + AJ_JB - 1) / AJ_JB, OBN = NP / AJ_OB;
 
   // zero the padded query slots so that vectorised reads of sj never see garbage
@@ -95,26 +104,35 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
     for (int a = 0; a < AJ_IB; ++a)
 #pragma unroll
       for (int c = 0; c < AJ_JB; ++c) { acc[a][c][0] = 0.f; acc[a][c][1] = 0.f; acc[a][c][2] = 0.f; }
-    for (int ch = 0; ch < nchunk; ++ch) {
-      __syncthreads();
-      stage_chunk(qs, qbase, ld, NR, ch, hd);
-      stage_chunk(ks, kbase, ld, NR, ch, hd);
+    __syncthreads();  // staging regions are free (previous pass / zero-fill above)
+    stage_async(stg(0), qbase, ld, NR, 0, hd);
+    stage_async(stg(1), kbase, ld, NR, 0, hd);  // (one commit group each: q and k of a sub-chunk = 2 groups)
+    for (int sb = 0; sb < nsub; ++sb) {
+      const float* qs = stg(2 * (sb & 1));
+      const float* ks = stg(2 * (sb & 1) + 1);
+      if (sb + 1 < nsub) {
+        stage_async(stg(2 * ((sb + 1) & 1)), qbase, ld, NR, sb + 1, hd);
+        stage_async(stg(2 * ((sb + 1) & 1) + 1), kbase, ld, NR, sb + 1, hd);
+        asm volatile("cp.async.wait_group 2;" ::: "memory");  // everything but the two groups just issued
+      } else {
+        stage_wait_all();
+      }
       __syncthreads();
       if (active) {
 #pragma unroll
-        for (int f = 0; f < AJ_CH; f += 4) {
+        for (int f = 0; f < AJ_SUB / 4; ++f) {
           float4 qr[AJ_IB], q0[AJ_IB];
 #pragma unroll
           for (int a = 0; a < AJ_IB; ++a) {
             const int i = min(i0 + a, N - 1);
-            qr[a] = *reinterpret_cast<const float4*>(qs + (i * R + r) * AJ_STRIDE + f);
-            q0[a] = *reinterpret_cast<const float4*>(qs + (i * R) * AJ_STRIDE + f);
+            qr[a] = staged(qs, i * R + r, f);
+            q0[a] = staged(qs, i * R, f);
           }
 #pragma unroll
           for (int c = 0; c < AJ_JB; ++c) {
             const int j = min(j0 + c, N - 1);
-            const float4 kr = *reinterpret_cast<const float4*>(ks + (j * R + r) * AJ_STRIDE + f);
-            const float4 k0 = *reinterpret_cast<const float4*>(ks + (j * R) * AJ_STRIDE + f);
+            const float4 kr = staged(ks, j * R + r, f);
+            const float4 k0 = staged(ks, j * R, f);
 #pragma unroll
             for (int a = 0; a < AJ_IB; ++a) {
               acc[a][c][0] = dot4(qr[a], k0, acc[a][c][0]);
@@ -124,6 +142,7 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
           }
         }
       }
+      __syncthreads();  // all reads of this buffer are done before it is refilled two iterations later
     }
     if (active) {
 #pragma unroll
@@ -200,11 +219,20 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   }
   // ------------------------------------------------------------------ phase 3: o = P V jets
   float* obase = o + b * NR * (int64_t)D + hh * hd;
-  float* vs = qs;  // staged v chunk
   const int rS = rw.S(), rT0 = rw.T(0), rD0 = rw.D(0);
+  // a 16-column step of v = two staged sub-chunks; steps are double-buffered over the four regions
+  __syncthreads();
+  stage_async(stg(0), vbase, ld, NR, 0, hd);
+  stage_async(stg(1), vbase, ld, NR, 1, hd);
   for (int ch = 0; ch < nchunk; ++ch) {
-    __syncthreads();
-    stage_chunk(vs, vbase, ld, NR, ch, hd);
+    const float* vpair = stg(2 * (ch & 1));  // sub-chunk u of this step at vpair + u * NR * AJ_SUB
+    if (ch + 1 < nchunk) {
+      stage_async(stg(2 * ((ch + 1) & 1)), vbase, ld, NR, 2 * (ch + 1), hd);
+      stage_async(stg(2 * ((ch + 1) & 1) + 1), vbase, ld, NR, 2 * (ch + 1) + 1, hd);
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+    } else {
+      stage_wait_all();
+    }
     __syncthreads();
     // ---- S-row cross term: xs[i][c] = 2 sum_j sum_k p_ij^(Jk) v_j^(Jk)[c] ; warp = (query block, float4), lanes = k
     for (int wi = warp; wi < OBN * 4; wi += AJ_THREADS / 32) {
@@ -215,7 +243,7 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
       for (int kk = lane; kk < 2 * N; kk += 32) {
         const int r = rw.J(kk);
         for (int j = 0; j < N; ++j) {
-          const float4 v = *reinterpret_cast<const float4*>(vs + (j * R + r) * AJ_STRIDE + f4 * 4);
+          const float4 v = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R + r, f4 & 1);
           const float2* pp = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
           const float2 pa = pp[0], pb = pp[1], pc = pp[2];
           axpy4(acc[0], pa.x, v); axpy4(acc[1], pa.y, v);
@@ -245,21 +273,21 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
       const bool isT = r >= rT0;
       const int rd = isT ? rD0 + (r - rT0) : 0;
       for (int j = 0; j < N; ++j) {
-        const float4 v0 = *reinterpret_cast<const float4*>(vs + (j * R) * AJ_STRIDE + f4 * 4);
+        const float4 v0 = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R, f4 & 1);
         const float2* pr = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
         const float2 a0 = pr[0], a1 = pr[1], a2 = pr[2];
         axpy4(acc[0], a0.x, v0); axpy4(acc[1], a0.y, v0);
         axpy4(acc[2], a1.x, v0); axpy4(acc[3], a1.y, v0);
         axpy4(acc[4], a2.x, v0); axpy4(acc[5], a2.y, v0);
         if (r != 0) {
-          const float4 vr = *reinterpret_cast<const float4*>(vs + (j * R + r) * AJ_STRIDE + f4 * 4);
+          const float4 vr = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R + r, f4 & 1);
           const float2* pz = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, 0));
           const float2 b0 = pz[0], b1 = pz[1], b2 = pz[2];
           axpy4(acc[0], b0.x, vr); axpy4(acc[1], b0.y, vr);
           axpy4(acc[2], b1.x, vr); axpy4(acc[3], b1.y, vr);
           axpy4(acc[4], b2.x, vr); axpy4(acc[5], b2.y, vr);
           if (isT) {
-            const float4 vd = *reinterpret_cast<const float4*>(vs + (j * R + rd) * AJ_STRIDE + f4 * 4);
+            const float4 vd = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R + rd, f4 & 1);
             const float2* pd = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, rd));
             const float2 c0 = pd[0], c1 = pd[1], c2 = pd[2];
             axpy4(acc[0], 2.f * c0.x, vd); axpy4(acc[1], 2.f * c0.y, vd);
@@ -288,6 +316,7 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
         }
       }
     }
+    __syncthreads();  // v buffers of this step and xs are free again
   }
 #undef SJ
 }
