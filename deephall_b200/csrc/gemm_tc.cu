@@ -5,23 +5,26 @@
 // Every operand x is written x = hi + lo with 11-bit-significand pieces and the product is taken as
 // hi*hi + lo*hi + hi*lo on the tensor cores with fp32 accumulation in tensor memory (the dropped
 // lo*lo term is 2^-22 relative).  Two instantiations of the same kernel:
-//   * kind::tf32 ("3xTF32"):  pieces are TF32 numbers, K step 8 per MMA, 32 K-elements per stage;
+//   * kind::tf32 ("3xTF32"):  pieces are TF32 numbers, K step 8 per MMA; 2-stage operand ring of 96 KB stages;
 //   * kind::f16  ("3xFP16"):  pieces are fp16 numbers -- the same 11-bit significand, so inside fp16's
 //     normal range the three products are bit-identical to the TF32 ones -- K step 16 per MMA at twice
-//     the TF32 rate, 64 K-elements per stage, half the operand bytes per flop.  fp16's narrow exponent
+//     the TF32 rate, half the operand bytes per flop, 4-stage operand ring of 48 KB stages.  fp16's narrow exponent
 //     range is handled by a per-matrix power-of-two weight scale (undone exactly in the epilogue),
 //     saturating conversions, and gradual underflow of `lo` (absolute error <= 2^-25, below fp32
-//     rounding of O(1) activations; oracle emulation in DESIGN.md).  Used when K % 64 == 0.
+//     rounding of O(1) activations; oracle emulation in DESIGN.md).
 // W is given pre-transposed ([Npad][K], K-major) and pre-split (split_weight_tc, once per parameter
 // update).  A is split inside the kernel: TMA lands the fp32 tile in shared memory (128B swizzle),
 // four warps rewrite it in place as the hi / lo operand tiles, one elected thread issues the MMAs.
 //
-// PERSISTENT kernel, one CTA per SM, 448 threads, CTA tile 128 x (<=256) x K:
-//   warp 0      TMA producer           (2-stage ring of 96 KB stages, runs ahead across tiles)
+// PERSISTENT kernel, one CTA per SM, 576 threads, CTA tile 128 x (<=256) x K:
+//   warp 0      TMA producer           (192 KB operand ring of 32-K-element stages, runs ahead across tiles)
 //   warp 1      TMEM allocator + MMA issuer
 //   warps 2..9   splitter              (fp32 -> hi / lo pieces, in shared memory)
-//   warps 10..13 epilogue              (tcgen05.ld -> scale, +bias -> swizzled smem staging -> TMA store)
-// so the loads and the split of tile t+1 overlap the drain and the stores of tile t.  The two
+//   warps 10..17 epilogue              (tcgen05.ld -> scale, +bias -> swizzled smem staging -> TMA store)
+// Launched as clusters of `cl` CTAs (1, 2 or 4) working on different row bands but the same column tile at the
+// same time: each CTA fetches 1/cl of the weight tile and TMA-multicasts it to the whole cluster, which cuts the
+// L2 -> SM traffic of the re-streamed weights (the measured limiter at cl = 1) by cl.
+// The loads and the split of tile t+1 overlap the drain and the stores of tile t.  The two
 // accumulators (main, correction) fill all 512 TMEM columns, so the first MMA of tile t+1 waits
 // until the epilogue has read tile t out of TMEM (not until its stores have landed).
 #include <cuda.h>
@@ -38,17 +41,18 @@ namespace tc {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
-constexpr int STAGES = 2;
-constexpr int A_BYTES = BLOCK_M * 128;  // 16 KB: one operand tile of 128 rows x one 128-byte swizzle row
-constexpr int B_BYTES = BLOCK_N * 128;  // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 96 KB
+constexpr int BLOCK_K = 32;             // K elements per pipeline stage (both kinds)
+constexpr int A_BYTES = BLOCK_M * 128;  // 16 KB: the fp32 A tile TMA lands (128 rows x 32 floats, 128B swizzle)
+constexpr int RING_BYTES = 192 * 1024;  // operand ring: tf32 pieces 2 stages x 96 KB, fp16 pieces 4 stages x 48 KB
+constexpr int MAX_STAGES = 4;
 constexpr int EPI_CHUNK = 32;                            // accumulator columns per epilogue step
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 4;        // 32 rows x 32 floats = 4 KB (one warp, one step)
-constexpr int EPI_BYTES = 4 * 2 * EPI_BUF_BYTES;         // 4 warps x 2 buffers = 32 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                             // two per TMEM lane quarter, alternating 32-column chunks
+constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES;     // one staging buffer per warp = 32 KB
+constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int SPLIT_WARPS = 8;
 constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;  // first epilogue warp
-constexpr int THREADS = 32 * (EPI_WARP0 + 4);  // 448
+constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 576
 constexpr int TMEM_COLS = 512;  // [0,256): hi*hi accumulator, [256,512): correction (lo*hi + hi*lo) accumulator
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,15 +84,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// same, delivered to the same shared-memory offsets (and signalling the same barrier offset) in every CTA of
+// the cluster selected by cta_mask
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1,
+                                               uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+template <bool SW64>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO), LBO unused (=1), version 1 (sm_100)
+  // K-major operand tile whose rows are one swizzle span: SWIZZLE_128B (layout 2, 8-row groups 1024 B apart) or
+  // SWIZZLE_64B (layout 4, 8-row groups 512 B apart); SBO = group stride, LBO unused (=1), version 1 (sm_100)
   const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
-  const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+  const uint32_t hi = ((SW64 ? 512u : 1024u) >> 4) | (1u << 14) | ((SW64 ? 4u : 2u) << 29);
   return (uint64_t)lo | ((uint64_t)hi << 32);
 }
 template <bool F16>
@@ -141,6 +156,15 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the barrier at the same offset in every CTA of cta_mask when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -172,43 +196,63 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // tma_store != 0: C is written through tmC (box 32 x 32 floats, 128B swizzle); otherwise (ldc not a
 // multiple of 4 floats, or misaligned C) by direct global stores.
-template <bool F16>
+template <bool F16, bool MERGED>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
-               int N, int K, int64_t ldc, int rpg, int tma_store, int merged, unsigned long long* __restrict__ prof) {
-  constexpr int BLOCK_K = F16 ? 64 : 32;  // K elements per stage
+               int N, int K, int64_t ldc, int rpg, int tma_store, int cl, unsigned long long* __restrict__ prof) {
+  constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
-  constexpr int A_TX_BYTES = BLOCK_M * BLOCK_K * 4;  // fp32 bytes TMA lands for A per stage
+  // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
+  //                fp16 pieces: [A hi 8 KB | A lo 8 KB (together = the landed fp32 tile) | B hi 16 KB | B lo 16 KB],
+  //                operand rows of 64 B (SWIZZLE_64B).
+  constexpr int STAGES = F16 ? 4 : 2;
+  constexpr int ROW_BYTES = F16 ? 64 : 128;            // operand tile row = BLOCK_K pieces
+  constexpr int AP_BYTES = BLOCK_M * ROW_BYTES;        // one A piece tile
+  constexpr int B_BYTES = BLOCK_N * ROW_BYTES;         // one B piece tile
+  constexpr int STAGE_BYTES = 2 * AP_BYTES + 2 * B_BYTES;
+  static_assert(STAGES * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
+  constexpr int A_TX_BYTES = A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  uint8_t* epi_smem = smem + RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
   // bars: [0..S) full, [S..2S) split, [2S..3S) empty, [3S] tmem_full, [3S+1] tmem_empty ; then tmem ptr
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto split_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto split_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   // merged == 0: main accumulator in TMEM columns [0,256), correction accumulator in [256,512), one tile in
   //              flight (the issuer waits for the drain of the previous tile);
   // merged != 0: all three products of a tile go to ONE accumulator, tiles alternate between columns [0,256)
   //              and [256,512), so tile t+1 is computed while tile t is drained -- at the price of 3x as many
   //              truncating additions into the accumulator ("accumulator modes").
-  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };
-  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };
+  auto tmem_full_bar = [&](int b) { return bar_base + 8u * (3 * MAX_STAGES + b); };
+  auto tmem_empty_bar = [&](int b) { return bar_base + 8u * (3 * MAX_STAGES + 2 + b); };
   auto a_hi = [&](int s) { return smem_base + s * STAGE_BYTES; };
-  auto a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + A_BYTES; };
-  auto b_hi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_BYTES; };
-  auto b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES; };
+  auto a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + AP_BYTES; };
+  auto b_hi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES; };
+  auto b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES + B_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = K / BLOCK_K;
   const int n_ntiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int64_t n_mtiles = (M + BLOCK_M - 1) / BLOCK_M;
-  const int64_t total_tiles = n_mtiles * n_ntiles;
+  // Tile order: a CTA takes 128-row bands blockIdx.x, blockIdx.x + gridDim.x, ... and walks all column tiles
+  // of a band before moving on, so a band's A rows are fetched from HBM once and re-read from L2.
+  // Every CTA of a cluster runs the same number of tiles (the weight multicast is collective): bands past
+  // the end of the matrix load zeros and their stores are clipped.
+  uint32_t crank = 0;
+  if (cl > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+  const int64_t cbase = (int64_t)blockIdx.x - crank;  // first CTA of this cluster
+  const int64_t my_bands = cbase < n_mtiles ? (n_mtiles - cbase + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_tiles = my_bands * n_ntiles;
+  auto band_of = [&](int64_t k) { return (int64_t)blockIdx.x + (k / n_ntiles) * gridDim.x; };
+  auto ntile_of = [&](int64_t k) { return (int)(k % n_ntiles); };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -218,11 +262,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(split_bar(s), SPLIT_WARPS);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), (uint32_t)cl);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), 4);
+      mbar_init(tmem_empty_bar(b), EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -233,6 +277,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (cl > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrival
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   // developer instrumentation (DH_GEMM_PROF=1): cycles each role spends blocked, summed over CTAs
@@ -252,18 +297,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (int)((tile / n_ntiles) * BLOCK_M);
-        const int n0 = (int)(tile % n_ntiles) * BLOCK_N;
+      for (int64_t tk = 0; tk < my_tiles; ++tk) {
+        const int m0 = (int)(band_of(tk) * BLOCK_M);
+        const int n0 = ntile_of(tk) * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           timed_wait(empty_bar(s), ph ^ 1, 0);
           mbar_arrive_expect_tx(full_bar(s), A_TX_BYTES + 2 * B_BYTES);
           tma_load_2d(a_hi(s), &tmA, full_bar(s), kb * BLOCK_K, m0);
-          if (F16) tma_load_2d(a_lo(s), &tmA, full_bar(s), kb * BLOCK_K + 32, m0);  // second 32-float half
-          tma_load_2d(b_hi(s), &tmBhi, full_bar(s), kb * BLOCK_K, n0);
-          tma_load_2d(b_lo(s), &tmBlo, full_bar(s), kb * BLOCK_K, n0);
+          if (cl == 1) {
+            tma_load_2d(b_hi(s), &tmBhi, full_bar(s), kb * BLOCK_K, n0);
+            tma_load_2d(b_lo(s), &tmBlo, full_bar(s), kb * BLOCK_K, n0);
+          } else {
+            // rows [crank * 256/cl, (crank+1) * 256/cl) of the weight tile, delivered to every CTA of the cluster
+            const int brows = BLOCK_N / cl;
+            tma_load_2d_mc(b_hi(s) + crank * brows * ROW_BYTES, &tmBhi, full_bar(s), kb * BLOCK_K, n0 + (int)crank * brows, cmask);
+            tma_load_2d_mc(b_lo(s) + crank * brows * ROW_BYTES, &tmBlo, full_bar(s), kb * BLOCK_K, n0 + (int)crank * brows, cmask);
+          }
         }
       }
       if (prof) { atomicAdd(prof + 0, pw[0]); atomicAdd(prof + 10, (unsigned long long)(clock64() - t_begin)); }
@@ -272,8 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       uint32_t it = 0, tl = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-        const int n0 = (int)(tile % n_ntiles) * BLOCK_N;
+      for (int64_t tk = 0; tk < my_tiles; ++tk, ++tl) {
+        const int n0 = ntile_of(tk) * BLOCK_N;
         int n_tile = N - n0 < BLOCK_N ? N - n0 : BLOCK_N;
         n_tile = (n_tile + 15) & ~15;  // Wt buffers are zero-padded to a multiple of 16 rows
         const uint32_t idesc = make_idesc<F16>(BLOCK_M, n_tile);
@@ -289,8 +340,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           timed_wait(full_bar(s), ph, 1);
           timed_wait(split_bar(s), ph, 2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t dah = make_smem_desc(a_hi(s)), dal = make_smem_desc(a_lo(s));
-          const uint64_t dbh = make_smem_desc(b_hi(s)), dbl = make_smem_desc(b_lo(s));
+          const uint64_t dah = make_smem_desc<F16>(a_hi(s)), dal = make_smem_desc<F16>(a_lo(s));
+          const uint64_t dbh = make_smem_desc<F16>(b_hi(s)), dbl = make_smem_desc<F16>(b_lo(s));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adv = (uint64_t)(k * 2);  // 32 operand bytes per MMA; start-address field is in 16-byte units
@@ -307,7 +358,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma<F16>(tmem_base, dah + adv, dbh + adv, idesc, (kb | k) != 0);
             }
           }
-          umma_commit(empty_bar(s));  // arrives when the MMAs reading this stage have completed
+          // arrives (in every CTA of the cluster: their TMA writes into this stage too) when the MMAs reading
+          // this stage have completed
+          if (cl == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
         }
         umma_commit(tmem_full_bar(ab));
       }
@@ -318,42 +371,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ splitter (8 warps)
     const int t = threadIdx.x - 64;  // 0..255
     uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int64_t tk = 0; tk < my_tiles; ++tk) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         if (t == 0) timed_wait(full_bar(s), ph, 0); else mbar_wait(full_bar(s), ph);
         const long long ts0 = (prof && t == 0) ? clock64() : 0;
         if (F16) {
-          // Two threads per tile row r: thread (r, h) converts the 32 floats k = 32h .. 32h+31, which TMA put
-          // in region h (16-byte piece j of row r at position j ^ (r & 7)).  The fp16 hi tile (64 halves =
-          // 128 B per row) replaces region 0 and the lo tile region 1, row r in place: only the two threads
-          // of a row touch its bytes, they sit in the same warp, and a __syncwarp separates reads from writes.
+          // Two threads per tile row r: thread (r, h) converts the 16 floats k = 16h .. 16h+15 of the landed fp32
+          // tile (row r = 128 B at r*128, 16-byte piece j at position j ^ (r & 7)).  The fp16 hi tile (rows of
+          // 64 B at r*64, piece c at position c ^ ((r >> 1) & 3)) overwrites the first 8 KB of the same region and
+          // the lo tile the second 8 KB, so all 256 splitter threads read before any of them writes.
           const int r = t >> 1, h = t & 1, sw = r & 7;
-          uint8_t* row0 = smem + s * STAGE_BYTES + r * 128;
-          uint8_t* row1 = row0 + A_BYTES;
-          const uint8_t* src = h ? row1 : row0;
-          float4 v[8];  // v[j] = 16-byte piece j ^ 4h of this thread's 32 floats: the two threads of a row
-                        // start 64 B apart, so a quarter-warp never hits a bank twice
+          uint8_t* reg = smem + s * STAGE_BYTES;
+          const uint8_t* src = reg + r * 128;
+          float4 v[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(src + (((j ^ (h << 2)) ^ sw) << 4));
-          __syncwarp();
+          for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(src + (((4 * h + j) ^ sw) << 4));
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * SPLIT_WARPS) : "memory");
+          const int sw2 = (r >> 1) & 3;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {  // v[2cc], v[2cc+1] are floats 8c .. 8c+7 with c = cc ^ 2h: fp16 piece 4h + c
-            const int c = cc ^ (h << 1);
-            const float4 a = v[2 * cc], b = v[2 * cc + 1];
+          for (int c = 0; c < 2; ++c) {  // piece 2h + c of the fp16 row = floats 8c .. 8c+7 of this thread
+            const float4 a = v[2 * c], b = v[2 * c + 1];
             uint4 hi, lo;
             split_f16x2(a.x, a.y, hi.x, lo.x);
             split_f16x2(a.z, a.w, hi.y, lo.y);
             split_f16x2(b.x, b.y, hi.z, lo.z);
             split_f16x2(b.z, b.w, hi.w, lo.w);
-            const int pos = ((4 * h + c) ^ sw) << 4;
-            *reinterpret_cast<uint4*>(row0 + pos) = hi;
-            *reinterpret_cast<uint4*>(row1 + pos) = lo;
+            const int pos = r * 64 + (((2 * h + c) ^ sw2) << 4);
+            *reinterpret_cast<uint4*>(reg + pos) = hi;
+            *reinterpret_cast<uint4*>(reg + AP_BYTES + pos) = lo;
           }
         } else {
           float4* hi = reinterpret_cast<float4*>(smem + s * STAGE_BYTES);
-          float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + A_BYTES);
+          float4* lo = reinterpret_cast<float4*>(smem + s * STAGE_BYTES + AP_BYTES);
 #pragma unroll
           for (int i = 0; i < A_BYTES / 16 / (32 * SPLIT_WARPS); ++i) {
             const int idx = t + i * 32 * SPLIT_WARPS;
@@ -372,16 +423,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (prof && t == 0) { atomicAdd(prof + 4, pw[0]); atomicAdd(prof + 5, pw[1]); }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int chalf = (warp - EPI_WARP0) >> 2;    // this warp takes the 32-column chunks with index % 2 == chalf
     const int row = q * 32 + lane;
     const bool lead = warp == EPI_WARP0 && lane == 0;
-    uint8_t* my_epi = epi_smem + (warp - EPI_WARP0) * 2 * EPI_BUF_BYTES;
-    uint32_t tl = 0, nstore = 0;
+    uint8_t* buf = epi_smem + (warp - EPI_WARP0) * EPI_BUF_BYTES;
+    uint32_t tl = 0;
     const float inv_scale = inv_scale_ptr ? __ldg(inv_scale_ptr) : 1.f;  // undoes the fp16 weight scale (power of two)
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
-      const int64_t m0 = (tile / n_ntiles) * BLOCK_M;
-      const int n0 = (int)(tile % n_ntiles) * BLOCK_N;
+    for (int64_t tk = 0; tk < my_tiles; ++tk, ++tl) {
+      const int64_t m0 = band_of(tk) * BLOCK_M;
+      const int n0 = ntile_of(tk) * BLOCK_N;
       int n_tile = N - n0 < BLOCK_N ? N - n0 : BLOCK_N;
       n_tile = (n_tile + 15) & ~15;
       const int64_t m = m0 + row;
@@ -394,24 +446,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long te0 = (prof && lead) ? clock64() : 0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * BLOCK_N;
-      for (int c0 = 0; c0 < n_tile; c0 += EPI_CHUNK) {
-        uint32_t v[32], w[32];
+      bool released = false;
+      for (int c0 = chalf * EPI_CHUNK; c0 < n_tile; c0 += 2 * EPI_CHUNK) {
+        uint32_t v[32];
         long long tp0 = (prof && lead) ? clock64() : 0, tp1;
 #define DH_LAP(slot) if (prof && lead) { tp1 = clock64(); pe[slot] += (unsigned long long)(tp1 - tp0); tp0 = tp1; }
+        float o[32];
         tmem_ld32(tbase + (uint32_t)c0, v);
-        if (!merged) tmem_ld32(tbase + (uint32_t)c0 + BLOCK_N, w);
         // lane j fetches bias column j of this step (coalesced)
         const float bl = (bias != nullptr && n0 + c0 + lane < N) ? __ldg(bias + n0 + c0 + lane) : 0.f;
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        DH_LAP(0)
-        float o[32];
+        if (!MERGED) {
+          uint32_t w[32];
+          tmem_ld32(tbase + (uint32_t)c0 + BLOCK_N, w);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(v[j]) + (merged ? 0.f : __uint_as_float(w[j]))) * inv_scale;
-        if (c0 + EPI_CHUNK >= n_tile) {
-          // last read of this tile's accumulators: hand TMEM back to the MMA issuer
+          for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(v[j]) + __uint_as_float(w[j])) * inv_scale;
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]) * inv_scale;
+        }
+        DH_LAP(0)
+        if (c0 + 2 * EPI_CHUNK >= n_tile) {
+          // this warp's last read of the tile's accumulators: hand TMEM back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
+          released = true;
           if (prof && lead) pw[1] += (unsigned long long)(clock64() - te0);
         }
         if (bias != nullptr && (rpg <= 1 || !tma_store)) {
@@ -424,11 +485,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         DH_LAP(1)
         if (tma_store) {
-          // staging buffer `nstore & 1` of this warp: wait until the TMA store issued two steps ago has read it
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          // the staging buffer of this warp: wait until the previous TMA store has read it
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
           DH_LAP(2)
-          uint8_t* buf = my_epi + (nstore & 1) * EPI_BUF_BYTES;
           // row `lane` of the 32 x 32 chunk; 16-byte piece j lives at piece position j ^ (lane & 7) (128B swizzle)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -450,7 +510,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmC, smem_u32(buf), n0 + c0, (int)(m0 + q * 32));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          ++nstore;
           DH_LAP(4)
         } else if (m < M) {
           float* crow = C + m * ldc + n0 + c0;
@@ -458,6 +517,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j)
             if (n0 + c0 + j < N) crow[j] = o[j];
         }
+      }
+      if (!released) {  // a narrow tile left this warp without a chunk
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
       }
     }
     if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -467,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (cl > 1) cluster_sync_all();  // no CTA leaves while a peer can still write into its shared memory
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
@@ -544,19 +609,20 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D tensor [rows][cols] of fp32 (or fp16) with row stride ld (elements); box = one 128-byte swizzle
-// row (32 floats / 64 halves) x box_rows
+// 2-D tensor [rows][cols] of fp32 (or fp16) with row stride ld (elements); box = 32 elements x box_rows, the box
+// row being one swizzle span (128 B of fp32 / 64 B of fp16)
 static int make_map(CUtensorMap* tm, const void* base, bool half, uint64_t rows, uint64_t cols, uint64_t ld,
                     uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -2;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * (half ? 2 : 4)};
-  cuuint32_t box[2] = {(cuuint32_t)(half ? 64 : 32), box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
@@ -573,7 +639,7 @@ static int num_sms() {
 }  // namespace tc
 
 int gemm_tc_supported(int N, int K) { return N >= 1 && K >= 32 && K % 32 == 0; }
-int gemm_tc_f16_ok(int K) { return K >= 64 && K % 64 == 0; }
+int gemm_tc_f16_ok(int K) { return K >= 32 && K % 32 == 0; }
 
 int weight_maxabs_tc(const float* W, int64_t ldw, int K, int N, float* scale_slot, cudaStream_t stream) {
   const int64_t n = (int64_t)K * N;
@@ -605,8 +671,6 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   CUtensorMap tmA, tmBh, tmBl, tmC;
   int rc;
   if ((rc = tc::make_map(&tmA, A, false, (uint64_t)M, (uint64_t)K, (uint64_t)K, tc::BLOCK_M))) return rc;
-  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N))) return rc;
-  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N))) return rc;
   const int tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 4) == 0) ? 1 : 0;
   if (tma_store) {
     if ((rc = tc::make_map(&tmC, C, false, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32))) return rc;
@@ -615,15 +679,27 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int64_t tiles = ((M + tc::BLOCK_M - 1) / tc::BLOCK_M) * ((N + tc::BLOCK_N - 1) / tc::BLOCK_N);
+  const int64_t bands = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
+  const int64_t tiles = bands * ((N + tc::BLOCK_N - 1) / tc::BLOCK_N);
   const int sms = tc::num_sms();
-  dim3 grid((unsigned)(tiles < sms ? tiles : sms));
+  // cluster size: DH_GEMM_CLUSTER = 1 | 2 | 4; small problems run un-clustered.  Default 1: with the
+  // 192 KB operand ring the kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic, and the
+  // multicast measured no faster at 2 and slower at 4 (profiles/r1_gemm_tc_notes.md).
+  static const int cl_env = getenv("DH_GEMM_CLUSTER") ? atoi(getenv("DH_GEMM_CLUSTER")) : 1;
+  int cl = (cl_env == 4 || cl_env == 2) ? cl_env : 1;
+  if (bands < 2 * sms) cl = 1;
+  int64_t g = bands < sms ? bands : sms;
+  g = g / cl * cl;
+  dim3 grid((unsigned)g);
+  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N / cl))) return rc;
+  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N / cl))) return rc;
   static const bool want_prof = getenv("DH_GEMM_PROF") != nullptr;
   unsigned long long* prof = nullptr;
   if (want_prof) {
@@ -632,10 +708,26 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
     cudaMemsetAsync(buf, 0, 32 * sizeof(unsigned long long), stream);
     prof = buf;
   }
-  if (f16)
-    tc::gemm_tc_kernel<true><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K, ldc, rpg, tma_store, merged, prof);
-  else
-    tc::gemm_tc_kernel<false><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K, ldc, rpg, tma_store, merged, prof);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = grid;
+  lc.blockDim = dim3(tc::THREADS);
+  lc.dynamicSmemBytes = tc::SMEM_BYTES;
+  lc.stream = stream;
+  cudaLaunchAttribute lattr[1];
+  lattr[0].id = cudaLaunchAttributeClusterDimension;
+  lattr[0].val.clusterDim.x = (unsigned)cl;
+  lattr[0].val.clusterDim.y = 1;
+  lattr[0].val.clusterDim.z = 1;
+  lc.attrs = lattr;
+  lc.numAttrs = 1;
+  cudaError_t le;
+#define DH_LAUNCH_TC(F, MG) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG>, tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, \
+                                                    N, K, ldc, rpg, tma_store, cl, prof)
+  if (f16) { if (merged) DH_LAUNCH_TC(true, true); else DH_LAUNCH_TC(true, false); }
+  else { if (merged) DH_LAUNCH_TC(false, true); else DH_LAUNCH_TC(false, false); }
+#undef DH_LAUNCH_TC
+  if (le != cudaSuccess) return (int)le;
   if (want_prof) {
     unsigned long long h[32];
     cudaStreamSynchronize(stream);

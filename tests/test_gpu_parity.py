@@ -275,6 +275,20 @@ def test_gemm_tcgen05_dynamic_range(nat):
     assert torch.isfinite(out[3]).all() and torch.isnan(out[7]).all() and torch.isfinite(out[:3]).all()
 
 
+def test_gemm_tcgen05_cluster_multicast():
+    """The cluster / TMA-multicast variant of the weight loads (DH_GEMM_CLUSTER is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cl in ("2", "4"):
+        env = dict(os.environ, DH_GEMM_CLUSTER=cl)
+        out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_gemm_quick.py")], env=env, cwd=root,
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and "GEMM ok" in out.stdout, (cl, out.stdout[-2000:], out.stderr[-2000:])
+
+
 def test_tcgen05_path_matches_simt_path(nat, monkeypatch):
     """The tensor-core path (folded MHA-out . Dense, layer-0 q|k|v from the features, split operands) and
     the plain fp32-FMA path compute the same network."""
