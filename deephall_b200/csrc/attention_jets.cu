@@ -59,10 +59,13 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
   acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
 }
 
+// NT > 0: the electron count is a compile-time constant (index arithmetic folds, j-loops unroll);
+// NT == 0: generic.
+template <int NT>
 __global__ void __launch_bounds__(AJ_THREADS, 2)
 attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
   extern __shared__ __align__(16) float smem[];
-  const int N = dm.N, R = dm.R, D = dm.D, hd = dm.hd;
+  const int N = NT > 0 ? NT : dm.N, R = 2 * N + 8, D = dm.D, hd = dm.hd;
   const int NP = aj_np(N);
   const int hh = blockIdx.x;
   const int64_t b = blockIdx.y;
@@ -325,14 +328,25 @@ int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_
   if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
   const size_t smem = attention_jets_smem(d);
   if (smem > 227 * 1024) return -2;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    attr_smem = smem;
-  }
   dim3 grid((unsigned)d.H, (unsigned)B);
-  attention_jets_kernel<<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);
+#define DH_AJ_LAUNCH(NT)                                                                                              \
+  do {                                                                                                                \
+    static size_t attr_smem = 0;                                                                                      \
+    if (smem > attr_smem) {                                                                                           \
+      cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      if (e != cudaSuccess) return (int)e;                                                                            \
+      attr_smem = smem;                                                                                               \
+    }                                                                                                                 \
+    attention_jets_kernel<NT><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                                             \
+  } while (0)
+  switch (d.N) {
+    case 6: DH_AJ_LAUNCH(6); break;
+    case 10: DH_AJ_LAUNCH(10); break;
+    case 12: DH_AJ_LAUNCH(12); break;
+    case 16: DH_AJ_LAUNCH(16); break;
+    default: DH_AJ_LAUNCH(0); break;
+  }
+#undef DH_AJ_LAUNCH
   return (int)cudaGetLastError();
 }
 
