@@ -22,11 +22,14 @@ __device__ void envelope_jets(float theta, float phi, int twoQ, const double* __
                               dcplx* upow, dcplx* vpow, cplx* env, int nslots) {
   const int L = twoQ + 1;
   const int tid = threadIdx.x;
-  double st, ct, sp, cp, sh, ch, sph, cph;
-  sincos((double)theta, &st, &ct);
-  sincos((double)phi, &sp, &cp);
-  sincos(0.5 * (double)theta, &sh, &ch);
-  sincos(0.5 * (double)phi, &sph, &cph);
+  // the four double-precision sincos are done once (threads 0..3) and shared through upow[0..3] scratch
+  __shared__ double trig[8];
+  if (tid < 4) {
+    const double ang = tid == 0 ? (double)theta : tid == 1 ? (double)phi : tid == 2 ? 0.5 * (double)theta : 0.5 * (double)phi;
+    sincos(ang, &trig[2 * tid], &trig[2 * tid + 1]);
+  }
+  __syncthreads();
+  const double st = trig[0], ct = trig[1], sp = trig[2], cp = trig[3], sh = trig[4], ch = trig[5], sph = trig[6], cph = trig[7];
   const dcplx u = make_double2(ch * cph, ch * sph);
   const dcplx v = make_double2(sh * cph, -sh * sph);
   if (tid < 2) {
