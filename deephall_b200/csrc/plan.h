@@ -72,8 +72,20 @@ struct FwdWs {
 
 static inline size_t al(size_t n) { return (n + 63) / 64 * 64; }  // 256-byte granules
 
+// Walkers per internal pass.  Default: as many as keep the pass's activation workspace near 6 GiB
+// (jets: 1024 at c3, 256 at c5 with 4 determinants), so the workspace does not grow with B.
 static inline int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
-  int64_t c = p->cfg.chunk_walkers > 0 ? p->cfg.chunk_walkers : (jets ? 1024 : 16384);
+  int64_t c = p->cfg.chunk_walkers;
+  if (c <= 0) {
+    const int R = jets ? 2 * p->N + 8 : 1;
+    const double per_walker = (double)p->N * R * (7.0 * p->D + 2.0 * p->LNK) * sizeof(float) +
+                              (double)p->K * R * p->N * p->N * 2 * sizeof(float);
+    c = (int64_t)(6.0 * 1024 * 1024 * 1024 / per_walker);
+    const int64_t cap = jets ? 1024 : 16384;
+    if (c > cap) c = cap;
+    c = c / 32 * 32;
+    if (c < 32) c = 32;
+  }
   return B < c ? B : c;
 }
 
