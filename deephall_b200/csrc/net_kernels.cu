@@ -101,7 +101,21 @@ int features_linear(const float* x, const float* W, const float* bias, float* ou
 // out = LayerNorm(a + b) or LayerNorm(a + tanh(b)), with jets.  One warp per (walker, electron);
 // lane l owns columns l, l+32, ...  (D <= 256, D % 32 == 0).
 // =============================================================================================
+#ifndef DH_TANH
+#define DH_TANH tanhf
+#endif
 constexpr int LN_VPL = 8;
+
+// tanh with absolute error < 2e-7 (odd polynomial below 0.3, 1 - 2/(e^{2|x|}+1) with the fast exponential above)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float ax = fabsf(x);
+  const float x2 = x * x;
+  const float p = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 0.021869488536155203f, -0.053968253968253971f), 0.13333333333333333f),
+                               -0.33333333333333331f), 1.0f);
+  const float e = __expf(2.0f * ax);
+  const float t = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+  return ax < 0.3f ? p : t;
+}
 
 template <bool TANH>
 __global__ void __launch_bounds__(128)
@@ -135,7 +149,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
     if (v < vpl) {
       float av = ga[lane + 32 * v], bv = gb[lane + 32 * v];
       if (TANH) {
-        float t = tanhf(bv);
+        float t = DH_TANH(bv);
         t1[v] = 1.f - t * t;
         t2[v] = -2.f * t * t1[v];
         bv = t;
@@ -267,9 +281,77 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   }
 }
 
+// value-only form (R = 1, D = 256): one warp per row, lane l owns columns 4l..4l+3 and 128+4l..128+4l+3
+// (two 512-byte requests per tensor), two rows in flight per warp.
+template <bool TANH>
+__global__ void __launch_bounds__(256)
+layernorm_value256_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ scale,
+                          const float* __restrict__ bias, float* __restrict__ out, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const float4 g0 = *reinterpret_cast<const float4*>(scale + 4 * lane), g1 = *reinterpret_cast<const float4*>(scale + 128 + 4 * lane);
+  const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * lane), b1 = *reinterpret_cast<const float4*>(bias + 128 + 4 * lane);
+  const int64_t r0 = warp * 2;
+  if (r0 >= rows) return;
+  const bool two = r0 + 1 < rows;
+  float4 xa[2][2], xb[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int64_t r = (u == 0 || two) ? r0 + u : r0;
+    xa[u][0] = *reinterpret_cast<const float4*>(a + r * 256 + 4 * lane);
+    xa[u][1] = *reinterpret_cast<const float4*>(a + r * 256 + 128 + 4 * lane);
+    xb[u][0] = *reinterpret_cast<const float4*>(b + r * 256 + 4 * lane);
+    xb[u][1] = *reinterpret_cast<const float4*>(b + r * 256 + 128 + 4 * lane);
+  }
+  float x[2][8], sum[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float av[8] = {xa[u][0].x, xa[u][0].y, xa[u][0].z, xa[u][0].w, xa[u][1].x, xa[u][1].y, xa[u][1].z, xa[u][1].w};
+    const float bv[8] = {xb[u][0].x, xb[u][0].y, xb[u][0].z, xb[u][0].w, xb[u][1].x, xb[u][1].y, xb[u][1].z, xb[u][1].w};
+    sum[u] = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      x[u][v] = av[v] + (TANH ? DH_TANH(bv[v]) : bv[v]);
+      sum[u] += x[u][v];
+    }
+  }
+  sum[0] = warp_sum(sum[0]);
+  sum[1] = warp_sum(sum[1]);
+  float sq[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const float mu = sum[u] * (1.0f / 256.0f);
+    sq[u] = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { x[u][v] -= mu; sq[u] = fmaf(x[u][v], x[u][v], sq[u]); }
+  }
+  sq[0] = warp_sum(sq[0]);
+  sq[1] = warp_sum(sq[1]);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    if (u == 1 && !two) break;
+    const float rho = rsqrtf(sq[u] * (1.0f / 256.0f) + 1e-5f);
+    float4 o0, o1;
+    o0.x = fmaf(x[u][0] * rho, g0.x, b0.x); o0.y = fmaf(x[u][1] * rho, g0.y, b0.y);
+    o0.z = fmaf(x[u][2] * rho, g0.z, b0.z); o0.w = fmaf(x[u][3] * rho, g0.w, b0.w);
+    o1.x = fmaf(x[u][4] * rho, g1.x, b1.x); o1.y = fmaf(x[u][5] * rho, g1.y, b1.y);
+    o1.z = fmaf(x[u][6] * rho, g1.z, b1.z); o1.w = fmaf(x[u][7] * rho, g1.w, b1.w);
+    *reinterpret_cast<float4*>(out + (r0 + u) * 256 + 4 * lane) = o0;
+    *reinterpret_cast<float4*>(out + (r0 + u) * 256 + 128 + 4 * lane) = o1;
+  }
+}
+
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s) {
   if (d.D % 32 != 0 || d.D > 32 * LN_VPL) return -2;
+  if (d.R == 1 && d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
+                                  reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
+    const int64_t rows = B * d.N;
+    const unsigned grid = (unsigned)((rows + 15) / 16);
+    if (tanh_mode) layernorm_value256_kernel<true><<<grid, 256, 0, s>>>(a, b, scale, bias, out, rows);
+    else layernorm_value256_kernel<false><<<grid, 256, 0, s>>>(a, b, scale, bias, out, rows);
+    return (int)cudaGetLastError();
+  }
   const int64_t groups = B * d.N;
   const int wpb = 4;
   unsigned grid = (unsigned)((groups + wpb - 1) / wpb);
