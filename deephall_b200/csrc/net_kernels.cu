@@ -117,7 +117,9 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return ax < 0.3f ? p : t;
 }
 
-template <bool TANH>
+// VEC4 (D = 256, 16-byte aligned tensors): lane l owns columns 4l..4l+3 and 128+4l..128+4l+3, moved as two
+// float4 per row (512-byte requests); otherwise lane l owns columns l, l+32, ...
+template <bool TANH, bool VEC4>
 __global__ void __launch_bounds__(128)
 residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                           const float* __restrict__ scale, const float* __restrict__ bias,
@@ -126,35 +128,58 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= groups) return;
   const int R = dm.R, D = dm.D, N = dm.N;
-  const int vpl = D >> 5;
+  const int vpl = VEC4 ? LN_VPL : (D >> 5);
   const float invD = 1.0f / (float)D;
   const float* ga = a + g * R * D;
   const float* gb = b + g * R * D;
   float* go = out + g * R * D;
 
+  // one row (D floats at `base`) <-> the LN_VPL values this lane owns
+  auto ldrow = [&](const float* base, float (&dst)[LN_VPL]) {
+    if (VEC4) {
+      const float4 p = *reinterpret_cast<const float4*>(base + 4 * lane);
+      const float4 q = *reinterpret_cast<const float4*>(base + 128 + 4 * lane);
+      dst[0] = p.x; dst[1] = p.y; dst[2] = p.z; dst[3] = p.w;
+      dst[4] = q.x; dst[5] = q.y; dst[6] = q.z; dst[7] = q.w;
+    } else {
+#pragma unroll
+      for (int v = 0; v < LN_VPL; ++v) dst[v] = v < vpl ? base[lane + 32 * v] : 0.f;
+    }
+  };
+  auto strow = [&](float* base, const float (&src)[LN_VPL]) {
+    if (VEC4) {
+      *reinterpret_cast<float4*>(base + 4 * lane) = make_float4(src[0], src[1], src[2], src[3]);
+      *reinterpret_cast<float4*>(base + 128 + 4 * lane) = make_float4(src[4], src[5], src[6], src[7]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < LN_VPL; ++v)
+        if (v < vpl) base[lane + 32 * v] = src[v];
+    }
+  };
+
   float gam[LN_VPL], bet[LN_VPL];
   float c0[LN_VPL], t1[LN_VPL], t2[LN_VPL];  // centred value row; tanh' and tanh''
+  ldrow(scale, gam);
+  ldrow(bias, bet);
 #pragma unroll
-  for (int v = 0; v < LN_VPL; ++v) {
-    if (v < vpl) { gam[v] = scale[lane + 32 * v]; bet[v] = bias[lane + 32 * v]; }
-    else { gam[v] = 0.f; bet[v] = 0.f; }
-    t1[v] = 1.f; t2[v] = 0.f;
-  }
+  for (int v = 0; v < LN_VPL; ++v) { t1[v] = 1.f; t2[v] = 0.f; }
   // ---- value row
-  float xr[LN_VPL];
+  float xr[LN_VPL], ra[LN_VPL], rb[LN_VPL], ro[LN_VPL];
+  ldrow(ga, ra);
+  ldrow(gb, rb);
   float sum = 0.f;
 #pragma unroll
   for (int v = 0; v < LN_VPL; ++v) {
     xr[v] = 0.f;
     if (v < vpl) {
-      float av = ga[lane + 32 * v], bv = gb[lane + 32 * v];
+      float bv = rb[v];
       if (TANH) {
         float t = DH_TANH(bv);
         t1[v] = 1.f - t * t;
         t2[v] = -2.f * t * t1[v];
         bv = t;
       }
-      xr[v] = av + bv;
+      xr[v] = ra[v] + bv;
       sum += xr[v];
     }
   }
@@ -170,8 +195,8 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   const float rho1 = -0.5f * rho0 / var;          // d rho / d var
   const float rho2 = 0.75f * rho0 / (var * var);  // d2 rho / d var2
 #pragma unroll
-  for (int v = 0; v < LN_VPL; ++v)
-    if (v < vpl) go[lane + 32 * v] = fmaf(c0[v] * rho0, gam[v], bet[v]);
+  for (int v = 0; v < LN_VPL; ++v) ro[v] = fmaf(c0[v] * rho0, gam[v], bet[v]);
+  strow(go, ro);
   if (R == 1) return;
 
   Rows rw(N, true);
@@ -183,13 +208,14 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   // first-order row helper: loads x_r, centres it, returns mean(c0*c_r), mean(c_r^2)
   auto load_first = [&](int r, float (&cr)[LN_VPL], float (&braw)[LN_VPL], float& m_c0c, float& m_cc) {
     float s1 = 0.f;
+    float av[LN_VPL];
+    ldrow(ga + (int64_t)r * D, av);
+    ldrow(gb + (int64_t)r * D, braw);
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) {
-      cr[v] = 0.f; braw[v] = 0.f;
+      cr[v] = 0.f;
       if (v < vpl) {
-        float av = ga[(int64_t)r * D + lane + 32 * v], bv = gb[(int64_t)r * D + lane + 32 * v];
-        braw[v] = bv;
-        cr[v] = av + (TANH ? t1[v] * bv : bv);
+        cr[v] = av[v] + (TANH ? t1[v] * braw[v] : braw[v]);
         s1 += cr[v];
       }
     }
@@ -207,12 +233,14 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   // second-order row helper: x_r = a_r + t1*b_r + t2*extra ; returns centred row and mean(c0*c_r)
   auto load_second = [&](int r, const float (&extra)[LN_VPL], float (&cr)[LN_VPL], float& m_c0c) {
     float s1 = 0.f;
+    float av[LN_VPL], bv[LN_VPL];
+    ldrow(ga + (int64_t)r * D, av);
+    ldrow(gb + (int64_t)r * D, bv);
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) {
       cr[v] = 0.f;
       if (v < vpl) {
-        float av = ga[(int64_t)r * D + lane + 32 * v], bv = gb[(int64_t)r * D + lane + 32 * v];
-        cr[v] = av + (TANH ? fmaf(t1[v], bv, t2[v] * extra[v]) : bv);
+        cr[v] = av[v] + (TANH ? fmaf(t1[v], bv[v], t2[v] * extra[v]) : bv[v]);
         s1 += cr[v];
       }
     }
@@ -238,12 +266,11 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
     sum_vv += vJ * vJ;
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) {
-      if (v < vpl) {
-        go[(int64_t)r * D + lane + 32 * v] = gam[v] * fmaf(cr[v], rho0, c0[v] * rhoJ);
-        accS[v] = fmaf(cr[v], rhoJ, accS[v]);
-        if (TANH) bsq[v] = fmaf(braw[v], braw[v], bsq[v]);
-      }
+      ro[v] = gam[v] * fmaf(cr[v], rho0, c0[v] * rhoJ);
+      accS[v] = fmaf(cr[v], rhoJ, accS[v]);
+      if (TANH) bsq[v] = fmaf(braw[v], braw[v], bsq[v]);
     }
+    strow(go + (int64_t)r * D, ro);
   }
   // ---- S row
   {
@@ -253,9 +280,8 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
     const float vS = 2.f * m_c0c + 2.f * sum_cc;
     const float rhoS = rho1 * vS + rho2 * sum_vv;
 #pragma unroll
-    for (int v = 0; v < LN_VPL; ++v)
-      if (v < vpl)
-        go[(int64_t)r * D + lane + 32 * v] = gam[v] * (fmaf(cr[v], rho0, c0[v] * rhoS) + 2.f * accS[v]);
+    for (int v = 0; v < LN_VPL; ++v) ro[v] = gam[v] * (fmaf(cr[v], rho0, c0[v] * rhoS) + 2.f * accS[v]);
+    strow(go + (int64_t)r * D, ro);
   }
   // ---- D_a / T_a rows
   for (int a3 = 0; a3 < 3; ++a3) {
@@ -267,17 +293,16 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) {
       bD2[v] = bD[v] * bD[v];
-      if (v < vpl) go[(int64_t)rw.D(a3) * D + lane + 32 * v] = gam[v] * fmaf(cD[v], rho0, c0[v] * rhoD);
+      ro[v] = gam[v] * fmaf(cD[v], rho0, c0[v] * rhoD);
     }
+    strow(go + (int64_t)rw.D(a3) * D, ro);
     float m2;
     load_second(rw.T(a3), bD2, cr, m2);
     const float vT = 2.f * m2 + 2.f * m_cc;
     const float rhoT = rho1 * vT + rho2 * vD * vD;
 #pragma unroll
-    for (int v = 0; v < LN_VPL; ++v)
-      if (v < vpl)
-        go[(int64_t)rw.T(a3) * D + lane + 32 * v] =
-            gam[v] * (fmaf(cr[v], rho0, c0[v] * rhoT) + 2.f * cD[v] * rhoD);
+    for (int v = 0; v < LN_VPL; ++v) ro[v] = gam[v] * (fmaf(cr[v], rho0, c0[v] * rhoT) + 2.f * cD[v] * rhoD);
+    strow(go + (int64_t)rw.T(a3) * D, ro);
   }
 }
 
@@ -355,10 +380,15 @@ int residual_layernorm(const float* a, const float* b, const float* scale, const
   const int64_t groups = B * d.N;
   const int wpb = 4;
   unsigned grid = (unsigned)((groups + wpb - 1) / wpb);
-  if (tanh_mode)
-    residual_layernorm_kernel<true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
-  else
-    residual_layernorm_kernel<false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+  const bool vec4 = d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
+                                    reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+  if (tanh_mode) {
+    if (vec4) residual_layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+    else residual_layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+  } else {
+    if (vec4) residual_layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+    else residual_layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+  }
   return (int)cudaGetLastError();
 }
 
