@@ -396,9 +396,9 @@ int residual_layernorm(const float* a, const float* b, const float* scale, const
 // value-only attention: one block of 256 threads per walker.
 // qkv rows: [q (D) | k (D) | v (D)], head h owns columns h*hd .. (h+1)*hd of each.
 //   stage q|k|v of the walker in shared memory (row stride 3D + 4 floats: conflict-free float4 reads)
-//   scores   thread = (head, query, key): one hd-long dot product
+//   scores   thread = (head, 2 queries, 2 keys): four hd-long dot products from four float4 streams
 //   softmax  thread = (head, query)
-//   output   thread = (query, head, 4 head-dim columns)
+//   output   thread = (2 queries, head, 4 head-dim columns)
 // =============================================================================================
 constexpr int ATT_NMAX = 32;
 
@@ -417,20 +417,32 @@ attention_value_kernel(const float* __restrict__ qkv, float* __restrict__ o, Net
   }
   __syncthreads();
   const float scl = rsqrtf((float)hd);
-  for (int t = threadIdx.x; t < H * N * N; t += blockDim.x) {
-    const int j = t % N, i = (t / N) % N, hh = t / (N * N);
-    const float4* q = reinterpret_cast<const float4*>(sm + i * ld + hh * hd);
-    const float4* k = reinterpret_cast<const float4*>(sm + j * ld + D + hh * hd);
-    float p0 = 0.f, p1 = 0.f;
-    for (int d = 0; d < hd / 4; d += 2) {
-      const float4 a0 = q[d], b0 = k[d];
-      p0 = fmaf(a0.x, b0.x, p0); p0 = fmaf(a0.y, b0.y, p0); p0 = fmaf(a0.z, b0.z, p0); p0 = fmaf(a0.w, b0.w, p0);
-      if (d + 1 < hd / 4) {
-        const float4 a1 = q[d + 1], b1 = k[d + 1];
-        p1 = fmaf(a1.x, b1.x, p1); p1 = fmaf(a1.y, b1.y, p1); p1 = fmaf(a1.z, b1.z, p1); p1 = fmaf(a1.w, b1.w, p1);
-      }
+  // scores: one thread per (head, 2 queries, 2 keys): 4 float4 loads feed 16 FMAs
+  const int N2 = (N + 1) / 2;
+  for (int t = threadIdx.x; t < H * N2 * N2; t += blockDim.x) {
+    const int jb = t % N2, ib = (t / N2) % N2, hh = t / (N2 * N2);
+    const int i0 = 2 * ib, i1 = min(i0 + 1, N - 1), j0 = 2 * jb, j1 = min(j0 + 1, N - 1);
+    const float4* qa = reinterpret_cast<const float4*>(sm + i0 * ld + hh * hd);
+    const float4* qb = reinterpret_cast<const float4*>(sm + i1 * ld + hh * hd);
+    const float4* ka = reinterpret_cast<const float4*>(sm + j0 * ld + D + hh * hd);
+    const float4* kb = reinterpret_cast<const float4*>(sm + j1 * ld + D + hh * hd);
+    float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < hd / 4; ++d) {
+      const float4 a0 = qa[d], a1 = qb[d], b0 = ka[d], b1 = kb[d];
+      s00 = fmaf(a0.x, b0.x, s00); s00 = fmaf(a0.y, b0.y, s00); s00 = fmaf(a0.z, b0.z, s00); s00 = fmaf(a0.w, b0.w, s00);
+      s01 = fmaf(a0.x, b1.x, s01); s01 = fmaf(a0.y, b1.y, s01); s01 = fmaf(a0.z, b1.z, s01); s01 = fmaf(a0.w, b1.w, s01);
+      s10 = fmaf(a1.x, b0.x, s10); s10 = fmaf(a1.y, b0.y, s10); s10 = fmaf(a1.z, b0.z, s10); s10 = fmaf(a1.w, b0.w, s10);
+      s11 = fmaf(a1.x, b1.x, s11); s11 = fmaf(a1.y, b1.y, s11); s11 = fmaf(a1.z, b1.z, s11); s11 = fmaf(a1.w, b1.w, s11);
     }
-    sc[t] = (p0 + p1) * scl;
+    float* s0 = sc + (hh * N + i0) * N;
+    float* s1 = sc + (hh * N + i0 + 1) * N;
+    s0[j0] = s00 * scl;
+    if (j0 + 1 < N) s0[j0 + 1] = s01 * scl;
+    if (i0 + 1 < N) {
+      s1[j0] = s10 * scl;
+      if (j0 + 1 < N) s1[j0 + 1] = s11 * scl;
+    }
   }
   __syncthreads();
   for (int t = threadIdx.x; t < H * N; t += blockDim.x) {
@@ -443,17 +455,22 @@ attention_value_kernel(const float* __restrict__ qkv, float* __restrict__ o, Net
     for (int j = 0; j < N; ++j) s[j] *= iz;
   }
   __syncthreads();
+  // output: one thread per (2 queries, head, 4 head-dim columns)
   const int hd4 = hd / 4;
-  for (int t = threadIdx.x; t < N * H * hd4; t += blockDim.x) {
-    const int d4 = t % hd4, hh = (t / hd4) % H, i = t / (hd4 * H);
-    const float* p = sc + (hh * N + i) * N;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = threadIdx.x; t < N2 * H * hd4; t += blockDim.x) {
+    const int d4 = t % hd4, hh = (t / hd4) % H, i0 = 2 * (t / (hd4 * H));
+    const bool has1 = i0 + 1 < N;
+    const float* p0 = sc + (hh * N + i0) * N;
+    const float* p1 = sc + (hh * N + (has1 ? i0 + 1 : i0)) * N;
+    float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
     for (int j = 0; j < N; ++j) {
       const float4 v = *reinterpret_cast<const float4*>(sm + j * ld + 2 * D + hh * hd + 4 * d4);
-      const float pj = p[j];
-      acc.x = fmaf(pj, v.x, acc.x); acc.y = fmaf(pj, v.y, acc.y); acc.z = fmaf(pj, v.z, acc.z); acc.w = fmaf(pj, v.w, acc.w);
+      const float pa = p0[j], pb = p1[j];
+      acc0.x = fmaf(pa, v.x, acc0.x); acc0.y = fmaf(pa, v.y, acc0.y); acc0.z = fmaf(pa, v.z, acc0.z); acc0.w = fmaf(pa, v.w, acc0.w);
+      acc1.x = fmaf(pb, v.x, acc1.x); acc1.y = fmaf(pb, v.y, acc1.y); acc1.z = fmaf(pb, v.z, acc1.z); acc1.w = fmaf(pb, v.w, acc1.w);
     }
-    *reinterpret_cast<float4*>(o + (b * N + i) * D + hh * hd + 4 * d4) = acc;
+    *reinterpret_cast<float4*>(o + (b * N + i0) * D + hh * hd + 4 * d4) = acc0;
+    if (has1) *reinterpret_cast<float4*>(o + (b * N + i0 + 1) * D + hh * hd + 4 * d4) = acc1;
   }
 }
 
