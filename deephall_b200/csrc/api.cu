@@ -110,10 +110,25 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       sl.bias = SIZE_MAX;
       if (has_bias) { sl.bias = off; off += al((size_t)Nout); }
       sl.scale = off; off += al(3);
+      sl.ldw = D;
       p->slots.push_back(sl);
     };
     for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); slot(D, true); }
     slot(2 * p->LNK, true);
+    // reverse-pass planes: [D rows][Kpad], Kpad = K rounded up to 32
+    auto vslot = [&](int K) {
+      dh_plan::Slot sl;
+      sl.Nout = D;
+      sl.ldw = (K + 31) & ~31;
+      sl.hi = off; off += al((size_t)D * sl.ldw);
+      sl.lo = off; off += al((size_t)D * sl.ldw);
+      sl.bias = SIZE_MAX;
+      sl.scale = off; off += al(3);
+      p->vslots.push_back(sl);
+    };
+    for (int l = 0; l < p->nl; ++l) { vslot(D); vslot(D); vslot(D); vslot(3 * D); }
+    vslot(2 * p->LNK);
+    p->cot_scale = off; off += al(2);
     p->w0qkv = off; off += al((size_t)4 * 3 * D);
     p->fold_tmp = off; off += al((size_t)D * D);
     p->prep_floats = off;
@@ -295,6 +310,45 @@ int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
   if ((rc = cp(sb.bias, p->orb_re_b, LNK))) return rc;
   if ((rc = cp(sb.bias + LNK, p->orb_im_b, LNK))) return rc;
   p->launches += p->nl * (f16 ? 18 : 11) + 5 + (f16 ? 4 : 2);
+  return 0;
+}
+
+// Planes for the reverse pass: dX = G @ W^T is C = A . B with A = G and the [N][K] operand = W as stored.
+int prepare_weights_vjp(dh_plan* p, const float* P, cudaStream_t s) {
+  if (p->gemm_impl != 1) return 0;
+  const int D = p->D, LNK = p->LNK, f16 = p->tc_f16;
+  int rc;
+  auto plane = [&](size_t off_floats) -> void* { return (void*)(p->prep + off_floats); };
+  struct Part { const float* W; int64_t ldw; int k; };
+  auto fill = [&](const dh_plan::Slot& sl, const Part* parts, int nparts) -> int {
+    float* slot = p->prep + sl.scale;
+    const size_t bytes = (size_t)D * sl.ldw * (f16 ? 2 : 4);
+    DH_CHECK(cudaMemsetAsync(plane(sl.hi), 0, bytes, s));
+    DH_CHECK(cudaMemsetAsync(plane(sl.lo), 0, bytes, s));
+    DH_CHECK(cudaMemsetAsync(slot, 0, 3 * sizeof(float), s));
+    if (f16)
+      for (int t = 0; t < nparts; ++t)
+        if ((rc = weight_maxabs_tc(parts[t].W, parts[t].ldw, D, parts[t].k, slot, s))) return rc;
+    int koff = 0;
+    for (int t = 0; t < nparts; ++t) {
+      if ((rc = split_weight_nt_tc(parts[t].W, parts[t].ldw, D, parts[t].k, koff, sl.ldw, plane(sl.hi), plane(sl.lo), slot, f16, s)))
+        return rc;
+      koff += parts[t].k;
+    }
+    return 0;
+  };
+  for (int l = 0; l < p->nl; ++l) {
+    const LayerOff& o = p->layer[l];
+    const Part pd2 = {P + o.d2_k, D, D}, pd1 = {P + o.d1_k, D, D}, po = {P + o.o_k, D, D};
+    const Part pq[3] = {{P + o.q_k, D, D}, {P + o.k_k, D, D}, {P + o.v_k, D, D}};
+    if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_D2], &pd2, 1))) return rc;
+    if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_D1], &pd1, 1))) return rc;
+    if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_O], &po, 1))) return rc;
+    if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_QKV], pq, 3))) return rc;
+  }
+  const Part pb[2] = {{P + p->orb_re_k, LNK, LNK}, {P + p->orb_im_k, LNK, LNK}};
+  if ((rc = fill(p->vslots[p->nl * VS_PER_LAYER], pb, 2))) return rc;
+  p->launches += (p->nl * 6 + 2) * (f16 ? 2 : 1);
   return 0;
 }
 

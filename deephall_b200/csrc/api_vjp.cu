@@ -53,6 +53,24 @@ int dense_bwd_x(const dh_plan* p, const float* G, int64_t ldg, const float* W, i
   return gemm_simt(G, W, nullptr, C, rows, Din, Nout, ldg, 1, 1, Nout, Din, 1, accumulate, 1, s);
 }
 
+// tensor-core form of the same product through the prepared reverse-pass planes of slot `vs` (K = Nout columns of G)
+bool bwd_x_tc_ok(const dh_plan* p, const float* G, int64_t ldg, const float* C) {
+  return p->gemm_impl == 1 && (ldg % 4) == 0 && ((reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(C)) & 15) == 0;
+}
+int dense_bwd_x_tc(const dh_plan* p, const float* G, int64_t ldg, int vs, int K, float* C, int64_t rows, int accumulate,
+                   cudaStream_t s) {
+  const dh_plan::Slot& sl = p->vslots[vs];
+  ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * K * p->D, s);
+  TcGemm g;
+  g.A = G; g.lda = ldg;
+  g.Wt_hi = p->prep + sl.hi; g.Wt_lo = p->prep + sl.lo; g.ldw = sl.ldw;
+  g.bias = nullptr; g.inv_scale = p->tc_f16 ? p->prep + sl.scale + 1 : nullptr;
+  g.C = C; g.ldc = p->D; g.M = rows; g.N = p->D; g.K = K; g.rpg = 1;
+  g.f16 = p->tc_f16; g.merged = p->tc_merged; g.reduce_add = accumulate;
+  g.a_scale = p->prep + p->cot_scale;  // gradients scale with the cotangents (O(1/B)): keep the fp16 pieces in range
+  return gemm_tc_ex(g, s);
+}
+
 // dW[Din, Nout] += X[rows, Din]^T @ G[rows, Nout] (ldg)
 int dense_bwd_w(const dh_plan* p, const float* X, int Din, const float* G, int64_t ldg, int Nout, float* dW,
                 int64_t rows, cudaStream_t s) {
@@ -84,6 +102,8 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
   TailDims td{N, 1, p->L, p->K, p->twoQ, p->cfg.n_up};
   int rc;
   if ((rc = prepare_weights(p, P, s))) return rc;
+  if ((rc = prepare_weights_vjp(p, P, s))) return rc;
+  if (p->gemm_impl == 1 && (rc = pow2_scale_tc(cot, 2 * B, p->prep + p->cot_scale, s))) return rc;
 #define RUN(cat, call)                          \
   do {                                          \
     ProfScope _ps(p, cat, 0, s);                \
@@ -130,8 +150,12 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
     if ((rc = dense_bwd_w(p, hf, D, w.gCb + LNK, 2 * (int64_t)LNK, LNK, grad + p->orb_im_k, rows, s))) return rc;
     RUN(PC_OTHER, colsum_add(w.gCb, grad + p->orb_re_b, rows, LNK, 2 * (int64_t)LNK, s));
     RUN(PC_OTHER, colsum_add(w.gCb + LNK, grad + p->orb_im_b, rows, LNK, 2 * (int64_t)LNK, s));
-    if ((rc = dense_bwd_x(p, w.gCb, 2 * (int64_t)LNK, P + p->orb_re_k, LNK, w.gH, rows, D, 0, s))) return rc;
-    if ((rc = dense_bwd_x(p, w.gCb + LNK, 2 * (int64_t)LNK, P + p->orb_im_k, LNK, w.gH, rows, D, 1, s))) return rc;
+    if (bwd_x_tc_ok(p, w.gCb, 2 * (int64_t)LNK, w.gH)) {
+      if ((rc = dense_bwd_x_tc(p, w.gCb, 2 * (int64_t)LNK, nl * VS_PER_LAYER, 2 * LNK, w.gH, rows, 0, s))) return rc;
+    } else {
+      if ((rc = dense_bwd_x(p, w.gCb, 2 * (int64_t)LNK, P + p->orb_re_k, LNK, w.gH, rows, D, 0, s))) return rc;
+      if ((rc = dense_bwd_x(p, w.gCb + LNK, 2 * (int64_t)LNK, P + p->orb_im_k, LNK, w.gH, rows, D, 1, s))) return rc;
+    }
     for (int l = nl - 1; l >= 0; --l) {
       const LayerOff& o = p->layer[l];
       // h_out = LN1(hA + tanh(z)) : gH -> (gA = d/d hA, gB = d/d z)
@@ -139,23 +163,29 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
                                                grad + o.ln1_b, rows, D, 1, s));
       if ((rc = dense_bwd_w(p, w.hA[l], D, w.gB, D, D, grad + o.d2_k, rows, s))) return rc;
       RUN(PC_OTHER, colsum_add(w.gB, grad + o.d2_b, rows, D, D, s));
-      if ((rc = dense_bwd_x(p, w.gB, D, P + o.d2_k, D, w.gA, rows, D, 1, s))) return rc;
+      const bool tc = bwd_x_tc_ok(p, w.gB, D, w.gA) && bwd_x_tc_ok(p, w.gC, D, w.gH) && bwd_x_tc_ok(p, w.gQKV, 3 * D, w.gH);
+      if (tc) { if ((rc = dense_bwd_x_tc(p, w.gB, D, l * VS_PER_LAYER + VS_D2, D, w.gA, rows, 1, s))) return rc; }
+      else if ((rc = dense_bwd_x(p, w.gB, D, P + o.d2_k, D, w.gA, rows, D, 1, s))) return rc;
       // hA = LN0(h_in + t2) : gA -> (gH = d/d h_in, gB = d/d t2)
       RUN(PC_LAYERNORM, residual_layernorm_bwd(w.hs[l], w.t2[l], P + o.ln0_s, w.gA, w.gH, w.gB, grad + o.ln0_s,
                                                grad + o.ln0_b, rows, D, 0, s));
       if ((rc = dense_bwd_w(p, w.t1[l], D, w.gB, D, D, grad + o.d1_k, rows, s))) return rc;
-      if ((rc = dense_bwd_x(p, w.gB, D, P + o.d1_k, D, w.gC, rows, D, 0, s))) return rc;   // gC = d/d t1
+      if (tc) { if ((rc = dense_bwd_x_tc(p, w.gB, D, l * VS_PER_LAYER + VS_D1, D, w.gC, rows, 0, s))) return rc; }
+      else if ((rc = dense_bwd_x(p, w.gB, D, P + o.d1_k, D, w.gC, rows, D, 0, s))) return rc;   // gC = d/d t1
       if ((rc = dense_bwd_w(p, w.att[l], D, w.gC, D, D, grad + o.o_k, rows, s))) return rc;
       RUN(PC_OTHER, colsum_add(w.gC, grad + o.o_b, rows, D, D, s));
-      if ((rc = dense_bwd_x(p, w.gC, D, P + o.o_k, D, w.gB, rows, D, 0, s))) return rc;    // gB = d/d att
+      if (tc) { if ((rc = dense_bwd_x_tc(p, w.gC, D, l * VS_PER_LAYER + VS_O, D, w.gB, rows, 0, s))) return rc; }
+      else if ((rc = dense_bwd_x(p, w.gC, D, P + o.o_k, D, w.gB, rows, D, 0, s))) return rc;    // gB = d/d att
       RUN(PC_ATTENTION, attention_value_bwd(w.qkv[l], w.gB, w.gQKV, Bc, nd, s));
       const int64_t qk[3] = {o.q_k, o.k_k, o.v_k};
       const int64_t qb[3] = {o.q_b, o.k_b, o.v_b};
       for (int t = 0; t < 3; ++t) {
         if ((rc = dense_bwd_w(p, w.hs[l], D, w.gQKV + t * D, 3 * D, D, grad + qk[t], rows, s))) return rc;
         RUN(PC_OTHER, colsum_add(w.gQKV + t * D, grad + qb[t], rows, D, 3 * D, s));
-        if ((rc = dense_bwd_x(p, w.gQKV + t * D, 3 * D, P + qk[t], D, w.gH, rows, D, 1, s))) return rc;
+        if (!tc && (rc = dense_bwd_x(p, w.gQKV + t * D, 3 * D, P + qk[t], D, w.gH, rows, D, 1, s))) return rc;
       }
+      // gH += gQKV[rows, 3D] @ (Wq | Wk | Wv)^T : one K = 3D contraction added to the residual-path gradient
+      if (tc && (rc = dense_bwd_x_tc(p, w.gQKV, 3 * D, l * VS_PER_LAYER + VS_QKV, 3 * D, w.gH, rows, 1, s))) return rc;
     }
     RUN(PC_OTHER, features_dense0_bwd(xc, w.gH, grad + p->off_W0, Bc, nd, s));
   }

@@ -98,6 +98,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
                ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// same, but the tile is ADDED to global memory (fp32 reduction performed by the TMA unit / L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 template <bool SW64>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   // K-major operand tile whose rows are one swizzle span: SWIZZLE_128B (layout 2, 8-row groups 1024 B apart) or
@@ -201,7 +207,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
-               int N, int K, int64_t ldc, int rpg, int tma_store, int cl, unsigned long long* __restrict__ prof) {
+               int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
+               unsigned long long* __restrict__ prof) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
@@ -238,7 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES + B_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = K / BLOCK_K;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;  // a K tail is zero-filled by TMA (A) and zero-padded (W planes)
   const int n_ntiles = (N + BLOCK_N - 1) / BLOCK_N;
   const int64_t n_mtiles = (M + BLOCK_M - 1) / BLOCK_M;
   // Tile order: a CTA takes 128-row bands blockIdx.x, blockIdx.x + gridDim.x, ... and walks all column tiles
@@ -370,6 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp < EPI_WARP0) {
     // ------------------------------------------------------------------ splitter (8 warps)
     const int t = threadIdx.x - 64;  // 0..255
+    // optional power-of-two scale of A (reverse pass: gradients are O(1/B) and would underflow fp16 pieces);
+    // a_scale_ptr = {scale, 1/scale}, the epilogue undoes it
+    const float asc = a_scale_ptr ? __ldg(a_scale_ptr) : 1.f;
     uint32_t it = 0;
     for (int64_t tk = 0; tk < my_tiles; ++tk) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -387,7 +397,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint8_t* src = reg + r * 128;
           float4 v[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4*>(src + (((4 * h + j) ^ sw) << 4));
+          for (int j = 0; j < 4; ++j) {
+            v[j] = *reinterpret_cast<const float4*>(src + (((4 * h + j) ^ sw) << 4));
+            v[j].x *= asc; v[j].y *= asc; v[j].z *= asc; v[j].w *= asc;
+          }
           asm volatile("bar.sync 1, %0;" ::"n"(32 * SPLIT_WARPS) : "memory");
           const int sw2 = (r >> 1) & 3;
 #pragma unroll
@@ -409,6 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < A_BYTES / 16 / (32 * SPLIT_WARPS); ++i) {
             const int idx = t + i * 32 * SPLIT_WARPS;
             float4 v = hi[idx], h, l;
+            v.x *= asc; v.y *= asc; v.z *= asc; v.w *= asc;
             h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
             l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
             hi[idx] = h;
@@ -430,7 +444,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool lead = warp == EPI_WARP0 && lane == 0;
     uint8_t* buf = epi_smem + (warp - EPI_WARP0) * EPI_BUF_BYTES;
     uint32_t tl = 0;
-    const float inv_scale = inv_scale_ptr ? __ldg(inv_scale_ptr) : 1.f;  // undoes the fp16 weight scale (power of two)
+    // undoes the fp16 weight scale and the optional A scale (powers of two)
+    const float inv_scale = (inv_scale_ptr ? __ldg(inv_scale_ptr) : 1.f) * (a_scale_ptr ? __ldg(a_scale_ptr + 1) : 1.f);
     for (int64_t tk = 0; tk < my_tiles; ++tk, ++tl) {
       const int64_t m0 = band_of(tk) * BLOCK_M;
       const int n0 = ntile_of(tk) * BLOCK_N;
@@ -507,7 +522,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           DH_LAP(3)
           if (lane == 0) {
-            tma_store_2d(&tmC, smem_u32(buf), n0 + c0, (int)(m0 + q * 32));
+            if (reduce_add) tma_reduce_add_2d(&tmC, smem_u32(buf), n0 + c0, (int)(m0 + q * 32));
+            else tma_store_2d(&tmC, smem_u32(buf), n0 + c0, (int)(m0 + q * 32));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           DH_LAP(4)
@@ -515,7 +531,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float* crow = C + m * ldc + n0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < N) crow[j] = o[j];
+            if (n0 + c0 + j < N) {
+              if (reduce_add) atomicAdd(crow + j, o[j]); else crow[j] = o[j];
+            }
         }
       }
       if (!released) {  // a narrow tile left this warp without a chunk
@@ -593,6 +611,55 @@ __global__ void split_weight_kernel(const float* __restrict__ W, int64_t ldw, in
   }
 }
 
+// planes[n][k_off + k] = W[n][k] * scale for n < N, k < Kpart (no transpose: W is already [N][K], row stride ldw)
+template <bool F16>
+__global__ void split_weight_nt_kernel(const float* __restrict__ W, int64_t ldw, int N, int Kpart, int k_off, int64_t ldp,
+                                       void* __restrict__ hi_, void* __restrict__ lo_, float* __restrict__ slot) {
+  float scale = 1.f;
+  if (F16) {
+    scale = f16_weight_scale(reinterpret_cast<const unsigned*>(slot));
+    if (blockIdx.x == 0 && threadIdx.x == 0) { slot[1] = 1.f / scale; slot[2] = scale; }
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (int64_t)N * Kpart; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / Kpart), k = (int)(i % Kpart);
+    const float w = W[n * ldw + k] * scale;
+    const int64_t o = n * ldp + k_off + k;
+    if (F16) {
+      __half h, l;
+      split_f16(w, h, l);
+      reinterpret_cast<__half*>(hi_)[o] = h;
+      reinterpret_cast<__half*>(lo_)[o] = l;
+    } else {
+      const float h = rna_tf32(w);
+      reinterpret_cast<float*>(hi_)[o] = h;
+      reinterpret_cast<float*>(lo_)[o] = rna_tf32(w - h);
+    }
+  }
+}
+
+// slot = {s, 1/s} with s the power of two that brings max|v| into [1, 2)  (one block)
+__global__ void pow2_scale_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ slot) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = fabsf(v[i]);
+    if (a < INFINITY) m = fmaxf(m, a);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) {
+      float sc = 1.f;
+      if (m > 0.f) { int e; frexpf(m, &e); sc = ldexpf(1.f, 1 - e); }
+      slot[0] = sc;
+      slot[1] = 1.f / sc;
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -660,17 +727,45 @@ int split_weight_tc(const float* W, int64_t ldw, int K, int N, int pad_rows, voi
   return (int)cudaGetLastError();
 }
 
+int pow2_scale_tc(const float* v, int64_t n, float* slot, cudaStream_t stream) {
+  tc::pow2_scale_kernel<<<1, 1024, 0, stream>>>(v, n, slot);
+  return (int)cudaGetLastError();
+}
+
+int split_weight_nt_tc(const float* W, int64_t ldw, int N, int Kpart, int k_off, int64_t ldp, void* hi, void* lo,
+                       float* scale_slot, int f16, cudaStream_t stream) {
+  const int64_t n = (int64_t)N * Kpart;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 592) blocks = 592;
+  if (f16) tc::split_weight_nt_kernel<true><<<blocks, 256, 0, stream>>>(W, ldw, N, Kpart, k_off, ldp, hi, lo, scale_slot);
+  else tc::split_weight_nt_kernel<false><<<blocks, 256, 0, stream>>>(W, ldw, N, Kpart, k_off, ldp, hi, lo, scale_slot);
+  return (int)cudaGetLastError();
+}
+
 int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* bias, const float* inv_scale, float* C,
             int64_t M, int N, int K, int64_t ldc, int rpg, int f16, int merged, cudaStream_t stream) {
+  if (!gemm_tc_supported(N, K)) return -2;
+  TcGemm g;
+  g.A = A; g.lda = K; g.Wt_hi = Wt_hi; g.Wt_lo = Wt_lo; g.ldw = K; g.bias = bias; g.inv_scale = inv_scale;
+  g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.rpg = rpg; g.f16 = f16; g.merged = merged; g.reduce_add = 0;
+  g.a_scale = nullptr;
+  return gemm_tc_ex(g, stream);
+}
+
+int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
+  const float* A = gm.A; const void* Wt_hi = gm.Wt_hi; const void* Wt_lo = gm.Wt_lo;
+  const float* bias = gm.bias; const float* inv_scale = gm.inv_scale; float* C = gm.C;
+  const int64_t M = gm.M, ldc = gm.ldc; const int N = gm.N, K = gm.K, rpg = gm.rpg, f16 = gm.f16, merged = gm.merged;
+  const int reduce_add = gm.reduce_add;
   if (M <= 0) return 0;
-  if (!gemm_tc_supported(N, K) || (f16 && !gemm_tc_f16_ok(K)) || M > 0x7fffff00LL) return -2;
+  if (N < 1 || K < 1 || gm.ldw % 32 != 0 || gm.ldw < K || (gm.lda % 4) != 0 || M > 0x7fffff00LL) return -2;
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(Wt_hi) & 15) ||
       (reinterpret_cast<uintptr_t>(Wt_lo) & 15))
     return -1;
   const int Npad = (N + 15) & ~15;
   CUtensorMap tmA, tmBh, tmBl, tmC;
   int rc;
-  if ((rc = tc::make_map(&tmA, A, false, (uint64_t)M, (uint64_t)K, (uint64_t)K, tc::BLOCK_M))) return rc;
+  if ((rc = tc::make_map(&tmA, A, false, (uint64_t)M, (uint64_t)K, (uint64_t)gm.lda, tc::BLOCK_M))) return rc;
   const int tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 4) == 0) ? 1 : 0;
   if (tma_store) {
     if ((rc = tc::make_map(&tmC, C, false, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32))) return rc;
@@ -698,8 +793,8 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   int64_t g = bands < sms ? bands : sms;
   g = g / cl * cl;
   dim3 grid((unsigned)g);
-  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N / cl))) return rc;
-  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)K, (uint64_t)K, tc::BLOCK_N / cl))) return rc;
+  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, tc::BLOCK_N / cl))) return rc;
+  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, tc::BLOCK_N / cl))) return rc;
   static const bool want_prof = getenv("DH_GEMM_PROF") != nullptr;
   unsigned long long* prof = nullptr;
   if (want_prof) {
@@ -723,7 +818,7 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   lc.numAttrs = 1;
   cudaError_t le;
 #define DH_LAUNCH_TC(F, MG) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG>, tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, \
-                                                    N, K, ldc, rpg, tma_store, cl, prof)
+                                                    N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, prof)
   if (f16) { if (merged) DH_LAUNCH_TC(true, true); else DH_LAUNCH_TC(true, false); }
   else { if (merged) DH_LAUNCH_TC(false, true); else DH_LAUNCH_TC(false, false); }
 #undef DH_LAUNCH_TC

@@ -20,6 +20,22 @@ int gemm_tc_supported(int N, int K);
 int gemm_tc_f16_ok(int K);
 int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* bias, const float* inv_scale, float* C,
             int64_t M, int N, int K, int64_t ldc, int rpg, int f16, int merged, cudaStream_t stream);
+// General form: A row stride lda (floats, multiple of 4), any K >= 1 (the planes are [Npad][ldw] with ldw = K rounded
+// up to 32 and the tail zero), reduce_add = 1 adds the product to C (TMA reduce) instead of storing it.
+struct TcGemm {
+  const float* A; int64_t lda;
+  const void *Wt_hi, *Wt_lo; int64_t ldw;
+  const float *bias, *inv_scale;
+  float* C; int64_t ldc;
+  int64_t M; int N, K, rpg, f16, merged, reduce_add;
+  const float* a_scale;  // optional device {s, 1/s}: A is multiplied by s before the split, C by 1/s
+};
+// slot = {s, 1/s}, s = power of two bringing max|v| into [1, 2)
+int pow2_scale_tc(const float* v, int64_t n, float* slot, cudaStream_t stream);
+int gemm_tc_ex(const TcGemm& g, cudaStream_t stream);
+// planes[n][k_off + k] = W[n*ldw + k] * scale (no transpose); the slot must hold max|W| (weight_maxabs_tc)
+int split_weight_nt_tc(const float* W, int64_t ldw, int N, int Kpart, int k_off, int64_t ldp, void* hi, void* lo,
+                       float* scale_slot, int f16, cudaStream_t stream);
 int weight_maxabs_tc(const float* W, int64_t ldw, int K, int N, float* scale_slot, cudaStream_t stream);
 int split_weight_tc(const float* W, int64_t ldw, int K, int N, int pad_rows, void* Wt_hi, void* Wt_lo,
                     float* scale_slot, int f16, cudaStream_t stream);

@@ -31,8 +31,11 @@ struct dh_plan {
   float* prep;            // device buffer owned by the plan
   size_t prep_floats;
   const float* prep_src;  // params pointer the preparation was made from
-  struct Slot { int Nout; size_t hi, lo, bias, scale; };  // float offsets into prep (bias: SIZE_MAX = none); scale: 3 floats
+  struct Slot { int Nout; size_t hi, lo, bias, scale; int ldw; };  // float offsets into prep (bias: SIZE_MAX = none); scale: 3 floats; ldw: plane row length
   std::vector<Slot> slots;  // per layer: qkv, o, d1, d2, od (= o folded into d1) ; last: orbitals (re | im)
+  // reverse pass (dX = G @ W^T): planes of W itself, [D][Kpad]; per layer d2, d1, o, qkv ; last: orbitals
+  std::vector<Slot> vslots;
+  size_t cot_scale;         // float offset into prep: {s, 1/s} for the cotangents of the current dh_logpsi_vjp call
   size_t w0qkv;             // float offset into prep: [4][3D] = W0 @ (Wq|Wk|Wv) of layer 0 (fp32)
   size_t fold_tmp;          // float offset into prep: [D][D] scratch for Wo @ W1 (fp32)
   // ---- instrumentation (dh_profile_*): CUDA-event timing of kernel categories, launch count
@@ -131,6 +134,7 @@ static inline float* align_ws(void* ws) {
 
 // --------------------------------------------------------------------------------- forward
 enum { SL_QKV = 0, SL_O = 1, SL_D1 = 2, SL_D2 = 3, SL_OD = 4, SL_PER_LAYER = 5 };
+enum { VS_D2 = 0, VS_D1 = 1, VS_O = 2, VS_QKV = 3, VS_PER_LAYER = 4 };
 
 // tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows)
 static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C, int64_t rows, int64_t ldc, int R,
@@ -178,4 +182,5 @@ static inline int dense_orb(const dh_plan* p, const float* P, const float* A, fl
   return dense(p, A, P + p->orb_im_k, P + p->orb_im_b, cbuf + LNK, rows, LNK, 2 * (int64_t)LNK, R, s);
 }
 
-int prepare_weights(dh_plan* p, const float* P, cudaStream_t s);  // api.cu
+int prepare_weights(dh_plan* p, const float* P, cudaStream_t s);      // api.cu
+int prepare_weights_vjp(dh_plan* p, const float* P, cudaStream_t s);  // api.cu

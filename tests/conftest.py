@@ -17,3 +17,13 @@ def golden():
     import numpy as np
 
     return np.load(os.path.join(ROOT, "tests", "golden", "psiformer_small.npz"))
+
+
+@pytest.fixture(autouse=True)
+def _deterministic_torch_rng():
+    """Every test starts from the same torch RNG state (CPU and CUDA), so a test's random inputs do not
+    depend on which tests ran before it."""
+    import torch
+
+    torch.manual_seed(20261018)
+    yield
