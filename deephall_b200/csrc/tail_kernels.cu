@@ -349,7 +349,35 @@ logdet_jets_kernel(const float* __restrict__ Mj, float* __restrict__ ldout, floa
   }
 }
 
+// value-only form without the inverse (log psi / Metropolis passes): one warp per matrix, eight per block
+__global__ void __launch_bounds__(256)
+logdet_value_kernel(const float* __restrict__ Mj, float* __restrict__ ldout, int64_t nmat, int N) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int NN = N * N;
+  cplx* a = reinterpret_cast<cplx*>(smraw) + (size_t)warp * NN;
+  const int64_t bk = (int64_t)blockIdx.x * 8 + warp;
+  if (bk >= nmat) return;  // whole warps leave; only warp-level synchronisation below
+  const cplx* M0 = reinterpret_cast<const cplx*>(Mj) + bk * NN;
+  for (int t = lane; t < NN; t += 32) a[t] = M0[t];
+  __syncwarp();
+  float la;
+  cplx ph;
+  warp_gauss_jordan(a, N, N, N, la, ph);
+  if (lane == 0) {
+    float* o = ldout + bk * 2;
+    o[0] = la;
+    o[1] = (ph.x == 0.f && ph.y == 0.f) ? 0.f : atan2f(ph.y, ph.x);
+  }
+}
+
 int logdet_jets_impl(const float* Mj, float* ld, float* Minv, int64_t B, TailDims d, cudaStream_t s) {
+  if (d.R == 1 && Minv == nullptr) {
+    const int64_t nmat = B * d.K;
+    const size_t smem1 = (size_t)8 * d.N * d.N * sizeof(cplx);
+    logdet_value_kernel<<<(unsigned)((nmat + 7) / 8), 256, smem1, s>>>(Mj, ld, nmat, d.N);
+    return (int)cudaGetLastError();
+  }
   const int nwarp = 4;
   size_t smem = ((size_t)d.N * 2 * d.N + (size_t)nwarp * 2 * d.N * d.N + 2 * (size_t)d.R) * sizeof(cplx);
   if (smem > 48 * 1024) {
