@@ -49,6 +49,8 @@ SIGNATURES = OrderedDict(
     dh_version=(C.c_char_p, []),
     dh_param_count=(_i64, [_vp]),
     dh_param_layout=(C.c_int, [_vp, C.POINTER(dh_param_entry), C.POINTER(_i32)]),
+    dh_params_prepare=(C.c_int, [_vp, _vp, _vp]),
+    dh_plan_set_auto_prepare=(C.c_int, [_vp, _i32]),
     dh_workspace_bytes=(C.c_int, [_vp, C.c_int, _i64, C.POINTER(C.c_size_t)]),
     dh_logpsi=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     dh_local_energy=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
@@ -133,6 +135,10 @@ class Plan:
         _check(self.lib.dh_plan_create(C.byref(self.cfg), C.byref(h)), "dh_plan_create")
         self.handle = h
         self._ws = None
+        # prepared weights are refreshed here, only when the parameter tensor changed (torch's in-place version
+        # counter catches params.add_() style updates as well as new tensors)
+        _check(self.lib.dh_plan_set_auto_prepare(self.handle, 0), "dh_plan_set_auto_prepare")
+        self._prepared = None
 
     def __del__(self):
         try:
@@ -188,8 +194,17 @@ class Plan:
         _check(self.lib.dh_profile_end(self.handle, ms, cnt, fl), "dh_profile_end")
         return {c: {"ms": ms[i], "count": cnt[i], "flops": fl[i]} for i, c in enumerate(PROFILE_CATEGORIES)}
 
+    def _prepare(self, params):
+        # identity + in-place version of the tensor the copies were made from; the strong reference keeps its
+        # memory from being recycled for a different tensor at the same address
+        prev = self._prepared
+        if prev is None or prev[0] is not params or prev[1] != params._version:
+            _check(self.lib.dh_params_prepare(self.handle, _ptr(params), _stream()), "dh_params_prepare")
+            self._prepared = (params, params._version)
+
     # ---- ops
     def logpsi(self, params, x):
+        self._prepare(params)
         B = x.shape[0]
         out = torch.empty((B, 2), dtype=torch.float32, device=x.device)
         ws = self.workspace(OP_LOGPSI, B)
@@ -197,6 +212,7 @@ class Plan:
         return torch.view_as_complex(out)
 
     def local_energy(self, params, x):
+        self._prepare(params)
         B = x.shape[0]
         dev = x.device
         el = torch.empty((B, 2), dtype=torch.float32, device=dev)
@@ -226,6 +242,7 @@ class Plan:
 
     def mcmc_sweep(self, params, x, steps, width, seed=0, offset=0, subsequence0=0, randoms=None, want_lp=False):
         """In-place on x.  Returns (naccept device int64 tensor, lp or None)."""
+        self._prepare(params)
         B = x.shape[0]
         nacc = torch.zeros((1,), dtype=torch.int64, device=x.device)
         lp = torch.empty((B,), dtype=torch.float32, device=x.device) if want_lp else None
@@ -255,6 +272,7 @@ class Plan:
         return x
 
     def logpsi_vjp(self, params, x, cot, want_logpsi=False):
+        self._prepare(params)
         B = x.shape[0]
         grad = torch.empty_like(params)
         lpsi = torch.empty((B, 2), dtype=torch.float32, device=x.device) if want_logpsi else None

@@ -58,6 +58,9 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->prep = nullptr;
   p->prep_floats = 0;
   p->prep_src = nullptr;
+  p->auto_prepare = 1;
+  p->prep_fwd_valid = false;
+  p->prep_vjp_valid = false;
   p->prof_on = false;
   p->prof_used = 0;
   p->launches = 0;
@@ -234,7 +237,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   return finalize(fa, Bc, td, s);
 }
 
-int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
+static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
   if (p->gemm_impl != 1) return 0;
   const int D = p->D, LNK = p->LNK, f16 = p->tc_f16;
   int rc;
@@ -314,7 +317,7 @@ int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
 }
 
 // Planes for the reverse pass: dX = G @ W^T is C = A . B with A = G and the [N][K] operand = W as stored.
-int prepare_weights_vjp(dh_plan* p, const float* P, cudaStream_t s) {
+static int prepare_weights_vjp_now(dh_plan* p, const float* P, cudaStream_t s) {
   if (p->gemm_impl != 1) return 0;
   const int D = p->D, LNK = p->LNK, f16 = p->tc_f16;
   int rc;
@@ -349,6 +352,42 @@ int prepare_weights_vjp(dh_plan* p, const float* P, cudaStream_t s) {
   const Part pb[2] = {{P + p->orb_re_k, LNK, LNK}, {P + p->orb_im_k, LNK, LNK}};
   if ((rc = fill(p->vslots[p->nl * VS_PER_LAYER], pb, 2))) return rc;
   p->launches += (p->nl * 6 + 2) * (f16 ? 2 : 1);
+  return 0;
+}
+
+// Called by every op.  With auto_prepare the prepared weights are rebuilt from `P` each time (the library
+// cannot see in-place parameter updates); otherwise the caller promised to call dh_params_prepare after
+// every update and the planes made there are reused (the reverse-pass planes lazily, on the first VJP).
+int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
+  if (p->auto_prepare) return prepare_weights_now(p, P, s);
+  if (p->prep_fwd_valid && p->prep_src == P) return 0;
+  int rc = prepare_weights_now(p, P, s);
+  if (!rc) { p->prep_src = P; p->prep_fwd_valid = true; p->prep_vjp_valid = false; }
+  return rc;
+}
+int prepare_weights_vjp(dh_plan* p, const float* P, cudaStream_t s) {
+  if (p->auto_prepare) return prepare_weights_vjp_now(p, P, s);
+  if (p->prep_vjp_valid && p->prep_src == P) return 0;
+  int rc = prepare_weights_vjp_now(p, P, s);
+  if (!rc) p->prep_vjp_valid = true;
+  return rc;
+}
+
+extern "C" int dh_params_prepare(dh_plan* p, const float* params, void* stream) {
+  if (!p || !params) return DH_E_BADARG;
+  int rc = prepare_weights_now(p, params, (cudaStream_t)stream);
+  if (rc) return rc;
+  p->prep_src = params;
+  p->prep_fwd_valid = true;
+  p->prep_vjp_valid = false;
+  return 0;
+}
+
+extern "C" int dh_plan_set_auto_prepare(dh_plan* p, int32_t on) {
+  if (!p) return DH_E_BADARG;
+  p->auto_prepare = on ? 1 : 0;
+  p->prep_fwd_valid = false;
+  p->prep_vjp_valid = false;
   return 0;
 }
 

@@ -31,6 +31,9 @@ struct dh_plan {
   float* prep;            // device buffer owned by the plan
   size_t prep_floats;
   const float* prep_src;  // params pointer the preparation was made from
+  int auto_prepare;       // 1 (default): every op refreshes the prepared weights itself; 0: the caller does
+                          // (dh_params_prepare) after each parameter update
+  bool prep_fwd_valid, prep_vjp_valid;  // what dh_params_prepare has produced for prep_src
   struct Slot { int Nout; size_t hi, lo, bias, scale; int ldw; };  // float offsets into prep (bias: SIZE_MAX = none); scale: 3 floats; ldw: plane row length
   std::vector<Slot> slots;  // per layer: qkv, o, d1, d2, od (= o folded into d1) ; last: orbitals (re | im)
   // reverse pass (dX = G @ W^T): planes of W itself, [D][Kpad]; per layer d2, d1, o, qkv ; last: orbitals

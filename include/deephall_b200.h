@@ -78,6 +78,14 @@ const char* dh_version(void);
 int64_t dh_param_count(const dh_plan* plan);
 int dh_param_layout(const dh_plan* plan, dh_param_entry* entries_host, int32_t* n_entries_host);
 
+/* Prepared weights.  The tensor-core contractions use transposed, two-piece-split copies of the dense kernels
+ * (plus two folded products), kept in a plan-owned buffer.  By default (auto_prepare = 1) every op rebuilds them
+ * from `params` (about 40 tiny launches), because the library cannot see in-place updates.  A caller that
+ * updates the parameters once per optimisation step (train.py:140) can switch that off and call
+ * dh_params_prepare after each update; ops then reuse the copies as long as they are given the same pointer. */
+int dh_params_prepare(dh_plan* plan, const float* params, void* stream);
+int dh_plan_set_auto_prepare(dh_plan* plan, int32_t on);
+
 /* Bytes of device workspace an op needs for a batch of B walkers. */
 int dh_workspace_bytes(const dh_plan* plan, int op, int64_t B, size_t* bytes_host);
 

@@ -424,6 +424,23 @@ def test_vjp_linearity_full_batch(nat):
     assert (g12 - (g1 + 2 * g2)).norm() / g12.norm() < 1e-4
 
 
+def test_prepared_weights_follow_parameter_updates(nat):
+    """The binding re-prepares the split / folded weight copies when the parameter tensor is replaced OR
+    updated in place (dh_params_prepare + torch's version counter)."""
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c1"], 32, burn=0)
+    a = plan.logpsi(flat, x).clone()
+    flat2 = flat.clone()
+    flat2.mul_(1.01)                       # in-place update of a tensor the plan has not seen
+    b = plan.logpsi(flat2, x).clone()
+    flat2.mul_(1.0 / 1.01)                 # in-place update of the tensor the copies were made from
+    c = plan.logpsi(flat2, x).clone()
+    fresh = make_plan(nat, cfg)
+    b_ref = fresh.logpsi((flat * 1.01).contiguous(), x)
+    assert (a - b).abs().max() > 1e-4
+    assert (b - b_ref).abs().max() < 1e-5
+    assert (a - c).abs().max() < 1e-4
+
+
 def test_facade_matches_reference_api(nat):
     """make_network / model.apply / local_energy / make_mcmc_step / make_loss_fn keep the reference's
     call shapes (networks/__init__.py:22, hamiltonian.py:175, mcmc.py:105, loss.py:47)."""
