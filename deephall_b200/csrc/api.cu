@@ -205,10 +205,11 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       // h = feat @ W0 is linear in the features: q|k|v = feat @ (W0 Wqkv) + b, a 4-deep contraction
       ProfScope ps(p, PC_OTHER, 0, s);
       const dh_plan::Slot& q = p->slots[SL_QKV];
-      if ((rc = features_linear(x, p->prep + p->w0qkv, p->prep + q.bias, w.qkv, 3 * D, Bc, nd, s))) return rc;
+      // (jets: only the 10 non-zero rows per electron are written; attention_jets' first-layer form reads them)
+      if ((rc = features_linear(x, p->prep + p->w0qkv, p->prep + q.bias, w.qkv, 3 * D, Bc, nd, jets ? 1 : 0, s))) return rc;
     } else if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s))) return rc;
     { ProfScope ps(p, PC_ATTENTION, 0, s);
-      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, s);
+      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, (l == 0 && p->gemm_impl == 1) ? 1 : 0, s);
       else rc = attention_value(w.qkv, w.att, Bc, nd, s);
       if (rc) return rc; }
     if (p->gemm_impl == 1) {

@@ -10,22 +10,28 @@
 // Phase 3  output jets o_i^(r) = sum_j [ p^(r) v^(0) + p^(0) v^(r) (+ cross terms) ]
 //          one thread owns (row r, 4 head-dim columns, 6 queries); the S-row cross term
 //          2 sum_{j,k} p^(Jk) v^(Jk) is computed by warps whose lanes run over k and warp-reduced.
+// FIRST-LAYER form (L0): q, k, v of the first layer depend on their own electron only, so their jets have
+// just 10 non-zero rows per electron: value | own tangent flows (2) | S | D_a (3) | T_a (3).  The kernel then
+// takes that compressed [B*N*10][3D] tensor (written by the feature kernel), does the score products on the
+// 10 rows, scatters the own-flow products into the full row set (row J(2i+t) gets q_i^(t).k_j, row J(2j+t)
+// gets q_i.k_j^(t)), runs the same softmax jets, and in P.V only touches the v rows that exist.
 #include "kernels.h"
 
 namespace dh {
 
 constexpr int AJ_THREADS = 256;
+constexpr int AJ_RC = 10;      // compressed first-layer rows per electron
 constexpr int AJ_CH = 16;      // head-dim columns per phase-3 step (two staged sub-chunks)
 constexpr int AJ_SUB = 8;      // head-dim columns per staged sub-chunk (one 32-byte row)
 constexpr int AJ_IB = 3, AJ_JB = 6, AJ_OB = 6;
 
 __host__ __device__ inline int aj_np(int N) { return (N + AJ_OB - 1) / AJ_OB * AJ_OB; }  // padded query count
-__host__ __device__ inline size_t aj_smem_floats(int N, int R) {
+__host__ __device__ inline size_t aj_smem_floats(int N, int R, int RI) {
   const int NP = aj_np(N);
-  // four staging regions [N*R][SUB] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [NP][CH]
-  return 4 * (size_t)N * R * AJ_SUB + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + (size_t)NP * AJ_CH;
+  // four staging regions [N*RI][SUB] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [NP][CH]
+  return 4 * (size_t)N * RI * AJ_SUB + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + (size_t)NP * AJ_CH;
 }
-size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R) * sizeof(float); }
+size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R, d.R) * sizeof(float); }
 
 // asynchronous copy of head-dim columns [sub*8, sub*8+8) of NR rows into a staging region
 __device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int64_t ld, int NR, int sub, int hd) {
@@ -61,20 +67,23 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
 
 // NT > 0: the electron count is a compile-time constant (index arithmetic folds, j-loops unroll);
 // NT == 0: generic.
-template <int NT>
+template <int NT, bool L0>
 __global__ void __launch_bounds__(AJ_THREADS, 2)
 attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
   extern __shared__ __align__(16) float smem[];
   const int N = NT > 0 ? NT : dm.N, R = 2 * N + 8, D = dm.D, hd = dm.hd;
+  const int RI = L0 ? AJ_RC : R;  // rows per electron of the input tensor
+  constexpr int JB = L0 ? 2 : AJ_JB;  // keys per thread in phase 1 (fewer rows -> smaller tiles keep all threads busy)
   const int NP = aj_np(N);
   const int hh = blockIdx.x;
   const int64_t b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NR = N * R;
+  const int NR = N * R;    // output rows of one walker
+  const int NRI = N * RI;  // input rows of one walker
   Rows rw(N, true);
   // four staging regions: phase 1 uses (q, k) x 2 buffers, phase 3 two 16-column steps of v
-  auto stg = [&](int u) { return smem + (size_t)u * NR * AJ_SUB; };
-  float* sj = smem + (size_t)4 * NR * AJ_SUB;  // SJ(i,j,r)
+  auto stg = [&](int u) { return smem + (size_t)u * NRI * AJ_SUB; };
+  float* sj = smem + (size_t)4 * NRI * AJ_SUB;  // SJ(i,j,r)
   float* cr = sj + (size_t)N * R * NP;
   float* p0 = cr + (size_t)N * R * NP;      // [j][NP] (query index fastest)
   float* qq = p0 + N * NP;
@@ -82,40 +91,40 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   float* xs = p0 + ((5 * N * NP + 3) & ~3);  // [NP][CH] S-row cross term of the current chunk (16-byte aligned)
 #define SJ(i, j, r) (((j) * R + (r)) * NP + (i))
   const int64_t ld = 3 * (int64_t)D;
-  const float* qbase = qkv + b * NR * ld + hh * hd;
+  const float* qbase = qkv + b * NRI * ld + hh * hd;
   const float* kbase = qbase + D;
   const float* vbase = qbase + 2 * D;
   const float scl = rsqrtf((float)hd);
   const int nchunk = (hd + AJ_CH - 1) / AJ_CH;
   const int nsub = (hd + AJ_SUB - 1) / AJ_SUB;
-  const int IBN = (N + AJ_IB - 1) / AJ_IB, JBN = (N + AJ_JB - 1) / AJ_JB, OBN = NP / AJ_OB;
+  const int IBN = (N + AJ_IB - 1) / AJ_IB, JBN = (N + JB - 1) / JB, OBN = NP / AJ_OB;
 
   // zero the padded query slots so that vectorised reads of sj never see garbage
   for (int t = tid; t < 2 * N * R * NP; t += AJ_THREADS) sj[t] = 0.f;  // sj and cr are contiguous
 
   // ------------------------------------------------------------------ phase 1: score jets
-  const int items1 = R * IBN * JBN;
+  const int items1 = RI * IBN * JBN;
   for (int it0 = 0; it0 < items1; it0 += AJ_THREADS) {
     const int item = it0 + tid;
     const bool active = item < items1;
-    const int r = active ? item % R : 0;
-    const int ib = active ? (item / R) % IBN : 0;
-    const int jb = active ? item / (R * IBN) : 0;
-    const int i0 = ib * AJ_IB, j0 = jb * AJ_JB;
-    float acc[AJ_IB][AJ_JB][3];
+    const int r = active ? item % RI : 0;  // input row (L0: compressed row index)
+    const int ib = active ? (item / RI) % IBN : 0;
+    const int jb = active ? item / (RI * IBN) : 0;
+    const int i0 = ib * AJ_IB, j0 = jb * JB;
+    float acc[AJ_IB][JB][3];
 #pragma unroll
     for (int a = 0; a < AJ_IB; ++a)
 #pragma unroll
-      for (int c = 0; c < AJ_JB; ++c) { acc[a][c][0] = 0.f; acc[a][c][1] = 0.f; acc[a][c][2] = 0.f; }
+      for (int c = 0; c < JB; ++c) { acc[a][c][0] = 0.f; acc[a][c][1] = 0.f; acc[a][c][2] = 0.f; }
     __syncthreads();  // staging regions are free (previous pass / zero-fill above)
-    stage_async(stg(0), qbase, ld, NR, 0, hd);
-    stage_async(stg(1), kbase, ld, NR, 0, hd);  // (one commit group each: q and k of a sub-chunk = 2 groups)
+    stage_async(stg(0), qbase, ld, NRI, 0, hd);
+    stage_async(stg(1), kbase, ld, NRI, 0, hd);  // (one commit group each: q and k of a sub-chunk = 2 groups)
     for (int sb = 0; sb < nsub; ++sb) {
       const float* qs = stg(2 * (sb & 1));
       const float* ks = stg(2 * (sb & 1) + 1);
       if (sb + 1 < nsub) {
-        stage_async(stg(2 * ((sb + 1) & 1)), qbase, ld, NR, sb + 1, hd);
-        stage_async(stg(2 * ((sb + 1) & 1) + 1), kbase, ld, NR, sb + 1, hd);
+        stage_async(stg(2 * ((sb + 1) & 1)), qbase, ld, NRI, sb + 1, hd);
+        stage_async(stg(2 * ((sb + 1) & 1) + 1), kbase, ld, NRI, sb + 1, hd);
         asm volatile("cp.async.wait_group 2;" ::: "memory");  // everything but the two groups just issued
       } else {
         stage_wait_all();
@@ -128,14 +137,14 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
 #pragma unroll
           for (int a = 0; a < AJ_IB; ++a) {
             const int i = min(i0 + a, N - 1);
-            qr[a] = staged(qs, i * R + r, f);
-            q0[a] = staged(qs, i * R, f);
+            qr[a] = staged(qs, i * RI + r, f);
+            q0[a] = staged(qs, i * RI, f);
           }
 #pragma unroll
-          for (int c = 0; c < AJ_JB; ++c) {
+          for (int c = 0; c < JB; ++c) {
             const int j = min(j0 + c, N - 1);
-            const float4 kr = staged(ks, j * R + r, f);
-            const float4 k0 = staged(ks, j * R, f);
+            const float4 kr = staged(ks, j * RI + r, f);
+            const float4 k0 = staged(ks, j * RI, f);
 #pragma unroll
             for (int a = 0; a < AJ_IB; ++a) {
               acc[a][c][0] = dot4(qr[a], k0, acc[a][c][0]);
@@ -151,11 +160,26 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
 #pragma unroll
       for (int a = 0; a < AJ_IB; ++a)
 #pragma unroll
-        for (int c = 0; c < AJ_JB; ++c) {
+        for (int c = 0; c < JB; ++c) {
           const int i = i0 + a, j = j0 + c;
           if (i < N && j < N) {
-            sj[SJ(i, j, r)] = (r == 0) ? acc[a][c][2] * scl : (acc[a][c][0] + acc[a][c][1]) * scl;
-            cr[SJ(i, j, r)] = acc[a][c][2] * scl;
+            if (!L0) {
+              sj[SJ(i, j, r)] = (r == 0) ? acc[a][c][2] * scl : (acc[a][c][0] + acc[a][c][1]) * scl;
+              cr[SJ(i, j, r)] = acc[a][c][2] * scl;
+            } else if (r == 0) {
+              sj[SJ(i, j, 0)] = acc[a][c][2] * scl;
+            } else if (r <= 2) {
+              // own tangent flow t of the query electron moves q_i only, of the key electron k_j only; no other
+              // thread writes these two entries (they coincide when i == j)
+              const int t = r - 1;
+              sj[SJ(i, j, rw.J(2 * i + t))] += acc[a][c][0] * scl;
+              sj[SJ(i, j, rw.J(2 * j + t))] += acc[a][c][1] * scl;
+              if (i == j) cr[SJ(i, j, rw.J(2 * i + t))] = acc[a][c][2] * scl;
+            } else {
+              const int rf = r == 3 ? rw.S() : (r <= 6 ? rw.D(r - 4) : rw.T(r - 7));
+              sj[SJ(i, j, rf)] = (acc[a][c][0] + acc[a][c][1]) * scl;
+              cr[SJ(i, j, rf)] = acc[a][c][2] * scl;
+            }
           }
         }
     }
@@ -225,13 +249,13 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   const int rS = rw.S(), rT0 = rw.T(0), rD0 = rw.D(0);
   // a 16-column step of v = two staged sub-chunks; steps are double-buffered over the four regions
   __syncthreads();
-  stage_async(stg(0), vbase, ld, NR, 0, hd);
-  stage_async(stg(1), vbase, ld, NR, 1, hd);
+  stage_async(stg(0), vbase, ld, NRI, 0, hd);
+  stage_async(stg(1), vbase, ld, NRI, 1, hd);
   for (int ch = 0; ch < nchunk; ++ch) {
-    const float* vpair = stg(2 * (ch & 1));  // sub-chunk u of this step at vpair + u * NR * AJ_SUB
+    const float* vpair = stg(2 * (ch & 1));  // sub-chunk u of this step at vpair + u * NRI * AJ_SUB
     if (ch + 1 < nchunk) {
-      stage_async(stg(2 * ((ch + 1) & 1)), vbase, ld, NR, 2 * (ch + 1), hd);
-      stage_async(stg(2 * ((ch + 1) & 1) + 1), vbase, ld, NR, 2 * (ch + 1) + 1, hd);
+      stage_async(stg(2 * ((ch + 1) & 1)), vbase, ld, NRI, 2 * (ch + 1), hd);
+      stage_async(stg(2 * ((ch + 1) & 1) + 1), vbase, ld, NRI, 2 * (ch + 1) + 1, hd);
       asm volatile("cp.async.wait_group 2;" ::: "memory");
     } else {
       stage_wait_all();
@@ -245,8 +269,9 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
       for (int a = 0; a < AJ_OB; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kk = lane; kk < 2 * N; kk += 32) {
         const int r = rw.J(kk);
-        for (int j = 0; j < N; ++j) {
-          const float4 v = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R + r, f4 & 1);
+        // L0: v_j moves along flow kk only if j is that flow's electron
+        for (int j = L0 ? (kk >> 1) : 0; j < (L0 ? (kk >> 1) + 1 : N); ++j) {
+          const float4 v = staged(vpair + (size_t)(f4 >> 1) * NRI * AJ_SUB, L0 ? j * RI + 1 + (kk & 1) : j * R + r, f4 & 1);
           const float2* pp = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
           const float2 pa = pp[0], pb = pp[1], pc = pp[2];
           axpy4(acc[0], pa.x, v); axpy4(acc[1], pa.y, v);
@@ -275,22 +300,27 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
       for (int a = 0; a < AJ_OB; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool isT = r >= rT0;
       const int rd = isT ? rD0 + (r - rT0) : 0;
+      // L0: input row of v that carries output row r (own-flow rows exist for one electron only)
+      const bool isJ = r >= 1 && r <= 2 * N;
+      const int jown = isJ ? (r - 1) >> 1 : -1;
+      const int rin = !L0 ? r : (isJ ? 1 + ((r - 1) & 1) : (r == rS ? 3 : (isT ? 7 + (r - rT0) : (r == 0 ? 0 : 4 + (r - rD0)))));
+      const int rdin = L0 ? 4 + (r - rT0) : rd;
       for (int j = 0; j < N; ++j) {
-        const float4 v0 = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R, f4 & 1);
+        const float4 v0 = staged(vpair + (size_t)(f4 >> 1) * NRI * AJ_SUB, j * RI, f4 & 1);
         const float2* pr = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
         const float2 a0 = pr[0], a1 = pr[1], a2 = pr[2];
         axpy4(acc[0], a0.x, v0); axpy4(acc[1], a0.y, v0);
         axpy4(acc[2], a1.x, v0); axpy4(acc[3], a1.y, v0);
         axpy4(acc[4], a2.x, v0); axpy4(acc[5], a2.y, v0);
-        if (r != 0) {
-          const float4 vr = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R + r, f4 & 1);
+        if (r != 0 && (!L0 || !isJ || j == jown)) {
+          const float4 vr = staged(vpair + (size_t)(f4 >> 1) * NRI * AJ_SUB, j * RI + rin, f4 & 1);
           const float2* pz = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, 0));
           const float2 b0 = pz[0], b1 = pz[1], b2 = pz[2];
           axpy4(acc[0], b0.x, vr); axpy4(acc[1], b0.y, vr);
           axpy4(acc[2], b1.x, vr); axpy4(acc[3], b1.y, vr);
           axpy4(acc[4], b2.x, vr); axpy4(acc[5], b2.y, vr);
           if (isT) {
-            const float4 vd = staged(vpair + (size_t)(f4 >> 1) * NR * AJ_SUB, j * R + rd, f4 & 1);
+            const float4 vd = staged(vpair + (size_t)(f4 >> 1) * NRI * AJ_SUB, j * RI + rdin, f4 & 1);
             const float2* pd = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, rd));
             const float2 c0 = pd[0], c1 = pd[1], c2 = pd[2];
             axpy4(acc[0], 2.f * c0.x, vd); axpy4(acc[1], 2.f * c0.y, vd);
@@ -324,28 +354,30 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
 #undef SJ
 }
 
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s) {
   if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
-  const size_t smem = attention_jets_smem(d);
+  const size_t smem = aj_smem_floats(d.N, d.R, layer0 ? AJ_RC : d.R) * sizeof(float);
   if (smem > 227 * 1024) return -2;
   dim3 grid((unsigned)d.H, (unsigned)B);
-#define DH_AJ_LAUNCH(NT)                                                                                              \
+#define DH_AJ_LAUNCH(NT, LZ)                                                                                          \
   do {                                                                                                                \
     static size_t attr_smem = 0;                                                                                      \
     if (smem > attr_smem) {                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel<NT, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       if (e != cudaSuccess) return (int)e;                                                                            \
       attr_smem = smem;                                                                                               \
     }                                                                                                                 \
-    attention_jets_kernel<NT><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                                             \
+    attention_jets_kernel<NT, LZ><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                                         \
   } while (0)
+#define DH_AJ_BOTH(NT) do { if (layer0) DH_AJ_LAUNCH(NT, true); else DH_AJ_LAUNCH(NT, false); } while (0)
   switch (d.N) {
-    case 6: DH_AJ_LAUNCH(6); break;
-    case 10: DH_AJ_LAUNCH(10); break;
-    case 12: DH_AJ_LAUNCH(12); break;
-    case 16: DH_AJ_LAUNCH(16); break;
-    default: DH_AJ_LAUNCH(0); break;
+    case 6: DH_AJ_BOTH(6); break;
+    case 10: DH_AJ_BOTH(10); break;
+    case 12: DH_AJ_BOTH(12); break;
+    case 16: DH_AJ_BOTH(16); break;
+    default: DH_AJ_BOTH(0); break;
   }
+#undef DH_AJ_BOTH
 #undef DH_AJ_LAUNCH
   return (int)cudaGetLastError();
 }

@@ -50,13 +50,16 @@ struct NetDims {
 };
 int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDims d, cudaStream_t s);
 // out[rows, Nout] = feature jets @ W[4][Nout] (+ bias on value rows)
+//   compressed != 0 (jets only): only the 10 rows per electron that are non-zero are written, in the order
+//   value | own tangent flows (2) | S | D_a (3) | T_a (3)
 int features_linear(const float* x, const float* W, const float* bias, float* out, int Nout, int64_t B, NetDims d,
-                    cudaStream_t s);
+                    int compressed, cudaStream_t s);
 // out = LN(a + (tanh_mode ? tanh(b) : b)) with jets; a/b/out are [B*N*R, D]
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s);
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
+// layer0 != 0: qkv is the compressed first-layer tensor [B*N*10][3D] (features_linear with compressed = 1)
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s);
 size_t attention_jets_smem(NetDims d);
 
 // ---- tail_kernels.cu

@@ -16,7 +16,8 @@ namespace dh {
 // (+ bias on the value row) -- also used for the FIRST layer's q|k|v, whose input h = feat @ W0
 // is linear in the features, so q|k|v = feat @ (W0 Wqkv) + b needs no 256-deep contraction.
 __global__ void features_dense0_kernel(const float* __restrict__ x, const float* __restrict__ W0,
-                                       const float* __restrict__ bias, float* __restrict__ h, int Nout, NetDims dm) {
+                                       const float* __restrict__ bias, float* __restrict__ h, int Nout, NetDims dm,
+                                       int compressed) {
   extern __shared__ float feat[];  // [R][4]
   const int N = dm.N, R = dm.R, D = Nout;
   const int64_t bi = blockIdx.x;
@@ -50,20 +51,24 @@ __global__ void features_dense0_kernel(const float* __restrict__ x, const float*
     }
   }
   __syncthreads();
-  float* out = h + bi * R * D;
+  const int Rout = compressed ? 10 : R;
+  float* out = h + bi * Rout * D;
+  Rows rwc(N, true);
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float w0 = W0[d], w1 = W0[D + d], w2 = W0[2 * D + d], w3 = W0[3 * D + d];
-    for (int r = 0; r < R; ++r) {
+    for (int ro = 0; ro < Rout; ++ro) {
+      // compressed: value | own tangent flows | S | D_a | T_a  (every other row of the full layout is zero)
+      const int r = !compressed ? ro : (ro == 0 ? 0 : (ro <= 2 ? rwc.J(2 * i + ro - 1) : rwc.S() + (ro - 3)));
       const float* f = feat + r * 4;
       float v = fmaf(f[0], w0, fmaf(f[1], w1, fmaf(f[2], w2, f[3] * w3)));
       if (r == 0 && bias != nullptr) v += bias[d];
-      out[(int64_t)r * D + d] = v;
+      out[(int64_t)ro * D + d] = v;
     }
   }
 }
 
 int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDims d, cudaStream_t s) {
-  return features_linear(x, W0, nullptr, h, d.D, B, d, s);
+  return features_linear(x, W0, nullptr, h, d.D, B, d, 0, s);
 }
 
 // value-only form (R = 1): one warp per (walker, electron), eight per block
@@ -86,14 +91,14 @@ features_value_kernel(const float* __restrict__ x, const float* __restrict__ W, 
 }
 
 int features_linear(const float* x, const float* W, const float* bias, float* out, int Nout, int64_t B, NetDims d,
-                    cudaStream_t s) {
+                    int compressed, cudaStream_t s) {
   if (d.R == 1) {
     const int64_t rows = B * d.N;
     features_value_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, W, bias, out, Nout, rows, d);
     return (int)cudaGetLastError();
   }
   int threads = Nout >= 256 ? 256 : ((Nout + 31) / 32 * 32);
-  features_dense0_kernel<<<(unsigned)(B * d.N), threads, d.R * 4 * sizeof(float), s>>>(x, W, bias, out, Nout, d);
+  features_dense0_kernel<<<(unsigned)(B * d.N), threads, d.R * 4 * sizeof(float), s>>>(x, W, bias, out, Nout, d, compressed);
   return (int)cudaGetLastError();
 }
 
