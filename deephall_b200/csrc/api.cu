@@ -198,7 +198,11 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   NetDims nd{N, R, D, p->H, p->hd, p->cfg.n_up};
   TailDims td{N, R, p->L, p->K, p->twoQ, p->cfg.n_up};
   int rc;
-  { ProfScope ps(p, PC_OTHER, 0, s); if ((rc = features_dense0(x, P + p->off_W0, w.h, Bc, nd, s))) return rc; }
+  // jets on the tensor-core path: Dense_0's output has 10 non-zero jet rows per electron; it is written in that
+  // compressed form (into t1, which is free until the second Dense of the layer) and expanded by the first LayerNorm
+  const bool h0_comp = jets && p->gemm_impl == 1 && p->nl > 0;
+  { ProfScope ps(p, PC_OTHER, 0, s);
+    if ((rc = features_linear(x, P + p->off_W0, nullptr, h0_comp ? w.t1 : w.h, D, Bc, nd, h0_comp ? 1 : 0, s))) return rc; }
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
     if (l == 0 && p->gemm_impl == 1) {
@@ -219,7 +223,10 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
       if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
     }
-    { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s))) return rc; }
+    { ProfScope ps(p, PC_LAYERNORM, 0, s);
+      if (l == 0 && h0_comp) rc = residual_layernorm_ex(w.t1, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 1, s);
+      else rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s);
+      if (rc) return rc; }
     if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s))) return rc;
     { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc; }
   }

@@ -57,6 +57,9 @@ int features_linear(const float* x, const float* W, const float* bias, float* ou
 // out = LN(a + (tanh_mode ? tanh(b) : b)) with jets; a/b/out are [B*N*R, D]
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s);
+// a_comp != 0 (jets): `a` holds only the 10 non-zero rows per electron of the first layer's Dense_0 output
+int residual_layernorm_ex(const float* a, const float* b, const float* scale, const float* bias, float* out,
+                          int64_t B, NetDims d, int tanh_mode, int a_comp, cudaStream_t s);
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
 // layer0 != 0: qkv is the compressed first-layer tensor [B*N*10][3D] (features_linear with compressed = 1)
 int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s);

@@ -128,14 +128,17 @@ template <bool TANH, bool VEC4>
 __global__ void __launch_bounds__(128)
 residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                           const float* __restrict__ scale, const float* __restrict__ bias,
-                          float* __restrict__ out, int64_t groups, NetDims dm) {
+                          float* __restrict__ out, int64_t groups, NetDims dm, int a_comp) {
   const int lane = threadIdx.x & 31;
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= groups) return;
   const int R = dm.R, D = dm.D, N = dm.N;
   const int vpl = VEC4 ? LN_VPL : (D >> 5);
   const float invD = 1.0f / (float)D;
-  const float* ga = a + g * R * D;
+  // a_comp: `a` is the first layer's Dense_0 output in compressed form, 10 rows per electron
+  // (value | own tangent flows | S | D_a | T_a); every other jet row of it is zero
+  const int iel = (int)(g % N);
+  const float* ga = a + g * (a_comp ? 10 : R) * D;
   const float* gb = b + g * R * D;
   float* go = out + g * R * D;
 
@@ -159,6 +162,20 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
 #pragma unroll
       for (int v = 0; v < LN_VPL; ++v)
         if (v < vpl) base[lane + 32 * v] = src[v];
+    }
+  };
+
+  auto lda = [&](int r, float (&dst)[LN_VPL]) {  // row r of `a`
+    if (!a_comp) { ldrow(ga + (int64_t)r * D, dst); return; }
+    int rc;
+    if (r == 0) rc = 0;
+    else if (r <= 2 * N) rc = ((r - 1) >> 1) == iel ? 1 + ((r - 1) & 1) : -1;
+    else rc = 3 + (r - (2 * N + 1));
+    if (rc < 0) {
+#pragma unroll
+      for (int v = 0; v < LN_VPL; ++v) dst[v] = 0.f;
+    } else {
+      ldrow(ga + (int64_t)rc * D, dst);
     }
   };
 
@@ -214,7 +231,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   auto load_first = [&](int r, float (&cr)[LN_VPL], float (&braw)[LN_VPL], float& m_c0c, float& m_cc) {
     float s1 = 0.f;
     float av[LN_VPL];
-    ldrow(ga + (int64_t)r * D, av);
+    lda(r, av);
     ldrow(gb + (int64_t)r * D, braw);
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) {
@@ -239,7 +256,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   auto load_second = [&](int r, const float (&extra)[LN_VPL], float (&cr)[LN_VPL], float& m_c0c) {
     float s1 = 0.f;
     float av[LN_VPL], bv[LN_VPL];
-    ldrow(ga + (int64_t)r * D, av);
+    lda(r, av);
     ldrow(gb + (int64_t)r * D, bv);
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) {
@@ -373,7 +390,12 @@ layernorm_value256_kernel(const float* __restrict__ a, const float* __restrict__
 
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s) {
-  if (d.D % 32 != 0 || d.D > 32 * LN_VPL) return -2;
+  return residual_layernorm_ex(a, b, scale, bias, out, B, d, tanh_mode, 0, s);
+}
+
+int residual_layernorm_ex(const float* a, const float* b, const float* scale, const float* bias, float* out,
+                          int64_t B, NetDims d, int tanh_mode, int a_comp, cudaStream_t s) {
+  if (d.D % 32 != 0 || d.D > 32 * LN_VPL || (a_comp && d.R == 1)) return -2;
   if (d.R == 1 && d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
                                   reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
     const int64_t rows = B * d.N;
@@ -388,11 +410,11 @@ int residual_layernorm(const float* a, const float* b, const float* scale, const
   const bool vec4 = d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
                                     reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
   if (tanh_mode) {
-    if (vec4) residual_layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
-    else residual_layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+    if (vec4) residual_layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
+    else residual_layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
   } else {
-    if (vec4) residual_layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
-    else residual_layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d);
+    if (vec4) residual_layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
+    else residual_layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
   }
   return (int)cudaGetLastError();
 }
