@@ -28,8 +28,8 @@ constexpr int AJ_IB = 3, AJ_JB = 6, AJ_OB = 6;
 __host__ __device__ inline int aj_np(int N) { return (N + AJ_OB - 1) / AJ_OB * AJ_OB; }  // padded query count
 __host__ __device__ inline size_t aj_smem_floats(int N, int R, int RI) {
   const int NP = aj_np(N);
-  // four staging regions [N*RI][SUB] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [NP][CH]
-  return 4 * (size_t)N * RI * AJ_SUB + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + (size_t)NP * AJ_CH;
+  // four staging regions [N*RI][SUB] ; sj, cr : [N][R][NP] ; p0, qq : [N][NP] ; dd : [3][N][NP] ; xs : [2][NP][CH]
+  return 4 * (size_t)N * RI * AJ_SUB + 2 * (size_t)N * R * NP + ((5 * (size_t)N * NP + 3) & ~(size_t)3) + 2 * (size_t)NP * AJ_CH;
 }
 size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R, d.R) * sizeof(float); }
 
@@ -67,7 +67,9 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
 
 // NT > 0: the electron count is a compile-time constant (index arithmetic folds, j-loops unroll);
 // NT == 0: generic.
-template <int NT, bool L0>
+// Q12 (7 <= N <= 12): phase 3 gives every thread all 12 (padded) queries of one (row, 4 columns) -- twice the FMAs
+// per shared-memory wavefront -- and the two halves of the block work on two 16-column steps at once.
+template <int NT, bool L0, bool Q12>
 __global__ void __launch_bounds__(AJ_THREADS, 2)
 attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
   extern __shared__ __align__(16) float smem[];
@@ -247,6 +249,98 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   // ------------------------------------------------------------------ phase 3: o = P V jets
   float* obase = o + b * NR * (int64_t)D + hh * hd;
   const int rS = rw.S(), rT0 = rw.T(0), rD0 = rw.D(0);
+  if (Q12) {
+    // two 16-column steps at a time: threads 0..127 take step cp (regions 0, 1), threads 128..255 step cp + 1
+    // (regions 2, 3); thread = (f4, r) owns all 12 query slots
+    for (int cp = 0; cp < nchunk; cp += 2) {
+      __syncthreads();  // staging regions and xs are free
+      for (int u = 0; u < 4; ++u)
+        if (cp + (u >> 1) < nchunk) stage_async(stg(u), vbase, ld, NRI, 2 * cp + u, hd);
+      stage_wait_all();
+      __syncthreads();
+      // ---- S-row cross term of both steps: warp item = (step, query block, float4), lanes = k
+      for (int wi = warp; wi < 2 * OBN * 4; wi += AJ_THREADS / 32) {
+        const int c2 = wi / (OBN * 4), ob = (wi >> 2) % OBN, f4 = wi & 3;
+        if (cp + c2 >= nchunk) continue;
+        const float* vpair = stg(2 * c2);
+        float4 acc[AJ_OB];
+#pragma unroll
+        for (int a = 0; a < AJ_OB; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int kk = lane; kk < 2 * N; kk += 32) {
+          const int r = rw.J(kk);
+          for (int j = L0 ? (kk >> 1) : 0; j < (L0 ? (kk >> 1) + 1 : N); ++j) {
+            const float4 v = staged(vpair + (size_t)(f4 >> 1) * NRI * AJ_SUB, L0 ? j * RI + 1 + (kk & 1) : j * R + r, f4 & 1);
+            const float2* pp = reinterpret_cast<const float2*>(sj + SJ(ob * AJ_OB, j, r));
+            const float2 pa = pp[0], pb = pp[1], pc = pp[2];
+            axpy4(acc[0], pa.x, v); axpy4(acc[1], pa.y, v);
+            axpy4(acc[2], pb.x, v); axpy4(acc[3], pb.y, v);
+            axpy4(acc[4], pc.x, v); axpy4(acc[5], pc.y, v);
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < AJ_OB; ++a) {
+          acc[a].x = warp_sum(acc[a].x); acc[a].y = warp_sum(acc[a].y);
+          acc[a].z = warp_sum(acc[a].z); acc[a].w = warp_sum(acc[a].w);
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int a = 0; a < AJ_OB; ++a)
+            *reinterpret_cast<float4*>(xs + (c2 * NP + ob * AJ_OB + a) * AJ_CH + f4 * 4) =
+                make_float4(2.f * acc[a].x, 2.f * acc[a].y, 2.f * acc[a].z, 2.f * acc[a].w);
+        }
+      }
+      __syncthreads();
+      // ---- all rows
+      const int c2 = tid >> 7, idx = tid & 127;
+      if (idx < 4 * R && cp + c2 < nchunk) {
+        const int f4 = idx & 3, r = idx >> 2;
+        const float* vsub = stg(2 * c2) + (size_t)(f4 >> 1) * NRI * AJ_SUB;
+        const int fh = f4 & 1;
+        float4 acc[12];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool isT = r >= rT0;
+        const int rd = isT ? rD0 + (r - rT0) : 0;
+        const bool isJ = r >= 1 && r <= 2 * N;
+        const int jown = isJ ? (r - 1) >> 1 : -1;
+        const int rin = !L0 ? r : (isJ ? 1 + ((r - 1) & 1) : (r == rS ? 3 : (isT ? 7 + (r - rT0) : (r == 0 ? 0 : 4 + (r - rD0)))));
+        const int rdin = L0 ? 4 + (r - rT0) : rd;
+        auto axpy12 = [&](const float* prow, float w, const float4& v) {  // acc[i] += w * prow[i] * v, i < 12
+          const float4* p4 = reinterpret_cast<const float4*>(prow);
+          const float4 a0 = p4[0], a1 = p4[1], a2 = p4[2];
+          axpy4(acc[0], w * a0.x, v); axpy4(acc[1], w * a0.y, v); axpy4(acc[2], w * a0.z, v); axpy4(acc[3], w * a0.w, v);
+          axpy4(acc[4], w * a1.x, v); axpy4(acc[5], w * a1.y, v); axpy4(acc[6], w * a1.z, v); axpy4(acc[7], w * a1.w, v);
+          axpy4(acc[8], w * a2.x, v); axpy4(acc[9], w * a2.y, v); axpy4(acc[10], w * a2.z, v); axpy4(acc[11], w * a2.w, v);
+        };
+        for (int j = 0; j < N; ++j) {
+          axpy12(sj + SJ(0, j, r), 1.f, staged(vsub, j * RI, fh));
+          if (r != 0 && (!L0 || !isJ || j == jown)) {
+            axpy12(sj + SJ(0, j, 0), 1.f, staged(vsub, j * RI + rin, fh));
+            if (isT) axpy12(sj + SJ(0, j, rd), 2.f, staged(vsub, j * RI + rdin, fh));
+          }
+        }
+        const int dcol = (cp + c2) * AJ_CH + f4 * 4;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          if (i < N) {
+            float4 out = acc[i];
+            if (r == rS) {
+              const float4 x4 = *reinterpret_cast<const float4*>(xs + (c2 * NP + i) * AJ_CH + f4 * 4);
+              out.x += x4.x; out.y += x4.y; out.z += x4.z; out.w += x4.w;
+            }
+            float* dst = obase + (int64_t)(i * R + r) * D + dcol;
+            if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = out;
+            else {
+              if (dcol < hd) dst[0] = out.x;
+              if (dcol + 1 < hd) dst[1] = out.y;
+              if (dcol + 2 < hd) dst[2] = out.z;
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
   // a 16-column step of v = two staged sub-chunks; steps are double-buffered over the four regions
   __syncthreads();
   stage_async(stg(0), vbase, ld, NRI, 0, hd);
@@ -363,11 +457,12 @@ int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0,
   do {                                                                                                                \
     static size_t attr_smem = 0;                                                                                      \
     if (smem > attr_smem) {                                                                                           \
-      cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel<NT, LZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaError_t e = cudaFuncSetAttribute(attention_jets_kernel<NT, LZ, (NT >= 7 && NT <= 12)>,                    \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
       if (e != cudaSuccess) return (int)e;                                                                            \
       attr_smem = smem;                                                                                               \
     }                                                                                                                 \
-    attention_jets_kernel<NT, LZ><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                                         \
+    attention_jets_kernel<NT, LZ, (NT >= 7 && NT <= 12)><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                  \
   } while (0)
 #define DH_AJ_BOTH(NT) do { if (layer0) DH_AJ_LAUNCH(NT, true); else DH_AJ_LAUNCH(NT, false); } while (0)
   switch (d.N) {
