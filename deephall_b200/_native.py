@@ -32,6 +32,8 @@ class dh_config(C.Structure):
         ("interaction_strength", C.c_float),
         ("radius", C.c_float),
         ("chunk_walkers", C.c_int32),
+        ("network_type", C.c_int32),
+        ("cf_flux", C.c_int32),
     ]
 
 
@@ -102,7 +104,7 @@ def _check(rc: int, what: str):
 
 
 def _ptr(t):
-    if t is None:
+    if t is None or t.numel() == 0:
         return None
     assert t.is_cuda and t.is_contiguous(), "device, contiguous tensors only"
     return C.c_void_p(t.data_ptr())
@@ -121,13 +123,15 @@ class Plan:
     """One plan per (device, configuration).  Thin, stream-ordered wrappers over the C ABI."""
 
     def __init__(self, nspins=(3, 0), flux=2, ndets=1, num_heads=4, heads_dim=64, num_layers=2,
-                 interaction_type="coulomb", interaction_strength=1.0, radius=None, chunk_walkers=0):
+                 interaction_type="coulomb", interaction_strength=1.0, radius=None, chunk_walkers=0,
+                 network_type="psiformer", cf_flux=1):
         _need_cuda()
         self.lib = load()
         self.cfg = dh_config(
             int(nspins[0]), int(nspins[1]), int(flux), int(ndets), int(num_heads), int(heads_dim), int(num_layers),
             0 if str(interaction_type) == "coulomb" else 1, float(interaction_strength),
             float(radius) if radius else 0.0, int(chunk_walkers),
+            1 if str(network_type) == "laughlin" else 0, int(cf_flux),
         )
         self.N = int(nspins[0]) + int(nspins[1])
         self.R = 2 * self.N + 8
@@ -195,6 +199,8 @@ class Plan:
         return {c: {"ms": ms[i], "count": cnt[i], "flops": fl[i]} for i, c in enumerate(PROFILE_CATEGORIES)}
 
     def _prepare(self, params):
+        if params.numel() == 0:  # parameter-free network (Laughlin)
+            return
         # identity + in-place version of the tensor the copies were made from; the strong reference keeps its
         # memory from being recycled for a different tensor at the same address
         prev = self._prepared
@@ -274,7 +280,7 @@ class Plan:
     def logpsi_vjp(self, params, x, cot, want_logpsi=False):
         self._prepare(params)
         B = x.shape[0]
-        grad = torch.empty_like(params)
+        grad = torch.zeros_like(params)
         lpsi = torch.empty((B, 2), dtype=torch.float32, device=x.device) if want_logpsi else None
         ws = self.workspace(OP_VJP, B)
         _check(self.lib.dh_logpsi_vjp(self.handle, _ptr(params), _ptr(x), B, _ptr(cot), _ptr(grad), _ptr(lpsi), _ptr(ws),

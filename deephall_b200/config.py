@@ -34,7 +34,7 @@ class PsiformerNetwork:  # config.py:92-97
 
 @dc.dataclass
 class Network:  # config.py:100-104
-    type: str = "psiformer"  # "psiformer" | "laughlin" (laughlin: not on the CUDA path yet)
+    type: str = "psiformer"  # "psiformer" | "laughlin" (analytic ground state, networks/laughlin.py)
     orbital: str = "full"  # "full" | "sparse" (sparse: next row N4)
     psiformer: PsiformerNetwork = dc.field(default_factory=PsiformerNetwork)
 

@@ -64,7 +64,34 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->prof_on = false;
   p->prof_used = 0;
   p->launches = 0;
+  p->laughlin = cfg->network_type == 1 ? 1 : 0;
+  p->twoQ1 = 0;
+  if (cfg->network_type != 0 && cfg->network_type != 1) { delete p; return DH_E_BADARG; }
   if (p->N > 16 || p->D % 32 != 0 || p->D > 256 || p->hd % 4 != 0) { delete p; return DH_E_UNSUPPORTED; }
+  if (p->laughlin) {
+    // networks/laughlin.py:33-37: Q1 = flux/2 - p (N - 1); only the ground state N = 2 Q1 + 1 is built
+    const int pf = cfg->cf_flux > 0 ? cfg->cf_flux : 1;
+    p->twoQ1 = cfg->flux - 2 * pf * (p->N - 1);
+    if (p->twoQ1 != p->N - 1) { delete p; return DH_E_UNSUPPORTED; }
+    p->L = p->N;
+    p->K = 1;
+    p->nl = 0;
+    p->LNK = p->L * p->N * p->K;
+    p->gemm_impl = 0;
+    p->tc_f16 = 0;
+    p->tc_merged = 0;
+    p->ee_par = -1;
+    p->orb_re_k = p->orb_re_b = p->orb_im_k = p->orb_im_b = -1;
+    p->off_W0 = -1;
+    p->w0qkv = p->fold_tmp = p->cot_scale = 0;
+    std::vector<double> ones(p->L, 1.0);
+    cudaError_t e1 = cudaMalloc(&p->d_normfac, p->L * sizeof(double));
+    if (e1 != cudaSuccess) { delete p; return (int)e1; }
+    e1 = cudaMemcpy(p->d_normfac, ones.data(), p->L * sizeof(double), cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess) { cudaFree(p->d_normfac); delete p; return (int)e1; }
+    *out = p;
+    return 0;
+  }
   const int D = p->D, H = p->H, hd = p->hd, N = p->N, L = p->L, K = p->K;
   const std::string pl = "PsiformerLayers_0/";
   add_entry(p, pl + "Dense_0/kernel", {4, D}, &p->off_W0);
@@ -198,6 +225,22 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   NetDims nd{N, R, D, p->H, p->hd, p->cfg.n_up};
   TailDims td{N, R, p->L, p->K, p->twoQ, p->cfg.n_up};
   int rc;
+  if (p->laughlin) {
+    // analytic Laughlin ground state: orbital-matrix jets straight from the coordinates, then the same tail
+    TailDims tl{N, R, p->L, 1, p->twoQ1, p->cfg.n_up};
+    ProfScope pst(p, PC_TAIL, 0, s, 3);
+    if ((rc = laughlin_orbital_jets(x, p->d_normfac, w.Mj, Bc, tl, s))) return rc;
+    if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, tl, s))) return rc;
+    fa.ld = w.ld;
+    fa.x = x;
+    fa.ee_par = nullptr;
+    fa.Q = p->Q;
+    fa.radius = p->radius;
+    fa.interaction_strength = p->cfg.interaction_strength;
+    fa.interaction_type = p->cfg.interaction_type;
+    fa.lpjet = jets ? w.lpjet : nullptr;
+    return finalize(fa, Bc, tl, s);
+  }
   // jets on the tensor-core path: Dense_0's output has 10 non-zero jet rows per electron; it is written in that
   // compressed form (into t1, which is free until the second Dense of the layer) and expanded by the first LayerNorm
   const bool h0_comp = jets && p->gemm_impl == 1 && p->nl > 0;
@@ -382,7 +425,9 @@ int prepare_weights_vjp(dh_plan* p, const float* P, cudaStream_t s) {
 }
 
 extern "C" int dh_params_prepare(dh_plan* p, const float* params, void* stream) {
-  if (!p || !params) return DH_E_BADARG;
+  if (!p) return DH_E_BADARG;
+  if (p->laughlin) return 0;
+  if (!params) return DH_E_BADARG;
   int rc = prepare_weights_now(p, params, (cudaStream_t)stream);
   if (rc) return rc;
   p->prep_src = params;
@@ -404,7 +449,7 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
                        float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (!p || B < 0) return DH_E_BADARG;
   if (B == 0) return 0;
-  if (!params || !x) return DH_E_BADARG;
+  if ((!params && p->nparams > 0) || !x) return DH_E_BADARG;
   if (B == 0) return 0;
   const int64_t chunk = pick_chunk(p, jets, B);
   float* base = align_ws(ws);
@@ -430,7 +475,7 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
 extern "C" int dh_logpsi(dh_plan* p, const float* params, const float* x, int64_t B, float* out_logpsi,
                          void* ws, size_t ws_bytes, void* stream) {
   if (!out_logpsi && B > 0) return DH_E_BADARG;
-  if (p && params && B > 0) { int rc = prepare_weights(p, params, (cudaStream_t)stream); if (rc) return rc; }
+  if (p && params && B > 0 && !p->laughlin) { int rc = prepare_weights(p, params, (cudaStream_t)stream); if (rc) return rc; }
   return run_forward(p, params, x, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_logpsi, ws,
                      ws_bytes, (cudaStream_t)stream);
 }
@@ -438,7 +483,7 @@ extern "C" int dh_logpsi(dh_plan* p, const float* params, const float* x, int64_
 extern "C" int dh_local_energy(dh_plan* p, const float* params, const float* x, int64_t B, float* out_el,
                                float* out_kinetic, float* out_potential, float* out_lz, float* out_lz2,
                                float* out_l2, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
-  if (p && params && B > 0) { int rc = prepare_weights(p, params, (cudaStream_t)stream); if (rc) return rc; }
+  if (p && params && B > 0 && !p->laughlin) { int rc = prepare_weights(p, params, (cudaStream_t)stream); if (rc) return rc; }
   return run_forward(p, params, x, B, true, out_el, out_kinetic, out_potential, out_lz, out_lz2, out_l2,
                      out_logpsi, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -477,7 +522,7 @@ extern "C" int dh_init_walkers(dh_plan* p, float* x, int64_t B, uint64_t seed, u
 extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t B, int32_t steps, float width,
                              uint64_t seed, uint64_t offset, uint64_t subsequence0, const float* randoms,
                              long long* out_naccept, float* out_lp, void* ws, size_t ws_bytes, void* stream) {
-  if (!p || !params || !x || !out_naccept || steps < 0) return DH_E_BADARG;
+  if (!p || (!params && p->nparams > 0) || !x || !out_naccept || steps < 0) return DH_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (B == 0) return (int)cudaMemsetAsync(out_naccept, 0, sizeof(long long), s);
   float* base = align_ws(ws);
@@ -490,7 +535,7 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
   int rc;
   DH_CHECK(cudaMemsetAsync(out_naccept, 0, sizeof(long long), s));
   // mcmc.py:142 -- log-probability of the incoming configurations
-  if ((rc = prepare_weights(p, params, s))) return rc;
+  if (!p->laughlin && (rc = prepare_weights(p, params, s))) return rc;
   if ((rc = run_forward(p, params, x, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase,
                         fwd_bytes, s)))
     return rc;

@@ -89,7 +89,12 @@ size_t vjp_ws_floats(const dh_plan* p, int64_t Bc) { return carve_vjp(p, nullptr
 
 extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot,
                              float* grad, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
-  if (!p || !P || !grad || B < 0 || (B > 0 && (!x || !cot))) return DH_E_BADARG;
+  if (!p) return DH_E_BADARG;
+  if (p->laughlin) {  // no parameters: nothing to differentiate; log psi on request
+    if (out_logpsi && B > 0) return dh_logpsi(p, P, x, B, out_logpsi, ws, ws_bytes, stream);
+    return 0;
+  }
+  if (!P || !grad || B < 0 || (B > 0 && (!x || !cot))) return DH_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
   if (B == 0) return 0;

@@ -74,6 +74,9 @@ struct TailDims {
 // c: [B*N*R, 2*L*N*K] (re block | im block) -> M jets [B][K][R][N][N] complex
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s);
+// Laughlin ground-state orbital matrix jets (networks/laughlin.py:59-71): Mj [B][1][R][N][N] complex; d.L == d.N,
+// d.twoQ = 2 Q1 = N - 1, `ones` = L doubles equal to 1
+int laughlin_orbital_jets(const float* x, const double* ones, float* Mj, int64_t B, TailDims d, cudaStream_t s);
 // M jets -> per-det logdet jets ld [B][K][R] complex
 int logdet_jets(const float* Mj, float* ld, int64_t B, TailDims d, cudaStream_t s);
 // same, also writing the inverse of the value matrix ([b][kd][N][N] complex) when Minv != nullptr

@@ -17,6 +17,8 @@ struct LayerOff {
 struct dh_plan {
   dh_config cfg;
   int N, L, K, D, H, hd, nl, twoQ, LNK;
+  int laughlin;  // analytic Laughlin ground state instead of the Psiformer (no parameters)
+  int twoQ1;     // laughlin: 2 Q1 = flux - 2 p (N - 1) = N - 1
   float Q, radius;
   std::vector<dh_param_entry> entries;
   int64_t nparams;
@@ -97,7 +99,7 @@ static inline int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
 
 static inline FwdWs carve_fwd(const dh_plan* p, float* base, int64_t Bc, bool jets, bool keep_inverse) {
   const int R = jets ? 2 * p->N + 8 : 1;
-  const size_t rows = (size_t)Bc * p->N * R;
+  const size_t rows = p->laughlin ? 0 : (size_t)Bc * p->N * R;  // the analytic network has no body activations
   FwdWs w;
   size_t off = 0;
   auto take = [&](size_t n) { float* q = base ? base + off : nullptr; off += al(n); return q; };

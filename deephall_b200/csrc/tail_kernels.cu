@@ -132,6 +132,113 @@ orbital_contract_kernel(const float* __restrict__ c, const float* __restrict__ x
   }
 }
 
+// =============================================================================================
+// Laughlin ground state (networks/laughlin.py:59-71, `full_orbitals`): orbital matrix
+//   O[i][m] = u_i^m v_i^(2Q1-m) * Jas_i,   Jas_i = prod_{j != i} e_ij,   e_ij = u_i v_j - u_j v_i
+// with its jets along the rotation flows.  One block per (walker, electron i).
+//   * P_im = u_i^m v_i^(2Q1-m) and its jets come from envelope_jets (unit norm factors);
+//   * e_ij is an SU(2) singlet: global rotations leave Jas_i unchanged (D_a, T_a act on P only);
+//   * a flow on electron e != i touches one factor: delta Jas_i / Jas_i = g = (u_i dv_e - du_e v_i)/e_ie and
+//     delta^2 Jas_i / Jas_i = -1/4  (delta^2 (u, v) = -(u, v)/4);
+//   * a flow on electron i touches every factor: with g_j = (du_i v_j - u_j dv_i)/e_ij,
+//     delta Jas/Jas = sum_j g_j,  delta^2 Jas/Jas = -(N-1)/4 - sum_j g_j^2 + (sum_j g_j)^2.
+// =============================================================================================
+__device__ inline dcplx ddiv(dcplx a, dcplx b) {
+  const double d = 1.0 / (b.x * b.x + b.y * b.y);
+  return make_double2((a.x * b.x + a.y * b.y) * d, (a.y * b.x - a.x * b.y) * d);
+}
+__device__ inline dcplx dsub(dcplx a, dcplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+
+__global__ void __launch_bounds__(128)
+laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restrict__ ones, float* __restrict__ Mj,
+                             TailDims dm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int N = dm.N, R = dm.R, L = dm.L;
+  dcplx* upow = reinterpret_cast<dcplx*>(smraw);
+  dcplx* vpow = upow + L;
+  dcplx* U = vpow + L;        // [N]
+  dcplx* V = U + N;           // [N]
+  dcplx* dU = V + N;          // [N][2] own tangent flows of every electron
+  dcplx* dV = dU + 2 * N;     // [N][2]
+  dcplx* gE = dV + 2 * N;     // [N][2] delta Jas_i / Jas_i for a flow on electron e
+  dcplx* sc = gE + 2 * N;     // [0] Jas, [1..2] dL_t, [3..4] q_t
+  cplx* env = reinterpret_cast<cplx*>(sc + 5);
+  const int64_t bi = blockIdx.x;
+  const int64_t b = bi / N;
+  const int i = (int)(bi % N);
+  const int tid = threadIdx.x;
+  const int nslots = R > 1 ? ENV_SLOTS : 1;
+  const float* xw = x + b * N * 2;
+  if (tid < N) {
+    double st, ct, sp, cp, sh, ch, sph, cph;
+    sincos((double)xw[2 * tid], &st, &ct);
+    sincos((double)xw[2 * tid + 1], &sp, &cp);
+    sincos(0.5 * (double)xw[2 * tid], &sh, &ch);
+    sincos(0.5 * (double)xw[2 * tid + 1], &sph, &cph);
+    const dcplx u = make_double2(ch * cph, ch * sph), v = make_double2(sh * cph, -sh * sph);
+    U[tid] = u; V[tid] = v;
+    const double ax[2][3] = {{ct * cp, ct * sp, -st}, {-sp, cp, 0.0}};  // theta_hat, phi_hat
+    for (int t = 0; t < 2; ++t) {
+      const double nx = ax[t][0], ny = ax[t][1], nz = ax[t][2];
+      const dcplx t1 = dadd(dscale(u, nz), dmul(make_double2(nx, ny), v));
+      const dcplx t2 = dadd(dmul(make_double2(nx, -ny), u), dscale(v, -nz));
+      dU[2 * tid + t] = make_double2(-0.5 * t1.y, 0.5 * t1.x);
+      dV[2 * tid + t] = make_double2(-0.5 * t2.y, 0.5 * t2.x);
+    }
+  }
+  envelope_jets(xw[2 * i], xw[2 * i + 1], dm.twoQ, ones, upow, vpow, env, nslots);  // (contains __syncthreads)
+  if (tid == 0) {
+    dcplx jas = make_double2(1.0, 0.0), dl0 = make_double2(0, 0), dl1 = dl0, s0 = dl0, s1 = dl0;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      const dcplx e = dsub(dmul(U[i], V[j]), dmul(U[j], V[i]));
+      jas = dmul(jas, e);
+      const dcplx g0 = ddiv(dsub(dmul(dU[2 * i], V[j]), dmul(U[j], dV[2 * i])), e);
+      const dcplx g1 = ddiv(dsub(dmul(dU[2 * i + 1], V[j]), dmul(U[j], dV[2 * i + 1])), e);
+      dl0 = dadd(dl0, g0); dl1 = dadd(dl1, g1);
+      s0 = dadd(s0, dmul(g0, g0)); s1 = dadd(s1, dmul(g1, g1));
+      gE[2 * j] = ddiv(dsub(dmul(U[i], dV[2 * j]), dmul(dU[2 * j], V[i])), e);
+      gE[2 * j + 1] = ddiv(dsub(dmul(U[i], dV[2 * j + 1]), dmul(dU[2 * j + 1], V[i])), e);
+    }
+    const double c = -0.25 * (N - 1);
+    sc[0] = jas; sc[1] = dl0; sc[2] = dl1;
+    sc[3] = dadd(make_double2(c, 0.0), dsub(dmul(dl0, dl0), s0));
+    sc[4] = dadd(make_double2(c, 0.0), dsub(dmul(dl1, dl1), s1));
+  }
+  __syncthreads();
+  const dcplx jas = sc[0];
+  Rows rw(N, R > 1);
+  auto E = [&](int slot, int m) { const cplx e = env[slot * L + m]; return make_double2((double)e.x, (double)e.y); };
+  for (int t = tid; t < R * L; t += blockDim.x) {
+    const int r = t / L, m = t % L;
+    const dcplx P = E(0, m);
+    dcplx val;
+    if (r == 0) val = dmul(P, jas);
+    else if (r <= 2 * N) {
+      const int e = (r - 1) >> 1, tt = (r - 1) & 1;
+      if (e == i) val = dmul(dadd(E(1 + tt, m), dmul(P, sc[1 + tt])), jas);
+      else val = dmul(dmul(P, jas), gE[2 * e + tt]);
+    } else if (r == rw.S()) {
+      dcplx acc = E(3, m);
+      acc = dadd(acc, dscale(dadd(dmul(E(1, m), sc[1]), dmul(E(2, m), sc[2])), 2.0));
+      acc = dadd(acc, dmul(P, dadd(sc[3], sc[4])));
+      acc = dadd(acc, dscale(P, -0.5 * (N - 1)));
+      val = dmul(acc, jas);
+    } else if (r < rw.T(0)) val = dmul(E(4 + (r - rw.D(0)), m), jas);
+    else val = dmul(E(7 + (r - rw.T(0)), m), jas);
+    float* dst = Mj + (((b * R + r) * N + i) * N + m) * 2;
+    dst[0] = (float)val.x;
+    dst[1] = (float)val.y;
+  }
+}
+
+int laughlin_orbital_jets(const float* x, const double* ones, float* Mj, int64_t B, TailDims d, cudaStream_t s) {
+  if (d.L != d.N || d.K != 1) return -2;
+  const size_t smem = (2 * (size_t)d.L + 8 * (size_t)d.N + 5) * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
+  laughlin_orbital_jets_kernel<<<(unsigned)(B * d.N), 128, smem, s>>>(x, ones, Mj, d);
+  return (int)cudaGetLastError();
+}
+
 // Value-only form (R = 1): one warp per (walker, electron), eight per block.
 //   env[m] = sqrt(C(2Q,m)) cos^m(theta/2) sin^(2Q-m)(theta/2) e^{i (m - Q) phi}: magnitudes by repeated squaring
 //   in double (exponents reach 2Q), phase angle reduced in double and evaluated in fp32;

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 
 from .config import System
-from .networks import Psiformer
+from .networks import B200Network as Psiformer  # any network of this engine
 
 
 def _network_of(f) -> Psiformer:

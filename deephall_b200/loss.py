@@ -14,7 +14,7 @@ import torch
 from . import constants
 from .config import System
 from .hamiltonian import local_energy
-from .networks import Psiformer
+from .networks import B200Network as Psiformer  # any network of this engine
 
 
 def iqr_clip_real(x: torch.Tensor, scale: float = 100.0) -> torch.Tensor:

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import constants
-from .networks import Psiformer
+from .networks import B200Network as Psiformer  # any network of this engine
 
 
 @dataclass(frozen=True)

@@ -23,16 +23,62 @@ _PLANS: dict = {}
 
 
 def get_plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type="coulomb",
-             interaction_strength=1.0, radius=None, chunk_walkers=0) -> _native.Plan:
+             interaction_strength=1.0, radius=None, chunk_walkers=0, network_type="psiformer", cf_flux=1) -> _native.Plan:
     key = (tuple(nspins), int(flux), ndets, num_heads, heads_dim, num_layers, str(interaction_type),
-           float(interaction_strength), radius, chunk_walkers, torch.cuda.current_device())
+           float(interaction_strength), radius, chunk_walkers, str(network_type), int(cf_flux), torch.cuda.current_device())
     if key not in _PLANS:
         _PLANS[key] = _native.Plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type,
-                                   interaction_strength, radius, chunk_walkers)
+                                   interaction_strength, radius, chunk_walkers, network_type, cf_flux)
     return _PLANS[key]
 
 
-class Psiformer:
+class B200Network:
+    """Common surface of the networks this engine evaluates: `plan(system)`, `init`, `apply`, `nelec`."""
+
+    nspins: tuple
+
+    @property
+    def nelec(self) -> int:
+        return sum(self.nspins)
+
+    def apply(self, params: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        """complex64 log psi.  x: (N, 2) -> scalar, or (B, N, 2) -> (B,)."""
+        single = x.dim() == 2
+        xb = (x[None] if single else x).contiguous().float()
+        out = self.plan().logpsi(params, xb)
+        return out[0] if single else out
+
+    __call__ = apply
+
+
+class Laughlin(B200Network):
+    """Analytic Laughlin ground state (networks/laughlin.py:19-71), evaluated by the same tail kernels
+    (log-determinant jets, local-energy assembly, Metropolis sweep).  It has no parameters."""
+
+    def __init__(self, nspins, flux, cf_flux=1, excitation_lz=0):
+        self.nspins = (int(nspins[0]), int(nspins[1]))
+        self.flux = int(flux)
+        self.cf_flux = int(cf_flux)
+        n = sum(self.nspins)
+        if self.nspins[1] != 0 or self.flux - 2 * self.cf_flux * (n - 1) != n - 1 or excitation_lz:
+            raise NotImplementedError("only the spin-polarised Laughlin ground state (N = 2 Q1 + 1) is built; "
+                                      "quasihole / quasiparticle states are a 'next' row (SURVEY 8f N3)")
+
+    def plan(self, system: System | None = None) -> _native.Plan:
+        kw = dict(network_type="laughlin", cf_flux=self.cf_flux)
+        if system is None:
+            return get_plan(self.nspins, self.flux, 1, 4, 64, 0, **kw)
+        return get_plan(self.nspins, self.flux, 1, 4, 64, 0, system.interaction_type, system.interaction_strength,
+                        system.radius, **kw)
+
+    def init(self, key=None, x=None, device="cuda") -> torch.Tensor:
+        return torch.zeros(0, dtype=torch.float32, device=device)
+
+    def param_layout(self):
+        return OrderedDict()
+
+
+class Psiformer(B200Network):
     """B200 Psiformer (networks/psiformer.py:63-91).  Constructor arguments are the ones
     `make_network` passes in the reference."""
 
@@ -51,10 +97,6 @@ class Psiformer:
             return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers)
         return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers,
                         system.interaction_type, system.interaction_strength, system.radius)
-
-    @property
-    def nelec(self) -> int:
-        return sum(self.nspins)
 
     def param_layout(self) -> "OrderedDict[str, tuple[int, tuple[int, ...]]]":
         return self.plan().param_layout()
@@ -109,22 +151,10 @@ class Psiformer:
             flat[off : off + arr.numel()] = arr.reshape(-1)
         return flat.to(device)
 
-    # ---- model.apply
-    def apply(self, params: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-        """complex64 log psi.  x: (N, 2) -> scalar, or (B, N, 2) -> (B,)."""
-        single = x.dim() == 2
-        xb = (x[None] if single else x).contiguous().float()
-        out = self.plan().logpsi(params, xb)
-        return out[0] if single else out
-
-    __call__ = apply
-
-
-def make_network(system: System, network: Network) -> Psiformer:
+def make_network(system: System, network: Network) -> B200Network:
     """networks/__init__.py:22-37."""
     if str(network.type) == "laughlin":
-        raise NotImplementedError("the analytic Laughlin network is a 'next' row (SURVEY 8f N3); "
-                                  "oracle/laughlin.py holds its CPU restatement for tests")
+        return Laughlin(system.nspins, system.flux)
     ps = network.psiformer
     return Psiformer(
         Q=system.flux / 2,

@@ -17,6 +17,8 @@
  *   dh_slogdet         <- jnp.linalg.slogdet + tail         psiformer.py:74-76
  *   dh_param_layout    <- the flax parameter tree           psiformer.py, blocks.py
  *   dh_init_walkers    <- init_guess                        train.py:40-54
+ *   network_type = 1   <- Laughlin(nspins, flux).apply      networks/laughlin.py:19-71 (ground state;
+ *                         no parameters: dh_param_count = 0, dh_logpsi_vjp writes nothing)
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
@@ -56,6 +58,8 @@ typedef struct dh_config {
   float interaction_strength; /* system.interaction_strength                          */
   float radius;             /* system.radius; <= 0 means sqrt(Q) (hamiltonian.py:189) */
   int32_t chunk_walkers;    /* walkers per internal pass (0 = library default)        */
+  int32_t network_type;     /* network.type: 0 = psiformer, 1 = laughlin (config.py:82-84)          */
+  int32_t cf_flux;          /* laughlin: composite-fermion flux p (networks/laughlin.py:25), 0 -> 1  */
 } dh_config;
 
 typedef struct dh_plan dh_plan;

@@ -486,3 +486,68 @@ def test_facade_matches_reference_api(nat):
     for _ in range(3):
         pm, st = vmc.step()
     assert abs(float(st["energy"].real) - 1.5) < 0.2  # train_test.py:46-48: energy hovers around N/2
+
+
+# --------------------------------------------------------------------------------- Laughlin (analytic, pinned)
+LAUGHLIN_CASES = [(3, 6), (4, 9), (5, 12), (6, 15)]  # (N, flux = 3 (N - 1)): the 1/3 Laughlin state
+
+
+@pytest.mark.parametrize("N,flux", LAUGHLIN_CASES)
+def test_laughlin_logpsi_and_local_energy_parity(nat, N, flux):
+    """Laughlin ground state (networks/laughlin.py:59-71) through the same tail kernels: log psi vs the fp64
+    oracle, and kinetic energy / L_z / L^2 vs the reference's gradient + Hessian formulas
+    (hamiltonian.py:96-170) applied to it.  For this lowest-Landau-level eigenstate KE = N/2 * (Q / r^2) = N/2
+    and L^2 = 0 exactly (the known answers tests/hamiltonian_test.py:65-76 uses for LLL states)."""
+    from oracle import laughlin as OL
+
+    plan = nat.Plan(nspins=(N, 0), flux=flux, network_type="laughlin")
+    assert plan.num_params == 0
+    B = 24
+    x = plan.init_walkers(B, seed=5)
+    params = torch.zeros(0, device=DEV)
+    lp = plan.logpsi(params, x).cpu().to(torch.complex128)
+    x64 = x.cpu().double()
+    ref = torch.stack([OL.logpsi(x64[b], flux) for b in range(B)])
+    assert (lp.real - ref.real).abs().max() < 2e-5 * max(1.0, ref.real.abs().max().item())
+    assert phase_diff(lp.imag, ref.imag).abs().max() < 5e-5
+    out = plan.local_energy(params, x)
+    res = OH.batch_local_energy(lambda xx: OL.logpsi(xx, flux), x64, flux / 2, chunk=B)
+    for k, tol in (("kinetic", 2e-4), ("angular_momentum_z", 2e-4), ("angular_momentum_square", 2e-3), ("potential", 1e-5)):
+        got, want = out[k].cpu(), res[k]
+        want = want.real if want.is_complex() and not got.is_complex() else want
+        err = (got.to(want.dtype) - want).abs().max().item()
+        assert err < tol * max(1.0, want.abs().max().item()), (k, err)
+    assert (out["kinetic"].real.cpu() - N / 2).abs().max() < 5e-4          # filled-LLL-like exact eigenvalue
+    assert out["angular_momentum_square"].abs().max().item() < 5e-3          # L = 0 state
+
+
+def test_laughlin_pinned_energy_through_the_gpu_path(nat):
+    """tests/cli_test.py:24-54 of the reference: Laughlin network, nspins [3,0], flux 6, optimizer none, batch 3360
+    prints `energy=2.58...` and `L_square=0.0000`.  Same system through the facade on the GPU: Metropolis sweeps
+    (dh_mcmc_sweep with in-kernel Philox), local energy (dh_local_energy) and the loss statistics."""
+    from deephall_b200 import hamiltonian, loss, mcmc, networks
+    from deephall_b200.config import Network, System
+
+    system = System(flux=6, nspins=(3, 0))
+    model = networks.make_network(system, Network(type="laughlin"))
+    params = model.init(0)
+    B = 3360
+    data = mcmc.init_guess(42, B, 3, model)
+    step = mcmc.make_mcmc_step(model.apply, B, steps=10)
+    key = mcmc.PhiloxKey(7)
+    for _ in range(60):  # burn-in
+        key, sub = key.split()
+        data, pmove = step(params, data, sub, 0.4)
+    loss_fn = loss.make_loss_fn(model.apply, system, loss.LossMode.ENERGY_DIFF)
+    energies, l2s = [], []
+    for _ in range(8):
+        key, sub = key.split()
+        data, pmove = step(params, data, sub, 0.4)
+        stats, _diff = loss_fn(params, data)
+        energies.append(float(stats["energy"].real))
+        l2s.append(float(stats["angular_momentum_square"]))
+    e = sum(energies) / len(energies)
+    assert abs(e - 2.5866) < 0.01, e      # the reference prints energy=2.58...
+    assert f"{e:.4f}".startswith("2.58")
+    assert abs(sum(l2s) / len(l2s)) < 5e-4  # L_square=0.0000
+    assert 0.2 < float(pmove) < 0.9
