@@ -551,3 +551,26 @@ def test_laughlin_pinned_energy_through_the_gpu_path(nat):
     assert f"{e:.4f}".startswith("2.58")
     assert abs(sum(l2s) / len(l2s)) < 5e-4  # L_square=0.0000
     assert 0.2 < float(pmove) < 0.9
+
+
+def test_checkpoint_wire_format_roundtrip(nat, tmp_path):
+    """deephall/log.py:174-216: npz with `step`, pickled `{'params': {...}}` tree, `data (B, N, 2)`, `opt_state`,
+    `mcmc_width`; restoring resumes at step + 1 with the same log psi."""
+    from deephall_b200 import checkpoint, networks
+    from deephall_b200.optimizers import AdamState, CheckpointState
+
+    model = networks.Psiformer((3, 0), 1.0, num_layers=1)
+    params = model.init(3)
+    data = model.plan().init_walkers(16, seed=2)
+    opt = AdamState(5, torch.full_like(params, 0.25), torch.full_like(params, 0.5))
+    path = tmp_path / "ckpt_000041.npz"
+    checkpoint.save_checkpoint(path, 41, model, CheckpointState(params, data, opt, 0.11))
+    with np.load(path, allow_pickle=True) as f:   # what the reference's reader does (log.py:203-213)
+        assert int(f["step"].tolist()) == 41 and f["data"].shape == (16, 3, 2)
+        tree = f["params"].tolist()
+        assert tree["params"]["PsiformerLayers_0"]["Dense_0"]["kernel"].shape == (4, 256)
+        assert tree["params"]["Orbitals_0"]["featured_orbitals"]["DenseGeneral_0"]["kernel"].shape == (256, 3, 3, 1)
+    step, st = checkpoint.restore_checkpoint(path, model)
+    assert step == 42 and abs(st.mcmc_width - 0.11) < 1e-7 and st.opt_state.count == 5
+    assert torch.equal(st.params, params) and torch.equal(st.data, data) and torch.equal(st.opt_state.nu, opt.nu)
+    assert torch.equal(model.apply(st.params, st.data), model.apply(params, data))
