@@ -80,7 +80,7 @@ __device__ void envelope_jets(float theta, float phi, int twoQ, const double* __
 }
 
 // c rows: [(b,i,r)][ re: (m, j, kdet) | im: (m, j, kdet) ]  ->  Mj[b][kdet][r][i][j] complex
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)  // <= 64 registers: the kernel is load-latency bound, occupancy matters
 orbital_contract_kernel(const float* __restrict__ c, const float* __restrict__ x,
                         const double* __restrict__ normfac, float* __restrict__ Mj, TailDims dm) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -106,7 +106,15 @@ orbital_contract_kernel(const float* __restrict__ c, const float* __restrict__ x
       const float* cr = cbase + (int64_t)crow * ldc + jk;
       const cplx* e = env + slot * L;
       cplx s = cmake(0.f, 0.f);
-      for (int m = 0; m < L; ++m) s = cfma(cmake(cr[m * NK], cr[LNK + m * NK]), e[m], s);
+      int m = 0;
+      for (; m + 8 <= L; m += 8) {  // eight independent load pairs in flight before the first FMA needs one
+        float re[8], im[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { re[u] = cr[(m + u) * NK]; im[u] = cr[LNK + (m + u) * NK]; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s = cfma(cmake(re[u], im[u]), e[m + u], s);
+      }
+      for (; m < L; ++m) s = cfma(cmake(cr[m * NK], cr[LNK + m * NK]), e[m], s);
       acc.x = fmaf(w, s.x, acc.x);
       acc.y = fmaf(w, s.y, acc.y);
     };
