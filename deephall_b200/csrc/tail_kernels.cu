@@ -464,21 +464,70 @@ logdet_jets_kernel(const float* __restrict__ Mj, float* __restrict__ ldout, floa
   }
 }
 
+// Register-resident LU with partial pivoting for n <= 16: lane i holds row i (16 complex registers), pivots are
+// found by a warp arg-max, rows swapped and the pivot row broadcast by shuffles.  Returns log|det| and the phase
+// with jax slogdet semantics (singular -> (-inf, 0)).  All loops are fully unrolled (no dynamic register indexing).
+__device__ __forceinline__ void warp_lu_regs(cplx (&a)[16], int n, float& logabs, cplx& phase) {
+  const int lane = threadIdx.x & 31;
+  float la = 0.f;
+  cplx ph = cmake(1.f, 0.f);
+  bool singular = false;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    if (p < n) {
+      // pivot: largest |a[i][p]| over rows i >= p (ties -> smallest row)
+      float best = (lane >= p && lane < n) ? cabs2(a[p]) : -1.f;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (bi != p) {
+        const int src = lane == p ? bi : (lane == bi ? p : lane);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          a[c].x = __shfl_sync(0xffffffffu, a[c].x, src);
+          a[c].y = __shfl_sync(0xffffffffu, a[c].y, src);
+        }
+        ph = cmake(-ph.x, -ph.y);
+      }
+      const cplx d = cmake(__shfl_sync(0xffffffffu, a[p].x, p), __shfl_sync(0xffffffffu, a[p].y, p));
+      const float ad = hypotf(d.x, d.y);
+      la += logf(ad);
+      if (ad == 0.f && !isnan(la)) singular = true;
+      ph = ad > 0.f ? cmul(ph, cmake(d.x / ad, d.y / ad)) : cmake(0.f, 0.f);
+      const cplx f = (lane > p && lane < n) ? cmul(a[p], cinv(d)) : cmake(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        if (c > p) {
+          const cplx pv = cmake(__shfl_sync(0xffffffffu, a[c].x, p), __shfl_sync(0xffffffffu, a[c].y, p));
+          a[c] = cmake(a[c].x - (f.x * pv.x - f.y * pv.y), a[c].y - (f.x * pv.y + f.y * pv.x));
+        }
+      }
+    }
+  }
+  const float pn = hypotf(ph.x, ph.y);
+  if (pn > 0.f) ph = cmake(ph.x / pn, ph.y / pn);
+  if (singular) { la = -INFINITY; ph = cmake(0.f, 0.f); }
+  logabs = la;
+  phase = ph;
+}
+
 // value-only form without the inverse (log psi / Metropolis passes): one warp per matrix, eight per block
 __global__ void __launch_bounds__(256)
 logdet_value_kernel(const float* __restrict__ Mj, float* __restrict__ ldout, int64_t nmat, int N) {
-  extern __shared__ __align__(16) unsigned char smraw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int NN = N * N;
-  cplx* a = reinterpret_cast<cplx*>(smraw) + (size_t)warp * NN;
   const int64_t bk = (int64_t)blockIdx.x * 8 + warp;
-  if (bk >= nmat) return;  // whole warps leave; only warp-level synchronisation below
-  const cplx* M0 = reinterpret_cast<const cplx*>(Mj) + bk * NN;
-  for (int t = lane; t < NN; t += 32) a[t] = M0[t];
-  __syncwarp();
+  if (bk >= nmat) return;  // whole warps leave; only warp-level primitives below
+  const cplx* M0 = reinterpret_cast<const cplx*>(Mj) + bk * N * N;
+  cplx a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) a[c] = (lane < N && c < N) ? M0[lane * N + c] : cmake(0.f, 0.f);
   float la;
   cplx ph;
-  warp_gauss_jordan(a, N, N, N, la, ph);
+  warp_lu_regs(a, N, la, ph);
   if (lane == 0) {
     float* o = ldout + bk * 2;
     o[0] = la;
@@ -489,8 +538,8 @@ logdet_value_kernel(const float* __restrict__ Mj, float* __restrict__ ldout, int
 int logdet_jets_impl(const float* Mj, float* ld, float* Minv, int64_t B, TailDims d, cudaStream_t s) {
   if (d.R == 1 && Minv == nullptr) {
     const int64_t nmat = B * d.K;
-    const size_t smem1 = (size_t)8 * d.N * d.N * sizeof(cplx);
-    logdet_value_kernel<<<(unsigned)((nmat + 7) / 8), 256, smem1, s>>>(Mj, ld, nmat, d.N);
+    if (d.N > 16) return -2;
+    logdet_value_kernel<<<(unsigned)((nmat + 7) / 8), 256, 0, s>>>(Mj, ld, nmat, d.N);
     return (int)cudaGetLastError();
   }
   const int nwarp = 4;
@@ -728,11 +777,18 @@ slogdet_kernel(const float* __restrict__ mats, int64_t B, int K, int n, float* _
   float mx = -INFINITY, sr = 0.f, si = 0.f;
   for (int k = 0; k < K; ++k) {
     const cplx* src = reinterpret_cast<const cplx*>(mats) + (b * K + k) * n * n;
-    for (int t = lane; t < n * n; t += 32) A[t] = src[t];
-    __syncwarp();
     float la;
     cplx ph;
-    warp_gauss_jordan(A, n, n, n, la, ph);
+    if (n <= 16) {  // register-resident LU
+      cplx a[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) a[c] = (lane < n && c < n) ? src[lane * n + c] : cmake(0.f, 0.f);
+      warp_lu_regs(a, n, la, ph);
+    } else {
+      for (int t = lane; t < n * n; t += 32) A[t] = src[t];
+      __syncwarp();
+      warp_gauss_jordan(A, n, n, n, la, ph);
+    }
     if (lane == 0) {
       if (out_sign) { out_sign[(b * K + k) * 2] = ph.x; out_sign[(b * K + k) * 2 + 1] = ph.y; }
       if (out_logabs) out_logabs[b * K + k] = la;
