@@ -83,6 +83,23 @@ features_value_kernel(const float* __restrict__ x, const float* __restrict__ W, 
   sincosf(x[row * 2 + 1], &sp, &cp);
   const float f0 = ct, f1 = st * cp, f2 = st * sp, f3 = ((int)(row % dm.N) < dm.n_up) ? 1.f : -1.f;  // (z, x, y, spin)
   float* o = out + row * Nout;
+  if ((Nout & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
+    for (int d = 4 * lane; d < Nout; d += 128) {  // 16-byte accesses
+      const float4 w0 = *reinterpret_cast<const float4*>(W + d), w1 = *reinterpret_cast<const float4*>(W + Nout + d);
+      const float4 w2 = *reinterpret_cast<const float4*>(W + 2 * Nout + d), w3 = *reinterpret_cast<const float4*>(W + 3 * Nout + d);
+      float4 v;
+      v.x = fmaf(f0, w0.x, fmaf(f1, w1.x, fmaf(f2, w2.x, f3 * w3.x)));
+      v.y = fmaf(f0, w0.y, fmaf(f1, w1.y, fmaf(f2, w2.y, f3 * w3.y)));
+      v.z = fmaf(f0, w0.z, fmaf(f1, w1.z, fmaf(f2, w2.z, f3 * w3.z)));
+      v.w = fmaf(f0, w0.w, fmaf(f1, w1.w, fmaf(f2, w2.w, f3 * w3.w)));
+      if (bias != nullptr) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias + d);
+        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      }
+      *reinterpret_cast<float4*>(o + d) = v;
+    }
+    return;
+  }
   for (int d = lane; d < Nout; d += 32) {
     float v = fmaf(f0, W[d], fmaf(f1, W[Nout + d], fmaf(f2, W[2 * Nout + d], f3 * W[3 * Nout + d])));
     if (bias != nullptr) v += bias[d];
@@ -438,10 +455,14 @@ attention_value_kernel(const float* __restrict__ qkv, float* __restrict__ o, Net
   const int64_t b = blockIdx.x;
   const float4* src = reinterpret_cast<const float4*>(qkv + b * N * 3 * D);
   const int row4 = 3 * D / 4;
+  // asynchronous copies: all of a thread's 16-byte pieces are in flight at once
   for (int t = threadIdx.x; t < N * row4; t += blockDim.x) {
     const int r = t / row4, c = t % row4;
-    *reinterpret_cast<float4*>(sm + r * ld + 4 * c) = src[t];
+    const unsigned da = (unsigned)__cvta_generic_to_shared(sm + r * ld + 4 * c);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + t) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   const float scl = rsqrtf((float)hd);
   // scores: one thread per (head, 2 queries, 2 keys): 4 float4 loads feed 16 FMAs

@@ -296,7 +296,21 @@ orbital_value_kernel(const float* __restrict__ c, const float* __restrict__ x, c
     cplx acc = cmake(0.f, 0.f);
     if (jl < width) {
       const float* p = cr + jk0 + jl;
-      for (int m = g; m < L; m += G) acc = cfma(cmake(p[m * NK], p[LNK + m * NK]), env[m], acc);
+      // batches of 6 m-values: the 12 loads of a batch are issued before the first FMA needs one
+      for (int m0 = g; m0 < L; m0 += 6 * G) {
+        float re[6], im[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int m = m0 + u * G;
+          re[u] = m < L ? p[m * NK] : 0.f;
+          im[u] = m < L ? p[LNK + m * NK] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int m = m0 + u * G;
+          if (m < L) acc = cfma(cmake(re[u], im[u]), env[m], acc);
+        }
+      }
     }
     for (int off = NKp; off < 32; off <<= 1) {
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
