@@ -220,69 +220,93 @@ int residual_layernorm_bwd(const float* a, const float* b, const float* scale, c
 __global__ void __launch_bounds__(256)
 attention_value_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ g_o,
                            float* __restrict__ g_qkv, NetDims dm) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int N = dm.N, D = dm.D, H = dm.H, hd = dm.hd;
-  float* sq = sm;                   // [N][3D]
-  float* sgo = sq + N * 3 * D;      // [N][D]
-  float* sp = sgo + N * D;          // [H][N][N] probabilities
-  float* sgs = sp + H * N * N;      // [H][N][N] dL/ds
+  const int ldq = 3 * D + 4, ldg = D + 4;  // padded rows: conflict-free float4 reads across electrons
+  float* sq = sm;                   // [N][3D + 4]
+  float* sgo = sq + N * ldq;        // [N][D + 4]
+  float* sp = sgo + N * ldg;        // [H][N][N] scores -> probabilities
+  float* sgs = sp + H * N * N;      // [H][N][N] dL/dp -> dL/ds
   const int64_t b = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-  for (int t = tid; t < N * 3 * D; t += blockDim.x) sq[t] = qkv[b * N * 3 * D + t];
-  for (int t = tid; t < N * D; t += blockDim.x) sgo[t] = g_o[b * N * D + t];
-  __syncthreads();
-  const float scl = rsqrtf((float)hd);
-  // scores + softmax + dL/dp -> dL/ds ; one warp per (h, i)
-  for (int w = warp; w < H * N; w += nwarp) {
-    const int hh = w / N, i = w % N;
-    const float* q = sq + i * 3 * D + hh * hd;
-    const float* go = sgo + i * D + hh * hd;
-    float sc[32], gp[32];
-    float mx = -INFINITY;
-    for (int j = 0; j < N; ++j) {
-      const float* k = sq + j * 3 * D + D + hh * hd;
-      const float* v = sq + j * 3 * D + 2 * D + hh * hd;
-      float p = 0.f, g = 0.f;
-      for (int d = lane; d < hd; d += 32) { p = fmaf(q[d], k[d], p); g = fmaf(go[d], v[d], g); }
-      sc[j] = warp_sum(p) * scl;
-      gp[j] = warp_sum(g);
-      mx = fmaxf(mx, sc[j]);
+  const int tid = threadIdx.x;
+  {
+    const float4* src = reinterpret_cast<const float4*>(qkv + b * N * 3 * D);
+    const int row4 = 3 * D / 4;
+    for (int t = tid; t < N * row4; t += blockDim.x) {
+      const unsigned da = (unsigned)__cvta_generic_to_shared(sq + (t / row4) * ldq + 4 * (t % row4));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + t) : "memory");
     }
-    float Z = 0.f;
-    for (int j = 0; j < N; ++j) { sc[j] = expf(sc[j] - mx); Z += sc[j]; }
-    const float iz = 1.f / Z;
-    float dot = 0.f;
-    for (int j = 0; j < N; ++j) { sc[j] *= iz; dot = fmaf(sc[j], gp[j], dot); }
-    if (lane == 0) {
-      for (int j = 0; j < N; ++j) {
-        sp[(hh * N + i) * N + j] = sc[j];
-        sgs[(hh * N + i) * N + j] = sc[j] * (gp[j] - dot) * scl;
-      }
+    const float4* srg = reinterpret_cast<const float4*>(g_o + b * N * D);
+    const int rg4 = D / 4;
+    for (int t = tid; t < N * rg4; t += blockDim.x) {
+      const unsigned da = (unsigned)__cvta_generic_to_shared(sgo + (t / rg4) * ldg + 4 * (t % rg4));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(srg + t) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  // g_q_i = sum_j gs_ij k_j ; g_k_j = sum_i gs_ij q_i ; g_v_j = sum_i p_ij go_i
-  float* out = g_qkv + b * N * 3 * D;
-  for (int t = tid; t < N * D; t += blockDim.x) {
-    const int n = t / D, c = t % D, hh = c / hd;
-    float gq = 0.f, gk = 0.f, gv = 0.f;
-    for (int m = 0; m < N; ++m) {
-      gq = fmaf(sgs[(hh * N + n) * N + m], sq[m * 3 * D + D + c], gq);
-      gk = fmaf(sgs[(hh * N + m) * N + n], sq[m * 3 * D + c], gk);
-      gv = fmaf(sp[(hh * N + m) * N + n], sgo[m * D + c], gv);
+  const float scl = rsqrtf((float)hd);
+  // scores s_ij = q_i.k_j * scl and dL/dp_ij = go_i.v_j : one thread per (head, i, j)
+  for (int t = tid; t < H * N * N; t += blockDim.x) {
+    const int j = t % N, i = (t / N) % N, hh = t / (N * N);
+    const float4* q = reinterpret_cast<const float4*>(sq + i * ldq + hh * hd);
+    const float4* k = reinterpret_cast<const float4*>(sq + j * ldq + D + hh * hd);
+    const float4* v = reinterpret_cast<const float4*>(sq + j * ldq + 2 * D + hh * hd);
+    const float4* go = reinterpret_cast<const float4*>(sgo + i * ldg + hh * hd);
+    float p = 0.f, g = 0.f;
+    for (int d = 0; d < hd / 4; ++d) {
+      const float4 a = q[d], bb = k[d], c = go[d], e = v[d];
+      p = fmaf(a.x, bb.x, p); p = fmaf(a.y, bb.y, p); p = fmaf(a.z, bb.z, p); p = fmaf(a.w, bb.w, p);
+      g = fmaf(c.x, e.x, g); g = fmaf(c.y, e.y, g); g = fmaf(c.z, e.z, g); g = fmaf(c.w, e.w, g);
     }
-    out[n * 3 * D + c] = gq;
-    out[n * 3 * D + D + c] = gk;
-    out[n * 3 * D + 2 * D + c] = gv;
+    sp[t] = p * scl;
+    sgs[t] = g;
+  }
+  __syncthreads();
+  // softmax and dL/ds_ij = p_ij (dL/dp_ij - sum_j p_ij dL/dp_ij) * scl : one thread per (head, i)
+  for (int t = tid; t < H * N; t += blockDim.x) {
+    float* s = sp + t * N;
+    float* gs = sgs + t * N;
+    float mx = -INFINITY;
+    for (int j = 0; j < N; ++j) mx = fmaxf(mx, s[j]);
+    float Z = 0.f;
+    for (int j = 0; j < N; ++j) { const float ex = expf(s[j] - mx); s[j] = ex; Z += ex; }
+    const float iz = 1.f / Z;
+    float dot = 0.f;
+    for (int j = 0; j < N; ++j) { s[j] *= iz; dot = fmaf(s[j], gs[j], dot); }
+    for (int j = 0; j < N; ++j) gs[j] = s[j] * (gs[j] - dot) * scl;
+  }
+  __syncthreads();
+  // g_q_n = sum_m gs_nm k_m ; g_k_n = sum_m gs_mn q_m ; g_v_n = sum_m p_mn go_m : one thread per (n, 4 columns)
+  float* out = g_qkv + b * N * 3 * D;
+  const int D4 = D / 4;
+  for (int t = tid; t < N * D4; t += blockDim.x) {
+    const int n = t / D4, c = 4 * (t % D4), hh = c / hd;
+    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f), gk = gq, gv = gq;
+    for (int m = 0; m < N; ++m) {
+      const float a = sgs[(hh * N + n) * N + m], bb = sgs[(hh * N + m) * N + n], pp = sp[(hh * N + m) * N + n];
+      const float4 km = *reinterpret_cast<const float4*>(sq + m * ldq + D + c);
+      const float4 qm = *reinterpret_cast<const float4*>(sq + m * ldq + c);
+      const float4 gm = *reinterpret_cast<const float4*>(sgo + m * ldg + c);
+      gq.x = fmaf(a, km.x, gq.x); gq.y = fmaf(a, km.y, gq.y); gq.z = fmaf(a, km.z, gq.z); gq.w = fmaf(a, km.w, gq.w);
+      gk.x = fmaf(bb, qm.x, gk.x); gk.y = fmaf(bb, qm.y, gk.y); gk.z = fmaf(bb, qm.z, gk.z); gk.w = fmaf(bb, qm.w, gk.w);
+      gv.x = fmaf(pp, gm.x, gv.x); gv.y = fmaf(pp, gm.y, gv.y); gv.z = fmaf(pp, gm.z, gv.z); gv.w = fmaf(pp, gm.w, gv.w);
+    }
+    *reinterpret_cast<float4*>(out + n * 3 * D + c) = gq;
+    *reinterpret_cast<float4*>(out + n * 3 * D + D + c) = gk;
+    *reinterpret_cast<float4*>(out + n * 3 * D + 2 * D + c) = gv;
   }
 }
 
 int attention_value_bwd(const float* qkv, const float* g_o, float* g_qkv, int64_t B, NetDims d, cudaStream_t s) {
-  if (d.N > 32) return -2;
-  size_t smem = ((size_t)d.N * 4 * d.D + 2 * (size_t)d.H * d.N * d.N) * sizeof(float);
-  if (smem > 48 * 1024) {
+  if (d.N > 32 || (d.hd % 4) != 0) return -2;
+  const size_t smem = ((size_t)d.N * (3 * d.D + 4) + (size_t)d.N * (d.D + 4) + 2 * (size_t)d.H * d.N * d.N) * sizeof(float);
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(attention_value_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
+    attr_smem = smem;
   }
   attention_value_bwd_kernel<<<(unsigned)B, 256, smem, s>>>(qkv, g_o, g_qkv, d);
   return (int)cudaGetLastError();
