@@ -80,6 +80,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->gemm_impl = 0;
     p->tc_f16 = 0;
     p->tc_merged = 0;
+    p->a_planes = 0;
     p->ee_par = -1;
     p->orb_re_k = p->orb_re_b = p->orb_im_k = p->orb_im_b = -1;
     p->off_W0 = -1;
@@ -130,6 +131,11 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->tc_f16 = (gemm_tc_f16_ok(D) && !(env && std::string(env) == "tf32")) ? 1 : 0;
     const char* acc = getenv("DH_GEMM_ACC");  // "split" | "merged"; default: merged for fp16 pieces, split for tf32
     p->tc_merged = acc ? (std::string(acc) == "merged" ? 1 : 0) : p->tc_f16;
+    // DH_A_PLANES=1 (experiment, off by default): activations that feed a contraction are written as fp16 hi / lo
+    // planes by the attention / LayerNorm kernels and the contraction skips its in-kernel split.  Measured at c3:
+    // contractions 13.9 -> 13.1 ms, but attention +3.2 ms and LayerNorm +1.5 ms (8-byte plane stores), a net loss.
+    const char* apl = getenv("DH_A_PLANES");
+    p->a_planes = (p->gemm_impl == 1 && p->tc_f16 && D == 256 && p->nl > 0 && apl && std::string(apl) == "1") ? 1 : 0;
     size_t off = 0;
     auto slot = [&](int Nout, bool has_bias) {
       dh_plan::Slot sl;
@@ -246,6 +252,10 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   const bool h0_comp = jets && p->gemm_impl == 1 && p->nl > 0;
   { ProfScope ps(p, PC_OTHER, 0, s);
     if ((rc = features_linear(x, P + p->off_W0, nullptr, h0_comp ? w.t1 : w.h, D, Bc, nd, h0_comp ? 1 : 0, s))) return rc; }
+  // jet passes with fp16 pieces: every tensor that is the left operand of a contraction (att, h) lives as fp16
+  // hi / lo planes in its buffer -- written so by the attention and LayerNorm kernels, read back as hi + lo by the
+  // next LayerNorm's residual -- and the contraction takes its operand tiles straight from them by TMA
+  const bool pl = jets && p->a_planes;
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
     if (l == 0 && p->gemm_impl == 1) {
@@ -254,26 +264,27 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       const dh_plan::Slot& q = p->slots[SL_QKV];
       // (jets: only the 10 non-zero rows per electron are written; attention_jets' first-layer form reads them)
       if ((rc = features_linear(x, p->prep + p->w0qkv, p->prep + q.bias, w.qkv, 3 * D, Bc, nd, jets ? 1 : 0, s))) return rc;
-    } else if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s))) return rc;
+    } else if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s, pl))) return rc;
     { ProfScope ps(p, PC_ATTENTION, 0, s);
-      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, (l == 0 && p->gemm_impl == 1) ? 1 : 0, s);
+      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, (l == 0 && p->gemm_impl == 1) ? 1 : 0, pl ? 1 : 0, s);
       else rc = attention_value(w.qkv, w.att, Bc, nd, s);
       if (rc) return rc; }
     if (p->gemm_impl == 1) {
       // MHA out-projection and the bias-free Dense that follows it are one linear map (Wo W1, bo W1)
-      if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s))) return rc;
+      if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s, pl))) return rc;
     } else {
       if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
       if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
     }
     { ProfScope ps(p, PC_LAYERNORM, 0, s);
-      if (l == 0 && h0_comp) rc = residual_layernorm_ex(w.t1, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 1, s);
-      else rc = residual_layernorm(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, s);
+      if (l == 0 && h0_comp) rc = residual_layernorm_ex(w.t1, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 1, 0, pl ? 1 : 0, s);
+      else rc = residual_layernorm_ex(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 0, pl ? 1 : 0, pl ? 1 : 0, s);
       if (rc) return rc; }
-    if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s))) return rc;
-    { ProfScope ps(p, PC_LAYERNORM, 0, s); if ((rc = residual_layernorm(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, s))) return rc; }
+    if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s, pl))) return rc;
+    { ProfScope ps(p, PC_LAYERNORM, 0, s);
+      if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
   }
-  if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s))) return rc;
+  if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s, pl))) return rc;
   ProfScope pst(p, PC_TAIL, 0, s, 3);
   if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
   if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;

@@ -67,6 +67,7 @@ int dense_bwd_x_tc(const dh_plan* p, const float* G, int64_t ldg, int vs, int K,
   g.bias = nullptr; g.inv_scale = p->tc_f16 ? p->prep + sl.scale + 1 : nullptr;
   g.C = C; g.ldc = p->D; g.M = rows; g.N = p->D; g.K = K; g.rpg = 1;
   g.f16 = p->tc_f16; g.merged = p->tc_merged; g.reduce_add = accumulate;
+  g.A_lo = nullptr;
   g.a_scale = p->prep + p->cot_scale;  // gradients scale with the cotangents (O(1/B)): keep the fp16 pieces in range
   return gemm_tc_ex(g, s);
 }

@@ -71,7 +71,7 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
 // per shared-memory wavefront -- and the two halves of the block work on two 16-column steps at once.
 template <int NT, bool L0, bool Q12>
 __global__ void __launch_bounds__(AJ_THREADS, 2)
-attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm) {
+attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, int o_pl) {
   extern __shared__ __align__(16) float smem[];
   const int N = NT > 0 ? NT : dm.N, R = 2 * N + 8, D = dm.D, hd = dm.hd;
   const int RI = L0 ? AJ_RC : R;  // rows per electron of the input tensor
@@ -248,6 +248,9 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
   }
   // ------------------------------------------------------------------ phase 3: o = P V jets
   float* obase = o + b * NR * (int64_t)D + hh * hd;
+  // o_pl: the output goes out as fp16 hi / lo planes, the left operand of the contraction that follows
+  __half* opl = reinterpret_cast<__half*>(o) + b * NR * (int64_t)D + hh * hd;
+  const int64_t oplane = (int64_t)gridDim.y * NR * D;
   const int rS = rw.S(), rT0 = rw.T(0), rD0 = rw.D(0);
   if (Q12) {
     // two 16-column steps at a time: threads 0..127 take step cp (regions 0, 1), threads 128..255 step cp + 1
@@ -329,7 +332,8 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
               out.x += x4.x; out.y += x4.y; out.z += x4.z; out.w += x4.w;
             }
             float* dst = obase + (int64_t)(i * R + r) * D + dcol;
-            if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = out;
+            if (o_pl) { if (dcol < hd) st_planes4(opl, oplane, (int64_t)(i * R + r) * D + dcol, out); }
+            else if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = out;
             else {
               if (dcol < hd) dst[0] = out.x;
               if (dcol + 1 < hd) dst[1] = out.y;
@@ -434,7 +438,8 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
             out.x += x4.x; out.y += x4.y; out.z += x4.z; out.w += x4.w;
           }
           float* dst = obase + (int64_t)(i * R + r) * D + dcol;
-          if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = out;
+          if (o_pl) { if (dcol < hd) st_planes4(opl, oplane, (int64_t)(i * R + r) * D + dcol, out); }
+          else if (dcol + 3 < hd) *reinterpret_cast<float4*>(dst) = out;
           else {
             if (dcol < hd) dst[0] = out.x;
             if (dcol + 1 < hd) dst[1] = out.y;
@@ -448,7 +453,8 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
 #undef SJ
 }
 
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s) {
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int o_pl, cudaStream_t s) {
+  if (o_pl && ((d.D % 8) != 0 || (reinterpret_cast<uintptr_t>(o) & 15))) return -2;
   if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
   const size_t smem = aj_smem_floats(d.N, d.R, layer0 ? AJ_RC : d.R) * sizeof(float);
   if (smem > 227 * 1024) return -2;
@@ -462,7 +468,7 @@ int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0,
       if (e != cudaSuccess) return (int)e;                                                                            \
       attr_smem = smem;                                                                                               \
     }                                                                                                                 \
-    attention_jets_kernel<NT, LZ, (NT >= 7 && NT <= 12)><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d);                  \
+    attention_jets_kernel<NT, LZ, (NT >= 7 && NT <= 12)><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d, o_pl);                 \
   } while (0)
 #define DH_AJ_BOTH(NT) do { if (layer0) DH_AJ_LAUNCH(NT, true); else DH_AJ_LAUNCH(NT, false); } while (0)
   switch (d.N) {

@@ -1,5 +1,6 @@
 // Shared device helpers for the deephall_b200 kernels (sm_100a).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -55,6 +56,47 @@ __device__ inline float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// ---- two-piece fp16 split of an fp32 number (operands of the tcgen05 contraction, gemm_tc.cu)
+// fp16 piece of x with saturation to the largest finite fp16 (NaN stays NaN)
+__device__ __forceinline__ float sat_f16_range(float x) { return fabsf(x) > 65504.f ? copysignf(65504.f, x) : x; }
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(sat_f16_range(x));
+  lo = __float2half_rn(sat_f16_range(x - __half2float(hi)));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {  // a in the low half
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// two floats -> packed fp16 pair (x0 in the low half), round-to-nearest, saturating to +-65504, NaN kept
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float x0, float x1) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
+  return r;
+}
+// (x0, x1) -> hi pair, lo pair:  hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2_sat(x0, x1);
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  lo = cvt_f16x2_sat(x0 - hf.x, x1 - hf.y);
+}
+
+// Activation tensors that feed the tcgen05 contraction can be kept as its operands: a [rows][D] fp32 buffer viewed
+// as two fp16 planes [rows][D], hi at the start of the buffer and lo `plane` = rows * D halves later (same bytes).
+// Four consecutive columns starting at element index idx:
+__device__ __forceinline__ void st_planes4(__half* hi, int64_t plane, int64_t idx, const float4& v) {
+  uint2 h, l;
+  split_f16x2(v.x, v.y, h.x, l.x);
+  split_f16x2(v.z, v.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(hi + idx) = h;
+  *reinterpret_cast<uint2*>(hi + plane + idx) = l;
+}
+__device__ __forceinline__ float4 ld_planes4(const __half* hi, int64_t plane, int64_t idx) {
+  const uint2 h = *reinterpret_cast<const uint2*>(hi + idx);
+  const uint2 l = *reinterpret_cast<const uint2*>(hi + plane + idx);
+  const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+  const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
 }
 
 // Philox4x32-10 (Salmon et al. 2011), counter = (offset_lo, offset_hi, subseq_lo, subseq_hi).

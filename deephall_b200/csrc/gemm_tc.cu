@@ -44,7 +44,7 @@ constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 32;             // K elements per pipeline stage (both kinds)
 constexpr int A_BYTES = BLOCK_M * 128;  // 16 KB: the fp32 A tile TMA lands (128 rows x 32 floats, 128B swizzle)
 constexpr int RING_BYTES = 192 * 1024;  // operand ring: tf32 pieces 2 stages x 96 KB, fp16 pieces 4 stages x 48 KB
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 6;
 constexpr int EPI_CHUNK = 32;                            // accumulator columns per epilogue step
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 4;        // 32 rows x 32 floats = 4 KB (one warp, one step)
 constexpr int EPI_WARPS = 8;                             // two per TMEM lane quarter, alternating 32-column chunks
@@ -138,33 +138,57 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
         : "memory");
   }
 }
-// fp16 piece of x with saturation to the largest finite fp16 (NaN stays NaN)
-__device__ __forceinline__ float sat_f16_range(float x) { return fabsf(x) > 65504.f ? copysignf(65504.f, x) : x; }
-__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
-  hi = __float2half_rn(sat_f16_range(x));
-  lo = __float2half_rn(sat_f16_range(x - __half2float(hi)));
-}
-__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {  // a in the low half
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
-}
-// two floats -> packed fp16 pair (x0 in the low half), round-to-nearest, saturating to +-65504, NaN kept
-__device__ __forceinline__ uint32_t cvt_f16x2_sat(float x0, float x1) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(x1), "f"(x0));
-  return r;
-}
-// (x0, x1) -> hi pair, lo pair:  hi = fp16(x), lo = fp16(x - hi)
-__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_f16x2_sat(x0, x1);
-  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  lo = cvt_f16x2_sat(x0 - hf.x, x1 - hf.y);
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // arrive on the barrier at the same offset in every CTA of cta_mask when the MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+// ---- CTA-pair (cta_group::2) forms: one MMA spans the two CTAs of a cluster (M = 256, 128 rows each); every CTA
+// stages its own A rows and HALF of the weight tile, so a CTA's shared memory serves 8 KB instead of 12 KB of
+// operand reads per MMA and receives 32 KB instead of 48 KB per pipeline stage
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta_rank) {  // shared::cluster address of `addr` in CTA cta_rank
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+// (default semantics, release at CTA scope: a cluster-scope release costs ~1000 cycles per arrival and the data it
+// would publish -- operand tiles behind a fence.proxy.async, accumulators behind tcgen05 fences -- is read by the
+// tensor core / after the tcgen05 fence, not by generic loads of the other CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquires what remote arrivals released
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// TMA load into this CTA's shared memory whose completion bytes are counted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_pair_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -202,22 +226,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // tma_store != 0: C is written through tmC (box 32 x 32 floats, 128B swizzle); otherwise (ldc not a
 // multiple of 4 floats, or misaligned C) by direct global stores.
-template <bool F16, bool MERGED>
+// PAIR (fp16 pieces, merged accumulator): clusters of two CTAs run `tcgen05.mma.cta_group::2` -- see the helpers above.
+template <bool F16, bool MERGED, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
                int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
-               unsigned long long* __restrict__ prof) {
+               int a_pre, unsigned long long* __restrict__ prof) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
   //                fp16 pieces: [A hi 8 KB | A lo 8 KB (together = the landed fp32 tile) | B hi 16 KB | B lo 16 KB],
   //                operand rows of 64 B (SWIZZLE_64B).
-  constexpr int STAGES = F16 ? 4 : 2;
+  //                PAIR:        [A hi 8 KB | A lo 8 KB | B hi 8 KB | B lo 8 KB]: this CTA's 128 of the tile's 256 weight rows.
+  static_assert(!PAIR || (F16 && MERGED), "the CTA-pair form exists for fp16 pieces with the merged accumulator");
+  constexpr int STAGES = PAIR ? 6 : (F16 ? 4 : 2);
   constexpr int ROW_BYTES = F16 ? 64 : 128;            // operand tile row = BLOCK_K pieces
   constexpr int AP_BYTES = BLOCK_M * ROW_BYTES;        // one A piece tile
-  constexpr int B_BYTES = BLOCK_N * ROW_BYTES;         // one B piece tile
+  constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * ROW_BYTES;  // one B piece tile (PAIR: this CTA's half)
   constexpr int STAGE_BYTES = 2 * AP_BYTES + 2 * B_BYTES;
   static_assert(STAGES * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
   constexpr int A_TX_BYTES = A_BYTES;
@@ -253,13 +281,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Every CTA of a cluster runs the same number of tiles (the weight multicast is collective): bands past
   // the end of the matrix load zeros and their stores are clipped.
   uint32_t crank = 0;
-  if (cl > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  if (PAIR || cl > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
   const int64_t cbase = (int64_t)blockIdx.x - crank;  // first CTA of this cluster
-  const int64_t my_bands = cbase < n_mtiles ? (n_mtiles - cbase + gridDim.x - 1) / gridDim.x : 0;
+  // PAIR: the cluster takes PAIRS of adjacent bands (2u, 2u + 1), u = cluster index, + number of clusters, ...
+  const int64_t n_units = PAIR ? (n_mtiles + 1) / 2 : n_mtiles;
+  const int64_t unit0 = PAIR ? (int64_t)(blockIdx.x >> 1) : cbase;
+  const int64_t ustride = PAIR ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t my_bands = unit0 < n_units ? (n_units - unit0 + ustride - 1) / ustride : 0;
   const int64_t my_tiles = my_bands * n_ntiles;
-  auto band_of = [&](int64_t k) { return (int64_t)blockIdx.x + (k / n_ntiles) * gridDim.x; };
+  auto band_of = [&](int64_t k) {
+    return PAIR ? 2 * (unit0 + (k / n_ntiles) * ustride) + crank : (int64_t)blockIdx.x + (k / n_ntiles) * gridDim.x;
+  };
   auto ntile_of = [&](int64_t k) { return (int)(k % n_ntiles); };
+  // PAIR: barriers of the leader CTA (rank 0) that the other CTA signals
+  auto leader = [&](uint32_t bar) { return mapa_u32(bar, 0); };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -268,23 +304,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(split_bar(s), SPLIT_WARPS);
-      mbar_init(empty_bar(s), (uint32_t)cl);  // one tcgen05.commit arrival from every CTA of the cluster
+      mbar_init(split_bar(s), PAIR ? 2 * SPLIT_WARPS : SPLIT_WARPS);  // PAIR: the leader's barrier counts both CTAs' splitters
+      mbar_init(empty_bar(s), PAIR ? 1u : (uint32_t)cl);  // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar(b), 1);
-      mbar_init(tmem_empty_bar(b), EPI_WARPS);
+      mbar_init(tmem_empty_bar(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {  // collective over the pair: the same columns in both CTAs' tensor memory
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (cl > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrival
+  if (PAIR || cl > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrival
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
   // developer instrumentation (DH_GEMM_PROF=1): cycles each role spends blocked, summed over CTAs
@@ -293,10 +335,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
     if (prof) {
       const long long t0 = clock64();
-      mbar_wait(bar, parity);
+      if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
       pw[slot] += (unsigned long long)(clock64() - t0);
     } else {
-      mbar_wait(bar, parity);
+      if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
     }
   };
 
@@ -311,8 +353,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           timed_wait(empty_bar(s), ph ^ 1, 0);
-          mbar_arrive_expect_tx(full_bar(s), A_TX_BYTES + 2 * B_BYTES);
-          tma_load_2d(a_hi(s), &tmA, full_bar(s), kb * BLOCK_K, m0);
+          if (PAIR) {
+            // A: this CTA's band, counted on its own barrier (its splitter waits there).  Weights: this CTA's half
+            // of the tile's rows, counted on the LEADER's barrier together with the leader's own loads.
+            const int n_tile = N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N;
+            const int nb = n0 + (int)crank * (n_tile / 2);
+            mbar_arrive_expect_tx(full_bar(s), crank == 0 ? A_TX_BYTES + 4 * B_BYTES : A_TX_BYTES);
+            tma_load_2d(a_hi(s), &tmA, full_bar(s), kb * BLOCK_K, m0);
+            tma_load_2d_pair(b_hi(s), &tmBhi, leader(full_bar(s)), kb * BLOCK_K, nb);
+            tma_load_2d_pair(b_lo(s), &tmBlo, leader(full_bar(s)), kb * BLOCK_K, nb);
+            continue;
+          }
+          if (a_pre) {
+            // A arrives already split (fp16 hi / lo planes written by the producing kernel): operand tiles by TMA
+            mbar_arrive_expect_tx(full_bar(s), 2 * AP_BYTES + 2 * B_BYTES);
+            tma_load_2d(a_hi(s), &tmA, full_bar(s), kb * BLOCK_K, m0);
+            tma_load_2d(a_lo(s), &tmAlo, full_bar(s), kb * BLOCK_K, m0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(s), A_TX_BYTES + 2 * B_BYTES);
+            tma_load_2d(a_hi(s), &tmA, full_bar(s), kb * BLOCK_K, m0);
+          }
           if (cl == 1) {
             tma_load_2d(b_hi(s), &tmBhi, full_bar(s), kb * BLOCK_K, n0);
             tma_load_2d(b_lo(s), &tmBlo, full_bar(s), kb * BLOCK_K, n0);
@@ -327,14 +387,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (prof) { atomicAdd(prof + 0, pw[0]); atomicAdd(prof + 10, (unsigned long long)(clock64() - t_begin)); }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA's, for both)
+    if (lane == 0 && (!PAIR || crank == 0)) {
       uint32_t it = 0, tl = 0;
       for (int64_t tk = 0; tk < my_tiles; ++tk, ++tl) {
         const int n0 = ntile_of(tk) * BLOCK_N;
         int n_tile = N - n0 < BLOCK_N ? N - n0 : BLOCK_N;
         n_tile = (n_tile + 15) & ~15;  // Wt buffers are zero-padded to a multiple of 16 rows
-        const uint32_t idesc = make_idesc<F16>(BLOCK_M, n_tile);
+        const uint32_t idesc = make_idesc<F16>(PAIR ? 2 * BLOCK_M : BLOCK_M, n_tile);
         // the epilogue has read the previous user of this accumulator out of TMEM
         const int ab = merged ? (int)(tl & 1) : 0;
         const uint32_t au = merged ? (tl >> 1) : tl;  // how many times this accumulator has been used before
@@ -345,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           timed_wait(full_bar(s), ph, 1);
-          timed_wait(split_bar(s), ph, 2);
+          if (!a_pre) timed_wait(split_bar(s), ph, 2);  // PAIR: both CTAs' A tiles have landed and are split
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t dah = make_smem_desc<F16>(a_hi(s)), dal = make_smem_desc<F16>(a_lo(s));
           const uint64_t dbh = make_smem_desc<F16>(b_hi(s)), dbl = make_smem_desc<F16>(b_lo(s));
@@ -355,7 +415,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // The tensor core rounds toward zero when it adds into the fp32 accumulator, a bias that
             // grows with the number of additions: keep the small correction terms in their own
             // accumulator so the main one sees K/8 additions instead of 3K/8.
-            if (merged) {
+            if (PAIR) {
+              umma_pair_f16(acc, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+              umma_pair_f16(acc, dah + adv, dbl + adv, idesc, 1);
+              umma_pair_f16(acc, dah + adv, dbh + adv, idesc, 1);
+            } else if (merged) {
               umma<F16>(acc, dal + adv, dbh + adv, idesc, (kb | k) != 0);
               umma<F16>(acc, dah + adv, dbl + adv, idesc, 1);
               umma<F16>(acc, dah + adv, dbh + adv, idesc, 1);
@@ -367,9 +431,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // arrives (in every CTA of the cluster: their TMA writes into this stage too) when the MMAs reading
           // this stage have completed
-          if (cl == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
+          if (PAIR) umma_commit_pair(empty_bar(s), 3);
+          else if (cl == 1) umma_commit(empty_bar(s)); else umma_commit_mc(empty_bar(s), cmask);
         }
-        umma_commit(tmem_full_bar(ab));
+        if (PAIR) umma_commit_pair(tmem_full_bar(ab), 3); else umma_commit(tmem_full_bar(ab));
       }
       if (prof) { atomicAdd(prof + 1, pw[0]); atomicAdd(prof + 2, pw[1]); atomicAdd(prof + 3, pw[2]);
                   atomicAdd(prof + 11, (unsigned long long)(clock64() - t_begin)); }
@@ -381,7 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // a_scale_ptr = {scale, 1/scale}, the epilogue undoes it
     const float asc = a_scale_ptr ? __ldg(a_scale_ptr) : 1.f;
     uint32_t it = 0;
-    for (int64_t tk = 0; tk < my_tiles; ++tk) {
+    for (int64_t tk = 0; tk < (a_pre ? 0 : my_tiles); ++tk) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -431,7 +496,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) mbar_arrive(split_bar(s));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(split_bar(s))); else mbar_arrive(split_bar(s)); }
         if (prof && t == 0) pw[1] += (unsigned long long)(clock64() - ts0);
       }
     }
@@ -486,7 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // this warp's last read of the tile's accumulators: hand TMEM back to the MMA issuer
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(tmem_empty_bar(ab))); else mbar_arrive(tmem_empty_bar(ab)); }
           released = true;
           if (prof && lead) pw[1] += (unsigned long long)(clock64() - te0);
         }
@@ -539,7 +604,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!released) {  // a narrow tile left this warp without a chunk
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(ab));
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(tmem_empty_bar(ab))); else mbar_arrive(tmem_empty_bar(ab)); }
       }
     }
     if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -549,10 +614,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (cl > 1) cluster_sync_all();  // no CTA leaves while a peer can still write into its shared memory
+  if (PAIR || cl > 1) cluster_sync_all();  // no CTA leaves while a peer can still write into its shared memory
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -749,6 +815,7 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   g.A = A; g.lda = K; g.Wt_hi = Wt_hi; g.Wt_lo = Wt_lo; g.ldw = K; g.bias = bias; g.inv_scale = inv_scale;
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.rpg = rpg; g.f16 = f16; g.merged = merged; g.reduce_add = 0;
   g.a_scale = nullptr;
+  g.A_lo = nullptr;
   return gemm_tc_ex(g, stream);
 }
 
@@ -765,7 +832,12 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   const int Npad = (N + 15) & ~15;
   CUtensorMap tmA, tmBh, tmBl, tmC;
   int rc;
-  if ((rc = tc::make_map(&tmA, A, false, (uint64_t)M, (uint64_t)K, (uint64_t)gm.lda, tc::BLOCK_M))) return rc;
+  const int a_pre = gm.A_lo != nullptr ? 1 : 0;  // A given as fp16 hi / lo planes ([M][lda] halves each)
+  if (a_pre && (!f16 || gm.a_scale != nullptr || (reinterpret_cast<uintptr_t>(gm.A_lo) & 15) || (gm.lda % 8) != 0)) return -2;
+  CUtensorMap tmAlo;
+  if ((rc = tc::make_map(&tmA, A, a_pre != 0, (uint64_t)M, (uint64_t)K, (uint64_t)gm.lda, tc::BLOCK_M))) return rc;
+  if (a_pre) { if ((rc = tc::make_map(&tmAlo, gm.A_lo, true, (uint64_t)M, (uint64_t)K, (uint64_t)gm.lda, tc::BLOCK_M))) return rc; }
+  else tmAlo = tmA;
   const int tma_store = ((reinterpret_cast<uintptr_t>(C) & 15) == 0 && (ldc % 4) == 0) ? 1 : 0;
   if (tma_store) {
     if ((rc = tc::make_map(&tmC, C, false, (uint64_t)M, (uint64_t)N, (uint64_t)ldc, 32))) return rc;
@@ -774,27 +846,36 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t bands = (M + tc::BLOCK_M - 1) / tc::BLOCK_M;
   const int64_t tiles = bands * ((N + tc::BLOCK_N - 1) / tc::BLOCK_N);
   const int sms = tc::num_sms();
+  // CTA pairs (tcgen05.mma.cta_group::2): fp16 pieces with the merged accumulator, fp32 A; DH_GEMM_PAIR=0 disables
+  static const bool pair_env = !(getenv("DH_GEMM_PAIR") && atoi(getenv("DH_GEMM_PAIR")) == 0);
+  const bool pair = pair_env && f16 && merged && !a_pre && bands >= 2;
   // cluster size: DH_GEMM_CLUSTER = 1 | 2 | 4; small problems run un-clustered.  Default 1: with the
   // 192 KB operand ring the kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic, and the
   // multicast measured no faster at 2 and slower at 4 (profiles/r1_gemm_tc_notes.md).
   static const int cl_env = getenv("DH_GEMM_CLUSTER") ? atoi(getenv("DH_GEMM_CLUSTER")) : 1;
   int cl = (cl_env == 4 || cl_env == 2) ? cl_env : 1;
-  if (bands < 2 * sms) cl = 1;
+  if (bands < 2 * sms || pair) cl = 1;
   int64_t g = bands < sms ? bands : sms;
   g = g / cl * cl;
+  if (pair) {  // one cluster of two CTAs per pair of bands, at most one CTA per SM
+    const int64_t units = (bands + 1) / 2;
+    g = 2 * (units < sms / 2 ? units : sms / 2);
+  }
   dim3 grid((unsigned)g);
-  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, tc::BLOCK_N / cl))) return rc;
-  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, tc::BLOCK_N / cl))) return rc;
+  const uint32_t b_box = pair ? tc::BLOCK_N / 2 : tc::BLOCK_N / cl;
+  if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, b_box))) return rc;
+  if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, b_box))) return rc;
   static const bool want_prof = getenv("DH_GEMM_PROF") != nullptr;
   unsigned long long* prof = nullptr;
   if (want_prof) {
@@ -811,16 +892,17 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   lc.stream = stream;
   cudaLaunchAttribute lattr[1];
   lattr[0].id = cudaLaunchAttributeClusterDimension;
-  lattr[0].val.clusterDim.x = (unsigned)cl;
+  lattr[0].val.clusterDim.x = pair ? 2u : (unsigned)cl;
   lattr[0].val.clusterDim.y = 1;
   lattr[0].val.clusterDim.z = 1;
   lc.attrs = lattr;
   lc.numAttrs = 1;
   cudaError_t le;
-#define DH_LAUNCH_TC(F, MG) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG>, tmA, tmBh, tmBl, tmC, bias, inv_scale, C, M, \
-                                                    N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, prof)
-  if (f16) { if (merged) DH_LAUNCH_TC(true, true); else DH_LAUNCH_TC(true, false); }
-  else { if (merged) DH_LAUNCH_TC(false, true); else DH_LAUNCH_TC(false, false); }
+#define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
+                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, prof)
+  if (pair) DH_LAUNCH_TC(true, true, true);
+  else if (f16) { if (merged) DH_LAUNCH_TC(true, true, false); else DH_LAUNCH_TC(true, false, false); }
+  else { if (merged) DH_LAUNCH_TC(false, true, false); else DH_LAUNCH_TC(false, false, false); }
 #undef DH_LAUNCH_TC
   if (le != cudaSuccess) return (int)le;
   if (want_prof) {

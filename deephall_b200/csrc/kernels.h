@@ -29,6 +29,8 @@ struct TcGemm {
   float* C; int64_t ldc;
   int64_t M; int N, K, rpg, f16, merged, reduce_add;
   const float* a_scale;  // optional device {s, 1/s}: A is multiplied by s before the split, C by 1/s
+  const void* A_lo;      // non-null (fp16 pieces only): A and A_lo are fp16 hi / lo planes [M][lda] written by the
+                         // producing kernel; the in-kernel split is skipped
 };
 // slot = {s, 1/s}, s = power of two bringing max|v| into [1, 2)
 int pow2_scale_tc(const float* v, int64_t n, float* slot, cudaStream_t stream);
@@ -58,11 +60,13 @@ int features_linear(const float* x, const float* W, const float* bias, float* ou
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s);
 // a_comp != 0 (jets): `a` holds only the 10 non-zero rows per electron of the first layer's Dense_0 output
+// a_pl / o_pl != 0 (D = 256): `a` / `out` are fp16 hi / lo planes (common.cuh) instead of fp32 rows
 int residual_layernorm_ex(const float* a, const float* b, const float* scale, const float* bias, float* out,
-                          int64_t B, NetDims d, int tanh_mode, int a_comp, cudaStream_t s);
+                          int64_t B, NetDims d, int tanh_mode, int a_comp, int a_pl, int o_pl, cudaStream_t s);
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
 // layer0 != 0: qkv is the compressed first-layer tensor [B*N*10][3D] (features_linear with compressed = 1)
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s);
+// o_pl != 0: o is written as fp16 hi / lo planes (common.cuh)
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int o_pl, cudaStream_t s);
 size_t attention_jets_smem(NetDims d);
 
 // ---- tail_kernels.cu

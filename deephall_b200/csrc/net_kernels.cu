@@ -145,7 +145,7 @@ template <bool TANH, bool VEC4>
 __global__ void __launch_bounds__(128)
 residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                           const float* __restrict__ scale, const float* __restrict__ bias,
-                          float* __restrict__ out, int64_t groups, NetDims dm, int a_comp) {
+                          float* __restrict__ out, int64_t groups, NetDims dm, int a_comp, int a_pl, int o_pl) {
   const int lane = threadIdx.x & 31;
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (g >= groups) return;
@@ -158,6 +158,11 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   const float* ga = a + g * (a_comp ? 10 : R) * D;
   const float* gb = b + g * R * D;
   float* go = out + g * R * D;
+  // a_pl / o_pl (VEC4 only): `a` / `out` are fp16 hi / lo planes (common.cuh), the form the tcgen05 contraction
+  // takes its left operand in
+  const int64_t plane = groups * R * D;
+  const __half* pa = reinterpret_cast<const __half*>(a) + g * R * D;
+  __half* po = reinterpret_cast<__half*>(out) + g * R * D;
 
   // one row (D floats at `base`) <-> the LN_VPL values this lane owns
   auto ldrow = [&](const float* base, float (&dst)[LN_VPL]) {
@@ -182,7 +187,22 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
     }
   };
 
+  auto sto = [&](int r, const float (&src)[LN_VPL]) {  // row r of `out`
+    if (VEC4 && o_pl) {
+      st_planes4(po, plane, (int64_t)r * D + 4 * lane, make_float4(src[0], src[1], src[2], src[3]));
+      st_planes4(po, plane, (int64_t)r * D + 128 + 4 * lane, make_float4(src[4], src[5], src[6], src[7]));
+    } else {
+      strow(go + (int64_t)r * D, src);
+    }
+  };
   auto lda = [&](int r, float (&dst)[LN_VPL]) {  // row r of `a`
+    if (VEC4 && a_pl) {
+      const float4 p = ld_planes4(pa, plane, (int64_t)r * D + 4 * lane);
+      const float4 q = ld_planes4(pa, plane, (int64_t)r * D + 128 + 4 * lane);
+      dst[0] = p.x; dst[1] = p.y; dst[2] = p.z; dst[3] = p.w;
+      dst[4] = q.x; dst[5] = q.y; dst[6] = q.z; dst[7] = q.w;
+      return;
+    }
     if (!a_comp) { ldrow(ga + (int64_t)r * D, dst); return; }
     int rc;
     if (r == 0) rc = 0;
@@ -204,7 +224,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   for (int v = 0; v < LN_VPL; ++v) { t1[v] = 1.f; t2[v] = 0.f; }
   // ---- value row
   float xr[LN_VPL], ra[LN_VPL], rb[LN_VPL], ro[LN_VPL];
-  ldrow(ga, ra);
+  lda(0, ra);
   ldrow(gb, rb);
   float sum = 0.f;
 #pragma unroll
@@ -235,7 +255,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
   const float rho2 = 0.75f * rho0 / (var * var);  // d2 rho / d var2
 #pragma unroll
   for (int v = 0; v < LN_VPL; ++v) ro[v] = fmaf(c0[v] * rho0, gam[v], bet[v]);
-  strow(go, ro);
+  sto(0, ro);
   if (R == 1) return;
 
   Rows rw(N, true);
@@ -309,7 +329,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
       accS[v] = fmaf(cr[v], rhoJ, accS[v]);
       if (TANH) bsq[v] = fmaf(braw[v], braw[v], bsq[v]);
     }
-    strow(go + (int64_t)r * D, ro);
+    sto(r, ro);
   }
   // ---- S row
   {
@@ -320,7 +340,7 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
     const float rhoS = rho1 * vS + rho2 * sum_vv;
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) ro[v] = gam[v] * (fmaf(cr[v], rho0, c0[v] * rhoS) + 2.f * accS[v]);
-    strow(go + (int64_t)r * D, ro);
+    sto(r, ro);
   }
   // ---- D_a / T_a rows
   for (int a3 = 0; a3 < 3; ++a3) {
@@ -334,14 +354,14 @@ residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__
       bD2[v] = bD[v] * bD[v];
       ro[v] = gam[v] * fmaf(cD[v], rho0, c0[v] * rhoD);
     }
-    strow(go + (int64_t)rw.D(a3) * D, ro);
+    sto(rw.D(a3), ro);
     float m2;
     load_second(rw.T(a3), bD2, cr, m2);
     const float vT = 2.f * m2 + 2.f * m_cc;
     const float rhoT = rho1 * vT + rho2 * vD * vD;
 #pragma unroll
     for (int v = 0; v < LN_VPL; ++v) ro[v] = gam[v] * (fmaf(cr[v], rho0, c0[v] * rhoT) + 2.f * cD[v] * rhoD);
-    strow(go + (int64_t)rw.T(a3) * D, ro);
+    sto(rw.T(a3), ro);
   }
 }
 
@@ -407,13 +427,13 @@ layernorm_value256_kernel(const float* __restrict__ a, const float* __restrict__
 
 int residual_layernorm(const float* a, const float* b, const float* scale, const float* bias, float* out,
                        int64_t B, NetDims d, int tanh_mode, cudaStream_t s) {
-  return residual_layernorm_ex(a, b, scale, bias, out, B, d, tanh_mode, 0, s);
+  return residual_layernorm_ex(a, b, scale, bias, out, B, d, tanh_mode, 0, 0, 0, s);
 }
 
 int residual_layernorm_ex(const float* a, const float* b, const float* scale, const float* bias, float* out,
-                          int64_t B, NetDims d, int tanh_mode, int a_comp, cudaStream_t s) {
-  if (d.D % 32 != 0 || d.D > 32 * LN_VPL || (a_comp && d.R == 1)) return -2;
-  if (d.R == 1 && d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
+                          int64_t B, NetDims d, int tanh_mode, int a_comp, int a_pl, int o_pl, cudaStream_t s) {
+  if (d.D % 32 != 0 || d.D > 32 * LN_VPL || (a_comp && d.R == 1) || (a_comp && a_pl)) return -2;
+  if (!a_pl && !o_pl && d.R == 1 && d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
                                   reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
     const int64_t rows = B * d.N;
     const unsigned grid = (unsigned)((rows + 15) / 16);
@@ -426,12 +446,13 @@ int residual_layernorm_ex(const float* a, const float* b, const float* scale, co
   unsigned grid = (unsigned)((groups + wpb - 1) / wpb);
   const bool vec4 = d.D == 256 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out) |
                                     reinterpret_cast<uintptr_t>(scale) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0;
+  if ((a_pl || o_pl) && !vec4) return -2;
   if (tanh_mode) {
-    if (vec4) residual_layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
-    else residual_layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
+    if (vec4) residual_layernorm_kernel<true, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp, a_pl, o_pl);
+    else residual_layernorm_kernel<true, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp, a_pl, o_pl);
   } else {
-    if (vec4) residual_layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
-    else residual_layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp);
+    if (vec4) residual_layernorm_kernel<false, true><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp, a_pl, o_pl);
+    else residual_layernorm_kernel<false, false><<<grid, wpb * 32, 0, s>>>(a, b, scale, bias, out, groups, d, a_comp, a_pl, o_pl);
   }
   return (int)cudaGetLastError();
 }

@@ -29,6 +29,7 @@ struct dh_plan {
   int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
   int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators
   int tc_f16;     // tcgen05 path: 1 = kind::f16 pieces (D % 64 == 0), 0 = kind::tf32 pieces
+  int a_planes;   // jet passes keep the activations that feed a contraction as fp16 hi / lo planes (fp16 pieces, D = 256)
   // prepared (pre-split, transposed) weights for the tcgen05 path
   float* prep;            // device buffer owned by the plan
   size_t prep_floats;
@@ -141,13 +142,20 @@ static inline float* align_ws(void* ws) {
 enum { SL_QKV = 0, SL_O = 1, SL_D1 = 2, SL_D2 = 3, SL_OD = 4, SL_PER_LAYER = 5 };
 enum { VS_D2 = 0, VS_D1 = 1, VS_O = 2, VS_QKV = 3, VS_PER_LAYER = 4 };
 
-// tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows)
+// tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows).
+// a_planes: A is the fp16 hi / lo plane view of a [rows][D] buffer (common.cuh), written by the producing kernel.
 static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C, int64_t rows, int64_t ldc, int R,
-                           cudaStream_t s) {
+                           cudaStream_t s, bool a_planes = false) {
   const dh_plan::Slot& sl = p->slots[slot];
   ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * sl.Nout * p->D, s);
-  return gemm_tc(A, p->prep + sl.hi, p->prep + sl.lo, sl.bias == SIZE_MAX ? nullptr : p->prep + sl.bias,
-                 p->tc_f16 ? p->prep + sl.scale + 1 : nullptr, C, rows, sl.Nout, p->D, ldc, R, p->tc_f16, p->tc_merged, s);
+  TcGemm g;
+  g.A = A; g.lda = p->D; g.Wt_hi = p->prep + sl.hi; g.Wt_lo = p->prep + sl.lo; g.ldw = p->D;
+  g.bias = sl.bias == SIZE_MAX ? nullptr : p->prep + sl.bias;
+  g.inv_scale = p->tc_f16 ? p->prep + sl.scale + 1 : nullptr;
+  g.C = C; g.ldc = ldc; g.M = rows; g.N = sl.Nout; g.K = p->D; g.rpg = R;
+  g.f16 = p->tc_f16; g.merged = p->tc_merged; g.reduce_add = 0; g.a_scale = nullptr;
+  g.A_lo = a_planes ? reinterpret_cast<const __half*>(A) + rows * p->D : nullptr;
+  return gemm_tc_ex(g, s);
 }
 
 // SIMT path: C[rows, Nout] (ldc) = A[rows, D] @ W[D, Nout] (+ bias on value rows)
@@ -160,9 +168,9 @@ static inline int dense(const dh_plan* p, const float* A, const float* W, const 
 
 // The five dense contractions of the network, on whichever implementation the plan selected.
 static inline int dense_qkv(const dh_plan* p, const float* P, int l, const float* A, float* qkv, int64_t rows, int R,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool a_planes = false) {
   const int D = p->D;
-  if (p->gemm_impl == 1) return dense_tc(p, A, l * SL_PER_LAYER + SL_QKV, qkv, rows, 3 * D, R, s);
+  if (p->gemm_impl == 1) return dense_tc(p, A, l * SL_PER_LAYER + SL_QKV, qkv, rows, 3 * D, R, s, a_planes);
   const LayerOff& o = p->layer[l];
   int rc;
   if ((rc = dense(p, A, P + o.q_k, P + o.q_b, qkv, rows, D, 3 * D, R, s))) return rc;
@@ -170,18 +178,18 @@ static inline int dense_qkv(const dh_plan* p, const float* P, int l, const float
   return dense(p, A, P + o.v_k, P + o.v_b, qkv + 2 * D, rows, D, 3 * D, R, s);
 }
 static inline int dense_layer(const dh_plan* p, const float* P, int l, int which, const float* A, float* C,
-                              int64_t rows, int R, cudaStream_t s) {
+                              int64_t rows, int R, cudaStream_t s, bool a_planes = false) {
   const int D = p->D;
-  if (p->gemm_impl == 1) return dense_tc(p, A, l * SL_PER_LAYER + which, C, rows, D, R, s);
+  if (p->gemm_impl == 1) return dense_tc(p, A, l * SL_PER_LAYER + which, C, rows, D, R, s, a_planes);
   const LayerOff& o = p->layer[l];
   if (which == SL_O) return dense(p, A, P + o.o_k, P + o.o_b, C, rows, D, D, R, s);
   if (which == SL_D1) return dense(p, A, P + o.d1_k, nullptr, C, rows, D, D, R, s);
   return dense(p, A, P + o.d2_k, P + o.d2_b, C, rows, D, D, R, s);
 }
 static inline int dense_orb(const dh_plan* p, const float* P, const float* A, float* cbuf, int64_t rows, int R,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool a_planes = false) {
   const int LNK = p->LNK;
-  if (p->gemm_impl == 1) return dense_tc(p, A, p->nl * SL_PER_LAYER, cbuf, rows, 2 * (int64_t)LNK, R, s);
+  if (p->gemm_impl == 1) return dense_tc(p, A, p->nl * SL_PER_LAYER, cbuf, rows, 2 * (int64_t)LNK, R, s, a_planes);
   int rc;
   if ((rc = dense(p, A, P + p->orb_re_k, P + p->orb_re_b, cbuf, rows, LNK, 2 * (int64_t)LNK, R, s))) return rc;
   return dense(p, A, P + p->orb_im_k, P + p->orb_im_b, cbuf + LNK, rows, LNK, 2 * (int64_t)LNK, R, s);

@@ -16,6 +16,7 @@ CASES = [("c1", dict(nspins=(3, 0), flux=2), 96, 0.0), ("c2", dict(nspins=(6, 0)
 MODES = [("fp32 FMA (simt)", dict(DH_GEMM_IMPL="simt")),
          ("fp16 pieces, main+correction accumulators", dict(DH_GEMM_ACC="split")),
          ("fp16 pieces, one accumulator (default)", dict()),
+         ("fp16 pieces, one accumulator, activations as fp16 hi/lo planes (DH_A_PLANES=1)", dict(DH_A_PLANES="1")),
          ("tf32 pieces, main+correction accumulators", dict(DH_GEMM_IMPL="tf32"))]
 
 
@@ -33,7 +34,7 @@ for name, kw, B, kappa in CASES:
     p64 = OP.unflatten_params(flat32.double(), cfg)
     ref = None
     for label, env in MODES:
-        for k in ("DH_GEMM_IMPL", "DH_GEMM_ACC"):
+        for k in ("DH_GEMM_IMPL", "DH_GEMM_ACC", "DH_A_PLANES"):
             os.environ.pop(k, None)
         os.environ.update(env)
         plan = nat.Plan(nspins=cfg.nspins, flux=cfg.flux, interaction_strength=kappa)

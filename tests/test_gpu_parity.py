@@ -277,15 +277,17 @@ def test_gemm_tcgen05_dynamic_range(nat):
     assert torch.isfinite(out[3]).all() and torch.isnan(out[7]).all() and torch.isfinite(out[:3]).all()
 
 
-def test_gemm_tcgen05_cluster_multicast():
-    """The cluster / TMA-multicast variant of the weight loads (DH_GEMM_CLUSTER is read once per process)."""
+def test_gemm_tcgen05_launch_forms():
+    """The default form runs CTA pairs (tcgen05.mma.cta_group::2, covered by the tests above); this checks the
+    single-CTA form and its cluster / TMA-multicast variants of the weight loads (the switches are read once per
+    process)."""
     import os
     import subprocess
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for cl in ("2", "4"):
-        env = dict(os.environ, DH_GEMM_CLUSTER=cl)
+    for cl in ("1", "2", "4"):
+        env = dict(os.environ, DH_GEMM_PAIR="0", DH_GEMM_CLUSTER=cl)
         out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_gemm_quick.py")], env=env, cwd=root,
                              capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and "GEMM ok" in out.stdout, (cl, out.stdout[-2000:], out.stderr[-2000:])
@@ -298,15 +300,19 @@ def test_tcgen05_path_matches_simt_path(nat, monkeypatch):
     p64 = OP.init_params(cfg, 5, torch.float64, 0.1)
     flat = OP.flatten_params(p64).float().to(DEV)
     outs = {}
-    for impl in ("simt", "tc", "tf32"):
-        if impl == "tc":
+    for impl in ("simt", "tc", "tc_planes", "tf32"):
+        monkeypatch.delenv("DH_A_PLANES", raising=False)
+        if impl == "tc":  # default: fp16 pieces, activations as fp32 rows, split inside the contraction
             monkeypatch.delenv("DH_GEMM_IMPL", raising=False)
+        elif impl == "tc_planes":  # fp16 pieces, activations kept as fp16 hi / lo planes between the kernels
+            monkeypatch.delenv("DH_GEMM_IMPL", raising=False)
+            monkeypatch.setenv("DH_A_PLANES", "1")
         else:
             monkeypatch.setenv("DH_GEMM_IMPL", impl)
         plan = make_plan(nat, cfg)
         x = plan.init_walkers(40, seed=9)
         outs[impl] = plan.local_energy(flat, x)
-    for impl in ("tc", "tf32"):
+    for impl in ("tc", "tc_planes", "tf32"):
         for k in ("energy", "kinetic", "angular_momentum_square"):
             a, b = outs[impl][k], outs["simt"][k]
             rel = ((a - b).abs() / b.abs().clamp(min=1.0)).median().item()
