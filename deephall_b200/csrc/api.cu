@@ -40,7 +40,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   if (cfg->n_up < 1 || cfg->flux < 0 || cfg->ndets < 1 || cfg->num_heads < 1 || cfg->heads_dim < 1 ||
       cfg->num_layers < 0)
     return DH_E_BADARG;
-  if (cfg->n_dn != 0) return DH_E_UNSUPPORTED;  // spin-unpolarised systems: SURVEY 8f N4 (next)
+  if (cfg->n_dn < 0 || (cfg->network_type == 1 && cfg->n_dn != 0)) return DH_E_BADARG;
   dh_plan* p = new dh_plan();
   p->cfg = *cfg;
   p->N = cfg->n_up + cfg->n_dn;
@@ -54,6 +54,8 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->Q = 0.5f * cfg->flux;
   p->radius = cfg->radius > 0.f ? cfg->radius : sqrtf(p->Q);
   p->LNK = p->L * p->N * p->K;
+  p->nsb = cfg->n_dn > 0 ? 2 : 1;
+  p->orbN = 2 * p->nsb * p->LNK;
   p->nparams = 0;
   p->prep = nullptr;
   p->prep_floats = 0;
@@ -77,12 +79,13 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->K = 1;
     p->nl = 0;
     p->LNK = p->L * p->N * p->K;
+    p->orbN = 2 * p->LNK;
     p->gemm_impl = 0;
     p->tc_f16 = 0;
     p->tc_merged = 0;
     p->a_planes = 0;
-    p->ee_par = -1;
-    p->orb_re_k = p->orb_re_b = p->orb_im_k = p->orb_im_b = -1;
+    p->ee_par = p->ee_anti = -1;
+    for (int t = 0; t < 4; ++t) p->orb_k[t] = p->orb_b[t] = -1;
     p->off_W0 = -1;
     p->w0qkv = p->fold_tmp = p->cot_scale = 0;
     std::vector<double> ones(p->L, 1.0);
@@ -117,12 +120,15 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     add_entry(p, pl + "LayerNorm_" + std::to_string(2 * l + 1) + "/bias", {D}, &o.ln1_b);
   }
   const std::string ob = "Orbitals_0/featured_orbitals/";
-  add_entry(p, ob + "DenseGeneral_0/kernel", {D, L, N, K}, &p->orb_re_k);
-  add_entry(p, ob + "DenseGeneral_0/bias", {L, N, K}, &p->orb_re_b);
-  add_entry(p, ob + "DenseGeneral_1/kernel", {D, L, N, K}, &p->orb_im_k);
-  add_entry(p, ob + "DenseGeneral_1/bias", {L, N, K}, &p->orb_im_b);
-  p->ee_par = -1;
-  if (cfg->n_up >= 2) add_entry(p, "Jastrow_0/ee_par", {1}, &p->ee_par);
+  for (int t = 0; t < 4; ++t) p->orb_k[t] = p->orb_b[t] = -1;
+  for (int t = 0; t < 2 * p->nsb; ++t) {  // blocks.py:29-34: one (re, im) pair of DenseGeneral per non-empty spin block
+    add_entry(p, ob + "DenseGeneral_" + std::to_string(t) + "/kernel", {D, L, N, K}, &p->orb_k[t]);
+    add_entry(p, ob + "DenseGeneral_" + std::to_string(t) + "/bias", {L, N, K}, &p->orb_b[t]);
+  }
+  p->ee_par = p->ee_anti = -1;
+  const int nu = cfg->n_up, nd = cfg->n_dn;
+  if (nu * (nu - 1) / 2 + nd * (nd - 1) / 2 > 0) add_entry(p, "Jastrow_0/ee_par", {1}, &p->ee_par);  // blocks.py:91
+  if (nu * nd > 0) add_entry(p, "Jastrow_0/ee_anti", {1}, &p->ee_anti);                                 // blocks.py:99
 
   // prepared-weight slots for the tcgen05 path: [Npad][D] hi | lo, plus fused biases
   {
@@ -150,7 +156,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       p->slots.push_back(sl);
     };
     for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); slot(D, true); }
-    slot(2 * p->LNK, true);
+    slot(p->orbN, true);
     // reverse-pass planes: [D rows][Kpad], Kpad = K rounded up to 32
     auto vslot = [&](int K) {
       dh_plan::Slot sl;
@@ -163,7 +169,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       p->vslots.push_back(sl);
     };
     for (int l = 0; l < p->nl; ++l) { vslot(D); vslot(D); vslot(D); vslot(3 * D); }
-    vslot(2 * p->LNK);
+    vslot(p->orbN);
     p->cot_scale = off; off += al(2);
     p->w0qkv = off; off += al((size_t)4 * 3 * D);
     p->fold_tmp = off; off += al((size_t)D * D);
@@ -229,17 +235,18 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   const int R = jets ? 2 * N + 8 : 1;
   const int64_t rows = Bc * N * R;
   NetDims nd{N, R, D, p->H, p->hd, p->cfg.n_up};
-  TailDims td{N, R, p->L, p->K, p->twoQ, p->cfg.n_up};
+  TailDims td{N, R, p->L, p->K, p->twoQ, p->cfg.n_up, p->cfg.n_dn};
   int rc;
   if (p->laughlin) {
     // analytic Laughlin ground state: orbital-matrix jets straight from the coordinates, then the same tail
-    TailDims tl{N, R, p->L, 1, p->twoQ1, p->cfg.n_up};
+    TailDims tl{N, R, p->L, 1, p->twoQ1, p->cfg.n_up, 0};
     ProfScope pst(p, PC_TAIL, 0, s, 3);
     if ((rc = laughlin_orbital_jets(x, p->d_normfac, w.Mj, Bc, tl, s))) return rc;
     if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, tl, s))) return rc;
     fa.ld = w.ld;
     fa.x = x;
     fa.ee_par = nullptr;
+    fa.ee_anti = nullptr;
     fa.Q = p->Q;
     fa.radius = p->radius;
     fa.interaction_strength = p->cfg.interaction_strength;
@@ -291,6 +298,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   fa.ld = w.ld;
   fa.x = x;
   fa.ee_par = p->ee_par >= 0 ? P + p->ee_par : nullptr;
+  fa.ee_anti = p->ee_anti >= 0 ? P + p->ee_anti : nullptr;
   fa.Q = p->Q;
   fa.radius = p->radius;
   fa.interaction_strength = p->cfg.interaction_strength;
@@ -368,12 +376,13 @@ static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
     if ((rc = fill(s2, &p2, 1, false))) return rc;
     if ((rc = cp(s2.bias, o.d2_b, D))) return rc;
   }
-  // orbital projections: rows [0, LNK) = real part, rows [LNK, 2 LNK) = imaginary part; pad rows stay zero
+  // orbital projections, per spin block sb: rows [2 sb LNK, +LNK) = real part, the next LNK = imaginary part; pad rows stay zero
   const dh_plan::Slot& sb = p->slots[p->nl * SL_PER_LAYER];
-  const Part pb[2] = {{P + p->orb_re_k, LNK, LNK}, {P + p->orb_im_k, LNK, LNK}};
-  if ((rc = fill(sb, pb, 2, true))) return rc;
-  if ((rc = cp(sb.bias, p->orb_re_b, LNK))) return rc;
-  if ((rc = cp(sb.bias + LNK, p->orb_im_b, LNK))) return rc;
+  Part pb[4];
+  for (int t = 0; t < 2 * p->nsb; ++t) pb[t] = {P + p->orb_k[t], LNK, LNK};
+  if ((rc = fill(sb, pb, 2 * p->nsb, true))) return rc;
+  for (int t = 0; t < 2 * p->nsb; ++t)
+    if ((rc = cp(sb.bias + (size_t)t * LNK, p->orb_b[t], LNK))) return rc;
   p->launches += p->nl * (f16 ? 18 : 11) + 5 + (f16 ? 4 : 2);
   return 0;
 }
@@ -411,8 +420,9 @@ static int prepare_weights_vjp_now(dh_plan* p, const float* P, cudaStream_t s) {
     if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_O], &po, 1))) return rc;
     if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_QKV], pq, 3))) return rc;
   }
-  const Part pb[2] = {{P + p->orb_re_k, LNK, LNK}, {P + p->orb_im_k, LNK, LNK}};
-  if ((rc = fill(p->vslots[p->nl * VS_PER_LAYER], pb, 2))) return rc;
+  Part pb[4];
+  for (int t = 0; t < 2 * p->nsb; ++t) pb[t] = {P + p->orb_k[t], LNK, LNK};
+  if ((rc = fill(p->vslots[p->nl * VS_PER_LAYER], pb, 2 * p->nsb))) return rc;
   p->launches += (p->nl * 6 + 2) * (f16 ? 2 : 1);
   return 0;
 }
@@ -616,7 +626,7 @@ extern "C" int dh_debug_buffer(const dh_plan* p, int op, int64_t B, const char* 
   else if (n == "attn") { ptr = w.att; cnt = rows * p->D; }
   else if (n == "t1") { ptr = w.t1; cnt = rows * p->D; }
   else if (n == "t2") { ptr = w.t2; cnt = rows * p->D; }
-  else if (n == "c") { ptr = w.cbuf; cnt = rows * 2 * (int64_t)p->LNK; }
+  else if (n == "c") { ptr = w.cbuf; cnt = rows * (int64_t)p->orbN; }
   else if (n == "orb") { ptr = w.Mj; cnt = Bc * p->K * R * p->N * p->N * 2; }
   else if (n == "ld") { ptr = w.ld; cnt = Bc * p->K * R * 2; }
   else if (n == "lpjet") { ptr = w.lpjet; cnt = Bc * R * 2; }

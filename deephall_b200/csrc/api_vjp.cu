@@ -30,7 +30,7 @@ VjpWs carve_vjp(const dh_plan* p, float* base, int64_t Bc) {
     w.hA[l] = take(rows * D);
     w.z[l] = take(rows * D);
   }
-  w.cbuf = take(rows * 2 * (size_t)p->LNK);
+  w.cbuf = take(rows * (size_t)p->orbN);
   w.Mj = take((size_t)Bc * p->K * p->N * p->N * 2);
   w.ld = take((size_t)Bc * p->K * 2);
   w.Minv = take((size_t)Bc * p->K * p->N * p->N * 2);
@@ -41,7 +41,7 @@ VjpWs carve_vjp(const dh_plan* p, float* base, int64_t Bc) {
   w.gB = take(rows * D);
   w.gC = take(rows * D);
   w.gQKV = take(rows * 3 * D);
-  w.gCb = take(rows * 2 * (size_t)p->LNK);
+  w.gCb = take(rows * (size_t)p->orbN);
   w.floats = off;
   return w;
 }
@@ -105,7 +105,7 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
   if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
   const int N = p->N, D = p->D, nl = p->nl, LNK = p->LNK;
   NetDims nd{N, 1, D, p->H, p->hd, p->cfg.n_up};
-  TailDims td{N, 1, p->L, p->K, p->twoQ, p->cfg.n_up};
+  TailDims td{N, 1, p->L, p->K, p->twoQ, p->cfg.n_up, p->cfg.n_dn};
   int rc;
   if ((rc = prepare_weights(p, P, s))) return rc;
   if ((rc = prepare_weights_vjp(p, P, s))) return rc;
@@ -142,6 +142,7 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
       memset(&fa, 0, sizeof(fa));
       fa.ld = w.ld; fa.x = xc;
       fa.ee_par = p->ee_par >= 0 ? P + p->ee_par : nullptr;
+      fa.ee_anti = p->ee_anti >= 0 ? P + p->ee_anti : nullptr;
       fa.Q = p->Q; fa.radius = p->radius;
       fa.interaction_strength = p->cfg.interaction_strength;
       fa.interaction_type = p->cfg.interaction_type;
@@ -150,17 +151,21 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
     }
     // ------------------------------------------------------------ backward
     RUN(PC_TAIL, tail_bwd(cotc, w.ld, w.Minv, xc, p->d_normfac, w.gCb, Bc, td, s));
-    if (p->ee_par >= 0) RUN(PC_TAIL, jastrow_bwd(cotc, xc, P + p->ee_par, grad + p->ee_par, Bc, N, s));
-    // orbital projections
-    if ((rc = dense_bwd_w(p, hf, D, w.gCb, 2 * (int64_t)LNK, LNK, grad + p->orb_re_k, rows, s))) return rc;
-    if ((rc = dense_bwd_w(p, hf, D, w.gCb + LNK, 2 * (int64_t)LNK, LNK, grad + p->orb_im_k, rows, s))) return rc;
-    RUN(PC_OTHER, colsum_add(w.gCb, grad + p->orb_re_b, rows, LNK, 2 * (int64_t)LNK, s));
-    RUN(PC_OTHER, colsum_add(w.gCb + LNK, grad + p->orb_im_b, rows, LNK, 2 * (int64_t)LNK, s));
-    if (bwd_x_tc_ok(p, w.gCb, 2 * (int64_t)LNK, w.gH)) {
-      if ((rc = dense_bwd_x_tc(p, w.gCb, 2 * (int64_t)LNK, nl * VS_PER_LAYER, 2 * LNK, w.gH, rows, 0, s))) return rc;
+    if (p->ee_par >= 0 || p->ee_anti >= 0)
+      RUN(PC_TAIL, jastrow_bwd(cotc, xc, p->ee_par >= 0 ? P + p->ee_par : nullptr, p->ee_anti >= 0 ? P + p->ee_anti : nullptr,
+                               p->ee_par >= 0 ? grad + p->ee_par : nullptr, p->ee_anti >= 0 ? grad + p->ee_anti : nullptr, Bc,
+                               N, p->cfg.n_up, s));
+    // orbital projections (tail_bwd leaves zeros in the columns of the spin block a row's electron does not use)
+    const int64_t ldg = p->orbN;
+    for (int t = 0; t < 2 * p->nsb; ++t) {
+      if ((rc = dense_bwd_w(p, hf, D, w.gCb + (size_t)t * LNK, ldg, LNK, grad + p->orb_k[t], rows, s))) return rc;
+      RUN(PC_OTHER, colsum_add(w.gCb + (size_t)t * LNK, grad + p->orb_b[t], rows, LNK, ldg, s));
+    }
+    if (bwd_x_tc_ok(p, w.gCb, ldg, w.gH)) {
+      if ((rc = dense_bwd_x_tc(p, w.gCb, ldg, nl * VS_PER_LAYER, p->orbN, w.gH, rows, 0, s))) return rc;
     } else {
-      if ((rc = dense_bwd_x(p, w.gCb, 2 * (int64_t)LNK, P + p->orb_re_k, LNK, w.gH, rows, D, 0, s))) return rc;
-      if ((rc = dense_bwd_x(p, w.gCb + LNK, 2 * (int64_t)LNK, P + p->orb_im_k, LNK, w.gH, rows, D, 1, s))) return rc;
+      for (int t = 0; t < 2 * p->nsb; ++t)
+        if ((rc = dense_bwd_x(p, w.gCb + (size_t)t * LNK, ldg, P + p->orb_k[t], LNK, w.gH, rows, D, t > 0 ? 1 : 0, s))) return rc;
     }
     for (int l = nl - 1; l >= 0; --l) {
       const LayerOff& o = p->layer[l];

@@ -73,9 +73,9 @@ size_t attention_jets_smem(NetDims d);
 struct TailDims {
   int N, R, L, K;   // electrons, rows, orbitals (2Q+1), determinants
   int twoQ;
-  int n_up;
+  int n_up, n_dn;   // n_dn > 0: two spin blocks of orbital coefficients per row, electron i >= n_up reads the second
 };
-// c: [B*N*R, 2*L*N*K] (re block | im block) -> M jets [B][K][R][N][N] complex
+// c: [B*N*R, 2*nsb*L*N*K] (per spin block: re block | im block) -> M jets [B][K][R][N][N] complex
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s);
 // Laughlin ground-state orbital matrix jets (networks/laughlin.py:59-71): Mj [B][1][R][N][N] complex; d.L == d.N,
@@ -88,7 +88,8 @@ int logdet_jets_impl(const float* Mj, float* ld, float* Minv, int64_t B, TailDim
 struct FinalizeArgs {
   const float* ld;       // [B][K][R] complex
   const float* x;        // [B][N][2]
-  const float* ee_par;   // jastrow parameter (device scalar) or nullptr when N < 2
+  const float* ee_par;   // jastrow parameter of the parallel-spin pairs (device scalar) or nullptr when there are none
+  const float* ee_anti;  // same for the anti-parallel pairs
   float Q, radius, interaction_strength;
   int interaction_type;
   float* out_logpsi;     // [B] complex
@@ -115,8 +116,8 @@ int lp_from_logpsi(const float* logpsi_c, float* lp, int64_t B, cudaStream_t s);
 // ---- vjp_kernels.cu
 int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* x, const double* normfac,
              float* g_c, int64_t B, TailDims d, cudaStream_t s);
-int jastrow_bwd(const float* cot, const float* x, const float* ee_par, float* g_eepar, int64_t B, int N,
-                cudaStream_t s);
+int jastrow_bwd(const float* cot, const float* x, const float* ee_par, const float* ee_anti, float* g_eepar,
+                float* g_eeanti, int64_t B, int N, int n_up, cudaStream_t s);
 int residual_layernorm_bwd(const float* a, const float* b, const float* scale, const float* g_out, float* g_a,
                            float* g_b, float* g_scale, float* g_bias, int64_t rows, int D, int tanh_mode,
                            cudaStream_t s);

@@ -17,6 +17,8 @@ struct LayerOff {
 struct dh_plan {
   dh_config cfg;
   int N, L, K, D, H, hd, nl, twoQ, LNK;
+  int nsb;   // spin blocks with their own orbital projections (blocks.py:29-34): 1 (n_dn = 0) or 2
+  int orbN;  // columns of the orbital-coefficient tensor: 2 * nsb * LNK = [re | im] per spin block
   int laughlin;  // analytic Laughlin ground state instead of the Psiformer (no parameters)
   int twoQ1;     // laughlin: 2 Q1 = flux - 2 p (N - 1) = N - 1
   float Q, radius;
@@ -24,7 +26,8 @@ struct dh_plan {
   int64_t nparams;
   int64_t off_W0;
   std::vector<LayerOff> layer;
-  int64_t orb_re_k, orb_re_b, orb_im_k, orb_im_b, ee_par;
+  int64_t orb_k[4], orb_b[4];  // DenseGeneral_{2 sb + part}: spin block sb, part 0 = real, 1 = imaginary
+  int64_t ee_par, ee_anti;
   double* d_normfac;
   int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
   int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators
@@ -87,7 +90,7 @@ static inline int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
   int64_t c = p->cfg.chunk_walkers;
   if (c <= 0) {
     const int R = jets ? 2 * p->N + 8 : 1;
-    const double per_walker = (double)p->N * R * (7.0 * p->D + 2.0 * p->LNK) * sizeof(float) +
+    const double per_walker = (double)p->N * R * (7.0 * p->D + (double)p->orbN) * sizeof(float) +
                               (double)p->K * R * p->N * p->N * 2 * sizeof(float);
     c = (int64_t)(6.0 * 1024 * 1024 * 1024 / per_walker);
     const int64_t cap = jets ? 1024 : 16384;
@@ -109,7 +112,7 @@ static inline FwdWs carve_fwd(const dh_plan* p, float* base, int64_t Bc, bool je
   w.t2 = take(rows * p->D);
   w.qkv = take(rows * 3 * p->D);
   w.att = take(rows * p->D);
-  w.cbuf = take(rows * 2 * (size_t)p->LNK);
+  w.cbuf = take(rows * (size_t)p->orbN);
   w.Mj = take((size_t)Bc * p->K * R * p->N * p->N * 2);
   w.ld = take((size_t)Bc * p->K * R * 2);
   w.lpjet = take((size_t)Bc * R * 2);
@@ -189,10 +192,14 @@ static inline int dense_layer(const dh_plan* p, const float* P, int l, int which
 static inline int dense_orb(const dh_plan* p, const float* P, const float* A, float* cbuf, int64_t rows, int R,
                             cudaStream_t s, bool a_planes = false) {
   const int LNK = p->LNK;
-  if (p->gemm_impl == 1) return dense_tc(p, A, p->nl * SL_PER_LAYER, cbuf, rows, 2 * (int64_t)LNK, R, s, a_planes);
-  int rc;
-  if ((rc = dense(p, A, P + p->orb_re_k, P + p->orb_re_b, cbuf, rows, LNK, 2 * (int64_t)LNK, R, s))) return rc;
-  return dense(p, A, P + p->orb_im_k, P + p->orb_im_b, cbuf + LNK, rows, LNK, 2 * (int64_t)LNK, R, s);
+  // every row gets the projections of every spin block (columns [2 sb LNK, 2 (sb+1) LNK)); the tail kernels read
+  // the block of the row's electron
+  if (p->gemm_impl == 1) return dense_tc(p, A, p->nl * SL_PER_LAYER, cbuf, rows, p->orbN, R, s, a_planes);
+  for (int t = 0; t < 2 * p->nsb; ++t) {
+    int rc = dense(p, A, P + p->orb_k[t], P + p->orb_b[t], cbuf + (size_t)t * LNK, rows, LNK, p->orbN, R, s);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int prepare_weights(dh_plan* p, const float* P, cudaStream_t s);      // api.cu

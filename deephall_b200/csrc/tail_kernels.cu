@@ -95,8 +95,8 @@ orbital_contract_kernel(const float* __restrict__ c, const float* __restrict__ x
   envelope_jets(x[bi * 2], x[bi * 2 + 1], dm.twoQ, normfac, upow, vpow, env, nslots);
   const int NK = N * K;
   const int LNK = L * NK;
-  const int64_t ldc = 2 * (int64_t)LNK;
-  const float* cbase = c + bi * R * ldc;
+  const int64_t ldc = (dm.n_dn > 0 ? 4 : 2) * (int64_t)LNK;
+  const float* cbase = c + bi * R * ldc + ((dm.n_dn > 0 && i >= dm.n_up) ? 2 * LNK : 0);  // this electron's spin block
   Rows rw(N, R > 1);
   for (int t = threadIdx.x; t < R * NK; t += blockDim.x) {
     const int r = t / NK, jk = t % NK;
@@ -287,7 +287,7 @@ orbital_value_kernel(const float* __restrict__ c, const float* __restrict__ x, c
   }
   __syncwarp();
   const int NK = N * K, LNK = L * NK;
-  const float* cr = c + bi * 2 * (int64_t)LNK;
+  const float* cr = c + bi * (dm.n_dn > 0 ? 4 : 2) * (int64_t)LNK + ((dm.n_dn > 0 && i >= dm.n_up) ? 2 * LNK : 0);
   for (int jk0 = 0; jk0 < NK; jk0 += 32) {
     const int width = NK - jk0 < 32 ? NK - jk0 : 32;
     int NKp = 1;
@@ -578,11 +578,14 @@ struct PairTerms {  // per-walker pair sums computed by pair_terms()
 };
 
 // lane i < N handles electron i; returns warp-reduced sums and the per-lane J rows of the Jastrow.
-__device__ inline PairTerms pair_terms(const float* __restrict__ xw, int N, float alpha, bool want_jas,
-                                       float Q, float& jJ0, float& jJ1) {
+// Jastrow (blocks.py:91-105): parallel-spin pairs -a^2/4/(a + r) with a = ee_par, anti-parallel pairs
+// -a^2/2/(a + r) with a = ee_anti; a class without pairs has no parameter (pointer null, terms skipped).
+__device__ inline PairTerms pair_terms(const float* __restrict__ xw, int N, int n_up, const float* __restrict__ ee_par,
+                                       const float* __restrict__ ee_anti, float Q, float& jJ0, float& jJ1) {
   const int lane = threadIdx.x & 31;
   float jas = 0.f, jasS = 0.f, coul = 0.f, harm = 0.f;
   jJ0 = 0.f; jJ1 = 0.f;
+  const float a_par = ee_par ? ee_par[0] : 0.f, a_anti = ee_anti ? ee_anti[0] : 0.f;
   if (lane < N) {
     float st, ct, sp, cp;
     sincosf(xw[lane * 2], &st, &ct);
@@ -601,17 +604,19 @@ __device__ inline PairTerms pair_terms(const float* __restrict__ xw, int N, floa
       const float r2 = dx * dx + dy * dy + dz * dz;
       const float r = sqrtf(r2);
       const float cth = 1.f - 0.5f * r2;  // cos(theta_12)
-      if (want_jas) {
-        // f(r) = -a^2/4/(a+r)  ;  c = r_i.r_j ; dr/dc = -1/r ; d2r/dc2 = -1/r^3
+      const bool par = (lane < n_up) == (j < n_up);
+      if (par ? ee_par != nullptr : ee_anti != nullptr) {
+        // f(r) = -w a^2/(a+r), w = 1/4 (parallel) or 1/2 (anti-parallel) ;  c = r_i.r_j ; dr/dc = -1/r ; d2r/dc2 = -1/r^3
+        const float alpha = par ? a_par : a_anti, w = par ? 0.25f : 0.5f;
         const float ar = alpha + r;
-        const float fr = 0.25f * alpha * alpha / (ar * ar);         // df/dr
-        const float frr = -0.5f * alpha * alpha / (ar * ar * ar);   // d2f/dr2
-        const float fc = -fr / r;                                   // df/dc
-        const float fcc = frr / r2 - fr / (r2 * r);                 // d2f/dc2
+        const float fr = w * alpha * alpha / (ar * ar);                // df/dr
+        const float frr = -2.f * w * alpha * alpha / (ar * ar * ar);   // d2f/dr2
+        const float fc = -fr / r;                                      // df/dc
+        const float fcc = frr / r2 - fr / (r2 * r);                    // d2f/dc2
         jJ0 = fmaf(fc, w0x * qx + w0y * qy + w0z * qz, jJ0);
         jJ1 = fmaf(fc, w1x * qx + w1y * qy + w1z * qz, jJ1);
         if (j > lane) {
-          jas += -0.25f * alpha * alpha / ar;
+          jas += -w * alpha * alpha / ar;
           jasS += fc * (-4.f * cth) + fcc * 2.f * (1.f - cth * cth);
         }
       }
@@ -659,9 +664,8 @@ finalize_kernel(FinalizeArgs a, int64_t B, TailDims dm) {
     }
   }
   __syncwarp();
-  const float alpha = a.ee_par ? a.ee_par[0] : 0.f;
   float jJ0, jJ1;
-  PairTerms pt = pair_terms(a.x + b * N * 2, N, alpha, a.ee_par != nullptr, a.Q, jJ0, jJ1);
+  PairTerms pt = pair_terms(a.x + b * N * 2, N, dm.n_up, a.ee_par, a.ee_anti, a.Q, jJ0, jJ1);
   const float pot_raw = a.interaction_type == 0 ? pt.coul / a.radius : pt.harm;
   lp0.x += pt.jas;
   if (lane == 0 && a.out_logpsi) { a.out_logpsi[b * 2] = lp0.x; a.out_logpsi[b * 2 + 1] = lp0.y; }
@@ -716,7 +720,7 @@ finalize_kernel(FinalizeArgs a, int64_t B, TailDims dm) {
   }
   __syncwarp();
   // ---- add the Jastrow jets (real): J rows of own electron, S row; D/T rows vanish
-  if (a.ee_par != nullptr && lane < N) {
+  if ((a.ee_par != nullptr || a.ee_anti != nullptr) && lane < N) {
     lp[rw.J(2 * lane)].x += jJ0;
     lp[rw.J(2 * lane + 1)].x += jJ1;
   }
@@ -765,7 +769,7 @@ __global__ void potential_kernel(const float* __restrict__ x, float* __restrict_
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= B) return;
   float j0, j1;
-  PairTerms pt = pair_terms(x + b * N * 2, N, 0.f, false, Q, j0, j1);
+  PairTerms pt = pair_terms(x + b * N * 2, N, N, nullptr, nullptr, Q, j0, j1);
   if (lane == 0) out[b] = itype == 0 ? pt.coul / radius : pt.harm;
 }
 

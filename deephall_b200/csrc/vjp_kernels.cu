@@ -72,12 +72,19 @@ tail_bwd_kernel(const float* __restrict__ cot, const float* __restrict__ ld, con
   }
   __syncthreads();
   const int NK = N * K, LNK = L * NK;
-  float* row = g_c + bi * 2 * (int64_t)LNK;
+  // columns of this electron's spin block; the other block (if any) gets zeros
+  const int nsb = dm.n_dn > 0 ? 2 : 1, sbi = (dm.n_dn > 0 && i >= dm.n_up) ? 1 : 0;
+  float* row0 = g_c + bi * 2 * (int64_t)nsb * LNK;
+  float* row = row0 + 2 * (int64_t)sbi * LNK;
   for (int t = tid; t < LNK; t += blockDim.x) {
     const int m = t / NK, jk = t % NK;
     const cplx val = cmul(gm[jk], env[m]);
     row[t] = val.x;
     row[LNK + t] = -val.y;
+  }
+  if (nsb == 2) {
+    float* oth = row0 + 2 * (int64_t)(1 - sbi) * LNK;
+    for (int t = tid; t < 2 * LNK; t += blockDim.x) oth[t] = 0.f;
   }
 }
 
@@ -88,14 +95,16 @@ int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* 
   return (int)cudaGetLastError();
 }
 
-// d Jastrow / d ee_par summed over walkers with weight cot_re (the Jastrow is real).
+// d Jastrow / d ee_par and d ee_anti summed over walkers with weight cot_re (the Jastrow is real):
+// parallel pairs -a^2/4/(a+r) with a = ee_par, anti-parallel pairs -a^2/2/(a+r) with a = ee_anti (blocks.py:91-105).
 __global__ void jastrow_bwd_kernel(const float* __restrict__ cot, const float* __restrict__ x,
-                                   const float* __restrict__ ee_par, float* __restrict__ g_eepar, int64_t B, int N) {
+                                   const float* __restrict__ ee_par, const float* __restrict__ ee_anti,
+                                   float* __restrict__ g_eepar, float* __restrict__ g_eeanti, int64_t B, int N, int n_up) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-  float acc = 0.f;
+  float accp = 0.f, acca = 0.f;
   if (b < B && lane < N) {
-    const float a = ee_par[0];
+    const float ap = ee_par ? ee_par[0] : 0.f, aa = ee_anti ? ee_anti[0] : 0.f;
     const float* xw = x + b * N * 2;
     float st, ct, sp, cp;
     sincosf(xw[lane * 2], &st, &ct);
@@ -107,19 +116,27 @@ __global__ void jastrow_bwd_kernel(const float* __restrict__ cot, const float* _
       sincosf(xw[j * 2 + 1], &spj, &cpj);
       const float dx = rx - sj * cpj, dy = ry - sj * spj, dz = rz - cj;
       const float r = sqrtf(dx * dx + dy * dy + dz * dz);
+      const bool par = (lane < n_up) == (j < n_up);
+      const float a = par ? ap : aa;
       const float ar = a + r;
-      acc += -0.25f * (a * a + 2.f * a * r) / (ar * ar);  // d/da [-a^2/4/(a+r)]
+      const float d = -(a * a + 2.f * a * r) / (ar * ar);  // d/da [-a^2/(a+r)]
+      if (par) accp += 0.25f * d; else acca += 0.5f * d;
     }
-    acc *= cot[b * 2];
+    accp *= cot[b * 2];
+    acca *= cot[b * 2];
   }
-  acc = warp_sum(acc);
-  if (lane == 0 && b < B) atomicAdd(g_eepar, acc);
+  accp = warp_sum(accp);
+  acca = warp_sum(acca);
+  if (lane == 0 && b < B) {
+    if (g_eepar) atomicAdd(g_eepar, accp);
+    if (g_eeanti) atomicAdd(g_eeanti, acca);
+  }
 }
 
-int jastrow_bwd(const float* cot, const float* x, const float* ee_par, float* g_eepar, int64_t B, int N,
-                cudaStream_t s) {
+int jastrow_bwd(const float* cot, const float* x, const float* ee_par, const float* ee_anti, float* g_eepar,
+                float* g_eeanti, int64_t B, int N, int n_up, cudaStream_t s) {
   const int wpb = 4;
-  jastrow_bwd_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, s>>>(cot, x, ee_par, g_eepar, B, N);
+  jastrow_bwd_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, s>>>(cot, x, ee_par, ee_anti, g_eepar, g_eeanti, B, N, n_up);
   return (int)cudaGetLastError();
 }
 

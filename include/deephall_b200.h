@@ -48,7 +48,7 @@ extern "C" {
 
 /* System + network hyper-parameters: config.py:56-104 (System, PsiformerNetwork). */
 typedef struct dh_config {
-  int32_t n_up, n_dn;       /* system.nspins (n_dn must be 0 in this round)           */
+  int32_t n_up, n_dn;       /* system.nspins; n_up >= 1, n_dn >= 0 (Laughlin: n_dn = 0)  */
   int32_t flux;             /* system.flux = 2Q                                        */
   int32_t ndets;            /* network.psiformer.determinants                         */
   int32_t num_heads;        /* network.psiformer.num_heads                            */

@@ -61,8 +61,12 @@ CONFIGS = {
     "c4": dict(nspins=(10, 0), flux=21),
     "c5k4": dict(nspins=(16, 0), flux=45, ndets=4),
     "odd": dict(nspins=(5, 0), flux=11, ndets=3, num_heads=2, heads_dim=48, num_layers=1),
+    # spin-unpolarised systems: one (re, im) pair of orbital projections per spin block
+    # (blocks.py:29-34), spin feature -1 for the down electrons (psiformer.py:81), ee_anti Jastrow (blocks.py:99-105)
+    "spin32": dict(nspins=(3, 2), flux=8, ndets=2),
+    "spin11": dict(nspins=(1, 1), flux=2),
 }
-SIZES = {"c1": 64, "c2": 48, "c3": 24, "c4": 24, "c5k4": 8, "odd": 33}
+SIZES = {"c1": 64, "c2": 48, "c3": 24, "c4": 24, "c5k4": 8, "odd": 33, "spin32": 40, "spin11": 64}
 
 
 def test_param_layout_is_the_flax_tree(nat):
@@ -401,7 +405,7 @@ def test_mcmc_samples_psi_squared(nat):
 
 
 # --------------------------------------------------------------------------------- gradient + facade
-@pytest.mark.parametrize("name", ["c1", "odd", "c3"])
+@pytest.mark.parametrize("name", ["c1", "odd", "c3", "spin32", "spin11"])
 def test_vjp_parity(nat, name):
     B = 12
     cfg, p64, plan, flat, x = setup_case(nat, CONFIGS[name], B)
