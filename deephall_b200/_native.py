@@ -34,6 +34,7 @@ class dh_config(C.Structure):
         ("chunk_walkers", C.c_int32),
         ("network_type", C.c_int32),
         ("cf_flux", C.c_int32),
+        ("orbital_type", C.c_int32),
     ]
 
 
@@ -124,7 +125,7 @@ class Plan:
 
     def __init__(self, nspins=(3, 0), flux=2, ndets=1, num_heads=4, heads_dim=64, num_layers=2,
                  interaction_type="coulomb", interaction_strength=1.0, radius=None, chunk_walkers=0,
-                 network_type="psiformer", cf_flux=1):
+                 network_type="psiformer", cf_flux=1, orbital_type="full"):
         _need_cuda()
         self.lib = load()
         self.cfg = dh_config(
@@ -132,6 +133,7 @@ class Plan:
             0 if str(interaction_type) == "coulomb" else 1, float(interaction_strength),
             float(radius) if radius else 0.0, int(chunk_walkers),
             1 if str(network_type) == "laughlin" else 0, int(cf_flux),
+            1 if str(orbital_type) == "sparse" else 0,
         )
         self.N = int(nspins[0]) + int(nspins[1])
         self.R = 2 * self.N + 8

@@ -35,7 +35,7 @@ class PsiformerNetwork:  # config.py:92-97
 @dc.dataclass
 class Network:  # config.py:100-104
     type: str = "psiformer"  # "psiformer" | "laughlin" (analytic ground state, networks/laughlin.py)
-    orbital: str = "full"  # "full" | "sparse" (sparse: next row N4)
+    orbital: str = "full"  # OrbitalType, config.py:87-89: "full" | "sparse"
     psiformer: PsiformerNetwork = dc.field(default_factory=PsiformerNetwork)
 
 

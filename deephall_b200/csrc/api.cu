@@ -56,6 +56,10 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->LNK = p->L * p->N * p->K;
   p->nsb = cfg->n_dn > 0 ? 2 : 1;
   p->orbN = 2 * p->nsb * p->LNK;
+  p->sparse = cfg->orbital_type == 1 ? 1 : 0;
+  p->lll_k = p->lll_b = -1;
+  p->orb_eff = p->orb_geff = 0;
+  if (cfg->orbital_type != 0 && cfg->orbital_type != 1) { delete p; return DH_E_BADARG; }
   p->nparams = 0;
   p->prep = nullptr;
   p->prep_floats = 0;
@@ -80,6 +84,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->nl = 0;
     p->LNK = p->L * p->N * p->K;
     p->orbN = 2 * p->LNK;
+    p->sparse = 0;
     p->gemm_impl = 0;
     p->tc_f16 = 0;
     p->tc_merged = 0;
@@ -121,9 +126,14 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   }
   const std::string ob = "Orbitals_0/featured_orbitals/";
   for (int t = 0; t < 4; ++t) p->orb_k[t] = p->orb_b[t] = -1;
+  const int F = p->sparse ? 8 : L;  // blocks.py:47-56: sparse orbitals project to 8 features
   for (int t = 0; t < 2 * p->nsb; ++t) {  // blocks.py:29-34: one (re, im) pair of DenseGeneral per non-empty spin block
-    add_entry(p, ob + "DenseGeneral_" + std::to_string(t) + "/kernel", {D, L, N, K}, &p->orb_k[t]);
-    add_entry(p, ob + "DenseGeneral_" + std::to_string(t) + "/bias", {L, N, K}, &p->orb_b[t]);
+    add_entry(p, ob + "DenseGeneral_" + std::to_string(t) + "/kernel", {D, F, N, K}, &p->orb_k[t]);
+    add_entry(p, ob + "DenseGeneral_" + std::to_string(t) + "/bias", {F, N, K}, &p->orb_b[t]);
+  }
+  if (p->sparse) {  // blocks.py:57: nn.DenseGeneral(2Q + 1, axis=1) on the complex 8-feature orbitals
+    add_entry(p, "Orbitals_0/lll_weight/kernel", {8, L}, &p->lll_k);
+    add_entry(p, "Orbitals_0/lll_weight/bias", {L}, &p->lll_b);
   }
   p->ee_par = p->ee_anti = -1;
   const int nu = cfg->n_up, nd = cfg->n_dn;
@@ -173,6 +183,10 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->cot_scale = off; off += al(2);
     p->w0qkv = off; off += al((size_t)4 * 3 * D);
     p->fold_tmp = off; off += al((size_t)D * D);
+    if (p->sparse) {
+      p->orb_eff = off; off += al((size_t)2 * p->nsb * (D + 1) * p->LNK);
+      p->orb_geff = off; off += al((size_t)2 * p->nsb * (D + 1) * p->LNK);
+    }
     p->prep_floats = off;
     cudaError_t e0 = cudaMalloc(&p->prep, off * sizeof(float));
     if (e0 != cudaSuccess) { delete p; return (int)e0; }
@@ -308,9 +322,16 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
 }
 
 static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
-  if (p->gemm_impl != 1) return 0;
   const int D = p->D, LNK = p->LNK, f16 = p->tc_f16;
   int rc;
+  if (p->sparse) {  // effective full projections of the sparse orbitals (both contraction implementations read them)
+    for (int t = 0; t < 2 * p->nsb; ++t)
+      if ((rc = sparse_fold(P + p->orb_k[t], P + p->orb_b[t], P + p->lll_k, P + p->lll_b, (t & 1) == 0 ? 1 : 0,
+                            const_cast<float*>(orbW(p, P, t)), D, p->L, p->N * p->K, s)))
+        return rc;
+    p->launches += 2 * p->nsb;
+  }
+  if (p->gemm_impl != 1) return 0;
   auto cp = [&](size_t dst, int64_t src, size_t n) {
     return (int)cudaMemcpyAsync(p->prep + dst, P + src, n * sizeof(float), cudaMemcpyDeviceToDevice, s);
   };
@@ -379,10 +400,10 @@ static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
   // orbital projections, per spin block sb: rows [2 sb LNK, +LNK) = real part, the next LNK = imaginary part; pad rows stay zero
   const dh_plan::Slot& sb = p->slots[p->nl * SL_PER_LAYER];
   Part pb[4];
-  for (int t = 0; t < 2 * p->nsb; ++t) pb[t] = {P + p->orb_k[t], LNK, LNK};
+  for (int t = 0; t < 2 * p->nsb; ++t) pb[t] = {orbW(p, P, t), LNK, LNK};
   if ((rc = fill(sb, pb, 2 * p->nsb, true))) return rc;
   for (int t = 0; t < 2 * p->nsb; ++t)
-    if ((rc = cp(sb.bias + (size_t)t * LNK, p->orb_b[t], LNK))) return rc;
+    DH_CHECK(cudaMemcpyAsync(p->prep + sb.bias + (size_t)t * LNK, orbB(p, P, t), LNK * sizeof(float), cudaMemcpyDeviceToDevice, s));
   p->launches += p->nl * (f16 ? 18 : 11) + 5 + (f16 ? 4 : 2);
   return 0;
 }
@@ -421,7 +442,7 @@ static int prepare_weights_vjp_now(dh_plan* p, const float* P, cudaStream_t s) {
     if ((rc = fill(p->vslots[l * VS_PER_LAYER + VS_QKV], pq, 3))) return rc;
   }
   Part pb[4];
-  for (int t = 0; t < 2 * p->nsb; ++t) pb[t] = {P + p->orb_k[t], LNK, LNK};
+  for (int t = 0; t < 2 * p->nsb; ++t) pb[t] = {orbW(p, P, t), LNK, LNK};
   if ((rc = fill(p->vslots[p->nl * VS_PER_LAYER], pb, 2 * p->nsb))) return rc;
   p->launches += (p->nl * 6 + 2) * (f16 ? 2 : 1);
   return 0;

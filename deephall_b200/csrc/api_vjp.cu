@@ -99,6 +99,8 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
   cudaStream_t s = (cudaStream_t)stream;
   DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
   if (B == 0) return 0;
+  if (p->sparse)
+    DH_CHECK(cudaMemsetAsync(p->prep + p->orb_geff, 0, (size_t)2 * p->nsb * (p->D + 1) * p->LNK * sizeof(float), s));
   const int64_t chunk = pick_chunk(p, false, B);
   float* base = align_ws(ws);
   VjpWs w = carve_vjp(p, base, chunk);
@@ -157,15 +159,15 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
                                N, p->cfg.n_up, s));
     // orbital projections (tail_bwd leaves zeros in the columns of the spin block a row's electron does not use)
     const int64_t ldg = p->orbN;
-    for (int t = 0; t < 2 * p->nsb; ++t) {
-      if ((rc = dense_bwd_w(p, hf, D, w.gCb + (size_t)t * LNK, ldg, LNK, grad + p->orb_k[t], rows, s))) return rc;
-      RUN(PC_OTHER, colsum_add(w.gCb + (size_t)t * LNK, grad + p->orb_b[t], rows, LNK, ldg, s));
+    for (int t = 0; t < 2 * p->nsb; ++t) {  // (sparse orbitals: into the effective-kernel gradients, unfolded after the loop)
+      if ((rc = dense_bwd_w(p, hf, D, w.gCb + (size_t)t * LNK, ldg, LNK, orbGW(p, grad, t), rows, s))) return rc;
+      RUN(PC_OTHER, colsum_add(w.gCb + (size_t)t * LNK, orbGB(p, grad, t), rows, LNK, ldg, s));
     }
     if (bwd_x_tc_ok(p, w.gCb, ldg, w.gH)) {
       if ((rc = dense_bwd_x_tc(p, w.gCb, ldg, nl * VS_PER_LAYER, p->orbN, w.gH, rows, 0, s))) return rc;
     } else {
       for (int t = 0; t < 2 * p->nsb; ++t)
-        if ((rc = dense_bwd_x(p, w.gCb + (size_t)t * LNK, ldg, P + p->orb_k[t], LNK, w.gH, rows, D, t > 0 ? 1 : 0, s))) return rc;
+        if ((rc = dense_bwd_x(p, w.gCb + (size_t)t * LNK, ldg, orbW(p, P, t), LNK, w.gH, rows, D, t > 0 ? 1 : 0, s))) return rc;
     }
     for (int l = nl - 1; l >= 0; --l) {
       const LayerOff& o = p->layer[l];
@@ -199,6 +201,14 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
       if (tc && (rc = dense_bwd_x_tc(p, w.gQKV, 3 * D, l * VS_PER_LAYER + VS_QKV, 3 * D, w.gH, rows, 1, s))) return rc;
     }
     RUN(PC_OTHER, features_dense0_bwd(xc, w.gH, grad + p->off_W0, Bc, nd, s));
+  }
+  if (p->sparse) {
+    for (int t = 0; t < 2 * p->nsb; ++t) {
+      ProfScope ps(p, PC_OTHER, 0, s, 2);
+      if ((rc = sparse_fold_bwd(orbGW(p, grad, t), P + p->orb_k[t], P + p->orb_b[t], P + p->lll_k, (t & 1) == 0 ? 1 : 0,
+                                grad + p->orb_k[t], grad + p->orb_b[t], grad + p->lll_k, grad + p->lll_b, D, p->L, N * p->K, s)))
+        return rc;
+    }
   }
 #undef RUN
   return 0;

@@ -99,6 +99,13 @@ struct FinalizeArgs {
   float* lpjet;          // optional [B][R] complex debug copy of the log psi jets
 };
 int finalize(FinalizeArgs a, int64_t B, TailDims d, cudaStream_t s);
+// sparse orbitals (blocks.py:52-62).  W8 [D][8][NK], b8 [8][NK], Wl [8][L], bl [L] (added when add_bl != 0: the real
+// part) -> effective full projection Weff [(D + 1)][L][NK] whose last row is the bias; and the reverse map, which
+// ADDS into g_W8, g_b8, g_Wl (and g_bl when add_bl != 0) the gradients implied by g_Weff [(D + 1)][L][NK].
+int sparse_fold(const float* W8, const float* b8, const float* Wl, const float* bl, int add_bl, float* Weff, int D, int L,
+                int NK, cudaStream_t s);
+int sparse_fold_bwd(const float* g_Weff, const float* W8, const float* b8, const float* Wl, int add_bl, float* g_W8,
+                    float* g_b8, float* g_Wl, float* g_bl, int D, int L, int NK, cudaStream_t s);
 int potential(const float* x, float* out, int64_t B, int N, float Q, float radius, int interaction_type,
               cudaStream_t s);
 int slogdet_batched(const float* mats, int64_t B, int K, int n, float* out_sign, float* out_logabs,

@@ -28,6 +28,12 @@ struct dh_plan {
   std::vector<LayerOff> layer;
   int64_t orb_k[4], orb_b[4];  // DenseGeneral_{2 sb + part}: spin block sb, part 0 = real, 1 = imaginary
   int64_t ee_par, ee_anti;
+  // sparse orbitals (blocks.py:52-62): the projections have 8 features instead of L and a real (8, L) map
+  // `lll_weight` follows; both are linear, so prepare_weights folds them into effective full kernels
+  // [2 nsb][(D + 1) rows: D kernel rows + the bias row][LNK] kept at prep + orb_eff (gradients: prep + orb_geff)
+  int sparse;
+  int64_t lll_k, lll_b;
+  size_t orb_eff, orb_geff;
   double* d_normfac;
   int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
   int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators
@@ -141,6 +147,21 @@ static inline float* align_ws(void* ws) {
   return reinterpret_cast<float*>(a);
 }
 
+// kernel [D][LNK] and bias [LNK] of orbital projection t = 2 sb + part, as the contractions see them
+static inline const float* orbW(const dh_plan* p, const float* P, int t) {
+  return p->sparse ? p->prep + p->orb_eff + (size_t)t * (p->D + 1) * p->LNK : P + p->orb_k[t];
+}
+static inline const float* orbB(const dh_plan* p, const float* P, int t) {
+  return p->sparse ? orbW(p, P, t) + (size_t)p->D * p->LNK : P + p->orb_b[t];
+}
+// where the reverse pass accumulates d/d(kernel) and d/d(bias) of projection t
+static inline float* orbGW(const dh_plan* p, float* grad, int t) {
+  return p->sparse ? p->prep + p->orb_geff + (size_t)t * (p->D + 1) * p->LNK : grad + p->orb_k[t];
+}
+static inline float* orbGB(const dh_plan* p, float* grad, int t) {
+  return p->sparse ? orbGW(p, grad, t) + (size_t)p->D * p->LNK : grad + p->orb_b[t];
+}
+
 // --------------------------------------------------------------------------------- forward
 enum { SL_QKV = 0, SL_O = 1, SL_D1 = 2, SL_D2 = 3, SL_OD = 4, SL_PER_LAYER = 5 };
 enum { VS_D2 = 0, VS_D1 = 1, VS_O = 2, VS_QKV = 3, VS_PER_LAYER = 4 };
@@ -196,7 +217,7 @@ static inline int dense_orb(const dh_plan* p, const float* P, const float* A, fl
   // the block of the row's electron
   if (p->gemm_impl == 1) return dense_tc(p, A, p->nl * SL_PER_LAYER, cbuf, rows, p->orbN, R, s, a_planes);
   for (int t = 0; t < 2 * p->nsb; ++t) {
-    int rc = dense(p, A, P + p->orb_k[t], P + p->orb_b[t], cbuf + (size_t)t * LNK, rows, LNK, p->orbN, R, s);
+    int rc = dense(p, A, orbW(p, P, t), orbB(p, P, t), cbuf + (size_t)t * LNK, rows, LNK, p->orbN, R, s);
     if (rc) return rc;
   }
   return 0;

@@ -141,6 +141,75 @@ orbital_contract_kernel(const float* __restrict__ c, const float* __restrict__ x
 }
 
 // =============================================================================================
+// Sparse orbitals (blocks.py:52-62): c[i, m, j, k] = sum_s c8[i, s, j, k] Wl[s, m] + bl[m] with c8 the 8-feature
+// projection of h.  Both maps are linear, so they fold into one full projection (row d < D: kernel, row D: bias):
+//   Weff[d][m][jk] = sum_s W8[d][s][jk] Wl[s][m]          beff[m][jk] = sum_s b8[s][jk] Wl[s][m] (+ bl[m], real part)
+// =============================================================================================
+__global__ void sparse_fold_kernel(const float* __restrict__ W8, const float* __restrict__ b8, const float* __restrict__ Wl,
+                                   const float* __restrict__ bl, int add_bl, float* __restrict__ Weff, int D, int L, int NK) {
+  const int d = blockIdx.x;  // D = the bias row
+  const float* src = d < D ? W8 + (size_t)d * 8 * NK : b8;
+  float* dst = Weff + (size_t)d * L * NK;
+  for (int t = threadIdx.x; t < L * NK; t += blockDim.x) {
+    const int m = t / NK, jk = t % NK;
+    float acc = (d == D && add_bl) ? bl[m] : 0.f;
+#pragma unroll
+    for (int sft = 0; sft < 8; ++sft) acc = fmaf(src[sft * NK + jk], Wl[sft * L + m], acc);
+    dst[t] = acc;
+  }
+}
+// g_W8[d][s][jk] += sum_m g[d][m][jk] Wl[s][m]   (row D: g_b8)
+__global__ void sparse_fold_bwd_w8_kernel(const float* __restrict__ g, const float* __restrict__ Wl, float* __restrict__ g_W8,
+                                          float* __restrict__ g_b8, int D, int L, int NK) {
+  const int d = blockIdx.x;
+  const float* gr = g + (size_t)d * L * NK;
+  float* dst = d < D ? g_W8 + (size_t)d * 8 * NK : g_b8;
+  for (int t = threadIdx.x; t < 8 * NK; t += blockDim.x) {
+    const int sft = t / NK, jk = t % NK;
+    float acc = 0.f;
+    for (int m = 0; m < L; ++m) acc = fmaf(gr[m * NK + jk], Wl[sft * L + m], acc);
+    dst[t] += acc;
+  }
+}
+// g_Wl[s][m] += sum_{d <= D, jk} src[d][s][jk] g[d][m][jk]  (src row D = b8);  g_bl[m] += sum_jk g[D][m][jk]
+__global__ void sparse_fold_bwd_wl_kernel(const float* __restrict__ g, const float* __restrict__ W8, const float* __restrict__ b8,
+                                          int add_bl, float* __restrict__ g_Wl, float* __restrict__ g_bl, int D, int L, int NK) {
+  __shared__ float red[8];
+  const int sft = blockIdx.x / L, m = blockIdx.x % L;
+  float acc = 0.f, accb = 0.f;
+  for (int t = threadIdx.x; t < (D + 1) * NK; t += blockDim.x) {
+    const int d = t / NK, jk = t % NK;
+    const float gv = g[((size_t)d * L + m) * NK + jk];
+    const float w = d < D ? W8[((size_t)d * 8 + sft) * NK + jk] : b8[sft * NK + jk];
+    acc = fmaf(w, gv, acc);
+    if (d == D) accb += gv;
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    float v = warp_sum(pass == 0 ? acc : accb);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+      if (pass == 0) g_Wl[sft * L + m] += tot;
+      else if (add_bl && sft == 0) g_bl[m] += tot;
+    }
+  }
+}
+int sparse_fold(const float* W8, const float* b8, const float* Wl, const float* bl, int add_bl, float* Weff, int D, int L,
+                int NK, cudaStream_t s) {
+  sparse_fold_kernel<<<D + 1, 256, 0, s>>>(W8, b8, Wl, bl, add_bl, Weff, D, L, NK);
+  return (int)cudaGetLastError();
+}
+int sparse_fold_bwd(const float* g_Weff, const float* W8, const float* b8, const float* Wl, int add_bl, float* g_W8,
+                    float* g_b8, float* g_Wl, float* g_bl, int D, int L, int NK, cudaStream_t s) {
+  sparse_fold_bwd_w8_kernel<<<D + 1, 256, 0, s>>>(g_Weff, Wl, g_W8, g_b8, D, L, NK);
+  sparse_fold_bwd_wl_kernel<<<8 * L, 256, 0, s>>>(g_Weff, W8, b8, add_bl, g_Wl, g_bl, D, L, NK);
+  return (int)cudaGetLastError();
+}
+
+// =============================================================================================
 // Laughlin ground state (networks/laughlin.py:59-71, `full_orbitals`): orbital matrix
 //   O[i][m] = u_i^m v_i^(2Q1-m) * Jas_i,   Jas_i = prod_{j != i} e_ij,   e_ij = u_i v_j - u_j v_i
 // with its jets along the rotation flows.  One block per (walker, electron i).

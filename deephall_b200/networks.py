@@ -23,12 +23,14 @@ _PLANS: dict = {}
 
 
 def get_plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type="coulomb",
-             interaction_strength=1.0, radius=None, chunk_walkers=0, network_type="psiformer", cf_flux=1) -> _native.Plan:
+             interaction_strength=1.0, radius=None, chunk_walkers=0, network_type="psiformer", cf_flux=1,
+             orbital_type="full") -> _native.Plan:
     key = (tuple(nspins), int(flux), ndets, num_heads, heads_dim, num_layers, str(interaction_type),
-           float(interaction_strength), radius, chunk_walkers, str(network_type), int(cf_flux), torch.cuda.current_device())
+           float(interaction_strength), radius, chunk_walkers, str(network_type), int(cf_flux), str(orbital_type),
+           torch.cuda.current_device())
     if key not in _PLANS:
         _PLANS[key] = _native.Plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type,
-                                   interaction_strength, radius, chunk_walkers, network_type, cf_flux)
+                                   interaction_strength, radius, chunk_walkers, network_type, cf_flux, orbital_type)
     return _PLANS[key]
 
 
@@ -83,8 +85,9 @@ class Psiformer(B200Network):
     `make_network` passes in the reference."""
 
     def __init__(self, nspins, Q, ndets=1, num_heads=4, heads_dim=64, num_layers=2, orbital_type="full"):
-        if str(orbital_type) != "full":
-            raise NotImplementedError("orbital_type='sparse' is a 'next' row (SURVEY 8f N4)")
+        orbital_type = str(getattr(orbital_type, "value", orbital_type))  # OrbitalType enum or its string
+        if orbital_type not in ("full", "sparse"):
+            raise ValueError(f"orbital_type must be 'full' or 'sparse' (config.py:87-89), got {orbital_type!r}")
         self.nspins = (int(nspins[0]), int(nspins[1]))
         self.Q = float(Q)
         self.flux = int(round(2 * self.Q))
@@ -94,9 +97,10 @@ class Psiformer(B200Network):
     # ---- plan access (system-dependent parts default to the reference defaults)
     def plan(self, system: System | None = None) -> _native.Plan:
         if system is None:
-            return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers)
+            return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers,
+                            orbital_type=self.orbital_type)
         return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers,
-                        system.interaction_type, system.interaction_strength, system.radius)
+                        system.interaction_type, system.interaction_strength, system.radius, orbital_type=self.orbital_type)
 
     def param_layout(self) -> "OrderedDict[str, tuple[int, tuple[int, ...]]]":
         return self.plan().param_layout()
@@ -114,7 +118,7 @@ class Psiformer(B200Network):
         for name, (off, shape) in lay.items():
             n = int(np.prod(shape))
             if name.endswith("/kernel"):
-                fan_in = 4 if name.endswith("Dense_0/kernel") else D
+                fan_in = 4 if name.endswith("Dense_0/kernel") else (8 if name.endswith("lll_weight/kernel") else D)
                 std = math.sqrt(1.0 / fan_in) / 0.87962566103423978
                 t = torch.empty(n, dtype=torch.float64)
                 torch.nn.init.trunc_normal_(t, 0.0, 1.0, -2.0, 2.0, generator=gen)

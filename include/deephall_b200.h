@@ -60,6 +60,7 @@ typedef struct dh_config {
   int32_t chunk_walkers;    /* walkers per internal pass (0 = library default)        */
   int32_t network_type;     /* network.type: 0 = psiformer, 1 = laughlin (config.py:82-84)          */
   int32_t cf_flux;          /* laughlin: composite-fermion flux p (networks/laughlin.py:25), 0 -> 1  */
+  int32_t orbital_type;     /* network.orbital: 0 = full, 1 = sparse (config.py:87-89, blocks.py:47-62) */
 } dh_config;
 
 typedef struct dh_plan dh_plan;

@@ -288,7 +288,13 @@ def jet_logpsi(params, x, cfg: NetCfg):
             cs.append(torch.complex(re, im))
             idx += 2
         start += n_alpha
-    c = torch.cat(cs, dim=2).reshape(rw.R, B, N, L, N, K)
+    if cfg.orbital_type == "sparse":  # blocks.py:61-62: a linear map of the 8 features (bias on the value row only)
+        c8 = torch.cat(cs, dim=2).reshape(rw.R, B, N, 8, N, K)
+        w, b = params["Orbitals_0/lll_weight/kernel"], params["Orbitals_0/lll_weight/bias"]
+        c = torch.einsum("rbnsjk,sl->rbnljk", c8, w.to(c8.dtype))
+        c[0] = c[0] + b.to(c8.dtype)[:, None, None]
+    else:
+        c = torch.cat(cs, dim=2).reshape(rw.R, B, N, L, N, K)
     env = seed_envelope(x, cfg, rw)  # R,B,N,L
     orb = jet_mul(c, env[..., None, None], rw).sum(3)  # R,B,N(i),N(j),K
     M = orb.permute(0, 1, 4, 2, 3)  # R,B,K,N,N

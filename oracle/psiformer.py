@@ -36,6 +36,7 @@ class NetCfg:
     num_heads: int = 4
     heads_dim: int = 64
     num_layers: int = 2
+    orbital_type: str = "full"  # config.py:87-89: "full" | "sparse"
 
     @property
     def Q(self) -> float:
@@ -76,12 +77,16 @@ def param_shapes(cfg: NetCfg) -> "OrderedDict[str, tuple[int, ...]]":
         s[f"{p}LayerNorm_{2 * l + 1}/bias"] = (D,)
     o = "Orbitals_0/featured_orbitals/"
     idx = 0
+    F = L if cfg.orbital_type == "full" else 8  # blocks.py:47-56: sparse orbitals project to 8 features first
     for n_alpha in cfg.nspins:  # blocks.py:29-34: one (re, im) pair per non-empty spin block
         if n_alpha:
             for _ in range(2):
-                s[f"{o}DenseGeneral_{idx}/kernel"] = (D, L, N, K)
-                s[f"{o}DenseGeneral_{idx}/bias"] = (L, N, K)
+                s[f"{o}DenseGeneral_{idx}/kernel"] = (D, F, N, K)
+                s[f"{o}DenseGeneral_{idx}/bias"] = (F, N, K)
                 idx += 1
+    if cfg.orbital_type == "sparse":  # blocks.py:57: nn.DenseGeneral(2Q+1, axis=1), real parameters on complex input
+        s["Orbitals_0/lll_weight/kernel"] = (8, L)
+        s["Orbitals_0/lll_weight/bias"] = (L,)
     n_up, n_dn = cfg.nspins
     if n_up * (n_up - 1) // 2 + n_dn * (n_dn - 1) // 2 > 0:  # blocks.py:91
         s["Jastrow_0/ee_par"] = (1,)
@@ -114,6 +119,8 @@ def init_params(cfg: NetCfg, seed: int = 0, dtype=torch.float64, perturb: float 
         if name.endswith("/kernel"):
             if name.endswith("Dense_0/kernel"):
                 fan_in = 4
+            elif name.endswith("lll_weight/kernel"):
+                fan_in = 8
             else:
                 fan_in = D  # every other kernel contracts a D-dim (or HxHd = D) input
             t = _lecun_normal(gen, shape, fan_in)
@@ -213,7 +220,11 @@ def featured_orbitals(params, h, cfg: NetCfg):
             outs.append(torch.complex(re, im))
             idx += 2
         start += n_alpha
-    return torch.cat(outs, dim=-4)  # (..., N, L, N, K)
+    c = torch.cat(outs, dim=-4)  # (..., N, L or 8, N, K)
+    if cfg.orbital_type == "sparse":  # blocks.py:61-62: contract the 8 features with the (8, L) kernel, add the (real) bias
+        w, b = params["Orbitals_0/lll_weight/kernel"], params["Orbitals_0/lll_weight/bias"]
+        c = torch.einsum("...nsjk,sl->...nljk", c, w.to(c.dtype)) + b.to(c.dtype)[:, None, None]
+    return c  # (..., N, L, N, K)
 
 
 def jastrow(params, x, cfg: NetCfg):

@@ -34,7 +34,7 @@ def nat():
 
 def make_plan(nat, cfg, **kw):
     return nat.Plan(nspins=cfg.nspins, flux=cfg.flux, ndets=cfg.ndets, num_heads=cfg.num_heads, heads_dim=cfg.heads_dim,
-                    num_layers=cfg.num_layers, **kw)
+                    num_layers=cfg.num_layers, orbital_type=cfg.orbital_type, **kw)
 
 
 def setup_case(nat, kw, B, seed=0, burn=3, **plan_kw):
@@ -65,8 +65,12 @@ CONFIGS = {
     # (blocks.py:29-34), spin feature -1 for the down electrons (psiformer.py:81), ee_anti Jastrow (blocks.py:99-105)
     "spin32": dict(nspins=(3, 2), flux=8, ndets=2),
     "spin11": dict(nspins=(1, 1), flux=2),
+    # sparse orbitals (blocks.py:52-62): 8-feature projections followed by the real (8, 2Q+1) map lll_weight
+    "sparse": dict(nspins=(4, 0), flux=9, orbital_type="sparse"),
+    "sparse_spin": dict(nspins=(2, 2), flux=5, ndets=2, orbital_type="sparse"),
 }
-SIZES = {"c1": 64, "c2": 48, "c3": 24, "c4": 24, "c5k4": 8, "odd": 33, "spin32": 40, "spin11": 64}
+SIZES = {"c1": 64, "c2": 48, "c3": 24, "c4": 24, "c5k4": 8, "odd": 33, "spin32": 40, "spin11": 64, "sparse": 40,
+         "sparse_spin": 40}
 
 
 def test_param_layout_is_the_flax_tree(nat):
@@ -405,7 +409,7 @@ def test_mcmc_samples_psi_squared(nat):
 
 
 # --------------------------------------------------------------------------------- gradient + facade
-@pytest.mark.parametrize("name", ["c1", "odd", "c3", "spin32", "spin11"])
+@pytest.mark.parametrize("name", ["c1", "odd", "c3", "spin32", "spin11", "sparse", "sparse_spin"])
 def test_vjp_parity(nat, name):
     B = 12
     cfg, p64, plan, flat, x = setup_case(nat, CONFIGS[name], B)
@@ -496,6 +500,41 @@ def test_facade_matches_reference_api(nat):
     for _ in range(3):
         pm, st = vmc.step()
     assert abs(float(st["energy"].real) - 1.5) < 0.2  # train_test.py:46-48: energy hovers around N/2
+
+
+def test_facade_spin_unpolarised_sparse_orbitals(nat):
+    """`make_network` surface beyond the BASELINE configs: nspins=[2, 2] with orbital='sparse' through
+    the reference-shaped calls -- parameter tree names of blocks.py:29-34,57,92,100, log psi, local energy, one
+    Metropolis sweep and the energy gradient against the oracle."""
+    from deephall_b200 import hamiltonian, loss, mcmc, networks
+    from deephall_b200.config import Network, PsiformerNetwork, System
+
+    system = System(flux=5, nspins=(2, 2))
+    net = Network(orbital="sparse", psiformer=PsiformerNetwork(num_heads=2, heads_dim=16, num_layers=1, determinants=2))
+    model = networks.make_network(system, net)
+    cfg = OP.NetCfg(nspins=(2, 2), flux=5, ndets=2, num_heads=2, heads_dim=16, num_layers=1, orbital_type="sparse")
+    assert list(model.param_layout().keys()) == list(OP.param_shapes(cfg).keys())
+    params = model.init(3)
+    tree = model.param_tree(params)["params"]
+    assert tree["Orbitals_0"]["featured_orbitals"]["DenseGeneral_3"]["kernel"].shape == (32, 8, 4, 2)
+    assert tree["Orbitals_0"]["lll_weight"]["kernel"].shape == (8, 6) and set(tree["Jastrow_0"]) == {"ee_par", "ee_anti"}
+    B = 64
+    data = mcmc.init_guess(0, B, 4, model)
+    data, pmove = mcmc.make_mcmc_step(model.apply, B, steps=10)(params, data, mcmc.PhiloxKey(1), 0.3)
+    assert 0 < float(pmove) <= 1
+    p64 = OP.unflatten_params(params.double().cpu(), cfg)
+    x64 = data.double().cpu()
+    lp = model.apply(params, data).cpu()
+    ref = OP.logpsi(p64, x64, cfg)
+    assert ((lp.real.double() - ref.real).abs() / ref.real.abs().clamp(min=1.0)).median() < TOL_MEDIAN
+    assert phase_diff(lp.imag.double(), ref.imag).abs().median() < TOL_MEDIAN
+    el, obs = hamiltonian.local_energy(model.apply, system)(params, data)
+    eref = OJ.local_energy(p64, x64, cfg)["energy"]
+    assert ((el.cpu().to(torch.complex128) - eref).abs() / eref.abs()).median() < TOL_MEDIAN
+    stats, grads = loss.make_loss_fn(model.apply, system)(params, data)
+    o_stats, o_diff = OLoss.loss_stats(el.cpu().to(torch.complex128), {k: (v.cpu().to(torch.complex128) if v.is_complex() else v.cpu().double()) for k, v in obs.items()})
+    gref = OLoss.energy_grad_vjp(lambda p, xx: OP.logpsi(OP.unflatten_params(p, cfg), xx, cfg), OP.flatten_params(p64), x64, o_diff)
+    assert (grads.cpu().double() - gref).norm() / gref.norm() < 2e-4
 
 
 # --------------------------------------------------------------------------------- Laughlin (analytic, pinned)
