@@ -72,14 +72,19 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
         stats["variance"] = mean_sq - loss.real**2  # loss.py:91 (pmean is linear)
         if mode == LossMode.ENERGY_DIFF:
             return stats, diff
-        if mode == LossMode.SR_F_VECTOR:
-            raise NotImplementedError("SR_F_VECTOR needs two VJPs; not used by the adam/none optimizers")
-        # loss.py:60-64,99-106: 2 * nanmean_b[ dRe_b Re(diff_b) + dIm_b Im(diff_b) ], nan_to_num
+        # loss.py:60-64,99-106: 2 * nanmean_b[(dRe_b - i dIm_b) diff_b], nan_to_num.  Its real part
+        # 2 * nanmean_b[dRe_b Re(diff_b) + dIm_b Im(diff_b)] is one VJP with cotangent (2/B)(Re, Im) diff_b.
         d = torch.view_as_real(diff)
         valid = ~torch.isnan(d).any(-1)
         nvalid = valid.sum().clamp(min=1).to(torch.float32)
         cot = torch.where(valid[:, None], d, torch.zeros_like(d)) * (2.0 / nvalid)
-        grads = plan.logpsi_vjp(params, data.contiguous(), cot.contiguous())
-        return stats, torch.nan_to_num(grads)
+        grads = torch.nan_to_num(plan.logpsi_vjp(params, data.contiguous(), cot.contiguous()))
+        if mode == LossMode.SR_F_VECTOR:
+            # loss.py:107-108 keeps the complex vector; its imaginary part 2 * nanmean_b[dRe_b Im(diff_b) - dIm_b Re(diff_b)]
+            # is a second VJP with cotangent (2/B)(Im, -Re) diff_b
+            cot_i = torch.stack([cot[:, 1], -cot[:, 0]], dim=-1).contiguous()
+            grads_i = torch.nan_to_num(plan.logpsi_vjp(params, data.contiguous(), cot_i))
+            return stats, torch.complex(grads, grads_i)
+        return stats, grads
 
     return loss_and_grad

@@ -86,3 +86,14 @@ def energy_grad_vjp(f_batch, params_flat, x, diff):
     obj = (2.0 / x.shape[0]) * (lp.real * diff.real + lp.imag * diff.imag).sum()
     (g,) = torch.autograd.grad(obj, p)
     return g
+
+
+def sr_f_vector(f_batch, params_flat, x, diff):
+    """LossMode.SR_F_VECTOR (loss.py:99-108): the complex vector 2 * mean_b[(dRe_b - i dIm_b) diff_b], by two
+    reverse passes (valid when no walker is NaN)."""
+    p = params_flat.detach().clone().requires_grad_(True)
+    lp = f_batch(p, x)
+    s = 2.0 / x.shape[0]
+    (gr,) = torch.autograd.grad(s * (lp.real * diff.real + lp.imag * diff.imag).sum(), p, retain_graph=True)
+    (gi,) = torch.autograd.grad(s * (lp.real * diff.imag - lp.imag * diff.real).sum(), p)
+    return torch.complex(gr, gi)

@@ -535,6 +535,12 @@ def test_facade_spin_unpolarised_sparse_orbitals(nat):
     o_stats, o_diff = OLoss.loss_stats(el.cpu().to(torch.complex128), {k: (v.cpu().to(torch.complex128) if v.is_complex() else v.cpu().double()) for k, v in obs.items()})
     gref = OLoss.energy_grad_vjp(lambda p, xx: OP.logpsi(OP.unflatten_params(p, cfg), xx, cfg), OP.flatten_params(p64), x64, o_diff)
     assert (grads.cpu().double() - gref).norm() / gref.norm() < 2e-4
+    # LossMode.SR_F_VECTOR keeps the complex vector (loss.py:107-108); ENERGY_DIFF returns the clipped differences
+    _, fvec = loss.make_loss_fn(model.apply, system, loss.LossMode.SR_F_VECTOR)(params, data)
+    fref = OLoss.sr_f_vector(lambda p, xx: OP.logpsi(OP.unflatten_params(p, cfg), xx, cfg), OP.flatten_params(p64), x64, o_diff)
+    assert fvec.is_complex() and (fvec.cpu().to(torch.complex128) - fref).norm() / fref.norm() < 2e-4
+    _, dd = loss.make_loss_fn(model.apply, system, loss.LossMode.ENERGY_DIFF)(params, data)
+    assert (dd.cpu().to(torch.complex128) - o_diff).abs().max() < 1e-4
 
 
 # --------------------------------------------------------------------------------- Laughlin (analytic, pinned)
