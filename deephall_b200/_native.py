@@ -42,7 +42,14 @@ class dh_param_entry(C.Structure):
     _fields_ = [("name", C.c_char * 96), ("offset", C.c_int64), ("ndim", C.c_int32), ("shape", C.c_int32 * 4)]
 
 
-OP_LOGPSI, OP_LOCAL_ENERGY, OP_MCMC, OP_VJP = 0, 1, 2, 3
+class dh_kfac_entry(C.Structure):
+    _fields_ = [("name", C.c_char * 96), ("kind", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32),
+                ("has_bias", C.c_int32), ("rows_per_walker", C.c_int32), ("kernel_offset", C.c_int64),
+                ("bias_offset", C.c_int64), ("xtx_offset", C.c_int64), ("xsum_offset", C.c_int64),
+                ("gtg_offset", C.c_int64), ("diag_offset", C.c_int64), ("size", C.c_int64)]
+
+
+OP_LOGPSI, OP_LOCAL_ENERGY, OP_MCMC, OP_VJP, OP_KFAC = 0, 1, 2, 3, 4
 
 # symbol -> (restype, argtypes); must list every function include/deephall_b200.h declares
 _vp, _i64, _i32, _u64, _f = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_float
@@ -67,6 +74,8 @@ SIGNATURES = OrderedDict(
     dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     dh_debug_buffer=(C.c_int, [_vp, C.c_int, _i64, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     dh_launch_count=(C.c_longlong, [_vp]),
+    dh_kfac_layout=(C.c_int, [_vp, C.POINTER(dh_kfac_entry), C.POINTER(_i32), C.POINTER(_i64)]),
+    dh_kfac_factors=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     dh_profile_begin=(C.c_int, [_vp, _i32]),
     dh_profile_end=(C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i32), C.POINTER(C.c_double)]),
 )
@@ -288,6 +297,39 @@ class Plan:
         _check(self.lib.dh_logpsi_vjp(self.handle, _ptr(params), _ptr(x), B, _ptr(cot), _ptr(grad), _ptr(lpsi), _ptr(ws),
                                       ws.numel(), _stream()), "dh_logpsi_vjp")
         return (grad, torch.view_as_complex(lpsi)) if want_logpsi else grad
+
+
+def _kfac_methods():
+    def kfac_layout(self):
+        """[(dict per curvature block)], number of floats of the factor vector (dh_kfac_layout)."""
+        n, nf = C.c_int32(0), C.c_int64(0)
+        _check(self.lib.dh_kfac_layout(self.handle, None, C.byref(n), C.byref(nf)), "dh_kfac_layout")
+        arr = (dh_kfac_entry * n.value)()
+        _check(self.lib.dh_kfac_layout(self.handle, arr, C.byref(n), C.byref(nf)), "dh_kfac_layout")
+        fields = [f[0] for f in dh_kfac_entry._fields_]
+        out = []
+        for e in arr:
+            d = {f: getattr(e, f) for f in fields}
+            d["name"] = e.name.decode()
+            out.append(d)
+        return out, int(nf.value)
+
+    def kfac_factors(self, params, x):
+        """Factor sums of the KFAC curvature blocks for the walkers x (dh_kfac_factors): flat f32 tensor."""
+        self._prepare(params)
+        B = x.shape[0]
+        _, nf = self.kfac_layout()
+        out = torch.empty(nf, dtype=torch.float32, device=x.device)
+        ws = self.workspace(OP_KFAC, B)
+        _check(self.lib.dh_kfac_factors(self.handle, _ptr(params), _ptr(x), B, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+               "dh_kfac_factors")
+        return out
+
+    Plan.kfac_layout = kfac_layout
+    Plan.kfac_factors = kfac_factors
+
+
+_kfac_methods()
 
 
 def slogdet(mats):

@@ -70,6 +70,8 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->prof_on = false;
   p->prof_used = 0;
   p->launches = 0;
+  p->kfac_floats = 0;
+  p->kf_dense0 = p->kf_eepar = p->kf_eeanti = -1;
   p->laughlin = cfg->network_type == 1 ? 1 : 0;
   p->twoQ1 = 0;
   if (cfg->network_type != 0 && cfg->network_type != 1) { delete p; return DH_E_BADARG; }
@@ -139,6 +141,73 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   const int nu = cfg->n_up, nd = cfg->n_dn;
   if (nu * (nu - 1) / 2 + nd * (nd - 1) / 2 > 0) add_entry(p, "Jastrow_0/ee_par", {1}, &p->ee_par);  // blocks.py:91
   if (nu * nd > 0) add_entry(p, "Jastrow_0/ee_anti", {1}, &p->ee_anti);                                 // blocks.py:99
+
+  // ---- KFAC curvature blocks, in parameter order (optimizers/kfac.py: every Dense / DenseGeneral is a repeated-dense
+  // block over the electron axis; everything else gets a diagonal block)
+  {
+    int64_t off = 0;
+    auto take = [&](int64_t n) { int64_t o = off; off += (n + 63) / 64 * 64; return o; };
+    auto dense = [&](const std::string& name, int64_t k_off, int64_t b_off, int in, int out, int rpw, int64_t xtx,
+                     int64_t xsum) {
+      dh_kfac_entry e;
+      memset(&e, 0, sizeof(e));
+      snprintf(e.name, sizeof(e.name), "%s", name.c_str());
+      e.kind = 0; e.in_dim = in; e.out_dim = out; e.has_bias = b_off >= 0 ? 1 : 0; e.rows_per_walker = rpw;
+      e.kernel_offset = k_off; e.bias_offset = b_off;
+      e.xtx_offset = xtx; e.xsum_offset = b_off >= 0 ? xsum : -1;
+      e.gtg_offset = take((int64_t)out * out);
+      e.diag_offset = -1; e.size = (int64_t)in * out;
+      p->kfac.push_back(e);
+      return (int)p->kfac.size() - 1;
+    };
+    auto diag = [&](const std::string& name, int64_t p_off, int n) {
+      dh_kfac_entry e;
+      memset(&e, 0, sizeof(e));
+      snprintf(e.name, sizeof(e.name), "%s", name.c_str());
+      e.kind = 1; e.in_dim = e.out_dim = 0; e.has_bias = 0; e.rows_per_walker = 1;
+      e.kernel_offset = p_off; e.bias_offset = -1;
+      e.xtx_offset = e.xsum_offset = e.gtg_offset = -1;
+      e.diag_offset = take(n); e.size = n;
+      p->kfac.push_back(e);
+      return (int)p->kfac.size() - 1;
+    };
+    p->kf_dense0 = dense(pl + "Dense_0/kernel", p->off_W0, -1, 4, D, N, -1, -1);
+    p->kf_layer.resize(p->nl);
+    for (int l = 0; l < p->nl; ++l) {
+      const LayerOff& o = p->layer[l];
+      KfLayer& k = p->kf_layer[l];
+      const std::string a = pl + "MultiHeadAttention_" + std::to_string(l) + "/";
+      const int64_t xh = take((int64_t)D * D), sh = take(D);  // q, k, v share their input h
+      k.q = dense(a + "query/kernel", o.q_k, o.q_b, D, D, N, xh, sh);
+      k.k = dense(a + "key/kernel", o.k_k, o.k_b, D, D, N, xh, sh);
+      k.v = dense(a + "value/kernel", o.v_k, o.v_b, D, D, N, xh, sh);
+      const int64_t xo = take((int64_t)D * D), so = take(D);
+      k.o = dense(a + "out/kernel", o.o_k, o.o_b, D, D, N, xo, so);
+      k.d1 = dense(pl + "Dense_" + std::to_string(1 + 2 * l) + "/kernel", o.d1_k, -1, D, D, N, take((int64_t)D * D), -1);
+      k.ln0s = diag(pl + "LayerNorm_" + std::to_string(2 * l) + "/scale", o.ln0_s, D);
+      k.ln0b = diag(pl + "LayerNorm_" + std::to_string(2 * l) + "/bias", o.ln0_b, D);
+      const int64_t x2 = take((int64_t)D * D), s2 = take(D);
+      k.d2 = dense(pl + "Dense_" + std::to_string(2 + 2 * l) + "/kernel", o.d2_k, o.d2_b, D, D, N, x2, s2);
+      k.ln1s = diag(pl + "LayerNorm_" + std::to_string(2 * l + 1) + "/scale", o.ln1_s, D);
+      k.ln1b = diag(pl + "LayerNorm_" + std::to_string(2 * l + 1) + "/bias", o.ln1_b, D);
+    }
+    for (int t = 0; t < 4; ++t) p->kf_orb[t] = -1;
+    for (int sbk = 0; sbk < p->nsb; ++sbk) {  // the (re, im) projections of a spin block share its electrons' h
+      const int64_t xb = take((int64_t)D * D), sbs = take(D);
+      const int n_alpha = p->nsb == 1 ? N : (sbk == 0 ? cfg->n_up : cfg->n_dn);
+      for (int part = 0; part < 2; ++part) {
+        const int t = 2 * sbk + part;
+        p->kf_orb[t] = dense(ob + "DenseGeneral_" + std::to_string(t) + "/kernel", p->orb_k[t], p->orb_b[t], D, p->LNK, n_alpha, xb, sbs);
+      }
+    }
+    // no layer pattern matches the Jastrow parameters: kfac_jax's generic tag, whose diagonal is "naive" -- the square of
+    // the batch-summed gradient; the factor vector carries that sum (kind 2)
+    p->kf_eepar = p->ee_par >= 0 ? diag("Jastrow_0/ee_par", p->ee_par, 1) : -1;
+    p->kf_eeanti = p->ee_anti >= 0 ? diag("Jastrow_0/ee_anti", p->ee_anti, 1) : -1;
+    if (p->kf_eepar >= 0) p->kfac[p->kf_eepar].kind = 2;
+    if (p->kf_eeanti >= 0) p->kfac[p->kf_eeanti].kind = 2;
+    p->kfac_floats = off;
+  }
 
   // prepared-weight slots for the tcgen05 path: [Npad][D] hi | lo, plus fused biases
   {
@@ -236,6 +305,9 @@ extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* b
       fl = carve_mcmc(p, nullptr, B).floats + carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats;
       break;
     case DH_OP_VJP: fl = vjp_ws_floats(p, pick_chunk(p, false, B)); break;
+    case DH_OP_KFAC:
+      fl = vjp_ws_floats(p, pick_chunk(p, false, B)) + al((size_t)pick_chunk(p, false, B) * 2) + al((size_t)p->nparams);
+      break;
     default: return DH_E_BADARG;
   }
   *bytes = fl * sizeof(float) + 256;

@@ -84,34 +84,53 @@ int dense_bwd_w(const dh_plan* p, const float* X, int Din, const float* G, int64
   return gemm_simt(X, G, nullptr, dW, Din, Nout, rows, 1, Din, ldg, 1, Nout, 1, 1, split, s);
 }
 
+// out[dim][dim] += X^T X over `rows` rows of X (row stride ldx): a Kronecker factor sum of the KFAC curvature blocks
+int gram(const dh_plan* p, const float* X, int64_t ldx, int dim, float* out, int64_t rows, cudaStream_t s) {
+  ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * dim * dim, s);
+  const int tiles = ((dim + 127) / 128) * ((dim + 127) / 128);
+  int split = 296 / tiles;
+  if (split < 1) split = 1;
+  const int64_t max_split = (rows + 127) / 128;
+  if (split > max_split) split = (int)max_split;
+  return gemm_simt(X, X, nullptr, out, dim, dim, rows, 1, ldx, ldx, 1, dim, 1, 1, split, s);
+}
+
 }  // namespace
 
 size_t vjp_ws_floats(const dh_plan* p, int64_t Bc) { return carve_vjp(p, nullptr, Bc).floats; }
 
-extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot,
-                             float* grad, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
-  if (!p) return DH_E_BADARG;
-  if (p->laughlin) {  // no parameters: nothing to differentiate; log psi on request
-    if (out_logpsi && B > 0) return dh_logpsi(p, P, x, B, out_logpsi, ws, ws_bytes, stream);
-    return 0;
-  }
-  if (!P || !grad || B < 0 || (B > 0 && (!x || !cot))) return DH_E_BADARG;
-  cudaStream_t s = (cudaStream_t)stream;
-  DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
+// One forward + reverse pass.  kf == nullptr: the parameter gradient for per-walker cotangents `cot` (dh_logpsi_vjp).
+// kf != nullptr: cotangent (1, 0) for every walker and, instead of parameter gradients, the factor sums of the KFAC
+// curvature blocks (dh_kfac_factors); `cot` is ignored and the parameter-shaped by-products go to a scratch vector.
+static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot, float* grad, float* kf,
+                    float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s) {
+  if (kf) DH_CHECK(cudaMemsetAsync(kf, 0, (size_t)p->kfac_floats * sizeof(float), s));
+  if (!kf) DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
   if (B == 0) return 0;
   if (p->sparse)
     DH_CHECK(cudaMemsetAsync(p->prep + p->orb_geff, 0, (size_t)2 * p->nsb * (p->D + 1) * p->LNK * sizeof(float), s));
   const int64_t chunk = pick_chunk(p, false, B);
   float* base = align_ws(ws);
   VjpWs w = carve_vjp(p, base, chunk);
-  if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
+  size_t need = w.floats;
+  float* unit_cot = nullptr;
+  if (kf) {  // extra workspace: the unit cotangents and a parameter-shaped scratch vector
+    unit_cot = base + need; need += al((size_t)chunk * 2);
+    grad = base + need; need += al((size_t)p->nparams);
+  }
+  if (!ws || (size_t)((char*)(base + need) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
+  if (kf) {
+    if (int rcu = fill_unit_cot(unit_cot, chunk, s)) return rcu;
+    DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
+  }
+  auto K = [&](int idx) -> const dh_kfac_entry& { return p->kfac[idx]; };
   const int N = p->N, D = p->D, nl = p->nl, LNK = p->LNK;
   NetDims nd{N, 1, D, p->H, p->hd, p->cfg.n_up};
   TailDims td{N, 1, p->L, p->K, p->twoQ, p->cfg.n_up, p->cfg.n_dn};
   int rc;
   if ((rc = prepare_weights(p, P, s))) return rc;
   if ((rc = prepare_weights_vjp(p, P, s))) return rc;
-  if (p->gemm_impl == 1 && (rc = pow2_scale_tc(cot, 2 * B, p->prep + p->cot_scale, s))) return rc;
+  if (p->gemm_impl == 1 && (rc = pow2_scale_tc(kf ? unit_cot : cot, 2 * (kf ? chunk : B), p->prep + p->cot_scale, s))) return rc;
 #define RUN(cat, call)                          \
   do {                                          \
     ProfScope _ps(p, cat, 0, s);                \
@@ -122,7 +141,7 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
     const int64_t Bc = (B - b0) < chunk ? (B - b0) : chunk;
     const int64_t rows = Bc * N;
     const float* xc = x + b0 * N * 2;
-    const float* cotc = cot + b0 * 2;
+    const float* cotc = kf ? unit_cot : cot + b0 * 2;
     // ------------------------------------------------------------ forward, keeping activations
     RUN(PC_OTHER, features_dense0(xc, P + p->off_W0, w.hs[0], Bc, nd, s));
     for (int l = 0; l < nl; ++l) {
@@ -155,13 +174,30 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
     RUN(PC_TAIL, tail_bwd(cotc, w.ld, w.Minv, xc, p->d_normfac, w.gCb, Bc, td, s));
     if (p->ee_par >= 0 || p->ee_anti >= 0)
       RUN(PC_TAIL, jastrow_bwd(cotc, xc, p->ee_par >= 0 ? P + p->ee_par : nullptr, p->ee_anti >= 0 ? P + p->ee_anti : nullptr,
-                               p->ee_par >= 0 ? grad + p->ee_par : nullptr, p->ee_anti >= 0 ? grad + p->ee_anti : nullptr, Bc,
-                               N, p->cfg.n_up, s));
+                               p->ee_par >= 0 ? grad + p->ee_par : nullptr, p->ee_anti >= 0 ? grad + p->ee_anti : nullptr,
+                               nullptr, nullptr, Bc, N, p->cfg.n_up, s));
     // orbital projections (tail_bwd leaves zeros in the columns of the spin block a row's electron does not use)
     const int64_t ldg = p->orbN;
-    for (int t = 0; t < 2 * p->nsb; ++t) {  // (sparse orbitals: into the effective-kernel gradients, unfolded after the loop)
-      if ((rc = dense_bwd_w(p, hf, D, w.gCb + (size_t)t * LNK, ldg, LNK, orbGW(p, grad, t), rows, s))) return rc;
-      RUN(PC_OTHER, colsum_add(w.gCb + (size_t)t * LNK, orbGB(p, grad, t), rows, LNK, ldg, s));
+    if (!kf) {
+      for (int t = 0; t < 2 * p->nsb; ++t) {  // (sparse orbitals: into the effective-kernel gradients, unfolded after the loop)
+        if ((rc = dense_bwd_w(p, hf, D, w.gCb + (size_t)t * LNK, ldg, LNK, orbGW(p, grad, t), rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.gCb + (size_t)t * LNK, orbGB(p, grad, t), rows, LNK, ldg, s));
+      }
+    } else {
+      for (int sbk = 0; sbk < p->nsb; ++sbk) {
+        const dh_kfac_entry& e = K(p->kf_orb[2 * sbk]);
+        const float* xin = hf;
+        if (p->nsb == 2) {  // only this spin block's electrons pass through its projections (blocks.py:29-34)
+          RUN(PC_OTHER, mask_rows_by_spin(hf, w.gA, rows, D, N, p->cfg.n_up, sbk, s));
+          xin = w.gA;
+        }
+        if ((rc = gram(p, xin, D, D, kf + e.xtx_offset, rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(xin, kf + e.xsum_offset, rows, D, D, s));
+        for (int part = 0; part < 2; ++part) {
+          const int t = 2 * sbk + part;
+          if ((rc = gram(p, w.gCb + (size_t)t * LNK, ldg, LNK, kf + K(p->kf_orb[t]).gtg_offset, rows, s))) return rc;
+        }
+      }
     }
     if (bwd_x_tc_ok(p, w.gCb, ldg, w.gH)) {
       if ((rc = dense_bwd_x_tc(p, w.gCb, ldg, nl * VS_PER_LAYER, p->orbN, w.gH, rows, 0, s))) return rc;
@@ -171,38 +207,78 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
     }
     for (int l = nl - 1; l >= 0; --l) {
       const LayerOff& o = p->layer[l];
+      const KfLayer* kl = kf ? &p->kf_layer[l] : nullptr;
       // h_out = LN1(hA + tanh(z)) : gH -> (gA = d/d hA, gB = d/d z)
+      if (kf) RUN(PC_LAYERNORM, ln_fisher_diag(w.hA[l], w.z[l], w.gH, kf + K(kl->ln1s).diag_offset, kf + K(kl->ln1b).diag_offset, Bc, N, D, 1, s));
       RUN(PC_LAYERNORM, residual_layernorm_bwd(w.hA[l], w.z[l], P + o.ln1_s, w.gH, w.gA, w.gB, grad + o.ln1_s,
                                                grad + o.ln1_b, rows, D, 1, s));
-      if ((rc = dense_bwd_w(p, w.hA[l], D, w.gB, D, D, grad + o.d2_k, rows, s))) return rc;
-      RUN(PC_OTHER, colsum_add(w.gB, grad + o.d2_b, rows, D, D, s));
+      if (!kf) {
+        if ((rc = dense_bwd_w(p, w.hA[l], D, w.gB, D, D, grad + o.d2_k, rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.gB, grad + o.d2_b, rows, D, D, s));
+      } else {
+        if ((rc = gram(p, w.hA[l], D, D, kf + K(kl->d2).xtx_offset, rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.hA[l], kf + K(kl->d2).xsum_offset, rows, D, D, s));
+        if ((rc = gram(p, w.gB, D, D, kf + K(kl->d2).gtg_offset, rows, s))) return rc;
+      }
       const bool tc = bwd_x_tc_ok(p, w.gB, D, w.gA) && bwd_x_tc_ok(p, w.gC, D, w.gH) && bwd_x_tc_ok(p, w.gQKV, 3 * D, w.gH);
       if (tc) { if ((rc = dense_bwd_x_tc(p, w.gB, D, l * VS_PER_LAYER + VS_D2, D, w.gA, rows, 1, s))) return rc; }
       else if ((rc = dense_bwd_x(p, w.gB, D, P + o.d2_k, D, w.gA, rows, D, 1, s))) return rc;
       // hA = LN0(h_in + t2) : gA -> (gH = d/d h_in, gB = d/d t2)
+      if (kf) RUN(PC_LAYERNORM, ln_fisher_diag(w.hs[l], w.t2[l], w.gA, kf + K(kl->ln0s).diag_offset, kf + K(kl->ln0b).diag_offset, Bc, N, D, 0, s));
       RUN(PC_LAYERNORM, residual_layernorm_bwd(w.hs[l], w.t2[l], P + o.ln0_s, w.gA, w.gH, w.gB, grad + o.ln0_s,
                                                grad + o.ln0_b, rows, D, 0, s));
-      if ((rc = dense_bwd_w(p, w.t1[l], D, w.gB, D, D, grad + o.d1_k, rows, s))) return rc;
+      if (!kf) {
+        if ((rc = dense_bwd_w(p, w.t1[l], D, w.gB, D, D, grad + o.d1_k, rows, s))) return rc;
+      } else {
+        if ((rc = gram(p, w.t1[l], D, D, kf + K(kl->d1).xtx_offset, rows, s))) return rc;
+        if ((rc = gram(p, w.gB, D, D, kf + K(kl->d1).gtg_offset, rows, s))) return rc;
+      }
       if (tc) { if ((rc = dense_bwd_x_tc(p, w.gB, D, l * VS_PER_LAYER + VS_D1, D, w.gC, rows, 0, s))) return rc; }
       else if ((rc = dense_bwd_x(p, w.gB, D, P + o.d1_k, D, w.gC, rows, D, 0, s))) return rc;   // gC = d/d t1
-      if ((rc = dense_bwd_w(p, w.att[l], D, w.gC, D, D, grad + o.o_k, rows, s))) return rc;
-      RUN(PC_OTHER, colsum_add(w.gC, grad + o.o_b, rows, D, D, s));
+      if (!kf) {
+        if ((rc = dense_bwd_w(p, w.att[l], D, w.gC, D, D, grad + o.o_k, rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.gC, grad + o.o_b, rows, D, D, s));
+      } else {
+        if ((rc = gram(p, w.att[l], D, D, kf + K(kl->o).xtx_offset, rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.att[l], kf + K(kl->o).xsum_offset, rows, D, D, s));
+        if ((rc = gram(p, w.gC, D, D, kf + K(kl->o).gtg_offset, rows, s))) return rc;
+      }
       if (tc) { if ((rc = dense_bwd_x_tc(p, w.gC, D, l * VS_PER_LAYER + VS_O, D, w.gB, rows, 0, s))) return rc; }
       else if ((rc = dense_bwd_x(p, w.gC, D, P + o.o_k, D, w.gB, rows, D, 0, s))) return rc;    // gB = d/d att
       RUN(PC_ATTENTION, attention_value_bwd(w.qkv[l], w.gB, w.gQKV, Bc, nd, s));
       const int64_t qk[3] = {o.q_k, o.k_k, o.v_k};
       const int64_t qb[3] = {o.q_b, o.k_b, o.v_b};
+      if (kf) {
+        if ((rc = gram(p, w.hs[l], D, D, kf + K(kl->q).xtx_offset, rows, s))) return rc;
+        RUN(PC_OTHER, colsum_add(w.hs[l], kf + K(kl->q).xsum_offset, rows, D, D, s));
+        const int kq[3] = {kl->q, kl->k, kl->v};
+        for (int t = 0; t < 3; ++t)
+          if ((rc = gram(p, w.gQKV + t * D, 3 * D, D, kf + K(kq[t]).gtg_offset, rows, s))) return rc;
+      }
       for (int t = 0; t < 3; ++t) {
-        if ((rc = dense_bwd_w(p, w.hs[l], D, w.gQKV + t * D, 3 * D, D, grad + qk[t], rows, s))) return rc;
-        RUN(PC_OTHER, colsum_add(w.gQKV + t * D, grad + qb[t], rows, D, 3 * D, s));
+        if (!kf) {
+          if ((rc = dense_bwd_w(p, w.hs[l], D, w.gQKV + t * D, 3 * D, D, grad + qk[t], rows, s))) return rc;
+          RUN(PC_OTHER, colsum_add(w.gQKV + t * D, grad + qb[t], rows, D, 3 * D, s));
+        }
         if (!tc && (rc = dense_bwd_x(p, w.gQKV + t * D, 3 * D, P + qk[t], D, w.gH, rows, D, 1, s))) return rc;
       }
       // gH += gQKV[rows, 3D] @ (Wq | Wk | Wv)^T : one K = 3D contraction added to the residual-path gradient
       if (tc && (rc = dense_bwd_x_tc(p, w.gQKV, 3 * D, l * VS_PER_LAYER + VS_QKV, 3 * D, w.gH, rows, 1, s))) return rc;
     }
+    if (kf) {  // Dense_0: the caller forms sum feat feat^T itself; here the output-gradient factor
+      if ((rc = gram(p, w.gH, D, D, kf + K(p->kf_dense0).gtg_offset, rows, s))) return rc;
+      continue;
+    }
     RUN(PC_OTHER, features_dense0_bwd(xc, w.gH, grad + p->off_W0, Bc, nd, s));
   }
-  if (p->sparse) {
+  if (kf) {  // naive-diagonal blocks: the batch-summed gradient of Re log psi (accumulated in the scratch vector)
+    const int idx[2] = {p->kf_eepar, p->kf_eeanti};
+    const int64_t src[2] = {p->ee_par, p->ee_anti};
+    for (int t = 0; t < 2; ++t)
+      if (idx[t] >= 0)
+        DH_CHECK(cudaMemcpyAsync(kf + K(idx[t]).diag_offset, grad + src[t], sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (p->sparse && !kf) {
     for (int t = 0; t < 2 * p->nsb; ++t) {
       ProfScope ps(p, PC_OTHER, 0, s, 2);
       if ((rc = sparse_fold_bwd(orbGW(p, grad, t), P + p->orb_k[t], P + p->orb_b[t], P + p->lll_k, (t & 1) == 0 ? 1 : 0,
@@ -212,4 +288,34 @@ extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t
   }
 #undef RUN
   return 0;
+}
+
+extern "C" int dh_logpsi_vjp(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot,
+                             float* grad, float* out_logpsi, void* ws, size_t ws_bytes, void* stream) {
+  if (!p) return DH_E_BADARG;
+  if (p->laughlin) {  // no parameters: nothing to differentiate; log psi on request
+    if (out_logpsi && B > 0) return dh_logpsi(p, P, x, B, out_logpsi, ws, ws_bytes, stream);
+    return 0;
+  }
+  if (!P || !grad || B < 0 || (B > 0 && (!x || !cot))) return DH_E_BADARG;
+  return vjp_core(p, P, x, B, cot, grad, nullptr, out_logpsi, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dh_kfac_layout(const dh_plan* p, dh_kfac_entry* entries, int32_t* n, int64_t* factor_floats) {
+  if (!p || !n) return DH_E_BADARG;
+  if (entries) {
+    if (*n < (int32_t)p->kfac.size()) return DH_E_BADARG;
+    memcpy(entries, p->kfac.data(), p->kfac.size() * sizeof(dh_kfac_entry));
+  }
+  *n = (int32_t)p->kfac.size();
+  if (factor_floats) *factor_floats = p->kfac_floats;
+  return 0;
+}
+
+extern "C" int dh_kfac_factors(dh_plan* p, const float* P, const float* x, int64_t B, float* factors, void* ws,
+                               size_t ws_bytes, void* stream) {
+  if (!p) return DH_E_BADARG;
+  if (p->laughlin || p->sparse) return DH_E_UNSUPPORTED;
+  if (!P || !factors || B < 0 || (B > 0 && !x)) return DH_E_BADARG;
+  return vjp_core(p, P, x, B, nullptr, nullptr, factors, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -124,7 +124,12 @@ int lp_from_logpsi(const float* logpsi_c, float* lp, int64_t B, cudaStream_t s);
 int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* x, const double* normfac,
              float* g_c, int64_t B, TailDims d, cudaStream_t s);
 int jastrow_bwd(const float* cot, const float* x, const float* ee_par, const float* ee_anti, float* g_eepar,
-                float* g_eeanti, int64_t B, int N, int n_up, cudaStream_t s);
+                float* g_eeanti, float* sq_eepar, float* sq_eeanti, int64_t B, int N, int n_up, cudaStream_t s);
+// KFAC factor pass (dh_kfac_factors)
+int fill_unit_cot(float* cot, int64_t n, cudaStream_t s);
+int mask_rows_by_spin(const float* src, float* dst, int64_t rows, int D, int N, int n_up, int sb, cudaStream_t s);
+int ln_fisher_diag(const float* a, const float* b, const float* gy, float* sq_scale, float* sq_bias, int64_t B, int N, int D,
+                   int tanh_mode, cudaStream_t s);
 int residual_layernorm_bwd(const float* a, const float* b, const float* scale, const float* g_out, float* g_a,
                            float* g_b, float* g_scale, float* g_bias, int64_t rows, int D, int tanh_mode,
                            cudaStream_t s);

@@ -14,6 +14,8 @@ struct LayerOff {
   int64_t q_k, q_b, k_k, k_b, v_k, v_b, o_k, o_b, d1_k, ln0_s, ln0_b, d2_k, d2_b, ln1_s, ln1_b;
 };
 
+struct KfLayer { int q, k, v, o, d1, d2, ln0s, ln0b, ln1s, ln1b; };  // indices into dh_plan::kfac
+
 struct dh_plan {
   dh_config cfg;
   int N, L, K, D, H, hd, nl, twoQ, LNK;
@@ -34,6 +36,11 @@ struct dh_plan {
   int sparse;
   int64_t lll_k, lll_b;
   size_t orb_eff, orb_geff;
+  // KFAC curvature blocks (dh_kfac_layout / dh_kfac_factors)
+  std::vector<dh_kfac_entry> kfac;
+  std::vector<KfLayer> kf_layer;
+  int kf_dense0, kf_orb[4], kf_eepar, kf_eeanti;
+  int64_t kfac_floats;
   double* d_normfac;
   int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
   int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators

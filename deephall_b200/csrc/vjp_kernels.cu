@@ -99,7 +99,8 @@ int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* 
 // parallel pairs -a^2/4/(a+r) with a = ee_par, anti-parallel pairs -a^2/2/(a+r) with a = ee_anti (blocks.py:91-105).
 __global__ void jastrow_bwd_kernel(const float* __restrict__ cot, const float* __restrict__ x,
                                    const float* __restrict__ ee_par, const float* __restrict__ ee_anti,
-                                   float* __restrict__ g_eepar, float* __restrict__ g_eeanti, int64_t B, int N, int n_up) {
+                                   float* __restrict__ g_eepar, float* __restrict__ g_eeanti, float* __restrict__ sq_eepar,
+                                   float* __restrict__ sq_eeanti, int64_t B, int N, int n_up) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   float accp = 0.f, acca = 0.f;
@@ -130,13 +131,76 @@ __global__ void jastrow_bwd_kernel(const float* __restrict__ cot, const float* _
   if (lane == 0 && b < B) {
     if (g_eepar) atomicAdd(g_eepar, accp);
     if (g_eeanti) atomicAdd(g_eeanti, acca);
+    // KFAC diagonal blocks: sum over walkers of the squared per-walker gradient
+    if (sq_eepar) atomicAdd(sq_eepar, accp * accp);
+    if (sq_eeanti) atomicAdd(sq_eeanti, acca * acca);
   }
 }
 
 int jastrow_bwd(const float* cot, const float* x, const float* ee_par, const float* ee_anti, float* g_eepar,
-                float* g_eeanti, int64_t B, int N, int n_up, cudaStream_t s) {
+                float* g_eeanti, float* sq_eepar, float* sq_eeanti, int64_t B, int N, int n_up, cudaStream_t s) {
   const int wpb = 4;
-  jastrow_bwd_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, s>>>(cot, x, ee_par, ee_anti, g_eepar, g_eeanti, B, N, n_up);
+  jastrow_bwd_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, 0, s>>>(cot, x, ee_par, ee_anti, g_eepar, g_eeanti, sq_eepar,
+                                                                      sq_eeanti, B, N, n_up);
+  return (int)cudaGetLastError();
+}
+
+// ---- helpers of the KFAC factor pass (dh_kfac_factors)
+__global__ void fill_unit_cot_kernel(float* __restrict__ cot, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { cot[2 * i] = 1.f; cot[2 * i + 1] = 0.f; }
+}
+int fill_unit_cot(float* cot, int64_t n, cudaStream_t s) {
+  fill_unit_cot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cot, n);
+  return (int)cudaGetLastError();
+}
+// dst = src on the rows whose electron belongs to spin block sb (0: i < n_up, 1: i >= n_up), zero elsewhere
+__global__ void mask_rows_by_spin_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n, int D, int N, int n_up,
+                                         int sb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int el = (int)((i / D) % N);
+  dst[i] = ((el >= n_up) == (sb == 1)) ? src[i] : 0.f;
+}
+int mask_rows_by_spin(const float* src, float* dst, int64_t rows, int D, int N, int n_up, int sb, cudaStream_t s) {
+  const int64_t n = rows * D;
+  mask_rows_by_spin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n, D, N, n_up, sb);
+  return (int)cudaGetLastError();
+}
+// Diagonal Fisher of a LayerNorm's scale and bias: y = xhat * scale + bias with xhat = LN(a + (TANH ? tanh b : b)), so the
+// per-walker gradients are sum_i xhat_i gy_i and sum_i gy_i over the walker's electrons; their squares are summed
+// over walkers.  One block per walker, thread = column (D <= 1024, D % 32 == 0).
+__global__ void ln_fisher_diag_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ gy,
+                                      float* __restrict__ sq_scale, float* __restrict__ sq_bias, int N, int D, int tanh_mode) {
+  __shared__ float red[2][32];
+  const int64_t w = blockIdx.x;
+  const int d = threadIdx.x, lane = d & 31, wid = d >> 5, nw = blockDim.x >> 5;
+  float ss = 0.f, sb = 0.f;
+  for (int i = 0; i < N; ++i) {
+    const int64_t idx = (w * N + i) * D + d;
+    float bv = b[idx];
+    if (tanh_mode) bv = tanhf(bv);
+    const float u = a[idx] + bv;
+    float s1 = warp_sum(u), s2 = warp_sum(u * u);
+    __syncthreads();
+    if (lane == 0) { red[0][wid] = s1; red[1][wid] = s2; }
+    __syncthreads();
+    float t1 = 0.f, t2 = 0.f;
+    for (int k = 0; k < nw; ++k) { t1 += red[0][k]; t2 += red[1][k]; }
+    const float mu = t1 / (float)D;
+    const float var = fmaxf(t2 / (float)D - mu * mu, 0.f);
+    const float xhat = (u - mu) * rsqrtf(var + 1e-5f);
+    const float g = gy[idx];
+    ss = fmaf(xhat, g, ss);
+    sb += g;
+  }
+  atomicAdd(sq_scale + d, ss * ss);
+  atomicAdd(sq_bias + d, sb * sb);
+}
+int ln_fisher_diag(const float* a, const float* b, const float* gy, float* sq_scale, float* sq_bias, int64_t B, int N, int D,
+                   int tanh_mode, cudaStream_t s) {
+  if (D % 32 != 0 || D > 1024) return -2;
+  ln_fisher_diag_kernel<<<(unsigned)B, D, 0, s>>>(a, b, gy, sq_scale, sq_bias, N, D, tanh_mode);
   return (int)cudaGetLastError();
 }
 

@@ -2,8 +2,8 @@
 
 `make_optimizer_step(cfg, network) -> (init, step)`; `step(state, key) -> (state, stats)`.
 adam (optimizers/adam.py:24-43, optax.adam defaults b1=0.9, b2=0.999, eps=1e-8, no weight
-decay) and none (optimizers/none.py:22-35) are provided.  KFAC is the reference default but
-lives in kfac_jax and is a 'next' row.
+decay), none (optimizers/none.py:22-35) and kfac (optimizers/kfac.py:198-241, the reference default; kfac.py here,
+curvature statistics from dh_kfac_factors) are provided.
 
 Unlike the reference's Adam path, which applies the device-local gradient un-reduced
 (SURVEY 2.1), the gradient is all-reduced (mean) over ranks so replicas cannot drift.
@@ -76,5 +76,7 @@ def make_optimizer_step(cfg: Config, network):
 
         return make_inference_step(make_loss_fn(network, cfg.system, LossMode.ENERGY_DIFF))
     if name == "kfac":
-        raise NotImplementedError("KFAC is a 'next' row (SURVEY 8f N1); use optim.optimizer=adam or none")
+        from .kfac import make_kfac_training_step
+
+        return make_kfac_training_step(cfg.optim.kfac, make_loss_fn(network, cfg.system), network, cfg.system)
     raise ValueError(f"Optimizer {cfg.optim.optimizer} is not implemented!")

@@ -14,6 +14,7 @@
  *   dh_mcmc_propose    <- sph_sampling                      mcmc.py:67-102
  *   dh_mcmc_accept     <- mh_update (accept/select part)    mcmc.py:56-62
  *   dh_logpsi_vjp      <- df_real/df_imag + loss_prod       loss.py:53-64,96-106
+ *   dh_kfac_factors    <- kfac_jax curvature estimation     optimizers/kfac.py:42-102, loss.py:98
  *   dh_slogdet         <- jnp.linalg.slogdet + tail         psiformer.py:74-76
  *   dh_param_layout    <- the flax parameter tree           psiformer.py, blocks.py
  *   dh_init_walkers    <- init_guess                        train.py:40-54
@@ -73,7 +74,26 @@ typedef struct dh_param_entry {
   int32_t shape[4];
 } dh_param_entry;
 
-enum dh_op { DH_OP_LOGPSI = 0, DH_OP_LOCAL_ENERGY = 1, DH_OP_MCMC = 2, DH_OP_VJP = 3 };
+enum dh_op { DH_OP_LOGPSI = 0, DH_OP_LOCAL_ENERGY = 1, DH_OP_MCMC = 2, DH_OP_VJP = 3, DH_OP_KFAC = 4 };
+
+/* One curvature block of the KFAC optimizer (optimizers/kfac.py:33-241; the reference's default optimizer).
+ * kind 0: a dense layer seen as a `repeated_dense` block (kfac.py:42-102: the electron axis is extra batch) with
+ *         Kronecker factors A = mean_rows[x~ x~^T] (x~ = layer input, plus a 1 when the layer has a bias) and
+ *         G = mean_rows[g g^T] (g = d Re log psi_b / d layer output).  dh_kfac_factors delivers the SUMS over rows
+ *         sum x x^T [in][in] at xtx_offset, sum x [in] at xsum_offset (has_bias only) and sum g g^T [out][out] at
+ *         gtg_offset; rows = B * rows_per_walker.  xtx_offset = -1: the caller forms it itself (Dense_0, whose
+ *         inputs are the four features of psiformer.py:51-60).  Layers that share their input share xtx / xsum.
+ * kind 1: LayerNorm scale / bias (kfac_jax's scale-and-shift blocks): diagonal Fisher from per-walker gradients,
+ *         sum_b (d Re log psi_b / d theta)^2 at diag_offset, `size` entries.
+ * kind 2: a parameter no layer pattern matches (Jastrow ee_par / ee_anti; kfac_jax's generic tag with its "naive"
+ *         diagonal = square of the batch-summed gradient): sum_b d Re log psi_b / d theta at diag_offset. */
+typedef struct dh_kfac_entry {
+  char name[96];             /* parameter path of the kernel (kind 0) or of the parameter (kind 1)      */
+  int32_t kind, in_dim, out_dim, has_bias, rows_per_walker;
+  int64_t kernel_offset, bias_offset;         /* into the flat parameter vector; bias_offset = -1: none */
+  int64_t xtx_offset, xsum_offset, gtg_offset, diag_offset; /* into the factor vector; -1: not present  */
+  int64_t size;              /* kind 1: number of parameters                                            */
+} dh_kfac_entry;
 
 int dh_plan_create(const dh_config* cfg, dh_plan** out);
 int dh_plan_destroy(dh_plan* plan);
@@ -142,6 +162,15 @@ int dh_init_walkers(dh_plan* plan, float* x, int64_t B, uint64_t seed, uint64_t 
 int dh_logpsi_vjp(dh_plan* plan, const float* params, const float* x, int64_t B,
                   const float* cot, float* grad_flat, float* out_logpsi, void* ws,
                   size_t ws_bytes, void* stream);
+
+/* Curvature statistics for KFAC with the reference's registration (loss.py:98: a unit-variance normal predictive
+ * distribution on Re log psi, `fisher_exact`): one forward + one reverse pass with cotangent (1, 0) per walker.
+ * dh_kfac_layout: entries == NULL -> *n = number of blocks; *factor_floats = length of the factor vector.
+ * dh_kfac_factors overwrites `factors` (factor_floats floats) with the sums described at dh_kfac_entry.
+ * Workspace: DH_OP_KFAC.  Not available for the Laughlin network (no parameters) and sparse orbitals. */
+int dh_kfac_layout(const dh_plan* plan, dh_kfac_entry* entries, int32_t* n, int64_t* factor_floats);
+int dh_kfac_factors(dh_plan* plan, const float* params, const float* x, int64_t B, float* factors, void* ws,
+                    size_t ws_bytes, void* stream);
 
 /* Batched complex slogdet with the reference's multi-determinant tail (psiformer.py:74-76).
  *   mats: (B, K, n, n) complex64, row-major.

@@ -543,6 +543,106 @@ def test_facade_spin_unpolarised_sparse_orbitals(nat):
     assert (dd.cpu().to(torch.complex128) - o_diff).abs().max() < 1e-4
 
 
+# --------------------------------------------------------------------------------- KFAC
+KFAC_CASES = {
+    "pol": dict(nspins=(3, 0), flux=2, ndets=2, num_heads=2, heads_dim=16, num_layers=1),
+    "spin": dict(nspins=(2, 1), flux=4, num_heads=2, heads_dim=16, num_layers=2),
+}
+
+
+def _kfac_blocks_from_gpu(plan, flat, x):
+    """dh_kfac_factors -> {kernel name: (A, G)}, {parameter name: diagonal}, normalised like oracle/kfac.py."""
+    from deephall_b200 import kfac as K
+
+    layout, _ = plan.kfac_layout()
+    raw = plan.kfac_factors(flat, x).double().cpu()
+    B = x.shape[0]
+    t2 = 1.0 / K.VARIANCE
+    dense, diag = {}, {}
+    for e in layout:
+        if e["kind"] == 0:
+            din, dout, rows = e["in_dim"], e["out_dim"], B * e["rows_per_walker"]
+            if e["xtx_offset"] < 0:
+                feat = K._features(x, plan.cfg.n_up).reshape(-1, 4).double().cpu()
+                xtx = feat.T @ feat / rows
+            else:
+                xtx = raw[e["xtx_offset"] : e["xtx_offset"] + din * din].view(din, din) / rows
+            if e["has_bias"]:
+                xs = raw[e["xsum_offset"] : e["xsum_offset"] + din] / rows
+                A = torch.zeros(din + 1, din + 1, dtype=torch.float64)
+                A[:din, :din], A[:din, din], A[din, :din], A[din, din] = xtx, xs, xs, 1.0
+            else:
+                A = xtx
+            G = raw[e["gtg_offset"] : e["gtg_offset"] + dout * dout].view(dout, dout) * t2 / rows
+            dense[e["name"]] = (A, G)
+        else:
+            v = raw[e["diag_offset"] : e["diag_offset"] + e["size"]]
+            diag[e["name"]] = (v if e["kind"] == 1 else v * v) * t2 / B
+    return dense, diag
+
+
+@pytest.mark.parametrize("name", list(KFAC_CASES))
+def test_kfac_curvature_statistics_parity(nat, name):
+    """Kronecker-factor sums and diagonal blocks of dh_kfac_factors against per-sample autograd of the oracle
+    (repeated-dense blocks over the electron axis, optimizers/kfac.py:42-102; loss tag loss.py:98)."""
+    from oracle import kfac as OK
+
+    B = 48
+    cfg, p64, plan, flat, x = setup_case(nat, KFAC_CASES[name], B)
+    dense, diag = _kfac_blocks_from_gpu(plan, flat, x)
+    rdense, rdiag = OK.curvature_stats(OP.flatten_params(p64), x.double().cpu(), cfg)
+    assert list(dense) == list(rdense) and set(diag) == set(rdiag)
+    for k in rdense:
+        for a, b, what in ((dense[k][0], rdense[k][0], "A"), (dense[k][1], rdense[k][1], "G")):
+            assert a.shape == b.shape, (k, what)
+            assert (a - b).norm() / b.norm().clamp(min=1e-30) < 2e-4, (k, what, ((a - b).norm() / b.norm()).item())
+    for k in rdiag:
+        assert (diag[k] - rdiag[k]).norm() / rdiag[k].norm().clamp(min=1e-30) < 2e-4, k
+
+
+def test_kfac_training_step_matches_the_restated_update(nat):
+    """Two `make_optimizer_step(cfg, apply)` steps with optimizer=kfac (the reference default, config.py:159) against
+    oracle/kfac.py's fp64 restatement of kfac_jax's update, fed the same gradients; and the energy of a short run
+    goes down (train_test.py:39-48 trains N=3, 2Q=2, kappa=0 towards 1.5 with KFAC)."""
+    from deephall_b200 import loss, mcmc, networks, optimizers
+    from deephall_b200.config import Config, Network, Optim, PsiformerNetwork, System
+    from oracle import kfac as OK
+
+    system = System(flux=2, nspins=(3, 0), interaction_strength=0.0)
+    net = Network(psiformer=PsiformerNetwork(num_heads=2, heads_dim=16, num_layers=1, determinants=1))
+    cfgt = Config(batch_size=256, seed=3, system=system, network=net, optim=Optim(iterations=4, optimizer="kfac"))
+    model = networks.make_network(system, net)
+    params = model.init(1)
+    B = 256
+    data = mcmc.init_guess(0, B, 3, model)
+    data, _ = mcmc.make_mcmc_step(model.apply, B, steps=20)(params, data, mcmc.PhiloxKey(2), 0.3)
+    init, step = optimizers.make_optimizer_step(cfgt, model.apply)
+    state = optimizers.CheckpointState(params, data, init(params, None, data), 0.1)
+    cfg = OP.NetCfg(nspins=(3, 0), flux=2, num_heads=2, heads_dim=16, num_layers=1)
+    ok = OK.Kfac(cfg, cfgt.optim.kfac.lr.schedule)
+    loss_fn = loss.make_loss_fn(model.apply, system)
+    p_ref = params.double().cpu()
+    for it in range(2):
+        _, g = loss_fn(state.params, state.data)  # the gradient the step is about to use
+        p_ref_next = ok.step(state.params.double().cpu(), g.double().cpu(), state.data.double().cpu())
+        prev = state.params
+        state, stats = step(state, None)
+        upd, upd_ref = (state.params - prev).double().cpu(), p_ref_next - prev.double().cpu()
+        assert torch.isfinite(upd).all() and upd.norm() > 0
+        assert (upd - upd_ref).norm() / upd_ref.norm() < 5e-3, (it, ((upd - upd_ref).norm() / upd_ref.norm()).item())
+    # a short training run with sampling between the updates: the energy falls towards the LLL floor N/2 = 1.5
+    from deephall_b200.train import VMC
+
+    vmc = VMC(Config(batch_size=512, seed=1, system=system, network=net, optim=Optim(iterations=30, optimizer="kfac")))
+    vmc.burn_in(5)
+    energies = []
+    for _ in range(30):
+        _, st = vmc.step()
+        energies.append(float(st["energy"].real))
+    assert all(math.isfinite(e) for e in energies)
+    assert sum(energies[-5:]) / 5 < sum(energies[:5]) / 5 and abs(sum(energies[-5:]) / 5 - 1.5) < 0.15, energies
+
+
 # --------------------------------------------------------------------------------- Laughlin (analytic, pinned)
 LAUGHLIN_CASES = [(3, 6), (4, 9), (5, 12), (6, 15)]  # (N, flux = 3 (N - 1)): the 1/3 Laughlin state
 
