@@ -241,6 +241,14 @@ def run_ours(args):
     k2 = max(1, min(args.steps, 3))
     ms_mcmc = timed(lambda: vmc.mcmc_step(params, data, mcmc.PhiloxKey(7), W["mcmc_width"]), k2, 1) / k2
     ms_vmc = timed(lambda: vmc.step(sync_stats=False), k2, 1) / k2
+    # the same iteration with the reference's default optimizer (config.py:159): KFAC, whose curvature statistics
+    # cost one more forward + reverse pass (dh_kfac_factors) and ~20 small matrix inverses per step
+    import dataclasses
+
+    vmc_k = VMC(dataclasses.replace(cfg, optim=Optim(optimizer="kfac")))
+    vmc_k.state = vmc_k.state._replace(data=data.clone())
+    ms_vmc_kfac = timed(lambda: vmc_k.step(sync_stats=False), k2, 1) / k2
+    del vmc_k
 
     # ---- roofline of the dominant kernel (dense contractions), CUDA-event timed per launch
     barrier()
@@ -288,6 +296,9 @@ def run_ours(args):
                 "mcmc_step_ms": ms_mcmc,
                 "vmc_steps_per_sec": 1.0 / (ms_vmc * 1e-3),
                 "vmc_step_ms": ms_vmc,
+                "vmc_optimizer": "adam (SURVEY 8d M3)",
+                "vmc_kfac_steps_per_sec": 1.0 / (ms_vmc_kfac * 1e-3),
+                "vmc_kfac_step_ms": ms_vmc_kfac,
                 "mean_energy": float(torch.nanmean(el.real)),
                 "algorithmic_flops_per_walker": flops_local_energy_per_walker(N, W["flux"] + 1, W["determinants"]),
             },

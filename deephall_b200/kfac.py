@@ -39,20 +39,6 @@ def _features(data: torch.Tensor, n_up: int) -> torch.Tensor:
     return torch.stack([torch.cos(theta), torch.sin(theta) * torch.cos(phi), torch.sin(theta) * torch.sin(phi), spin], dim=-1)
 
 
-def _pi_adjusted_inverses(A: torch.Tensor, G: torch.Tensor, damping: float):
-    """(A (x) G + damping I)^-1 ~ A_inv (x) G_inv with average-trace norms (kfac_jax.utils.pi_adjusted_kronecker_inverse)."""
-    ca, cg = torch.trace(A) / A.shape[0], torch.trace(G) / G.shape[0]
-    c = ca * cg
-    eye_a = torch.eye(A.shape[0], dtype=A.dtype, device=A.device)
-    eye_g = torch.eye(G.shape[0], dtype=G.dtype, device=G.device)
-    if not bool(c > 0):  # a factor that is still zero: plain damping
-        sd = math.sqrt(damping)
-        return eye_a / sd, eye_g / sd
-    d_hat = torch.sqrt(damping / c)
-    ck = torch.sqrt(c)
-    return torch.linalg.inv(A / ca + d_hat * eye_a) / ck, torch.linalg.inv(G / cg + d_hat * eye_g) / ck
-
-
 def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_constraint=1e-3, curvature_ema=0.95,
                             damping=1e-3):
     """-> (init, step) like optimizers/kfac.py:198-241.  `network` is `model.apply` of a deephall_b200 Psiformer."""
@@ -93,6 +79,9 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
         w = state.weight
         st = state.stats / w
         out = torch.zeros_like(grads)
+        # pass 1: the damped, trace-normalised factors of every dense block, grouped by size so that each size is
+        # inverted in ONE batched call (about 30 matrices of 256-410 rows per step)
+        blocks, groups = [], {}
         for e in layout:
             ko = e["kernel_offset"]
             if e["kind"] != 0:
@@ -114,12 +103,34 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
             else:
                 A = xtx
             G = st[e["gtg_offset"] : e["gtg_offset"] + dout * dout].view(dout, dout)
+            # (A (x) G + d I)^-1 ~ A_inv (x) G_inv, average-trace norms (kfac_jax.utils.pi_adjusted_kronecker_inverse);
+            # the block is npw * A (x) G (fixed_scale, kfac.py:79-81), so d = damping / npw
+            ca, cg = torch.trace(A) / A.shape[0], torch.trace(G) / G.shape[0]
+            c = ca * cg
+            ok = c > 0  # a factor that is still zero: plain damping
+            d_hat = torch.where(ok, torch.sqrt((damping / npw) / torch.where(ok, c, torch.ones_like(c))), torch.ones_like(c))
+            ck = torch.where(ok, torch.sqrt(torch.where(ok, c, torch.ones_like(c))), torch.full_like(c, math.sqrt(damping / npw)))
+            ma = torch.where(ok, A / torch.where(ok, ca, torch.ones_like(ca)), torch.zeros_like(A))
+            mg = torch.where(ok, G / torch.where(ok, cg, torch.ones_like(cg)), torch.zeros_like(G))
+            ma = ma + d_hat * torch.eye(A.shape[0], dtype=A.dtype, device=A.device)
+            mg = mg + d_hat * torch.eye(G.shape[0], dtype=G.dtype, device=G.device)
+            ia = groups.setdefault(A.shape[0], [])
+            ia.append(ma)
+            ja = len(ia) - 1
+            ig = groups.setdefault(G.shape[0], [])  # (the same list when both factors have the same size)
+            ig.append(mg)
+            blocks.append((e, (A.shape[0], ja), (G.shape[0], len(ig) - 1), ck))
+        # (torch.linalg.inv: on this torch build the batched LU path is the fastest of inv / cholesky_inverse for these
+        # sizes, scripts/gpu_kfac_timing.py)
+        inv = {n: torch.linalg.inv(torch.stack(ms)) for n, ms in groups.items()}
+        # pass 2: U = A_inv V G_inv / (c_k^2 npw)
+        for e, (na, ja), (ng, jg), ck in blocks:
+            din, dout, hb, npw, ko = e["in_dim"], e["out_dim"], e["has_bias"], e["rows_per_walker"], e["kernel_offset"]
             V = grads[ko : ko + din * dout].view(din, dout)
             if hb:
                 bo = e["bias_offset"]
                 V = torch.cat([V, grads[bo : bo + dout].view(1, dout)], dim=0)
-            ai, gi = _pi_adjusted_inverses(A, G, damping / npw)  # block = npw * A (x) G  (fixed_scale, kfac.py:79-81)
-            U = ai @ V @ gi / npw
+            U = inv[na][ja] @ V @ inv[ng][jg] / (ck * ck * npw)
             if hb:
                 out[bo : bo + dout] = U[din]
                 U = U[:din]
