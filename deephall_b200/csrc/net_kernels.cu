@@ -4,6 +4,9 @@
 //
 // Reference semantics: networks/psiformer.py:37-60 and flax 0.10.2 MultiHeadAttention /
 // LayerNorm(epsilon=1e-5).
+#include <stdlib.h>
+#include <string.h>
+
 #include "kernels.h"
 
 namespace dh {
@@ -543,8 +546,164 @@ attention_value_kernel(const float* __restrict__ qkv, float* __restrict__ o, Net
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-autonomous form (N <= 4 T, hd % 8 == 0, hd <= 64): ONE WARP per (walker, head), no block-level
+// synchronisation -- every warp stages its own 3 x N x hd floats with cp.async and runs on while its neighbours
+// are still loading, so a resident set of 16-24 warps per SM keeps ~200 KB of loads in flight.
+//   scores   lane = (d-half, T x T tile of (query, key)): T*T dot products over half of the head dimension from
+//            2T float4 streams, the two halves combined with one shuffle per product
+//   softmax  in registers, row maxima / sums over the four lanes that share a query tile
+//   output   lane = (query half, 4 head-dim columns): probabilities broadcast from shared memory
+// ---------------------------------------------------------------------------------------------
+constexpr int AVW_WARPS = 8;       // warps per block
+constexpr int AVW_LD = 64 + 4;     // row stride of the staged q / k / v rows (floats): conflict-free float4 tile reads
+
+// NT / HD > 0: electron count / head dimension as compile-time constants (the kernel is instruction-issue bound:
+// index arithmetic folds and every loop unrolls); 0: taken from dm at run time.
+template <int T, int NT, int HD>
+__global__ void __launch_bounds__(AVW_WARPS * 32)
+attention_value_warp_kernel(const float* __restrict__ qkv, float* __restrict__ o, int64_t n_items, NetDims dm) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NP = 4 * T;  // padded electron count
+  const int N = NT > 0 ? NT : dm.N, D = dm.D, H = dm.H, hd = HD > 0 ? HD : dm.hd;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t item = (int64_t)blockIdx.x * AVW_WARPS + warp;
+  if (item >= n_items) return;  // whole warps leave; only __syncwarp below
+  const int64_t b = item / H;
+  const int hh = (int)(item % H);
+  float* qs = sm + (size_t)warp * (3 * NP * AVW_LD + NP * NP);
+  float* ks = qs + NP * AVW_LD;
+  float* vs = ks + NP * AVW_LD;
+  float* ps = vs + NP * AVW_LD;  // [NP][NP] probabilities
+  const int hd4 = hd >> 2;
+  // ---- stage q, k, v of this head (rows beyond N: zeros, so that padded tiles read finite numbers)
+  {
+    const float* src = qkv + b * N * 3 * (int64_t)D + hh * hd;
+    const int per = NP * hd4;
+#pragma unroll
+    for (int t = lane; t < 3 * per; t += 32) {
+      const int part = t / per, r = (t % per) / hd4, c = t % hd4;
+      float* dst = qs + (part * NP + r) * AVW_LD + 4 * c;
+      if (r < N) {
+        const unsigned da = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + (int64_t)r * 3 * D + part * D + 4 * c) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  // ---- scores
+  const int half = lane >> 4, ti = (lane & 15) >> 2, tj = lane & 3;
+  float sc[T][T];
+#pragma unroll
+  for (int a = 0; a < T; ++a)
+#pragma unroll
+    for (int c = 0; c < T; ++c) sc[a][c] = 0.f;
+  {
+    const int dh4 = hd4 >> 1;  // float4 steps per half
+    const float* qb = qs + (T * ti) * AVW_LD + half * (hd >> 1);
+    const float* kb = ks + (T * tj) * AVW_LD + half * (hd >> 1);
+#pragma unroll
+    for (int d = 0; d < dh4; ++d) {
+      float4 qv[T], kv[T];
+#pragma unroll
+      for (int a = 0; a < T; ++a) {
+        qv[a] = *reinterpret_cast<const float4*>(qb + a * AVW_LD + 4 * d);
+        kv[a] = *reinterpret_cast<const float4*>(kb + a * AVW_LD + 4 * d);
+      }
+#pragma unroll
+      for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int c = 0; c < T; ++c) {
+          sc[a][c] = fmaf(qv[a].x, kv[c].x, sc[a][c]); sc[a][c] = fmaf(qv[a].y, kv[c].y, sc[a][c]);
+          sc[a][c] = fmaf(qv[a].z, kv[c].z, sc[a][c]); sc[a][c] = fmaf(qv[a].w, kv[c].w, sc[a][c]);
+        }
+    }
+  }
+  const float scl = rsqrtf((float)hd);
+  // ---- softmax over the keys of every query row: the row is spread over the tj = 0..3 lanes of this (half, ti)
+#pragma unroll
+  for (int a = 0; a < T; ++a) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < T; ++c) {
+      sc[a][c] = (sc[a][c] + __shfl_xor_sync(0xffffffffu, sc[a][c], 16)) * scl;  // the two d-halves
+      if (T * tj + c >= N) sc[a][c] = -INFINITY;                                 // padded keys
+      mx = fmaxf(mx, sc[a][c]);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    float Z = 0.f;
+#pragma unroll
+    for (int c = 0; c < T; ++c) { sc[a][c] = __expf(sc[a][c] - mx); Z += sc[a][c]; }
+    Z += __shfl_xor_sync(0xffffffffu, Z, 1);
+    Z += __shfl_xor_sync(0xffffffffu, Z, 2);
+    const float iz = 1.f / Z;
+    if (half == 0) {
+#pragma unroll
+      for (int c = 0; c < T; ++c) ps[(T * ti + a) * NP + T * tj + c] = sc[a][c] * iz;
+    }
+  }
+  __syncwarp();
+  // ---- output: lane = (query half qh, float4 column d4); queries qh * NP/2 .. + NP/2 - 1
+  {
+    constexpr int QH = NP / 2;
+    const int qh = lane >> 4, d4 = lane & 15;
+    if (d4 < hd4) {
+      float4 acc[QH];
+#pragma unroll
+      for (int a = 0; a < QH; ++a) acc[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float4 v = *reinterpret_cast<const float4*>(vs + j * AVW_LD + 4 * d4);
+#pragma unroll
+        for (int a = 0; a < QH; ++a) {
+          const float pw = ps[(qh * QH + a) * NP + j];
+          acc[a].x = fmaf(pw, v.x, acc[a].x); acc[a].y = fmaf(pw, v.y, acc[a].y);
+          acc[a].z = fmaf(pw, v.z, acc[a].z); acc[a].w = fmaf(pw, v.w, acc[a].w);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < QH; ++a) {
+        const int i = qh * QH + a;
+        if (i < N) *reinterpret_cast<float4*>(o + (b * N + i) * (int64_t)D + hh * hd + 4 * d4) = acc[a];
+      }
+    }
+  }
+}
+
+template <int T, int NT, int HD>
+static int attention_value_warp(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
+  constexpr int NP = 4 * T;
+  const size_t smem = (size_t)AVW_WARPS * (3 * NP * AVW_LD + NP * NP) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_value_warp_kernel<T, NT, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  const int64_t items = B * d.H;
+  attention_value_warp_kernel<T, NT, HD><<<(unsigned)((items + AVW_WARPS - 1) / AVW_WARPS), AVW_WARPS * 32, smem, s>>>(qkv, o, items, d);
+  return (int)cudaGetLastError();
+}
+
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
   if (d.N > ATT_NMAX || (d.hd % 4) != 0) return -2;
+  static const bool block_form = getenv("DH_ATTN_VALUE") && strcmp(getenv("DH_ATTN_VALUE"), "block") == 0;
+  if (!block_form && d.hd % 8 == 0 && d.hd <= 64 && (d.D % 4) == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+    if (d.hd == 64) {  // the BASELINE configurations: everything a compile-time constant
+      if (d.N == 6) return attention_value_warp<2, 6, 64>(qkv, o, B, d, s);
+      if (d.N == 10) return attention_value_warp<3, 10, 64>(qkv, o, B, d, s);
+      if (d.N == 12) return attention_value_warp<3, 12, 64>(qkv, o, B, d, s);
+      if (d.N == 16) return attention_value_warp<4, 16, 64>(qkv, o, B, d, s);
+    }
+    if (d.N <= 8) return attention_value_warp<2, 0, 0>(qkv, o, B, d, s);
+    if (d.N <= 12) return attention_value_warp<3, 0, 0>(qkv, o, B, d, s);
+    if (d.N <= 16) return attention_value_warp<4, 0, 0>(qkv, o, B, d, s);
+  }
   const size_t smem = ((size_t)d.N * (3 * d.D + 4) + (size_t)d.H * d.N * d.N) * sizeof(float);
   static size_t attr_smem = 48 * 1024;
   if (smem > attr_smem) {
