@@ -74,39 +74,58 @@ int features_dense0(const float* x, const float* W0, float* h, int64_t B, NetDim
   return features_linear(x, W0, nullptr, h, d.D, B, d, 0, s);
 }
 
-// value-only form (R = 1): one warp per (walker, electron), eight per block
+// value-only form (R = 1): one warp per FV_ROWS consecutive (walker, electron) rows, eight warps per block.  Lane r
+// evaluates the features of row r, the warp shares them by shuffles, and every 16-byte group of weight columns is
+// loaded once for all FV_ROWS rows (one warp per row re-read the weights from L1 for each row: L1 was 84 % busy).
+constexpr int FV_ROWS = 8;
+
 __global__ void __launch_bounds__(256)
 features_value_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                       float* __restrict__ out, int Nout, int64_t rows, NetDims dm) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  float st, ct, sp, cp;
-  sincosf(x[row * 2], &st, &ct);
-  sincosf(x[row * 2 + 1], &sp, &cp);
-  const float f0 = ct, f1 = st * cp, f2 = st * sp, f3 = ((int)(row % dm.N) < dm.n_up) ? 1.f : -1.f;  // (z, x, y, spin)
-  float* o = out + row * Nout;
+  const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * FV_ROWS;
+  if (row0 >= rows) return;
+  float fl[4] = {0.f, 0.f, 0.f, 0.f};
+  if (lane < FV_ROWS && row0 + lane < rows) {
+    const int64_t row = row0 + lane;
+    float st, ct, sp, cp;
+    sincosf(x[row * 2], &st, &ct);
+    sincosf(x[row * 2 + 1], &sp, &cp);
+    fl[0] = ct; fl[1] = st * cp; fl[2] = st * sp; fl[3] = ((int)(row % dm.N) < dm.n_up) ? 1.f : -1.f;  // (z, x, y, spin)
+  }
+  float f[FV_ROWS][4];
+#pragma unroll
+  for (int r = 0; r < FV_ROWS; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[r][k] = __shfl_sync(0xffffffffu, fl[k], r);
+  const int nrow = rows - row0 < FV_ROWS ? (int)(rows - row0) : FV_ROWS;
+  float* o = out + row0 * Nout;
   if ((Nout & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0) {
     for (int d = 4 * lane; d < Nout; d += 128) {  // 16-byte accesses
       const float4 w0 = *reinterpret_cast<const float4*>(W + d), w1 = *reinterpret_cast<const float4*>(W + Nout + d);
       const float4 w2 = *reinterpret_cast<const float4*>(W + 2 * Nout + d), w3 = *reinterpret_cast<const float4*>(W + 3 * Nout + d);
-      float4 v;
-      v.x = fmaf(f0, w0.x, fmaf(f1, w1.x, fmaf(f2, w2.x, f3 * w3.x)));
-      v.y = fmaf(f0, w0.y, fmaf(f1, w1.y, fmaf(f2, w2.y, f3 * w3.y)));
-      v.z = fmaf(f0, w0.z, fmaf(f1, w1.z, fmaf(f2, w2.z, f3 * w3.z)));
-      v.w = fmaf(f0, w0.w, fmaf(f1, w1.w, fmaf(f2, w2.w, f3 * w3.w)));
-      if (bias != nullptr) {
-        const float4 bb = *reinterpret_cast<const float4*>(bias + d);
-        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+      const float4 bb = bias != nullptr ? *reinterpret_cast<const float4*>(bias + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < FV_ROWS; ++r) {
+        if (r >= nrow) break;
+        float4 v;
+        v.x = fmaf(f[r][0], w0.x, fmaf(f[r][1], w1.x, fmaf(f[r][2], w2.x, f[r][3] * w3.x))) + bb.x;
+        v.y = fmaf(f[r][0], w0.y, fmaf(f[r][1], w1.y, fmaf(f[r][2], w2.y, f[r][3] * w3.y))) + bb.y;
+        v.z = fmaf(f[r][0], w0.z, fmaf(f[r][1], w1.z, fmaf(f[r][2], w2.z, f[r][3] * w3.z))) + bb.z;
+        v.w = fmaf(f[r][0], w0.w, fmaf(f[r][1], w1.w, fmaf(f[r][2], w2.w, f[r][3] * w3.w))) + bb.w;
+        *reinterpret_cast<float4*>(o + (int64_t)r * Nout + d) = v;
       }
-      *reinterpret_cast<float4*>(o + d) = v;
     }
     return;
   }
   for (int d = lane; d < Nout; d += 32) {
-    float v = fmaf(f0, W[d], fmaf(f1, W[Nout + d], fmaf(f2, W[2 * Nout + d], f3 * W[3 * Nout + d])));
-    if (bias != nullptr) v += bias[d];
-    o[d] = v;
+    const float w0 = W[d], w1 = W[Nout + d], w2 = W[2 * Nout + d], w3 = W[3 * Nout + d];
+    const float bb = bias != nullptr ? bias[d] : 0.f;
+#pragma unroll
+    for (int r = 0; r < FV_ROWS; ++r) {
+      if (r >= nrow) break;
+      o[(int64_t)r * Nout + d] = fmaf(f[r][0], w0, fmaf(f[r][1], w1, fmaf(f[r][2], w2, f[r][3] * w3))) + bb;
+    }
   }
 }
 
@@ -114,7 +133,7 @@ int features_linear(const float* x, const float* W, const float* bias, float* ou
                     int compressed, cudaStream_t s) {
   if (d.R == 1) {
     const int64_t rows = B * d.N;
-    features_value_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(x, W, bias, out, Nout, rows, d);
+    features_value_kernel<<<(unsigned)((rows + 8 * FV_ROWS - 1) / (8 * FV_ROWS)), 256, 0, s>>>(x, W, bias, out, Nout, rows, d);
     return (int)cudaGetLastError();
   }
   int threads = Nout >= 256 ? 256 : ((Nout + 31) / 32 * 32);
