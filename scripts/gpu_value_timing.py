@@ -31,3 +31,10 @@ plan.profile_begin()
 plan.logpsi(flat, x)
 prof = plan.profile_end()
 print({k: (round(v["ms"], 3), v["count"]) for k, v in prof.items() if v["count"]})
+cot = torch.randn(8192, 2, device="cuda") / 8192
+print(f"logpsi_vjp    {t(lambda: plan.logpsi_vjp(flat, x, cot), 5):7.3f} ms")
+plan.profile_begin()
+plan.logpsi_vjp(flat, x, cot)
+prof = plan.profile_end()
+print({k: (round(v["ms"], 3), v["count"], round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1)) for k, v in prof.items() if v["count"]})
+print(f"kfac_factors  {t(lambda: plan.kfac_factors(flat, x), 5):7.3f} ms")
