@@ -1,5 +1,8 @@
 // dh_logpsi_vjp: one reverse pass through the value-only network for a batch of walkers,
 // contracting d(Re, Im log psi_b)/d params with per-walker cotangents (loss.py:53-64,96-106).
+#include <stdlib.h>
+#include <string.h>
+
 #include <vector>
 
 #include "plan.h"
@@ -73,9 +76,19 @@ int dense_bwd_x_tc(const dh_plan* p, const float* G, int64_t ldg, int vs, int K,
 }
 
 // dW[Din, Nout] += X[rows, Din]^T @ G[rows, Nout] (ldg)
+// The "TN" contractions of the reverse pass (rows = the contracted index) run on the tensor cores when the operands
+// allow it (16-byte alignment, fp16 pieces); DH_VJP_DW=simt forces the fp32-FMA split-K kernel.
+bool tn_tc_ok(const dh_plan* p, const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc, int Ma) {
+  static const bool simt = getenv("DH_VJP_DW") && strcmp(getenv("DH_VJP_DW"), "simt") == 0;
+  return !simt && p->gemm_impl == 1 && p->tc_f16 && Ma >= 32 && gemm_tn_tc_ok(A, lda, B, ldb, C, ldc);
+}
+
+// dW[Din, Nout] += X[rows, Din]^T @ G[rows, Nout] (ldg); G is cotangent-sized, scaled by the plan's cotangent scale
 int dense_bwd_w(const dh_plan* p, const float* X, int Din, const float* G, int64_t ldg, int Nout, float* dW,
                 int64_t rows, cudaStream_t s) {
   ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * Nout * Din, s);
+  if (tn_tc_ok(p, X, Din, G, ldg, dW, Nout, Din))
+    return gemm_tn_tc(X, Din, Din, G, ldg, Nout, dW, Nout, rows, nullptr, p->prep + p->cot_scale, s);
   const int tiles = ((Din + 127) / 128) * ((Nout + 127) / 128);
   int split = 296 / tiles;
   if (split < 1) split = 1;
@@ -84,9 +97,14 @@ int dense_bwd_w(const dh_plan* p, const float* X, int Din, const float* G, int64
   return gemm_simt(X, G, nullptr, dW, Din, Nout, rows, 1, Din, ldg, 1, Nout, 1, 1, split, s);
 }
 
-// out[dim][dim] += X^T X over `rows` rows of X (row stride ldx): a Kronecker factor sum of the KFAC curvature blocks
-int gram(const dh_plan* p, const float* X, int64_t ldx, int dim, float* out, int64_t rows, cudaStream_t s) {
+// out[dim][dim] += X^T X over `rows` rows of X (row stride ldx): a Kronecker factor sum of the KFAC curvature blocks.
+// cot_sized: X is a gradient (scaled like the cotangents before the fp16 split)
+int gram(const dh_plan* p, const float* X, int64_t ldx, int dim, float* out, int64_t rows, cudaStream_t s, bool cot_sized = false) {
   ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * dim * dim, s);
+  if (tn_tc_ok(p, X, ldx, X, ldx, out, dim, dim)) {
+    const float* sc = cot_sized ? p->prep + p->cot_scale : nullptr;
+    return gemm_tn_tc(X, ldx, dim, X, ldx, dim, out, dim, rows, sc, sc, s);
+  }
   const int tiles = ((dim + 127) / 128) * ((dim + 127) / 128);
   int split = 296 / tiles;
   if (split < 1) split = 1;
@@ -195,7 +213,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
         RUN(PC_OTHER, colsum_add(xin, kf + e.xsum_offset, rows, D, D, s));
         for (int part = 0; part < 2; ++part) {
           const int t = 2 * sbk + part;
-          if ((rc = gram(p, w.gCb + (size_t)t * LNK, ldg, LNK, kf + K(p->kf_orb[t]).gtg_offset, rows, s))) return rc;
+          if ((rc = gram(p, w.gCb + (size_t)t * LNK, ldg, LNK, kf + K(p->kf_orb[t]).gtg_offset, rows, s, true))) return rc;
         }
       }
     }
@@ -218,7 +236,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
       } else {
         if ((rc = gram(p, w.hA[l], D, D, kf + K(kl->d2).xtx_offset, rows, s))) return rc;
         RUN(PC_OTHER, colsum_add(w.hA[l], kf + K(kl->d2).xsum_offset, rows, D, D, s));
-        if ((rc = gram(p, w.gB, D, D, kf + K(kl->d2).gtg_offset, rows, s))) return rc;
+        if ((rc = gram(p, w.gB, D, D, kf + K(kl->d2).gtg_offset, rows, s, true))) return rc;
       }
       const bool tc = bwd_x_tc_ok(p, w.gB, D, w.gA) && bwd_x_tc_ok(p, w.gC, D, w.gH) && bwd_x_tc_ok(p, w.gQKV, 3 * D, w.gH);
       if (tc) { if ((rc = dense_bwd_x_tc(p, w.gB, D, l * VS_PER_LAYER + VS_D2, D, w.gA, rows, 1, s))) return rc; }
@@ -231,7 +249,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
         if ((rc = dense_bwd_w(p, w.t1[l], D, w.gB, D, D, grad + o.d1_k, rows, s))) return rc;
       } else {
         if ((rc = gram(p, w.t1[l], D, D, kf + K(kl->d1).xtx_offset, rows, s))) return rc;
-        if ((rc = gram(p, w.gB, D, D, kf + K(kl->d1).gtg_offset, rows, s))) return rc;
+        if ((rc = gram(p, w.gB, D, D, kf + K(kl->d1).gtg_offset, rows, s, true))) return rc;
       }
       if (tc) { if ((rc = dense_bwd_x_tc(p, w.gB, D, l * VS_PER_LAYER + VS_D1, D, w.gC, rows, 0, s))) return rc; }
       else if ((rc = dense_bwd_x(p, w.gB, D, P + o.d1_k, D, w.gC, rows, D, 0, s))) return rc;   // gC = d/d t1
@@ -241,7 +259,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
       } else {
         if ((rc = gram(p, w.att[l], D, D, kf + K(kl->o).xtx_offset, rows, s))) return rc;
         RUN(PC_OTHER, colsum_add(w.att[l], kf + K(kl->o).xsum_offset, rows, D, D, s));
-        if ((rc = gram(p, w.gC, D, D, kf + K(kl->o).gtg_offset, rows, s))) return rc;
+        if ((rc = gram(p, w.gC, D, D, kf + K(kl->o).gtg_offset, rows, s, true))) return rc;
       }
       if (tc) { if ((rc = dense_bwd_x_tc(p, w.gC, D, l * VS_PER_LAYER + VS_O, D, w.gB, rows, 0, s))) return rc; }
       else if ((rc = dense_bwd_x(p, w.gC, D, P + o.o_k, D, w.gB, rows, D, 0, s))) return rc;    // gB = d/d att
@@ -253,7 +271,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
         RUN(PC_OTHER, colsum_add(w.hs[l], kf + K(kl->q).xsum_offset, rows, D, D, s));
         const int kq[3] = {kl->q, kl->k, kl->v};
         for (int t = 0; t < 3; ++t)
-          if ((rc = gram(p, w.gQKV + t * D, 3 * D, D, kf + K(kq[t]).gtg_offset, rows, s))) return rc;
+          if ((rc = gram(p, w.gQKV + t * D, 3 * D, D, kf + K(kq[t]).gtg_offset, rows, s, true))) return rc;
       }
       for (int t = 0; t < 3; ++t) {
         if (!kf) {
@@ -266,7 +284,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
       if (tc && (rc = dense_bwd_x_tc(p, w.gQKV, 3 * D, l * VS_PER_LAYER + VS_QKV, 3 * D, w.gH, rows, 1, s))) return rc;
     }
     if (kf) {  // Dense_0: the caller forms sum feat feat^T itself; here the output-gradient factor
-      if ((rc = gram(p, w.gH, D, D, kf + K(p->kf_dense0).gtg_offset, rows, s))) return rc;
+      if ((rc = gram(p, w.gH, D, D, kf + K(p->kf_dense0).gtg_offset, rows, s, true))) return rc;
       continue;
     }
     RUN(PC_OTHER, features_dense0_bwd(xc, w.gH, grad + p->off_W0, Bc, nd, s));

@@ -622,6 +622,181 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// =============================================================================================================
+// "TN" contraction for the reverse pass and the KFAC factor sums:   C[Ma, Nb] += A[rows, Ma]^T  B[rows, Nb]
+// (dW = X^T dY, Gram matrices X^T X and G^T G): the contracted index is the ROW index of both row-major operands, so
+// neither is K-major in memory.  One CTA owns one 256 x 256 block of C and a slice of the rows (split-K over the
+// grid); per 32-row step TMA lands the two fp32 tiles [32][256] as they lie, the 256 splitter threads -- thread t
+// = column t -- read their column (conflict-free), split it into fp16 hi / lo pieces and write ROW t of the K-major,
+// 64B-swizzled operand tiles (the transposition happens in this register pass), and one elected thread issues
+// 2 M-tiles x 2 K-steps x 3 products of tcgen05.mma into two 128 x 256 fp32 accumulators (all 512 TMEM columns).
+// After its last step the CTA adds its block into C with TMA reduce-add.  Optional power-of-two scales keep
+// small-magnitude operands (cotangent-sized gradients) inside fp16's range; the epilogue divides them out.
+// =============================================================================================================
+constexpr int TN_BK = 32;                        // rows (contracted index) per step
+constexpr int TN_LAND_BYTES = TN_BK * 256 * 4;    // one landed fp32 tile [32][256]
+constexpr int TN_OP_BYTES = 256 * 64;             // one fp16 operand piece tile: 256 rows of 64 B
+constexpr int TN_SMEM_BYTES = 4 * TN_LAND_BYTES + 4 * TN_OP_BYTES + EPI_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, int64_t rows, int nblk_n, int ksplit,
+                  const float* __restrict__ a_scale_ptr, const float* __restrict__ b_scale_ptr) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // [landing: 2 stages x (A 32 KB | B 32 KB)] [operands: A hi | A lo | B hi | B lo, 16 KB each] [epilogue staging] [barriers]
+  uint8_t* land = smem;
+  uint8_t* ops = smem + 4 * TN_LAND_BYTES;
+  uint8_t* epi_smem = ops + 4 * TN_OP_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };         // TMA landed stage s
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 + s); };  // splitters have read stage s
+  const uint32_t op_full = bar_base + 8u * 4;                        // operand tiles written
+  const uint32_t op_empty = bar_base + 8u * 5;                       // MMAs have read the operand tiles
+  const uint32_t acc_done = bar_base + 8u * 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item: block (bm, bn) of C and k-slice ks
+  const int blk = blockIdx.x / ksplit, ks = blockIdx.x % ksplit;
+  const int bm = blk / nblk_n, bn = blk % nblk_n;
+  const int64_t nkb = (rows + TN_BK - 1) / TN_BK;
+  const int64_t per = (nkb + ksplit - 1) / ksplit;
+  const int64_t kb0 = ks * per, kb1 = (kb0 + per < nkb) ? kb0 + per : nkb;
+  const int64_t my_kb = kb1 > kb0 ? kb1 - kb0 : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+    for (int s = 0; s < 2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), SPLIT_WARPS); }
+    mbar_init(op_full, SPLIT_WARPS);
+    mbar_init(op_empty, 1);
+    mbar_init(acc_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int64_t it = 0; it < my_kb; ++it) {
+        const int s = (int)(it & 1);
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_arrive_expect_tx(full_bar(s), 2 * TN_LAND_BYTES);
+        const int r0 = (int)((kb0 + it) * TN_BK);
+        tma_load_2d(smem_u32(land + s * 2 * TN_LAND_BYTES), &tmA, full_bar(s), bm * 256, r0);
+        tma_load_2d(smem_u32(land + s * 2 * TN_LAND_BYTES + TN_LAND_BYTES), &tmB, full_bar(s), bn * 256, r0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0 && my_kb > 0) {
+      const uint32_t idesc = make_idesc<true>(BLOCK_M, 256);
+      const uint32_t a_hi = smem_u32(ops), a_lo = a_hi + TN_OP_BYTES, b_hi = a_lo + TN_OP_BYTES, b_lo = b_hi + TN_OP_BYTES;
+      for (int64_t it = 0; it < my_kb; ++it) {
+        mbar_wait(op_full, (uint32_t)(it & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const uint64_t dah = make_smem_desc<true>(a_hi + mt * 128 * 64), dal = make_smem_desc<true>(a_lo + mt * 128 * 64);
+          const uint64_t dbh = make_smem_desc<true>(b_hi), dbl = make_smem_desc<true>(b_lo);
+          const uint32_t acc = tmem_base + (uint32_t)mt * 256;
+#pragma unroll
+          for (int k = 0; k < TN_BK / 16; ++k) {
+            const uint64_t adv = (uint64_t)(k * 2);
+            umma<true>(acc, dal + adv, dbh + adv, idesc, (it | k) != 0);
+            umma<true>(acc, dah + adv, dbl + adv, idesc, 1);
+            umma<true>(acc, dah + adv, dbh + adv, idesc, 1);
+          }
+        }
+        umma_commit(op_empty);
+      }
+      umma_commit(acc_done);
+    }
+  } else if (warp < EPI_WARP0) {
+    // ------------------------------------------------------------------ splitter / transposer (256 threads)
+    const int t = threadIdx.x - 64;  // column of the landed tiles = row of the operand tiles
+    const float asc = a_scale_ptr ? __ldg(a_scale_ptr) : 1.f, bsc = b_scale_ptr ? __ldg(b_scale_ptr) : 1.f;
+    const int sw = (t >> 1) & 3;
+    for (int64_t it = 0; it < my_kb; ++it) {
+      const int s = (int)(it & 1);
+      mbar_wait(full_bar(s), (uint32_t)((it >> 1) & 1));
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {
+        const float* src = reinterpret_cast<const float*>(land + s * 2 * TN_LAND_BYTES + op * TN_LAND_BYTES) + t;
+        const float sc = op == 0 ? asc : bsc;
+        float v[TN_BK];
+#pragma unroll
+        for (int k = 0; k < TN_BK; ++k) v[k] = src[k * 256] * sc;
+        // the operand tiles are free once the MMAs of the previous step have completed
+        if (op == 0 && it > 0) mbar_wait(op_empty, (uint32_t)((it - 1) & 1));
+        uint8_t* hi_t = ops + op * 2 * TN_OP_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // 16-byte piece c of row t = k elements 8c .. 8c+7
+          uint4 hi, lo;
+          split_f16x2(v[8 * c], v[8 * c + 1], hi.x, lo.x);
+          split_f16x2(v[8 * c + 2], v[8 * c + 3], hi.y, lo.y);
+          split_f16x2(v[8 * c + 4], v[8 * c + 5], hi.z, lo.z);
+          split_f16x2(v[8 * c + 6], v[8 * c + 7], hi.w, lo.w);
+          const int pos = t * 64 + ((c ^ sw) << 4);
+          *reinterpret_cast<uint4*>(hi_t + pos) = hi;
+          *reinterpret_cast<uint4*>(hi_t + TN_OP_BYTES + pos) = lo;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar(s));  // both landed tiles of this stage are in registers / written out
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(op_full);
+    }
+  } else if (my_kb > 0) {
+    // ------------------------------------------------------------------ epilogue (8 warps): C block += accumulators
+    const int q = warp & 3, chalf = (warp - EPI_WARP0) >> 2;
+    uint8_t* buf = epi_smem + (warp - EPI_WARP0) * EPI_BUF_BYTES;
+    const float inv = (a_scale_ptr ? __ldg(a_scale_ptr + 1) : 1.f) * (b_scale_ptr ? __ldg(b_scale_ptr + 1) : 1.f);
+    mbar_wait(acc_done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mt * 256;
+      for (int c0 = chalf * EPI_CHUNK; c0 < 256; c0 += 2 * EPI_CHUNK) {
+        uint32_t v[32];
+        tmem_ld32(tbase + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                          __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tmC, smem_u32(buf), bn * 256 + c0, bm * 256 + mt * 128 + q * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---- weight preparation ---------------------------------------------------------------------
 // scale slot (3 floats): [0] max |W| over the slot (as ordered uint bits), [1] 1/scale, [2] scale.
 __global__ void weight_maxabs_kernel(const float* __restrict__ W, int64_t ldw, int K, int N, unsigned* __restrict__ slot) {
@@ -770,6 +945,52 @@ static int num_sms() {
 }
 
 }  // namespace tc
+
+// Tensor map over a row-major fp32 matrix [rows][cols] (row stride ld) with an arbitrary box and no swizzle (the
+// landed tiles of the TN contraction) or the 32 x 32, 128B-swizzled box of the epilogue staging buffers.
+static int make_map_box(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                        uint32_t box_rows, bool swizzle128) {
+  tc::EncodeTiledFn enc = tc::get_encode();
+  if (!enc) return -2;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
+}
+
+int gemm_tn_tc_ok(const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc) {
+  return (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0 &&
+         ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0;
+}
+
+// C[Ma, Nb] (ldc) += A[rows, Ma]^T (lda) @ B[rows, Nb] (ldb) / (a_scale * b_scale); scales = device {s, 1/s} or null
+int gemm_tn_tc(const float* A, int64_t lda, int Ma, const float* B, int64_t ldb, int Nb, float* C, int64_t ldc, int64_t rows,
+               const float* a_scale, const float* b_scale, cudaStream_t stream) {
+  if (rows <= 0 || Ma <= 0 || Nb <= 0) return 0;
+  if (!gemm_tn_tc_ok(A, lda, B, ldb, C, ldc) || rows > 0x7fffff00LL) return -2;
+  CUtensorMap tmA, tmB, tmC;
+  int rc;
+  if ((rc = make_map_box(&tmA, A, (uint64_t)rows, (uint64_t)Ma, (uint64_t)lda, 256, tc::TN_BK, false))) return rc;
+  if ((rc = make_map_box(&tmB, B, (uint64_t)rows, (uint64_t)Nb, (uint64_t)ldb, 256, tc::TN_BK, false))) return rc;
+  if ((rc = make_map_box(&tmC, C, (uint64_t)Ma, (uint64_t)Nb, (uint64_t)ldc, 32, 32, true))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TN_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int nbm = (Ma + 255) / 256, nbn = (Nb + 255) / 256, nblk = nbm * nbn;
+  const int64_t nkb = (rows + tc::TN_BK - 1) / tc::TN_BK;
+  int ksplit = tc::num_sms() / nblk;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > nkb) ksplit = (int)nkb;
+  tc::gemm_tn_tc_kernel<<<nblk * ksplit, tc::THREADS, tc::TN_SMEM_BYTES, stream>>>(tmA, tmB, tmC, rows, nbn, ksplit, a_scale, b_scale);
+  return (int)cudaGetLastError();
+}
 
 int gemm_tc_supported(int N, int K) { return N >= 1 && K >= 32 && K % 32 == 0; }
 int gemm_tc_f16_ok(int K) { return K >= 32 && K % 32 == 0; }

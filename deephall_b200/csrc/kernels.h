@@ -32,6 +32,11 @@ struct TcGemm {
   const void* A_lo;      // non-null (fp16 pieces only): A and A_lo are fp16 hi / lo planes [M][lda] written by the
                          // producing kernel; the in-kernel split is skipped
 };
+// "TN" contraction on the tensor cores (reverse-pass dW = X^T dY, KFAC Gram sums): C[Ma, Nb] (ldc) += A[rows, Ma]^T B[rows, Nb]
+// / (a_scale * b_scale); a_scale / b_scale: optional device {s, 1/s} applied to the operand before the fp16 split
+int gemm_tn_tc_ok(const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc);
+int gemm_tn_tc(const float* A, int64_t lda, int Ma, const float* B, int64_t ldb, int Nb, float* C, int64_t ldc, int64_t rows,
+               const float* a_scale, const float* b_scale, cudaStream_t stream);
 // slot = {s, 1/s}, s = power of two bringing max|v| into [1, 2)
 int pow2_scale_tc(const float* v, int64_t n, float* slot, cudaStream_t stream);
 int gemm_tc_ex(const TcGemm& g, cudaStream_t stream);
