@@ -247,7 +247,7 @@ def run_ours(args):
 
     vmc_k = VMC(dataclasses.replace(cfg, optim=Optim(optimizer="kfac")))
     vmc_k.state = vmc_k.state._replace(data=data.clone())
-    ms_vmc_kfac = timed(lambda: vmc_k.step(sync_stats=False), k2, 1) / k2
+    ms_vmc_kfac = timed(lambda: vmc_k.step(sync_stats=False), k2, 3) / k2  # (3 warm-up steps: lazy library initialisation)
     del vmc_k
 
     # ---- roofline of the dominant kernel (dense contractions), CUDA-event timed per launch

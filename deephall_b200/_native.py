@@ -71,6 +71,7 @@ SIGNATURES = OrderedDict(
     dh_init_walkers=(C.c_int, [_vp, _vp, _i64, _u64, _u64, _vp]),
     dh_logpsi_vjp=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     dh_slogdet=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    dh_spd_inverse=(C.c_int, [_vp, _i32, _i32, _vp]),
     dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     dh_debug_buffer=(C.c_int, [_vp, C.c_int, _i64, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     dh_launch_count=(C.c_longlong, [_vp]),
@@ -330,6 +331,15 @@ def _kfac_methods():
 
 
 _kfac_methods()
+
+
+def spd_inverse(mats):
+    """Inverse of a batch of SPD matrices, (batch, n, n) f32 cuda, n <= 1024 (dh_spd_inverse); returns a new tensor."""
+    _need_cuda()
+    lib = load()
+    out = mats.contiguous().clone()
+    _check(lib.dh_spd_inverse(_ptr(out), out.shape[-1], out.shape[0], _stream()), "dh_spd_inverse")
+    return out
 
 
 def slogdet(mats):

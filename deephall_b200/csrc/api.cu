@@ -677,6 +677,12 @@ extern "C" int dh_slogdet(const float* mats, int64_t B, int32_t K, int32_t n, fl
   return slogdet_batched(mats, B, K, n, out_sign, out_logabs, out_logpsi, (cudaStream_t)stream);
 }
 
+extern "C" int dh_spd_inverse(float* mats, int32_t n, int32_t batch, void* stream) {
+  if (!mats && batch > 0) return DH_E_BADARG;
+  if (n > 1024) return DH_E_UNSUPPORTED;
+  return spd_inverse_batched(mats, n, batch, (cudaStream_t)stream);
+}
+
 extern "C" int dh_gemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
                        int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* stream) {
   if (!A || !W || !C) return DH_E_BADARG;

@@ -130,6 +130,7 @@ int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* 
              float* g_c, int64_t B, TailDims d, cudaStream_t s);
 int jastrow_bwd(const float* cot, const float* x, const float* ee_par, const float* ee_anti, float* g_eepar,
                 float* g_eeanti, float* sq_eepar, float* sq_eeanti, int64_t B, int N, int n_up, cudaStream_t s);
+int spd_inverse_batched(float* mats, int n, int batch, cudaStream_t s);
 // KFAC factor pass (dh_kfac_factors)
 int fill_unit_cot(float* cot, int64_t n, cudaStream_t s);
 int mask_rows_by_spin(const float* src, float* dst, int64_t rows, int D, int N, int n_up, int sb, cudaStream_t s);

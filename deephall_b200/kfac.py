@@ -17,7 +17,7 @@ from typing import NamedTuple
 
 import torch
 
-from . import constants
+from . import _native, constants
 from .networks import Psiformer
 from .optimizers import CheckpointState
 
@@ -120,9 +120,9 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
             ig = groups.setdefault(G.shape[0], [])  # (the same list when both factors have the same size)
             ig.append(mg)
             blocks.append((e, (A.shape[0], ja), (G.shape[0], len(ig) - 1), ck))
-        # (torch.linalg.inv: on this torch build the batched LU path is the fastest of inv / cholesky_inverse for these
-        # sizes, scripts/gpu_kfac_timing.py)
-        inv = {n: torch.linalg.inv(torch.stack(ms)) for n, ms in groups.items()}
+        # (dh_spd_inverse: one Gauss-Jordan block per matrix, no library initialisation or workspace; it beats the
+        # library's batched LU up to ~300 rows, scripts/gpu_kfac_timing.py)
+        inv = {n: (_native.spd_inverse(torch.stack(ms)) if n <= 320 else torch.linalg.inv(torch.stack(ms))) for n, ms in groups.items()}
         # pass 2: U = A_inv V G_inv / (c_k^2 npw)
         for e, (na, ja), (ng, jg), ck in blocks:
             din, dout, hb, npw, ko = e["in_dim"], e["out_dim"], e["has_bias"], e["rows_per_walker"], e["kernel_offset"]

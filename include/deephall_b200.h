@@ -172,6 +172,10 @@ int dh_kfac_layout(const dh_plan* plan, dh_kfac_entry* entries, int32_t* n, int6
 int dh_kfac_factors(dh_plan* plan, const float* params, const float* x, int64_t B, float* factors, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* In-place inverse of `batch` symmetric positive-definite n x n fp32 matrices (row-major, contiguous), n <= 1024: the
+ * damped Kronecker factors of the KFAC update (Gauss-Jordan without pivoting, one block per matrix). */
+int dh_spd_inverse(float* mats, int32_t n, int32_t batch, void* stream);
+
 /* Batched complex slogdet with the reference's multi-determinant tail (psiformer.py:74-76).
  *   mats: (B, K, n, n) complex64, row-major.
  *   out_sign (B,K) complex64 and out_logabs (B,K) f32 may be NULL;

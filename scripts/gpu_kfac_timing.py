@@ -28,4 +28,5 @@ for n, b in ((257, 13), (256, 14), (408, 2)):
     m = torch.randn(b, n, n, device="cuda")
     m = m @ m.transpose(1, 2) / n + 0.1 * torch.eye(n, device="cuda")
     print(f"{b} x {n}^2: inv {t(lambda: torch.linalg.inv(m)):6.2f} ms  cholesky_inverse {t(lambda: torch.cholesky_inverse(torch.linalg.cholesky(m))):6.2f} ms  "
-          f"one-by-one inv {t(lambda: [torch.linalg.inv(m[i]) for i in range(b)]):6.2f} ms")
+          f"one-by-one inv {t(lambda: [torch.linalg.inv(m[i]) for i in range(b)]):6.2f} ms  dh_spd_inverse {t(lambda: nat.spd_inverse(m)):6.2f} ms  "
+          f"max |dh - torch| / max |torch| {((nat.spd_inverse(m) - torch.linalg.inv(m)).abs().max() / torch.linalg.inv(m).abs().max()).item():.1e}")
