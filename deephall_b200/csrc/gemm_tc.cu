@@ -49,7 +49,7 @@ constexpr int EPI_CHUNK = 32;                            // accumulator columns 
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 4;        // 32 rows x 32 floats = 4 KB (one warp, one step)
 constexpr int EPI_WARPS = 8;                             // two per TMEM lane quarter, alternating 32-column chunks
 constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES;     // one staging buffer per warp = 32 KB
-constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 constexpr int SPLIT_WARPS = 8;
 constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;  // first epilogue warp
 constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 576
@@ -234,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
                int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
-               int a_pre, unsigned long long* __restrict__ prof) {
+               int a_pre, int res, unsigned long long* __restrict__ prof) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
@@ -271,6 +271,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto a_lo = [&](int s) { return smem_base + s * STAGE_BYTES + AP_BYTES; };
   auto b_hi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES; };
   auto b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES + B_BYTES; };
+  // res (PAIR, K <= 256, several column tiles per band): the band's A operand tiles stay RESIDENT for all its column
+  // tiles -- k-block kb of A lands in its own 16 KB region (8 regions = 128 KB) and is split in place ONCE per band
+  // instead of once per column tile; the weights stream through a separate ring of 4 x 16 KB stages.  Takes the
+  // repeated A loads and splits (half of the shared-memory traffic of a tile) off every column tile but the first.
+  constexpr int RES_KB = 8, RES_BST = 4;
+  auto ra_reg = [&](int kb) { return smem_base + kb * 2 * AP_BYTES; };
+  auto rb_hi = [&](int s) { return smem_base + RES_KB * 2 * AP_BYTES + s * 2 * B_BYTES; };
+  auto rb_lo = [&](int s) { return smem_base + RES_KB * 2 * AP_BYTES + s * 2 * B_BYTES + B_BYTES; };
+  auto ra_full = [&](int kb) { return bar_base + 8u * (24 + kb); };
+  auto ra_split = [&](int kb) { return bar_base + 8u * (32 + kb); };
+  auto ra_empty = [&](int kb) { return bar_base + 8u * (40 + kb); };
+  auto rb_full = [&](int s) { return bar_base + 8u * (48 + s); };
+  auto rb_empty = [&](int s) { return bar_base + 8u * (52 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;  // a K tail is zero-filled by TMA (A) and zero-padded (W planes)
@@ -311,6 +324,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tmem_full_bar(b), 1);
       mbar_init(tmem_empty_bar(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
+    if (PAIR && res) {
+      for (int kb = 0; kb < RES_KB; ++kb) { mbar_init(ra_full(kb), 1); mbar_init(ra_split(kb), 2 * SPLIT_WARPS); mbar_init(ra_empty(kb), 1); }
+      for (int st = 0; st < RES_BST; ++st) { mbar_init(rb_full(st), 1); mbar_init(rb_empty(st), 1); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -344,7 +361,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (lane == 0 && PAIR && res) {
+      uint32_t itb = 0;
+      for (int64_t bi = 0; bi < my_bands; ++bi) {
+        const int m0 = (int)(band_of(bi * n_ntiles) * BLOCK_M);
+        for (int nt = 0; nt < n_ntiles; ++nt) {
+          const int n0 = nt * BLOCK_N;
+          const int n_tile = N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N;
+          const int nb = n0 + (int)crank * (n_tile / 2);
+          for (int kb = 0; kb < num_kb; ++kb, ++itb) {
+            if (nt == 0) {  // the band's A: once, into region kb (free when the previous band's last column tile has read it)
+              mbar_wait(ra_empty(kb), (uint32_t)((bi & 1) ^ 1));
+              mbar_arrive_expect_tx(ra_full(kb), A_TX_BYTES);
+              tma_load_2d(ra_reg(kb), &tmA, ra_full(kb), kb * BLOCK_K, m0);
+            }
+            const int st = itb % RES_BST;
+            mbar_wait(rb_empty(st), ((itb / RES_BST) & 1) ^ 1);
+            if (crank == 0) mbar_arrive_expect_tx(rb_full(st), 4 * B_BYTES);  // both CTAs' halves, hi and lo
+            tma_load_2d_pair(rb_hi(st), &tmBhi, leader(rb_full(st)), kb * BLOCK_K, nb);
+            tma_load_2d_pair(rb_lo(st), &tmBlo, leader(rb_full(st)), kb * BLOCK_K, nb);
+          }
+        }
+      }
+    } else if (lane == 0) {
       uint32_t it = 0;
       for (int64_t tk = 0; tk < my_tiles; ++tk) {
         const int m0 = (int)(band_of(tk) * BLOCK_M);
@@ -388,7 +427,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (PAIR: the leader CTA's, for both)
-    if (lane == 0 && (!PAIR || crank == 0)) {
+    if (lane == 0 && PAIR && res && crank == 0) {
+      uint32_t itb = 0, tl = 0;
+      for (int64_t bi = 0; bi < my_bands; ++bi) {
+        for (int nt = 0; nt < n_ntiles; ++nt, ++tl) {
+          const int n0 = nt * BLOCK_N;
+          const int n_tile = N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N;
+          const uint32_t idesc = make_idesc<F16>(2 * BLOCK_M, n_tile);
+          const int ab = (int)(tl & 1);
+          const uint32_t acc = tmem_base + (uint32_t)ab * BLOCK_N;
+          timed_wait(tmem_empty_bar(ab), ((tl >> 1) & 1) ^ 1, 0);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          for (int kb = 0; kb < num_kb; ++kb, ++itb) {
+            if (nt == 0) timed_wait(ra_split(kb), (uint32_t)(bi & 1), 2);  // both CTAs' A tiles of this k-block landed and split
+            const int st = itb % RES_BST;
+            timed_wait(rb_full(st), (itb / RES_BST) & 1, 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t dah = make_smem_desc<F16>(ra_reg(kb)), dal = make_smem_desc<F16>(ra_reg(kb) + AP_BYTES);
+            const uint64_t dbh = make_smem_desc<F16>(rb_hi(st)), dbl = make_smem_desc<F16>(rb_lo(st));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t adv = (uint64_t)(k * 2);
+              umma_pair_f16(acc, dal + adv, dbh + adv, idesc, (kb | k) != 0);
+              umma_pair_f16(acc, dah + adv, dbl + adv, idesc, 1);
+              umma_pair_f16(acc, dah + adv, dbh + adv, idesc, 1);
+            }
+            umma_commit_pair(rb_empty(st), 3);
+            if (nt == n_ntiles - 1) umma_commit_pair(ra_empty(kb), 3);  // the band is done with this k-block of A
+          }
+          umma_commit_pair(tmem_full_bar(ab), 3);
+        }
+      }
+      if (prof) { atomicAdd(prof + 1, pw[0]); atomicAdd(prof + 2, pw[1]); atomicAdd(prof + 3, pw[2]);
+                  atomicAdd(prof + 11, (unsigned long long)(clock64() - t_begin)); }
+    } else if (lane == 0 && (!PAIR || crank == 0)) {
       uint32_t it = 0, tl = 0;
       for (int64_t tk = 0; tk < my_tiles; ++tk, ++tl) {
         const int n0 = ntile_of(tk) * BLOCK_N;
@@ -446,11 +518,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // a_scale_ptr = {scale, 1/scale}, the epilogue undoes it
     const float asc = a_scale_ptr ? __ldg(a_scale_ptr) : 1.f;
     uint32_t it = 0;
-    for (int64_t tk = 0; tk < (a_pre ? 0 : my_tiles); ++tk) {
+    const bool rs = PAIR && res;  // resident A: one split per (band, k-block), in region kb
+    for (int64_t tk = 0; tk < (a_pre ? 0 : (rs ? my_bands : my_tiles)); ++tk) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        if (t == 0) timed_wait(full_bar(s), ph, 0); else mbar_wait(full_bar(s), ph);
+        const uint32_t ph = rs ? (uint32_t)(tk & 1) : (it / STAGES) & 1;
+        const uint32_t wbar = rs ? ra_full(kb) : full_bar(s);
+        uint8_t* const stage_reg = rs ? smem + kb * 2 * AP_BYTES : smem + s * STAGE_BYTES;
+        if (t == 0) timed_wait(wbar, ph, 0); else mbar_wait(wbar, ph);
         const long long ts0 = (prof && t == 0) ? clock64() : 0;
         if (F16) {
           // Two threads per tile row r: thread (r, h) converts the 16 floats k = 16h .. 16h+15 of the landed fp32
@@ -458,7 +533,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // 64 B at r*64, piece c at position c ^ ((r >> 1) & 3)) overwrites the first 8 KB of the same region and
           // the lo tile the second 8 KB, so all 256 splitter threads read before any of them writes.
           const int r = t >> 1, h = t & 1, sw = r & 7;
-          uint8_t* reg = smem + s * STAGE_BYTES;
+          uint8_t* reg = stage_reg;
           const uint8_t* src = reg + r * 128;
           float4 v[4];
 #pragma unroll
@@ -496,7 +571,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(split_bar(s))); else mbar_arrive(split_bar(s)); }
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(rs ? ra_split(kb) : split_bar(s))); else mbar_arrive(split_bar(s)); }
         if (prof && t == 0) pw[1] += (unsigned long long)(clock64() - ts0);
       }
     }
@@ -1105,6 +1180,9 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
     cudaMemsetAsync(buf, 0, 32 * sizeof(unsigned long long), stream);
     prof = buf;
   }
+  // resident A (pair form): K <= 256 and more than one column tile per band; DH_GEMM_RES=0 disables
+  static const bool res_env = !(getenv("DH_GEMM_RES") && atoi(getenv("DH_GEMM_RES")) == 0);
+  const int res = (pair && res_env && K <= 8 * tc::BLOCK_K && N > tc::BLOCK_N) ? 1 : 0;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = grid;
@@ -1120,7 +1198,7 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   lc.numAttrs = 1;
   cudaError_t le;
 #define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
-                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, prof)
+                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, prof)
   if (pair) DH_LAUNCH_TC(true, true, true);
   else if (f16) { if (merged) DH_LAUNCH_TC(true, true, false); else DH_LAUNCH_TC(true, false, false); }
   else { if (merged) DH_LAUNCH_TC(false, true, false); else DH_LAUNCH_TC(false, false, false); }
