@@ -72,6 +72,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -272,18 +283,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto b_hi = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES; };
   auto b_lo = [&](int s) { return smem_base + s * STAGE_BYTES + 2 * AP_BYTES + B_BYTES; };
   // res (PAIR, K <= 256, several column tiles per band): the band's A operand tiles stay RESIDENT for all its column
-  // tiles -- k-block kb of A lands in its own 16 KB region (8 regions = 128 KB) and is split in place ONCE per band
-  // instead of once per column tile; the weights stream through a separate ring of 4 x 16 KB stages.  Takes the
-  // repeated A loads and splits (half of the shared-memory traffic of a tile) off every column tile but the first.
-  constexpr int RES_KB = 8, RES_BST = 4;
-  auto ra_reg = [&](int kb) { return smem_base + kb * 2 * AP_BYTES; };
-  auto rb_hi = [&](int s) { return smem_base + RES_KB * 2 * AP_BYTES + s * 2 * B_BYTES; };
-  auto rb_lo = [&](int s) { return smem_base + RES_KB * 2 * AP_BYTES + s * 2 * B_BYTES + B_BYTES; };
-  auto ra_full = [&](int kb) { return bar_base + 8u * (24 + kb); };
-  auto ra_split = [&](int kb) { return bar_base + 8u * (32 + kb); };
-  auto ra_empty = [&](int kb) { return bar_base + 8u * (40 + kb); };
-  auto rb_full = [&](int s) { return bar_base + 8u * (48 + s); };
-  auto rb_empty = [&](int s) { return bar_base + 8u * (52 + s); };
+  // tiles -- every (band, k-block) of A lands in one of RES_AR 16 KB regions (a ring over the sequence of k-blocks)
+  // and is split in place ONCE per band instead of once per column tile; the weights stream through a separate ring
+  // of RES_BST 16 KB stages.  The producer reloads a region for the NEXT band as soon as the last column tile of
+  // the current band has released it (non-blocking test between its weight loads), i.e. ~7 k-blocks before the MMA
+  // needs it.  Takes the repeated A loads and splits (half of a tile's shared-memory traffic) off every column tile
+  // but the first.
+  constexpr int RES_AR = 8, RES_BST = 4;
+  static_assert((RES_AR + RES_BST) * 16 * 1024 <= RING_BYTES, "resident-A layout");
+  auto ra_reg = [&](int r) { return smem_base + r * 2 * AP_BYTES; };
+  auto rb_hi = [&](int s) { return smem_base + RES_AR * 2 * AP_BYTES + s * 2 * B_BYTES; };
+  auto rb_lo = [&](int s) { return smem_base + RES_AR * 2 * AP_BYTES + s * 2 * B_BYTES + B_BYTES; };
+  auto ra_full = [&](int r) { return bar_base + 8u * (24 + r); };
+  auto ra_split = [&](int r) { return bar_base + 8u * (24 + RES_AR + r); };
+  auto ra_empty = [&](int r) { return bar_base + 8u * (24 + 2 * RES_AR + r); };
+  auto rb_full = [&](int s) { return bar_base + 8u * (24 + 3 * RES_AR + s); };
+  auto rb_empty = [&](int s) { return bar_base + 8u * (24 + 3 * RES_AR + RES_BST + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;  // a K tail is zero-filled by TMA (A) and zero-padded (W planes)
@@ -325,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tmem_empty_bar(b), PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     if (PAIR && res) {
-      for (int kb = 0; kb < RES_KB; ++kb) { mbar_init(ra_full(kb), 1); mbar_init(ra_split(kb), 2 * SPLIT_WARPS); mbar_init(ra_empty(kb), 1); }
+      for (int kb = 0; kb < RES_AR; ++kb) { mbar_init(ra_full(kb), 1); mbar_init(ra_split(kb), 2 * SPLIT_WARPS); mbar_init(ra_empty(kb), 1); }
       for (int st = 0; st < RES_BST; ++st) { mbar_init(rb_full(st), 1); mbar_init(rb_empty(st), 1); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -363,23 +378,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0 && PAIR && res) {
       uint32_t itb = 0;
+      int64_t ja = 0;  // A tiles issued so far, in (band, k-block) order
+      const int64_t total_a = my_bands * num_kb;
+      auto issue_a = [&](bool blocking) -> bool {
+        if (ja >= total_a) return false;
+        const int r = (int)(ja % RES_AR);
+        const uint32_t par = (uint32_t)(((ja / RES_AR) & 1) ^ 1);
+        if (blocking) mbar_wait(ra_empty(r), par); else if (!mbar_test(ra_empty(r), par)) return false;
+        const int64_t bi2 = ja / num_kb;
+        const int kb2 = (int)(ja % num_kb);
+        mbar_arrive_expect_tx(ra_full(r), A_TX_BYTES);
+        tma_load_2d(ra_reg(r), &tmA, ra_full(r), kb2 * BLOCK_K, (int)(band_of(bi2 * n_ntiles) * BLOCK_M));
+        ++ja;
+        return true;
+      };
       for (int64_t bi = 0; bi < my_bands; ++bi) {
-        const int m0 = (int)(band_of(bi * n_ntiles) * BLOCK_M);
         for (int nt = 0; nt < n_ntiles; ++nt) {
           const int n0 = nt * BLOCK_N;
           const int n_tile = N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N;
           const int nb = n0 + (int)crank * (n_tile / 2);
           for (int kb = 0; kb < num_kb; ++kb, ++itb) {
-            if (nt == 0) {  // the band's A: once, into region kb (free when the previous band's last column tile has read it)
-              mbar_wait(ra_empty(kb), (uint32_t)((bi & 1) ^ 1));
-              mbar_arrive_expect_tx(ra_full(kb), A_TX_BYTES);
-              tma_load_2d(ra_reg(kb), &tmA, ra_full(kb), kb * BLOCK_K, m0);
-            }
+            if (nt == 0) while (ja <= bi * num_kb + kb) issue_a(true);   // this step's A tile at the latest now
             const int st = itb % RES_BST;
             mbar_wait(rb_empty(st), ((itb / RES_BST) & 1) ^ 1);
             if (crank == 0) mbar_arrive_expect_tx(rb_full(st), 4 * B_BYTES);  // both CTAs' halves, hi and lo
             tma_load_2d_pair(rb_hi(st), &tmBhi, leader(rb_full(st)), kb * BLOCK_K, nb);
             tma_load_2d_pair(rb_lo(st), &tmBlo, leader(rb_full(st)), kb * BLOCK_K, nb);
+            // one tile of the next band per step, as regions come free, queued BEHIND the latency-critical weight
+            // loads (a burst of HBM-bound A loads in front of them starves the MMA)
+            if (ja < (bi + 2) * num_kb) issue_a(false);
           }
         }
       }
@@ -439,11 +466,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           timed_wait(tmem_empty_bar(ab), ((tl >> 1) & 1) ^ 1, 0);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int kb = 0; kb < num_kb; ++kb, ++itb) {
-            if (nt == 0) timed_wait(ra_split(kb), (uint32_t)(bi & 1), 2);  // both CTAs' A tiles of this k-block landed and split
+            const uint32_t ja = (uint32_t)(bi * num_kb + kb);  // position of this (band, k-block) in the A ring
+            const int r = ja % RES_AR;
+            if (nt == 0) timed_wait(ra_split(r), (ja / RES_AR) & 1, 2);  // both CTAs' A tiles of this k-block landed and split
             const int st = itb % RES_BST;
             timed_wait(rb_full(st), (itb / RES_BST) & 1, 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t dah = make_smem_desc<F16>(ra_reg(kb)), dal = make_smem_desc<F16>(ra_reg(kb) + AP_BYTES);
+            const uint64_t dah = make_smem_desc<F16>(ra_reg(r)), dal = make_smem_desc<F16>(ra_reg(r) + AP_BYTES);
             const uint64_t dbh = make_smem_desc<F16>(rb_hi(st)), dbl = make_smem_desc<F16>(rb_lo(st));
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -453,7 +482,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               umma_pair_f16(acc, dah + adv, dbh + adv, idesc, 1);
             }
             umma_commit_pair(rb_empty(st), 3);
-            if (nt == n_ntiles - 1) umma_commit_pair(ra_empty(kb), 3);  // the band is done with this k-block of A
+            if (nt == n_ntiles - 1) umma_commit_pair(ra_empty(r), 3);  // the band is done with this k-block of A
           }
           umma_commit_pair(tmem_full_bar(ab), 3);
         }
@@ -522,9 +551,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int64_t tk = 0; tk < (a_pre ? 0 : (rs ? my_bands : my_tiles)); ++tk) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % STAGES;
-        const uint32_t ph = rs ? (uint32_t)(tk & 1) : (it / STAGES) & 1;
-        const uint32_t wbar = rs ? ra_full(kb) : full_bar(s);
-        uint8_t* const stage_reg = rs ? smem + kb * 2 * AP_BYTES : smem + s * STAGE_BYTES;
+        const int rr = it % RES_AR;  // rs: `it` counts the (band, k-block) pairs = position in the A ring
+        const uint32_t ph = rs ? (it / RES_AR) & 1 : (it / STAGES) & 1;
+        const uint32_t wbar = rs ? ra_full(rr) : full_bar(s);
+        uint8_t* const stage_reg = rs ? smem + rr * 2 * AP_BYTES : smem + s * STAGE_BYTES;
         if (t == 0) timed_wait(wbar, ph, 0); else mbar_wait(wbar, ph);
         const long long ts0 = (prof && t == 0) ? clock64() : 0;
         if (F16) {
@@ -571,7 +601,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
         __syncwarp();
-        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(rs ? ra_split(kb) : split_bar(s))); else mbar_arrive(split_bar(s)); }
+        if (lane == 0) { if (PAIR) mbar_arrive_cluster(leader(rs ? ra_split(rr) : split_bar(s))); else mbar_arrive(split_bar(s)); }
         if (prof && t == 0) pw[1] += (unsigned long long)(clock64() - ts0);
       }
     }
