@@ -643,6 +643,18 @@ def test_kfac_training_step_matches_the_restated_update(nat):
     assert sum(energies[-5:]) / 5 < sum(energies[:5]) / 5 and abs(sum(energies[-5:]) / 5 - 1.5) < 0.15, energies
 
 
+def test_spd_inverse(nat):
+    """dh_spd_inverse (batched in-place Gauss-Jordan, the KFAC factor inverses) against torch.linalg.inv in fp64."""
+    g = torch.Generator().manual_seed(0)
+    for n, b in ((5, 3), (33, 4), (257, 2), (408, 1)):
+        m = torch.randn(b, n, n, generator=g, dtype=torch.float64)
+        m = m @ m.transpose(1, 2) / n + 0.05 * torch.eye(n, dtype=torch.float64)
+        got = nat.spd_inverse(m.float().to(DEV)).double().cpu()
+        ref = torch.linalg.inv(m)
+        assert (got - ref).abs().max() / ref.abs().max() < 2e-4, n
+        assert (got @ m - torch.eye(n, dtype=torch.float64)).abs().max() < 2e-3, n
+
+
 # --------------------------------------------------------------------------------- Laughlin (analytic, pinned)
 LAUGHLIN_CASES = [(3, 6), (4, 9), (5, 12), (6, 15)]  # (N, flux = 3 (N - 1)): the 1/3 Laughlin state
 
