@@ -91,6 +91,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->tc_f16 = 0;
     p->tc_merged = 0;
     p->a_planes = 0;
+    p->ln_fuse = 0;
     p->ee_par = p->ee_anti = -1;
     for (int t = 0; t < 4; ++t) p->orb_k[t] = p->orb_b[t] = -1;
     p->off_W0 = -1;
@@ -221,6 +222,8 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     // contractions 13.9 -> 13.1 ms, but attention +3.2 ms and LayerNorm +1.5 ms (8-byte plane stores), a net loss.
     const char* apl = getenv("DH_A_PLANES");
     p->a_planes = (p->gemm_impl == 1 && p->tc_f16 && D == 256 && p->nl > 0 && apl && std::string(apl) == "1") ? 1 : 0;
+    const char* lnf = getenv("DH_LN_FUSE");
+    p->ln_fuse = (p->gemm_impl == 1 && p->tc_f16 && p->tc_merged && D == 256 && !p->a_planes && lnf && std::string(lnf) == "1") ? 1 : 0;
     size_t off = 0;
     auto slot = [&](int Nout, bool has_bias) {
       dh_plan::Slot sl;
@@ -364,18 +367,30 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       if (rc) return rc; }
     if (p->gemm_impl == 1) {
       // MHA out-projection and the bias-free Dense that follows it are one linear map (Wo W1, bo W1)
-      if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s, pl))) return rc;
+      const bool lnf0 = jets && p->ln_fuse && R == 32 && !pl && rows % 128 == 0 && !(l == 0 && h0_comp);
+      if (lnf0) {
+        const LnArgs la{P + o.ln0_s, P + o.ln0_b, 0};
+        if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.h, rows, D, R, s, false, &la))) return rc;  // h = LN0(h + att Wod + bod)
+      } else if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s, pl))) return rc;
     } else {
       if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
       if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
     }
+    // R == 32 (N = 12): a 128-row tile holds whole electrons in whole warps, and the LayerNorm that follows a 256-wide
+    // contraction runs as its epilogue (gemm_tc.cu, LNF) -- the contraction's output never goes to HBM
+    const bool lnf = jets && p->ln_fuse && R == 32 && !pl && rows % 128 == 0;
     { ProfScope ps(p, PC_LAYERNORM, 0, s);
       if (l == 0 && h0_comp) rc = residual_layernorm_ex(w.t1, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 1, 0, pl ? 1 : 0, s);
-      else rc = residual_layernorm_ex(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 0, pl ? 1 : 0, pl ? 1 : 0, s);
+      else if (!lnf) rc = residual_layernorm_ex(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 0, pl ? 1 : 0, pl ? 1 : 0, s);
       if (rc) return rc; }
-    if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s, pl))) return rc;
-    { ProfScope ps(p, PC_LAYERNORM, 0, s);
-      if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
+    if (lnf) {
+      const LnArgs la{P + o.ln1_s, P + o.ln1_b, 1};
+      if ((rc = dense_tc(p, w.h, l * SL_PER_LAYER + SL_D2, w.h, rows, D, R, s, false, &la))) return rc;  // h = LN1(h + tanh(h W2 + b2))
+    } else {
+      if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s, pl))) return rc;
+      { ProfScope ps(p, PC_LAYERNORM, 0, s);
+        if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
+    }
   }
   if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s, pl))) return rc;
   ProfScope pst(p, PC_TAIL, 0, s, 3);

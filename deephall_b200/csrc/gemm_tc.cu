@@ -225,6 +225,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+// explicit shared-space accesses (pointers derived from the aligned dynamic shared-memory base are generic to the compiler)
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]), "f"(v[19]),
+        "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]), "f"(v[28]), "f"(v[29]),
+        "f"(v[30]), "f"(v[31])
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -238,14 +266,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // tma_store != 0: C is written through tmC (box 32 x 32 floats, 128B swizzle); otherwise (ldc not a
 // multiple of 4 floats, or misaligned C) by direct global stores.
 // PAIR (fp16 pieces, merged accumulator): clusters of two CTAs run `tcgen05.mma.cta_group::2` -- see the helpers above.
-template <bool F16, bool MERGED, bool PAIR>
+// LNF (pair form, N = 256, 32 jet rows per electron): the epilogue is the LayerNorm that follows the contraction --
+// out = LN(res + acc) or LN(res + tanh(acc + bias)) with forward-Laplacian jets -- see the epilogue.
+struct LnFuse {
+  const float* res;    // residual = output tensor [M][ldc] (in place)
+  const float* gamma;  // LayerNorm scale [256]
+  const float* beta;   // LayerNorm bias  [256]
+  int tanh_mode;
+};
+
+template <bool F16, bool MERGED, bool PAIR, bool LNF>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
                int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
-               int a_pre, int res, unsigned long long* __restrict__ prof) {
+               int a_pre, int res, LnFuse ln, unsigned long long* __restrict__ prof) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
@@ -253,12 +290,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   //                operand rows of 64 B (SWIZZLE_64B).
   //                PAIR:        [A hi 8 KB | A lo 8 KB | B hi 8 KB | B lo 8 KB]: this CTA's 128 of the tile's 256 weight rows.
   static_assert(!PAIR || (F16 && MERGED), "the CTA-pair form exists for fp16 pieces with the merged accumulator");
-  constexpr int STAGES = PAIR ? 6 : (F16 ? 4 : 2);
+  static_assert(!LNF || PAIR, "the fused LayerNorm epilogue exists for the pair form");
+  constexpr int STAGES = PAIR ? (LNF ? 5 : 6) : (F16 ? 4 : 2);  // LNF: the sixth stage's 32 KB are the epilogue's scratch
   constexpr int ROW_BYTES = F16 ? 64 : 128;            // operand tile row = BLOCK_K pieces
   constexpr int AP_BYTES = BLOCK_M * ROW_BYTES;        // one A piece tile
   constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * ROW_BYTES;  // one B piece tile (PAIR: this CTA's half)
   constexpr int STAGE_BYTES = 2 * AP_BYTES + 2 * B_BYTES;
-  static_assert(STAGES * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
+  static_assert((STAGES + (LNF ? 1 : 0)) * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
   constexpr int A_TX_BYTES = A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -631,6 +669,214 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long te0 = (prof && lead) ? clock64() : 0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * BLOCK_N;
+      if constexpr (LNF) {
+        // ---------------------------------------------------------------- fused residual + (tanh) + LayerNorm with jets
+        // The 32 rows of an electron (value | 24 J | S | 3 D | 3 T, common.cuh::Rows with N = 12) are the 32 lanes of
+        // this warp's TMEM quarter; two warps share a quarter and split the 8 column chunks.  Pass A builds
+        // x_r = res_r + jet of f(acc_r), stores it back into the accumulator and sums the row statistics; pass B
+        // reads x back, normalises with the jet rules of residual_layernorm_kernel and stores through the staging
+        // buffer.  Everything that couples ROWS at a fixed column (sum_k b_k^2, b_D^2 for tanh; sum_k c_k rho_k,
+        // c_D rho_D for the S / T rows) goes through the 32 x 32 staging tile: rows in, lane = column out.
+        // All shared-memory traffic uses explicit ld/st.shared with 16-byte broadcasts (the epilogue is issue-bound).
+        const bool isJ = lane >= 1 && lane <= 24, isS = lane == 25, isT = lane >= 29;
+        const int xr = isS ? 0 : (isT ? lane - 28 : -1);                      // which extra vector this row takes, if any
+        const uint32_t stg = smem_u32(buf);                                    // 32 x 32 staging tile, 128B-swizzled rows
+        auto st_row = [&](int k, int piece) { return stg + (uint32_t)(k * 128 + ((piece ^ (k & 7)) << 4)); };  // 16-byte piece
+        auto st_el = [&](int k, int vcol) { return stg + (uint32_t)(k * 128 + ((((vcol >> 2) ^ (k & 7)) << 4) | ((vcol & 3) << 2))); };
+        const uint32_t vec = smem_base + (uint32_t)(STAGES * STAGE_BYTES) + (uint32_t)(warp - EPI_WARP0) * 640u;  // bc[32] | ex[4][32]
+        const uint32_t xch = smem_base + (uint32_t)(STAGES * STAGE_BYTES) + 8u * 640u + (uint32_t)((tl & 1) * 4 + q) * 768u;
+        // gamma | beta | bias (256 floats each) live in shared memory: read with 16-byte broadcasts instead of __ldg
+        // (global loads between the shared-memory asm blocks cannot be hoisted and expose their latency 8x per chunk)
+        const uint32_t gbb = smem_base + (uint32_t)(STAGES * STAGE_BYTES) + 8u * 640u + 8u * 768u;
+        if (tl == 0) {
+          const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
+          sts32(gbb + 4u * et, __ldg(ln.gamma + et));
+          sts32(gbb + 1024u + 4u * et, __ldg(ln.beta + et));
+          sts32(gbb + 2048u + 4u * et, bias != nullptr ? __ldg(bias + et) : 0.f);
+          asm volatile("bar.sync 6, 256;" ::: "memory");
+        }
+        const bool mvalid = m < M;
+        const float* rrow = ln.res + (mvalid ? m : 0) * ldc;
+        float s_x = 0.f, s_xx = 0.f, s_x0x = 0.f;
+        auto stage_free = [&]() {  // the previous TMA store of this warp has read the staging tile
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+        };
+        // lane 0's 32 values -> every lane (through bc)
+        auto bcast32 = [&](float (&dst)[32], const float (&src)[32]) {
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128(vec + 16 * j, make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]));
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 f = lds128(vec + 16 * j);
+            dst[4 * j] = f.x; dst[4 * j + 1] = f.y; dst[4 * j + 2] = f.z; dst[4 * j + 3] = f.w;
+          }
+          __syncwarp();
+        };
+        // ---- pass A
+#pragma unroll 1
+        for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          // the residual line of this row for the NEXT chunk -> L1 (a thread reads one 128-byte line per chunk; without
+          // the prefetch every chunk exposes a full L2 round trip)
+          if (mvalid && c0 + 2 * EPI_CHUNK < BLOCK_N) asm volatile("prefetch.global.L1 [%0];" ::"l"(rrow + c0 + 2 * EPI_CHUNK));
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a4 = mvalid ? *reinterpret_cast<const float4*>(rrow + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[4 * j] = a4.x; x[4 * j + 1] = a4.y; x[4 * j + 2] = a4.z; x[4 * j + 3] = a4.w;
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (ln.tanh_mode) {
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(v[j]) * inv_scale;
+            if (lane == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = lds128(gbb + 2048u + 4u * c0 + 16u * j);
+                t[4 * j] += b4.x; t[4 * j + 1] += b4.y; t[4 * j + 2] += b4.z; t[4 * j + 3] += b4.w;
+              }
+            }
+            // stage the b rows; lane = column then takes tanh of the value row and the column sums of squares
+            stage_free();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts128(st_row(lane, j), make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]));
+            __syncwarp();
+            const float th_l = tanhf(lds32(st_el(0, lane)));
+            float bs = 0.f;
+#pragma unroll
+            for (int k = 1; k <= 24; ++k) { const float bk = lds32(st_el(k, lane)); bs = fmaf(bk, bk, bs); }
+            sts32(vec + 4 * lane, th_l);
+            sts32(vec + 128 + 4 * lane, bs);
+#pragma unroll
+            for (int a3 = 0; a3 < 3; ++a3) { const float bd = lds32(st_el(26 + a3, lane)); sts32(vec + 256 + 128 * a3 + 4 * lane, bd * bd); }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 th4 = lds128(vec + 16 * j);
+              const float4 e4 = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              const float thv[4] = {th4.x, th4.y, th4.z, th4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float t1 = fmaf(-thv[u], thv[u], 1.f), t2 = -2.f * thv[u] * t1;
+                x[4 * j + u] = lane == 0 ? x[4 * j + u] + thv[u] : fmaf(t2, ev[u], fmaf(t1, t[4 * j + u], x[4 * j + u]));
+              }
+            }
+            __syncwarp();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(v[j]), inv_scale, x[j]);
+            if (lane == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = lds128(gbb + 2048u + 4u * c0 + 16u * j);
+                x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+              }
+            }
+          }
+          // statistics: sum x, sum x^2, sum x_0 x (x_0 = the value row of this electron)
+          float x0[32];
+          bcast32(x0, x);
+          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, p4 = 0.f, p5 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            p0 += x[j]; p1 += x[j + 1];
+            p2 = fmaf(x[j], x[j], p2); p3 = fmaf(x[j + 1], x[j + 1], p3);
+            p4 = fmaf(x0[j], x[j], p4); p5 = fmaf(x0[j + 1], x[j + 1], p5);
+          }
+          s_x += p0 + p1; s_xx += p2 + p3; s_x0x += p4 + p5;
+          tmem_st32(tbase + (uint32_t)c0, x);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // ---- the two warps of the quarter exchange their halves of the row sums
+        sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u, s_x);
+        sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u + 4u, s_xx);
+        sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u + 8u, s_x0x);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        s_x += lds32(xch + (uint32_t)((1 - chalf) * 32 + lane) * 12u);
+        s_xx += lds32(xch + (uint32_t)((1 - chalf) * 32 + lane) * 12u + 4u);
+        s_x0x += lds32(xch + (uint32_t)((1 - chalf) * 32 + lane) * 12u + 8u);
+        constexpr float invD = 1.f / 256.f;
+        const float mu = s_x * invD;
+        const float mu0 = __shfl_sync(0xffffffffu, mu, 0);
+        const float var = fmaxf(__shfl_sync(0xffffffffu, s_xx, 0) * invD - mu0 * mu0, 0.f) + 1e-5f;
+        const float rho0 = rsqrtf(var), rho1 = -0.5f * rho0 / var, rho2 = 0.75f * rho0 / (var * var);
+        const float m_r = s_x0x * invD - mu0 * mu;  // mean(c_0 c_r)
+        const float q_r = s_xx * invD - mu * mu;    // mean(c_r^2)
+        const float v_r = 2.f * m_r;
+        float rho_r = rho1 * v_r;
+        const float sum_q = warp_sum(isJ ? q_r : 0.f), sum_vv = warp_sum(isJ ? v_r * v_r : 0.f);
+        const float vD = __shfl_sync(0xffffffffu, v_r, (lane + 29) & 31), qD = __shfl_sync(0xffffffffu, q_r, (lane + 29) & 31);
+        if (isS) rho_r = rho1 * (v_r + 2.f * sum_q) + rho2 * sum_vv;
+        if (isT) rho_r = rho1 * (v_r + 2.f * qD) + rho2 * vD * vD;
+        if (lane == 0) rho_r = 0.f;
+        const float rho_first = (isJ || (lane >= 26 && lane <= 28)) ? rho1 * v_r : 0.f;  // rho of a first-order row
+        // ---- pass B
+#pragma unroll 1
+        for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 2 * EPI_CHUNK >= BLOCK_N) {  // last read of this accumulator
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader(tmem_empty_bar(ab)));
+          }
+          if (c0 + 2 * EPI_CHUNK >= BLOCK_N && tk + 1 < my_tiles) {  // first residual line of the next tile
+            const int64_t mn = band_of(tk + 1) * BLOCK_M + row;
+            if (mn < M) asm volatile("prefetch.global.L1 [%0];" ::"l"(ln.res + mn * ldc + chalf * EPI_CHUNK));
+          }
+          float c[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) c[j] = __uint_as_float(v[j]) - mu;
+          stage_free();
+          // products c_r rho_r of the first-order rows -> staging tile; lane = column sums them (S) / picks them (T)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts128(st_row(lane, j), make_float4(c[4 * j] * rho_first, c[4 * j + 1] * rho_first, c[4 * j + 2] * rho_first, c[4 * j + 3] * rho_first));
+          float c0v[32];
+          bcast32(c0v, c);  // (its __syncwarp also publishes the staged products)
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int k = 1; k <= 24; k += 2) { a0 += lds32(st_el(k, lane)); a1 += lds32(st_el(k + 1, lane)); }
+          sts32(vec + 128 + 4 * lane, a0 + a1);
+#pragma unroll
+          for (int a3 = 0; a3 < 3; ++a3) sts32(vec + 256 + 128 * a3 + 4 * lane, lds32(st_el(26 + a3, lane)));
+          __syncwarp();
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 e4 = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 g4 = lds128(gbb + 4u * c0 + 16u * j);
+            const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              y[4 * j + u] = gv[u] * fmaf(2.f, ev[u], fmaf(c0v[4 * j + u], rho_r, c[4 * j + u] * rho0));
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b4 = lds128(gbb + 1024u + 4u * c0 + 16u * j);
+              y[4 * j] += b4.x; y[4 * j + 1] += b4.y; y[4 * j + 2] += b4.z; y[4 * j + 3] += b4.w;
+            }
+          }
+          __syncwarp();  // every lane has read the staged products before the tile is overwritten with the outputs
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sts128(st_row(lane, j), make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, stg, n0 + c0, (int)(m0 + q * 32));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        continue;
+      }
       bool released = false;
       for (int c0 = chalf * EPI_CHUNK; c0 < n_tile; c0 += 2 * EPI_CHUNK) {
         uint32_t v[32];
@@ -1142,6 +1388,7 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.rpg = rpg; g.f16 = f16; g.merged = merged; g.reduce_add = 0;
   g.a_scale = nullptr;
   g.A_lo = nullptr;
+  g.ln_res = nullptr; g.ln_gamma = nullptr; g.ln_beta = nullptr; g.ln_tanh = 0;
   return gemm_tc_ex(g, stream);
 }
 
@@ -1172,11 +1419,12 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -1213,6 +1461,13 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   // resident A (pair form): K <= 256 and more than one column tile per band; DH_GEMM_RES=0 disables
   static const bool res_env = !(getenv("DH_GEMM_RES") && atoi(getenv("DH_GEMM_RES")) == 0);
   const int res = (pair && res_env && K <= 8 * tc::BLOCK_K && N > tc::BLOCK_N) ? 1 : 0;
+  // fused LayerNorm epilogue: pair form, one 256-wide column tile, 32 jet rows per electron, TMA-stored output
+  tc::LnFuse lnf;
+  lnf.res = gm.ln_res; lnf.gamma = gm.ln_gamma; lnf.beta = gm.ln_beta; lnf.tanh_mode = gm.ln_tanh;
+  const bool ln_on = gm.ln_res != nullptr;
+  if (ln_on && !(pair && N == tc::BLOCK_N && rpg == 32 && tma_store && !reduce_add && gm.a_scale == nullptr && M % 32 == 0 &&
+                 (reinterpret_cast<uintptr_t>(gm.ln_res) & 15) == 0))
+    return -2;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = grid;
@@ -1227,9 +1482,12 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   lc.attrs = lattr;
   lc.numAttrs = 1;
   cudaError_t le;
-#define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
-                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, prof)
-  if (pair) DH_LAUNCH_TC(true, true, true);
+#define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR, false>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
+                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof)
+  if (ln_on)
+    le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<true, true, true, true>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K,
+                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof);
+  else if (pair) DH_LAUNCH_TC(true, true, true);
   else if (f16) { if (merged) DH_LAUNCH_TC(true, true, false); else DH_LAUNCH_TC(true, false, false); }
   else { if (merged) DH_LAUNCH_TC(false, true, false); else DH_LAUNCH_TC(false, false, false); }
 #undef DH_LAUNCH_TC

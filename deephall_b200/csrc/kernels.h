@@ -29,6 +29,9 @@ struct TcGemm {
   float* C; int64_t ldc;
   int64_t M; int N, K, rpg, f16, merged, reduce_add;
   const float* a_scale;  // optional device {s, 1/s}: A is multiplied by s before the split, C by 1/s
+  // fused LayerNorm epilogue (jet passes, pair form, N = 256, rpg = 32): C = LN(ln_res + acc) or LN(ln_res + tanh(acc + bias))
+  // with the jet rules of residual_layernorm_kernel, written in place over ln_res (= C); null = off
+  const float* ln_res; const float* ln_gamma; const float* ln_beta; int ln_tanh;
   const void* A_lo;      // non-null (fp16 pieces only): A and A_lo are fp16 hi / lo planes [M][lda] written by the
                          // producing kernel; the in-kernel split is skipped
 };

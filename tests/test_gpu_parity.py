@@ -329,6 +329,31 @@ def test_tcgen05_path_matches_simt_path(nat, monkeypatch):
         assert d.real.abs().max().item() < 1e-4 and phase_diff(d.imag.cpu().double(), torch.zeros(40, dtype=torch.float64)).abs().max() < 1e-4
 
 
+def test_layernorm_fused_into_the_contraction_epilogue(nat, monkeypatch):
+    """DH_LN_FUSE=1 (experimental, N = 12 only): residual + (tanh) + LayerNorm with jets as the epilogue of the 256-wide
+    contractions (accumulators normalised in tensor memory, the contraction's output never goes to HBM) against the
+    separate LayerNorm kernels and the fp64 oracle."""
+    cfg = OP.NetCfg(**CONFIGS["c3"])
+    p64 = OP.init_params(cfg, 2, torch.float64, 0.1)
+    flat32 = OP.flatten_params(p64).float()
+    p64 = OP.unflatten_params(flat32.double(), cfg)
+    flat = flat32.to(DEV)
+    outs = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DH_LN_FUSE", mode)
+        plan = make_plan(nat, cfg)
+        x = plan.init_walkers(24, seed=11)
+        plan.mcmc_sweep(flat, x, 20, 0.2, seed=1)
+        outs[mode] = plan.local_energy(flat, x)
+    monkeypatch.delenv("DH_LN_FUSE")
+    for k in ("energy", "kinetic", "angular_momentum_square", "angular_momentum_z"):
+        a, b = outs["1"][k], outs["0"][k]
+        assert ((a - b).abs() / b.abs().clamp(min=1.0)).median().item() < 2e-6, k
+    ref = OJ.local_energy(p64, x.double().cpu(), cfg)["energy"]
+    rel = (outs["1"]["energy"].cpu().to(torch.complex128) - ref).abs() / ref.abs()
+    assert rel.median() < TOL_MEDIAN and rel.max() < 5e-3
+
+
 # --------------------------------------------------------------------------------- MCMC
 def test_mcmc_proposal_and_decisions(nat):
     cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c2"], 256, burn=0)
