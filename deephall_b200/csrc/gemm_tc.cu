@@ -228,12 +228,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 // explicit shared-space accesses (pointers derived from the aligned dynamic shared-memory base are generic to the compiler)
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ float lds32(uint32_t a) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
@@ -750,21 +750,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const float th_l = tanhf(lds32(st_el(0, lane)));
             float bs = 0.f;
 #pragma unroll
-            for (int k = 1; k <= 24; ++k) { const float bk = lds32(st_el(k, lane)); bs = fmaf(bk, bk, bs); }
+            for (int k0 = 1; k0 <= 24; k0 += 8) {  // eight loads in flight before the first is used
+              float bk[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) bk[u] = lds32(st_el(k0 + u, lane));
+#pragma unroll
+              for (int u = 0; u < 8; ++u) bs = fmaf(bk[u], bk[u], bs);
+            }
             sts32(vec + 4 * lane, th_l);
             sts32(vec + 128 + 4 * lane, bs);
 #pragma unroll
             for (int a3 = 0; a3 < 3; ++a3) { const float bd = lds32(st_el(26 + a3, lane)); sts32(vec + 256 + 128 * a3 + 4 * lane, bd * bd); }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 th4 = lds128(vec + 16 * j);
-              const float4 e4 = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              const float thv[4] = {th4.x, th4.y, th4.z, th4.w}, ev[4] = {e4.x, e4.y, e4.z, e4.w};
+            for (int j0 = 0; j0 < 8; j0 += 4) {
+              float4 th4[4], e4[4];
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float t1 = fmaf(-thv[u], thv[u], 1.f), t2 = -2.f * thv[u] * t1;
-                x[4 * j + u] = lane == 0 ? x[4 * j + u] + thv[u] : fmaf(t2, ev[u], fmaf(t1, t[4 * j + u], x[4 * j + u]));
+              for (int jj = 0; jj < 4; ++jj) {
+                th4[jj] = lds128(vec + 16 * (j0 + jj));
+                e4[jj] = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * (j0 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const int j = j0 + jj;
+                const float thv[4] = {th4[jj].x, th4[jj].y, th4[jj].z, th4[jj].w}, ev[4] = {e4[jj].x, e4[jj].y, e4[jj].z, e4[jj].w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float t1 = fmaf(-thv[u], thv[u], 1.f), t2 = -2.f * thv[u] * t1;
+                  x[4 * j + u] = lane == 0 ? x[4 * j + u] + thv[u] : fmaf(t2, ev[u], fmaf(t1, t[4 * j + u], x[4 * j + u]));
+                }
               }
             }
             __syncwarp();
@@ -843,20 +857,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bcast32(c0v, c);  // (its __syncwarp also publishes the staged products)
           float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int k = 1; k <= 24; k += 2) { a0 += lds32(st_el(k, lane)); a1 += lds32(st_el(k + 1, lane)); }
+          for (int k0 = 1; k0 <= 24; k0 += 8) {  // eight loads in flight before the first is used
+            float wk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wk[u] = lds32(st_el(k0 + u, lane));
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) { a0 += wk[u]; a1 += wk[u + 1]; }
+          }
           sts32(vec + 128 + 4 * lane, a0 + a1);
 #pragma unroll
           for (int a3 = 0; a3 < 3; ++a3) sts32(vec + 256 + 128 * a3 + 4 * lane, lds32(st_el(26 + a3, lane)));
           __syncwarp();
           float y[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 e4 = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 g4 = lds128(gbb + 4u * c0 + 16u * j);
-            const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+          for (int j0 = 0; j0 < 8; j0 += 4) {
+            float4 e4[4], g4[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              y[4 * j + u] = gv[u] * fmaf(2.f, ev[u], fmaf(c0v[4 * j + u], rho_r, c[4 * j + u] * rho0));
+            for (int jj = 0; jj < 4; ++jj) {
+              e4[jj] = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * (j0 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              g4[jj] = lds128(gbb + 4u * c0 + 16u * (j0 + jj));
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j0 + jj;
+              const float ev[4] = {e4[jj].x, e4[jj].y, e4[jj].z, e4[jj].w}, gv[4] = {g4[jj].x, g4[jj].y, g4[jj].z, g4[jj].w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                y[4 * j + u] = gv[u] * fmaf(2.f, ev[u], fmaf(c0v[4 * j + u], rho_r, c[4 * j + u] * rho0));
+            }
           }
           if (lane == 0) {
 #pragma unroll
