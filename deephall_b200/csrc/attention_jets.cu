@@ -315,12 +315,15 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
           axpy4(acc[4], w * a1.x, v); axpy4(acc[5], w * a1.y, v); axpy4(acc[6], w * a1.z, v); axpy4(acc[7], w * a1.w, v);
           axpy4(acc[8], w * a2.x, v); axpy4(acc[9], w * a2.y, v); axpy4(acc[10], w * a2.z, v); axpy4(acc[11], w * a2.w, v);
         };
-        for (int j = 0; j < N; ++j) {
-          axpy12(sj + SJ(0, j, r), 1.f, staged(vsub, j * RI, fh));
-          if (r != 0 && (!L0 || !isJ || j == jown)) {
-            axpy12(sj + SJ(0, j, 0), 1.f, staged(vsub, j * RI + rin, fh));
-            if (isT) axpy12(sj + SJ(0, j, rd), 2.f, staged(vsub, j * RI + rdin, fh));
-          }
+        // (the row-dependent terms are separate loops: one branch per thread instead of one per key, and in the
+        // first-layer form an own-flow row touches a single key)
+        for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, r), 1.f, staged(vsub, j * RI, fh));
+        if (L0 && isJ) {
+          axpy12(sj + SJ(0, jown, 0), 1.f, staged(vsub, jown * RI + rin, fh));
+        } else if (r != 0) {
+          for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, 0), 1.f, staged(vsub, j * RI + rin, fh));
+          if (isT)
+            for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, rd), 2.f, staged(vsub, j * RI + rdin, fh));
         }
         const int dcol = (cp + c2) * AJ_CH + f4 * 4;
 #pragma unroll
