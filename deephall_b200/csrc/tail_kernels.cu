@@ -773,44 +773,42 @@ __device__ inline PairTerms pair_terms(const float* __restrict__ xw, int N, int 
   float jas = 0.f, jasS = 0.f, coul = 0.f, harm = 0.f;
   jJ0 = 0.f; jJ1 = 0.f;
   const float a_par = ee_par ? ee_par[0] : 0.f, a_anti = ee_anti ? ee_anti[0] : 0.f;
+  // every lane evaluates the trigonometry of ITS electron once; the partners' unit vectors come by shuffle
+  float st = 0.f, ct = 1.f, sp = 0.f, cp = 1.f;
   if (lane < N) {
-    float st, ct, sp, cp;
     sincosf(xw[lane * 2], &st, &ct);
     sincosf(xw[lane * 2 + 1], &sp, &cp);
-    const float rx = st * cp, ry = st * sp, rz = ct;
-    // tangent-flow velocities of r_i: theta_hat x r = -phi_hat ; phi_hat x r = theta_hat
-    const float w0x = sp, w0y = -cp, w0z = 0.f;
-    const float w1x = ct * cp, w1y = ct * sp, w1z = -st;
-    for (int j = 0; j < N; ++j) {
-      if (j == lane) continue;
-      float sj, cj, spj, cpj;
-      sincosf(xw[j * 2], &sj, &cj);
-      sincosf(xw[j * 2 + 1], &spj, &cpj);
-      const float qx = sj * cpj, qy = sj * spj, qz = cj;
-      const float dx = rx - qx, dy = ry - qy, dz = rz - qz;
-      const float r2 = dx * dx + dy * dy + dz * dz;
-      const float r = sqrtf(r2);
-      const float cth = 1.f - 0.5f * r2;  // cos(theta_12)
-      const bool par = (lane < n_up) == (j < n_up);
-      if (par ? ee_par != nullptr : ee_anti != nullptr) {
-        // f(r) = -w a^2/(a+r), w = 1/4 (parallel) or 1/2 (anti-parallel) ;  c = r_i.r_j ; dr/dc = -1/r ; d2r/dc2 = -1/r^3
-        const float alpha = par ? a_par : a_anti, w = par ? 0.25f : 0.5f;
-        const float ar = alpha + r;
-        const float fr = w * alpha * alpha / (ar * ar);                // df/dr
-        const float frr = -2.f * w * alpha * alpha / (ar * ar * ar);   // d2f/dr2
-        const float fc = -fr / r;                                      // df/dc
-        const float fcc = frr / r2 - fr / (r2 * r);                    // d2f/dc2
-        jJ0 = fmaf(fc, w0x * qx + w0y * qy + w0z * qz, jJ0);
-        jJ1 = fmaf(fc, w1x * qx + w1y * qy + w1z * qz, jJ1);
-        if (j > lane) {
-          jas += -w * alpha * alpha / ar;
-          jasS += fc * (-4.f * cth) + fcc * 2.f * (1.f - cth * cth);
-        }
-      }
+  }
+  const float rx = st * cp, ry = st * sp, rz = ct;
+  // tangent-flow velocities of r_i: theta_hat x r = -phi_hat ; phi_hat x r = theta_hat
+  const float w0x = sp, w0y = -cp, w0z = 0.f;
+  const float w1x = ct * cp, w1y = ct * sp, w1z = -st;
+  for (int j = 0; j < N; ++j) {
+    const float qx = __shfl_sync(0xffffffffu, rx, j), qy = __shfl_sync(0xffffffffu, ry, j), qz = __shfl_sync(0xffffffffu, rz, j);
+    if (lane >= N || j == lane) continue;
+    const float dx = rx - qx, dy = ry - qy, dz = rz - qz;
+    const float r2 = dx * dx + dy * dy + dz * dz;
+    const float r = sqrtf(r2);
+    const float cth = 1.f - 0.5f * r2;  // cos(theta_12)
+    const bool par = (lane < n_up) == (j < n_up);
+    if (par ? ee_par != nullptr : ee_anti != nullptr) {
+      // f(r) = -w a^2/(a+r), w = 1/4 (parallel) or 1/2 (anti-parallel) ;  c = r_i.r_j ; dr/dc = -1/r ; d2r/dc2 = -1/r^3
+      const float alpha = par ? a_par : a_anti, w = par ? 0.25f : 0.5f;
+      const float ar = alpha + r;
+      const float fr = w * alpha * alpha / (ar * ar);                // df/dr
+      const float frr = -2.f * w * alpha * alpha / (ar * ar * ar);   // d2f/dr2
+      const float fc = -fr / r;                                      // df/dc
+      const float fcc = frr / r2 - fr / (r2 * r);                    // d2f/dc2
+      jJ0 = fmaf(fc, w0x * qx + w0y * qy + w0z * qz, jJ0);
+      jJ1 = fmaf(fc, w1x * qx + w1y * qy + w1z * qz, jJ1);
       if (j > lane) {
-        coul += 1.f / r;
-        harm += 1.f + (Q + 1.f) / Q * cth;
+        jas += -w * alpha * alpha / ar;
+        jasS += fc * (-4.f * cth) + fcc * 2.f * (1.f - cth * cth);
       }
+    }
+    if (j > lane) {
+      coul += 1.f / r;
+      harm += 1.f + (Q + 1.f) / Q * cth;
     }
   }
   PairTerms out;
