@@ -72,6 +72,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!ok);
 }
+// wait with back-off: a warp that spins on try_wait issues instructions all the time and takes issue slots from the
+// warps that have work (the fused-LayerNorm epilogue shares its schedulers with eight waiting splitter warps)
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, bool cluster_scope, unsigned ns) {
+  uint32_t ok;
+  for (;;) {
+    if (cluster_scope)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    else
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(ns);
+  }
+}
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {  // non-blocking
   uint32_t ok;
   asm volatile(
@@ -403,13 +418,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   unsigned long long pw[3] = {0, 0, 0}, pe[5] = {0, 0, 0, 0, 0};
   const long long t_begin = prof ? clock64() : 0;
   auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
-    if (prof) {
-      const long long t0 = clock64();
-      if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
-      pw[slot] += (unsigned long long)(clock64() - t0);
-    } else {
-      if (PAIR) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
-    }
+    const long long t0 = prof ? clock64() : 0;
+    if (LNF) mbar_wait_sleep(bar, parity, true, 256);  // the epilogue is the critical path: waiting roles back off
+    else if (PAIR) mbar_wait_cluster(bar, parity);
+    else mbar_wait(bar, parity);
+    if (prof) pw[slot] += (unsigned long long)(clock64() - t0);
   };
 
   if (warp == 0) {
@@ -593,7 +606,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = rs ? (it / RES_AR) & 1 : (it / STAGES) & 1;
         const uint32_t wbar = rs ? ra_full(rr) : full_bar(s);
         uint8_t* const stage_reg = rs ? smem + rr * 2 * AP_BYTES : smem + s * STAGE_BYTES;
-        if (t == 0) timed_wait(wbar, ph, 0); else mbar_wait(wbar, ph);
+        if (t == 0) timed_wait(wbar, ph, 0); else if (LNF) mbar_wait_sleep(wbar, ph, false, 256); else mbar_wait(wbar, ph);
         const long long ts0 = (prof && t == 0) ? clock64() : 0;
         if (F16) {
           // Two threads per tile row r: thread (r, h) converts the 16 floats k = 16h .. 16h+15 of the landed fp32
@@ -716,10 +729,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();
         };
+        long long lt0 = (prof && lead) ? clock64() : 0, lt1;
+#define DH_LNLAP(slot) if (prof && lead) { lt1 = clock64(); atomicAdd(prof + 22 + (slot), (unsigned long long)(lt1 - lt0)); lt0 = lt1; }
         // ---- pass A
 #pragma unroll 1
         for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
           uint32_t v[32];
+          DH_LNLAP(9)
           tmem_ld32(tbase + (uint32_t)c0, v);
           // the residual line of this row for the NEXT chunk -> L1 (a thread reads one 128-byte line per chunk; without
           // the prefetch every chunk exposes a full L2 round trip)
@@ -731,6 +747,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             x[4 * j] = a4.x; x[4 * j + 1] = a4.y; x[4 * j + 2] = a4.z; x[4 * j + 3] = a4.w;
           }
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          DH_LNLAP(0)
           if (ln.tanh_mode) {
             float t[32];
 #pragma unroll
@@ -793,6 +810,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          DH_LNLAP(1)
           // statistics: sum x, sum x^2, sum x_0 x (x_0 = the value row of this electron)
           float x0[32];
           bcast32(x0, x);
@@ -804,9 +822,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             p4 = fmaf(x0[j], x[j], p4); p5 = fmaf(x0[j + 1], x[j + 1], p5);
           }
           s_x += p0 + p1; s_xx += p2 + p3; s_x0x += p4 + p5;
+          DH_LNLAP(2)
           tmem_st32(tbase + (uint32_t)c0, x);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        DH_LNLAP(3)
         // ---- the two warps of the quarter exchange their halves of the row sums
         sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u, s_x);
         sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u + 4u, s_xx);
@@ -830,12 +850,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (isT) rho_r = rho1 * (v_r + 2.f * qD) + rho2 * vD * vD;
         if (lane == 0) rho_r = 0.f;
         const float rho_first = (isJ || (lane >= 26 && lane <= 28)) ? rho1 * v_r : 0.f;  // rho of a first-order row
+        DH_LNLAP(4)
         // ---- pass B
 #pragma unroll 1
         for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
           uint32_t v[32];
+          DH_LNLAP(9)
           tmem_ld32(tbase + (uint32_t)c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          DH_LNLAP(5)
           if (c0 + 2 * EPI_CHUNK >= BLOCK_N) {  // last read of this accumulator
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -849,6 +872,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 32; ++j) c[j] = __uint_as_float(v[j]) - mu;
           stage_free();
+          DH_LNLAP(6)
           // products c_r rho_r of the first-order rows -> staging tile; lane = column sums them (S) / picks them (T)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -893,6 +917,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               y[4 * j] += b4.x; y[4 * j + 1] += b4.y; y[4 * j + 2] += b4.z; y[4 * j + 3] += b4.w;
             }
           }
+          DH_LNLAP(7)
           __syncwarp();  // every lane has read the staged products before the tile is overwritten with the outputs
 #pragma unroll
           for (int j = 0; j < 8; ++j) sts128(st_row(lane, j), make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]));
@@ -902,6 +927,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_store_2d(&tmC, stg, n0 + c0, (int)(m0 + q * 32));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          DH_LNLAP(8)
         }
         continue;
       }
@@ -1482,8 +1508,8 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   unsigned long long* prof = nullptr;
   if (want_prof) {
     static unsigned long long* buf = nullptr;
-    if (!buf) cudaMalloc(&buf, 32 * sizeof(unsigned long long));
-    cudaMemsetAsync(buf, 0, 32 * sizeof(unsigned long long), stream);
+    if (!buf) cudaMalloc(&buf, 40 * sizeof(unsigned long long));
+    cudaMemsetAsync(buf, 0, 40 * sizeof(unsigned long long), stream);
     prof = buf;
   }
   // resident A (pair form): K <= 256 and more than one column tile per band; DH_GEMM_RES=0 disables
@@ -1521,9 +1547,14 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
 #undef DH_LAUNCH_TC
   if (le != cudaSuccess) return (int)le;
   if (want_prof) {
-    unsigned long long h[32];
+    unsigned long long h[40];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+    if (ln_on)
+      fprintf(stderr, "[gemm_tc LN epilogue, tanh=%d] per CTA cycles: A tmem ld %.0f | A build x %.0f | A stats %.0f | A st wait %.0f | exchange %.0f | "
+              "B tmem ld %.0f | B stage_free %.0f | B sums + y %.0f | B store %.0f | between %.0f\n", gm.ln_tanh,
+              h[22] / (double)grid.x, h[23] / (double)grid.x, h[24] / (double)grid.x, h[25] / (double)grid.x, h[26] / (double)grid.x,
+              h[27] / (double)grid.x, h[28] / (double)grid.x, h[29] / (double)grid.x, h[30] / (double)grid.x, h[31] / (double)grid.x);
     const double g = (double)grid.x, tp = (double)tiles / g;
     fprintf(stderr, "[gemm_tc M=%lld N=%d f16=%d] per CTA: tiles %.1f | total cyc %.0f | producer wait empty %.0f | "
             "mma wait tmem_empty %.0f full %.0f split %.0f | splitter wait full %.0f work %.0f | epi wait tmem_full %.0f drain %.0f "
