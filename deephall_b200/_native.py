@@ -35,6 +35,7 @@ class dh_config(C.Structure):
         ("network_type", C.c_int32),
         ("cf_flux", C.c_int32),
         ("orbital_type", C.c_int32),
+        ("excitation_lz", C.c_float),
     ]
 
 
@@ -135,7 +136,7 @@ class Plan:
 
     def __init__(self, nspins=(3, 0), flux=2, ndets=1, num_heads=4, heads_dim=64, num_layers=2,
                  interaction_type="coulomb", interaction_strength=1.0, radius=None, chunk_walkers=0,
-                 network_type="psiformer", cf_flux=1, orbital_type="full"):
+                 network_type="psiformer", cf_flux=1, orbital_type="full", excitation_lz=0.0):
         _need_cuda()
         self.lib = load()
         self.cfg = dh_config(
@@ -143,7 +144,7 @@ class Plan:
             0 if str(interaction_type) == "coulomb" else 1, float(interaction_strength),
             float(radius) if radius else 0.0, int(chunk_walkers),
             1 if str(network_type) == "laughlin" else 0, int(cf_flux),
-            1 if str(orbital_type) == "sparse" else 0,
+            1 if str(orbital_type) == "sparse" else 0, float(excitation_lz),
         )
         self.N = int(nspins[0]) + int(nspins[1])
         self.R = 2 * self.N + 8

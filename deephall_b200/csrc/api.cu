@@ -74,14 +74,21 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->kf_dense0 = p->kf_eepar = p->kf_eeanti = -1;
   p->laughlin = cfg->network_type == 1 ? 1 : 0;
   p->twoQ1 = 0;
+  p->lskip = -1;
   if (cfg->network_type != 0 && cfg->network_type != 1) { delete p; return DH_E_BADARG; }
   if (p->N > 16 || p->D % 32 != 0 || p->D > 256 || p->hd % 4 != 0) { delete p; return DH_E_UNSUPPORTED; }
   if (p->laughlin) {
     // networks/laughlin.py:33-37: Q1 = flux/2 - p (N - 1); only the ground state N = 2 Q1 + 1 is built
     const int pf = cfg->cf_flux > 0 ? cfg->cf_flux : 1;
     p->twoQ1 = cfg->flux - 2 * pf * (p->N - 1);
-    if (p->twoQ1 != p->N - 1) { delete p; return DH_E_UNSUPPORTED; }
-    p->L = p->N;
+    p->lskip = -1;
+    if (p->twoQ1 == p->N) {  // quasihole (laughlin.py:38-41,73-83): the orbital m = -lz is left out of the N + 1
+      const double sk = 0.5 * p->twoQ1 - (double)cfg->excitation_lz;
+      const long ski = lround(sk);
+      if (fabs(sk - (double)ski) > 1e-6 || ski < 0 || ski > p->twoQ1) { delete p; return DH_E_BADARG; }
+      p->lskip = (int)ski;
+    } else if (p->twoQ1 != p->N - 1) { delete p; return DH_E_UNSUPPORTED; }  // (quasiparticle: N = 2 Q1 + 2, not built)
+    p->L = p->twoQ1 + 1;
     p->K = 1;
     p->nl = 0;
     p->LNK = p->L * p->N * p->K;
@@ -329,6 +336,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   if (p->laughlin) {
     // analytic Laughlin ground state: orbital-matrix jets straight from the coordinates, then the same tail
     TailDims tl{N, R, p->L, 1, p->twoQ1, p->cfg.n_up, 0};
+    tl.lskip = p->lskip;
     ProfScope pst(p, PC_TAIL, 0, s, 3);
     if ((rc = laughlin_orbital_jets(x, p->d_normfac, w.Mj, Bc, tl, s))) return rc;
     if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, tl, s))) return rc;

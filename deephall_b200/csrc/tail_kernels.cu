@@ -289,8 +289,10 @@ laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restri
   const dcplx jas = sc[0];
   Rows rw(N, R > 1);
   auto E = [&](int slot, int m) { const cplx e = env[slot * L + m]; return make_double2((double)e.x, (double)e.y); };
-  for (int t = tid; t < R * L; t += blockDim.x) {
-    const int r = t / L, m = t % L;
+  // columns: ground state a = 0 .. N-1; quasihole (laughlin.py:75-80): a = 0 .. skip-1, then 2Q1 down to skip+1
+  for (int t = tid; t < R * N; t += blockDim.x) {
+    const int r = t / N, col = t % N;
+    const int m = (dm.lskip < 0 || col < dm.lskip) ? col : dm.twoQ - (col - dm.lskip);
     const dcplx P = E(0, m);
     dcplx val;
     if (r == 0) val = dmul(P, jas);
@@ -306,14 +308,14 @@ laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restri
       val = dmul(acc, jas);
     } else if (r < rw.T(0)) val = dmul(E(4 + (r - rw.D(0)), m), jas);
     else val = dmul(E(7 + (r - rw.T(0)), m), jas);
-    float* dst = Mj + (((b * R + r) * N + i) * N + m) * 2;
+    float* dst = Mj + (((b * R + r) * N + i) * N + col) * 2;
     dst[0] = (float)val.x;
     dst[1] = (float)val.y;
   }
 }
 
 int laughlin_orbital_jets(const float* x, const double* ones, float* Mj, int64_t B, TailDims d, cudaStream_t s) {
-  if (d.L != d.N || d.K != 1) return -2;
+  if ((d.lskip < 0 ? d.L != d.N : d.L != d.N + 1) || d.K != 1) return -2;
   const size_t smem = (2 * (size_t)d.L + 8 * (size_t)d.N + 5) * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
   laughlin_orbital_jets_kernel<<<(unsigned)(B * d.N), 128, smem, s>>>(x, ones, Mj, d);
   return (int)cudaGetLastError();

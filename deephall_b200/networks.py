@@ -24,13 +24,14 @@ _PLANS: dict = {}
 
 def get_plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type="coulomb",
              interaction_strength=1.0, radius=None, chunk_walkers=0, network_type="psiformer", cf_flux=1,
-             orbital_type="full") -> _native.Plan:
+             orbital_type="full", excitation_lz=0.0) -> _native.Plan:
     key = (tuple(nspins), int(flux), ndets, num_heads, heads_dim, num_layers, str(interaction_type),
            float(interaction_strength), radius, chunk_walkers, str(network_type), int(cf_flux), str(orbital_type),
-           torch.cuda.current_device())
+           float(excitation_lz), torch.cuda.current_device())
     if key not in _PLANS:
         _PLANS[key] = _native.Plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type,
-                                   interaction_strength, radius, chunk_walkers, network_type, cf_flux, orbital_type)
+                                   interaction_strength, radius, chunk_walkers, network_type, cf_flux, orbital_type,
+                                   excitation_lz)
     return _PLANS[key]
 
 
@@ -54,20 +55,26 @@ class B200Network:
 
 
 class Laughlin(B200Network):
-    """Analytic Laughlin ground state (networks/laughlin.py:19-71), evaluated by the same tail kernels
+    """Analytic Laughlin ground state and quasihole (networks/laughlin.py:19-83), evaluated by the same tail kernels
     (log-determinant jets, local-energy assembly, Metropolis sweep).  It has no parameters."""
 
     def __init__(self, nspins, flux, cf_flux=1, excitation_lz=0):
         self.nspins = (int(nspins[0]), int(nspins[1]))
         self.flux = int(flux)
         self.cf_flux = int(cf_flux)
+        self.excitation_lz = float(excitation_lz)
         n = sum(self.nspins)
-        if self.nspins[1] != 0 or self.flux - 2 * self.cf_flux * (n - 1) != n - 1 or excitation_lz:
-            raise NotImplementedError("only the spin-polarised Laughlin ground state (N = 2 Q1 + 1) is built; "
-                                      "quasihole / quasiparticle states are a 'next' row (SURVEY 8f N3)")
+        two_q1 = self.flux - 2 * self.cf_flux * (n - 1)
+        if self.nspins[1] != 0 or two_q1 not in (n - 1, n):
+            raise NotImplementedError("the spin-polarised Laughlin ground state (N = 2 Q1 + 1) and quasihole (N = 2 Q1) are "
+                                      "built; the quasiparticle state is a 'next' row (SURVEY 8f N3)")
+        if two_q1 == n:  # laughlin.py:38-40,49-52
+            d = self.excitation_lz - two_q1 / 2
+            if abs(d - round(d)) > 1e-9 or abs(self.excitation_lz) > abs(two_q1 / 2):
+                raise AssertionError(f"Impossible Lz={self.excitation_lz} for excitation")
 
     def plan(self, system: System | None = None) -> _native.Plan:
-        kw = dict(network_type="laughlin", cf_flux=self.cf_flux)
+        kw = dict(network_type="laughlin", cf_flux=self.cf_flux, excitation_lz=self.excitation_lz)
         if system is None:
             return get_plan(self.nspins, self.flux, 1, 4, 64, 0, **kw)
         return get_plan(self.nspins, self.flux, 1, 4, 64, 0, system.interaction_type, system.interaction_strength,
@@ -158,7 +165,7 @@ class Psiformer(B200Network):
 def make_network(system: System, network: Network) -> B200Network:
     """networks/__init__.py:22-37."""
     if str(network.type) == "laughlin":
-        return Laughlin(system.nspins, system.flux)
+        return Laughlin(system.nspins, system.flux, excitation_lz=getattr(system, "lz_center", 0.0) or 0.0)
     ps = network.psiformer
     return Psiformer(
         Q=system.flux / 2,

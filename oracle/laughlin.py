@@ -1,4 +1,4 @@
-"""Torch-CPU restatement of deephall/networks/laughlin.py:59-71 (ground state only).
+"""Torch-CPU restatement of deephall/networks/laughlin.py:59-83 (ground state and quasihole).
 
 TEST INFRASTRUCTURE ONLY.  Used as an analytic oracle: the reference pins
 energy = 2.58... and L^2 = 0 for nspins [3,0], flux 6 (tests/cli_test.py:41-42).
@@ -10,20 +10,27 @@ import torch
 from .psiformer import slogdet_tail, spinors
 
 
-def laughlin_orbitals(x, flux: int, cf_flux: int = 1):
-    # laughlin.py:35-37,59-71 (full_orbitals)
+def laughlin_orbitals(x, flux: int, cf_flux: int = 1, excitation_lz: float = 0.0):
+    # laughlin.py:35-37,59-71 (full_orbitals) and :73-83 (quasihole_orbitals)
     N = x.shape[-2]
     Q1 = flux / 2 - cf_flux * (N - 1)
-    assert N == 2 * Q1 + 1, "only the Laughlin ground state is restated"
     u, v = spinors(x)
     u, v = u[..., None], v[..., None]
     twoQ1 = int(round(2 * Q1))
-    a = torch.arange(0, twoQ1 + 1)
+    if N == 2 * Q1 + 1:  # ground state: m = -Q .. Q  ->  exponents a = Q + m = 0 .. 2Q
+        a = torch.arange(0, twoQ1 + 1)
+    elif N == 2 * Q1:  # quasihole: m = -Q .. -lz-1, then Q, Q-1, .. -lz+1  (the orbital m = -lz is left out)
+        skip = Q1 - excitation_lz
+        assert abs(skip - round(skip)) < 1e-9 and -abs(Q1) <= excitation_lz <= abs(Q1)  # laughlin.py:49-52,39
+        skip = int(round(skip))
+        a = torch.cat([torch.arange(0, skip), torch.arange(twoQ1, skip, -1)])
+    else:
+        raise AssertionError("only the Laughlin ground state and quasihole are restated")
     eye = torch.eye(N, dtype=u.dtype)
     element = u * v[..., :, 0][..., None, :] - u[..., :, 0][..., None, :] * v + eye
     jas = element.prod(-1, keepdim=True)
     return u**a * v ** (twoQ1 - a) * jas
 
 
-def logpsi(x, flux: int):
-    return slogdet_tail(laughlin_orbitals(x, flux)[..., None, :, :])
+def logpsi(x, flux: int, cf_flux: int = 1, excitation_lz: float = 0.0):
+    return slogdet_tail(laughlin_orbitals(x, flux, cf_flux, excitation_lz)[..., None, :, :])

@@ -713,6 +713,34 @@ def test_laughlin_logpsi_and_local_energy_parity(nat, N, flux):
     assert out["angular_momentum_square"].abs().max().item() < 5e-3          # L = 0 state
 
 
+@pytest.mark.parametrize("N,lz", [(4, 1.0), (4, -2.0), (5, 0.5), (6, 3.0)])
+def test_laughlin_quasihole_parity(nat, N, lz):
+    """Laughlin quasihole (networks/laughlin.py:38-41,73-83: N = 2 Q1 electrons, the orbital m = -lz left out,
+    `excitation_lz = system.lz_center`): log psi, kinetic energy and angular momenta against the oracle's gradient +
+    Hessian route; the state is an L_z eigenstate with eigenvalue lz and a lowest-Landau-level state (KE = N/2)."""
+    from oracle import laughlin as OL
+
+    flux = N + 2 * (N - 1)  # 2 Q1 = flux - 2 (N - 1) = N
+    plan = nat.Plan(nspins=(N, 0), flux=flux, network_type="laughlin", excitation_lz=lz)
+    B = 24
+    x = plan.init_walkers(B, seed=7)
+    params = torch.zeros(0, device=DEV)
+    lp = plan.logpsi(params, x).cpu().to(torch.complex128)
+    x64 = x.cpu().double()
+    ref = torch.stack([OL.logpsi(x64[b], flux, 1, lz) for b in range(B)])
+    assert (lp.real - ref.real).abs().max() < 2e-5 * max(1.0, ref.real.abs().max().item())
+    assert phase_diff(lp.imag, ref.imag).abs().max() < 5e-5
+    out = plan.local_energy(params, x)
+    res = OH.batch_local_energy(lambda xx: OL.logpsi(xx, flux, 1, lz), x64, flux / 2, chunk=B)
+    for k, tol in (("kinetic", 2e-4), ("angular_momentum_z", 2e-4), ("angular_momentum_square", 2e-3), ("potential", 1e-5)):
+        got, want = out[k].cpu(), res[k]
+        want = want.real if want.is_complex() and not got.is_complex() else want
+        err = (got.to(want.dtype) - want).abs().max().item()
+        assert err < tol * max(1.0, want.abs().max().item()), (k, err)
+    assert (out["kinetic"].real.cpu() - N / 2).abs().max() < 5e-4
+    assert (out["angular_momentum_z"].cpu() - lz).abs().max() < 5e-4
+
+
 def test_laughlin_pinned_energy_through_the_gpu_path(nat):
     """tests/cli_test.py:24-54 of the reference: Laughlin network, nspins [3,0], flux 6, optimizer none, batch 3360
     prints `energy=2.58...` and `L_square=0.0000`.  Same system through the facade on the GPU: Metropolis sweeps

@@ -107,3 +107,16 @@ def test_psiformer_antisymmetry_and_lll_floor():
     res = OH.batch_local_energy(lambda xx: OP.logpsi(p, xx, cfg), x, cfg.Q, interaction_strength=0.0)
     assert torch.allclose(res["kinetic"].real, torch.full((3,), 3.0, dtype=torch.float64), atol=1e-8)
     assert res["kinetic"].imag.abs().max() < 1e-8
+
+
+@pytest.mark.parametrize("N,lz", [(4, 1.0), (4, -2.0), (5, 0.5)])
+def test_laughlin_quasihole_is_an_lll_lz_eigenstate(N, lz):
+    # networks/laughlin.py:38-41,73-83: N = 2 Q1 electrons, the orbital m = -lz left out of the 2 Q1 + 1.  The reference
+    # holds no number for it; the state it describes is a lowest-Landau-level state (KE = N/2) and an L_z eigenstate
+    # whose eigenvalue is the omitted orbital's -(-lz) = lz (a filled shell has L_z = 0).
+    flux = N + 2 * (N - 1)
+    x = sample(3, N, seed=5)
+    res = OH.batch_local_energy(lambda xx: OL.logpsi(xx, flux, 1, lz), x, flux / 2, chunk=3)
+    assert (res["kinetic"].real - N / 2).abs().max() < 1e-6
+    assert (res["angular_momentum_z"].real - lz).abs().max() < 1e-6
+    assert OL.laughlin_orbitals(x[0], flux, 1, lz).shape == (N, N)
