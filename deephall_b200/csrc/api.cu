@@ -287,6 +287,9 @@ extern "C" int dh_plan_destroy(dh_plan* p) {
   if (p->d_normfac) cudaFree(p->d_normfac);
   if (p->prep) cudaFree(p->prep);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
+  if (p->side_stream) cudaStreamDestroy(p->side_stream);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
   return 0;
 }
@@ -305,12 +308,17 @@ extern "C" int dh_param_layout(const dh_plan* p, dh_param_entry* entries, int32_
 
 size_t vjp_ws_floats(const dh_plan* p, int64_t Bc);  // api_vjp.cu
 
+static inline size_t fwd_ws_copies(const dh_plan* p, bool jets, int64_t B) {
+  return (dual_stream_env() && B > pick_chunk(p, jets, B)) ? 2 : 1;
+}
+
 extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* bytes) {
   if (!p || !bytes || B < 0) return DH_E_BADARG;
   size_t fl = 0;
   switch (op) {
-    case DH_OP_LOGPSI: fl = carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats; break;
-    case DH_OP_LOCAL_ENERGY: fl = carve_fwd(p, nullptr, pick_chunk(p, true, B), true, false).floats; break;
+    // (passes of two or more chunks interleave them on two streams: two activation workspaces)
+    case DH_OP_LOGPSI: fl = carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats * fwd_ws_copies(p, false, B); break;
+    case DH_OP_LOCAL_ENERGY: fl = carve_fwd(p, nullptr, pick_chunk(p, true, B), true, false).floats * fwd_ws_copies(p, true, B); break;
     case DH_OP_MCMC:
       fl = carve_mcmc(p, nullptr, B).floats + carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats;
       break;
@@ -592,7 +600,29 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
   float* base = align_ws(ws);
   FwdWs w = carve_fwd(p, base, chunk, jets, false);
   if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
-  for (int64_t b0 = 0; b0 < B; b0 += chunk) {
+  // Chunk interleave: with room for a second activation workspace, odd chunks run on the plan's side stream
+  // (forked from and joined back into `s` by events, so the call keeps stream semantics and stays capturable).
+  // Chunks are independent; one chunk's launch gaps and wave tails are filled by the other's kernels.
+  FwdWs w2 = w;
+  bool dual = dual_stream_env() && B > chunk && !p->prof_on &&
+              (size_t)((char*)(base + 2 * w.floats) - (char*)ws) <= ws_bytes;
+  if (dual && !p->side_stream) {
+    if (cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      p->side_stream = nullptr;
+      dual = false;
+    }
+  }
+  if (dual) {
+    w2 = carve_fwd(p, base + w.floats, chunk, jets, false);
+    if (cudaEventRecord(p->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0) != cudaSuccess)
+      return (int)cudaGetLastError();
+  }
+  int rc = 0;
+  int64_t k = 0;
+  for (int64_t b0 = 0; b0 < B && !rc; b0 += chunk, ++k) {
     const int64_t Bc = (B - b0) < chunk ? (B - b0) : chunk;
     FinalizeArgs fa;
     memset(&fa, 0, sizeof(fa));
@@ -603,10 +633,15 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
     fa.out_lz = out_lz ? out_lz + b0 : nullptr;
     fa.out_lz2 = out_lz2 ? out_lz2 + b0 : nullptr;
     fa.out_l2 = out_l2 ? out_l2 + b0 : nullptr;
-    int rc = forward_chunk(p, params, x + b0 * p->N * 2, Bc, jets, w, fa, s);
-    if (rc) return rc;
+    const bool odd = dual && (k & 1);
+    rc = forward_chunk(p, params, x + b0 * p->N * 2, Bc, jets, odd ? w2 : w, fa, odd ? p->side_stream : s);
   }
-  return 0;
+  if (dual) {  // join even after an error, so the side stream never outlives the call
+    cudaError_t e = cudaEventRecord(p->ev_join, p->side_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, p->ev_join, 0);
+    if (!rc && e != cudaSuccess) rc = (int)e;
+  }
+  return rc;
 }
 
 extern "C" int dh_logpsi(dh_plan* p, const float* params, const float* x, int64_t B, float* out_logpsi,

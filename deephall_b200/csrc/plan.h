@@ -69,7 +69,17 @@ struct dh_plan {
   std::vector<double> prof_flops;     // algorithmic flops of pair i
   size_t prof_used;
   long long launches;
+  // ---- chunk interleave: a pass of two or more chunks alternates them between the caller's stream and this one
+  // (each with its own activation workspace), so one chunk's launch gaps and wave tails are filled by the other's kernels
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
+
+// 0 disables the chunk interleave (DH_DUAL_STREAM=0)
+static inline bool dual_stream_env() {
+  static const bool on = !(getenv("DH_DUAL_STREAM") && atoi(getenv("DH_DUAL_STREAM")) == 0);
+  return on;
+}
 
 enum ProfCat { PC_GEMM = 0, PC_ATTENTION = 1, PC_LAYERNORM = 2, PC_TAIL = 3, PC_MCMC = 4, PC_OTHER = 5, PC_COUNT = 6 };
 
