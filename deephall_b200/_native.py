@@ -80,6 +80,10 @@ SIGNATURES = OrderedDict(
     dh_kfac_factors=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     dh_profile_begin=(C.c_int, [_vp, _i32]),
     dh_profile_end=(C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i32), C.POINTER(C.c_double)]),
+    dh_pair_correlation=(C.c_int, [_vp, _i64, _i32, _i32, _i64, _vp, _vp, _vp]),
+    dh_density_histogram=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
+    dh_overlap_sum=(C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    dh_overlap_ratio=(C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
 )
 
 PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "tail", "mcmc", "other")
@@ -365,3 +369,51 @@ def gemm(A, W, bias=None, rows_per_group=1, out=None, accumulate=False, impl=0):
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)
     _check(lib.dh_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, rows_per_group, int(accumulate), impl, _stream()), "dh_gemm")
     return out
+
+
+# ---- walker-ensemble estimators (plan-free entry points; netobs_bridge/observables)
+def pair_correlation(x, state, bins=None, batch_norm=0):
+    """state (bins, f32, device) += pair-correlation increment of the walkers x (B,N,2); see dh_pair_correlation."""
+    _need_cuda()
+    lib = load()
+    B, N = int(x.shape[0]), int(x.shape[1])
+    bins = int(state.numel() if bins is None else bins)
+    scratch = torch.empty(bins, dtype=torch.float64, device=x.device)
+    _check(lib.dh_pair_correlation(_ptr(x), B, N, bins, int(batch_norm), _ptr(state), _ptr(scratch), _stream()),
+           "dh_pair_correlation")
+    return state
+
+
+def density_histogram(x, counts):
+    """counts (bins, int64, device) += histogram of theta over all electrons of the walkers x (B,N,2)."""
+    _need_cuda()
+    lib = load()
+    assert counts.dtype == torch.int64
+    _check(lib.dh_density_histogram(_ptr(x), int(x.shape[0]), int(x.shape[1]), int(counts.numel()), _ptr(counts), _stream()),
+           "dh_density_histogram")
+    return counts
+
+
+def overlap_sum(logphi, logpsi):
+    """sum_b (logphi_b - logpsi_b) as a complex128 scalar tensor on the device."""
+    _need_cuda()
+    lib = load()
+    a = torch.view_as_real(logphi.contiguous())
+    b = torch.view_as_real(logpsi.contiguous())
+    out = torch.empty(2, dtype=torch.float64, device=a.device)
+    _check(lib.dh_overlap_sum(_ptr(a), _ptr(b), int(a.shape[0]), _ptr(out), _stream()), "dh_overlap_sum")
+    return torch.view_as_complex(out)
+
+
+def overlap_ratio(logphi, logpsi, shift):
+    """ratio_b = exp(logphi_b - logpsi_b - shift) (complex64) and |ratio_b|^2 (f32); shift: complex128 scalar tensor."""
+    _need_cuda()
+    lib = load()
+    a = torch.view_as_real(logphi.contiguous())
+    b = torch.view_as_real(logpsi.contiguous())
+    B = int(a.shape[0])
+    sh = torch.view_as_real(shift.to(torch.complex128).reshape(1)).reshape(2).contiguous()
+    ratio = torch.empty((B, 2), dtype=torch.float32, device=a.device)
+    rsq = torch.empty((B,), dtype=torch.float32, device=a.device)
+    _check(lib.dh_overlap_ratio(_ptr(a), _ptr(b), B, _ptr(sh), _ptr(ratio), _ptr(rsq), _stream()), "dh_overlap_ratio")
+    return torch.view_as_complex(ratio), rsq

@@ -1,0 +1,160 @@
+// Walker-ensemble estimators (the reference's netobs_bridge/observables): pair correlation g(theta_12), polar
+// density histogram, and the overlap ratio against a second wavefunction.  All are reductions over the walker batch:
+// HBM-bound reads of the (B, N, 2) coordinates (or of two (B) complex log-amplitudes), histogram / sum accumulators in
+// shared memory, one global atomic per bin and block.
+//
+//   dh_pair_correlation   <- PairCorrelationEstimator.evaluate   netobs_bridge/observables/pair_corr.py:42-60
+//   dh_density_histogram  <- DensityEstimator.evaluate           netobs_bridge/observables/density.py:42-49
+//   dh_overlap_sum / dh_overlap_ratio <- OverlapEstimator.evaluate  netobs_bridge/observables/overlap.py:55-63
+#include <math.h>
+
+#include "../../include/deephall_b200.h"
+#include "kernels.h"
+
+namespace dh {
+
+constexpr int OBS_THREADS = 256;
+constexpr int OBS_MAX_BINS = 4096;
+
+// theta_12 = arccos(r_i . r_j) of every pair i < j of every walker, weight 1 / sin(theta_12), `bins` equal bins over
+// [0, pi] (numpy / jnp.histogram: the last bin is closed on the right).  The geometry runs in fp64 from the fp32
+// coordinates, so that bin decisions do not depend on fp32 rounding of arccos; accumulation in fp64.
+__global__ void __launch_bounds__(OBS_THREADS)
+pair_correlation_kernel(const float* __restrict__ x, int64_t B, int N, int bins, double* __restrict__ hist) {
+  extern __shared__ double sh[];
+  for (int t = threadIdx.x; t < bins; t += blockDim.x) sh[t] = 0.0;
+  __syncthreads();
+  const int npair = N * (N - 1) / 2;
+  const int64_t items = B * npair;
+  const double scale = (double)bins / M_PI;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = it / npair;
+    int q = (int)(it - b * npair);
+    int i = 0;
+    while (q >= N - 1 - i) { q -= N - 1 - i; ++i; }  // triu_indices(N, 1) order: (0,1) (0,2) .. (1,2) ..
+    const int j = i + 1 + q;
+    const float* xw = x + b * N * 2;
+    double si, ci, spi, cpi, sj, cj, spj, cpj;
+    sincos((double)xw[2 * i], &si, &ci);
+    sincos((double)xw[2 * i + 1], &spi, &cpi);
+    sincos((double)xw[2 * j], &sj, &cj);
+    sincos((double)xw[2 * j + 1], &spj, &cpj);
+    double c12 = si * cpi * sj * cpj + si * spi * sj * spj + ci * cj;
+    c12 = fmin(1.0, fmax(-1.0, c12));
+    const double th = acos(c12);
+    int bin = (int)floor(th * scale);
+    if (bin >= bins) bin = bins - 1;  // th == pi belongs to the last bin
+    const double w = 1.0 / sin(th);
+    atomicAdd(&sh[bin], w);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < bins; t += blockDim.x)
+    if (sh[t] != 0.0) atomicAdd(&hist[t], sh[t]);
+}
+
+// state += hist * 4 bins / (B N^2 pi)   (pair_corr.py:59)
+__global__ void pair_correlation_scale_kernel(const double* __restrict__ hist, int bins, double factor,
+                                              float* __restrict__ state_inout) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < bins) state_inout[t] = (float)((double)state_inout[t] + hist[t] * factor);
+}
+
+// counts of theta over every electron of every walker, `bins` equal bins over [0, pi] (density.py:46-48); integer
+// accumulation: exact and order-independent.  bin = floor(theta * bins / pi) in fp64, theta == pi in the last bin.
+__global__ void __launch_bounds__(OBS_THREADS)
+density_histogram_kernel(const float* __restrict__ x, int64_t n_elec, int bins, unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int shc[];
+  for (int t = threadIdx.x; t < bins; t += blockDim.x) shc[t] = 0u;
+  __syncthreads();
+  const double scale = (double)bins / M_PI;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < n_elec; it += (int64_t)gridDim.x * blockDim.x) {
+    const double th = (double)x[2 * it];
+    if (!(th >= 0.0) || th > M_PI) continue;  // outside the range (or NaN): not counted
+    int bin = (int)floor(th * scale);
+    if (bin >= bins) bin = bins - 1;
+    atomicAdd(&shc[bin], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < bins; t += blockDim.x)
+    if (shc[t]) atomicAdd(&counts[t], (unsigned long long)shc[t]);
+}
+
+// sum_b (logphi_b - logpsi_b), complex, fp64, one block and a fixed summation order (deterministic)
+__global__ void __launch_bounds__(1024)
+overlap_sum_kernel(const float* __restrict__ logphi, const float* __restrict__ logpsi, int64_t B, double* __restrict__ out) {
+  __shared__ double sr[1024], si[1024];
+  double ar = 0.0, ai = 0.0;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
+    ar += (double)logphi[2 * b] - (double)logpsi[2 * b];
+    ai += (double)logphi[2 * b + 1] - (double)logpsi[2 * b + 1];
+  }
+  sr[threadIdx.x] = ar; si[threadIdx.x] = ai;
+  __syncthreads();
+  for (int s = 512; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) { sr[threadIdx.x] += sr[threadIdx.x + s]; si[threadIdx.x] += si[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = sr[0]; out[1] = si[0]; }
+}
+
+// ratio_b = exp(logphi_b - logpsi_b - shift), ratio_square_b = |ratio_b|^2   (overlap.py:60-62)
+__global__ void overlap_ratio_kernel(const float* __restrict__ logphi, const float* __restrict__ logpsi, int64_t B,
+                                     const double* __restrict__ shift, float* __restrict__ ratio,
+                                     float* __restrict__ ratio_sq) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double dr = (double)logphi[2 * b] - (double)logpsi[2 * b] - shift[0];
+  const double di = (double)logphi[2 * b + 1] - (double)logpsi[2 * b + 1] - shift[1];
+  const double m = exp(dr);
+  double s, c;
+  sincos(di, &s, &c);
+  if (ratio) { ratio[2 * b] = (float)(m * c); ratio[2 * b + 1] = (float)(m * s); }
+  if (ratio_sq) ratio_sq[b] = (float)(m * m);
+}
+
+static inline int obs_grid(int64_t items) {
+  int64_t g = (items + OBS_THREADS - 1) / OBS_THREADS;
+  const int64_t cap = 148 * 8;  // eight resident blocks of 256 threads on each of the 148 SMs
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace dh
+
+extern "C" int dh_pair_correlation(const float* x, int64_t B, int32_t N, int32_t bins, int64_t batch_norm,
+                                   float* state_inout, double* hist_ws, void* stream) {
+  if (!x || !state_inout || !hist_ws || B < 0 || N < 1 || bins < 1 || bins > dh::OBS_MAX_BINS) return DH_E_BADARG;
+  if (batch_norm <= 0) batch_norm = B;
+  if (B == 0 || N < 2) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(hist_ws, 0, (size_t)bins * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t items = B * (N * (N - 1) / 2);
+  dh::pair_correlation_kernel<<<dh::obs_grid(items), dh::OBS_THREADS, (size_t)bins * sizeof(double), s>>>(x, B, N, bins, hist_ws);
+  const double factor = 4.0 * bins / ((double)batch_norm * N * N * M_PI);
+  dh::pair_correlation_scale_kernel<<<(bins + 255) / 256, 256, 0, s>>>(hist_ws, bins, factor, state_inout);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dh_density_histogram(const float* x, int64_t B, int32_t N, int32_t bins,
+                                    unsigned long long* counts_inout, void* stream) {
+  if (!x || !counts_inout || B < 0 || N < 1 || bins < 1 || bins > dh::OBS_MAX_BINS) return DH_E_BADARG;
+  if (B == 0) return 0;
+  dh::density_histogram_kernel<<<dh::obs_grid(B * N), dh::OBS_THREADS, (size_t)bins * sizeof(unsigned int), (cudaStream_t)stream>>>(
+      x, B * N, bins, counts_inout);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dh_overlap_sum(const float* logphi, const float* logpsi, int64_t B, double* out_sum, void* stream) {
+  if (!logphi || !logpsi || !out_sum || B < 0) return DH_E_BADARG;
+  dh::overlap_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logphi, logpsi, B, out_sum);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dh_overlap_ratio(const float* logphi, const float* logpsi, int64_t B, const double* shift,
+                                float* out_ratio, float* out_ratio_square, void* stream) {
+  if (!logphi || !logpsi || !shift || B < 0) return DH_E_BADARG;
+  if (B == 0) return 0;
+  dh::overlap_ratio_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logphi, logpsi, B, shift, out_ratio,
+                                                                                       out_ratio_square);
+  return (int)cudaGetLastError();
+}

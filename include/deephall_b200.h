@@ -205,6 +205,29 @@ long long dh_launch_count(const dh_plan* plan);
 int dh_profile_begin(dh_plan* plan, int32_t max_launches);
 int dh_profile_end(dh_plan* plan, double* ms_host, int32_t* count_host, double* flops_host);
 
+/* ---- walker-ensemble estimators (netobs_bridge/observables).  Plan-free: they read walkers or
+ * log-amplitudes that the entry points above produced.
+ *
+ * dh_pair_correlation  <- PairCorrelationEstimator.evaluate (netobs_bridge/observables/pair_corr.py:42-60):
+ *   state_inout[bins] (f32, device) += histogram over [0, pi] of theta_12 = arccos(r_i . r_j), all pairs i < j of
+ *   all B walkers, weights 1 / sin(theta_12), times 4 bins / (batch_norm N^2 pi).  batch_norm: the batch size the
+ *   normalisation divides by (the global batch when walkers are sharded over ranks and the states are summed);
+ *   <= 0 -> B.  hist_ws: `bins` doubles of device scratch.  bins <= 4096.
+ * dh_density_histogram <- DensityEstimator.evaluate (netobs_bridge/observables/density.py:42-49):
+ *   counts_inout[bins] (u64, device) += counts of theta over all B N electrons, `bins` equal bins over [0, pi].
+ * dh_overlap_sum / dh_overlap_ratio <- OverlapEstimator.evaluate (netobs_bridge/observables/overlap.py:55-63):
+ *   logphi, logpsi: (B,2) f32 = (Re, Im) as dh_logpsi writes them.  dh_overlap_sum: out_sum[2] (f64, device) =
+ *   sum_b (logphi_b - logpsi_b); the host divides by the (global) batch to get `shift` (after an all-reduce when
+ *   sharded).  dh_overlap_ratio: ratio_b = exp(logphi_b - logpsi_b - shift) as (B,2) f32 and |ratio_b|^2 as (B) f32
+ *   (either output may be NULL); shift: 2 doubles on the device. */
+int dh_pair_correlation(const float* x, int64_t B, int32_t N, int32_t bins, int64_t batch_norm,
+                        float* state_inout, double* hist_ws, void* stream);
+int dh_density_histogram(const float* x, int64_t B, int32_t N, int32_t bins,
+                         unsigned long long* counts_inout, void* stream);
+int dh_overlap_sum(const float* logphi, const float* logpsi, int64_t B, double* out_sum, void* stream);
+int dh_overlap_ratio(const float* logphi, const float* logpsi, int64_t B, const double* shift,
+                     float* out_ratio, float* out_ratio_square, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -794,3 +794,97 @@ def test_checkpoint_wire_format_roundtrip(nat, tmp_path):
     assert step == 42 and abs(st.mcmc_width - 0.11) < 1e-7 and st.opt_state.count == 5
     assert torch.equal(st.params, params) and torch.equal(st.data, data) and torch.equal(st.opt_state.nu, opt.nu)
     assert torch.equal(model.apply(st.params, st.data), model.apply(params, data))
+
+
+# ------------------------------------------------------------------ estimators (netobs_bridge/observables)
+def _uniform_walkers(B, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    theta = torch.acos(torch.rand(B, N, generator=g) * 2 - 1)
+    phi = (torch.rand(B, N, generator=g) * 2 - 1) * math.pi
+    return torch.stack([theta, phi], -1).to(torch.float32).to(DEV).contiguous()
+
+
+@pytest.mark.parametrize("B,N,bins", [(1, 2, 7), (37, 3, 200), (1000, 12, 200), (8192, 12, 64), (5, 1, 10)])
+def test_pair_correlation_parity(nat, B, N, bins):
+    """dh_pair_correlation vs the numpy restatement of pair_corr.py:47-59 (ragged sizes, one pair, no pair)."""
+    from oracle import observables as OO
+
+    x = _uniform_walkers(B, N, seed=3)
+    state = torch.full((bins,), 0.25, device=DEV)  # accumulates on top of what is there
+    nat.pair_correlation(x, state)
+    want = 0.25 + (OO.pair_correlation_increment(x.cpu().numpy(), bins) if N > 1 else np.zeros(bins))
+    got = state.cpu().double().numpy()
+    assert abs(got - want).max() <= 2e-6 * max(1.0, abs(want).max())
+    # sharded normalisation: two half batches normalised by the global batch sum to the whole
+    if B >= 2 and N > 1:
+        s2 = torch.zeros(bins, device=DEV)
+        h = B // 2
+        nat.pair_correlation(x[:h].contiguous(), s2, batch_norm=B)
+        nat.pair_correlation(x[h:].contiguous(), s2, batch_norm=B)
+        assert abs(s2.cpu().double().numpy() - (want - 0.25)).max() <= 2e-6 * max(1.0, abs(want).max())
+
+
+@pytest.mark.parametrize("B,N,bins", [(1, 1, 3), (513, 7, 50), (8192, 12, 50)])
+def test_density_histogram_is_exact(nat, B, N, bins):
+    from oracle import observables as OO
+
+    x = _uniform_walkers(B, N, seed=11)
+    x[0, 0, 0] = 0.0
+    x[-1, -1, 0] = math.pi  # float32(pi) > pi: outside the range, as for numpy
+    counts = torch.ones(bins, dtype=torch.int64, device=DEV)
+    nat.density_histogram(x, counts)
+    want = 1 + OO.density_increment(x.cpu().numpy(), bins)
+    assert (counts.cpu().numpy() == want).all()
+
+
+def test_overlap_estimator(nat):
+    """OverlapEstimator (overlap.py:55-70): Laughlin against itself is 1; a random-init Psiformer against Laughlin
+    reproduces the oracle's ratio (up to the global branch phase), ratio_square and overlap."""
+    from deephall_b200 import networks, observables
+    from deephall_b200.config import Network, System
+    from oracle import observables as OO
+
+    system = System(flux=6, nspins=(3, 0))
+    B = 600
+    lau = networks.make_network(system, Network(type="laughlin"))
+    x = lau.plan(system).init_walkers(B, seed=2)
+    est = observables.OverlapEstimator(lau.apply, system, Network(type="laughlin"))
+    vals, _ = est.evaluate(0, torch.zeros(0, device=DEV), None, x, system, {})
+    assert (vals["ratio"] - 1).abs().max() < 1e-6 and (vals["ratio_square"] - 1).abs().max() < 1e-6
+    assert abs(est.digest(vals, {})["overlap"].item() - 1) < 1e-6
+
+    model = networks.make_network(system, Network())
+    params = model.init(0)
+    est = observables.OverlapEstimator(model.apply, system, Network())
+    vals, _ = est.evaluate(0, params, None, x, system, {})
+    logpsi = model.apply(params, x).cpu().numpy()
+    logphi = lau.apply(torch.zeros(0, device=DEV), x).cpu().numpy()
+    ref = OO.overlap_evaluate(logphi, logpsi)
+    rsq = vals["ratio_square"].cpu().double().numpy()
+    assert abs(rsq - ref["ratio_square"]).max() <= 1e-5 * ref["ratio_square"].max()
+    r = vals["ratio"].cpu().numpy()
+    assert abs(r - ref["ratio"]).max() <= 1e-5 * abs(ref["ratio"]).max()
+    ov = est.digest(vals, {})["overlap"].item()
+    assert abs(ov - OO.overlap_digest(ref["ratio"], ref["ratio_square"])) < 1e-5
+    assert 0.0 <= ov <= 1.0
+
+
+def test_estimators_through_the_reference_surface(nat):
+    """empty_val_state / evaluate / digest as NetObs drives them (pair_corr.py:36-65, density.py:31-57)."""
+    from deephall_b200 import observables
+    from oracle import observables as OO
+
+    plan = nat.Plan(nspins=(6, 0), flux=15)
+    pc, de = observables.PairCorrelationEstimator({"bins": 40}), observables.DensityEstimator()
+    _, s_pc = pc.empty_val_state(3)
+    _, s_de = de.empty_val_state(3)
+    want_pc, want_de = 0.0, 0
+    for step in range(3):
+        x = plan.init_walkers(256, seed=step)
+        _, s_pc = pc.evaluate(step, None, None, x.reshape(2, 128, 6, 2), None, s_pc)  # leading device axis is flattened
+        _, s_de = de.evaluate(step, None, None, x, None, s_de)
+        want_pc = want_pc + OO.pair_correlation_increment(x.cpu().numpy(), 40)
+        want_de = want_de + OO.density_increment(x.cpu().numpy(), 50)
+    assert abs(s_pc["pair_corr"].cpu().double().numpy() - want_pc).max() < 1e-5
+    assert (s_de["map"].cpu().numpy() == want_de).all()
+    assert pc.digest({}, s_pc) == {} and de.digest({}, s_de) == {}

@@ -120,3 +120,29 @@ def test_laughlin_quasihole_is_an_lll_lz_eigenstate(N, lz):
     assert (res["kinetic"].real - N / 2).abs().max() < 1e-6
     assert (res["angular_momentum_z"].real - lz).abs().max() < 1e-6
     assert OL.laughlin_orbitals(x[0], flux, 1, lz).shape == (N, N)
+
+
+def test_estimator_oracle_closed_forms():
+    # netobs_bridge/observables: the reference holds no numbers for these; closed forms pin the restatement.
+    import numpy as np
+
+    from oracle import observables as OO
+
+    rng = np.random.default_rng(0)
+    B, N, bins = 40000, 6, 10
+    data = np.stack([np.arccos(rng.uniform(-1, 1, (B, N))), rng.uniform(-np.pi, np.pi, (B, N))], -1)
+    # independent uniform points: theta_12 has density sin/2, so the 1/sin-weighted histogram is flat at (N-1)/N
+    g = OO.pair_correlation_increment(data, bins)
+    assert np.abs(g - (N - 1) / N).max() < 0.02
+    # density: counts sum to B N and follow sin(theta)/2
+    d = OO.density_increment(data, bins)
+    assert d.sum() == B * N
+    edges = np.linspace(0, np.pi, bins + 1)
+    expect = B * N * (np.cos(edges[:-1]) - np.cos(edges[1:])) / 2
+    assert np.abs(d - expect).max() < 5 * np.sqrt(expect.max())
+    # overlap of a state with itself (up to a constant factor) is 1; with a random other state it is < 1
+    lp = rng.normal(size=500) + 1j * rng.uniform(-np.pi, np.pi, 500)
+    ev = OO.overlap_evaluate(lp + (0.3 - 0.2j), lp)
+    assert abs(OO.overlap_digest(ev["ratio"], ev["ratio_square"]) - 1) < 1e-12
+    ev = OO.overlap_evaluate(lp + 0.5 * rng.normal(size=500), lp)
+    assert OO.overlap_digest(ev["ratio"], ev["ratio_square"]) < 0.95
