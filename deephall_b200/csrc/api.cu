@@ -78,7 +78,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   if (cfg->network_type != 0 && cfg->network_type != 1) { delete p; return DH_E_BADARG; }
   if (p->N > 16 || p->D % 32 != 0 || p->D > 256 || p->hd % 4 != 0) { delete p; return DH_E_UNSUPPORTED; }
   if (p->laughlin) {
-    // networks/laughlin.py:33-37: Q1 = flux/2 - p (N - 1); only the ground state N = 2 Q1 + 1 is built
+    // networks/laughlin.py:33-47: Q1 = flux/2 - p (N - 1); N = 2 Q1 + 1 ground state, 2 Q1 quasihole, 2 Q1 + 2 quasiparticle
     const int pf = cfg->cf_flux > 0 ? cfg->cf_flux : 1;
     p->twoQ1 = cfg->flux - 2 * pf * (p->N - 1);
     p->lskip = -1;
@@ -87,7 +87,13 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       const long ski = lround(sk);
       if (fabs(sk - (double)ski) > 1e-6 || ski < 0 || ski > p->twoQ1) { delete p; return DH_E_BADARG; }
       p->lskip = (int)ski;
-    } else if (p->twoQ1 != p->N - 1) { delete p; return DH_E_UNSUPPORTED; }  // (quasiparticle: N = 2 Q1 + 2, not built)
+    } else if (p->twoQ1 == p->N - 2 && p->twoQ1 >= 0) {  // quasiparticle (laughlin.py:42-46,85-100): shell + projected orbital
+      const double ea = 0.5 * p->twoQ1 + (double)cfg->excitation_lz;  // u exponent Q1 + lz of the excited orbital
+      const long eai = lround(ea);
+      if (fabs(ea - (double)eai) > 1e-6 || eai < -1 || eai > p->twoQ1 + 1) { delete p; return DH_E_BADARG; }
+      p->lqp = 1;
+      p->lqp_a = (int)eai;
+    } else if (p->twoQ1 != p->N - 1) { delete p; return DH_E_UNSUPPORTED; }
     p->L = p->twoQ1 + 1;
     p->K = 1;
     p->nl = 0;
@@ -345,6 +351,8 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     // analytic Laughlin ground state: orbital-matrix jets straight from the coordinates, then the same tail
     TailDims tl{N, R, p->L, 1, p->twoQ1, p->cfg.n_up, 0};
     tl.lskip = p->lskip;
+    tl.qp = p->lqp;
+    tl.qp_a = p->lqp_a;
     ProfScope pst(p, PC_TAIL, 0, s, 3);
     if ((rc = laughlin_orbital_jets(x, p->d_normfac, w.Mj, Bc, tl, s))) return rc;
     if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, tl, s))) return rc;

@@ -83,6 +83,8 @@ struct TailDims {
   int twoQ;
   int n_up, n_dn;   // n_dn > 0: two spin blocks of orbital coefficients per row, electron i >= n_up reads the second
   int lskip = -1;   // Laughlin quasihole: exponent index left out of the L = N + 1 orbitals (-1: none, L = N)
+  int qp = 0;       // Laughlin quasiparticle (L = N - 1 shell orbitals + one LLL-projected orbital)
+  int qp_a = 0;     // its u exponent Q1 + lz, in [-1, 2 Q1 + 1]
 };
 // c: [B*N*R, 2*nsb*L*N*K] (per spin block: re block | im block) -> M jets [B][K][R][N][N] complex
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,

@@ -22,8 +22,9 @@ struct dh_plan {
   int nsb;   // spin blocks with their own orbital projections (blocks.py:29-34): 1 (n_dn = 0) or 2
   int orbN;  // columns of the orbital-coefficient tensor: 2 * nsb * LNK = [re | im] per spin block
   int laughlin;  // analytic Laughlin ground state instead of the Psiformer (no parameters)
-  int twoQ1;     // laughlin: 2 Q1 = flux - 2 p (N - 1) = N - 1 (ground state) or N (quasihole)
+  int twoQ1;     // laughlin: 2 Q1 = flux - 2 p (N - 1) = N - 1 (ground state), N (quasihole) or N - 2 (quasiparticle)
   int lskip;     // laughlin quasihole: exponent index Q1 - lz of the orbital that is left out (-1: ground state)
+  int lqp = 0, lqp_a = 0;  // laughlin quasiparticle (N = 2 Q1 + 2): flag and the u exponent Q1 + lz of the projected orbital
   float Q, radius;
   std::vector<dh_param_entry> entries;
   int64_t nparams;

@@ -229,6 +229,30 @@ __device__ inline dcplx ddiv(dcplx a, dcplx b) {
 }
 __device__ inline dcplx dsub(dcplx a, dcplx b) { return make_double2(a.x - b.x, a.y - b.y); }
 
+// Second-order jet of a complex function along ONE flow: (f, delta f, delta^2 f).  Used for the quasiparticle's
+// LLL-projected orbital (networks/laughlin.py:85-100), which is not a product of a one-electron factor and an SU(2)
+// singlet: its rows are evaluated flow by flow with product / quotient rules instead of closed forms.
+struct Jet2 { dcplx f, d, dd; };
+__device__ inline Jet2 jconst(dcplx c) { return Jet2{c, make_double2(0, 0), make_double2(0, 0)}; }
+__device__ inline Jet2 jadd(Jet2 a, Jet2 b) { return Jet2{dadd(a.f, b.f), dadd(a.d, b.d), dadd(a.dd, b.dd)}; }
+__device__ inline Jet2 jsub(Jet2 a, Jet2 b) { return Jet2{dsub(a.f, b.f), dsub(a.d, b.d), dsub(a.dd, b.dd)}; }
+__device__ inline Jet2 jscale(Jet2 a, double s) { return Jet2{dscale(a.f, s), dscale(a.d, s), dscale(a.dd, s)}; }
+__device__ inline Jet2 jmul(Jet2 a, Jet2 b) {
+  return Jet2{dmul(a.f, b.f), dadd(dmul(a.d, b.f), dmul(a.f, b.d)),
+              dadd(dadd(dmul(a.dd, b.f), dmul(a.f, b.dd)), dscale(dmul(a.d, b.d), 2.0))};
+}
+__device__ inline Jet2 jinv(Jet2 a) {  // 1/a: (1/f, -d/f^2, -dd/f^2 + 2 d^2/f^3)
+  const dcplx r = ddiv(make_double2(1.0, 0.0), a.f);
+  const dcplx r2 = dmul(r, r);
+  const dcplx dr = dscale(dmul(a.d, r2), -1.0);
+  return Jet2{r, dr, dadd(dscale(dmul(a.dd, r2), -1.0), dscale(dmul(dmul(a.d, a.d), dmul(r2, r)), 2.0))};
+}
+__device__ inline Jet2 jpow(Jet2 a, int n) {  // n >= 0
+  Jet2 p = jconst(make_double2(1.0, 0.0));
+  for (int k = 0; k < n; ++k) p = jmul(p, a);
+  return p;
+}
+
 __global__ void __launch_bounds__(128)
 laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restrict__ ones, float* __restrict__ Mj,
                              TailDims dm) {
@@ -242,7 +266,9 @@ laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restri
   dcplx* dV = dU + 2 * N;     // [N][2]
   dcplx* gE = dV + 2 * N;     // [N][2] delta Jas_i / Jas_i for a flow on electron e
   dcplx* sc = gE + 2 * N;     // [0] Jas, [1..2] dL_t, [3..4] q_t
-  cplx* env = reinterpret_cast<cplx*>(sc + 5);
+  dcplx* exd = sc + 5;        // [2N+3] quasiparticle column: delta along flow f (own flows of every electron, then x, y, z)
+  dcplx* exdd = exd + 2 * N + 3;  // [2N+3] delta^2 along flow f; [2N+3]: the value
+  cplx* env = reinterpret_cast<cplx*>(exdd + 2 * N + 4);
   const int64_t bi = blockIdx.x;
   const int64_t b = bi / N;
   const int i = (int)(bi % N);
@@ -290,8 +316,10 @@ laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restri
   Rows rw(N, R > 1);
   auto E = [&](int slot, int m) { const cplx e = env[slot * L + m]; return make_double2((double)e.x, (double)e.y); };
   // columns: ground state a = 0 .. N-1; quasihole (laughlin.py:75-80): a = 0 .. skip-1, then 2Q1 down to skip+1
-  for (int t = tid; t < R * N; t += blockDim.x) {
-    const int r = t / N, col = t % N;
+  // quasiparticle (laughlin.py:85-100): the N - 1 shell columns a = 0 .. 2Q1, then the projected orbital (below)
+  const int ncol = dm.qp ? N - 1 : N;
+  for (int t = tid; t < R * ncol; t += blockDim.x) {
+    const int r = t / ncol, col = t % ncol;
     const int m = (dm.lskip < 0 || col < dm.lskip) ? col : dm.twoQ - (col - dm.lskip);
     const dcplx P = E(0, m);
     dcplx val;
@@ -312,11 +340,71 @@ laughlin_orbital_jets_kernel(const float* __restrict__ x, const double* __restri
     dst[0] = (float)val.x;
     dst[1] = (float)val.y;
   }
+  if (!dm.qp) return;
+  // Projected orbital of electron i (laughlin.py:89-99), with a = Q1 + lz, b = 2 Q1 - a:
+  //   X_i = Jas_i [ (a+1) u_i^a v_i^(b+1) A_i - (b+1) u_i^(a+1) v_i^b C_i ],  A_i = -sum_{j!=i} u_j / e_ij,  C_i = sum_{j!=i} v_j / e_ij
+  // (the reference's u^a v^b ((Q+1+lz) v dJas/dv - (Q+1-lz) u dJas/du); a or b = -1 only with a vanishing coefficient).
+  // Thread f < 2N + 3 carries (X, delta X, delta^2 X) along flow f: every spinor moves as delta (u, v) = (dU, dV) (own
+  // flows: one electron; f >= 2N: all electrons about the x, y, z axis), delta^2 (u, v) = -(u, v) / 4.
+  if (tid < 2 * N + 3) {
+    const int f = tid;
+    auto spinor = [&](int k, Jet2& ju, Jet2& jv) {
+      dcplx du = make_double2(0, 0), dv = du;
+      bool moves = false;
+      if (f < 2 * N) {
+        if ((f >> 1) == k) { du = dU[f]; dv = dV[f]; moves = true; }
+      } else {
+        const int a3 = f - 2 * N;
+        const double nx = a3 == 0, ny = a3 == 1, nz = a3 == 2;
+        const dcplx t1 = dadd(dscale(U[k], nz), dmul(make_double2(nx, ny), V[k]));
+        const dcplx t2 = dadd(dmul(make_double2(nx, -ny), U[k]), dscale(V[k], -nz));
+        du = make_double2(-0.5 * t1.y, 0.5 * t1.x);
+        dv = make_double2(-0.5 * t2.y, 0.5 * t2.x);
+        moves = true;
+      }
+      ju = Jet2{U[k], du, moves ? dscale(U[k], -0.25) : make_double2(0, 0)};
+      jv = Jet2{V[k], dv, moves ? dscale(V[k], -0.25) : make_double2(0, 0)};
+    };
+    Jet2 ui, vi;
+    spinor(i, ui, vi);
+    Jet2 jasj = jconst(make_double2(1.0, 0.0)), A = jconst(make_double2(0, 0)), Cc = A;
+    for (int j = 0; j < N; ++j) {
+      if (j == i) continue;
+      Jet2 uj, vj;
+      spinor(j, uj, vj);
+      const Jet2 e = jsub(jmul(ui, vj), jmul(uj, vi));
+      const Jet2 ie = jinv(e);
+      jasj = jmul(jasj, e);
+      A = jsub(A, jmul(uj, ie));
+      Cc = jadd(Cc, jmul(vj, ie));
+    }
+    const int a = dm.qp_a, bb = dm.twoQ - a;
+    Jet2 X = jconst(make_double2(0, 0));
+    if (a + 1 != 0) X = jadd(X, jscale(jmul(jmul(jpow(ui, a), jpow(vi, bb + 1)), A), (double)(a + 1)));
+    if (bb + 1 != 0) X = jsub(X, jscale(jmul(jmul(jpow(ui, a + 1), jpow(vi, bb)), Cc), (double)(bb + 1)));
+    X = jmul(X, jasj);
+    exd[f] = X.d;
+    exdd[f] = X.dd;
+    if (f == 0) exdd[2 * N + 3] = X.f;
+  }
+  __syncthreads();
+  for (int r = tid; r < R; r += blockDim.x) {
+    dcplx val;
+    if (r == 0) val = exdd[2 * N + 3];
+    else if (r <= 2 * N) val = exd[r - 1];
+    else if (r == rw.S()) { val = make_double2(0, 0); for (int f = 0; f < 2 * N; ++f) val = dadd(val, exdd[f]); }
+    else if (r < rw.T(0)) val = exd[2 * N + (r - rw.D(0))];
+    else val = exdd[2 * N + (r - rw.T(0))];
+    float* dst = Mj + (((b * R + r) * N + i) * N + (N - 1)) * 2;
+    dst[0] = (float)val.x;
+    dst[1] = (float)val.y;
+  }
 }
 
 int laughlin_orbital_jets(const float* x, const double* ones, float* Mj, int64_t B, TailDims d, cudaStream_t s) {
-  if ((d.lskip < 0 ? d.L != d.N : d.L != d.N + 1) || d.K != 1) return -2;
-  const size_t smem = (2 * (size_t)d.L + 8 * (size_t)d.N + 5) * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
+  if ((d.qp ? d.L != d.N - 1 : d.lskip < 0 ? d.L != d.N : d.L != d.N + 1) || d.K != 1) return -2;
+  if (d.qp && (d.qp_a < -1 || d.qp_a > d.twoQ + 1 || 2 * d.N + 3 > 128)) return -2;
+  const size_t smem = (2 * (size_t)d.L + 12 * (size_t)d.N + 12) * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
   laughlin_orbital_jets_kernel<<<(unsigned)(B * d.N), 128, smem, s>>>(x, ones, Mj, d);
   return (int)cudaGetLastError();
 }

@@ -55,7 +55,7 @@ class B200Network:
 
 
 class Laughlin(B200Network):
-    """Analytic Laughlin ground state and quasihole (networks/laughlin.py:19-83), evaluated by the same tail kernels
+    """Analytic Laughlin ground state, quasihole and quasiparticle (networks/laughlin.py:19-100), evaluated by the same tail kernels
     (log-determinant jets, local-energy assembly, Metropolis sweep).  It has no parameters."""
 
     def __init__(self, nspins, flux, cf_flux=1, excitation_lz=0):
@@ -65,12 +65,14 @@ class Laughlin(B200Network):
         self.excitation_lz = float(excitation_lz)
         n = sum(self.nspins)
         two_q1 = self.flux - 2 * self.cf_flux * (n - 1)
-        if self.nspins[1] != 0 or two_q1 not in (n - 1, n):
-            raise NotImplementedError("the spin-polarised Laughlin ground state (N = 2 Q1 + 1) and quasihole (N = 2 Q1) are "
-                                      "built; the quasiparticle state is a 'next' row (SURVEY 8f N3)")
-        if two_q1 == n:  # laughlin.py:38-40,49-52
+        if two_q1 not in (n - 2, n - 1, n) or two_q1 < 0:
+            raise ValueError("Filling not supported")  # laughlin.py:47
+        if self.nspins[1] != 0:
+            raise NotImplementedError("the analytic Laughlin states are built for spin-polarised systems")
+        if two_q1 != n - 1:  # quasihole / quasiparticle: laughlin.py:38-45,49-52
             d = self.excitation_lz - two_q1 / 2
-            if abs(d - round(d)) > 1e-9 or abs(self.excitation_lz) > abs(two_q1 / 2):
+            reach = abs(two_q1 / 2) + (1 if two_q1 == n - 2 else 0)
+            if abs(d - round(d)) > 1e-9 or abs(self.excitation_lz) > reach:
                 raise AssertionError(f"Impossible Lz={self.excitation_lz} for excitation")
 
     def plan(self, system: System | None = None) -> _native.Plan:

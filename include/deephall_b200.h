@@ -18,7 +18,7 @@
  *   dh_slogdet         <- jnp.linalg.slogdet + tail         psiformer.py:74-76
  *   dh_param_layout    <- the flax parameter tree           psiformer.py, blocks.py
  *   dh_init_walkers    <- init_guess                        train.py:40-54
- *   network_type = 1   <- Laughlin(nspins, flux).apply      networks/laughlin.py:19-83 (ground state, quasihole;
+ *   network_type = 1   <- Laughlin(nspins, flux).apply      networks/laughlin.py:19-100 (ground state, quasihole, quasiparticle;
  *                         no parameters: dh_param_count = 0, dh_logpsi_vjp writes nothing)
  *
  * Conventions
@@ -62,7 +62,7 @@ typedef struct dh_config {
   int32_t network_type;     /* network.type: 0 = psiformer, 1 = laughlin (config.py:82-84)          */
   int32_t cf_flux;          /* laughlin: composite-fermion flux p (networks/laughlin.py:25), 0 -> 1  */
   int32_t orbital_type;     /* network.orbital: 0 = full, 1 = sparse (config.py:87-89, blocks.py:47-62) */
-  float excitation_lz;      /* laughlin quasihole (N = 2 Q1): L_z of the excitation = system.lz_center (networks/__init__.py:25-27) */
+  float excitation_lz;      /* laughlin quasihole (N = 2 Q1) / quasiparticle (N = 2 Q1 + 2): L_z of the excitation = system.lz_center (networks/__init__.py:25-27) */
 } dh_config;
 
 typedef struct dh_plan dh_plan;

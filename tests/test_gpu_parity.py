@@ -741,6 +741,45 @@ def test_laughlin_quasihole_parity(nat, N, lz):
     assert (out["angular_momentum_z"].cpu() - lz).abs().max() < 5e-4
 
 
+@pytest.mark.parametrize("N,lz", [(2, 1.0), (3, 1.5), (4, 0.0), (4, -2.0), (5, 0.5), (5, -2.5), (6, 3.0), (8, 1.0)])
+def test_laughlin_quasiparticle_parity(nat, N, lz):
+    """Laughlin quasiparticle (networks/laughlin.py:42-46,85-100: N = 2 Q1 + 2 electrons, the filled shell plus one
+    LLL-projected orbital of L_z = lz): log psi, kinetic energy and angular momenta against the oracle's gradient +
+    Hessian route; the state is in the lowest Landau level (KE = N/2) with L_z = lz and L = Q1 + 1."""
+    from oracle import laughlin as OL
+
+    flux = (N - 2) + 2 * (N - 1)  # 2 Q1 = flux - 2 (N - 1) = N - 2
+    Q1 = (N - 2) / 2
+    plan = nat.Plan(nspins=(N, 0), flux=flux, network_type="laughlin", excitation_lz=lz)
+    B = 24
+    x = plan.init_walkers(B, seed=9)
+    params = torch.zeros(0, device=DEV)
+    lp = plan.logpsi(params, x).cpu().to(torch.complex128)
+    x64 = x.cpu().double()
+    ref = torch.stack([OL.logpsi(x64[b], flux, 1, lz) for b in range(B)])
+    assert (lp.real - ref.real).abs().max() < 2e-5 * max(1.0, ref.real.abs().max().item())
+    # (the fp32 determinant of a near-node walker -- Re log psi 20 below the others at N = 8 -- loses phase digits)
+    pd = phase_diff(lp.imag, ref.imag).abs()
+    assert pd.median() < 5e-6 and pd.max() < 5e-4
+    out = plan.local_energy(params, x)
+    res = OH.batch_local_energy(lambda xx: OL.logpsi(xx, flux, 1, lz), x64, flux / 2, chunk=B)
+    for k, tol in (("kinetic", 2e-4), ("angular_momentum_z", 2e-4), ("angular_momentum_square", 2e-3), ("potential", 1e-5)):
+        got, want = out[k].cpu(), res[k]
+        want = want.real if want.is_complex() and not got.is_complex() else want
+        err = (got.to(want.dtype) - want).abs()
+        scale = max(1.0, want.abs().max().item())
+        assert err.median().item() < tol * scale and err.max().item() < 20 * tol * scale, (k, err.max().item())
+    assert (out["kinetic"].real.cpu() - N / 2).abs().median() < 1e-3
+    assert (out["angular_momentum_z"].cpu() - lz).abs().median() < 1e-3
+    assert (out["angular_momentum_square"].cpu() - (Q1 + 1) * (Q1 + 2)).abs().median() < 2e-2
+    # Metropolis sweep (value-only form of the same kernel): 2 Re log psi of the final walkers matches a fresh evaluation
+    x2 = x.clone()
+    nacc, lp2 = plan.mcmc_sweep(params, x2, steps=3, width=0.3, seed=4, want_lp=True)
+    assert 0 < int(nacc) <= 3 * B
+    fresh = 2 * plan.logpsi(params, x2).real
+    assert (lp2 - fresh).abs().max() < 1e-4 * max(1.0, fresh.abs().max().item())
+
+
 def test_laughlin_pinned_energy_through_the_gpu_path(nat):
     """tests/cli_test.py:24-54 of the reference: Laughlin network, nspins [3,0], flux 6, optimizer none, batch 3360
     prints `energy=2.58...` and `L_square=0.0000`.  Same system through the facade on the GPU: Metropolis sweeps

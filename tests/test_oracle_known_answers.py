@@ -122,6 +122,19 @@ def test_laughlin_quasihole_is_an_lll_lz_eigenstate(N, lz):
     assert OL.laughlin_orbitals(x[0], flux, 1, lz).shape == (N, N)
 
 
+@pytest.mark.parametrize("N,lz", [(3, 1.5), (4, 0.0), (4, -2.0), (5, 0.5)])
+def test_laughlin_quasiparticle_is_an_lll_state_of_l_q1_plus_1(N, lz):
+    # networks/laughlin.py:42-46,85-100: N = 2 Q1 + 2 electrons, the filled shell plus one LLL-projected orbital.
+    # No number in the reference; what it describes: KE = N/2 (LLL), L_z = lz, L = Q1 + 1.
+    flux = (N - 2) + 2 * (N - 1)
+    Q1 = (N - 2) / 2
+    x = sample(3, N, seed=5)
+    res = OH.batch_local_energy(lambda xx: OL.logpsi(xx, flux, 1, lz), x, flux / 2, chunk=3)
+    assert (res["kinetic"].real - N / 2).abs().max() < 1e-6
+    assert (res["angular_momentum_z"].real - lz).abs().max() < 1e-6
+    assert (res["angular_momentum_square"].real - (Q1 + 1) * (Q1 + 2)).abs().max() < 1e-6
+
+
 def test_estimator_oracle_closed_forms():
     # netobs_bridge/observables: the reference holds no numbers for these; closed forms pin the restatement.
     import numpy as np
