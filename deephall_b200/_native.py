@@ -84,6 +84,9 @@ SIGNATURES = OrderedDict(
     dh_density_histogram=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp]),
     dh_overlap_sum=(C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     dh_overlap_ratio=(C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    dh_lll_orbitals=(C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    dh_one_rdm_scatter=(C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    dh_one_rdm_product=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
 )
 
 PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "tail", "mcmc", "other")
@@ -417,3 +420,38 @@ def overlap_ratio(logphi, logpsi, shift):
     rsq = torch.empty((B,), dtype=torch.float32, device=a.device)
     _check(lib.dh_overlap_ratio(_ptr(a), _ptr(b), B, _ptr(sh), _ptr(ratio), _ptr(rsq), _stream()), "dh_overlap_ratio")
     return torch.view_as_complex(ratio), rsq
+
+
+def lll_orbitals(points, flux):
+    """Y_{Q,Q,m} at points (..., 2) -> (..., flux + 1) complex64."""
+    _need_cuda()
+    lib = load()
+    pts = points.reshape(-1, 2).contiguous()
+    out = torch.empty((pts.shape[0], int(flux) + 1, 2), dtype=torch.float32, device=pts.device)
+    _check(lib.dh_lll_orbitals(_ptr(pts), int(pts.shape[0]), int(flux), _ptr(out), _stream()), "dh_lll_orbitals")
+    return torch.view_as_complex(out).reshape(*points.shape[:-1], int(flux) + 1)
+
+
+def one_rdm_scatter(x, r_prime):
+    """(B,N,2), (B,2) -> (B,N,N,2): copy a has electron a at r_prime."""
+    _need_cuda()
+    lib = load()
+    B, N = int(x.shape[0]), int(x.shape[1])
+    out = torch.empty((B, N, N, 2), dtype=torch.float32, device=x.device)
+    _check(lib.dh_one_rdm_scatter(_ptr(x.contiguous()), _ptr(r_prime.contiguous()), B, N, _ptr(out), _stream()), "dh_one_rdm_scatter")
+    return out
+
+
+def one_rdm_product(logpsi, logpsi_prime, phi, phi_prime, per_walker=True, out_sum=None):
+    """Per-walker (B,L,L) complex64 and/or the batch sum accumulated into out_sum (L,L) complex128."""
+    _need_cuda()
+    lib = load()
+    B, N, L = int(phi.shape[0]), int(phi.shape[1]), int(phi.shape[2])
+    a = torch.view_as_real(logpsi.contiguous())
+    b = torch.view_as_real(logpsi_prime.contiguous())
+    c = torch.view_as_real(phi.contiguous())
+    d = torch.view_as_real(phi_prime.contiguous())
+    out = torch.empty((B, L, L, 2), dtype=torch.float32, device=a.device) if per_walker else None
+    osum = torch.view_as_real(out_sum) if out_sum is not None else None
+    _check(lib.dh_one_rdm_product(_ptr(a), _ptr(b), _ptr(c), _ptr(d), B, N, L, _ptr(out), _ptr(osum), _stream()), "dh_one_rdm_product")
+    return torch.view_as_complex(out) if per_walker else None

@@ -112,6 +112,89 @@ __global__ void overlap_ratio_kernel(const float* __restrict__ logphi, const flo
   if (ratio_sq) ratio_sq[b] = (float)(m * m);
 }
 
+// ------------------------------------------------------------------ one-body reduced density matrix (one_rdm.py)
+// Y_{Q,Q,m}(theta, phi), m = -Q .. Q, as make_monopole_harm(Q, Q, m) builds it (one_rdm.py:34-58; with l = q the sum
+// has the single term s = 0): sqrt((2Q+1)/(4 pi) C(2Q, Q-m)^-1 ... ) folded into
+//   Y = sqrt((2Q+1)/(4 pi) * (Q-m)! (Q+m)! / (2Q)!) / 2^Q * (-1)^(Q-m) C(2Q, Q-m) (1-x)^((Q-m)/2) (1+x)^((Q+m)/2) e^{i m phi},
+// x = clip(cos theta, -1 + 1e-4, 1 - 1e-4).  One thread per (point, orbital); fp64.
+__global__ void lll_orbitals_kernel(const float* __restrict__ pts, int64_t n, int twoQ, float* __restrict__ out) {
+  const int L = twoQ + 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * L) return;
+  const int64_t pnt = t / L;
+  const int a = (int)(t - pnt * L);  // a = Q + m = 0 .. 2Q ;  Q - m = 2Q - a
+  const int bq = twoQ - a;
+  const double th = (double)pts[2 * pnt], ph = (double)pts[2 * pnt + 1];
+  const double x = fmin(1.0 - 1e-4, fmax(-1.0 + 1e-4, cos(th)));
+  // (Q-m)! (Q+m)! / (2Q)! = 1 / C(2Q, a);  norm * C(2Q, a) = sqrt((2Q+1)/(4 pi) C(2Q, a))
+  const double lc = lgamma((double)twoQ + 1.0) - lgamma((double)a + 1.0) - lgamma((double)bq + 1.0);
+  const double mag = sqrt((twoQ + 1.0) / (4.0 * M_PI)) * exp(0.5 * lc - 0.5 * twoQ * M_LN2) *
+                     pow(1.0 - x, 0.5 * bq) * pow(1.0 + x, 0.5 * a) * ((bq & 1) ? -1.0 : 1.0);
+  const double m = a - 0.5 * twoQ;
+  double sn, cs;
+  sincos(m * ph, &sn, &cs);
+  out[2 * t] = (float)(mag * cs);
+  out[2 * t + 1] = (float)(mag * sn);
+}
+
+// x' (B, N, N, 2): copy a of walker b is the walker with electron a moved to r'_b (one_rdm.py:92-94)
+__global__ void one_rdm_scatter_kernel(const float* __restrict__ x, const float* __restrict__ rp, int64_t B, int N,
+                                       float* __restrict__ xp) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * N * N) return;
+  const int e = (int)(t % N);
+  const int a = (int)((t / N) % N);
+  const int64_t b = t / ((int64_t)N * N);
+  const float2 v = e == a ? reinterpret_cast<const float2*>(rp)[b] : reinterpret_cast<const float2*>(x)[b * N + e];
+  reinterpret_cast<float2*>(xp)[t] = v;
+}
+
+// per walker: w_i = sum_a exp(logpsi'_a - logpsi) phi_i(r_a);  rdm_ij = 4 pi w_i conj(phi_j(r'))   (one_rdm.py:101-109)
+// One block per walker; optional per-walker output (B, L, L) c64 and batch sum (L, L) complex fp64 (atomics).
+__global__ void __launch_bounds__(256)
+one_rdm_product_kernel(const float* __restrict__ logpsi, const float* __restrict__ logpsi_prime,
+                       const float* __restrict__ phi, const float* __restrict__ phi_prime, int N, int L,
+                       float* __restrict__ out, double* __restrict__ out_sum) {
+  extern __shared__ double shw[];  // ratio [N][2] | w [L][2] | phi' [L][2]
+  double* ratio = shw;
+  double* w = ratio + 2 * N;
+  double* pp = w + 2 * L;
+  const int64_t b = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < N) {
+    const double dr = (double)logpsi_prime[2 * (b * N + tid)] - (double)logpsi[2 * b];
+    const double di = (double)logpsi_prime[2 * (b * N + tid) + 1] - (double)logpsi[2 * b + 1];
+    const double mg = exp(dr);
+    double sn, cs;
+    sincos(di, &sn, &cs);
+    ratio[2 * tid] = mg * cs;
+    ratio[2 * tid + 1] = mg * sn;
+  }
+  for (int j = tid; j < L; j += blockDim.x) {
+    pp[2 * j] = (double)phi_prime[2 * (b * L + j)];
+    pp[2 * j + 1] = (double)phi_prime[2 * (b * L + j) + 1];
+  }
+  __syncthreads();
+  for (int i = tid; i < L; i += blockDim.x) {
+    double wr = 0.0, wi = 0.0;
+    for (int a = 0; a < N; ++a) {
+      const double pr = (double)phi[2 * ((b * N + a) * L + i)], pi = (double)phi[2 * ((b * N + a) * L + i) + 1];
+      wr += ratio[2 * a] * pr - ratio[2 * a + 1] * pi;
+      wi += ratio[2 * a] * pi + ratio[2 * a + 1] * pr;
+    }
+    w[2 * i] = 4.0 * M_PI * wr;
+    w[2 * i + 1] = 4.0 * M_PI * wi;
+  }
+  __syncthreads();
+  for (int t = tid; t < L * L; t += blockDim.x) {
+    const int i = t / L, j = t % L;
+    const double re = w[2 * i] * pp[2 * j] + w[2 * i + 1] * pp[2 * j + 1];   // w_i * conj(p_j)
+    const double im = w[2 * i + 1] * pp[2 * j] - w[2 * i] * pp[2 * j + 1];
+    if (out) { out[2 * (b * L * L + t)] = (float)re; out[2 * (b * L * L + t) + 1] = (float)im; }
+    if (out_sum && !(isnan(re) || isnan(im))) { atomicAdd(&out_sum[2 * t], re); atomicAdd(&out_sum[2 * t + 1], im); }
+  }
+}
+
 static inline int obs_grid(int64_t items) {
   int64_t g = (items + OBS_THREADS - 1) / OBS_THREADS;
   const int64_t cap = 148 * 8;  // eight resident blocks of 256 threads on each of the 148 SMs
@@ -156,5 +239,33 @@ extern "C" int dh_overlap_ratio(const float* logphi, const float* logpsi, int64_
   if (B == 0) return 0;
   dh::overlap_ratio_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(logphi, logpsi, B, shift, out_ratio,
                                                                                        out_ratio_square);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dh_lll_orbitals(const float* points, int64_t n, int32_t flux, float* out_phi, void* stream) {
+  if (!points || !out_phi || n < 0 || flux < 0 || flux > 255) return DH_E_BADARG;
+  if (n == 0) return 0;
+  const int64_t items = n * (flux + 1);
+  dh::lll_orbitals_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(points, n, flux, out_phi);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dh_one_rdm_scatter(const float* x, const float* r_prime, int64_t B, int32_t N, float* out_x_prime,
+                                  void* stream) {
+  if (!x || !r_prime || !out_x_prime || B < 0 || N < 1) return DH_E_BADARG;
+  if (B == 0) return 0;
+  const int64_t items = B * N * N;
+  dh::one_rdm_scatter_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, r_prime, B, N, out_x_prime);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int dh_one_rdm_product(const float* logpsi, const float* logpsi_prime, const float* phi,
+                                  const float* phi_prime, int64_t B, int32_t N, int32_t L, float* out_rdm,
+                                  double* out_sum_inout, void* stream) {
+  if (!logpsi || !logpsi_prime || !phi || !phi_prime || B < 0 || N < 1 || N > 256 || L < 1 || L > 256) return DH_E_BADARG;
+  if (B == 0 || (!out_rdm && !out_sum_inout)) return 0;
+  const size_t smem = (size_t)(2 * N + 4 * L) * sizeof(double);
+  dh::one_rdm_product_kernel<<<(unsigned)B, 256, smem, (cudaStream_t)stream>>>(logpsi, logpsi_prime, phi, phi_prime, N, L,
+                                                                             out_rdm, out_sum_inout);
   return (int)cudaGetLastError();
 }

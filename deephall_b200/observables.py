@@ -9,6 +9,7 @@ are sharded one process per GPU, and where the reference sums over its pmap axis
   PairCorrelationEstimator  netobs_bridge/observables/pair_corr.py:29-65
   DensityEstimator          netobs_bridge/observables/density.py:24-57
   OverlapEstimator          netobs_bridge/observables/overlap.py:32-72
+  OneRDMEstimator           netobs_bridge/observables/one_rdm.py:28-124
 """
 from __future__ import annotations
 
@@ -125,3 +126,56 @@ class OverlapEstimator:
         den = _psum(torch.where(okq, ratio_square, torch.zeros_like(ratio_square)).to(torch.float64).sum())
         n2 = _psum(okq.sum().to(torch.float64))
         return {"overlap": ((num / n1).abs() ** 2 / (den / n2)).to(torch.float32)}
+
+
+class OneRDMEstimator:
+    """One-body reduced density matrix in the lowest-Landau-level basis Y_{Q,Q,m} (one_rdm.py:67-124).
+
+    Per walker one uniform point r' (one_rdm.py:61-64,116), N displaced copies of the walker evaluated by the network
+    in one batch of B N walkers, and rdm_ij = 4 pi sum_a Psi(R_a') / Psi(R) phi_i(r_a) conj(phi_j(r')).  `key` is the
+    Philox seed (or a PhiloxKey) the r' are drawn with; `evaluate` returns the per-walker matrices as the reference
+    does, or with `options["reduce"]` the batch mean only (an (L, L) matrix instead of B of them)."""
+
+    def __init__(self, network_apply, system: System, options: dict | None = None):
+        self.network_apply = network_apply
+        self.system = system
+        self.options = options or {}
+        self.flux = int(system.flux)
+        self.norbs = self.flux + 1
+        net = getattr(network_apply, "__self__", None)
+        self._plan = net.plan(system) if net is not None else None
+
+    def empty_val_state(self, steps: int):
+        return {"one_rdm": torch.zeros((steps, self.norbs, self.norbs), dtype=torch.complex64, device="cuda")}, {}
+
+    def uniform_sample(self, key, batch: int) -> torch.Tensor:
+        # one_rdm.py:61-64: theta = arccos(U(-1, 1)), phi = U(-pi, pi) -- the distribution dh_init_walkers draws
+        seed = int(getattr(key, "seed", key) or 0)
+        if self._plan is not None:
+            return self._plan.init_walkers(batch, seed=seed)[:, 0, :].contiguous()
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        u = torch.rand((batch, 2), generator=g, device="cuda")
+        return torch.stack([torch.acos(2 * u[:, 0] - 1), (2 * u[:, 1] - 1) * torch.pi], -1).contiguous()
+
+    def evaluate(self, i, params, key, data, system, state, aux_data=None, r_prime=None):
+        del i, system, aux_data
+        data = data.reshape(-1, *data.shape[-2:]).contiguous()
+        B, N = data.shape[0], data.shape[1]
+        if r_prime is None:
+            r_prime = self.uniform_sample(key, B)
+        data_prime = _native.one_rdm_scatter(data, r_prime)                      # one_rdm.py:92-94
+        logpsi = self.network_apply(params, data)                                # :96
+        logpsi_prime = self.network_apply(params, data_prime.reshape(B * N, N, 2)).reshape(B, N)  # :97
+        varphi = _native.lll_orbitals(data, self.flux)                           # :98
+        varphi_prime = _native.lll_orbitals(r_prime, self.flux)                  # :99
+        if self.options.get("reduce"):
+            total = torch.zeros((self.norbs, self.norbs), dtype=torch.complex128, device=data.device)
+            _native.one_rdm_product(logpsi, logpsi_prime, varphi, varphi_prime, per_walker=False, out_sum=total)
+            total = _psum(total) / (B * constants.world_size())
+            return {"one_rdm": total.to(torch.complex64)}, state
+        return {"one_rdm": _native.one_rdm_product(logpsi, logpsi_prime, varphi, varphi_prime)}, state
+
+    def digest(self, all_values, state):
+        del state
+        one_rdm = all_values["one_rdm"].mean(0)  # one_rdm.py:121-124
+        return {"diagonal": torch.diagonal(one_rdm), "trace": torch.trace(one_rdm)}

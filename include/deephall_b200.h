@@ -228,6 +228,21 @@ int dh_overlap_sum(const float* logphi, const float* logpsi, int64_t B, double* 
 int dh_overlap_ratio(const float* logphi, const float* logpsi, int64_t B, const double* shift,
                      float* out_ratio, float* out_ratio_square, void* stream);
 
+/* One-body reduced density matrix <- OneRDMEstimator.eval_product (netobs_bridge/observables/one_rdm.py:91-109).
+ * dh_lll_orbitals:    out_phi (n, flux+1, 2) f32 = Y_{Q,Q,m}(points), m = -Q..Q, Q = flux/2, exactly as
+ *                     make_monopole_harm(Q, Q, m) defines them (one_rdm.py:34-58, incl. the clip of cos theta).
+ * dh_one_rdm_scatter: out_x_prime (B, N, N, 2): copy a of walker b = the walker with electron a moved to
+ *                     r_prime[b] (B, 2) (one_rdm.py:92-94); feed it to dh_logpsi as B*N walkers.
+ * dh_one_rdm_product: per walker rdm_ij = 4 pi sum_a exp(logpsi'_a - logpsi) phi_i(r_a) conj(phi_j(r')) with
+ *                     logpsi (B,2), logpsi_prime (B,N,2), phi (B,N,L,2), phi_prime (B,L,2);
+ *                     out_rdm (B,L,L,2) f32 and/or out_sum_inout (L,L,2) f64 += the sum over non-NaN walkers. */
+int dh_lll_orbitals(const float* points, int64_t n, int32_t flux, float* out_phi, void* stream);
+int dh_one_rdm_scatter(const float* x, const float* r_prime, int64_t B, int32_t N, float* out_x_prime,
+                       void* stream);
+int dh_one_rdm_product(const float* logpsi, const float* logpsi_prime, const float* phi,
+                       const float* phi_prime, int64_t B, int32_t N, int32_t L, float* out_rdm,
+                       double* out_sum_inout, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -927,3 +927,60 @@ def test_estimators_through_the_reference_surface(nat):
     assert abs(s_pc["pair_corr"].cpu().double().numpy() - want_pc).max() < 1e-5
     assert (s_de["map"].cpu().numpy() == want_de).all()
     assert pc.digest({}, s_pc) == {} and de.digest({}, s_de) == {}
+
+
+@pytest.mark.parametrize("flux", [1, 2, 6, 33])
+def test_lll_orbitals_parity(nat, flux):
+    """dh_lll_orbitals vs make_monopole_harm(Q, Q, m) restated in numpy (one_rdm.py:34-58), poles and the clip included."""
+    from oracle import observables as OO
+
+    pts = _uniform_walkers(200, 1, seed=flux)[:, 0, :].contiguous()
+    pts[0, 0], pts[1, 0], pts[2, 0] = 0.0, math.pi, 1e-3
+    got = nat.lll_orbitals(pts, flux).cpu().numpy()
+    want = OO.lll_orbitals(flux, pts.cpu().numpy())
+    assert got.shape == want.shape == (200, flux + 1)
+    assert abs(got - want).max() <= 2e-6 * abs(want).max()
+    # orthonormality on the sphere is what makes trace(1-RDM) = N: sum_m |Y_m|^2 = (2Q+1)/(4 pi) away from the clip
+    assert abs((abs(want[3:]) ** 2).sum(-1) - (flux + 1) / (4 * math.pi)).max() < 1e-3
+
+
+def test_one_rdm_estimator(nat):
+    """OneRDMEstimator (one_rdm.py:91-124): per-walker matrices against the numpy restatement fed with the same
+    r', log psi and log psi'; on the equilibrated Laughlin ground state the digest gives trace = N and a uniform
+    diagonal N / (2Q + 1) (the closed form that pins the restatement)."""
+    from deephall_b200 import mcmc, networks, observables
+    from deephall_b200.config import Network, System
+    from oracle import observables as OO
+
+    system = System(flux=6, nspins=(3, 0))
+    N, L, B = 3, 7, 4096
+    lau = networks.make_network(system, Network(type="laughlin"))
+    params = torch.zeros(0, device=DEV)
+    data = mcmc.init_guess(0, B, N, lau)
+    step = mcmc.make_mcmc_step(lau.apply, B, steps=10)
+    for it in range(30):
+        data, _ = step(params, data, mcmc.PhiloxKey(100 + it), 0.5)
+    est = observables.OneRDMEstimator(lau.apply, system)
+    r_prime = est.uniform_sample(7, B)
+    assert r_prime.shape == (B, 2) and 0 <= r_prime[:, 0].min() and r_prime[:, 0].max() <= math.pi
+    vals, _ = est.evaluate(0, params, 7, data, system, {}, r_prime=r_prime)
+    got = vals["one_rdm"].cpu().numpy()
+    assert got.shape == (B, L, L)
+    dp = nat.one_rdm_scatter(data, r_prime)
+    assert (dp.cpu().numpy() == OO.one_rdm_data_prime(data.cpu().numpy(), r_prime.cpu().numpy())).all()
+    logpsi = lau.apply(params, data).cpu().numpy()
+    logpsi_prime = lau.apply(params, dp.reshape(B * N, N, 2)).reshape(B, N).cpu().numpy()
+    want = OO.one_rdm_product(6, data.cpu().numpy(), r_prime.cpu().numpy(), logpsi, logpsi_prime)
+    assert abs(got - want).max() <= 1e-5 * abs(want).max()
+    # digest over a few evaluation steps; reduced form agrees with the mean of the per-walker matrices
+    est_r = observables.OneRDMEstimator(lau.apply, system, {"reduce": True})
+    red, _ = est_r.evaluate(0, params, 7, data, system, {}, r_prime=r_prime)
+    assert abs(red["one_rdm"].cpu().numpy() - want.mean(0)).max() < 1e-5 * abs(want).max()
+    steps = []
+    for it in range(4):
+        data, _ = step(params, data, mcmc.PhiloxKey(200 + it), 0.5)
+        v, _ = est_r.evaluate(it, params, 300 + it, data, system, {})
+        steps.append(v["one_rdm"])
+    dg = est.digest({"one_rdm": torch.stack(steps)}, {})
+    assert abs(dg["trace"].item() - N) < 0.1
+    assert (dg["diagonal"] - N / L).abs().max().item() < 0.04

@@ -159,3 +159,30 @@ def test_estimator_oracle_closed_forms():
     assert abs(OO.overlap_digest(ev["ratio"], ev["ratio_square"]) - 1) < 1e-12
     ev = OO.overlap_evaluate(lp + 0.5 * rng.normal(size=500), lp)
     assert OO.overlap_digest(ev["ratio"], ev["ratio_square"]) < 0.95
+
+
+def test_one_rdm_oracle_on_the_filled_shell():
+    # one_rdm.py:91-124 restated.  Closed form: for the filled lowest Landau level (N = 2Q + 1 free fermions in the
+    # orbitals Y_{Q,Q,m}) every orbital is occupied once: the 1-RDM is the identity, trace N.  Sampling |psi|^2 is not
+    # needed for an exact check: with r' uniform the estimator is unbiased walker by walker only on average, so the
+    # mean over an equilibrated batch is compared statistically.
+    import numpy as np
+
+    from oracle import observables as OO
+
+    N, flux, B = 3, 2, 3000
+    gen = torch.Generator().manual_seed(0)
+    f = make_lll(N, flux / 2)
+    x = OM.init_guess(gen, B, N, torch.float64)
+    for _ in range(30):
+        x, _ = OM.mcmc_step(f, x, OM.draw_randoms(gen, 10, B, N, torch.float64), 0.7)
+    rng = np.random.default_rng(1)
+    rp = np.stack([np.arccos(rng.uniform(-1, 1, B)), rng.uniform(-np.pi, np.pi, B)], -1)
+    xn = x.numpy()
+    dp = OO.one_rdm_data_prime(xn, rp)
+    assert dp.shape == (B, N, N, 2) and (dp[5, 1, 1] == rp[5]).all() and (dp[5, 1, 0] == xn[5, 0]).all()
+    lp = f(x).numpy()
+    lpp = f(torch.from_numpy(dp.reshape(B * N, N, 2))).numpy().reshape(B, N)
+    rdm = OO.one_rdm_product(flux, xn, rp, lp, lpp).mean(0)
+    assert abs(rdm - np.eye(flux + 1)).max() < 0.12
+    assert abs(np.trace(rdm) - N) < 0.1
