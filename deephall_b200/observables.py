@@ -151,6 +151,8 @@ class OneRDMEstimator:
     def uniform_sample(self, key, batch: int) -> torch.Tensor:
         # one_rdm.py:61-64: theta = arccos(U(-1, 1)), phi = U(-pi, pi) -- the distribution dh_init_walkers draws
         seed = int(getattr(key, "seed", key) or 0)
+        if hasattr(key, "offset"):  # PhiloxKey: every subkey (offset block of 2^20) draws its own points
+            seed = (seed + 0x9E3779B97F4A7C15 * ((int(key.offset) >> 20) + 1)) & 0x7FFFFFFFFFFFFFFF
         if self._plan is not None:
             return self._plan.init_walkers(batch, seed=seed)[:, 0, :].contiguous()
         g = torch.Generator(device="cuda").manual_seed(seed)

@@ -984,3 +984,54 @@ def test_one_rdm_estimator(nat):
     dg = est.digest({"one_rdm": torch.stack(steps)}, {})
     assert abs(dg["trace"].item() - N) < 0.1
     assert (dg["diagonal"] - N / L).abs().max().item() < 0.04
+
+
+def test_netobs_adaptor_and_evaluation_loop(nat, tmp_path):
+    """DeepHallAdaptor (netobs_bridge/adaptor.py:35-121): restore from a checkpoint in the reference's wire format +
+    config.yml, the call_* methods, and the estimators driven through walk -> evaluate -> digest."""
+    import dataclasses
+
+    import yaml
+
+    from deephall_b200 import checkpoint, hamiltonian, mcmc, netobs_bridge, networks, observables
+    from deephall_b200.config import Config, Network, System
+    from deephall_b200.optimizers import CheckpointState
+
+    for net_type in ("psiformer", "laughlin"):
+        cfg = Config(batch_size=512, seed=3, system=System(flux=6, nspins=(3, 0)), network=Network(type=net_type))
+        model = networks.make_network(cfg.system, cfg.network)
+        params = model.init(1) if net_type == "psiformer" else torch.zeros(0, device=DEV)
+        data = mcmc.init_guess(5, cfg.batch_size, 3, model)
+        d = tmp_path / net_type
+        d.mkdir()
+        ck = d / "ckpt_000007.npz"
+        checkpoint.save_checkpoint(ck, 7, model, CheckpointState(params, data, None, 0.25))
+        as_dict = dataclasses.asdict(cfg)
+        as_dict["system"]["nspins"] = list(as_dict["system"]["nspins"])
+        (d / "config.yml").write_text(yaml.safe_dump(as_dict))
+
+        ad = netobs_bridge.DeepHallAdaptor()
+        with pytest.raises(ValueError):
+            ad.restore(None)
+        p2, x2, system, aux = ad.restore(str(ck))
+        assert torch.equal(p2, params) and torch.equal(x2, data)
+        assert system["flux"] == 6 and system["spins"] == [3, 0] and abs(aux["mcmc_width"] - 0.25) < 1e-7
+        sign, lp = ad.call_signed_network(p2, x2, system)
+        assert float(sign) == 1.0 and torch.equal(lp, model.apply(params, data))
+        el, obs = hamiltonian.local_energy(model.apply, cfg.system)(params, data)
+        assert torch.equal(ad.call_local_kinetic_energy(p2, None, x2, system), obs["kinetic"])
+        assert torch.allclose(ad.call_local_potential_energy(p2, None, x2, system), obs["potential"] * cfg.system.interaction_strength)
+        walk = ad.make_walking_step(None, 5, system)
+        x3, aux3 = walk(mcmc.PhiloxKey(11), p2, x2.clone(), aux)
+        assert x3.shape == x2.shape and not torch.equal(x3, x2) and aux3 is aux
+
+        dg, vals, st = netobs_bridge.evaluate_observable(ad, observables.PairCorrelationEstimator({"bins": 20}), str(ck), steps=3)
+        g = st["pair_corr"] / 3
+        assert dg == {} and torch.isfinite(g).all() and 0.3 < g.mean().item() < 1.2
+        assert g[0].item() < 0.5 * g.max().item()  # the correlation hole at short distance
+        dg, vals, _ = netobs_bridge.evaluate_observable(ad, observables.OverlapEstimator(ad.network, cfg.system, cfg.network), str(ck), steps=3)
+        assert vals["ratio"].shape == (3,) and 0.0 <= dg["overlap"].item() <= 1.0 + 1e-6
+        if net_type == "laughlin":
+            assert abs(dg["overlap"].item() - 1) < 1e-6
+        dg, vals, _ = netobs_bridge.evaluate_observable(ad, observables.OneRDMEstimator(ad.network, cfg.system), str(ck), steps=2)
+        assert vals["one_rdm"].shape == (2, 7, 7) and torch.isfinite(torch.view_as_real(dg["trace"])).all()
