@@ -314,8 +314,13 @@ extern "C" int dh_param_layout(const dh_plan* p, dh_param_entry* entries, int32_
 
 size_t vjp_ws_floats(const dh_plan* p, int64_t Bc);  // api_vjp.cu
 
-static inline size_t fwd_ws_copies(const dh_plan* p, bool jets, int64_t B) {
-  return (dual_stream_env() && B > pick_chunk(p, jets, B)) ? 2 : 1;
+// floats of forward workspace for a pass over B walkers (all copies of the chunk interleave)
+static inline size_t fwd_ws_floats(const dh_plan* p, bool jets, int64_t B) {
+  int copies;
+  const int64_t chunk = plan_chunks(p, jets, B, &copies);
+  const size_t one = carve_fwd(p, nullptr, pick_chunk(p, jets, B), jets, false).floats;  // single-stream fallback always fits
+  const size_t two = carve_fwd(p, nullptr, chunk, jets, false).floats * copies;
+  return one > two ? one : two;
 }
 
 extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* bytes) {
@@ -323,11 +328,9 @@ extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* b
   size_t fl = 0;
   switch (op) {
     // (passes of two or more chunks interleave them on two streams: two activation workspaces)
-    case DH_OP_LOGPSI: fl = carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats * fwd_ws_copies(p, false, B); break;
-    case DH_OP_LOCAL_ENERGY: fl = carve_fwd(p, nullptr, pick_chunk(p, true, B), true, false).floats * fwd_ws_copies(p, true, B); break;
-    case DH_OP_MCMC:
-      fl = carve_mcmc(p, nullptr, B).floats + carve_fwd(p, nullptr, pick_chunk(p, false, B), false, false).floats;
-      break;
+    case DH_OP_LOGPSI: fl = fwd_ws_floats(p, false, B); break;
+    case DH_OP_LOCAL_ENERGY: fl = fwd_ws_floats(p, true, B); break;
+    case DH_OP_MCMC: fl = carve_mcmc(p, nullptr, B).floats + fwd_ws_floats(p, false, B); break;
     case DH_OP_VJP: fl = vjp_ws_floats(p, pick_chunk(p, false, B)); break;
     case DH_OP_KFAC:
       fl = vjp_ws_floats(p, pick_chunk(p, false, B)) + al((size_t)pick_chunk(p, false, B) * 2) + al((size_t)p->nparams);
@@ -604,16 +607,21 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
   if (B == 0) return 0;
   if ((!params && p->nparams > 0) || !x) return DH_E_BADARG;
   if (B == 0) return 0;
-  const int64_t chunk = pick_chunk(p, jets, B);
+  int copies = 1;
+  int64_t chunk = plan_chunks(p, jets, B, &copies);
   float* base = align_ws(ws);
   FwdWs w = carve_fwd(p, base, chunk, jets, false);
-  if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
   // Chunk interleave: with room for a second activation workspace, odd chunks run on the plan's side stream
   // (forked from and joined back into `s` by events, so the call keeps stream semantics and stays capturable).
   // Chunks are independent; one chunk's launch gaps and wave tails are filled by the other's kernels.
   FwdWs w2 = w;
-  bool dual = dual_stream_env() && B > chunk && !p->prof_on &&
-              (size_t)((char*)(base + 2 * w.floats) - (char*)ws) <= ws_bytes;
+  bool dual = copies == 2 && !p->prof_on && ws && (size_t)((char*)(base + 2 * w.floats) - (char*)ws) <= ws_bytes;
+  if (!dual) {  // single stream: the plain chunking
+    chunk = pick_chunk(p, jets, B);
+    w = carve_fwd(p, base, chunk, jets, false);
+    w2 = w;
+  }
+  if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
   if (dual && !p->side_stream) {
     if (cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

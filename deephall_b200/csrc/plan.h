@@ -127,6 +127,23 @@ static inline int64_t pick_chunk(const dh_plan* p, bool jets, int64_t B) {
   return B < c ? B : c;
 }
 
+// Chunk interleave plan of a forward pass: walkers per chunk and the number of activation workspaces (1 or 2).
+// Two or more chunks alternate between two streams.  A value-only pass (Metropolis sweep, log psi) that fits one chunk
+// is cut in two halves when it has at least DH_DUAL_VALUE_MIN walkers (default 2048; 0 = never), so that the two
+// halves' short launches fill each other's gaps.
+static inline int64_t plan_chunks(const dh_plan* p, bool jets, int64_t B, int* copies) {
+  int64_t chunk = pick_chunk(p, jets, B);
+  *copies = 1;
+  if (!dual_stream_env()) return chunk;
+  if (B > chunk) { *copies = 2; return chunk; }
+  static const long vmin = getenv("DH_DUAL_VALUE_MIN") ? atol(getenv("DH_DUAL_VALUE_MIN")) : 2048;
+  if (!jets && vmin > 0 && B >= vmin && p->cfg.chunk_walkers <= 0) {
+    chunk = ((B + 1) / 2 + 31) / 32 * 32;
+    *copies = 2;
+  }
+  return chunk;
+}
+
 static inline FwdWs carve_fwd(const dh_plan* p, float* base, int64_t Bc, bool jets, bool keep_inverse) {
   const int R = jets ? 2 * p->N + 8 : 1;
   const size_t rows = p->laughlin ? 0 : (size_t)Bc * p->N * R;  // the analytic network has no body activations
