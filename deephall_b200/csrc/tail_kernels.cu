@@ -498,7 +498,7 @@ constexpr int OCV_THREADS = 160;
 template <int VEC>
 __global__ void __launch_bounds__(OCV_THREADS, 5)
 orbital_contract_vec_kernel(const float* __restrict__ c, const float* __restrict__ x, const double* __restrict__ normfac,
-                            float* __restrict__ Mj, TailDims dm) {
+                            float* __restrict__ Mj, TailDims dm, int prefetch) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int N = dm.N, R = dm.R, L = dm.L, K = dm.K;
   dcplx* upow = reinterpret_cast<dcplx*>(smraw);
@@ -509,10 +509,19 @@ orbital_contract_vec_kernel(const float* __restrict__ c, const float* __restrict
   const int64_t bi = blockIdx.x;
   const int64_t b = bi / N;
   const int i = (int)(bi % N);
-  envelope_jets(x[bi * 2], x[bi * 2 + 1], dm.twoQ, normfac, upow, vpow, env, ENV_SLOTS);  // ends with __syncthreads
   const int LNK = L * NK;
   const int64_t ldc = (dm.n_dn > 0 ? 4 : 2) * (int64_t)LNK;
   const float* cbase = c + bi * R * ldc + ((dm.n_dn > 0 && i >= dm.n_up) ? 2 * LNK : 0);
+  if (prefetch) {
+    // the electron's coefficient rows (R x 2 LNK floats, contiguous per row) start their way from HBM to L2 while the
+    // fp64 envelope prologue runs: the dot loops below then stream from L2
+    const int lines_per_row = (2 * LNK * (int)sizeof(float) + 127) / 128;
+    for (int t = threadIdx.x; t < R * lines_per_row; t += blockDim.x) {
+      const int r = t / lines_per_row, ln = t - r * lines_per_row;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(cbase + (int64_t)r * ldc) + (size_t)ln * 128));
+    }
+  }
+  envelope_jets(x[bi * 2], x[bi * 2 + 1], dm.twoQ, normfac, upow, vpow, env, ENV_SLOTS);  // ends with __syncthreads
   Rows rw(N, true);
   const int q = NK / VEC;
   const int ndots = R + 14;
@@ -600,13 +609,14 @@ int orbital_contract(const float* c, const float* x, const double* normfac, floa
   static const bool scalar_form = getenv("DH_ORB_CONTRACT") && strcmp(getenv("DH_ORB_CONTRACT"), "scalar") == 0;
   const int NK = d.N * d.K;
   const size_t smem_v = smem + (size_t)(d.R + 14) * NK * 2 * sizeof(float);
+  static const int prefetch = !(getenv("DH_ORB_PREFETCH") && atoi(getenv("DH_ORB_PREFETCH")) == 0);
   if (!scalar_form && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && smem_v <= 48 * 1024) {
     if (NK % 4 == 0) {
-      orbital_contract_vec_kernel<4><<<(unsigned)(B * d.N), OCV_THREADS, smem_v, s>>>(c, x, normfac, Mj, d);
+      orbital_contract_vec_kernel<4><<<(unsigned)(B * d.N), OCV_THREADS, smem_v, s>>>(c, x, normfac, Mj, d, prefetch);
       return (int)cudaGetLastError();
     }
     if (NK % 2 == 0) {
-      orbital_contract_vec_kernel<2><<<(unsigned)(B * d.N), OCV_THREADS, smem_v, s>>>(c, x, normfac, Mj, d);
+      orbital_contract_vec_kernel<2><<<(unsigned)(B * d.N), OCV_THREADS, smem_v, s>>>(c, x, normfac, Mj, d, prefetch);
       return (int)cudaGetLastError();
     }
   }
