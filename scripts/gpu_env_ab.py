@@ -25,6 +25,16 @@ if sys.argv[1] == "arm":
         out = plan.local_energy(params, x)
     e1.record()
     torch.cuda.synchronize()
+    for i in range(2):
+        plan.mcmc_sweep(params, x, steps=10, width=0.1, seed=5, offset=i * 10)
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for i in range(5):
+        plan.mcmc_sweep(params, x, steps=10, width=0.1, seed=5, offset=100 + i * 10)
+    s1.record()
+    torch.cuda.synchronize()
+    print(f"{var}={os.environ.get(var)} sweep(10) {s0.elapsed_time(s1) / 5:.3f} ms", flush=True)
     plan.profile_begin()
     out = plan.local_energy(params, x)
     prof = plan.profile_end()
