@@ -39,6 +39,56 @@ def _features(data: torch.Tensor, n_up: int) -> torch.Tensor:
     return torch.stack([torch.cos(theta), torch.sin(theta) * torch.cos(phi), torch.sin(theta) * torch.sin(phi), spin], dim=-1)
 
 
+_SIDE_STREAM = None
+
+
+def _batched_inverses(groups: dict) -> dict:
+    """{n: [n x n SPD matrices]} -> {n: (count, n, n) inverses}.
+
+    dh_spd_inverse runs one Gauss-Jordan block per matrix, so a launch with 13 matrices leaves 135 SMs idle and two
+    launches of 13 and 14 matrices take twice the time of one with 27.  All sizes up to 320 therefore go out as ONE
+    batch: a smaller matrix is embedded as diag(A, I) in the largest size of the batch (its inverse is diag(A^-1, I)).
+    The few larger factors (the orbital projection's 409 rows) are inverted by the library on a side stream at the
+    same time."""
+    global _SIDE_STREAM
+    small = {n: ms for n, ms in groups.items() if n <= 320}
+    large = {n: ms for n, ms in groups.items() if n > 320}
+    out = {}
+    cur = torch.cuda.current_stream()
+    done = None
+    if large:
+        if _SIDE_STREAM is None:
+            _SIDE_STREAM = torch.cuda.Stream()
+        stacked = {n: torch.stack(ms) for n, ms in large.items()}
+        _SIDE_STREAM.wait_stream(cur)
+        with torch.cuda.stream(_SIDE_STREAM):
+            for n, st in stacked.items():
+                out[n] = torch.linalg.inv(st)
+                out[n].record_stream(cur)
+                st.record_stream(_SIDE_STREAM)
+        done = _SIDE_STREAM
+    if small:
+        nmax = max(small)
+        dev = next(iter(small.values()))[0].device
+        total = sum(len(ms) for ms in small.values())
+        batch = torch.zeros((total, nmax, nmax), dtype=torch.float32, device=dev)
+        k = 0
+        where = {}
+        for n, ms in small.items():
+            where[n] = (k, len(ms))
+            batch[k : k + len(ms), :n, :n] = torch.stack(ms)
+            if n < nmax:
+                idx = torch.arange(n, nmax, device=dev)
+                batch[k : k + len(ms), idx, idx] = 1.0
+            k += len(ms)
+        inv = _native.spd_inverse(batch)
+        for n, (k0, cnt) in where.items():
+            out[n] = inv[k0 : k0 + cnt, :n, :n]
+    if done is not None:
+        cur.wait_stream(done)
+    return out
+
+
 def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_constraint=1e-3, curvature_ema=0.95,
                             damping=1e-3):
     """-> (init, step) like optimizers/kfac.py:198-241.  `network` is `model.apply` of a deephall_b200 Psiformer."""
@@ -122,7 +172,7 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
             blocks.append((e, (A.shape[0], ja), (G.shape[0], len(ig) - 1), ck))
         # (dh_spd_inverse: one Gauss-Jordan block per matrix, no library initialisation or workspace; it beats the
         # library's batched LU up to ~300 rows, scripts/gpu_kfac_timing.py)
-        inv = {n: (_native.spd_inverse(torch.stack(ms)) if n <= 320 else torch.linalg.inv(torch.stack(ms))) for n, ms in groups.items()}
+        inv = _batched_inverses(groups)
         # pass 2: U = A_inv V G_inv / (c_k^2 npw)
         for e, (na, ja), (ng, jg), ck in blocks:
             din, dout, hb, npw, ko = e["in_dim"], e["out_dim"], e["has_bias"], e["rows_per_walker"], e["kernel_offset"]
