@@ -35,6 +35,23 @@ static double binom(int n, int k) {
 
 extern "C" const char* dh_version(void) { return "deephall_b200 0.1 (sm_100a)"; }
 
+// side stream + fork / join events of the chunk interleave; made at plan creation so that the ops never allocate
+static bool ensure_side_stream(dh_plan* p) {
+  if (p->side_stream) return true;
+  if (cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    if (p->side_stream) cudaStreamDestroy(p->side_stream);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    p->side_stream = nullptr;
+    p->ev_fork = p->ev_join = nullptr;
+    return false;
+  }
+  return true;
+}
+
 extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   if (!cfg || !out) return DH_E_BADARG;
   if (cfg->n_up < 1 || cfg->flux < 0 || cfg->ndets < 1 || cfg->num_heads < 1 || cfg->heads_dim < 1 ||
@@ -114,6 +131,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     if (e1 != cudaSuccess) { delete p; return (int)e1; }
     e1 = cudaMemcpy(p->d_normfac, ones.data(), p->L * sizeof(double), cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess) { cudaFree(p->d_normfac); delete p; return (int)e1; }
+    if (dual_stream_env()) ensure_side_stream(p);
     *out = p;
     return 0;
   }
@@ -284,6 +302,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   if (e != cudaSuccess) { delete p; return (int)e; }
   e = cudaMemcpy(p->d_normfac, nf.data(), L * sizeof(double), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { cudaFree(p->d_normfac); delete p; return (int)e; }
+  if (dual_stream_env()) ensure_side_stream(p);
   *out = p;
   return 0;
 }
@@ -615,22 +634,14 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
   // (forked from and joined back into `s` by events, so the call keeps stream semantics and stays capturable).
   // Chunks are independent; one chunk's launch gaps and wave tails are filled by the other's kernels.
   FwdWs w2 = w;
-  bool dual = copies == 2 && !p->prof_on && ws && (size_t)((char*)(base + 2 * w.floats) - (char*)ws) <= ws_bytes;
+  const bool dual = copies == 2 && !p->prof_on && p->side_stream && ws &&
+                    (size_t)((char*)(base + 2 * w.floats) - (char*)ws) <= ws_bytes;
   if (!dual) {  // single stream: the plain chunking
     chunk = pick_chunk(p, jets, B);
     w = carve_fwd(p, base, chunk, jets, false);
     w2 = w;
   }
   if (!ws || (size_t)((char*)(base + w.floats) - (char*)ws) > ws_bytes) return DH_E_WORKSPACE;
-  if (dual && !p->side_stream) {
-    if (cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) {
-      cudaGetLastError();
-      p->side_stream = nullptr;
-      dual = false;
-    }
-  }
   if (dual) {
     w2 = carve_fwd(p, base + w.floats, chunk, jets, false);
     if (cudaEventRecord(p->ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0) != cudaSuccess)

@@ -18,6 +18,8 @@
  *   dh_slogdet         <- jnp.linalg.slogdet + tail         psiformer.py:74-76
  *   dh_param_layout    <- the flax parameter tree           psiformer.py, blocks.py
  *   dh_init_walkers    <- init_guess                        train.py:40-54
+ *   dh_pair_correlation, dh_density_histogram, dh_overlap_sum/_ratio, dh_lll_orbitals, dh_one_rdm_scatter/_product
+ *                      <- the NetObs estimators            netobs_bridge/observables/*.py (see the end of this file)
  *   network_type = 1   <- Laughlin(nspins, flux).apply      networks/laughlin.py:19-100 (ground state, quasihole, quasiparticle;
  *                         no parameters: dh_param_count = 0, dh_logpsi_vjp writes nothing)
  *
@@ -27,7 +29,9 @@
  *   - walkers `x` are (B, N, 2) = (theta, phi), exactly the reference layout (mcmc.py:68);
  *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*), performs
  *     no allocation and no host synchronisation; the caller owns every buffer including
- *     the workspace (size from dh_workspace_bytes);
+ *     the workspace (size from dh_workspace_bytes).  A pass over more walkers than one internal chunk
+ *     alternates its chunks between `stream` and a stream the plan owns (created by dh_plan_create,
+ *     forked from and joined back into `stream` by events): to the caller the call is still ordered on `stream`;
  *   - return value: 0 = ok, >0 = cudaError_t, <0 = DH_E_* argument error.  Numerical
  *     pathologies follow the reference: NaN/-inf propagate into the outputs
  *     (singular determinant -> log|psi| = -inf, NaN proposal -> rejected, mcmc.py:59).
