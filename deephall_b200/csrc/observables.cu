@@ -116,25 +116,52 @@ __global__ void overlap_ratio_kernel(const float* __restrict__ logphi, const flo
 // Y_{Q,Q,m}(theta, phi), m = -Q .. Q, as make_monopole_harm(Q, Q, m) builds it (one_rdm.py:34-58; with l = q the sum
 // has the single term s = 0): sqrt((2Q+1)/(4 pi) C(2Q, Q-m)^-1 ... ) folded into
 //   Y = sqrt((2Q+1)/(4 pi) * (Q-m)! (Q+m)! / (2Q)!) / 2^Q * (-1)^(Q-m) C(2Q, Q-m) (1-x)^((Q-m)/2) (1+x)^((Q+m)/2) e^{i m phi},
-// x = clip(cos theta, -1 + 1e-4, 1 - 1e-4).  One thread per (point, orbital); fp64.
-__global__ void lll_orbitals_kernel(const float* __restrict__ pts, int64_t n, int twoQ, float* __restrict__ out) {
+// x = clip(cos theta, -1 + 1e-4, 1 - 1e-4); fp64.
+// One block = 8 points x all orbitals.  Per block the L values 0.5 ln C(2Q, a) go into shared memory once; per point
+// the fp64 transcendental work is one cos, two logs and one sincos (by lanes 0..7 of the block's first warp, one
+// point each); per (point, orbital) it is one exp and one step of the phase table e^{i m phi} = e^{-i Q phi} (e^{i phi})^a,
+// built per point by repeated complex multiplication in fp64 (2Q + 1 <= 256 steps).
+constexpr int LLL_PTS = 8;
+__global__ void __launch_bounds__(256)
+lll_orbitals_kernel(const float* __restrict__ pts, int64_t n, int twoQ, float* __restrict__ out) {
+  extern __shared__ double shl[];  // lc[L] | per point: l1, l2 | phase table [LLL_PTS][L][2]
   const int L = twoQ + 1;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n * L) return;
-  const int64_t pnt = t / L;
-  const int a = (int)(t - pnt * L);  // a = Q + m = 0 .. 2Q ;  Q - m = 2Q - a
-  const int bq = twoQ - a;
-  const double th = (double)pts[2 * pnt], ph = (double)pts[2 * pnt + 1];
-  const double x = fmin(1.0 - 1e-4, fmax(-1.0 + 1e-4, cos(th)));
-  // (Q-m)! (Q+m)! / (2Q)! = 1 / C(2Q, a);  norm * C(2Q, a) = sqrt((2Q+1)/(4 pi) C(2Q, a))
-  const double lc = lgamma((double)twoQ + 1.0) - lgamma((double)a + 1.0) - lgamma((double)bq + 1.0);
-  const double mag = sqrt((twoQ + 1.0) / (4.0 * M_PI)) * exp(0.5 * lc - 0.5 * twoQ * M_LN2) *
-                     pow(1.0 - x, 0.5 * bq) * pow(1.0 + x, 0.5 * a) * ((bq & 1) ? -1.0 : 1.0);
-  const double m = a - 0.5 * twoQ;
-  double sn, cs;
-  sincos(m * ph, &sn, &cs);
-  out[2 * t] = (float)(mag * cs);
-  out[2 * t + 1] = (float)(mag * sn);
+  double* lc = shl;
+  double* pl = lc + L;                  // [LLL_PTS][2]
+  double* ph = pl + 2 * LLL_PTS;        // [LLL_PTS][L][2]
+  const int64_t p0 = (int64_t)blockIdx.x * LLL_PTS;
+  const int tid = threadIdx.x;
+  for (int a = tid; a < L; a += blockDim.x)
+    lc[a] = 0.5 * (lgamma((double)twoQ + 1.0) - lgamma((double)a + 1.0) - lgamma((double)(twoQ - a) + 1.0));
+  if (tid < LLL_PTS && p0 + tid < n) {
+    const double th = (double)pts[2 * (p0 + tid)], phi = (double)pts[2 * (p0 + tid) + 1];
+    const double x = fmin(1.0 - 1e-4, fmax(-1.0 + 1e-4, cos(th)));  // one_rdm.py:49
+    pl[2 * tid] = 0.5 * log(0.5 * (1.0 - x));
+    pl[2 * tid + 1] = 0.5 * log(0.5 * (1.0 + x));
+    double s1, c1, s0, c0;
+    sincos(phi, &s1, &c1);
+    sincos(-0.5 * twoQ * phi, &s0, &c0);
+    double* t = ph + (size_t)tid * L * 2;
+    for (int a = 0; a < L; ++a) {
+      t[2 * a] = c0; t[2 * a + 1] = s0;
+      const double cn = c0 * c1 - s0 * s1;
+      s0 = c0 * s1 + s0 * c1;
+      c0 = cn;
+    }
+  }
+  __syncthreads();
+  const double norm = sqrt((twoQ + 1.0) / (4.0 * M_PI));
+  for (int t = tid; t < LLL_PTS * L; t += blockDim.x) {
+    const int q = t / L, a = t - q * L;
+    if (p0 + q >= n) break;
+    const int bq = twoQ - a;
+    // Y = sqrt((2Q+1)/(4 pi) C(2Q,a)) (-1)^(Q-m) ((1-x)/2)^((Q-m)/2) ((1+x)/2)^((Q+m)/2) e^{i m phi},  a = Q + m
+    const double mag = norm * exp(lc[a] + bq * pl[2 * q] + a * pl[2 * q + 1]) * ((bq & 1) ? -1.0 : 1.0);
+    const double* e = ph + ((size_t)q * L + a) * 2;
+    float* o = out + ((p0 + q) * L + a) * 2;  // consecutive t -> consecutive addresses
+    o[0] = (float)(mag * e[0]);
+    o[1] = (float)(mag * e[1]);
+  }
 }
 
 // x' (B, N, N, 2): copy a of walker b is the walker with electron a moved to r'_b (one_rdm.py:92-94)
@@ -245,8 +272,9 @@ extern "C" int dh_overlap_ratio(const float* logphi, const float* logpsi, int64_
 extern "C" int dh_lll_orbitals(const float* points, int64_t n, int32_t flux, float* out_phi, void* stream) {
   if (!points || !out_phi || n < 0 || flux < 0 || flux > 255) return DH_E_BADARG;
   if (n == 0) return 0;
-  const int64_t items = n * (flux + 1);
-  dh::lll_orbitals_kernel<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(points, n, flux, out_phi);
+  const int L = flux + 1;
+  const size_t smem = (size_t)(L + 2 * dh::LLL_PTS + 2 * dh::LLL_PTS * L) * sizeof(double);
+  dh::lll_orbitals_kernel<<<(unsigned)((n + dh::LLL_PTS - 1) / dh::LLL_PTS), 256, smem, (cudaStream_t)stream>>>(points, n, flux, out_phi);
   return (int)cudaGetLastError();
 }
 
