@@ -71,8 +71,10 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
 // per shared-memory wavefront -- and the two halves of the block work on two 16-column steps at once.
 template <int NT, bool L0, bool Q12>
 __global__ void __launch_bounds__(AJ_THREADS, 2)
-attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, int o_pl) {
+attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, int o_flags) {
   extern __shared__ __align__(16) float smem[];
+  const int o_pl = o_flags & 1;        // output as fp16 hi / lo planes
+  const int row_rot = o_flags & 2;     // phase 3 (Q12): the second half of the block takes its rows rotated by 8
   const int N = NT > 0 ? NT : dm.N, R = 2 * N + 8, D = dm.D, hd = dm.hd;
   const int RI = L0 ? AJ_RC : R;  // rows per electron of the input tensor
   constexpr int JB = L0 ? 2 : AJ_JB;  // keys per thread in phase 1 (fewer rows -> smaller tiles keep all threads busy)
@@ -296,7 +298,13 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
       // ---- all rows
       const int c2 = tid >> 7, idx = tid & 127;
       if (idx < 4 * R && cp + c2 < nchunk) {
-        const int f4 = idx & 3, r = idx >> 2;
+        // The T rows carry a third product loop (36 key passes against 24), so the warp that holds them is the slow
+        // one of its half.  Warps 3 and 7 share a scheduler (warp % 4): with the same row order in both halves that
+        // scheduler would issue 72 units per step against 48 for the others.  The second half therefore takes its
+        // rows rotated by one warp (8 rows): its slow warp is warp 6, and the per-scheduler maximum drops to 60.
+        const int f4 = idx & 3;
+        int r = idx >> 2;
+        if (row_rot && c2) { r += 8; if (r >= R) r -= R; }
         const float* vsub = stg(2 * c2) + (size_t)(f4 >> 1) * NRI * AJ_SUB;
         const int fh = f4 & 1;
         float4 acc[12];
@@ -462,6 +470,8 @@ int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0,
   const size_t smem = aj_smem_floats(d.N, d.R, layer0 ? AJ_RC : d.R) * sizeof(float);
   if (smem > 227 * 1024) return -2;
   dim3 grid((unsigned)d.H, (unsigned)B);
+  static const int row_rot = (getenv("DH_ATT_ROT") && atoi(getenv("DH_ATT_ROT")) == 0) ? 0 : 2;
+  const int o_flags = (o_pl ? 1 : 0) | row_rot;
 #define DH_AJ_LAUNCH(NT, LZ)                                                                                          \
   do {                                                                                                                \
     static size_t attr_smem = 0;                                                                                      \
@@ -471,7 +481,7 @@ int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0,
       if (e != cudaSuccess) return (int)e;                                                                            \
       attr_smem = smem;                                                                                               \
     }                                                                                                                 \
-    attention_jets_kernel<NT, LZ, (NT >= 7 && NT <= 12)><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d, o_pl);                 \
+    attention_jets_kernel<NT, LZ, (NT >= 7 && NT <= 12)><<<grid, AJ_THREADS, smem, s>>>(qkv, o, d, o_flags);                \
   } while (0)
 #define DH_AJ_BOTH(NT) do { if (layer0) DH_AJ_LAUNCH(NT, true); else DH_AJ_LAUNCH(NT, false); } while (0)
   switch (d.N) {
