@@ -302,9 +302,15 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
         // one of its half.  Warps 3 and 7 share a scheduler (warp % 4): with the same row order in both halves that
         // scheduler would issue 72 units per step against 48 for the others.  The second half therefore takes its
         // rows rotated by one warp (8 rows): its slow warp is warp 6, and the per-scheduler maximum drops to 60.
+        // Blocks alternate (by block number / 128, which separates most pairs of blocks that share an SM in the first
+        // waves) between slow warps on schedulers {3, 2} and {1, 0}.
         const int f4 = idx & 3;
         int r = idx >> 2;
-        if (row_rot && c2) { r += 8; if (r >= R) r -= R; }
+        if (row_rot) {
+          const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+          r += 8 * ((c2 + 2 * ((bid >> 7) & 1)) & 3);
+          while (r >= R) r -= R;
+        }
         const float* vsub = stg(2 * c2) + (size_t)(f4 >> 1) * NRI * AJ_SUB;
         const int fh = f4 & 1;
         float4 acc[12];
