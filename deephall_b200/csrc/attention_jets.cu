@@ -65,6 +65,38 @@ __device__ __forceinline__ void axpy4(float4& acc, float p, const float4& v) {
   acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
 }
 
+// Sum of 24 per-lane values (6 queries x 4 columns) over the 32 lanes of a warp by recursive halving: each of the
+// first three exchange rounds halves the number of values a lane keeps (12, 6, 3 shuffles), two more rounds finish the
+// three that are left (27 shuffles in all, against 24 x 5 for one butterfly per value).  On return the lanes with
+// (lane & 3) == 0 hold, in z[0..2], the complete sums of values base .. base + 2, base = 12 [lane & 16] + 6 [lane & 8]
+// + 3 [lane & 4]; value index = query * 4 + column.
+__device__ __forceinline__ int warp_sum24(const float4 (&acc)[6], float (&z)[3]) {
+  const int lane = threadIdx.x & 31;
+  const float v[24] = {acc[0].x, acc[0].y, acc[0].z, acc[0].w, acc[1].x, acc[1].y, acc[1].z, acc[1].w,
+                       acc[2].x, acc[2].y, acc[2].z, acc[2].w, acc[3].x, acc[3].y, acc[3].z, acc[3].w,
+                       acc[4].x, acc[4].y, acc[4].z, acc[4].w, acc[5].x, acc[5].y, acc[5].z, acc[5].w};
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0;
+  float w[12], u[6];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) {
+    const float keep = h16 ? v[12 + t] : v[t], send = h16 ? v[t] : v[12 + t];
+    w[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    const float keep = h8 ? w[6 + t] : w[t], send = h8 ? w[t] : w[6 + t];
+    u[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    const float keep = h4 ? u[3 + t] : u[t], send = h4 ? u[t] : u[3 + t];
+    z[t] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    z[t] += __shfl_xor_sync(0xffffffffu, z[t], 2);
+    z[t] += __shfl_xor_sync(0xffffffffu, z[t], 1);
+  }
+  return (h16 ? 12 : 0) + (h8 ? 6 : 0) + (h4 ? 3 : 0);
+}
+
 // NT > 0: the electron count is a compile-time constant (index arithmetic folds, j-loops unroll);
 // NT == 0: generic.
 // Q12 (7 <= N <= 12): phase 3 gives every thread all 12 (padded) queries of one (row, 4 columns) -- twice the FMAs
@@ -282,16 +314,12 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
             axpy4(acc[4], pc.x, v); axpy4(acc[5], pc.y, v);
           }
         }
+        float z[3];
+        const int zb = warp_sum24(acc, z);
+        if ((lane & 3) == 0) {
 #pragma unroll
-        for (int a = 0; a < AJ_OB; ++a) {
-          acc[a].x = warp_sum(acc[a].x); acc[a].y = warp_sum(acc[a].y);
-          acc[a].z = warp_sum(acc[a].z); acc[a].w = warp_sum(acc[a].w);
-        }
-        if (lane == 0) {
-#pragma unroll
-          for (int a = 0; a < AJ_OB; ++a)
-            *reinterpret_cast<float4*>(xs + (c2 * NP + ob * AJ_OB + a) * AJ_CH + f4 * 4) =
-                make_float4(2.f * acc[a].x, 2.f * acc[a].y, 2.f * acc[a].z, 2.f * acc[a].w);
+          for (int t = 0; t < 3; ++t)
+            xs[(c2 * NP + ob * AJ_OB + ((zb + t) >> 2)) * AJ_CH + f4 * 4 + ((zb + t) & 3)] = 2.f * z[t];
         }
       }
       __syncthreads();
@@ -394,16 +422,12 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
           axpy4(acc[4], pc.x, v); axpy4(acc[5], pc.y, v);
         }
       }
+      float z[3];
+      const int zb = warp_sum24(acc, z);
+      if ((lane & 3) == 0) {
 #pragma unroll
-      for (int a = 0; a < AJ_OB; ++a) {
-        acc[a].x = warp_sum(acc[a].x); acc[a].y = warp_sum(acc[a].y);
-        acc[a].z = warp_sum(acc[a].z); acc[a].w = warp_sum(acc[a].w);
-      }
-      if (lane == 0) {
-#pragma unroll
-        for (int a = 0; a < AJ_OB; ++a)
-          *reinterpret_cast<float4*>(xs + (ob * AJ_OB + a) * AJ_CH + f4 * 4) =
-              make_float4(2.f * acc[a].x, 2.f * acc[a].y, 2.f * acc[a].z, 2.f * acc[a].w);
+        for (int t = 0; t < 3; ++t)
+          xs[(ob * AJ_OB + ((zb + t) >> 2)) * AJ_CH + f4 * 4 + ((zb + t) & 3)] = 2.f * z[t];
       }
     }
     __syncthreads();
