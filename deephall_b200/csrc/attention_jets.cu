@@ -359,13 +359,16 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
         };
         // (the row-dependent terms are separate loops: one branch per thread instead of one per key, and in the
         // first-layer form an own-flow row touches a single key)
+        if (isT) {  // 2 sum_j p^(D_a) v^(D_a) first, doubled once in the accumulators (not once per product)
+          for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, rd), 1.f, staged(vsub, j * RI + rdin, fh));
+#pragma unroll
+          for (int a = 0; a < 12; ++a) { acc[a].x *= 2.f; acc[a].y *= 2.f; acc[a].z *= 2.f; acc[a].w *= 2.f; }
+        }
         for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, r), 1.f, staged(vsub, j * RI, fh));
         if (L0 && isJ) {
           axpy12(sj + SJ(0, jown, 0), 1.f, staged(vsub, jown * RI + rin, fh));
         } else if (r != 0) {
           for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, 0), 1.f, staged(vsub, j * RI + rin, fh));
-          if (isT)
-            for (int j = 0; j < N; ++j) axpy12(sj + SJ(0, j, rd), 2.f, staged(vsub, j * RI + rdin, fh));
         }
         const int dcol = (cp + c2) * AJ_CH + f4 * 4;
 #pragma unroll
