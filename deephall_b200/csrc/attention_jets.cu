@@ -35,16 +35,21 @@ size_t attention_jets_smem(NetDims d) { return aj_smem_floats(d.N, d.R, d.R) * s
 
 // asynchronous copy of head-dim columns [sub*8, sub*8+8) of NR rows into a staging region
 __device__ __forceinline__ void stage_async(float* dst, const float* __restrict__ src, int64_t ld, int NR, int sub, int hd) {
-  for (int t = threadIdx.x; t < NR * 2; t += AJ_THREADS) {
-    const int row = t >> 1, h = t & 1;
-    const int dcol = sub * AJ_SUB + h * 4;
-    float* d = dst + row * AJ_SUB + ((h ^ ((row >> 2) & 1)) << 2);
-    if (dcol < hd) {  // hd % 4 == 0: a 16-byte piece is entirely inside or entirely outside the head
+  // thread t takes the 16-byte half h = t & 1 of rows t >> 1, t >> 1 + 128, ...: with 256 threads h, the swizzle bit
+  // ((row >> 2) & 1) and the column are the same for every row of a thread, so both addresses advance by constants
+  static_assert(AJ_THREADS == 256, "the row stride of a thread must be a multiple of 8");
+  const int h = threadIdx.x & 1, row0 = threadIdx.x >> 1;
+  const int dcol = sub * AJ_SUB + h * 4;
+  float* d = dst + row0 * AJ_SUB + ((h ^ ((row0 >> 2) & 1)) << 2);
+  const float* sp = src + row0 * ld + dcol;
+  if (dcol < hd) {  // hd % 4 == 0: a 16-byte piece is entirely inside or entirely outside the head
+    for (int row = row0; row < NR; row += AJ_THREADS / 2, d += (AJ_THREADS / 2) * AJ_SUB, sp += (AJ_THREADS / 2) * ld) {
       const unsigned da = (unsigned)__cvta_generic_to_shared(d);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(src + row * ld + dcol) : "memory");
-    } else {
-      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da), "l"(sp) : "memory");
     }
+  } else {
+    for (int row = row0; row < NR; row += AJ_THREADS / 2, d += (AJ_THREADS / 2) * AJ_SUB)
+      *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
