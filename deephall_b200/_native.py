@@ -129,6 +129,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
+def _f32(t, what):
+    """The C ABI reads params / walkers / cotangents as float32: reject anything else instead of reinterpreting it."""
+    if t is not None and t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32, got {t.dtype}")
+    return t
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -219,6 +226,7 @@ class Plan:
         return {c: {"ms": ms[i], "count": cnt[i], "flops": fl[i]} for i, c in enumerate(PROFILE_CATEGORIES)}
 
     def _prepare(self, params):
+        _f32(params, "params")
         if params.numel() == 0:  # parameter-free network (Laughlin)
             return
         # identity + in-place version of the tensor the copies were made from; the strong reference keeps its
@@ -231,6 +239,7 @@ class Plan:
     # ---- ops
     def logpsi(self, params, x):
         self._prepare(params)
+        _f32(x, "walkers")
         B = x.shape[0]
         out = torch.empty((B, 2), dtype=torch.float32, device=x.device)
         ws = self.workspace(OP_LOGPSI, B)
@@ -239,6 +248,7 @@ class Plan:
 
     def local_energy(self, params, x):
         self._prepare(params)
+        _f32(x, "walkers")
         B = x.shape[0]
         dev = x.device
         el = torch.empty((B, 2), dtype=torch.float32, device=dev)
@@ -262,6 +272,7 @@ class Plan:
         }
 
     def potential(self, x):
+        _f32(x, "walkers")
         out = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
         _check(self.lib.dh_potential(self.handle, _ptr(x), x.shape[0], _ptr(out), _stream()), "dh_potential")
         return out
@@ -269,6 +280,7 @@ class Plan:
     def mcmc_sweep(self, params, x, steps, width, seed=0, offset=0, subsequence0=0, randoms=None, want_lp=False):
         """In-place on x.  Returns (naccept device int64 tensor, lp or None)."""
         self._prepare(params)
+        _f32(x, "walkers"), _f32(randoms, "randoms")
         B = x.shape[0]
         nacc = torch.zeros((1,), dtype=torch.int64, device=x.device)
         lp = torch.empty((B,), dtype=torch.float32, device=x.device) if want_lp else None
@@ -299,6 +311,7 @@ class Plan:
 
     def logpsi_vjp(self, params, x, cot, want_logpsi=False):
         self._prepare(params)
+        _f32(x, "walkers"), _f32(cot, "cotangents")
         B = x.shape[0]
         grad = torch.zeros_like(params)
         lpsi = torch.empty((B, 2), dtype=torch.float32, device=x.device) if want_logpsi else None
@@ -326,6 +339,7 @@ def _kfac_methods():
     def kfac_factors(self, params, x):
         """Factor sums of the KFAC curvature blocks for the walkers x (dh_kfac_factors): flat f32 tensor."""
         self._prepare(params)
+        _f32(x, "walkers")
         B = x.shape[0]
         _, nf = self.kfac_layout()
         out = torch.empty(nf, dtype=torch.float32, device=x.device)

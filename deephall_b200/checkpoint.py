@@ -20,6 +20,10 @@ import torch
 from .optimizers import AdamState, CheckpointState
 
 
+def _is_kfac_state(opt) -> bool:
+    return hasattr(opt, "_fields") and tuple(opt._fields) == ("step", "weight", "stats", "dense0_xtx")
+
+
 def _to_numpy_tree(tree):
     if isinstance(tree, dict):
         return {k: _to_numpy_tree(v) for k, v in tree.items()}
@@ -31,6 +35,11 @@ def save_checkpoint(path, step: int, model, state: CheckpointState) -> None:
     opt = state.opt_state
     if isinstance(opt, AdamState):
         opt = {"count": opt.count, "mu": _to_numpy_tree(model.param_tree(opt.mu)), "nu": _to_numpy_tree(model.param_tree(opt.nu))}
+    elif _is_kfac_state(opt):  # kfac.KfacState (the default optimizer): moving averages in the factor-vector layout
+        opt = {"kfac_step": int(opt.step), "weight": float(opt.weight), "stats": opt.stats.detach().cpu().numpy(),
+               "dense0_xtx": opt.dense0_xtx.detach().cpu().numpy()}
+    elif opt is not None:
+        raise TypeError(f"save_checkpoint: unknown optimizer state {type(opt).__name__}")
     with open(path, "wb") as f:
         np.savez_compressed(f, step=step, params=np.asarray(params, dtype="object"), data=state.data.detach().cpu().numpy(),
                             opt_state=np.asarray(opt, dtype="object"), mcmc_width=np.float32(state.mcmc_width))
@@ -46,5 +55,11 @@ def restore_checkpoint(path, model, device="cuda") -> tuple[int, CheckpointState
         opt = f["opt_state"].tolist()
         if isinstance(opt, dict) and {"count", "mu", "nu"} <= set(opt):
             opt = AdamState(int(opt["count"]), model.from_tree(opt["mu"], device=device), model.from_tree(opt["nu"], device=device))
+        elif isinstance(opt, dict) and {"kfac_step", "weight", "stats", "dense0_xtx"} <= set(opt):
+            from .kfac import KfacState
+
+            opt = KfacState(int(opt["kfac_step"]), float(opt["weight"]),
+                            torch.as_tensor(np.asarray(opt["stats"], dtype=np.float32)).to(device),
+                            torch.as_tensor(np.asarray(opt["dense0_xtx"], dtype=np.float32)).to(device))
         width = float(np.asarray(f["mcmc_width"]).reshape(-1)[0])
     return step, CheckpointState(params, data, opt, width)

@@ -172,7 +172,9 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   p->ee_par = p->ee_anti = -1;
   const int nu = cfg->n_up, nd = cfg->n_dn;
   if (nu * (nu - 1) / 2 + nd * (nd - 1) / 2 > 0) add_entry(p, "Jastrow_0/ee_par", {1}, &p->ee_par);  // blocks.py:91
-  if (nu * nd > 0) add_entry(p, "Jastrow_0/ee_anti", {1}, &p->ee_anti);                                 // blocks.py:99
+  // blocks.py:99 tests r_ees[0][1].shape[0] > 0, and that block has shape (n_up, n_dn): the leaf exists whenever
+  // n_up > 0, also for spin-polarised systems, where it multiplies an empty sum (inert, zero gradient)
+  if (nu > 0) add_entry(p, "Jastrow_0/ee_anti", {1}, &p->ee_anti);
 
   // ---- KFAC curvature blocks, in parameter order (optimizers/kfac.py: every Dense / DenseGeneral is a repeated-dense
   // block over the electron axis; everything else gets a diagonal block)

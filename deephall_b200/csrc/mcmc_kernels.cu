@@ -104,7 +104,9 @@ __global__ void init_walkers_kernel(float* __restrict__ x, int64_t total, int N,
   const int64_t b = t / N;
   const int i = (int)(t % N);
   Philox ph(seed);
-  uint4 r = ph((uint64_t)i, subseq0 + (uint64_t)b);
+  // own counter domain (top bit set): the Metropolis moves use counters offset * 64 + slot < 2^63 on the same
+  // (seed, walker), so the first proposal is independent of the walker's starting point
+  uint4 r = ph((1ull << 63) | (uint64_t)i, subseq0 + (uint64_t)b);
   x[t * 2] = acosf(2.f * u01(r.x) - 1.f);
   x[t * 2 + 1] = (2.f * u01(r.y) - 1.f) * 3.14159265358979f;
 }

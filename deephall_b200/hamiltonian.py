@@ -44,9 +44,10 @@ def local_energy(f, system: System):
         if single:
             out = {k: v[0] for k, v in out.items()}
         energy = out.pop("energy")
-        out.pop("logpsi")
+        _e_l.last_logpsi = out.pop("logpsi")  # by-product of the same pass (loss.py masks non-finite walkers with it)
         return energy, out  # keys: angular_momentum_z, _z_square, _square, potential, kinetic
 
+    _e_l.last_logpsi = None
     return _e_l
 
 

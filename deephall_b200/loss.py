@@ -51,8 +51,22 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
     batch_local_energy = local_energy(net.apply, system)
     plan = net.plan(system)
 
+    def masked_vjp(params, data, cot, valid, lp):
+        """One VJP over the valid walkers only.  The reference's loss_prod is a per-parameter nanmean over walkers
+        (loss.py:60-64): a walker whose log psi is not finite drops out.  Here such a walker gets a zero cotangent AND
+        its coordinates replaced by those of a valid walker, so that no 0 * NaN reaches the batched reverse pass; all
+        of it stream-ordered (no host synchronisation).  lp: log psi of the same walkers from the local-energy pass."""
+        ok = valid & torch.isfinite(lp.real) & torch.isfinite(lp.imag)
+        first = ok.to(torch.int8).argmax()
+        data = torch.where(ok[:, None, None], data, data.index_select(0, first[None])).contiguous()
+        # nanmean's denominator: the walkers that stay
+        scale = (valid.sum().clamp(min=1) / ok.sum().clamp(min=1)).to(cot.dtype)
+        cot = torch.where(ok[:, None], cot, torch.zeros_like(cot)) * scale
+        return torch.nan_to_num(plan.logpsi_vjp(params, data, cot.contiguous()))
+
     def loss_and_grad(params: torch.Tensor, data: torch.Tensor):
         el, obs = batch_local_energy(params, data)  # loss.py:67
+        lp = batch_local_energy.last_logpsi
         # loss.py:68-74,91: means, pmean'd in one packed all-reduce
         names = list(obs.keys())
         local = [obs[k].mean() for k in names] + [_nanmean(el), _nanmean(iqr_clip(el)), torch.nanmean(el.real**2)]
@@ -78,12 +92,12 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
         valid = ~torch.isnan(d).any(-1)
         nvalid = valid.sum().clamp(min=1).to(torch.float32)
         cot = torch.where(valid[:, None], d, torch.zeros_like(d)) * (2.0 / nvalid)
-        grads = torch.nan_to_num(plan.logpsi_vjp(params, data.contiguous(), cot.contiguous()))
+        grads = masked_vjp(params, data, cot, valid, lp)
         if mode == LossMode.SR_F_VECTOR:
             # loss.py:107-108 keeps the complex vector; its imaginary part 2 * nanmean_b[dRe_b Im(diff_b) - dIm_b Re(diff_b)]
             # is a second VJP with cotangent (2/B)(Im, -Re) diff_b
             cot_i = torch.stack([cot[:, 1], -cot[:, 0]], dim=-1).contiguous()
-            grads_i = torch.nan_to_num(plan.logpsi_vjp(params, data.contiguous(), cot_i))
+            grads_i = masked_vjp(params, data, cot_i, valid, lp)
             return stats, torch.complex(grads, grads_i)
         return stats, grads
 

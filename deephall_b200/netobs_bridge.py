@@ -95,7 +95,12 @@ def evaluate_observable(adaptor: DeepHallAdaptor, estimator, ckpt_file: str, ste
         values, state = estimator.evaluate(i, params, k_eval, data, system, state, aux)
         for name, v in values.items():
             if v.dim() > all_values[name].dim() - 1:  # per-walker values: mean over the (global) batch
-                v = constants.pmean(v.mean(0))
+                # NaN-aware mean over all walkers of all ranks (the reference's digest uses nanmean): masked sum and
+                # count, reduced together, so one NaN ratio drops that walker, not the step
+                bad = torch.isnan(torch.view_as_real(v)).any(-1) if v.is_complex() else torch.isnan(v)
+                cnt = constants.pmean((~bad).sum(0).to(torch.float32))
+                tot = constants.pmean(torch.where(bad, torch.zeros_like(v), v).sum(0))
+                v = tot / cnt.clamp(min=1e-30)
             all_values[name][i] = v
     if hasattr(estimator, "gathered_state"):
         state = estimator.gathered_state(state)

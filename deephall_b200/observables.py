@@ -154,7 +154,8 @@ class OneRDMEstimator:
         if hasattr(key, "offset"):  # PhiloxKey: every subkey (offset block of 2^20) draws its own points
             seed = (seed + 0x9E3779B97F4A7C15 * ((int(key.offset) >> 20) + 1)) & 0x7FFFFFFFFFFFFFFF
         if self._plan is not None:
-            return self._plan.init_walkers(batch, seed=seed)[:, 0, :].contiguous()
+            # one subsequence per GLOBAL walker index: ranks draw different r' (as mcmc.make_mcmc_step does)
+            return self._plan.init_walkers(batch, seed=seed, subsequence0=constants.rank() * batch)[:, 0, :].contiguous()
         g = torch.Generator(device="cuda").manual_seed(seed)
         u = torch.rand((batch, 2), generator=g, device="cuda")
         return torch.stack([torch.acos(2 * u[:, 0] - 1), (2 * u[:, 1] - 1) * torch.pi], -1).contiguous()

@@ -90,7 +90,7 @@ def param_shapes(cfg: NetCfg) -> "OrderedDict[str, tuple[int, ...]]":
     n_up, n_dn = cfg.nspins
     if n_up * (n_up - 1) // 2 + n_dn * (n_dn - 1) // 2 > 0:  # blocks.py:91
         s["Jastrow_0/ee_par"] = (1,)
-    if n_up * n_dn > 0:  # blocks.py:99
+    if n_up > 0:  # blocks.py:99: r_ees[0][1] has shape (n_up, n_dn) and the test is on shape[0] -> inert leaf when n_dn = 0
         s["Jastrow_0/ee_anti"] = (1,)
     return s
 
@@ -243,7 +243,7 @@ def jastrow(params, x, cfg: NetCfg):
     if par.shape[-1] > 0:
         a = params["Jastrow_0/ee_par"]
         total = total + (-(0.25 * a**2) / (a + par)).sum(-1)
-    if n_up * n_dn > 0:
+    if n_up > 0:  # blocks.py:99 (shape[0] of the (n_up, n_dn) block); an empty sum when n_dn = 0
         a = params["Jastrow_0/ee_anti"]
         anti = r_ee[..., :n_up, n_up:]
         total = total + (-(0.5 * a**2) / (a + anti)).sum((-1, -2))
