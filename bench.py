@@ -4,11 +4,20 @@ evals/sec and VMC steps/sec at N=12).
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host CPUs
 
-A "step" is one `local_energy` pass (E_L + the five observables, hamiltonian.py:207-210) over
-the batch.  Workload = BASELINE.json configs[2] (the configuration the metric is quoted on):
-nspins=[12,0], flux=33, default Psiformer (4x64, 2 layers, 1 det), batch 8192 walkers per GPU,
-interaction_strength 1.  Walkers are sharded over GPUs with no data-path collective (weak
-scaling); one JSON line is printed by rank 0.
+A "step" is one energy evaluation of the walker batch as the reference's inference step runs it
+(optimizers/none.py:32 -> loss.py:66-94, LossMode.ENERGY_DIFF): the `local_energy` pass (E_L + the
+five observables, hamiltonian.py:207-210) over the rank's walkers followed by the pmean'd energy
+statistics (one packed NCCL all-reduce when N > 1).  Default workload = BASELINE.json configs[2]
+(the configuration the metric is quoted on): nspins=[12,0], flux=33, default Psiformer (4x64,
+2 layers, 1 det), GLOBAL batch 8192 walkers, interaction_strength 1.
+
+  --config c2|c3|c4|c5k4   the other BASELINE configurations (global batch 4096 / 8192 / 8192 / 16384)
+  --scaling strong|weak    strong (default, what BASELINE.json asks: "batch 8192 at 1/2/4/8 B200"): the global
+                           batch is sharded, B/N walkers per GPU; weak: the full batch on every GPU
+
+`extra` carries the other BASELINE metrics at the same N and scaling mode -- walker-steps/s of `mcmc_step`
+and VMC steps/s (mcmc_step + loss_and_grad + optimizer + the statistics and gradient all-reduces) with
+Adam and with KFAC -- and, when N > 1, the weak-scaling local-energy figure.  One JSON line is printed by rank 0.
 """
 from __future__ import annotations
 
@@ -25,9 +34,20 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-WORKLOAD = dict(nspins=(12, 0), flux=33, num_heads=4, heads_dim=64, num_layers=2, determinants=1,
-                batch_per_gpu=8192, interaction_strength=1.0, mcmc_steps=10, mcmc_width=0.1)
-WORKLOAD_NAME = "c3: nspins=[12,0] flux=33 (1/3 filling), default Psiformer, batch 8192 per GPU"
+_COMMON = dict(num_heads=4, heads_dim=64, num_layers=2, interaction_strength=1.0, mcmc_steps=10, mcmc_width=0.1)
+WORKLOADS = {  # BASELINE.json configs[1..4]
+    "c2": dict(nspins=(6, 0), flux=15, determinants=1, global_batch=4096, **_COMMON,
+               name="c2: nspins=[6,0] flux=15 (1/3 Laughlin), default Psiformer, global batch 4096"),
+    "c3": dict(nspins=(12, 0), flux=33, determinants=1, global_batch=8192, **_COMMON,
+               name="c3: nspins=[12,0] flux=33 (1/3 filling), default Psiformer, global batch 8192"),
+    "c4": dict(nspins=(10, 0), flux=21, determinants=1, global_batch=8192, **_COMMON,
+               name="c4: nspins=[10,0] flux=21 (2/5 filling), default Psiformer, global batch 8192"),
+    "c5k4": dict(nspins=(16, 0), flux=45, determinants=4, global_batch=16384, **_COMMON,
+                 name="c5: nspins=[16,0] flux=45 (1/3 filling), Psiformer with 4 determinants, global batch 16384"),
+}
+WORKLOAD = WORKLOADS["c3"]
+WORKLOAD_NAME = WORKLOAD["name"]
+CPU_SAMPLE = 64  # walkers per CPU step: the same in `cpu_baseline` and in `--impl reference`
 METRIC = "local_energy_evals_per_sec"
 UNIT = "walker local-energy evals/s"
 
@@ -106,17 +126,19 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------- CPU reference leg
-def cpu_reference_local_energy(nwalkers, steps=1, warmup=0):
+def cpu_reference_local_energy(W, nwalkers=CPU_SAMPLE, steps=3, warmup=1):
     """Times the reference's algorithm (complex gradient + full Hessian of log psi,
-    hamiltonian.py:105-133) restated in torch on the host cores, fp32, on `nwalkers` walkers."""
+    hamiltonian.py:105-133) restated in torch on the host cores, fp32, on `nwalkers` walkers per step.
+    ONE protocol for both CPU legs (`cpu_baseline` and `--impl reference`): same sample, >= 1 warm-up pass, >= 3 timed
+    passes, throughput from the mean pass time."""
     from oracle import hamiltonian as OH
     from oracle import mcmc as OM
     from oracle import psiformer as OP
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = OP.NetCfg(nspins=WORKLOAD["nspins"], flux=WORKLOAD["flux"], ndets=WORKLOAD["determinants"],
-                    num_heads=WORKLOAD["num_heads"], heads_dim=WORKLOAD["heads_dim"], num_layers=WORKLOAD["num_layers"])
+    cfg = OP.NetCfg(nspins=W["nspins"], flux=W["flux"], ndets=W["determinants"],
+                    num_heads=W["num_heads"], heads_dim=W["heads_dim"], num_layers=W["num_layers"])
     params = OP.init_params(cfg, 0, torch.float32)
     x = OM.init_guess(torch.Generator().manual_seed(42), nwalkers, cfg.nelec, torch.float32)
 
@@ -124,10 +146,11 @@ def cpu_reference_local_energy(nwalkers, steps=1, warmup=0):
         return OP.logpsi(params, xx, cfg)
 
     def one():
-        return OH.batch_local_energy(f, x, cfg.Q, interaction_strength=WORKLOAD["interaction_strength"], chunk=32)
+        return OH.batch_local_energy(f, x, cfg.Q, interaction_strength=W["interaction_strength"], chunk=32)
 
-    for _ in range(warmup):
+    for _ in range(max(warmup, 1)):
         one()
+    steps = max(steps, 1)
     t0 = time.perf_counter()
     for _ in range(steps):
         out = one()
@@ -136,20 +159,25 @@ def cpu_reference_local_energy(nwalkers, steps=1, warmup=0):
     return nwalkers * steps / dt, dt / steps, cores
 
 
+def cpu_sample_note(steps, sps):
+    return (f"{CPU_SAMPLE} walkers of the same workload per step, 1 warm-up + {steps} timed steps ({sps:.2f} s each); torch-CPU "
+            "restatement of the reference algorithm (grad + full Hessian, oracle/hamiltonian.py), eager fp32, all host cores; "
+            "the JAX reference is not installable here (XLA-CPU would be several times faster than eager torch)")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 64
-    val, spstep, cores = cpu_reference_local_energy(sample, steps=args.steps, warmup=min(args.warmup, 1))
+    W = WORKLOADS[args.config]
+    steps = max(args.steps, 3)
+    val, spstep, cores = cpu_reference_local_energy(W, steps=steps, warmup=max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (uniform walkers on the sphere, random-init parameters)",
-        "config": {"workload": WORKLOAD_NAME, "sample": f"{sample} walkers per step"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} walkers/step x {args.steps} steps; torch-CPU restatement of the reference algorithm "
-                                   "(jax/flax are not installable here, so the reference itself cannot run)"},
+        "config": {"workload": W["name"], "sample": f"{CPU_SAMPLE} walkers per step (throughput is per walker)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_note(steps, spstep)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -157,6 +185,8 @@ def run_reference(args):
 
 # --------------------------------------------------------------------------------- CUDA arm
 def run_ours(args):
+    import dataclasses
+
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,23 +196,30 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from deephall_b200 import hamiltonian, mcmc, networks
+    from deephall_b200 import loss, mcmc, networks  # noqa: F401
     from deephall_b200.config import Config, MCMC, Network, Optim, PsiformerNetwork, System
     from deephall_b200.train import VMC
 
-    W = WORKLOAD
-    B = W["batch_per_gpu"]
+    W = WORKLOADS[args.config]
+    strong = args.scaling == "strong"
+    if strong and W["global_batch"] % world:
+        raise SystemExit(f"global batch {W['global_batch']} does not shard over {world} GPUs")
+    B = W["global_batch"] // world if strong else W["global_batch"]  # walkers per GPU
     N = sum(W["nspins"])
     system = System(flux=W["flux"], nspins=W["nspins"], interaction_strength=W["interaction_strength"])
     network = Network(psiformer=PsiformerNetwork(W["num_heads"], W["heads_dim"], W["num_layers"], W["determinants"]))
-    cfg = Config(batch_size=B * world, seed=42, system=system, network=network,
-                 mcmc=MCMC(steps=W["mcmc_steps"], width=W["mcmc_width"]), optim=Optim(optimizer="adam"))
-    vmc = VMC(cfg)
+
+    def make_vmc(per_gpu, optimizer="adam"):
+        cfg = Config(batch_size=per_gpu * world, seed=42, system=system, network=network,
+                     mcmc=MCMC(steps=W["mcmc_steps"], width=W["mcmc_width"]), optim=Optim(optimizer=optimizer))
+        return VMC(cfg)
+
+    vmc = make_vmc(B)
     model, params = vmc.model, vmc.state.params
     vmc.burn_in(20)  # synthetic walkers: short equilibration, not timed
     data = vmc.state.data
     plan = model.plan(system)
-    e_l = hamiltonian.local_energy(model.apply, system)
+    energy_step = loss.make_loss_fn(model.apply, system, loss.LossMode.ENERGY_DIFF)  # what optimizers/none.py:32 runs
 
     def barrier():
         if world > 1:
@@ -205,11 +242,11 @@ def run_ours(args):
         return float(ms.item())
 
     sampler = ClockSampler(local_rank)
-    # ---- headline: device-resident local-energy passes
+    # ---- headline: device-resident energy evaluations (local-energy pass + pmean'd statistics)
     result = {}
 
     def le_step():
-        result["el"] = plan.local_energy(params, data)
+        result["stats"], result["diff"] = energy_step(params, data)
 
     for _ in range(args.warmup):
         le_step()
@@ -223,15 +260,17 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = B * world * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host walkers -> public API -> host energies, every step
+    # ---- e2e: host walkers -> public API -> host energy statistics + per-walker clipped differences, every step
     x_host = data.cpu().pin_memory()
-    el_host = torch.empty((B,), dtype=torch.complex64).pin_memory()
+    diff_host = torch.empty((B,), dtype=torch.complex64).pin_memory()
+    stat_host = torch.empty((2,), dtype=torch.float32).pin_memory()
     x_dev = torch.empty_like(data)
 
     def e2e_step():
         x_dev.copy_(x_host, non_blocking=True)
-        el, _obs = e_l(params, x_dev)
-        el_host.copy_(el, non_blocking=True)
+        stats, diff = energy_step(params, x_dev)
+        diff_host.copy_(diff, non_blocking=True)
+        stat_host.copy_(torch.view_as_real(stats["energy"].reshape(1)).reshape(2).float(), non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     ms_e2e = timed(e2e_step, args.steps, 1)
@@ -240,15 +279,23 @@ def run_ours(args):
     # ---- the other two metrics of BASELINE.json (same hygiene, fewer steps)
     k2 = max(1, min(args.steps, 3))
     ms_mcmc = timed(lambda: vmc.mcmc_step(params, data, mcmc.PhiloxKey(7), W["mcmc_width"]), k2, 1) / k2
-    ms_vmc = timed(lambda: vmc.step(sync_stats=False), k2, 1) / k2
+    ms_vmc = timed(lambda: vmc.step(sync_stats=False), k2, 2) / k2
     # the same iteration with the reference's default optimizer (config.py:159): KFAC, whose curvature statistics
-    # cost one more forward + reverse pass (dh_kfac_factors) and ~20 small matrix inverses per step
-    import dataclasses
-
-    vmc_k = VMC(dataclasses.replace(cfg, optim=Optim(optimizer="kfac")))
+    # cost one more forward + reverse pass (dh_kfac_factors) and ~30 small matrix inverses per step
+    vmc_k = make_vmc(B, "kfac")
     vmc_k.state = vmc_k.state._replace(data=data.clone())
     ms_vmc_kfac = timed(lambda: vmc_k.step(sync_stats=False), k2, 3) / k2  # (3 warm-up steps: lazy library initialisation)
     del vmc_k
+    extra_weak = None
+    if world > 1 and strong:  # the weak-scaling figure next to the strong one: the full batch on every GPU
+        vw = make_vmc(W["global_batch"])
+        vw.burn_in(3)
+        dw = vw.state.data
+        ms_w = timed(lambda: energy_step(vw.state.params, dw), k2, 2) / k2
+        ms_vw = timed(lambda: vw.step(sync_stats=False), k2, 1) / k2
+        extra_weak = {"walkers_per_gpu": W["global_batch"], "local_energy_evals_per_sec": W["global_batch"] * world / (ms_w * 1e-3),
+                      "ms_per_step": ms_w, "vmc_step_ms": ms_vw}
+        del vw, dw
 
     # ---- roofline of the dominant kernel (dense contractions), CUDA-event timed per launch
     barrier()
@@ -259,35 +306,35 @@ def run_ours(args):
     g = prof["gemm"]
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak = peaks["bf16_tflops_sustained"]
+    total_ms = sum(v["ms"] for v in prof.values())
     roofline = {
-        "bound": "tensor", "kernel": "dense contraction (dh::gemm_*)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "bound": "tensor", "kernel": "dense contraction (dh::tc::gemm_*)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": achieved / peak, "traffic": gemm_traffic_per_launch(),
         "launches": g["count"], "avg_launch_ms": g["ms"] / max(g["count"], 1),
-        "share_of_step": g["ms"] / sum(v["ms"] for v in prof.values()),
+        "share_of_step": g["ms"] / total_ms,
         "peak_source": peaks["source"] + ", dense bf16 sustained. fp32 accuracy costs 3 fp16-rate MMAs (hi*hi, lo*hi, hi*lo) per "
                        "algorithmic MAC, so the attainable frac is 1/3; `achieved` counts algorithmic flops (2MNK per launch)",
         "tensor_pipe_frac_incl_split": 3.0 * achieved / peak,
         "per_category_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
+        "whole_pass": {"tflops": sum(v["flops"] for v in prof.values()) / (total_ms * 1e-3) / 1e12,
+                       "frac": sum(v["flops"] for v in prof.values()) / (total_ms * 1e-3) / 1e12 / peak},
     }
 
     if rank == 0:
         cpu = None
         if world == 1:
-            sample = 256
-            v, sps, cores = cpu_reference_local_energy(sample, steps=1, warmup=0)
-            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{sample} walkers of the same workload, one pass ({sps:.1f} s); torch-CPU restatement of the reference "
-                             "algorithm (grad + full Hessian), eager fp32; the JAX reference is not installable here"}
-        el = result["el"]["energy"]
+            v, sps, cores = cpu_reference_local_energy(W, steps=3, warmup=1)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_note(3, sps)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic (Philox uniform walkers + 20 burn-in sweeps, random-init parameters)",
-            "config": {"workload": WORKLOAD_NAME, "global_batch": B * world, "parallelism": f"walkers sharded x{world}",
+            "config": {"workload": W["name"], "global_batch": B * world, "walkers_per_gpu": B,
+                       "parallelism": f"walkers sharded x{world}; energy statistics all-reduced (NCCL) inside the timed step",
                        "l2": "per-pass working set (GBs of jet activations) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4 * world,
-                    "d2h_bytes_per_step": el_host.numel() * 8 * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": (diff_host.numel() * 8 + 8) * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -296,10 +343,11 @@ def run_ours(args):
                 "mcmc_step_ms": ms_mcmc,
                 "vmc_steps_per_sec": 1.0 / (ms_vmc * 1e-3),
                 "vmc_step_ms": ms_vmc,
-                "vmc_optimizer": "adam (SURVEY 8d M3)",
+                "vmc_optimizer": "adam (SURVEY 8d M3); statistics + gradient all-reduces inside the step",
                 "vmc_kfac_steps_per_sec": 1.0 / (ms_vmc_kfac * 1e-3),
                 "vmc_kfac_step_ms": ms_vmc_kfac,
-                "mean_energy": float(torch.nanmean(el.real)),
+                "weak_scaling": extra_weak,
+                "mean_energy": float(result["stats"]["energy"].real),
                 "algorithmic_flops_per_walker": flops_local_energy_per_walker(N, W["flux"] + 1, W["determinants"]),
             },
         }
@@ -314,6 +362,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
