@@ -15,6 +15,9 @@
 // takes that compressed [B*N*10][3D] tensor (written by the feature kernel), does the score products on the
 // 10 rows, scatters the own-flow products into the full row set (row J(2i+t) gets q_i^(t).k_j, row J(2j+t)
 // gets q_i.k_j^(t)), runs the same softmax jets, and in P.V only touches the v rows that exist.
+#include <stdlib.h>
+#include <string.h>
+
 #include "kernels.h"
 
 namespace dh {
@@ -503,6 +506,10 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
 }
 
 int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int o_pl, cudaStream_t s) {
+  // head size 64 and the electron counts of the BASELINE configurations: contractions on the tensor cores
+  // (attention_tc.cu).  DH_ATT_IMPL=simt keeps this file's fp32-FMA form for cross-checks.
+  static const bool simt_only = getenv("DH_ATT_IMPL") && strcmp(getenv("DH_ATT_IMPL"), "simt") == 0;
+  if (!o_pl && !simt_only && attention_jets_tc_ok(d)) return attention_jets_tc(qkv, o, B, d, layer0, s);
   if (o_pl && ((d.D % 8) != 0 || (reinterpret_cast<uintptr_t>(o) & 15))) return -2;
   if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
   const size_t smem = aj_smem_floats(d.N, d.R, layer0 ? AJ_RC : d.R) * sizeof(float);

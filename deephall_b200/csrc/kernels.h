@@ -76,6 +76,9 @@ int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream
 // o_pl != 0: o is written as fp16 hi / lo planes (common.cuh)
 int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int o_pl, cudaStream_t s);
 size_t attention_jets_smem(NetDims d);
+// attention_tc.cu: the same op with its contractions as mma.sync (fp16 hi / lo split), hd = 64, N in {3, 6, 10, 12, 16}
+bool attention_jets_tc_ok(NetDims d);
+int attention_jets_tc(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s);
 
 // ---- tail_kernels.cu
 struct TailDims {
