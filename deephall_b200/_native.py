@@ -355,11 +355,12 @@ def _kfac_methods():
 _kfac_methods()
 
 
-def spd_inverse(mats):
-    """Inverse of a batch of SPD matrices, (batch, n, n) f32 cuda, n <= 1024 (dh_spd_inverse); returns a new tensor."""
+def spd_inverse(mats, inplace=False):
+    """Inverse of a batch of SPD matrices, (batch, n, n) f32 cuda, n <= 1024 (dh_spd_inverse); returns a new tensor
+    (or `mats` itself when inplace and contiguous)."""
     _need_cuda()
     lib = load()
-    out = mats.contiguous().clone()
+    out = mats if (inplace and mats.is_contiguous()) else mats.contiguous().clone()
     _check(lib.dh_spd_inverse(_ptr(out), out.shape[-1], out.shape[0], _stream()), "dh_spd_inverse")
     return out
 

@@ -32,6 +32,22 @@ def pmean(x: torch.Tensor) -> torch.Tensor:
     return y / w
 
 
+def pmean_async(x: torch.Tensor):
+    """Mean over ranks started now, finished when the returned function is called: the collective runs on NCCL's own
+    stream while the caller keeps launching work that does not depend on it (the KFAC curvature pass, optimizers/kfac.py)."""
+    w = world_size()
+    if w == 1:
+        return lambda: x
+    y = x.clone().contiguous()
+    work = dist.all_reduce(y, op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish():
+        work.wait()
+        return y / w
+
+    return finish
+
+
 def pmean_packed(values: list[torch.Tensor]) -> list[torch.Tensor]:
     """One all-reduce for a list of scalars (packed stats vector)."""
     w = world_size()

@@ -231,9 +231,82 @@ spd_inverse_kernel(float* __restrict__ mats, int n) {
     __syncthreads();
   }
 }
+// Cluster form (the one the KFAC step runs): a thread-block CLUSTER of 8 CTAs per matrix, the matrix resident in the
+// cluster's distributed shared memory (CTA c holds rows [c rpc, (c + 1) rpc)), so a step costs one pivot-row
+// broadcast through DSMEM + one cluster barrier instead of a round trip of the whole matrix through L2:
+//   step k: the CTA that owns row k writes the OLD row k into every CTA's row buffer (double-buffered by k & 1),
+//           barrier.cluster, then every CTA updates its own rows (it holds its own entries of the old column k).
+// One barrier per step is enough: the buffer of step k is rewritten at step k + 2, after barrier k + 1, which a CTA
+// only passes once every CTA has finished the update of step k.
+constexpr int SPD_CL = 8;
+__device__ __forceinline__ uint32_t spd_mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__global__ void __cluster_dims__(SPD_CL, 1, 1) __launch_bounds__(1024, 1)
+spd_inverse_cluster_kernel(float* __restrict__ mats, int n, int rpc, int ldn) {
+  extern __shared__ __align__(16) float spd_smem[];
+  float* rows = spd_smem;                 // [rpc][ldn]  this CTA's rows
+  float* rowbuf = spd_smem + rpc * ldn;   // [2][ldn]    pivot row of the current / next step
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  float* a = mats + (size_t)(blockIdx.x / SPD_CL) * n * n;
+  const int r0 = (int)rank * rpc, nr = max(0, min(rpc, n - r0));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int i = warp; i < nr; i += nw)
+    for (int j = lane; j < n; j += 32) rows[i * ldn + j] = a[(size_t)(r0 + i) * n + j];
+  __syncthreads();
+  const uint32_t rowbuf_s = (uint32_t)__cvta_generic_to_shared(rowbuf);
+  for (int k = 0; k < n; ++k) {
+    const int owner = k / rpc;
+    if ((int)rank == owner) {  // broadcast the old row k (own copy included)
+      const float* src = rows + (k - r0) * ldn;
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const float v = src[j];
+        const uint32_t dst = rowbuf_s + (uint32_t)(((k & 1) * ldn + j) * 4);
+#pragma unroll
+        for (int c = 0; c < SPD_CL; ++c) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(spd_mapa(dst, c)), "f"(v) : "memory");
+      }
+    }
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    const float* rk = rowbuf + (k & 1) * ldn;
+    const float d = 1.f / rk[k];
+    for (int i = warp; i < nr; i += nw) {
+      float* ai = rows + i * ldn;
+      if (r0 + i == k) {
+        for (int j = lane; j < n; j += 32) ai[j] = j == k ? d : rk[j] * d;
+      } else {
+        const float f = ai[k] * d;
+        __syncwarp();  // every lane has read the old a[i][k] before lane k % 32 overwrites it
+        for (int j = lane; j < n; j += 32) ai[j] = j == k ? -f : fmaf(-f, rk[j], ai[j]);
+      }
+    }
+    __syncthreads();  // this CTA's rows are complete before the owner of step k + 1 reads its row
+  }
+  for (int i = warp; i < nr; i += nw)
+    for (int j = lane; j < n; j += 32) a[(size_t)(r0 + i) * n + j] = rows[i * ldn + j];
+  // no CTA may exit while another one can still write into its row buffer (the last broadcast precedes the last
+  // barrier, so this is already guaranteed; the trailing barrier keeps the invariant explicit)
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 int spd_inverse_batched(float* mats, int n, int batch, cudaStream_t s) {
   if (n < 1 || n > 1024 || batch < 0) return -2;
   if (batch == 0) return 0;
+  const int rpc = (n + SPD_CL - 1) / SPD_CL, ldn = (n + 3) & ~3;
+  const size_t smem = (size_t)(rpc + 2) * ldn * sizeof(float);
+  if (smem <= 220 * 1024) {
+    static size_t attr = 0;
+    if (smem > attr) {
+      cudaError_t e = cudaFuncSetAttribute(spd_inverse_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return (int)e;
+      attr = smem;
+    }
+    spd_inverse_cluster_kernel<<<batch * SPD_CL, 1024, smem, s>>>(mats, n, rpc, ldn);
+    return (int)cudaGetLastError();
+  }
   spd_inverse_kernel<<<batch, 1024, 0, s>>>(mats, n);
   return (int)cudaGetLastError();
 }

@@ -39,53 +39,49 @@ def _features(data: torch.Tensor, n_up: int) -> torch.Tensor:
     return torch.stack([torch.cos(theta), torch.sin(theta) * torch.cos(phi), torch.sin(theta) * torch.sin(phi), spin], dim=-1)
 
 
-_SIDE_STREAM = None
-
-
 def _batched_inverses(groups: dict) -> dict:
-    """{n: [n x n SPD matrices]} -> {n: (count, n, n) inverses}.
+    """{n: [n x n SPD matrices]} -> {n: (count, n, n) inverses}, by the library's own kernel (dh_spd_inverse).
 
-    dh_spd_inverse runs one Gauss-Jordan block per matrix, so a launch with 13 matrices leaves 135 SMs idle and two
-    launches of 13 and 14 matrices take twice the time of one with 27.  All sizes up to 320 therefore go out as ONE
-    batch: a smaller matrix is embedded as diag(A, I) in the largest size of the batch (its inverse is diag(A^-1, I)).
-    The few larger factors (the orbital projection's 409 rows) are inverted by the library on a side stream at the
-    same time."""
-    global _SIDE_STREAM
-    small = {n: ms for n, ms in groups.items() if n <= 320}
-    large = {n: ms for n, ms in groups.items() if n > 320}
-    out = {}
-    cur = torch.cuda.current_stream()
-    done = None
-    if large:
-        if _SIDE_STREAM is None:
-            _SIDE_STREAM = torch.cuda.Stream()
-        stacked = {n: torch.stack(ms) for n, ms in large.items()}
-        _SIDE_STREAM.wait_stream(cur)
-        with torch.cuda.stream(_SIDE_STREAM):
-            for n, st in stacked.items():
-                out[n] = torch.linalg.inv(st)
-                out[n].record_stream(cur)
-                st.record_stream(_SIDE_STREAM)
-        done = _SIDE_STREAM
-    if small:
-        nmax = max(small)
-        dev = next(iter(small.values()))[0].device
-        total = sum(len(ms) for ms in small.values())
-        batch = torch.zeros((total, nmax, nmax), dtype=torch.float32, device=dev)
-        k = 0
-        where = {}
-        for n, ms in small.items():
-            where[n] = (k, len(ms))
-            batch[k : k + len(ms), :n, :n] = torch.stack(ms)
-            if n < nmax:
-                idx = torch.arange(n, nmax, device=dev)
-                batch[k : k + len(ms), idx, idx] = 1.0
-            k += len(ms)
-        inv = _native.spd_inverse(batch)
-        for n, (k0, cnt) in where.items():
-            out[n] = inv[k0 : k0 + cnt, :n, :n]
-    if done is not None:
-        cur.wait_stream(done)
+    All sizes up to 1024 go out as ONE batch: a smaller matrix is embedded as diag(A, I) in the largest size of the
+    batch (its inverse is diag(A^-1, I)); dh_spd_inverse runs one 8-CTA cluster per matrix with the matrix in
+    distributed shared memory, so the batch takes the time of its largest member (~0.2 ms at 410 rows).
+    With more than one rank the matrices are dealt out round-robin -- every rank inverts 1/world of them -- and the
+    inverses are exchanged with one all-gather (the statistics they come from are already identical on all ranks).
+    Factors with more than 1024 rows (orbital projections of multi-determinant c5-sized networks) are outside the
+    kernel's range and go to torch.linalg.inv."""
+    small = {n: ms for n, ms in groups.items() if n <= 1024}
+    out = {n: torch.linalg.inv(torch.stack(ms)) for n, ms in groups.items() if n > 1024}
+    if not small:
+        return out
+    nmax = max(small)
+    dev = next(iter(small.values()))[0].device
+    world, rank = constants.world_size(), constants.rank()
+    total = sum(len(ms) for ms in small.values())
+    padded = (total + world - 1) // world * world
+    batch = torch.zeros((padded, nmax, nmax), dtype=torch.float32, device=dev)
+    diag = torch.arange(nmax, device=dev)
+    k = 0
+    where = {}
+    for n, ms in small.items():
+        where[n] = (k, len(ms))
+        batch[k : k + len(ms), :n, :n] = torch.stack(ms)
+        if n < nmax:
+            batch[k : k + len(ms), diag[n:], diag[n:]] = 1.0
+        k += len(ms)
+    if padded > total:
+        batch[total:, diag, diag] = 1.0
+    if world == 1:
+        inv = _native.spd_inverse(batch, inplace=True)
+    else:
+        # matrix m belongs to rank m % world: a strided view keeps the all-gather layout trivial
+        per = padded // world
+        mine = batch.view(per, world, nmax, nmax)[:, rank].contiguous()
+        _native.spd_inverse(mine, inplace=True)
+        gathered = torch.empty((world, per, nmax, nmax), dtype=torch.float32, device=dev)
+        torch.distributed.all_gather_into_tensor(gathered, mine)
+        inv = gathered.permute(1, 0, 2, 3).reshape(padded, nmax, nmax)
+    for n, (k0, cnt) in where.items():
+        out[n] = inv[k0 : k0 + cnt, :n, :n]
     return out
 
 
@@ -100,30 +96,36 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
     n_up = net.nspins[0]
     t2 = 1.0 / VARIANCE  # squared loss tangent
 
+    scale_cache: dict = {}
+
+    def stat_scales(B: int, device):
+        """Per-entry normalisation of the factor vector for a shard of B walkers (one multiply per step instead of one
+        small kernel per curvature block), and the slices of the naive-diagonal entries, which are squared first."""
+        if B not in scale_cache:
+            sc = torch.zeros(nfloats, dtype=torch.float32)
+            naive = []
+            for e in layout:
+                rows = float(B * e["rows_per_walker"])
+                if e["kind"] == 0:
+                    for key, n in (("xtx_offset", e["in_dim"] ** 2), ("xsum_offset", e["in_dim"])):
+                        if e[key] >= 0:
+                            sc[e[key] : e[key] + n] = 1.0 / rows
+                    sc[e["gtg_offset"] : e["gtg_offset"] + e["out_dim"] ** 2] = t2 / rows
+                else:  # kind 1: per-walker squares; kind 2 (naive diagonal): (batch-summed gradient)^2 / batch
+                    sc[e["diag_offset"] : e["diag_offset"] + e["size"]] = t2 / B
+                    if e["kind"] == 2:
+                        naive.append((e["diag_offset"], e["size"]))
+            scale_cache[B] = (sc.to(device), naive)
+        return scale_cache[B]
+
     def normalised_stats(params, data):
         """This step's statistics (local shard), each already divided by its batch size."""
-        B = data.shape[0]
         raw = plan.kfac_factors(params, data.contiguous())
-        out = torch.zeros_like(raw)
-        done = set()
-        for e in layout:
-            rows = float(B * e["rows_per_walker"])
-            if e["kind"] == 0:
-                for key, n in (("xtx_offset", e["in_dim"] ** 2), ("xsum_offset", e["in_dim"])):
-                    o = e[key]
-                    if o >= 0 and o not in done:
-                        out[o : o + n] = raw[o : o + n] / rows
-                        done.add(o)
-                o, n = e["gtg_offset"], e["out_dim"] ** 2
-                out[o : o + n] = raw[o : o + n] * (t2 / rows)
-            elif e["kind"] == 1:  # per-walker squares
-                o, n = e["diag_offset"], e["size"]
-                out[o : o + n] = raw[o : o + n] * (t2 / B)
-            else:  # naive diagonal: (batch-summed gradient)^2 / batch
-                o, n = e["diag_offset"], e["size"]
-                out[o : o + n] = raw[o : o + n] ** 2 * (t2 / B)
+        sc, naive = stat_scales(data.shape[0], raw.device)
+        for o, n in naive:
+            raw[o : o + n] = raw[o : o + n] ** 2
         feat = _features(data, n_up).reshape(-1, 4)
-        return out, feat.T @ feat / feat.shape[0]
+        return raw * sc, feat.T @ feat / feat.shape[0]
 
     def precondition(state: KfacState, grads: torch.Tensor) -> torch.Tensor:
         w = state.weight
@@ -180,7 +182,8 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
             if hb:
                 bo = e["bias_offset"]
                 V = torch.cat([V, grads[bo : bo + dout].view(1, dout)], dim=0)
-            U = inv[na][ja] @ V @ inv[ng][jg] / (ck * ck * npw)
+            # A_inv V G_inv with the library's fp32 contraction (dh_gemm), not a vendor GEMM
+            U = _native.gemm(_native.gemm(inv[na][ja].contiguous(), V.contiguous()), inv[ng][jg].contiguous()) / (ck * ck * npw)
             if hb:
                 out[bo : bo + dout] = U[din]
                 U = U[:din]
@@ -196,16 +199,18 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
         del key
         params, data, opt, width = state
         stats, grads = loss_grad_fn(params, data)
-        grads = constants.pmean(grads)
+        grads_red = constants.pmean_async(grads)  # NCCL runs it while the curvature pass below computes
         # kfac_jax order: curvature estimate (same batch) and inverses first, then the update
         new, x0 = normalised_stats(params, data)
         new, x0 = constants.pmean(new), constants.pmean(x0)
+        grads = grads_red()
         opt = KfacState(opt.step, opt.weight * curvature_ema + 1.0, opt.stats * curvature_ema + new,
                         opt.dense0_xtx * curvature_ema + x0)
         pg = precondition(opt, grads)
         lr = optim_cfg.lr.schedule(opt.step)
-        sq = float((pg * grads).sum()) * lr * lr
-        coeff = min(1.0, math.sqrt(norm_constraint / sq)) if sq > 0 else 1.0
+        # norm constraint on the device (no host synchronisation): coeff = min(1, sqrt(c / (lr^2 <pg, g>)))
+        sq = (pg * grads).sum() * (lr * lr)
+        coeff = torch.where(sq > 0, torch.clamp(torch.sqrt(norm_constraint / sq.clamp(min=1e-38)), max=1.0), torch.ones_like(sq))
         params = params - (lr * coeff) * pg
         return CheckpointState(params, data, KfacState(opt.step + 1, opt.weight, opt.stats, opt.dense0_xtx), width), stats
 
