@@ -35,6 +35,7 @@ class dh_config(C.Structure):
         ("network_type", C.c_int32),
         ("cf_flux", C.c_int32),
         ("orbital_type", C.c_int32),
+        ("contraction", C.c_int32),
         ("excitation_lz", C.c_float),
     ]
 
@@ -57,6 +58,8 @@ _vp, _i64, _i32, _u64, _f = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_fl
 SIGNATURES = OrderedDict(
     dh_plan_create=(C.c_int, [C.POINTER(dh_config), C.POINTER(_vp)]),
     dh_plan_destroy=(C.c_int, [_vp]),
+    dh_plan_status=(C.c_int, [_vp, _i32, C.POINTER(C.c_uint32), _vp]),
+    dh_plan_status_copy=(C.c_int, [_vp, _vp, _vp]),
     dh_version=(C.c_char_p, []),
     dh_param_count=(_i64, [_vp]),
     dh_param_layout=(C.c_int, [_vp, C.POINTER(dh_param_entry), C.POINTER(_i32)]),
@@ -88,6 +91,9 @@ SIGNATURES = OrderedDict(
     dh_one_rdm_scatter=(C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     dh_one_rdm_product=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
 )
+
+# dh_config.contraction: arithmetic of the dense / attention contractions
+CONTRACTIONS = {"f16": 0, "tf32": 1, "fp32": 2}
 
 PROFILE_CATEGORIES = ("gemm", "attention", "layernorm", "tail", "mcmc", "other")
 
@@ -150,7 +156,7 @@ class Plan:
 
     def __init__(self, nspins=(3, 0), flux=2, ndets=1, num_heads=4, heads_dim=64, num_layers=2,
                  interaction_type="coulomb", interaction_strength=1.0, radius=None, chunk_walkers=0,
-                 network_type="psiformer", cf_flux=1, orbital_type="full", excitation_lz=0.0):
+                 network_type="psiformer", cf_flux=1, orbital_type="full", excitation_lz=0.0, contraction="f16"):
         _need_cuda()
         self.lib = load()
         self.cfg = dh_config(
@@ -158,7 +164,7 @@ class Plan:
             0 if str(interaction_type) == "coulomb" else 1, float(interaction_strength),
             float(radius) if radius else 0.0, int(chunk_walkers),
             1 if str(network_type) == "laughlin" else 0, int(cf_flux),
-            1 if str(orbital_type) == "sparse" else 0, float(excitation_lz),
+            1 if str(orbital_type) == "sparse" else 0, CONTRACTIONS[str(contraction)], float(excitation_lz),
         )
         self.N = int(nspins[0]) + int(nspins[1])
         self.R = 2 * self.N + 8
@@ -178,6 +184,19 @@ class Plan:
                 self.handle = None
         except Exception:
             pass
+
+    # ---- range guard of the fp16-piece contractions (dh_plan_status)
+    def status(self, clear=True) -> int:
+        """Status bits of the ops run so far (synchronises): bit 0 = an operand piece saturated fp16's range."""
+        bits = C.c_uint32(0)
+        _check(self.lib.dh_plan_status(self.handle, 1 if clear else 0, C.byref(bits), _stream()), "dh_plan_status")
+        return int(bits.value)
+
+    def status_tensor(self) -> torch.Tensor:
+        """The same word as a device tensor, copied stream-ordered (no synchronisation)."""
+        out = torch.empty((1,), dtype=torch.int32, device="cuda")
+        _check(self.lib.dh_plan_status_copy(self.handle, _ptr(out), _stream()), "dh_plan_status_copy")
+        return out
 
     # ---- parameters
     @property

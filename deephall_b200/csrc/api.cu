@@ -59,6 +59,10 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     return DH_E_BADARG;
   if (cfg->n_dn < 0 || (cfg->network_type == 1 && cfg->n_dn != 0)) return DH_E_BADARG;
   dh_plan* p = new dh_plan();
+  if (cudaMalloc(&p->d_status, sizeof(unsigned)) != cudaSuccess || cudaMemset(p->d_status, 0, sizeof(unsigned)) != cudaSuccess) {
+    delete p;
+    return (int)cudaGetLastError();
+  }
   p->cfg = *cfg;
   p->N = cfg->n_up + cfg->n_dn;
   p->twoQ = cfg->flux;
@@ -245,18 +249,16 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
 
   // prepared-weight slots for the tcgen05 path: [Npad][D] hi | lo, plus fused biases
   {
-    const char* env = getenv("DH_GEMM_IMPL");
-    p->gemm_impl = (env && std::string(env) == "simt") ? 0 : 1;
-    p->tc_f16 = (gemm_tc_f16_ok(D) && !(env && std::string(env) == "tf32")) ? 1 : 0;
-    const char* acc = getenv("DH_GEMM_ACC");  // "split" | "merged"; default: merged for fp16 pieces, split for tf32
-    p->tc_merged = acc ? (std::string(acc) == "merged" ? 1 : 0) : p->tc_f16;
-    // DH_A_PLANES=1 (experiment, off by default): activations that feed a contraction are written as fp16 hi / lo
-    // planes by the attention / LayerNorm kernels and the contraction skips its in-kernel split.  Measured at c3:
-    // contractions 13.9 -> 13.1 ms, but attention +3.2 ms and LayerNorm +1.5 ms (8-byte plane stores), a net loss.
-    const char* apl = getenv("DH_A_PLANES");
-    p->a_planes = (p->gemm_impl == 1 && p->tc_f16 && D == 256 && p->nl > 0 && apl && std::string(apl) == "1") ? 1 : 0;
-    const char* lnf = getenv("DH_LN_FUSE");
-    p->ln_fuse = (p->gemm_impl == 1 && p->tc_f16 && p->tc_merged && D == 256 && !p->a_planes && lnf && std::string(lnf) == "1") ? 1 : 0;
+    // dh_config.contraction: 0 fp16 pieces (one accumulator per tile, double-buffered), 1 TF32 pieces (main + correction
+    // accumulators), 2 plain fp32 FMA
+    const int mode = cfg->contraction;
+    if (mode < 0 || mode > 2) { delete p; return DH_E_BADARG; }
+    p->gemm_impl = mode == 2 ? 0 : 1;
+    p->tc_f16 = (gemm_tc_f16_ok(D) && mode == 0) ? 1 : 0;
+    p->tc_merged = p->tc_f16;
+    p->a_planes = 0;
+    const char* lnf = dbg_env("DH_LN_FUSE");
+    p->ln_fuse = (p->gemm_impl == 1 && p->tc_f16 && p->tc_merged && D == 256 && lnf && std::string(lnf) == "1") ? 1 : 0;
     size_t off = 0;
     auto slot = [&](int Nout, bool has_bias) {
       dh_plan::Slot sl;
@@ -309,8 +311,26 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
   return 0;
 }
 
+extern "C" int dh_plan_status(dh_plan* p, int32_t clear, uint32_t* out_bits, void* stream) {
+  if (!p || !out_bits) return DH_E_BADARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  *out_bits = 0;
+  if (!p->d_status) return 0;
+  DH_CHECK(cudaMemcpyAsync(out_bits, p->d_status, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  if (clear) DH_CHECK(cudaMemsetAsync(p->d_status, 0, sizeof(uint32_t), s));
+  DH_CHECK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int dh_plan_status_copy(dh_plan* p, uint32_t* dst_device, void* stream) {
+  if (!p || !dst_device) return DH_E_BADARG;
+  if (!p->d_status) return (int)cudaMemsetAsync(dst_device, 0, sizeof(uint32_t), (cudaStream_t)stream);
+  return (int)cudaMemcpyAsync(dst_device, p->d_status, sizeof(uint32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
+
 extern "C" int dh_plan_destroy(dh_plan* p) {
   if (!p) return DH_E_BADARG;
+  if (p->d_status) cudaFree(p->d_status);
   if (p->d_normfac) cudaFree(p->d_normfac);
   if (p->prep) cudaFree(p->prep);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
@@ -410,7 +430,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       if ((rc = features_linear(x, p->prep + p->w0qkv, p->prep + q.bias, w.qkv, 3 * D, Bc, nd, jets ? 1 : 0, s))) return rc;
     } else if ((rc = dense_qkv(p, P, l, w.h, w.qkv, rows, R, s, pl))) return rc;
     { ProfScope ps(p, PC_ATTENTION, 0, s);
-      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, (l == 0 && p->gemm_impl == 1) ? 1 : 0, pl ? 1 : 0, s);
+      if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, (l == 0 && p->gemm_impl == 1) ? 1 : 0, p->tc_f16 ? 0 : 1, s);
       else rc = attention_value(w.qkv, w.att, Bc, nd, s);
       if (rc) return rc; }
     if (p->gemm_impl == 1) {
@@ -587,6 +607,7 @@ static int prepare_weights_vjp_now(dh_plan* p, const float* P, cudaStream_t s) {
 // cannot see in-place parameter updates); otherwise the caller promised to call dh_params_prepare after
 // every update and the planes made there are reused (the reverse-pass planes lazily, on the first VJP).
 int prepare_weights(dh_plan* p, const float* P, cudaStream_t s) {
+  range_flag_set(p->d_status);  // every op of this plan starts here: its kernels report into this plan's status word
   if (p->auto_prepare) return prepare_weights_now(p, P, s);
   if (p->prep_fwd_valid && p->prep_src == P) return 0;
   int rc = prepare_weights_now(p, P, s);

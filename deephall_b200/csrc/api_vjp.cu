@@ -80,7 +80,7 @@ int dense_bwd_x_tc(const dh_plan* p, const float* G, int64_t ldg, int vs, int K,
 // The "TN" contractions of the reverse pass (rows = the contracted index) run on the tensor cores when the operands
 // allow it (16-byte alignment, fp16 pieces); DH_VJP_DW=simt forces the fp32-FMA split-K kernel.
 bool tn_tc_ok(const dh_plan* p, const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc, int Ma) {
-  static const bool simt = getenv("DH_VJP_DW") && strcmp(getenv("DH_VJP_DW"), "simt") == 0;
+  static const bool simt = dbg_env("DH_VJP_DW") && strcmp(dbg_env("DH_VJP_DW"), "simt") == 0;
   return !simt && p->gemm_impl == 1 && p->tc_f16 && Ma >= 32 && gemm_tn_tc_ok(A, lda, B, ldb, C, ldc);
 }
 

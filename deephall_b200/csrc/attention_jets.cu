@@ -505,17 +505,17 @@ attention_jets_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetD
 #undef SJ
 }
 
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int o_pl, cudaStream_t s) {
-  // head size 64 and the electron counts of the BASELINE configurations: contractions on the tensor cores
-  // (attention_tc.cu).  DH_ATT_IMPL=simt keeps this file's fp32-FMA form for cross-checks.
-  static const bool simt_only = getenv("DH_ATT_IMPL") && strcmp(getenv("DH_ATT_IMPL"), "simt") == 0;
-  if (!o_pl && !simt_only && attention_jets_tc_ok(d)) return attention_jets_tc(qkv, o, B, d, layer0, s);
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int fp32_only, cudaStream_t s) {
+  // head size 64 and the electron counts of the BASELINE configurations: contractions on the tensor cores with fp16
+  // pieces (attention_tc.cu).  fp32_only (plans with contraction = tf32 / fp32): this file's fp32-FMA form.
+  if (!fp32_only && attention_jets_tc_ok(d)) return attention_jets_tc(qkv, o, B, d, layer0, s);
+  const int o_pl = 0;
   if (o_pl && ((d.D % 8) != 0 || (reinterpret_cast<uintptr_t>(o) & 15))) return -2;
   if (d.N > 16 || d.R != 2 * d.N + 8 || (d.hd % 4) != 0 || (d.D % 4) != 0) return -2;
   const size_t smem = aj_smem_floats(d.N, d.R, layer0 ? AJ_RC : d.R) * sizeof(float);
   if (smem > 227 * 1024) return -2;
   dim3 grid((unsigned)d.H, (unsigned)B);
-  static const int row_rot = (getenv("DH_ATT_ROT") && atoi(getenv("DH_ATT_ROT")) == 0) ? 0 : 2;
+  static const int row_rot = (dbg_env("DH_ATT_ROT") && atoi(dbg_env("DH_ATT_ROT")) == 0) ? 0 : 2;
   const int o_flags = (o_pl ? 1 : 0) | row_rot;
 #define DH_AJ_LAUNCH(NT, LZ)                                                                                          \
   do {                                                                                                                \

@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #define DH_CHECK(expr)                         \
   do {                                         \
@@ -17,6 +18,14 @@
   } while (0)
 
 namespace dh {
+
+// Developer A/B switches read from the environment exist only in builds made with -DDH_DEBUG_SWITCHES (make DEBUG=1);
+// the shipped library has ONE code path per operation and reads no environment variable.
+#ifdef DH_DEBUG_SWITCHES
+inline const char* dbg_env(const char* name) { return getenv(name); }
+#else
+inline const char* dbg_env(const char*) { return nullptr; }
+#endif
 
 // Row layout of a jet group (see oracle/jets.py): R = 2N + 8 rows per electron.
 //   0: value | 1..2N: J_k | 2N+1: S | 2N+2..4: D_a | 2N+5..7: T_a

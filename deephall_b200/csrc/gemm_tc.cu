@@ -297,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
                int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
-               int a_pre, int res, LnFuse ln, unsigned long long* __restrict__ prof) {
+               int a_pre, int res, LnFuse ln, unsigned long long* __restrict__ prof, unsigned* __restrict__ rflag) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
@@ -597,6 +597,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // optional power-of-two scale of A (reverse pass: gradients are O(1/B) and would underflow fp16 pieces);
     // a_scale_ptr = {scale, 1/scale}, the epilogue undoes it
     const float asc = a_scale_ptr ? __ldg(a_scale_ptr) : 1.f;
+    float amax = 0.f;  // largest |a| this thread split: an fp16 piece saturates beyond 65504 (reported through rflag)
     uint32_t it = 0;
     const bool rs = PAIR && res;  // resident A: one split per (band, k-block), in region kb
     for (int64_t tk = 0; tk < (a_pre ? 0 : (rs ? my_bands : my_tiles)); ++tk) {
@@ -621,6 +622,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 4; ++j) {
             v[j] = *reinterpret_cast<const float4*>(src + (((4 * h + j) ^ sw) << 4));
             v[j].x *= asc; v[j].y *= asc; v[j].z *= asc; v[j].w *= asc;
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
           }
           asm volatile("bar.sync 1, %0;" ::"n"(32 * SPLIT_WARPS) : "memory");
           const int sw2 = (r >> 1) & 3;
@@ -657,6 +659,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     if (prof && t == 0) { atomicAdd(prof + 4, pw[0]); atomicAdd(prof + 5, pw[1]); }
+    // fp16 pieces have a narrower range than the reference's fp32: a saturated piece is reported, never silent
+    if (F16 && rflag != nullptr && !(amax <= 65504.f)) atomicOr(rflag, 1u);
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -1397,6 +1401,12 @@ int gemm_tn_tc(const float* A, int64_t lda, int Ma, const float* B, int64_t ldb,
   return (int)cudaGetLastError();
 }
 
+// Device word that the fp16-piece kernels OR a bit into when an operand piece saturates (dh_plan_status); set by the
+// API entry points for the plan they run (host launches of one plan are sequential).
+static thread_local unsigned* g_range_flag = nullptr;
+void range_flag_set(unsigned* flag) { g_range_flag = flag; }
+unsigned* range_flag_get() { return g_range_flag; }
+
 int gemm_tc_supported(int N, int K) { return N >= 1 && K >= 32 && K % 32 == 0; }
 int gemm_tc_f16_ok(int K) { return K >= 32 && K % 32 == 0; }
 
@@ -1486,12 +1496,12 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   const int64_t tiles = bands * ((N + tc::BLOCK_N - 1) / tc::BLOCK_N);
   const int sms = tc::num_sms();
   // CTA pairs (tcgen05.mma.cta_group::2): fp16 pieces with the merged accumulator, fp32 A; DH_GEMM_PAIR=0 disables
-  static const bool pair_env = !(getenv("DH_GEMM_PAIR") && atoi(getenv("DH_GEMM_PAIR")) == 0);
+  static const bool pair_env = !(dbg_env("DH_GEMM_PAIR") && atoi(dbg_env("DH_GEMM_PAIR")) == 0);
   const bool pair = pair_env && f16 && merged && !a_pre && bands >= 2;
   // cluster size: DH_GEMM_CLUSTER = 1 | 2 | 4; small problems run un-clustered.  Default 1: with the
   // 192 KB operand ring the kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic, and the
   // multicast measured no faster at 2 and slower at 4 (profiles/r1_gemm_tc_notes.md).
-  static const int cl_env = getenv("DH_GEMM_CLUSTER") ? atoi(getenv("DH_GEMM_CLUSTER")) : 1;
+  static const int cl_env = dbg_env("DH_GEMM_CLUSTER") ? atoi(dbg_env("DH_GEMM_CLUSTER")) : 1;
   int cl = (cl_env == 4 || cl_env == 2) ? cl_env : 1;
   if (bands < 2 * sms || pair) cl = 1;
   int64_t g = bands < sms ? bands : sms;
@@ -1504,7 +1514,7 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   const uint32_t b_box = pair ? tc::BLOCK_N / 2 : tc::BLOCK_N / cl;
   if ((rc = tc::make_map(&tmBh, Wt_hi, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, b_box))) return rc;
   if ((rc = tc::make_map(&tmBl, Wt_lo, f16 != 0, (uint64_t)Npad, (uint64_t)gm.ldw, (uint64_t)gm.ldw, b_box))) return rc;
-  static const bool want_prof = getenv("DH_GEMM_PROF") != nullptr;
+  static const bool want_prof = dbg_env("DH_GEMM_PROF") != nullptr;
   unsigned long long* prof = nullptr;
   if (want_prof) {
     static unsigned long long* buf = nullptr;
@@ -1513,7 +1523,7 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
     prof = buf;
   }
   // resident A (pair form): K <= 256 and more than one column tile per band; DH_GEMM_RES=0 disables
-  static const bool res_env = !(getenv("DH_GEMM_RES") && atoi(getenv("DH_GEMM_RES")) == 0);
+  static const bool res_env = !(dbg_env("DH_GEMM_RES") && atoi(dbg_env("DH_GEMM_RES")) == 0);
   const int res = (pair && res_env && K <= 8 * tc::BLOCK_K && N > tc::BLOCK_N) ? 1 : 0;
   // fused LayerNorm epilogue: pair form, one 256-wide column tile, 32 jet rows per electron, TMA-stored output
   tc::LnFuse lnf;
@@ -1537,10 +1547,11 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   lc.numAttrs = 1;
   cudaError_t le;
 #define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR, false>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
-                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof)
+                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof, \
+                                                        g_range_flag)
   if (ln_on)
     le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<true, true, true, true>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K,
-                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof);
+                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof, g_range_flag);
   else if (pair) DH_LAUNCH_TC(true, true, true);
   else if (f16) { if (merged) DH_LAUNCH_TC(true, true, false); else DH_LAUNCH_TC(true, false, false); }
   else { if (merged) DH_LAUNCH_TC(false, true, false); else DH_LAUNCH_TC(false, false, false); }

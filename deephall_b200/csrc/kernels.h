@@ -73,9 +73,13 @@ int residual_layernorm_ex(const float* a, const float* b, const float* scale, co
                           int64_t B, NetDims d, int tanh_mode, int a_comp, int a_pl, int o_pl, cudaStream_t s);
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s);
 // layer0 != 0: qkv is the compressed first-layer tensor [B*N*10][3D] (features_linear with compressed = 1)
-// o_pl != 0: o is written as fp16 hi / lo planes (common.cuh)
-int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int o_pl, cudaStream_t s);
+// fp32_only != 0: never the fp16-piece tensor-core form (plans whose contraction mode is tf32 / fp32)
+int attention_jets(const float* qkv, float* o, int64_t B, NetDims d, int layer0, int fp32_only, cudaStream_t s);
 size_t attention_jets_smem(NetDims d);
+// Device status word of the running plan: the fp16-piece kernels (gemm_tc.cu, attention_tc.cu) OR bit 0 into it when an
+// operand piece saturates fp16's range (dh_plan_status).  Set by the API entry points; nullptr = no reporting.
+void range_flag_set(unsigned* flag);
+unsigned* range_flag_get();
 // attention_tc.cu: the same op with its contractions as mma.sync (fp16 hi / lo split), hd = 64, N in {3, 6, 10, 12, 16}
 bool attention_jets_tc_ok(NetDims d);
 int attention_jets_tc(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s);

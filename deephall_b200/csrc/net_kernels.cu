@@ -732,7 +732,7 @@ static int attention_value_warp(const float* qkv, float* o, int64_t B, NetDims d
 
 int attention_value(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
   if (d.N > ATT_NMAX || (d.hd % 4) != 0) return -2;
-  static const bool block_form = getenv("DH_ATTN_VALUE") && strcmp(getenv("DH_ATTN_VALUE"), "block") == 0;
+  static const bool block_form = dbg_env("DH_ATTN_VALUE") && strcmp(dbg_env("DH_ATTN_VALUE"), "block") == 0;
   if (!block_form && d.hd % 8 == 0 && d.hd <= 64 && (d.D % 4) == 0 && ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
     if (d.hd == 64) {  // the BASELINE configurations: everything a compile-time constant
       if (d.N == 6) return attention_value_warp<2, 6, 64>(qkv, o, B, d, s);

@@ -18,6 +18,7 @@ struct KfLayer { int q, k, v, o, d1, d2, ln0s, ln0b, ln1s, ln1b; };  // indices 
 
 struct dh_plan {
   dh_config cfg;
+  unsigned* d_status = nullptr;  // device status word (dh_plan_status): bit 0 = an fp16 operand piece saturated
   int N, L, K, D, H, hd, nl, twoQ, LNK;
   int nsb;   // spin blocks with their own orbital projections (blocks.py:29-34): 1 (n_dn = 0) or 2
   int orbN;  // columns of the orbital-coefficient tensor: 2 * nsb * LNK = [re | im] per spin block
@@ -78,7 +79,7 @@ struct dh_plan {
 
 // 0 disables the chunk interleave (DH_DUAL_STREAM=0)
 static inline bool dual_stream_env() {
-  static const bool on = !(getenv("DH_DUAL_STREAM") && atoi(getenv("DH_DUAL_STREAM")) == 0);
+  static const bool on = !(dbg_env("DH_DUAL_STREAM") && atoi(dbg_env("DH_DUAL_STREAM")) == 0);
   return on;
 }
 
@@ -136,7 +137,7 @@ static inline int64_t plan_chunks(const dh_plan* p, bool jets, int64_t B, int* c
   *copies = 1;
   if (!dual_stream_env()) return chunk;
   if (B > chunk) { *copies = 2; return chunk; }
-  static const long vmin = getenv("DH_DUAL_VALUE_MIN") ? atol(getenv("DH_DUAL_VALUE_MIN")) : 2048;
+  static const long vmin = dbg_env("DH_DUAL_VALUE_MIN") ? atol(dbg_env("DH_DUAL_VALUE_MIN")) : 2048;
   if (!jets && vmin > 0 && B >= vmin && p->cfg.chunk_walkers <= 0) {
     chunk = ((B + 1) / 2 + 31) / 32 * 32;
     *copies = 2;

@@ -601,14 +601,14 @@ orbital_contract_vec_kernel(const float* __restrict__ c, const float* __restrict
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s) {
   // (the value-only kernel measured 1 % slower with the same prefetch: its prologue is one warp's, not a block's)
-  static const int prefetch = !(getenv("DH_ORB_PREFETCH") && atoi(getenv("DH_ORB_PREFETCH")) == 0);
+  static const int prefetch = !(dbg_env("DH_ORB_PREFETCH") && atoi(dbg_env("DH_ORB_PREFETCH")) == 0);
   if (d.R == 1) {
     const int64_t rows = B * d.N;
     orbital_value_kernel<<<(unsigned)((rows + 7) / 8), 256, 8 * d.L * sizeof(cplx), s>>>(c, x, normfac, Mj, rows, d);
     return (int)cudaGetLastError();
   }
   size_t smem = 2 * d.L * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
-  static const bool scalar_form = getenv("DH_ORB_CONTRACT") && strcmp(getenv("DH_ORB_CONTRACT"), "scalar") == 0;
+  static const bool scalar_form = dbg_env("DH_ORB_CONTRACT") && strcmp(dbg_env("DH_ORB_CONTRACT"), "scalar") == 0;
   const int NK = d.N * d.K;
   const size_t smem_v = smem + (size_t)(d.R + 14) * NK * 2 * sizeof(float);
   if (!scalar_form && (reinterpret_cast<uintptr_t>(c) & 15) == 0 && smem_v <= 48 * 1024) {

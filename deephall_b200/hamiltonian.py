@@ -23,11 +23,9 @@ def _network_of(f) -> Psiformer:
 
 def make_potential(system: System, network: Psiformer):
     """hamiltonian.py:63-80: potential(data) WITHOUT the interaction_strength factor."""
-    plan = network.plan(system)
-
     def potential(data: torch.Tensor) -> torch.Tensor:
         single = data.dim() == 2
-        out = plan.potential((data[None] if single else data).contiguous().float())
+        out = network.plan(system).potential((data[None] if single else data).contiguous().float())
         return out[0] if single else out
 
     return potential
@@ -36,11 +34,10 @@ def make_potential(system: System, network: Psiformer):
 def local_energy(f, system: System):
     """hamiltonian.py:175-212."""
     net = _network_of(f)
-    plan = net.plan(system)
 
     def _e_l(params: torch.Tensor, data: torch.Tensor):
         single = data.dim() == 2
-        out = plan.local_energy(params, (data[None] if single else data).contiguous().float())
+        out = net.plan(system).local_energy(params, (data[None] if single else data).contiguous().float())
         if single:
             out = {k: v[0] for k, v in out.items()}
         energy = out.pop("energy")

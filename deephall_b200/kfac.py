@@ -120,7 +120,7 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
 
     def normalised_stats(params, data):
         """This step's statistics (local shard), each already divided by its batch size."""
-        raw = plan.kfac_factors(params, data.contiguous())
+        raw = net.plan(system).kfac_factors(params, data.contiguous())
         sc, naive = stat_scales(data.shape[0], raw.device)
         for o, n in naive:
             raw[o : o + n] = raw[o : o + n] ** 2

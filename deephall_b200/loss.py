@@ -49,7 +49,6 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
     if not isinstance(net, Psiformer):
         raise TypeError("network must be `model.apply` of a deephall_b200 network")
     batch_local_energy = local_energy(net.apply, system)
-    plan = net.plan(system)
 
     def masked_vjp(params, data, cot, valid, lp):
         """One VJP over the valid walkers only.  The reference's loss_prod is a per-parameter nanmean over walkers
@@ -62,7 +61,7 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
         # nanmean's denominator: the walkers that stay
         scale = (valid.sum().clamp(min=1) / ok.sum().clamp(min=1)).to(cot.dtype)
         cot = torch.where(ok[:, None], cot, torch.zeros_like(cot)) * scale
-        return torch.nan_to_num(plan.logpsi_vjp(params, data, cot.contiguous()))
+        return torch.nan_to_num(net.plan(system).logpsi_vjp(params, data, cot.contiguous()))
 
     def loss_and_grad(params: torch.Tensor, data: torch.Tensor):
         el, obs = batch_local_energy(params, data)  # loss.py:67

@@ -39,12 +39,11 @@ def make_mcmc_step(batch_network, batch_per_device: int, steps: int = 10):
     net = getattr(batch_network, "__self__", batch_network)
     if not isinstance(net, Psiformer):
         raise TypeError("batch_network must be `model.apply` of a deephall_b200 network")
-    plan = net.plan()
 
     def mcmc_step(params: torch.Tensor, data: torch.Tensor, key: PhiloxKey, width):
         assert data.shape[0] == batch_per_device
         w = float(width)
-        nacc, _ = plan.mcmc_sweep(params, data, steps, w, seed=key.seed, offset=key.offset,
+        nacc, _ = net.plan().mcmc_sweep(params, data, steps, w, seed=key.seed, offset=key.offset,
                                   subsequence0=constants.rank() * batch_per_device)
         pmove = nacc.to(torch.float32) / (steps * batch_per_device)  # mcmc.py:146
         pmove = constants.pmean(pmove)  # mcmc.py:147

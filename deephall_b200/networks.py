@@ -24,14 +24,14 @@ _PLANS: dict = {}
 
 def get_plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type="coulomb",
              interaction_strength=1.0, radius=None, chunk_walkers=0, network_type="psiformer", cf_flux=1,
-             orbital_type="full", excitation_lz=0.0) -> _native.Plan:
+             orbital_type="full", excitation_lz=0.0, contraction="f16") -> _native.Plan:
     key = (tuple(nspins), int(flux), ndets, num_heads, heads_dim, num_layers, str(interaction_type),
            float(interaction_strength), radius, chunk_walkers, str(network_type), int(cf_flux), str(orbital_type),
-           float(excitation_lz), torch.cuda.current_device())
+           float(excitation_lz), str(contraction), torch.cuda.current_device())
     if key not in _PLANS:
         _PLANS[key] = _native.Plan(nspins, flux, ndets, num_heads, heads_dim, num_layers, interaction_type,
                                    interaction_strength, radius, chunk_walkers, network_type, cf_flux, orbital_type,
-                                   excitation_lz)
+                                   excitation_lz, contraction)
     return _PLANS[key]
 
 
@@ -102,14 +102,18 @@ class Psiformer(B200Network):
         self.flux = int(round(2 * self.Q))
         self.ndets, self.num_heads, self.heads_dim, self.num_layers = int(ndets), int(num_heads), int(heads_dim), int(num_layers)
         self.orbital_type = str(orbital_type)
+        # arithmetic of the contractions: "f16" = fp16 hi/lo pieces (default); "tf32" = TF32 pieces, the fp32-exponent-range
+        # fallback a caller switches to when `plan().status()` reports a saturated fp16 piece; "fp32" = plain FMA
+        self.contraction = "f16"
 
     # ---- plan access (system-dependent parts default to the reference defaults)
     def plan(self, system: System | None = None) -> _native.Plan:
         if system is None:
             return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers,
-                            orbital_type=self.orbital_type)
+                            orbital_type=self.orbital_type, contraction=self.contraction)
         return get_plan(self.nspins, self.flux, self.ndets, self.num_heads, self.heads_dim, self.num_layers,
-                        system.interaction_type, system.interaction_strength, system.radius, orbital_type=self.orbital_type)
+                        system.interaction_type, system.interaction_strength, system.radius, orbital_type=self.orbital_type,
+                        contraction=self.contraction)
 
     def param_layout(self) -> "OrderedDict[str, tuple[int, tuple[int, ...]]]":
         return self.plan().param_layout()

@@ -41,8 +41,31 @@ class VMC:
             self.key, sub = self.key.split()
             self.mcmc_step(self.state.params, self.state.data, sub, self.state.mcmc_width)
 
+    def _range_overflow(self) -> bool:
+        """True if any rank's fp16-piece contraction saturated an operand since the last check (dh_plan_status)."""
+        bits = 0
+        for plan in {id(p): p for p in (self.model.plan(), self.model.plan(self.cfg.system))}.values():
+            bits |= plan.status()
+        flag = torch.tensor([float(bits & 1)], device=self.state.params.device)
+        return bool(constants.pmean(flag).item() > 0)
+
     def step(self, sync_stats=True):
-        """One iteration of train.py:126-140.  Returns (pmove, stats)."""
+        """One iteration of train.py:126-140.  Returns (pmove, stats).
+
+        With sync_stats (the reference's loop synchronises here as well, mcmc.py:180) the fp16 range guard is checked: if
+        a contraction saturated an fp16 operand piece during the iteration, the iteration is redone from the saved state
+        with TF32 pieces (fp32 exponent range, the reference's range) and the network stays in that mode."""
+        if sync_stats and getattr(self.model, "contraction", None) == "f16":
+            saved = (self.state._replace(data=self.state.data.clone()), self.key, self.t, self.pmoves.copy())
+            out = self._step(sync_stats)
+            if self._range_overflow():
+                self.model.contraction = "tf32"
+                self.state, self.key, self.t, self.pmoves = saved
+                out = self._step(sync_stats)
+            return out
+        return self._step(sync_stats)
+
+    def _step(self, sync_stats=True):
         st = self.state
         self.key, sub = self.key.split()
         data, pmove = self.mcmc_step(st.params, st.data, sub, st.mcmc_width)

@@ -66,6 +66,9 @@ typedef struct dh_config {
   int32_t network_type;     /* network.type: 0 = psiformer, 1 = laughlin (config.py:82-84)          */
   int32_t cf_flux;          /* laughlin: composite-fermion flux p (networks/laughlin.py:25), 0 -> 1  */
   int32_t orbital_type;     /* network.orbital: 0 = full, 1 = sparse (config.py:87-89, blocks.py:47-62) */
+  int32_t contraction;      /* arithmetic of the dense / attention contractions: 0 = fp16 hi/lo pieces on the tensor cores (default),
+                               1 = TF32 hi/lo pieces (fp32 exponent range; the fallback when dh_plan_status reports saturation),
+                               2 = plain fp32 FMA (cross-check) */
   float excitation_lz;      /* laughlin quasihole (N = 2 Q1) / quasiparticle (N = 2 Q1 + 2): L_z of the excitation = system.lz_center (networks/__init__.py:25-27) */
 } dh_config;
 
@@ -167,6 +170,17 @@ int dh_init_walkers(dh_plan* plan, float* x, int64_t B, uint64_t seed, uint64_t 
 int dh_logpsi_vjp(dh_plan* plan, const float* params, const float* x, int64_t B,
                   const float* cot, float* grad_flat, float* out_logpsi, void* ws,
                   size_t ws_bytes, void* stream);
+
+/* Range guard of the fp16-piece contractions.  The dense and attention contractions split every fp32 operand into two
+ * fp16 pieces; fp16 tops out at 65504 where the reference's fp32 does not.  A piece that saturates is never silent: the
+ * kernel that saturates it ORs bit 0 into the plan's device status word.
+ *   dh_plan_status      copies the word to the host (synchronises `stream`), optionally clearing it.
+ *   dh_plan_status_copy copies it device-to-device, stream-ordered, into `dst_device` (no synchronisation): lets a
+ *                       caller fold the flag into statistics it reads back anyway.
+ * A plan created with dh_config.contraction = 1 runs every contraction on TF32 pieces (fp32 exponent range) instead;
+ * callers re-run an op that reported saturation on such a plan (deephall_b200/train.py does so automatically). */
+int dh_plan_status(dh_plan* plan, int32_t clear, uint32_t* out_bits, void* stream);
+int dh_plan_status_copy(dh_plan* plan, uint32_t* dst_device, void* stream);
 
 /* Curvature statistics for KFAC with the reference's registration (loss.py:98: a unit-variance normal predictive
  * distribution on Re log psi, `fisher_exact`): one forward + one reverse pass with cotangent (1, 0) per walker.
