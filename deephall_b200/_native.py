@@ -76,7 +76,8 @@ SIGNATURES = OrderedDict(
     dh_logpsi_vjp=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     dh_slogdet=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
     dh_spd_inverse=(C.c_int, [_vp, _i32, _i32, _vp]),
-    dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    dh_gemm_workspace_bytes=(C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_size_t)]),
+    dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _vp]),
     dh_debug_buffer=(C.c_int, [_vp, C.c_int, _i64, C.c_char_p, C.POINTER(_i64), C.POINTER(_i64)]),
     dh_launch_count=(C.c_longlong, [_vp]),
     dh_kfac_layout=(C.c_int, [_vp, C.POINTER(dh_kfac_entry), C.POINTER(_i32), C.POINTER(_i64)]),
@@ -404,7 +405,11 @@ def gemm(A, W, bias=None, rows_per_group=1, out=None, accumulate=False, impl=0):
     N = W.shape[1]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=A.device)
-    _check(lib.dh_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, rows_per_group, int(accumulate), impl, _stream()), "dh_gemm")
+    nbytes = C.c_size_t(0)
+    _check(lib.dh_gemm_workspace_bytes(N, K, impl, C.byref(nbytes)), "dh_gemm_workspace_bytes")
+    ws = torch.empty(max(int(nbytes.value), 16), dtype=torch.uint8, device=A.device)  # torch's caching allocator: no cudaMalloc
+    _check(lib.dh_gemm(_ptr(A), _ptr(W), _ptr(bias), _ptr(out), M, N, K, rows_per_group, int(accumulate), impl, _ptr(ws),
+                       ws.numel(), _stream()), "dh_gemm")
     return out
 
 

@@ -791,27 +791,36 @@ extern "C" int dh_spd_inverse(float* mats, int32_t n, int32_t batch, void* strea
   return spd_inverse_batched(mats, n, batch, (cudaStream_t)stream);
 }
 
+extern "C" int dh_gemm_workspace_bytes(int32_t N, int32_t K, int32_t impl, size_t* bytes) {
+  if (!bytes || N < 1 || K < 1) return DH_E_BADARG;
+  const size_t npad = (size_t)((N + 15) & ~15);
+  *bytes = impl == 0 ? 0 : (2 * npad * K + 64) * sizeof(float);  // split weight planes + the scale slot
+  return 0;
+}
+
 extern "C" int dh_gemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
-                       int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* stream) {
+                       int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* ws, size_t ws_bytes,
+                       void* stream) {
   if (!A || !W || !C) return DH_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
   if (impl == 0) return gemm_simt(A, W, bias, C, M, N, K, K, 1, N, 1, N, rows_per_group, accumulate, 1, s);
   if (!gemm_tc_supported(N, K) || accumulate) return DH_E_UNSUPPORTED;
-  // test/bench entry point: the split weights are made on the fly (the plan ops keep them cached).
-  // impl 1: kind::f16 pieces when K % 64 == 0, else kind::tf32;  impl 2: kind::tf32 pieces;
-  // impl 3: kind::f16 pieces with separate main / correction accumulators.
+  // test / bench / optimizer entry point: the split weights are made on the fly in the caller's workspace (the plan
+  // ops keep theirs cached).  Stream-ordered, no allocation, no synchronisation -- like every other entry point.
+  // impl 1: tcgen05 with fp16 hi/lo pieces, one accumulator per tile (the default of the plan ops) when K % 32 == 0;
+  // impl 2: tcgen05 with TF32 hi/lo pieces;  impl 3: fp16 pieces with separate main / correction accumulators.
+  size_t need = 0;
+  dh_gemm_workspace_bytes(N, K, impl, &need);
+  if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15)) return DH_E_WORKSPACE;
   const int f16 = ((impl == 1 || impl == 3) && gemm_tc_f16_ok(K)) ? 1 : 0;
   const int merged = (impl == 1 && f16) ? 1 : 0;
-  float* wt = nullptr;
+  float* wt = static_cast<float*>(ws);
   const size_t npad = (size_t)((N + 15) & ~15);
-  DH_CHECK(cudaMalloc(&wt, (2 * npad * K + 64) * sizeof(float)));
   float* slot = wt + 2 * npad * K;
   int rc = (int)cudaMemsetAsync(slot, 0, 3 * sizeof(float), s);
   if (!rc && f16) rc = weight_maxabs_tc(W, N, K, N, slot, s);
   if (!rc) rc = split_weight_tc(W, N, K, N, 1, wt, wt + npad * K, slot, f16, s);
   if (!rc) rc = gemm_tc(A, wt, wt + npad * K, bias, f16 ? slot + 1 : nullptr, C, M, N, K, N, rows_per_group, f16, merged, s);
-  cudaStreamSynchronize(s);
-  cudaFree(wt);
   return rc;
 }
 

@@ -202,11 +202,17 @@ int dh_spd_inverse(float* mats, int32_t n, int32_t batch, void* stream);
 int dh_slogdet(const float* mats, int64_t B, int32_t K, int32_t n, float* out_sign,
                float* out_logabs, float* out_logpsi, void* stream);
 
-/* fp32 GEMM used by the network (exposed for parity tests and the roofline bench):
+/* fp32-accurate GEMM used by the network (exposed for parity tests, the roofline bench and the KFAC preconditioner):
  *   C[M,N] = A[M,K] @ W[K,N] (+ bias[N] on rows r with r % rows_per_group == 0) (+ C if accumulate)
- *   impl: 0 = SIMT fp32 FMA, 1 = tcgen05 3xTF32. */
+ *   impl: 0 = fp32 FMA (any shape, no workspace);
+ *         1 = tcgen05 / TMEM / TMA with fp16 hi/lo pieces, one accumulator per tile ("3xFP16", the plan ops' default);
+ *         2 = tcgen05 with TF32 hi/lo pieces ("3xTF32");  3 = fp16 pieces, separate main / correction accumulators.
+ *   impl >= 1 needs K % 32 == 0 and a caller workspace of dh_gemm_workspace_bytes (16-byte aligned) for the split
+ *   weight planes.  Stream-ordered; no allocation and no host synchronisation. */
+int dh_gemm_workspace_bytes(int32_t N, int32_t K, int32_t impl, size_t* bytes);
 int dh_gemm(const float* A, const float* W, const float* bias, float* C, int64_t M, int32_t N,
-            int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* stream);
+            int32_t K, int32_t rows_per_group, int32_t accumulate, int32_t impl, void* ws, size_t ws_bytes,
+            void* stream);
 
 /* Debug: after dh_logpsi / dh_local_energy with B <= chunk, intermediate buffers live in
  * the workspace.  Returns the float offset and count of a named buffer ("h", "qkv", "attn",
