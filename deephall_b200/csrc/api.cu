@@ -59,7 +59,8 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     return DH_E_BADARG;
   if (cfg->n_dn < 0 || (cfg->network_type == 1 && cfg->n_dn != 0)) return DH_E_BADARG;
   dh_plan* p = new dh_plan();
-  if (cudaMalloc(&p->d_status, sizeof(unsigned)) != cudaSuccess || cudaMemset(p->d_status, 0, sizeof(unsigned)) != cudaSuccess) {
+  if (cudaMalloc(&p->d_status, sizeof(unsigned)) != cudaSuccess || cudaMemset(p->d_status, 0, sizeof(unsigned)) != cudaSuccess ||
+      cudaMalloc(&p->d_mcmc, sizeof(McmcDev)) != cudaSuccess) {
     delete p;
     return (int)cudaGetLastError();
   }
@@ -296,6 +297,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     }
     p->prep_floats = off;
     cudaError_t e0 = cudaMalloc(&p->prep, off * sizeof(float));
+    if (e0 == cudaSuccess) e0 = cudaMalloc(&p->raw_params, (size_t)p->nparams * sizeof(float));
     if (e0 != cudaSuccess) { delete p; return (int)e0; }
   }
 
@@ -331,6 +333,9 @@ extern "C" int dh_plan_status_copy(dh_plan* p, uint32_t* dst_device, void* strea
 extern "C" int dh_plan_destroy(dh_plan* p) {
   if (!p) return DH_E_BADARG;
   if (p->d_status) cudaFree(p->d_status);
+  for (auto& g : p->move_graphs) cudaGraphExecDestroy(g.exec);
+  if (p->d_mcmc) cudaFree(p->d_mcmc);
+  if (p->raw_params) cudaFree(p->raw_params);
   if (p->d_normfac) cudaFree(p->d_normfac);
   if (p->prep) cudaFree(p->prep);
   for (cudaEvent_t e : p->prof_ev) cudaEventDestroy(e);
@@ -763,6 +768,49 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
     return rc;
   if ((rc = lp_from_logpsi(mw.logpsi2, mw.lp1, B, s))) return rc;
   const int64_t rstride = B * (2 * (int64_t)p->N + 1);
+  // ---- production path: in-kernel Philox, the move replayed from a captured CUDA graph (a sweep is ~17 short launches
+  // per move; at 1024 walkers per GPU their launch gaps are a third of the sweep)
+  static const bool graphs_env = !(dbg_env("DH_MCMC_GRAPH") && atoi(dbg_env("DH_MCMC_GRAPH")) == 0);
+  if (!randoms && steps >= 2 && !p->prof_on && p->graphs_ok && graphs_env && p->d_mcmc && (p->laughlin || p->raw_params)) {
+    const float* Pg = p->laughlin ? params : p->raw_params;
+    if (!p->laughlin) DH_CHECK(cudaMemcpyAsync(p->raw_params, params, p->nparams * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if ((rc = mcmc_dev_init(p->d_mcmc, seed, offset, subsequence0, width, s))) return rc;
+    dh_plan::MoveGraph* mg = nullptr;
+    for (auto& g : p->move_graphs) if (g.x == x && g.ws == ws && g.B == B) mg = &g;
+    if (!mg) {
+      cudaGraph_t graph = nullptr;
+      const long long l0 = p->launches;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        rc = mcmc_propose_dev(x, mw.x2, B, p->N, p->d_mcmc, s);
+        if (!rc) rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s);
+        if (!rc) rc = mcmc_accept_dev(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, p->d_mcmc, s);
+        if (!rc) rc = mcmc_dev_advance(p->d_mcmc, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        cudaGraphExec_t exec = nullptr;
+        if (!rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          if (p->move_graphs.size() >= 4) { cudaGraphExecDestroy(p->move_graphs.front().exec); p->move_graphs.erase(p->move_graphs.begin()); }
+          p->move_graphs.push_back({x, ws, B, exec, p->launches - l0 + 2});
+          mg = &p->move_graphs.back();
+        } else {
+          p->graphs_ok = 0;
+          cudaGetLastError();
+        }
+        if (graph) cudaGraphDestroy(graph);
+        p->launches = l0;
+      } else {
+        p->graphs_ok = 0;
+        cudaGetLastError();
+      }
+    }
+    if (mg) {
+      for (int st = 0; st < steps; ++st) DH_CHECK(cudaGraphLaunch(mg->exec, s));
+      p->launches += mg->launches * steps;
+      DH_CHECK(cudaMemcpyAsync(out_naccept, &p->d_mcmc->naccept, sizeof(long long), cudaMemcpyDeviceToDevice, s));
+      if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      return 0;
+    }
+    // capture refused: fall through to the launch-by-launch loop (the dev block is simply unused)
+  }
   for (int st = 0; st < steps; ++st) {
     const float* rnd = randoms ? randoms + st * rstride : nullptr;
     { ProfScope ps(p, PC_MCMC, 0, s); if ((rc = mcmc_propose(x, mw.x2, B, p->N, width, seed, offset + st, subsequence0, rnd, s))) return rc; }

@@ -11,11 +11,29 @@ namespace dh {
 
 constexpr float kTwoPi = 6.283185307179586f;
 
+// Device-resident arguments of a Metropolis move (McmcDev, kernels.h): when a kernel is given this block it reads the
+// Philox key / offset / width from it instead of from its launch arguments, so ONE captured CUDA graph of a move
+// (propose -> log psi -> accept -> advance) can be replayed for every move of every sweep.
+__global__ void mcmc_dev_init_kernel(McmcDev* dv, unsigned long long seed, unsigned long long offset,
+                                     unsigned long long subseq0, float width) {
+  dv->seed = seed; dv->offset = offset; dv->subseq0 = subseq0; dv->naccept = 0ull; dv->width = width;
+}
+__global__ void mcmc_dev_advance_kernel(McmcDev* dv) { dv->offset += 1ull; }
+int mcmc_dev_init(McmcDev* dv, uint64_t seed, uint64_t offset, uint64_t subseq0, float width, cudaStream_t s) {
+  mcmc_dev_init_kernel<<<1, 1, 0, s>>>(dv, seed, offset, subseq0, width);
+  return (int)cudaGetLastError();
+}
+int mcmc_dev_advance(McmcDev* dv, cudaStream_t s) {
+  mcmc_dev_advance_kernel<<<1, 1, 0, s>>>(dv);
+  return (int)cudaGetLastError();
+}
+
 __global__ void mcmc_propose_kernel(const float* __restrict__ x1, float* __restrict__ x2, int64_t total, int N,
                                     float width, uint64_t seed, uint64_t offset, uint64_t subseq0,
-                                    const float* __restrict__ randoms) {
+                                    const float* __restrict__ randoms, const McmcDev* __restrict__ dv) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
+  if (dv != nullptr) { seed = dv->seed; offset = dv->offset; subseq0 = dv->subseq0; width = dv->width; }
   const int64_t b = t / N;
   const int i = (int)(t % N);
   float nrm, uph;
@@ -58,7 +76,12 @@ int mcmc_propose(const float* x1, float* x2, int64_t B, int N, float width, uint
                  uint64_t subseq0, const float* randoms, cudaStream_t s) {
   const int64_t total = B * N;
   mcmc_propose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x1, x2, total, N, width, seed, offset,
-                                                                      subseq0, randoms);
+                                                                      subseq0, randoms, nullptr);
+  return (int)cudaGetLastError();
+}
+int mcmc_propose_dev(const float* x1, float* x2, int64_t B, int N, const McmcDev* dv, cudaStream_t s) {
+  const int64_t total = B * N;
+  mcmc_propose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x1, x2, total, N, 0.f, 0, 0, 0, nullptr, dv);
   return (int)cudaGetLastError();
 }
 
@@ -67,9 +90,10 @@ int mcmc_propose(const float* x1, float* x2, int64_t B, int N, float width, uint
 __global__ void mcmc_accept_kernel(float* __restrict__ x1, const float* __restrict__ x2, float* __restrict__ lp1,
                                    const float* __restrict__ lp2c, int lp2_stride, int64_t B, int N, uint64_t seed,
                                    uint64_t offset, uint64_t subseq0, const float* __restrict__ randoms,
-                                   unsigned long long* __restrict__ naccept) {
+                                   unsigned long long* __restrict__ naccept, McmcDev* __restrict__ dv) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool acc = false;
+  if (dv != nullptr) { seed = dv->seed; offset = dv->offset; subseq0 = dv->subseq0; naccept = &dv->naccept; }
   if (b < B) {
     float u;
     if (randoms != nullptr) u = randoms[b * (2 * N + 1) + 2 * N];
@@ -94,7 +118,12 @@ int mcmc_accept(float* x1, const float* x2, float* lp1, const float* lp2c, int l
                 uint64_t seed, uint64_t offset, uint64_t subseq0, const float* randoms,
                 unsigned long long* naccept, cudaStream_t s) {
   mcmc_accept_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(x1, x2, lp1, lp2c, lp2_stride, B, N, seed, offset,
-                                                                subseq0, randoms, naccept);
+                                                                subseq0, randoms, naccept, nullptr);
+  return (int)cudaGetLastError();
+}
+int mcmc_accept_dev(float* x1, const float* x2, float* lp1, const float* lp2c, int lp2_stride, int64_t B, int N, McmcDev* dv,
+                    cudaStream_t s) {
+  mcmc_accept_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(x1, x2, lp1, lp2c, lp2_stride, B, N, 0, 0, 0, nullptr, nullptr, dv);
   return (int)cudaGetLastError();
 }
 

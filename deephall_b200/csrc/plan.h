@@ -18,6 +18,13 @@ struct KfLayer { int q, k, v, o, d1, d2, ln0s, ln0b, ln1s, ln1b; };  // indices 
 
 struct dh_plan {
   dh_config cfg;
+  // Metropolis sweep as a replayed CUDA graph: one captured move (propose -> log psi -> accept -> advance) per
+  // (walker buffer, workspace, batch); the move's scalar arguments live in d_mcmc, the parameters it reads in raw_params
+  struct MoveGraph { const void* x; const void* ws; int64_t B; cudaGraphExec_t exec; long long launches; };
+  std::vector<MoveGraph> move_graphs;
+  McmcDev* d_mcmc = nullptr;
+  float* raw_params = nullptr;   // plan-owned copy of the parameter vector (address-stable across optimizer steps)
+  int graphs_ok = 1;             // cleared if a capture ever fails: the sweep then launches its kernels one by one
   unsigned* d_status = nullptr;  // device status word (dh_plan_status): bit 0 = an fp16 operand piece saturated
   int N, L, K, D, H, hd, nl, twoQ, LNK;
   int nsb;   // spin blocks with their own orbital projections (blocks.py:29-34): 1 (n_dn = 0) or 2

@@ -459,6 +459,25 @@ def test_mcmc_philox_stream(nat):
     assert abs(w[..., 1].mean()) < 1e-2 and abs(w[..., 1].var() - math.pi**2 / 3) < 2e-2
 
 
+def test_graph_replayed_sweep_is_the_same_chain(nat):
+    """dh_mcmc_sweep replays one captured CUDA graph of a move (device-resident Philox offset); the chain is bit-identical
+    to the same moves launched one by one (steps = 1 calls take the launch-by-launch path), also after the parameters
+    change at the same address or move to another tensor."""
+    cfg, p64, plan, flat, x0 = setup_case(nat, CONFIGS["c2"], 512, burn=0)
+    for trial in range(3):
+        xa, xb = x0.clone(), x0.clone()
+        na, _ = plan.mcmc_sweep(flat, xa, 6, 0.15, seed=9, offset=40)
+        nb = 0
+        for st in range(6):
+            n1, _ = plan.mcmc_sweep(flat, xb, 1, 0.15, seed=9, offset=40 + st)
+            nb += int(n1)
+        assert torch.equal(xa, xb) and int(na) == nb and 0 < nb < 6 * 512
+        if trial == 0:
+            flat.mul_(1.01)              # in-place update: same address, new values
+        else:
+            flat = (flat * 0.99).clone()  # new tensor
+
+
 def test_mcmc_samples_psi_squared(nat):
     """Filled-LLL N=3 state: <KE> = 1.5 exactly for every walker, and the sampled Coulomb energy of
     the chain is stationary -- the chain equilibrates to a distribution with E = 1.5 + <V>."""
