@@ -126,7 +126,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->tc_f16 = 0;
     p->tc_merged = 0;
     p->a_planes = 0;
-    p->ln_fuse = 0;
+    p->orb_fuse = 0;
     p->ee_par = p->ee_anti = -1;
     for (int t = 0; t < 4; ++t) p->orb_k[t] = p->orb_b[t] = -1;
     p->off_W0 = -1;
@@ -258,8 +258,10 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->tc_f16 = (gemm_tc_f16_ok(D) && mode == 0) ? 1 : 0;
     p->tc_merged = p->tc_f16;
     p->a_planes = 0;
-    const char* lnf = dbg_env("DH_LN_FUSE");
-    p->ln_fuse = (p->gemm_impl == 1 && p->tc_f16 && p->tc_merged && D == 256 && lnf && std::string(lnf) == "1") ? 1 : 0;
+    // envelope contraction as the epilogue of the orbital projection (gemm_tc.cu, ORB): 32 jet rows per electron (N = 12),
+    // one determinant, one spin block, full orbitals, at most 48 orbitals
+    p->orb_fuse = (p->gemm_impl == 1 && p->tc_f16 && D == 256 && N == 12 && K == 1 && p->nsb == 1 && !p->sparse && L <= 48 &&
+                   !(dbg_env("DH_ORB_FUSE") && atoi(dbg_env("DH_ORB_FUSE")) == 0)) ? 1 : 0;
     size_t off = 0;
     auto slot = [&](int Nout, bool has_bias) {
       dh_plan::Slot sl;
@@ -275,6 +277,11 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     };
     for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); slot(D, true); }
     slot(p->orbN, true);
+    if (p->orb_fuse) {  // the same projection with its output columns permuted to [tile][m][re | im][column], 10 m per tile
+      const int nperm = (L - 1) / 10 * 256 + ((L - 1) % 10 + 1) * 24;
+      slot(nperm, true);
+      p->orb_perm = off; off += al((size_t)(D + 1) * nperm);  // fp32 staging of the permuted kernel [D][nperm] and bias [nperm]
+    }
     // reverse-pass planes: [D rows][Kpad], Kpad = K rounded up to 32
     auto vslot = [&](int K) {
       dh_plan::Slot sl;
@@ -440,34 +447,40 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       if (rc) return rc; }
     if (p->gemm_impl == 1) {
       // MHA out-projection and the bias-free Dense that follows it are one linear map (Wo W1, bo W1)
-      const bool lnf0 = jets && p->ln_fuse && R == 32 && !pl && rows % 128 == 0 && !(l == 0 && h0_comp);
-      if (lnf0) {
-        const LnArgs la{P + o.ln0_s, P + o.ln0_b, 0};
-        if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.h, rows, D, R, s, false, &la))) return rc;  // h = LN0(h + att Wod + bod)
-      } else if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s, pl))) return rc;
+      if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s, pl))) return rc;
     } else {
       if ((rc = dense_layer(p, P, l, SL_O, w.att, w.t1, rows, R, s))) return rc;
       if ((rc = dense_layer(p, P, l, SL_D1, w.t1, w.t2, rows, R, s))) return rc;
     }
-    // R == 32 (N = 12): a 128-row tile holds whole electrons in whole warps, and the LayerNorm that follows a 256-wide
-    // contraction runs as its epilogue (gemm_tc.cu, LNF) -- the contraction's output never goes to HBM
-    const bool lnf = jets && p->ln_fuse && R == 32 && !pl && rows % 128 == 0;
     { ProfScope ps(p, PC_LAYERNORM, 0, s);
       if (l == 0 && h0_comp) rc = residual_layernorm_ex(w.t1, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 1, 0, pl ? 1 : 0, s);
-      else if (!lnf) rc = residual_layernorm_ex(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 0, pl ? 1 : 0, pl ? 1 : 0, s);
+      else rc = residual_layernorm_ex(w.h, w.t2, P + o.ln0_s, P + o.ln0_b, w.h, Bc, nd, 0, 0, pl ? 1 : 0, pl ? 1 : 0, s);
       if (rc) return rc; }
-    if (lnf) {
-      const LnArgs la{P + o.ln1_s, P + o.ln1_b, 1};
-      if ((rc = dense_tc(p, w.h, l * SL_PER_LAYER + SL_D2, w.h, rows, D, R, s, false, &la))) return rc;  // h = LN1(h + tanh(h W2 + b2))
-    } else {
-      if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s, pl))) return rc;
-      { ProfScope ps(p, PC_LAYERNORM, 0, s);
-        if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
-    }
+    if ((rc = dense_layer(p, P, l, SL_D2, w.h, w.t1, rows, R, s, pl))) return rc;
+    { ProfScope ps(p, PC_LAYERNORM, 0, s);
+      if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
   }
-  if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s, pl))) return rc;
-  ProfScope pst(p, PC_TAIL, 0, s, 3);
-  if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
+  if (jets && p->orb_fuse && rows % 128 == 0) {
+    // The envelope contraction (blocks.py:59-70) is the EPILOGUE of the orbital projection (blocks.py:28-35): the per-electron
+    // envelope jets go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the contraction reads
+    // its coefficients out of tensor memory and writes the orbital-matrix jets -- c[rows][2 L N] never exists in HBM
+    { ProfScope pse(p, PC_TAIL, 0, s);
+      if ((rc = envelope_table(x, p->d_normfac, w.cbuf, Bc, td, s))) return rc; }
+    const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
+    ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * p->orbN * p->D, s);
+    TcGemm g;
+    g.A = w.h; g.lda = p->D; g.Wt_hi = p->prep + sl.hi; g.Wt_lo = p->prep + sl.lo; g.ldw = p->D;
+    g.bias = p->prep + sl.bias; g.inv_scale = p->prep + sl.scale + 1;
+    g.C = w.Mj; g.ldc = sl.Nout; g.M = rows; g.N = sl.Nout; g.K = p->D; g.rpg = R;
+    g.f16 = 1; g.merged = 1; g.reduce_add = 0; g.a_scale = nullptr; g.A_lo = nullptr;
+    g.orb_env = w.cbuf; g.orb_Mj = w.Mj; g.orb_L = p->L;
+    if ((rc = gemm_tc_ex(g, s))) return rc;
+  } else {
+    if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s, pl))) return rc;
+    ProfScope psc(p, PC_TAIL, 0, s);
+    if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
+  }
+  ProfScope pst(p, PC_TAIL, 0, s, 2);
   if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;
   fa.ld = w.ld;
   fa.x = x;
@@ -564,6 +577,17 @@ static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
   if ((rc = fill(sb, pb, 2 * p->nsb, true))) return rc;
   for (int t = 0; t < 2 * p->nsb; ++t)
     DH_CHECK(cudaMemcpyAsync(p->prep + sb.bias + (size_t)t * LNK, orbB(p, P, t), LNK * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (p->orb_fuse) {  // the same projection with permuted output columns (fused envelope contraction of the jet passes)
+    const dh_plan::Slot& sp = p->slots[p->nl * SL_PER_LAYER + 1];
+    float* Wp = p->prep + p->orb_perm;
+    float* bp = Wp + (size_t)D * sp.Nout;
+    if ((rc = orb_permute_weights(orbW(p, P, 0), orbW(p, P, 1), orbB(p, P, 0), orbB(p, P, 1), Wp, bp, D, p->L, p->N * p->K, sp.Nout, s)))
+      return rc;
+    const Part pp = {Wp, sp.Nout, sp.Nout};
+    if ((rc = fill(sp, &pp, 1, true))) return rc;
+    DH_CHECK(cudaMemcpyAsync(p->prep + sp.bias, bp, sp.Nout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    p->launches += 4;
+  }
   p->launches += p->nl * (f16 ? 18 : 11) + 5 + (f16 ? 4 : 2);
   return 0;
 }

@@ -268,6 +268,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -281,23 +289,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // tma_store != 0: C is written through tmC (box 32 x 32 floats, 128B swizzle); otherwise (ldc not a
 // multiple of 4 floats, or misaligned C) by direct global stores.
 // PAIR (fp16 pieces, merged accumulator): clusters of two CTAs run `tcgen05.mma.cta_group::2` -- see the helpers above.
-// LNF (pair form, N = 256, 32 jet rows per electron): the epilogue is the LayerNorm that follows the contraction --
-// out = LN(res + acc) or LN(res + tanh(acc + bias)) with forward-Laplacian jets -- see the epilogue.
-struct LnFuse {
-  const float* res;    // residual = output tensor [M][ldc] (in place)
-  const float* gamma;  // LayerNorm scale [256]
-  const float* beta;   // LayerNorm bias  [256]
-  int tanh_mode;
+// ORB (pair form, resident A, 32 jet rows per electron, N K = 12): the contraction is the orbital projection
+// (blocks.py:28-35) and its epilogue is the envelope contraction that follows it (blocks.py:59-70) -- the coefficient
+// tensor c[rows][2 L N] (the largest activation of the pass) never goes to HBM.  See the epilogue.
+struct OrbFuse {
+  const float* env;  // [electrons][10 slots][L] complex: envelope jets per electron (envelope_table, tail_kernels.cu)
+  float* Mj;         // out: orbital-matrix jets [walkers][32 rows][12 electrons][12 orbitals] complex
+  int L;             // orbitals 2Q + 1
 };
+constexpr int ORB_NK = 12;               // orbital columns per (part, m) group
+constexpr int ORB_GW = 2 * ORB_NK;       // accumulator columns per m: [re (12) | im (12)]
+constexpr int ORB_MPT = BLOCK_N / ORB_GW;  // m per column tile: 10 (the last 16 columns of a full tile are zero weights)
 
-template <bool F16, bool MERGED, bool PAIR, bool LNF>
+template <bool F16, bool MERGED, bool PAIR, bool ORB>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
                int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
-               int a_pre, int res, LnFuse ln, unsigned long long* __restrict__ prof, unsigned* __restrict__ rflag) {
+               int a_pre, int res, OrbFuse orb, unsigned long long* __restrict__ prof, unsigned* __restrict__ rflag) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
@@ -305,13 +316,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   //                operand rows of 64 B (SWIZZLE_64B).
   //                PAIR:        [A hi 8 KB | A lo 8 KB | B hi 8 KB | B lo 8 KB]: this CTA's 128 of the tile's 256 weight rows.
   static_assert(!PAIR || (F16 && MERGED), "the CTA-pair form exists for fp16 pieces with the merged accumulator");
-  static_assert(!LNF || PAIR, "the fused LayerNorm epilogue exists for the pair form");
-  constexpr int STAGES = PAIR ? (LNF ? 5 : 6) : (F16 ? 4 : 2);  // LNF: the sixth stage's 32 KB are the epilogue's scratch
+  static_assert(!ORB || PAIR, "the fused orbital-contraction epilogue exists for the pair form");
+  constexpr int STAGES = PAIR ? 6 : (F16 ? 4 : 2);
   constexpr int ROW_BYTES = F16 ? 64 : 128;            // operand tile row = BLOCK_K pieces
   constexpr int AP_BYTES = BLOCK_M * ROW_BYTES;        // one A piece tile
   constexpr int B_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * ROW_BYTES;  // one B piece tile (PAIR: this CTA's half)
   constexpr int STAGE_BYTES = 2 * AP_BYTES + 2 * B_BYTES;
-  static_assert((STAGES + (LNF ? 1 : 0)) * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
+  static_assert(STAGES * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
   constexpr int A_TX_BYTES = A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -419,8 +430,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const long long t_begin = prof ? clock64() : 0;
   auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
     const long long t0 = prof ? clock64() : 0;
-    if (LNF) mbar_wait_sleep(bar, parity, true, 256);  // the epilogue is the critical path: waiting roles back off
-    else if (PAIR) mbar_wait_cluster(bar, parity);
+    if (PAIR) mbar_wait_cluster(bar, parity);
     else mbar_wait(bar, parity);
     if (prof) pw[slot] += (unsigned long long)(clock64() - t0);
   };
@@ -607,7 +617,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = rs ? (it / RES_AR) & 1 : (it / STAGES) & 1;
         const uint32_t wbar = rs ? ra_full(rr) : full_bar(s);
         uint8_t* const stage_reg = rs ? smem + rr * 2 * AP_BYTES : smem + s * STAGE_BYTES;
-        if (t == 0) timed_wait(wbar, ph, 0); else if (LNF) mbar_wait_sleep(wbar, ph, false, 256); else mbar_wait(wbar, ph);
+        if (t == 0) timed_wait(wbar, ph, 0); else mbar_wait(wbar, ph);
         const long long ts0 = (prof && t == 0) ? clock64() : 0;
         if (F16) {
           // Two threads per tile row r: thread (r, h) converts the 16 floats k = 16h .. 16h+15 of the landed fp32
@@ -671,6 +681,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tl = 0;
     // undoes the fp16 weight scale and the optional A scale (powers of two)
     const float inv_scale = (inv_scale_ptr ? __ldg(inv_scale_ptr) : 1.f) * (a_scale_ptr ? __ldg(a_scale_ptr + 1) : 1.f);
+    float oacc[ORB ? ORB_GW : 1], oacc2[ORB ? ORB_GW : 1];  // ORB: this row's 12 complex outputs, carried over a band's column tiles
+    (void)oacc; (void)oacc2;
     for (int64_t tk = 0; tk < my_tiles; ++tk, ++tl) {
       const int64_t m0 = band_of(tk) * BLOCK_M;
       const int n0 = ntile_of(tk) * BLOCK_N;
@@ -686,252 +698,111 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long te0 = (prof && lead) ? clock64() : 0;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * BLOCK_N;
-      if constexpr (LNF) {
-        // ---------------------------------------------------------------- fused residual + (tanh) + LayerNorm with jets
-        // The 32 rows of an electron (value | 24 J | S | 3 D | 3 T, common.cuh::Rows with N = 12) are the 32 lanes of
-        // this warp's TMEM quarter; two warps share a quarter and split the 8 column chunks.  Pass A builds
-        // x_r = res_r + jet of f(acc_r), stores it back into the accumulator and sums the row statistics; pass B
-        // reads x back, normalises with the jet rules of residual_layernorm_kernel and stores through the staging
-        // buffer.  Everything that couples ROWS at a fixed column (sum_k b_k^2, b_D^2 for tanh; sum_k c_k rho_k,
-        // c_D rho_D for the S / T rows) goes through the 32 x 32 staging tile: rows in, lane = column out.
-        // All shared-memory traffic uses explicit ld/st.shared with 16-byte broadcasts (the epilogue is issue-bound).
-        const bool isJ = lane >= 1 && lane <= 24, isS = lane == 25, isT = lane >= 29;
-        const int xr = isS ? 0 : (isT ? lane - 28 : -1);                      // which extra vector this row takes, if any
-        const uint32_t stg = smem_u32(buf);                                    // 32 x 32 staging tile, 128B-swizzled rows
-        auto st_row = [&](int k, int piece) { return stg + (uint32_t)(k * 128 + ((piece ^ (k & 7)) << 4)); };  // 16-byte piece
-        auto st_el = [&](int k, int vcol) { return stg + (uint32_t)(k * 128 + ((((vcol >> 2) ^ (k & 7)) << 4) | ((vcol & 3) << 2))); };
-        const uint32_t vec = smem_base + (uint32_t)(STAGES * STAGE_BYTES) + (uint32_t)(warp - EPI_WARP0) * 640u;  // bc[32] | ex[4][32]
-        const uint32_t xch = smem_base + (uint32_t)(STAGES * STAGE_BYTES) + 8u * 640u + (uint32_t)((tl & 1) * 4 + q) * 768u;
-        // gamma | beta | bias (256 floats each) live in shared memory: read with 16-byte broadcasts instead of __ldg
-        // (global loads between the shared-memory asm blocks cannot be hoisted and expose their latency 8x per chunk)
-        const uint32_t gbb = smem_base + (uint32_t)(STAGES * STAGE_BYTES) + 8u * 640u + 8u * 768u;
-        if (tl == 0) {
-          const int et = threadIdx.x - EPI_WARP0 * 32;  // 0..255
-          sts32(gbb + 4u * et, __ldg(ln.gamma + et));
-          sts32(gbb + 1024u + 4u * et, __ldg(ln.beta + et));
-          sts32(gbb + 2048u + 4u * et, bias != nullptr ? __ldg(bias + et) : 0.f);
-          asm volatile("bar.sync 6, 256;" ::: "memory");
+      if constexpr (ORB) {
+        // ---------------------------------------------------------------- fused envelope contraction (orbital matrices)
+        // Accumulator columns of tile nt: m = 10 nt + ml, ml < 10, at [24 ml, 24 ml + 24) = [re c(m, 0..11) | im c(m, 0..11)]
+        // (the weights were laid out so by orb_permute_weights).  The 32 lanes of this warp are the 32 jet rows of ONE
+        // electron (value | 24 J | S | 3 D | 3 T); the two warps of a lane quarter take the even / odd ml.
+        //   out_r[j] = sum_m c_r[m, j] env_0[m]                                  every row
+        //            + sum_m c_0[m, j] env_s[m]   s = slot of row r               own-flow J rows, S, D_a, T_a  (product rule)
+        //   S  += 2 sum_e (c_J(2i+e) . env_(1+e)),  T_a += 2 (c_D_a . env_(4+a))  second accumulator of rows J(2i+e), D_a,
+        //                                                                        handed to S / T_a at the end of the band
+        // env_t[m]: envelope jets of THIS electron (a per-electron table in global memory, staged in shared memory per band).
+        const int nt = ntile_of(tk);
+        const int64_t ge = (m0 >> 5) + q;            // global electron index (M % 128 == 0: bands hold whole electrons)
+        const int ei = (int)(ge % 12);               // electron within its walker
+        const int L = orb.L;
+        // this warp pair's scratch: env table [10][L] complex (<= 10 * 48 * 8 B) | partial sums of the odd warp [32][48]
+        float* envs = reinterpret_cast<float*>(epi_smem + q * (2 * EPI_BUF_BYTES));   // 8 KB per quarter
+        float* xsum = envs;  // [48][32] partial sums of the odd warp: reuses the table's space once the band's groups are read
+        static_assert(2 * EPI_BUF_BYTES >= 32 * 2 * ORB_GW * 4 && 2 * EPI_BUF_BYTES >= 10 * 96 * 4, "per-quarter scratch");
+        const int r = lane;
+        // slot whose envelope jets multiply the VALUE row into this row (0 = none), and the slot of the second accumulator
+        int s1 = 0, s2 = 0;
+        if (r == 1 + 2 * ei) { s1 = 1; s2 = 1; }
+        else if (r == 2 + 2 * ei) { s1 = 2; s2 = 2; }
+        else if (r == 25) s1 = 3;
+        else if (r >= 26 && r <= 28) { s1 = 4 + (r - 26); s2 = s1; }
+        else if (r >= 29) s1 = 7 + (r - 29);
+        if (nt == 0) {
+          // stage this electron's envelope table; both warps of the quarter fill and read it
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // the previous band's reads are done
+          const float* eg = orb.env + ge * (int64_t)(10 * 2) * L;
+          for (int t = chalf * 32 + lane; t < 10 * 2 * L; t += 64) {
+            const int sl = t / (2 * L), rest = t - sl * 2 * L;
+            envs[sl * 96 + rest] = (m0 + q * 32 < M) ? __ldg(eg + t) : 0.f;
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+#pragma unroll
+          for (int j = 0; j < ORB_GW; ++j) { oacc[j] = 0.f; oacc2[j] = 0.f; }
         }
-        const bool mvalid = m < M;
-        const float* rrow = ln.res + (mvalid ? m : 0) * ldc;
-        float s_x = 0.f, s_xx = 0.f, s_x0x = 0.f;
-        auto stage_free = [&]() {  // the previous TMA store of this warp has read the staging tile
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          __syncwarp();
-        };
-        // lane 0's 32 values -> every lane (through bc)
-        auto bcast32 = [&](float (&dst)[32], const float (&src)[32]) {
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sts128(vec + 16 * j, make_float4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]));
-          }
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 f = lds128(vec + 16 * j);
-            dst[4 * j] = f.x; dst[4 * j + 1] = f.y; dst[4 * j + 2] = f.z; dst[4 * j + 3] = f.w;
-          }
-          __syncwarp();
-        };
-        long long lt0 = (prof && lead) ? clock64() : 0, lt1;
-#define DH_LNLAP(slot) if (prof && lead) { lt1 = clock64(); atomicAdd(prof + 22 + (slot), (unsigned long long)(lt1 - lt0)); lt0 = lt1; }
-        // ---- pass A
+        const int mt = min(ORB_MPT, L - ORB_MPT * nt);  // m's in this tile
 #pragma unroll 1
-        for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
-          uint32_t v[32];
-          DH_LNLAP(9)
-          tmem_ld32(tbase + (uint32_t)c0, v);
-          // the residual line of this row for the NEXT chunk -> L1 (a thread reads one 128-byte line per chunk; without
-          // the prefetch every chunk exposes a full L2 round trip)
-          if (mvalid && c0 + 2 * EPI_CHUNK < BLOCK_N) asm volatile("prefetch.global.L1 [%0];" ::"l"(rrow + c0 + 2 * EPI_CHUNK));
-          float x[32];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 a4 = mvalid ? *reinterpret_cast<const float4*>(rrow + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            x[4 * j] = a4.x; x[4 * j + 1] = a4.y; x[4 * j + 2] = a4.z; x[4 * j + 3] = a4.w;
-          }
+        for (int ml = chalf; ml < mt; ml += 2) {
+          const int mm = ORB_MPT * nt + ml;
+          uint32_t v[24];
+          tmem_ld16(tbase + (uint32_t)(ORB_GW * ml), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+          tmem_ld8(tbase + (uint32_t)(ORB_GW * ml + 16), *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
+          const float2 e0 = *reinterpret_cast<const float2*>(envs + 2 * mm);
+          const float2 e1 = *reinterpret_cast<const float2*>(envs + s1 * 96 + 2 * mm);
+          const float2 e2 = *reinterpret_cast<const float2*>(envs + s2 * 96 + 2 * mm);
+          const float w1 = s1 ? 1.f : 0.f, w2 = s2 ? 1.f : 0.f;
+          const float bre = (bias != nullptr && lane < ORB_GW) ? __ldg(bias + n0 + ORB_GW * ml + lane) : 0.f;  // lane j: bias of column j
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          DH_LNLAP(0)
-          if (ln.tanh_mode) {
-            float t[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) t[j] = __uint_as_float(v[j]) * inv_scale;
-            if (lane == 0) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = lds128(gbb + 2048u + 4u * c0 + 16u * j);
-                t[4 * j] += b4.x; t[4 * j + 1] += b4.y; t[4 * j + 2] += b4.z; t[4 * j + 3] += b4.w;
-              }
-            }
-            // stage the b rows; lane = column then takes tanh of the value row and the column sums of squares
-            stage_free();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) sts128(st_row(lane, j), make_float4(t[4 * j], t[4 * j + 1], t[4 * j + 2], t[4 * j + 3]));
-            __syncwarp();
-            const float th_l = tanhf(lds32(st_el(0, lane)));
-            float bs = 0.f;
-#pragma unroll
-            for (int k0 = 1; k0 <= 24; k0 += 8) {  // eight loads in flight before the first is used
-              float bk[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) bk[u] = lds32(st_el(k0 + u, lane));
-#pragma unroll
-              for (int u = 0; u < 8; ++u) bs = fmaf(bk[u], bk[u], bs);
-            }
-            sts32(vec + 4 * lane, th_l);
-            sts32(vec + 128 + 4 * lane, bs);
-#pragma unroll
-            for (int a3 = 0; a3 < 3; ++a3) { const float bd = lds32(st_el(26 + a3, lane)); sts32(vec + 256 + 128 * a3 + 4 * lane, bd * bd); }
-            __syncwarp();
-#pragma unroll
-            for (int j0 = 0; j0 < 8; j0 += 4) {
-              float4 th4[4], e4[4];
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                th4[jj] = lds128(vec + 16 * (j0 + jj));
-                e4[jj] = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * (j0 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const int j = j0 + jj;
-                const float thv[4] = {th4[jj].x, th4[jj].y, th4[jj].z, th4[jj].w}, ev[4] = {e4[jj].x, e4[jj].y, e4[jj].z, e4[jj].w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float t1 = fmaf(-thv[u], thv[u], 1.f), t2 = -2.f * thv[u] * t1;
-                  x[4 * j + u] = lane == 0 ? x[4 * j + u] + thv[u] : fmaf(t2, ev[u], fmaf(t1, t[4 * j + u], x[4 * j + u]));
-                }
-              }
-            }
-            __syncwarp();
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = fmaf(__uint_as_float(v[j]), inv_scale, x[j]);
-            if (lane == 0) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 b4 = lds128(gbb + 2048u + 4u * c0 + 16u * j);
-                x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
-              }
-            }
-          }
-          DH_LNLAP(1)
-          // statistics: sum x, sum x^2, sum x_0 x (x_0 = the value row of this electron)
-          float x0[32];
-          bcast32(x0, x);
-          float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, p4 = 0.f, p5 = 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            p0 += x[j]; p1 += x[j + 1];
-            p2 = fmaf(x[j], x[j], p2); p3 = fmaf(x[j + 1], x[j + 1], p3);
-            p4 = fmaf(x0[j], x[j], p4); p5 = fmaf(x0[j + 1], x[j + 1], p5);
-          }
-          s_x += p0 + p1; s_xx += p2 + p3; s_x0x += p4 + p5;
-          DH_LNLAP(2)
-          tmem_st32(tbase + (uint32_t)c0, x);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        DH_LNLAP(3)
-        // ---- the two warps of the quarter exchange their halves of the row sums
-        sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u, s_x);
-        sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u + 4u, s_xx);
-        sts32(xch + (uint32_t)(chalf * 32 + lane) * 12u + 8u, s_x0x);
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        s_x += lds32(xch + (uint32_t)((1 - chalf) * 32 + lane) * 12u);
-        s_xx += lds32(xch + (uint32_t)((1 - chalf) * 32 + lane) * 12u + 4u);
-        s_x0x += lds32(xch + (uint32_t)((1 - chalf) * 32 + lane) * 12u + 8u);
-        constexpr float invD = 1.f / 256.f;
-        const float mu = s_x * invD;
-        const float mu0 = __shfl_sync(0xffffffffu, mu, 0);
-        const float var = fmaxf(__shfl_sync(0xffffffffu, s_xx, 0) * invD - mu0 * mu0, 0.f) + 1e-5f;
-        const float rho0 = rsqrtf(var), rho1 = -0.5f * rho0 / var, rho2 = 0.75f * rho0 / (var * var);
-        const float m_r = s_x0x * invD - mu0 * mu;  // mean(c_0 c_r)
-        const float q_r = s_xx * invD - mu * mu;    // mean(c_r^2)
-        const float v_r = 2.f * m_r;
-        float rho_r = rho1 * v_r;
-        const float sum_q = warp_sum(isJ ? q_r : 0.f), sum_vv = warp_sum(isJ ? v_r * v_r : 0.f);
-        const float vD = __shfl_sync(0xffffffffu, v_r, (lane + 29) & 31), qD = __shfl_sync(0xffffffffu, q_r, (lane + 29) & 31);
-        if (isS) rho_r = rho1 * (v_r + 2.f * sum_q) + rho2 * sum_vv;
-        if (isT) rho_r = rho1 * (v_r + 2.f * qD) + rho2 * vD * vD;
-        if (lane == 0) rho_r = 0.f;
-        const float rho_first = (isJ || (lane >= 26 && lane <= 28)) ? rho1 * v_r : 0.f;  // rho of a first-order row
-        DH_LNLAP(4)
-        // ---- pass B
-#pragma unroll 1
-        for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
-          uint32_t v[32];
-          DH_LNLAP(9)
-          tmem_ld32(tbase + (uint32_t)c0, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          DH_LNLAP(5)
-          if (c0 + 2 * EPI_CHUNK >= BLOCK_N) {  // last read of this accumulator
+          if (ml + 2 >= mt) {  // this warp's last read of the tile's accumulators: hand TMEM back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(leader(tmem_empty_bar(ab)));
           }
-          if (c0 + 2 * EPI_CHUNK >= BLOCK_N && tk + 1 < my_tiles) {  // first residual line of the next tile
-            const int64_t mn = band_of(tk + 1) * BLOCK_M + row;
-            if (mn < M) asm volatile("prefetch.global.L1 [%0];" ::"l"(ln.res + mn * ldc + chalf * EPI_CHUNK));
+#pragma unroll
+          for (int j = 0; j < ORB_NK; ++j) {
+            float cr = __uint_as_float(v[j]) * inv_scale, ci = __uint_as_float(v[ORB_NK + j]) * inv_scale;
+            const float br = __shfl_sync(0xffffffffu, bre, j), bi = __shfl_sync(0xffffffffu, bre, ORB_NK + j);
+            if (lane == 0) { cr += br; ci += bi; }  // the bias belongs to the value row only
+            const float c0r = __shfl_sync(0xffffffffu, cr, 0), c0i = __shfl_sync(0xffffffffu, ci, 0);
+            // own row x env_0
+            oacc[j] = fmaf(cr, e0.x, fmaf(-ci, e0.y, oacc[j]));
+            oacc[ORB_NK + j] = fmaf(cr, e0.y, fmaf(ci, e0.x, oacc[ORB_NK + j]));
+            // value row x env_s1 (product rule)
+            oacc[j] = fmaf(w1 * c0r, e1.x, fmaf(-w1 * c0i, e1.y, oacc[j]));
+            oacc[ORB_NK + j] = fmaf(w1 * c0r, e1.y, fmaf(w1 * c0i, e1.x, oacc[ORB_NK + j]));
+            // own row x env_s2 (second accumulator: goes to S / T_a doubled)
+            oacc2[j] = fmaf(w2 * cr, e2.x, fmaf(-w2 * ci, e2.y, oacc2[j]));
+            oacc2[ORB_NK + j] = fmaf(w2 * cr, e2.y, fmaf(w2 * ci, e2.x, oacc2[ORB_NK + j]));
           }
-          float c[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) c[j] = __uint_as_float(v[j]) - mu;
-          stage_free();
-          DH_LNLAP(6)
-          // products c_r rho_r of the first-order rows -> staging tile; lane = column sums them (S) / picks them (T)
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts128(st_row(lane, j), make_float4(c[4 * j] * rho_first, c[4 * j + 1] * rho_first, c[4 * j + 2] * rho_first, c[4 * j + 3] * rho_first));
-          float c0v[32];
-          bcast32(c0v, c);  // (its __syncwarp also publishes the staged products)
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-          for (int k0 = 1; k0 <= 24; k0 += 8) {  // eight loads in flight before the first is used
-            float wk[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) wk[u] = lds32(st_el(k0 + u, lane));
-#pragma unroll
-            for (int u = 0; u < 8; u += 2) { a0 += wk[u]; a1 += wk[u + 1]; }
-          }
-          sts32(vec + 128 + 4 * lane, a0 + a1);
-#pragma unroll
-          for (int a3 = 0; a3 < 3; ++a3) sts32(vec + 256 + 128 * a3 + 4 * lane, lds32(st_el(26 + a3, lane)));
+        }
+        if (mt <= chalf) {  // a narrow last tile can leave the odd warp without a group
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          float y[32];
+          if (lane == 0) mbar_arrive_cluster(leader(tmem_empty_bar(ab)));
+        }
+        if (nt == n_ntiles - 1) {
+          // the band is complete: the odd warp hands its partial sums to the even one, which assembles and stores
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // both warps are done with the envelope table
+          if (chalf == 1) {
 #pragma unroll
-          for (int j0 = 0; j0 < 8; j0 += 4) {
-            float4 e4[4], g4[4];
+            for (int j = 0; j < ORB_GW; ++j) { xsum[j * 32 + lane] = oacc[j]; xsum[(ORB_GW + j) * 32 + lane] = oacc2[j]; }
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+          if (chalf == 0) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              e4[jj] = xr >= 0 ? lds128(vec + 128 + 128 * xr + 16 * (j0 + jj)) : make_float4(0.f, 0.f, 0.f, 0.f);
-              g4[jj] = lds128(gbb + 4u * c0 + 16u * (j0 + jj));
+            for (int j = 0; j < ORB_GW; ++j) { oacc[j] += xsum[j * 32 + lane]; oacc2[j] += xsum[(ORB_GW + j) * 32 + lane]; }
+            // S += 2 (acc2 of J(2i) + acc2 of J(2i+1)); T_a += 2 acc2 of D_a
+            const int srcA = r == 25 ? 1 + 2 * ei : (r >= 29 ? r - 3 : 0), srcB = 2 + 2 * ei;
+            const float wA = (r == 25 || r >= 29) ? 2.f : 0.f, wB = r == 25 ? 2.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < ORB_GW; ++j) {
+              const float a = __shfl_sync(0xffffffffu, oacc2[j], srcA), b2 = __shfl_sync(0xffffffffu, oacc2[j], srcB);
+              oacc[j] = fmaf(wA, a, fmaf(wB, b2, oacc[j]));
             }
+            if (m < M) {
+              const int64_t wb = ge / 12;
+              float* dst = orb.Mj + (((wb * 32 + r) * 12 + ei) * 12) * 2;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j0 + jj;
-              const float ev[4] = {e4[jj].x, e4[jj].y, e4[jj].z, e4[jj].w}, gv[4] = {g4[jj].x, g4[jj].y, g4[jj].z, g4[jj].w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u)
-                y[4 * j + u] = gv[u] * fmaf(2.f, ev[u], fmaf(c0v[4 * j + u], rho_r, c[4 * j + u] * rho0));
+              for (int j = 0; j < ORB_NK; j += 2)
+                *reinterpret_cast<float4*>(dst + 2 * j) = make_float4(oacc[j], oacc[ORB_NK + j], oacc[j + 1], oacc[ORB_NK + j + 1]);
             }
           }
-          if (lane == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b4 = lds128(gbb + 1024u + 4u * c0 + 16u * j);
-              y[4 * j] += b4.x; y[4 * j + 1] += b4.y; y[4 * j + 2] += b4.z; y[4 * j + 3] += b4.w;
-            }
-          }
-          DH_LNLAP(7)
-          __syncwarp();  // every lane has read the staged products before the tile is overwritten with the outputs
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sts128(st_row(lane, j), make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]));
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmC, stg, n0 + c0, (int)(m0 + q * 32));
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          DH_LNLAP(8)
         }
         continue;
       }
@@ -1452,7 +1323,7 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.rpg = rpg; g.f16 = f16; g.merged = merged; g.reduce_add = 0;
   g.a_scale = nullptr;
   g.A_lo = nullptr;
-  g.ln_res = nullptr; g.ln_gamma = nullptr; g.ln_beta = nullptr; g.ln_tanh = 0;
+  g.orb_env = nullptr; g.orb_Mj = nullptr; g.orb_L = 0;
   return gemm_tc_ex(g, stream);
 }
 
@@ -1525,12 +1396,13 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   // resident A (pair form): K <= 256 and more than one column tile per band; DH_GEMM_RES=0 disables
   static const bool res_env = !(dbg_env("DH_GEMM_RES") && atoi(dbg_env("DH_GEMM_RES")) == 0);
   const int res = (pair && res_env && K <= 8 * tc::BLOCK_K && N > tc::BLOCK_N) ? 1 : 0;
-  // fused LayerNorm epilogue: pair form, one 256-wide column tile, 32 jet rows per electron, TMA-stored output
-  tc::LnFuse lnf;
-  lnf.res = gm.ln_res; lnf.gamma = gm.ln_gamma; lnf.beta = gm.ln_beta; lnf.tanh_mode = gm.ln_tanh;
-  const bool ln_on = gm.ln_res != nullptr;
-  if (ln_on && !(pair && N == tc::BLOCK_N && rpg == 32 && tma_store && !reduce_add && gm.a_scale == nullptr && M % 32 == 0 &&
-                 (reinterpret_cast<uintptr_t>(gm.ln_res) & 15) == 0))
+  // fused envelope contraction (orbital matrices): pair form with resident A, 32 jet rows per electron, whole electrons per
+  // band, weights in the permuted [tile][m][re | im] layout (10 m per 256-column tile)
+  tc::OrbFuse orb;
+  orb.env = gm.orb_env; orb.Mj = gm.orb_Mj; orb.L = gm.orb_L;
+  const bool orb_on = gm.orb_env != nullptr;
+  if (orb_on && !(pair && res && rpg == 32 && !reduce_add && gm.a_scale == nullptr && M % 128 == 0 && gm.orb_L >= 1 && gm.orb_L <= 48 &&
+                  N == (gm.orb_L - 1) / tc::ORB_MPT * tc::BLOCK_N + ((gm.orb_L - 1) % tc::ORB_MPT + 1) * tc::ORB_GW))
     return -2;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
@@ -1547,11 +1419,11 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   lc.numAttrs = 1;
   cudaError_t le;
 #define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR, false>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
-                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof, \
+                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, prof, \
                                                         g_range_flag)
-  if (ln_on)
+  if (orb_on)
     le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<true, true, true, true>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K,
-                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, lnf, prof, g_range_flag);
+                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, prof, g_range_flag);
   else if (pair) DH_LAUNCH_TC(true, true, true);
   else if (f16) { if (merged) DH_LAUNCH_TC(true, true, false); else DH_LAUNCH_TC(true, false, false); }
   else { if (merged) DH_LAUNCH_TC(false, true, false); else DH_LAUNCH_TC(false, false, false); }
@@ -1561,11 +1433,6 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
     unsigned long long h[40];
     cudaStreamSynchronize(stream);
     cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
-    if (ln_on)
-      fprintf(stderr, "[gemm_tc LN epilogue, tanh=%d] per CTA cycles: A tmem ld %.0f | A build x %.0f | A stats %.0f | A st wait %.0f | exchange %.0f | "
-              "B tmem ld %.0f | B stage_free %.0f | B sums + y %.0f | B store %.0f | between %.0f\n", gm.ln_tanh,
-              h[22] / (double)grid.x, h[23] / (double)grid.x, h[24] / (double)grid.x, h[25] / (double)grid.x, h[26] / (double)grid.x,
-              h[27] / (double)grid.x, h[28] / (double)grid.x, h[29] / (double)grid.x, h[30] / (double)grid.x, h[31] / (double)grid.x);
     const double g = (double)grid.x, tp = (double)tiles / g;
     fprintf(stderr, "[gemm_tc M=%lld N=%d f16=%d] per CTA: tiles %.1f | total cyc %.0f | producer wait empty %.0f | "
             "mma wait tmem_empty %.0f full %.0f split %.0f | splitter wait full %.0f work %.0f | epi wait tmem_full %.0f drain %.0f "

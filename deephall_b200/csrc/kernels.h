@@ -29,9 +29,11 @@ struct TcGemm {
   float* C; int64_t ldc;
   int64_t M; int N, K, rpg, f16, merged, reduce_add;
   const float* a_scale;  // optional device {s, 1/s}: A is multiplied by s before the split, C by 1/s
-  // fused LayerNorm epilogue (jet passes, pair form, N = 256, rpg = 32): C = LN(ln_res + acc) or LN(ln_res + tanh(acc + bias))
-  // with the jet rules of residual_layernorm_kernel, written in place over ln_res (= C); null = off
-  const float* ln_res; const float* ln_gamma; const float* ln_beta; int ln_tanh;
+  // fused envelope contraction (jet passes at N = 12, one determinant, pair form with resident A): the contraction is the
+  // orbital projection with its weights in the permuted [tile][m][re | im][column] layout (orb_permute_weights) and the
+  // epilogue contracts the coefficients with the per-electron envelope table orb_env [electrons][10][orb_L] complex into the
+  // orbital-matrix jets orb_Mj -- C is not written; null = off
+  const float* orb_env; float* orb_Mj; int orb_L;
   const void* A_lo;      // non-null (fp16 pieces only): A and A_lo are fp16 hi / lo planes [M][lda] written by the
                          // producing kernel; the in-kernel split is skipped
 };
@@ -94,6 +96,11 @@ struct TailDims {
   int qp_a = 0;     // its u exponent Q1 + lz, in [-1, 2 Q1 + 1]
 };
 // c: [B*N*R, 2*nsb*L*N*K] (per spin block: re block | im block) -> M jets [B][K][R][N][N] complex
+// envelope jets of every electron as a table [B N][10][L] complex (right operand of the fused envelope contraction)
+int envelope_table(const float* x, const double* normfac, float* tab, int64_t B, TailDims d, cudaStream_t s);
+// orbital-projection kernels / biases -> fp32 [D][ncol] + [ncol] with columns ordered [tile][m (10)][re | im][NK]
+int orb_permute_weights(const float* Wre, const float* Wim, const float* bre, const float* bim, float* Wp, float* bp, int D, int L,
+                        int NK, int ncol, cudaStream_t s);
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s);
 // Laughlin ground-state orbital matrix jets (networks/laughlin.py:59-71): Mj [B][1][R][N][N] complex; d.L == d.N,

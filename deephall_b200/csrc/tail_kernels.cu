@@ -598,6 +598,50 @@ orbital_contract_vec_kernel(const float* __restrict__ c, const float* __restrict
   }
 }
 
+// Envelope jets of every electron as a table [electrons][ENV_SLOTS][L] complex: the right operand of the envelope
+// contraction when it runs as the epilogue of the orbital projection (gemm_tc.cu, ORB).  One block per electron.
+__global__ void __launch_bounds__(64)
+envelope_table_kernel(const float* __restrict__ x, const double* __restrict__ normfac, float* __restrict__ tab, TailDims dm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int L = dm.L;
+  dcplx* upow = reinterpret_cast<dcplx*>(smraw);
+  dcplx* vpow = upow + L;
+  cplx* env = reinterpret_cast<cplx*>(vpow + L);  // [ENV_SLOTS][L]
+  const int64_t bi = blockIdx.x;
+  envelope_jets(x[bi * 2], x[bi * 2 + 1], dm.twoQ, normfac, upow, vpow, env, ENV_SLOTS);  // ends with __syncthreads
+  float* dst = tab + bi * (int64_t)(ENV_SLOTS * 2) * L;
+  const float* src = reinterpret_cast<const float*>(env);
+  for (int t = threadIdx.x; t < ENV_SLOTS * 2 * L; t += blockDim.x) dst[t] = src[t];
+}
+int envelope_table(const float* x, const double* normfac, float* tab, int64_t B, TailDims d, cudaStream_t s) {
+  const size_t smem = 2 * d.L * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
+  envelope_table_kernel<<<(unsigned)(B * d.N), 64, smem, s>>>(x, normfac, tab, d);
+  return (int)cudaGetLastError();
+}
+
+// Orbital-projection kernels [D][L N] (real part, imaginary part) and biases -> ONE fp32 matrix [D][ncol] and bias [ncol]
+// whose columns are ordered for the fused envelope contraction: tile t (256 columns) holds the orbitals m = 10 t .. 10 t + 9,
+// each as 24 columns [re(m, 0..11) | im(m, 0..11)]; the remaining columns of a tile are zero.
+__global__ void orb_permute_weights_kernel(const float* __restrict__ Wre, const float* __restrict__ Wim, const float* __restrict__ bre,
+                                           const float* __restrict__ bim, float* __restrict__ Wp, float* __restrict__ bp, int D,
+                                           int L, int NK, int ncol) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)(D + 1) * ncol) return;
+  const int k = (int)(t / ncol), n = (int)(t % ncol);
+  const int tile = n >> 8, rem = n & 255, ml = rem / (2 * NK), w = rem - ml * 2 * NK;
+  const int m = 10 * tile + ml, part = w / NK, col = w - part * NK;
+  const bool valid = ml < 10 && m < L;
+  const int src = m * NK + col;
+  if (k < D) Wp[(int64_t)k * ncol + n] = valid ? (part ? Wim : Wre)[(int64_t)k * L * NK + src] : 0.f;
+  else bp[n] = valid ? (part ? bim : bre)[src] : 0.f;
+}
+int orb_permute_weights(const float* Wre, const float* Wim, const float* bre, const float* bim, float* Wp, float* bp, int D, int L,
+                        int NK, int ncol, cudaStream_t s) {
+  const int64_t n = (int64_t)(D + 1) * ncol;
+  orb_permute_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Wre, Wim, bre, bim, Wp, bp, D, L, NK, ncol);
+  return (int)cudaGetLastError();
+}
+
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s) {
   // (the value-only kernel measured 1 % slower with the same prefetch: its prologue is one warp's, not a block's)
