@@ -464,13 +464,13 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     // The envelope contraction (blocks.py:59-70) is the EPILOGUE of the orbital projection (blocks.py:28-35): the per-electron
     // envelope jets go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the contraction reads
     // its coefficients out of tensor memory and writes the orbital-matrix jets -- c[rows][2 L N] never exists in HBM
-    { ProfScope pse(p, PC_TAIL, 0, s);
-      if ((rc = envelope_table(x, p->d_normfac, w.cbuf, Bc, td, s))) return rc; }
     const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
+    { ProfScope pse(p, PC_TAIL, 0, s);
+      if ((rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s))) return rc; }
     ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * p->orbN * p->D, s);
     TcGemm g;
     g.A = w.h; g.lda = p->D; g.Wt_hi = p->prep + sl.hi; g.Wt_lo = p->prep + sl.lo; g.ldw = p->D;
-    g.bias = p->prep + sl.bias; g.inv_scale = p->prep + sl.scale + 1;
+    g.bias = nullptr; g.inv_scale = nullptr;  // both are folded into the envelope table
     g.C = w.Mj; g.ldc = sl.Nout; g.M = rows; g.N = sl.Nout; g.K = p->D; g.rpg = R;
     g.f16 = 1; g.merged = 1; g.reduce_add = 0; g.a_scale = nullptr; g.A_lo = nullptr;
     g.orb_env = w.cbuf; g.orb_Mj = w.Mj; g.orb_L = p->L;

@@ -293,7 +293,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // (blocks.py:28-35) and its epilogue is the envelope contraction that follows it (blocks.py:59-70) -- the coefficient
 // tensor c[rows][2 L N] (the largest activation of the pass) never goes to HBM.  See the epilogue.
 struct OrbFuse {
-  const float* env;  // [electrons][10 slots][L] complex: envelope jets per electron (envelope_table, tail_kernels.cu)
+  const float* env;  // per electron: [10 slots][L] complex envelope jets, pre-multiplied by the weight un-scale factor, then
+                     // [10][12] complex bias products sum_m bias(m, j) env_s[m]  (envelope_table, tail_kernels.cu)
   float* Mj;         // out: orbital-matrix jets [walkers][32 rows][12 electrons][12 orbitals] complex
   int L;             // orbitals 2Q + 1
 };
@@ -727,11 +728,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (nt == 0) {
           // stage this electron's envelope table; both warps of the quarter fill and read it
           asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // the previous band's reads are done
-          const float* eg = orb.env + ge * (int64_t)(10 * 2) * L;
+          const float* eg = orb.env + ge * (int64_t)(10 * 2 * L + 10 * 2 * ORB_NK);
+          const bool live = m0 + q * 32 < M;
           for (int t = chalf * 32 + lane; t < 10 * 2 * L; t += 64) {
             const int sl = t / (2 * L), rest = t - sl * 2 * L;
-            envs[sl * 96 + rest] = (m0 + q * 32 < M) ? __ldg(eg + t) : 0.f;
+            envs[sl * 96 + rest] = live ? __ldg(eg + t) : 0.f;
           }
+          for (int t = chalf * 32 + lane; t < 10 * 2 * ORB_NK; t += 64) envs[1536 + t] = live ? __ldg(eg + 10 * 2 * L + t) : 0.f;
           asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
 #pragma unroll
           for (int j = 0; j < ORB_GW; ++j) { oacc[j] = 0.f; oacc2[j] = 0.f; }
@@ -743,11 +746,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint32_t v[24];
           tmem_ld16(tbase + (uint32_t)(ORB_GW * ml), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
           tmem_ld8(tbase + (uint32_t)(ORB_GW * ml + 16), *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
+          // (the table carries the weight un-scale factor; rows without a product-rule term read slot 0 with weight 0)
           const float2 e0 = *reinterpret_cast<const float2*>(envs + 2 * mm);
-          const float2 e1 = *reinterpret_cast<const float2*>(envs + s1 * 96 + 2 * mm);
-          const float2 e2 = *reinterpret_cast<const float2*>(envs + s2 * 96 + 2 * mm);
-          const float w1 = s1 ? 1.f : 0.f, w2 = s2 ? 1.f : 0.f;
-          const float bre = (bias != nullptr && lane < ORB_GW) ? __ldg(bias + n0 + ORB_GW * ml + lane) : 0.f;  // lane j: bias of column j
+          float2 e1 = *reinterpret_cast<const float2*>(envs + s1 * 96 + 2 * mm);
+          float2 e2 = *reinterpret_cast<const float2*>(envs + s2 * 96 + 2 * mm);
+          if (!s1) e1 = make_float2(0.f, 0.f);
+          if (!s2) e2 = make_float2(0.f, 0.f);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (ml + 2 >= mt) {  // this warp's last read of the tile's accumulators: hand TMEM back to the MMA issuer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -756,19 +760,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < ORB_NK; ++j) {
-            float cr = __uint_as_float(v[j]) * inv_scale, ci = __uint_as_float(v[ORB_NK + j]) * inv_scale;
-            const float br = __shfl_sync(0xffffffffu, bre, j), bi = __shfl_sync(0xffffffffu, bre, ORB_NK + j);
-            if (lane == 0) { cr += br; ci += bi; }  // the bias belongs to the value row only
+            const float cr = __uint_as_float(v[j]), ci = __uint_as_float(v[ORB_NK + j]);
             const float c0r = __shfl_sync(0xffffffffu, cr, 0), c0i = __shfl_sync(0xffffffffu, ci, 0);
             // own row x env_0
             oacc[j] = fmaf(cr, e0.x, fmaf(-ci, e0.y, oacc[j]));
             oacc[ORB_NK + j] = fmaf(cr, e0.y, fmaf(ci, e0.x, oacc[ORB_NK + j]));
             // value row x env_s1 (product rule)
-            oacc[j] = fmaf(w1 * c0r, e1.x, fmaf(-w1 * c0i, e1.y, oacc[j]));
-            oacc[ORB_NK + j] = fmaf(w1 * c0r, e1.y, fmaf(w1 * c0i, e1.x, oacc[ORB_NK + j]));
+            oacc[j] = fmaf(c0r, e1.x, fmaf(-c0i, e1.y, oacc[j]));
+            oacc[ORB_NK + j] = fmaf(c0r, e1.y, fmaf(c0i, e1.x, oacc[ORB_NK + j]));
             // own row x env_s2 (second accumulator: goes to S / T_a doubled)
-            oacc2[j] = fmaf(w2 * cr, e2.x, fmaf(-w2 * ci, e2.y, oacc2[j]));
-            oacc2[ORB_NK + j] = fmaf(w2 * cr, e2.y, fmaf(w2 * ci, e2.x, oacc2[ORB_NK + j]));
+            oacc2[j] = fmaf(cr, e2.x, fmaf(-ci, e2.y, oacc2[j]));
+            oacc2[ORB_NK + j] = fmaf(cr, e2.y, fmaf(ci, e2.x, oacc2[ORB_NK + j]));
           }
         }
         if (mt <= chalf) {  // a narrow last tile can leave the odd warp without a group
@@ -794,6 +796,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < ORB_GW; ++j) {
               const float a = __shfl_sync(0xffffffffu, oacc2[j], srcA), b2 = __shfl_sync(0xffffffffu, oacc2[j], srcB);
               oacc[j] = fmaf(wA, a, fmaf(wB, b2, oacc[j]));
+            }
+            // the bias sits on the value row only: its products with the envelope slots come ready-made from the table
+            {
+              const float* bp0 = envs + 1536;              // slot 0: the value row's own output
+              const float* bp1 = envs + 1536 + s1 * 2 * ORB_NK;  // slot s1: the product-rule term of this row
+              const float u0 = r == 0 ? 1.f : 0.f, u1 = s1 ? 1.f : 0.f;
+#pragma unroll
+              for (int j = 0; j < ORB_NK; ++j) {
+                oacc[j] = fmaf(u0, bp0[2 * j], fmaf(u1, bp1[2 * j], oacc[j]));
+                oacc[ORB_NK + j] = fmaf(u0, bp0[2 * j + 1], fmaf(u1, bp1[2 * j + 1], oacc[ORB_NK + j]));
+              }
             }
             if (m < M) {
               const int64_t wb = ge / 12;

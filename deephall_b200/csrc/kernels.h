@@ -96,8 +96,10 @@ struct TailDims {
   int qp_a = 0;     // its u exponent Q1 + lz, in [-1, 2 Q1 + 1]
 };
 // c: [B*N*R, 2*nsb*L*N*K] (per spin block: re block | im block) -> M jets [B][K][R][N][N] complex
-// envelope jets of every electron as a table [B N][10][L] complex (right operand of the fused envelope contraction)
-int envelope_table(const float* x, const double* normfac, float* tab, int64_t B, TailDims d, cudaStream_t s);
+// per electron: envelope jets [10][L] complex, multiplied by *unscale, followed by the bias products [10][N K] complex
+// (sum_m bias(m, j) env_s[m]): the right operand of the fused envelope contraction (gemm_tc.cu, ORB)
+int envelope_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
+                   int64_t B, TailDims d, cudaStream_t s);
 // orbital-projection kernels / biases -> fp32 [D][ncol] + [ncol] with columns ordered [tile][m (10)][re | im][NK]
 int orb_permute_weights(const float* Wre, const float* Wim, const float* bre, const float* bim, float* Wp, float* bp, int D, int L,
                         int NK, int ncol, cudaStream_t s);

@@ -601,21 +601,32 @@ orbital_contract_vec_kernel(const float* __restrict__ c, const float* __restrict
 // Envelope jets of every electron as a table [electrons][ENV_SLOTS][L] complex: the right operand of the envelope
 // contraction when it runs as the epilogue of the orbital projection (gemm_tc.cu, ORB).  One block per electron.
 __global__ void __launch_bounds__(64)
-envelope_table_kernel(const float* __restrict__ x, const double* __restrict__ normfac, float* __restrict__ tab, TailDims dm) {
+envelope_table_kernel(const float* __restrict__ x, const double* __restrict__ normfac, const float* __restrict__ bre,
+                      const float* __restrict__ bim, const float* __restrict__ unscale, float* __restrict__ tab, TailDims dm) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int L = dm.L;
+  const int L = dm.L, NK = dm.N * dm.K;
   dcplx* upow = reinterpret_cast<dcplx*>(smraw);
   dcplx* vpow = upow + L;
   cplx* env = reinterpret_cast<cplx*>(vpow + L);  // [ENV_SLOTS][L]
   const int64_t bi = blockIdx.x;
   envelope_jets(x[bi * 2], x[bi * 2 + 1], dm.twoQ, normfac, upow, vpow, env, ENV_SLOTS);  // ends with __syncthreads
-  float* dst = tab + bi * (int64_t)(ENV_SLOTS * 2) * L;
+  float* dst = tab + bi * (int64_t)(ENV_SLOTS * 2 * L + ENV_SLOTS * 2 * NK);
+  const float us = unscale ? __ldg(unscale) : 1.f;  // the contraction's accumulators are (weights x power of two): undone here
   const float* src = reinterpret_cast<const float*>(env);
-  for (int t = threadIdx.x; t < ENV_SLOTS * 2 * L; t += blockDim.x) dst[t] = src[t];
+  for (int t = threadIdx.x; t < ENV_SLOTS * 2 * L; t += blockDim.x) dst[t] = src[t] * us;
+  // bias products: the bias sits on the value row, so its share of every output is sum_m bias(m, j) env_s[m]
+  for (int t = threadIdx.x; t < ENV_SLOTS * NK; t += blockDim.x) {
+    const int sl = t / NK, j = t - sl * NK;
+    cplx acc = cmake(0.f, 0.f);
+    for (int m = 0; m < L; ++m) acc = cfma(cmake(bre[m * NK + j], bim[m * NK + j]), env[sl * L + m], acc);
+    dst[ENV_SLOTS * 2 * L + 2 * t] = acc.x;
+    dst[ENV_SLOTS * 2 * L + 2 * t + 1] = acc.y;
+  }
 }
-int envelope_table(const float* x, const double* normfac, float* tab, int64_t B, TailDims d, cudaStream_t s) {
+int envelope_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
+                   int64_t B, TailDims d, cudaStream_t s) {
   const size_t smem = 2 * d.L * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
-  envelope_table_kernel<<<(unsigned)(B * d.N), 64, smem, s>>>(x, normfac, tab, d);
+  envelope_table_kernel<<<(unsigned)(B * d.N), 64, smem, s>>>(x, normfac, bre, bim, unscale, tab, d);
   return (int)cudaGetLastError();
 }
 
