@@ -62,7 +62,7 @@ def flops_local_energy_per_walker(N, L, K, D=256, nl=2):
 
 def gemm_traffic_per_launch():
     """dram bytes (read + write) per launch of the dominant kernel from the committed ncu --set full
-    summary (profiles/r1_gemm_traffic.json), or None."""
+    summary (profiles/r2_gemm_traffic.json), or None."""
     try:
         with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
             return json.load(f)["avg_dram_bytes_per_launch"]
@@ -216,7 +216,7 @@ def run_ours(args):
 
     vmc = make_vmc(B)
     model, params = vmc.model, vmc.state.params
-    vmc.burn_in(20)  # synthetic walkers: short equilibration, not timed
+    vmc.burn_in(args.burn_in)  # synthetic walkers: short equilibration, not timed
     data = vmc.state.data
     plan = model.plan(system)
     energy_step = loss.make_loss_fn(model.apply, system, loss.LossMode.ENERGY_DIFF)  # what optimizers/none.py:32 runs
@@ -328,7 +328,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (Philox uniform walkers + 20 burn-in sweeps, random-init parameters)",
+            "data": f"synthetic (Philox uniform walkers + {args.burn_in} burn-in sweeps, random-init parameters)",
             "config": {"workload": W["name"], "global_batch": B * world, "walkers_per_gpu": B,
                        "parallelism": f"walkers sharded x{world}; energy statistics all-reduced (NCCL) inside the timed step",
                        "l2": "per-pass working set (GBs of jet activations) exceeds the 126 MB L2; no explicit flush"},
@@ -364,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--burn-in", type=int, default=20, help="untimed Metropolis sweeps before the measurement (profiling runs use 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
