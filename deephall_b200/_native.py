@@ -75,6 +75,8 @@ SIGNATURES = OrderedDict(
     dh_init_walkers=(C.c_int, [_vp, _vp, _i64, _u64, _u64, _vp]),
     dh_logpsi_vjp=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     dh_slogdet=(C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp]),
+    dh_energy_stats=(C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    dh_energy_diff=(C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     dh_spd_inverse=(C.c_int, [_vp, _i32, _i32, _vp]),
     dh_gemm_workspace_bytes=(C.c_int, [_i32, _i32, _i32, C.POINTER(C.c_size_t)]),
     dh_gemm=(C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp, C.c_size_t, _vp]),
@@ -383,6 +385,43 @@ def spd_inverse(mats, inplace=False):
     out = mats if (inplace and mats.is_contiguous()) else mats.contiguous().clone()
     _check(lib.dh_spd_inverse(_ptr(out), out.shape[-1], out.shape[0], _stream()), "dh_spd_inverse")
     return out
+
+
+ENERGY_STATS_MAX_BATCH = 32768  # walkers per rank the statistics kernels sort in shared memory
+
+
+def energy_stats(el, obs):
+    """Rank-local packed statistics vector (16 floats, device) of dh_energy_stats; el complex64 (B,), obs the
+    OtherObservables dict of (B,) tensors."""
+    _need_cuda()
+    lib = load()
+    B = int(el.shape[0])
+    out = torch.empty(16, dtype=torch.float32, device=el.device)
+    e = torch.view_as_real(el.contiguous())
+    k = torch.view_as_real(obs["kinetic"].contiguous())
+    _check(lib.dh_energy_stats(_ptr(e), _ptr(k), _ptr(_f32(obs["potential"].contiguous(), "potential")),
+                               _ptr(obs["angular_momentum_z"].contiguous()), _ptr(obs["angular_momentum_z_square"].contiguous()),
+                               _ptr(obs["angular_momentum_square"].contiguous()), B, _ptr(out), _stream()), "dh_energy_stats")
+    return out
+
+
+def energy_diff(el, obs, reduced, lz_penalty=0.0, lz_center=0.0, l2_penalty=0.0, logpsi=None):
+    """-> (diff complex64 (B,), cot (B, 2) f32, ok (B,) f32, counts (2,) f32) of dh_energy_diff."""
+    _need_cuda()
+    lib = load()
+    B = int(el.shape[0])
+    dev = el.device
+    diff = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    cot = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    ok = torch.empty((B,), dtype=torch.float32, device=dev)
+    counts = torch.empty((2,), dtype=torch.float32, device=dev)
+    e = torch.view_as_real(el.contiguous())
+    lp = torch.view_as_real(logpsi.contiguous()) if logpsi is not None else None
+    _check(lib.dh_energy_diff(_ptr(e), _ptr(obs["angular_momentum_z"].contiguous()), _ptr(obs["angular_momentum_z_square"].contiguous()),
+                              _ptr(obs["angular_momentum_square"].contiguous()), _ptr(lp), B, _ptr(_f32(reduced.contiguous(), "reduced")),
+                              float(lz_penalty), float(lz_center), float(l2_penalty), _ptr(diff), _ptr(cot), _ptr(ok), _ptr(counts),
+                              _stream()), "dh_energy_diff")
+    return torch.view_as_complex(diff), cot, ok, counts
 
 
 def slogdet(mats):

@@ -850,6 +850,24 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
   return 0;
 }
 
+// --------------------------------------------------------------------------------- energy statistics (loss.py:66-92)
+extern "C" int dh_energy_stats(const float* el, const float* kinetic, const float* potential, const float* lz, const float* lz2,
+                               const float* l2, int64_t B, float* out16, void* stream) {
+  if (!el || !kinetic || !potential || !lz || !lz2 || !l2 || !out16) return DH_E_BADARG;
+  if (B < 1 || B > 32768) return DH_E_UNSUPPORTED;
+  return energy_stats(el, kinetic, potential, lz, lz2, l2, B, out16, (cudaStream_t)stream);
+}
+
+extern "C" int dh_energy_diff(const float* el, const float* lz, const float* lz2, const float* l2, const float* logpsi, int64_t B,
+                              const float* reduced16, float lz_penalty, float lz_center, float l2_penalty, float* out_diff,
+                              float* out_cot, float* out_ok, float* out_counts, void* stream) {
+  if (!el || !reduced16 || !out_diff || !out_cot) return DH_E_BADARG;
+  if ((lz_penalty != 0.f && (!lz || !lz2)) || (l2_penalty != 0.f && !l2)) return DH_E_BADARG;
+  if (B < 1 || B > 32768) return DH_E_UNSUPPORTED;
+  return energy_diff(el, lz, lz2, l2, logpsi, B, reduced16, lz_penalty, lz_center, l2_penalty, out_diff, out_cot, out_ok, out_counts,
+                     (cudaStream_t)stream);
+}
+
 extern "C" int dh_slogdet(const float* mats, int64_t B, int32_t K, int32_t n, float* out_sign,
                           float* out_logabs, float* out_logpsi, void* stream) {
   if (!mats) return DH_E_BADARG;

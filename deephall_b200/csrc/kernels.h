@@ -146,6 +146,11 @@ int mcmc_accept(float* x1, const float* x2, float* lp1, const float* lp2c, int l
                 unsigned long long* naccept, cudaStream_t s);
 int init_walkers(float* x, int64_t B, int N, uint64_t seed, uint64_t subseq0, cudaStream_t s);
 int lp_from_logpsi(const float* logpsi_c, float* lp, int64_t B, cudaStream_t s);
+// ---- stats_kernels.cu: energy statistics of a walker batch (loss.py:30-38,66-92); B <= 32768 per rank
+int energy_stats(const float* el, const float* kin, const float* pot, const float* lz, const float* lz2, const float* l2, int64_t B,
+                 float* out16, cudaStream_t s);
+int energy_diff(const float* el, const float* lz, const float* lz2, const float* l2, const float* lp, int64_t B, const float* red_stats,
+                float lz_penalty, float lz_center, float l2_penalty, float* diff, float* cot, float* ok, float* counts, cudaStream_t s);
 // device-resident arguments of a Metropolis move: lets one captured CUDA graph of a move be replayed for every move
 struct McmcDev { unsigned long long seed, offset, subseq0, naccept; float width; };
 int mcmc_dev_init(McmcDev* dv, uint64_t seed, uint64_t offset, uint64_t subseq0, float width, cudaStream_t s);

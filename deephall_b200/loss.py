@@ -3,7 +3,9 @@
 `make_loss_fn(network, system, mode)` returns `loss_and_grad(params, data)` as loss.py:47-110.
 The per-walker parameter gradients the reference materialises (loss.py:53-58, B x P x 2
 floats) are replaced by ONE vector-Jacobian product with cotangent (2/B_valid) * diff_b
-(dh_logpsi_vjp), which is the same number (loss.py:60-64,99-106).
+(dh_logpsi_vjp), which is the same number (loss.py:60-64,99-106).  The statistics themselves
+(iqr_clip, nanmean, nanquantile: loss.py:30-38,66-92) run as two kernels of the library
+(dh_energy_stats, dh_energy_diff) around ONE packed all-reduce.
 """
 from __future__ import annotations
 
@@ -11,7 +13,7 @@ import enum
 
 import torch
 
-from . import constants
+from . import _native, constants
 from .config import System
 from .hamiltonian import local_energy
 from .networks import B200Network as Psiformer  # any network of this engine
@@ -50,22 +52,43 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
         raise TypeError("network must be `model.apply` of a deephall_b200 network")
     batch_local_energy = local_energy(net.apply, system)
 
-    def masked_vjp(params, data, cot, valid, lp):
-        """One VJP over the valid walkers only.  The reference's loss_prod is a per-parameter nanmean over walkers
-        (loss.py:60-64): a walker whose log psi is not finite drops out.  Here such a walker gets a zero cotangent AND
-        its coordinates replaced by those of a valid walker, so that no 0 * NaN reaches the batched reverse pass; all
-        of it stream-ordered (no host synchronisation).  lp: log psi of the same walkers from the local-energy pass."""
-        ok = valid & torch.isfinite(lp.real) & torch.isfinite(lp.imag)
+    def vjp_over(params, data, cot, ok):
+        """One VJP with the cotangents `cot` (already zero for walkers outside `ok`); those walkers' coordinates are replaced
+        by an ok walker's, so that no 0 * NaN reaches the batched reverse pass (stream-ordered, no host synchronisation)."""
         first = ok.to(torch.int8).argmax()
         data = torch.where(ok[:, None, None], data, data.index_select(0, first[None])).contiguous()
-        # nanmean's denominator: the walkers that stay
-        scale = (valid.sum().clamp(min=1) / ok.sum().clamp(min=1)).to(cot.dtype)
-        cot = torch.where(ok[:, None], cot, torch.zeros_like(cot)) * scale
         return torch.nan_to_num(net.plan(system).logpsi_vjp(params, data, cot.contiguous()))
 
     def loss_and_grad(params: torch.Tensor, data: torch.Tensor):
         el, obs = batch_local_energy(params, data)  # loss.py:67
         lp = batch_local_energy.last_logpsi
+        if el.shape[0] > _native.ENERGY_STATS_MAX_BATCH:
+            return loss_and_grad_tensor_ops(params, data, el, obs, lp)
+        # loss.py:68-74,79-91: every rank-local mean in ONE kernel and ONE packed all-reduce (dh_energy_stats), then the
+        # clipped differences and the gradient's cotangents in a second kernel (dh_energy_diff)
+        red = constants.pmean(_native.energy_stats(el, obs))
+        diff, cot, ok, _counts = _native.energy_diff(el, obs, red, system.lz_penalty or 0.0, system.lz_center or 0.0,
+                                                     system.l2_penalty or 0.0, logpsi=lp)
+        stats = {
+            "angular_momentum_z": red[3], "angular_momentum_z_square": red[4], "angular_momentum_square": red[5],
+            "potential": red[2], "kinetic": torch.complex(red[0], red[1]),
+            "energy": torch.complex(red[6], red[7]), "variance": red[10] - red[6] * red[6],  # loss.py:91 (pmean is linear)
+        }
+        if mode == LossMode.ENERGY_DIFF:
+            return stats, diff
+        # loss.py:60-64,99-106: 2 * nanmean_b[(dRe_b - i dIm_b) diff_b], nan_to_num.  Its real part
+        # 2 * nanmean_b[dRe_b Re(diff_b) + dIm_b Im(diff_b)] is one VJP with cotangent (2/B_ok)(Re, Im) diff_b.
+        okb = ok > 0
+        grads = vjp_over(params, data, cot, okb)
+        if mode == LossMode.SR_F_VECTOR:
+            # loss.py:107-108 keeps the complex vector; its imaginary part 2 * nanmean_b[dRe_b Im(diff_b) - dIm_b Re(diff_b)]
+            # is a second VJP with cotangent (2/B)(Im, -Re) diff_b
+            cot_i = torch.stack([cot[:, 1], -cot[:, 0]], dim=-1)
+            return stats, torch.complex(grads, vjp_over(params, data, cot_i, okb))
+        return stats, grads
+
+    def loss_and_grad_tensor_ops(params, data, el, obs, lp):
+        """The same statistics with tensor ops: shards of more than 32768 walkers per rank (beyond the kernels' range)."""
         # loss.py:68-74,91: means, pmean'd in one packed all-reduce
         names = list(obs.keys())
         local = [obs[k].mean() for k in names] + [_nanmean(el), _nanmean(iqr_clip(el)), torch.nanmean(el.real**2)]
@@ -85,19 +108,14 @@ def make_loss_fn(network, system: System, mode: LossMode = LossMode.ENERGY_GRAD)
         stats["variance"] = mean_sq - loss.real**2  # loss.py:91 (pmean is linear)
         if mode == LossMode.ENERGY_DIFF:
             return stats, diff
-        # loss.py:60-64,99-106: 2 * nanmean_b[(dRe_b - i dIm_b) diff_b], nan_to_num.  Its real part
-        # 2 * nanmean_b[dRe_b Re(diff_b) + dIm_b Im(diff_b)] is one VJP with cotangent (2/B)(Re, Im) diff_b.
         d = torch.view_as_real(diff)
         valid = ~torch.isnan(d).any(-1)
-        nvalid = valid.sum().clamp(min=1).to(torch.float32)
-        cot = torch.where(valid[:, None], d, torch.zeros_like(d)) * (2.0 / nvalid)
-        grads = masked_vjp(params, data, cot, valid, lp)
+        ok = valid & torch.isfinite(lp.real) & torch.isfinite(lp.imag)
+        cot = torch.where(ok[:, None], d, torch.zeros_like(d)) * (2.0 / ok.sum().clamp(min=1).to(torch.float32))
+        grads = vjp_over(params, data, cot, ok)
         if mode == LossMode.SR_F_VECTOR:
-            # loss.py:107-108 keeps the complex vector; its imaginary part 2 * nanmean_b[dRe_b Im(diff_b) - dIm_b Re(diff_b)]
-            # is a second VJP with cotangent (2/B)(Im, -Re) diff_b
-            cot_i = torch.stack([cot[:, 1], -cot[:, 0]], dim=-1).contiguous()
-            grads_i = masked_vjp(params, data, cot_i, valid, lp)
-            return stats, torch.complex(grads, grads_i)
+            cot_i = torch.stack([cot[:, 1], -cot[:, 0]], dim=-1)
+            return stats, torch.complex(grads, vjp_over(params, data, cot_i, ok))
         return stats, grads
 
     return loss_and_grad

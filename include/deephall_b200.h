@@ -171,6 +171,24 @@ int dh_logpsi_vjp(dh_plan* plan, const float* params, const float* x, int64_t B,
                   const float* cot, float* grad_flat, float* out_logpsi, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* Energy statistics of a walker batch, replaces loss.py:30-38,66-92 (iqr_clip, nanmean, nanquantile on the rank's shard).
+ * dh_energy_stats: the rank-local means the reference `pmean`s, packed in out16 (device, 16 floats):
+ *   [0],[1] mean kinetic (re, im)   [2] mean potential   [3] mean L_z   [4] mean L_z^2   [5] mean L^2     (plain means, :68-71)
+ *   [6],[7] nanmean E_L (:73)       [8],[9] nanmean iqr_clip(E_L) (:74)                  [10] nanmean (Re E_L)^2 (:91)
+ *   [11] nanmean iqr_clip(L_z^2)    [12] nanmean iqr_clip(L_z)    [13] nanmean iqr_clip(L^2)              (:79,:80,:87)
+ *   The caller all-reduces (means) the vector over ranks -- ONE collective -- and hands it to
+ * dh_energy_diff: out_diff (B complex) = iqr_clip(E_L - clipped [+ lz_penalty ((L_z^2 - c) - 2 lz_center (L_z - c)) + l2_penalty
+ *   (L^2 - c)]) (:75-89); out_cot (B x 2) = (2 / n_ok) diff for walkers whose diff is a number and whose log psi (optional,
+ *   B complex, NULL = not checked) is finite, 0 otherwise: the cotangent of the gradient's VJP (:60-64,99-106);
+ *   out_ok (B floats, 1 / 0, may be NULL); out_counts (2 floats: walkers with a numeric diff, n_ok; may be NULL).
+ * Quantiles are rank-local (the reference's nanquantile runs on the local shard).  E_L / kinetic / logpsi are complex64
+ * (interleaved), the observables f32.  B <= 32768 walkers per rank (one shared-memory sort per array). */
+int dh_energy_stats(const float* el, const float* kinetic, const float* potential, const float* lz, const float* lz2,
+                    const float* l2, int64_t B, float* out16, void* stream);
+int dh_energy_diff(const float* el, const float* lz, const float* lz2, const float* l2, const float* logpsi, int64_t B,
+                   const float* reduced16, float lz_penalty, float lz_center, float l2_penalty, float* out_diff,
+                   float* out_cot, float* out_ok, float* out_counts, void* stream);
+
 /* Range guard of the fp16-piece contractions.  The dense and attention contractions split every fp32 operand into two
  * fp16 pieces; fp16 tops out at 65504 where the reference's fp32 does not.  A piece that saturates is never silent: the
  * kernel that saturates it ORs bit 0 into the plan's device status word.

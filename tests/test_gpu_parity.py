@@ -588,6 +588,47 @@ def test_facade_matches_reference_api(nat):
     assert abs(float(st["energy"].real) - 1.5) < 0.2  # train_test.py:46-48: energy hovers around N/2
 
 
+@pytest.mark.parametrize("B", [1, 2, 3, 37, 1000, 8192, 32768])
+def test_energy_statistics_kernels(nat, B):
+    """dh_energy_stats / dh_energy_diff against oracle/loss.py:36-50 (loss.py:30-38,66-92) on synthetic energies: ragged and
+    maximum batch sizes, NaN walkers (either part), heavy tails that the IQR clip cuts, penalties."""
+    g = torch.Generator().manual_seed(B)
+    el = torch.complex(20 + torch.randn(B, generator=g, dtype=torch.float64), 0.1 * torch.randn(B, generator=g, dtype=torch.float64))
+    obs = {"kinetic": torch.complex(6 + torch.randn(B, generator=g, dtype=torch.float64), 0.1 * torch.randn(B, generator=g, dtype=torch.float64)),
+           "potential": 14 + torch.randn(B, generator=g, dtype=torch.float64),
+           "angular_momentum_z": torch.randn(B, generator=g, dtype=torch.float64),
+           "angular_momentum_z_square": 2 + torch.randn(B, generator=g, dtype=torch.float64),
+           "angular_momentum_square": 5 + torch.randn(B, generator=g, dtype=torch.float64)}
+    if B >= 37:
+        el[3] = complex(1e9, -1e7)          # outliers far outside q3 + 100 iqr
+        el[11] = complex(-1e8, 5e6)
+        el[5] = complex(float("nan"), 0.3)   # NaN in one part only
+        el[17] = complex(19.0, float("nan"))
+        obs["angular_momentum_square"][7] = 1e7
+    to32 = lambda t: (t.to(torch.complex64) if t.is_complex() else t.float()).to(DEV)  # noqa: E731
+    el32, obs32 = to32(el), {k: to32(v) for k, v in obs.items()}
+    el_o, obs_o = el32.cpu().to(torch.complex128), {k: (v.cpu().to(torch.complex128) if v.is_complex() else v.cpu().double()) for k, v in obs32.items()}
+    for lz_pen, lz_c, l2_pen in ((0.0, 0.0, 0.0), (0.3, 1.5, 0.2)):
+        o_stats, o_diff = OLoss.loss_stats(el_o, obs_o, lz_penalty=lz_pen, lz_center=lz_c, l2_penalty=l2_pen)
+        vec = nat.energy_stats(el32, obs32)
+        diff, cot, ok, counts = nat.energy_diff(el32, obs32, vec, lz_pen, lz_c, l2_pen)
+        v = vec.cpu().double()
+        close = lambda a, b, tol=2e-6: abs(a - b) <= tol * max(1.0, abs(b)) or (math.isnan(a) and math.isnan(b))  # noqa: E731
+        assert close(v[6].item(), o_stats["energy"].real.item()) and close(v[7].item(), o_stats["energy"].imag.item())
+        assert close((v[10] - v[6] ** 2).item(), o_stats["variance"].item(), 1e-4)
+        for i, k in ((2, "potential"), (3, "angular_momentum_z"), (4, "angular_momentum_z_square"), (5, "angular_momentum_square")):
+            assert close(v[i].item(), o_stats[k].item(), 1e-5), k
+        assert close(v[0].item(), o_stats["kinetic"].real.item()) and close(v[1].item(), o_stats["kinetic"].imag.item())
+        d, od = diff.cpu().to(torch.complex128), o_diff
+        bad = torch.isnan(od.real) | torch.isnan(od.imag)
+        assert torch.equal(torch.isnan(d.real) | torch.isnan(d.imag), bad)
+        assert ((d - od)[~bad].abs() <= 2e-5 * od[~bad].abs().clamp(min=1.0)).all()
+        assert int(counts[0]) == int((~bad).sum()) and torch.equal(ok.cpu() > 0, ~bad)
+        ref_cot = torch.where(bad[:, None], torch.zeros(B, 2, dtype=torch.float64), torch.view_as_real(od)) * (2.0 / max(int((~bad).sum()), 1))
+        # (diff = E_L - mean: fp32 rounding of E_L ~ 20 is an ABSOLUTE error of ~2e-6 on diff; cot = diff * 2 / n)
+        assert (cot.cpu().double() - ref_cot).abs().max() <= 1e-5 * (2.0 / max(int((~bad).sum()), 1)) * 20 + 1e-12
+
+
 def test_loss_penalties_match_the_oracle(nat):
     """lz / l2 penalties (loss.py:76-88): `diff` (ENERGY_DIFF mode) and the gradient built from it against
     oracle/loss.py:36-50 fed with the same per-walker energies and observables."""
