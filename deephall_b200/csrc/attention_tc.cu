@@ -147,6 +147,63 @@ struct AtStager {
   }
 };
 
+// Softmax jets (log-sum-exp Hessian = diag(p) - p p^T) on the score jets in shared memory: on return sj holds
+// l^(r) = p^(r) / p for r > 0 and p0 the probabilities; qq, dd are scratch.  Ends with a barrier.
+template <int NT>
+__device__ __forceinline__ void softmax_jets(float* sj, float* p0, float* qq, float* dd) {
+  using G = AtGeom<NT>;
+  constexpr int N = G::N, NP = AT_NP;
+  const int tid = threadIdx.x;
+  Rows rw(N, true);
+#define SJ(i, j, r) ((j) * G::SJ_J + (r) * NP + (i))
+  for (int i = tid; i < N; i += AT_THREADS) {
+    float mx = -INFINITY;
+    for (int j = 0; j < N; ++j) mx = fmaxf(mx, sj[SJ(i, j, 0)]);
+    float Z = 0.f;
+    for (int j = 0; j < N; ++j) { const float e = expf(sj[SJ(i, j, 0)] - mx); p0[j * NP + i] = e; Z += e; }
+    const float iz = 1.f / Z;
+    for (int j = 0; j < N; ++j) p0[j * NP + i] *= iz;
+  }
+  if constexpr (NP > N) {  // padded query slots
+    for (int t = tid; t < N * (NP - N); t += AT_THREADS) p0[(t / (NP - N)) * NP + N + t % (NP - N)] = 0.f;
+  }
+  __syncthreads();
+  constexpr int nfirst = 2 * N + 3;
+  for (int t = tid; t < N * nfirst; t += AT_THREADS) {  // first-order rows: l = s - lse
+    const int i = t % N, q = t / N;
+    const int r = q < 2 * N ? rw.J(q) : rw.D(q - 2 * N);
+    float lse = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) lse = fmaf(p0[j * NP + i], sj[SJ(i, j, r)], lse);
+#pragma unroll
+    for (int j = 0; j < N; ++j) sj[SJ(i, j, r)] -= lse;
+  }
+  __syncthreads();
+  for (int t = tid; t < N * N; t += AT_THREADS) {
+    const int i = t % N, j = t / N;
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * N; ++k) { const float l = sj[SJ(i, j, 1 + k)]; s2 = fmaf(l, l, s2); }
+    qq[j * NP + i] = s2;
+    for (int a3 = 0; a3 < 3; ++a3) { const float l = sj[SJ(i, j, rw.D(a3))]; dd[(a3 * N + j) * NP + i] = l * l; }
+  }
+  __syncthreads();
+  for (int t = tid; t < N * 4; t += AT_THREADS) {  // second-order rows
+    const int i = t % N, w = t / N;
+    const int r = w == 0 ? rw.S() : rw.T(w - 1);
+    const float* extra = w == 0 ? qq : dd + (w - 1) * N * NP;
+    float lse = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float v = sj[SJ(i, j, r)] + extra[j * NP + i];
+      sj[SJ(i, j, r)] = v;
+      lse = fmaf(p0[j * NP + i], v, lse);
+    }
+    for (int j = 0; j < N; ++j) sj[SJ(i, j, r)] -= lse;
+  }
+  __syncthreads();  // sj holds l^(r) = p^(r) / p for r > 0; the p jets are formed in the fragments: p^(r) = p l^(r)
+#undef SJ
+}
+
 template <int NT, bool L0>
 __global__ void __launch_bounds__(AT_THREADS, NT <= 12 ? 2 : 1)
 attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, unsigned* __restrict__ rflag) {
@@ -333,51 +390,7 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
   }
   __syncthreads();
   // ------------------------------------------------------------------ phase 2: softmax jets (as attention_jets.cu)
-  for (int i = tid; i < N; i += AT_THREADS) {
-    float mx = -INFINITY;
-    for (int j = 0; j < N; ++j) mx = fmaxf(mx, sj[SJ(i, j, 0)]);
-    float Z = 0.f;
-    for (int j = 0; j < N; ++j) { const float e = expf(sj[SJ(i, j, 0)] - mx); p0[j * NP + i] = e; Z += e; }
-    const float iz = 1.f / Z;
-    for (int j = 0; j < N; ++j) p0[j * NP + i] *= iz;
-  }
-  if constexpr (NP > N) {  // padded query slots
-    for (int t = tid; t < N * (NP - N); t += AT_THREADS) p0[(t / (NP - N)) * NP + N + t % (NP - N)] = 0.f;
-  }
-  __syncthreads();
-  constexpr int nfirst = 2 * N + 3;
-  for (int t = tid; t < N * nfirst; t += AT_THREADS) {  // first-order rows: l = s - lse
-    const int i = t % N, q = t / N;
-    const int r = q < 2 * N ? rw.J(q) : rw.D(q - 2 * N);
-    float lse = 0.f;
-#pragma unroll
-    for (int j = 0; j < N; ++j) lse = fmaf(p0[j * NP + i], sj[SJ(i, j, r)], lse);
-#pragma unroll
-    for (int j = 0; j < N; ++j) sj[SJ(i, j, r)] -= lse;
-  }
-  __syncthreads();
-  for (int t = tid; t < N * N; t += AT_THREADS) {
-    const int i = t % N, j = t / N;
-    float s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 2 * N; ++k) { const float l = sj[SJ(i, j, 1 + k)]; s2 = fmaf(l, l, s2); }
-    qq[j * NP + i] = s2;
-    for (int a3 = 0; a3 < 3; ++a3) { const float l = sj[SJ(i, j, rw.D(a3))]; dd[(a3 * N + j) * NP + i] = l * l; }
-  }
-  __syncthreads();
-  for (int t = tid; t < N * 4; t += AT_THREADS) {  // second-order rows
-    const int i = t % N, w = t / N;
-    const int r = w == 0 ? rw.S() : rw.T(w - 1);
-    const float* extra = w == 0 ? qq : dd + (w - 1) * N * NP;
-    float lse = 0.f;
-    for (int j = 0; j < N; ++j) {
-      const float v = sj[SJ(i, j, r)] + extra[j * NP + i];
-      sj[SJ(i, j, r)] = v;
-      lse = fmaf(p0[j * NP + i], v, lse);
-    }
-    for (int j = 0; j < N; ++j) sj[SJ(i, j, r)] -= lse;
-  }
-  __syncthreads();  // sj holds l^(r) = p^(r) / p for r > 0; the p jets are formed in the fragments: p^(r) = p l^(r)
+  softmax_jets<NT>(sj, p0, qq, dd);
   // ------------------------------------------------------------------ phase 3: o = P V jets on the tensor cores
   {
     const uint32_t vh_s = pl_s, vl_s = pl_s + G::PL;
@@ -530,6 +543,444 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
 #undef SJ
 }
 
+// =============================================================================================================
+// FIRST-LAYER kernel.  q, k, v of the first layer depend on their own electron only, so their jets have just 10
+// non-zero rows per electron (value | own flows (2) | S | D_a | T_a) and arrive compressed [B N 10][3 D].  Instead of
+// expanding them to the full row set (two thirds of the products would multiply zeros) the contractions run on the
+// compressed rows:
+//   scores   U_c[(i,c), j] = q_i^(c) . k_j,  W_c[(j,c), i] = k_j^(c) . q_i      [10 N x 64] x [64 x N]   (3.2x fewer rows)
+//            s^(J(2e+t))_ij = [i = e] U_c[(e,1+t), j] + [j = e] W_c[(e,1+t), i];   S, D_a, T_a rows as in the full form;
+//            cross terms: own flows only touch the diagonal (S_ii += 2 sum_t q_i^(1+t) . k_i^(1+t)), D_a as before
+//   P.V      o^(r) = P^(r) V^(0) on the tensor cores for every row; P^(0) V^(r) is a rank-one update for the 2N own-flow
+//            rows (v^(J(2e+t)) lives on electron e only) and a tensor-core product for S, D_a, T_a; the S-row cross
+//            term is the sum of 2N rank-one updates.
+// 1,536 HMMA per block instead of 4,776, a third of the staging conversions.
+// =============================================================================================================
+template <int NT>
+struct AtGeomC {
+  static constexpr int N = NT, R = 2 * NT + 8, RC = AT_RC, NRC = N * RC, NR = N * R;
+  static constexpr int MT = (NRC + 15) / 16, TPW = (MT + AT_WARPS - 1) / AT_WARPS;
+  static constexpr int RPW = (R + AT_WARPS - 1) / AT_WARPS;
+  static constexpr int EB = RC * 32 + 16;                  // bytes per electron of a 16-column fp16 plane
+  static constexpr int PL = N * EB;
+  static constexpr int SCRATCH = 4 * (5 * N * AT_NP + 11 * 256);
+  static constexpr int PLANES = 4 * PL > SCRATCH ? 4 * PL : SCRATCH;
+  static constexpr int RAW = NRC * 64;
+  static constexpr int OFF_RAW = PLANES, OFF_SJ = OFF_RAW + 2 * RAW, OFF_P0 = OFF_SJ + 4 * AtGeom<NT>::SJ_FLOATS;
+  static constexpr int OFF_RED = OFF_P0 + 4 * N * AT_NP;
+  static constexpr size_t SMEM = OFF_RED + 4 * AT_WARPS * 256;
+  static constexpr int SLOTS = RC * 4, EPP = AT_THREADS / SLOTS;
+};
+template <int NT>
+__device__ __forceinline__ uint32_t plane_off_c(int e, int c, int chunk) {
+  return (uint32_t)(e * AtGeomC<NT>::EB + c * 32 + ((chunk ^ ((c >> 2) & 1)) << 4));
+}
+template <int NT>
+struct AtStagerC {
+  using G = AtGeomC<NT>;
+  int c, q4, egrp;
+  bool active;
+  float amax;
+  uint32_t raw_off, pl_off;
+  __device__ __forceinline__ void init() {
+    const int slot = threadIdx.x % G::SLOTS;
+    egrp = threadIdx.x / G::SLOTS;
+    active = egrp < G::EPP;
+    amax = 0.f;
+    c = slot >> 2;
+    q4 = slot & 3;
+    raw_off = (uint32_t)(((egrp * G::RC + c) * 4 + q4) * 16);
+    pl_off = plane_off_c<NT>(egrp, c, q4 >> 1) + (uint32_t)((q4 & 1) << 3);
+  }
+  __device__ __forceinline__ void issue(uint32_t raw_s, const float* __restrict__ src, int64_t ld) const {
+    if (active) {
+#pragma unroll
+      for (int e = egrp, k = 0; e < G::N; e += G::EPP, ++k) {
+        const float* gp = src + (int64_t)(e * G::RC + c) * ld + 4 * q4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + raw_off + (uint32_t)(k * G::EPP * G::RC * 64)), "l"(gp) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  __device__ __forceinline__ void convert(const uint8_t* raw, uint8_t* hi, uint8_t* lo) {
+    if (active) {
+#pragma unroll
+      for (int e = egrp, k = 0; e < G::N; e += G::EPP, ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(raw + raw_off + k * G::EPP * G::RC * 64);
+        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        uint2 h, l;
+        split_f16x2(v.x, v.y, h.x, l.x);
+        split_f16x2(v.z, v.w, h.y, l.y);
+        const uint32_t off = pl_off + (uint32_t)(k * G::EPP * G::EB);
+        *reinterpret_cast<uint2*>(hi + off) = h;
+        *reinterpret_cast<uint2*>(lo + off) = l;
+      }
+    }
+  }
+};
+
+template <int NT>
+__global__ void __launch_bounds__(AT_THREADS, NT <= 12 ? 2 : 1)
+attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, unsigned* __restrict__ rflag) {
+  using G = AtGeomC<NT>;
+  using GF = AtGeom<NT>;
+  constexpr int N = G::N, R = G::R, RC = G::RC, NRC = G::NRC, NP = AT_NP;
+  extern __shared__ __align__(128) uint8_t smem_at[];
+  uint8_t* planes = smem_at;
+  uint8_t* raw = smem_at + G::OFF_RAW;
+  float* sj = reinterpret_cast<float*>(smem_at + G::OFF_SJ);
+  float* p0 = reinterpret_cast<float*>(smem_at + G::OFF_P0);
+  float* red = reinterpret_cast<float*>(smem_at + G::OFF_RED);
+  float* qq = reinterpret_cast<float*>(planes);
+  float* dd = qq + N * NP;
+  float* xw = dd + 3 * N * NP;      // [warp][16 x 16]: own-flow cross products (warps 0, 1)
+  float* dw = xw + AT_WARPS * 256;  // [3][16 x 16]
+#define SJ(i, j, r) ((j) * GF::SJ_J + (r) * NP + (i))
+  const int D = dm.D;
+  const int hh = blockIdx.x;
+  const int64_t b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int64_t ld = 3 * (int64_t)D;
+  const float* qbase = qkv + b * (int64_t)NRC * ld + hh * AT_HD;
+  const float* kbase = qbase + D;
+  const float* vbase = qbase + 2 * D;
+  const float scl = rsqrtf((float)AT_HD);
+  Rows rw(N, true);
+  const int rS = rw.S(), rD0 = rw.D(0), rT0 = rw.T(0);
+  // full jet row of compressed row c of electron e
+  auto full_row = [&](int e, int c) { return c == 0 ? 0 : (c <= 2 ? 2 * e + c : (c == 3 ? rS : (c <= 6 ? rD0 + (c - 4) : rT0 + (c - 7)))); };
+  AtStagerC<NT> stg;
+  stg.init();
+  const uint32_t raw_s = sm_u32(raw), pl_s = sm_u32(planes);
+  for (int t = tid; t < GF::SJ_FLOATS; t += AT_THREADS) sj[t] = 0.f;
+
+  // ------------------------------------------------------------------ phase 1: score jets of the compressed rows
+  {
+    const uint32_t qh_s = pl_s, ql_s = pl_s + G::PL, kh_s = pl_s + 2 * G::PL, kl_s = pl_s + 3 * G::PL;
+    float g1[G::TPW][2][4], g2[G::TPW][2][4], xa[2][4], da[2][4];
+#pragma unroll
+    for (int ts = 0; ts < G::TPW; ++ts)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { g1[ts][n][c] = 0.f; g2[ts][n][c] = 0.f; }
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { xa[n][c] = 0.f; da[n][c] = 0.f; }
+    const int a_r = (lane & 7) + ((lane >> 3) & 1) * 8, a_c = lane >> 4;
+    const int b_n = (lane & 7) + (lane >> 4) * 8, b_c = (lane >> 3) & 1;
+    const int b_e = b_n < N ? b_n : N - 1, a_e = a_r < N ? a_r : N - 1;
+    const uint32_t b0_off = plane_off_c<NT>(b_e, 0, b_c);
+    uint32_t t_off[G::TPW];
+#pragma unroll
+    for (int ts = 0; ts < G::TPW; ++ts) {
+      int arow = (warp + AT_WARPS * ts) * 16 + a_r;
+      arow = arow < NRC ? arow : NRC - 1;
+      t_off[ts] = plane_off_c<NT>(arow / RC, arow % RC, a_c);
+    }
+    // cross flows: warp 0, 1 -> own flows t = 0, 1 (compressed rows 1, 2; only the diagonal is used);
+    //              warp 2 + a -> D_a (compressed row 4 + a)
+    const int xc = warp < 2 ? 1 + warp : 4 + (warp - 2);
+    const uint32_t xa_off = plane_off_c<NT>(a_e, xc, a_c), xb_off = plane_off_c<NT>(b_e, xc, b_c);
+    stg.issue(raw_s, qbase, ld);
+    stg.issue(raw_s + G::RAW, kbase, ld);
+#pragma unroll 1
+    for (int st = 0; st < AT_HD / 16; ++st) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      stg.convert(raw, planes, planes + G::PL);
+      stg.convert(raw + G::RAW, planes + 2 * G::PL, planes + 3 * G::PL);
+      __syncthreads();
+      if (st + 1 < AT_HD / 16) {
+        stg.issue(raw_s, qbase + (st + 1) * 16, ld);
+        stg.issue(raw_s + G::RAW, kbase + (st + 1) * 16, ld);
+      }
+      uint32_t k0h[4], k0l[4], q0h[4], q0l[4];
+      ldsm_x4(kh_s + b0_off, k0h); ldsm_x4(kl_s + b0_off, k0l);
+      ldsm_x4(qh_s + b0_off, q0h); ldsm_x4(ql_s + b0_off, q0l);
+#pragma unroll
+      for (int ts = 0; ts < G::TPW; ++ts) {
+        if (warp + AT_WARPS * ts < G::MT) {
+          uint32_t ah[4], al[4], ch[4], cl[4];
+          ldsm_x4(qh_s + t_off[ts], ah); ldsm_x4(ql_s + t_off[ts], al);
+          ldsm_x4(kh_s + t_off[ts], ch); ldsm_x4(kl_s + t_off[ts], cl);
+          mma16816(g1[ts][0], al, k0h[0], k0h[1]); mma16816(g1[ts][1], al, k0h[2], k0h[3]);
+          mma16816(g2[ts][0], cl, q0h[0], q0h[1]); mma16816(g2[ts][1], cl, q0h[2], q0h[3]);
+          mma16816(g1[ts][0], ah, k0l[0], k0l[1]); mma16816(g1[ts][1], ah, k0l[2], k0l[3]);
+          mma16816(g2[ts][0], ch, q0l[0], q0l[1]); mma16816(g2[ts][1], ch, q0l[2], q0l[3]);
+          mma16816(g1[ts][0], ah, k0h[0], k0h[1]); mma16816(g1[ts][1], ah, k0h[2], k0h[3]);
+          mma16816(g2[ts][0], ch, q0h[0], q0h[1]); mma16816(g2[ts][1], ch, q0h[2], q0h[3]);
+        }
+      }
+      if (warp < 5) {
+        uint32_t ah[4], al[4], bh[4], bl[4];
+        ldsm_x4(qh_s + xa_off, ah); ldsm_x4(ql_s + xa_off, al);
+        ldsm_x4(kh_s + xb_off, bh); ldsm_x4(kl_s + xb_off, bl);
+        if (warp < 2) {
+          mma16816(xa[0], al, bh[0], bh[1]); mma16816(xa[1], al, bh[2], bh[3]);
+          mma16816(xa[0], ah, bl[0], bl[1]); mma16816(xa[1], ah, bl[2], bl[3]);
+          mma16816(xa[0], ah, bh[0], bh[1]); mma16816(xa[1], ah, bh[2], bh[3]);
+        } else {
+          mma16816(da[0], al, bh[0], bh[1]); mma16816(da[1], al, bh[2], bh[3]);
+          mma16816(da[0], ah, bl[0], bl[1]); mma16816(da[1], ah, bl[2], bl[3]);
+          mma16816(da[0], ah, bh[0], bh[1]); mma16816(da[1], ah, bh[2], bh[3]);
+        }
+      }
+    }
+    __syncthreads();  // every warp is done with the planes (xw, dw live there); sj was zeroed at the start
+    // G1: q_e^(c) . k_x -> s^(r)_{e x}
+#pragma unroll
+    for (int ts = 0; ts < G::TPW; ++ts) {
+      const int mt = warp + AT_WARPS * ts;
+      if (mt < G::MT) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = mt * 16 + g + 8 * h;
+          if (row < NRC) {
+            const int e = row / RC, r = full_row(e, row - e * RC);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const int x = nt * 8 + 2 * t4 + c;
+                if (x < N) sj[SJ(e, x, r)] = g1[ts][nt][2 * h + c] * scl;
+              }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int idx = (g + 8 * (c >> 1)) * 16 + nt * 8 + 2 * t4 + (c & 1);  // (i, j)
+        xw[warp * 256 + idx] = xa[nt][c];
+        if (warp >= 2 && warp < 5) dw[(warp - 2) * 256 + idx] = da[nt][c];
+      }
+    stg.issue(raw_s, vbase, ld);
+    __syncthreads();
+    // G2: k_e^(c) . q_x -> s^(r)_{x e}   (r > 0; the entry (e, e, r) already holds its G1 term)
+#pragma unroll
+    for (int ts = 0; ts < G::TPW; ++ts) {
+      const int mt = warp + AT_WARPS * ts;
+      if (mt < G::MT) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = mt * 16 + g + 8 * h;
+          if (row < NRC) {
+            const int e = row / RC, c0 = row - e * RC;
+            if (c0 != 0) {
+              float* dst = sj + SJ(0, e, full_row(e, c0));
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                  const int x = nt * 8 + 2 * t4 + c;
+                  if (x < N) dst[x] += g2[ts][nt][2 * h + c] * scl;
+                }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // second-order rows pick up the cross products: S_ii += 2 sum_t q_i^(t) . k_i^(t) ; T_a += 2 qDa . kDa
+  for (int t = tid; t < N * N * 4; t += AT_THREADS) {
+    const int w = t & 3, ij = t >> 2;
+    const int i = ij % N, j = ij / N;
+    if (w == 0) {
+      if (i == j) sj[SJ(i, i, rS)] += 2.f * scl * (xw[i * 16 + i] + xw[256 + i * 16 + i]);
+    } else {
+      sj[SJ(i, j, rw.T(w - 1))] += 2.f * scl * dw[(w - 1) * 256 + i * 16 + j];
+    }
+  }
+  __syncthreads();
+  // ------------------------------------------------------------------ phase 2: softmax jets
+  softmax_jets<NT>(sj, p0, qq, dd);
+  // ------------------------------------------------------------------ phase 3: o = P V jets
+  {
+    const uint32_t vh_s = pl_s, vl_s = pl_s + G::PL;
+    const uint8_t* vh = planes;
+    const uint8_t* vl = planes + G::PL;
+    float* obase = o + b * (int64_t)G::NR * D + hh * AT_HD + 2 * t4;
+    const int ob0 = g * R * D, ob1 = (g + 8) * R * D;
+    float pw[2][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 2 * t4 + (jj & 1) + 8 * (jj >> 1);
+      pw[0][jj] = j < N ? p0[j * NP + g] : 0.f;
+      pw[1][jj] = j < N ? p0[j * NP + g + 8] : 0.f;
+    }
+    auto pfrag = [&](int r, uint32_t (&ph)[4], uint32_t (&pl)[4]) {
+#pragma unroll
+      for (int jh = 0; jh < 2; ++jh) {
+        const int j0 = 2 * t4 + 8 * jh;
+        float x0 = pw[0][2 * jh], x1 = pw[0][2 * jh + 1], y0 = pw[1][2 * jh], y1 = pw[1][2 * jh + 1];
+        if (r != 0) {
+          if (j0 < N) { x0 *= sj[SJ(g, j0, r)]; y0 *= sj[SJ(g + 8, j0, r)]; }
+          if (j0 + 1 < N) { x1 *= sj[SJ(g, j0 + 1, r)]; y1 *= sj[SJ(g + 8, j0 + 1, r)]; }
+        }
+        stg.amax = fmaxf(stg.amax, fmaxf(fmaxf(fabsf(x0), fabsf(x1)), fmaxf(fabsf(y0), fabsf(y1))));
+        split_f16x2(x0, x1, ph[2 * jh], pl[2 * jh]);
+        split_f16x2(y0, y1, ph[2 * jh + 1], pl[2 * jh + 1]);
+      }
+    };
+    uint32_t p0h[4], p0l[4], prh[G::RPW][4], prl[G::RPW][4], pdh[4], pdl[4];
+    pfrag(0, p0h, p0l);
+#pragma unroll
+    for (int k = 0; k < G::RPW; ++k) {
+      const int r = warp + AT_WARPS * k;
+      if (r < R) pfrag(r, prh[k], prl[k]);
+      if (r < R && r >= rT0) pfrag(r - 3, pdh, pdl);
+    }
+    const int v_j = (lane & 7) + ((lane >> 3) & 1) * 8, v_c = lane >> 4;
+    const int v_e = v_j < N ? v_j : N - 1;
+    auto vfrag = [&](int c, uint32_t (&fh)[4], uint32_t (&fl)[4]) {  // compressed row c of every electron
+      const uint32_t off = plane_off_c<NT>(v_e, c, v_c);
+      ldsm_x4_t(vh_s + off, fh);
+      ldsm_x4_t(vl_s + off, fl);
+    };
+    float accS[2][4];
+    auto finish_s = [&](int qt) {
+      if (warp == rS % AT_WARPS) {
+#pragma unroll
+        for (int u = 0; u < AT_WARPS; ++u) {
+          const float4 x = *reinterpret_cast<const float4*>(red + (u * 32 + lane) * 8);
+          const float4 y = *reinterpret_cast<const float4*>(red + (u * 32 + lane) * 8 + 4);
+          accS[0][0] = fmaf(2.f, x.x, accS[0][0]); accS[0][1] = fmaf(2.f, x.y, accS[0][1]);
+          accS[0][2] = fmaf(2.f, x.z, accS[0][2]); accS[0][3] = fmaf(2.f, x.w, accS[0][3]);
+          accS[1][0] = fmaf(2.f, y.x, accS[1][0]); accS[1][1] = fmaf(2.f, y.y, accS[1][1]);
+          accS[1][2] = fmaf(2.f, y.z, accS[1][2]); accS[1][3] = fmaf(2.f, y.w, accS[1][3]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (g + 8 * h < N) {
+            float* dst = obase + ((h ? ob1 : ob0) + rS * D + qt * 16);
+            *reinterpret_cast<float2*>(dst) = make_float2(accS[0][2 * h], accS[0][2 * h + 1]);
+            *reinterpret_cast<float2*>(dst + 8) = make_float2(accS[1][2 * h], accS[1][2 * h + 1]);
+          }
+        }
+      }
+    };
+#pragma unroll 1
+    for (int qt = 0; qt < AT_HD / 16; ++qt) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (qt > 0) finish_s(qt - 1);
+      stg.convert(raw, planes, planes + G::PL);
+      __syncthreads();
+      if (qt + 1 < AT_HD / 16) stg.issue(raw_s, vbase + (qt + 1) * 16, ld);
+      uint32_t v0h[4], v0l[4];
+      vfrag(0, v0h, v0l);
+      float sx[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { sx[n][c] = 0.f; accS[n][c] = 0.f; }
+#pragma unroll
+      for (int k = 0; k < G::RPW; ++k) {
+        const int r = warp + AT_WARPS * k;
+        if (r < R) {
+          float acc[2][4];
+#pragma unroll
+          for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[n][c] = 0.f;
+          if (r == 0) {
+            mma16816(acc[0], p0l, v0h[0], v0h[1]); mma16816(acc[1], p0l, v0h[2], v0h[3]);
+            mma16816(acc[0], p0h, v0l[0], v0l[1]); mma16816(acc[1], p0h, v0l[2], v0l[3]);
+            mma16816(acc[0], p0h, v0h[0], v0h[1]); mma16816(acc[1], p0h, v0h[2], v0h[3]);
+          } else if (r <= 2 * N) {
+            // own-flow row of electron e: P^(r) V^(0) on the tensor cores, P^(0) V^(r) and the S-row cross term as rank-one
+            // updates with v_e^(1+t) (this lane's four columns, hi + lo pieces back to fp32)
+            mma16816(acc[0], prl[k], v0h[0], v0h[1]); mma16816(acc[1], prl[k], v0h[2], v0h[3]);
+            mma16816(acc[0], prh[k], v0l[0], v0l[1]); mma16816(acc[1], prh[k], v0l[2], v0l[3]);
+            mma16816(acc[0], prh[k], v0h[0], v0h[1]); mma16816(acc[1], prh[k], v0h[2], v0h[3]);
+            const int e = (r - 1) >> 1, c = 1 + ((r - 1) & 1);
+            float vv[2][2];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+              const uint32_t off = plane_off_c<NT>(e, c, nt) + (uint32_t)(4 * t4);  // columns 8 nt + 2 t4, + 1
+              const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(vh + off));
+              const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(vl + off));
+              vv[nt][0] = fh.x + fl.x; vv[nt][1] = fh.y + fl.y;
+            }
+            const float pa = p0[e * NP + g], pb = p0[e * NP + g + 8];
+            const float qa = pa * sj[SJ(g, e, r)], qb = pb * sj[SJ(g + 8, e, r)];  // P^(r)[i, e]
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+              for (int c2 = 0; c2 < 2; ++c2) {
+                acc[nt][c2] = fmaf(pa, vv[nt][c2], acc[nt][c2]);
+                acc[nt][2 + c2] = fmaf(pb, vv[nt][c2], acc[nt][2 + c2]);
+                sx[nt][c2] = fmaf(qa, vv[nt][c2], sx[nt][c2]);
+                sx[nt][2 + c2] = fmaf(qb, vv[nt][c2], sx[nt][2 + c2]);
+              }
+          } else {
+            uint32_t fh[4], fl[4];
+            const int c = r == rS ? 3 : (r < rT0 ? 4 + (r - rD0) : 7 + (r - rT0));
+            if (r >= rT0) {  // 2 P^(D_a) V^(D_a) first, doubled once in the accumulators
+              vfrag(c - 3, fh, fl);
+              mma16816(acc[0], pdl, fh[0], fh[1]); mma16816(acc[1], pdl, fh[2], fh[3]);
+              mma16816(acc[0], pdh, fl[0], fl[1]); mma16816(acc[1], pdh, fl[2], fl[3]);
+              mma16816(acc[0], pdh, fh[0], fh[1]); mma16816(acc[1], pdh, fh[2], fh[3]);
+#pragma unroll
+              for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int c2 = 0; c2 < 4; ++c2) acc[n][c2] *= 2.f;
+            }
+            vfrag(c, fh, fl);
+            mma16816(acc[0], prl[k], v0h[0], v0h[1]); mma16816(acc[1], prl[k], v0h[2], v0h[3]);
+            mma16816(acc[0], p0l, fh[0], fh[1]); mma16816(acc[1], p0l, fh[2], fh[3]);
+            mma16816(acc[0], prh[k], v0l[0], v0l[1]); mma16816(acc[1], prh[k], v0l[2], v0l[3]);
+            mma16816(acc[0], p0h, fl[0], fl[1]); mma16816(acc[1], p0h, fl[2], fl[3]);
+            mma16816(acc[0], prh[k], v0h[0], v0h[1]); mma16816(acc[1], prh[k], v0h[2], v0h[3]);
+            mma16816(acc[0], p0h, fh[0], fh[1]); mma16816(acc[1], p0h, fh[2], fh[3]);
+          }
+          if (r == rS) {
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+              for (int c2 = 0; c2 < 4; ++c2) accS[n][c2] = acc[n][c2];
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (g + 8 * h < N) {
+                float* dst = obase + ((h ? ob1 : ob0) + r * D + qt * 16);
+                *reinterpret_cast<float2*>(dst) = make_float2(acc[0][2 * h], acc[0][2 * h + 1]);
+                *reinterpret_cast<float2*>(dst + 8) = make_float2(acc[1][2 * h], acc[1][2 * h + 1]);
+              }
+            }
+          }
+        }
+      }
+      *reinterpret_cast<float4*>(red + (warp * 32 + lane) * 8) = make_float4(sx[0][0], sx[0][1], sx[0][2], sx[0][3]);
+      *reinterpret_cast<float4*>(red + (warp * 32 + lane) * 8 + 4) = make_float4(sx[1][0], sx[1][1], sx[1][2], sx[1][3]);
+    }
+    __syncthreads();
+    finish_s(AT_HD / 16 - 1);
+  }
+  if (rflag != nullptr && !(stg.amax <= 65504.f)) atomicOr(rflag, 1u);
+#undef SJ
+}
+
+template <int NT>
+int launch_at_l0(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
+  using G = AtGeomC<NT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_jets_tc_l0_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)d.H, (unsigned)B);
+  attention_jets_tc_l0_kernel<NT><<<grid, AT_THREADS, G::SMEM, s>>>(qkv, o, d, range_flag_get());
+  return (int)cudaGetLastError();
+}
+
 template <int NT, bool L0>
 int launch_at(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
   using G = AtGeom<NT>;
@@ -553,7 +1004,7 @@ bool attention_jets_tc_ok(NetDims d) {
 
 int attention_jets_tc(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s) {
   if (!attention_jets_tc_ok(d)) return -2;
-#define DH_AT(NT) (layer0 ? launch_at<NT, true>(qkv, o, B, d, s) : launch_at<NT, false>(qkv, o, B, d, s))
+#define DH_AT(NT) (layer0 ? launch_at_l0<NT>(qkv, o, B, d, s) : launch_at<NT, false>(qkv, o, B, d, s))
   switch (d.N) {
     case 3: return DH_AT(3);
     case 6: return DH_AT(6);
