@@ -225,6 +225,18 @@ def test_chunking_is_invisible(nat):
     ga, gb = p_big.logpsi_vjp(flat, x, cot), p_small.logpsi_vjp(flat, x, cot)
     assert (ga - gb).norm() / ga.norm() < 1e-5  # split-K atomics reorder the sum
     assert p_big.local_energy(flat, x[:0].contiguous())["energy"].numel() == 0  # empty batch
+    # c3 (the fused orbital epilogue and the tensor-core attention forms): ragged chunks, a single walker and a single
+    # chunk give bit-identical per-walker results
+    cfg = OP.NetCfg(**CONFIGS["c3"])
+    flat = OP.flatten_params(OP.init_params(cfg, 0, torch.float64, 0.1)).float().to(DEV)
+    p_big, p_small = make_plan(nat, cfg), make_plan(nat, cfg, chunk_walkers=5)
+    x = p_big.init_walkers(13, seed=4)
+    a, b, one = p_big.local_energy(flat, x), p_small.local_energy(flat, x), p_big.local_energy(flat, x[7:8].contiguous())
+    for k in a:
+        va = torch.view_as_real(a[k]) if a[k].is_complex() else a[k]
+        vb = torch.view_as_real(b[k]) if b[k].is_complex() else b[k]
+        v1 = torch.view_as_real(one[k]) if one[k].is_complex() else one[k]
+        assert torch.equal(va, vb) and torch.equal(va[7:8], v1), k
 
 
 def test_potential(nat):
