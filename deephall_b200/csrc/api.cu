@@ -260,6 +260,7 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     p->a_planes = 0;
     // envelope contraction as the epilogue of the orbital projection (gemm_tc.cu, ORB): 32 jet rows per electron (N = 12),
     // one determinant, one spin block, full orbitals, at most 48 orbitals
+    p->ln_value_fuse = !(dbg_env("DH_LNV_FUSE") && atoi(dbg_env("DH_LNV_FUSE")) == 0) ? 1 : 0;
     p->orb_fuse = (p->gemm_impl == 1 && p->tc_f16 && D == 256 && N == 12 && K == 1 && p->nsb == 1 && !p->sparse && L <= 48 &&
                    !(dbg_env("DH_ORB_FUSE") && atoi(dbg_env("DH_ORB_FUSE")) == 0)) ? 1 : 0;
     size_t off = 0;
@@ -339,7 +340,10 @@ extern "C" int dh_plan_status_copy(dh_plan* p, uint32_t* dst_device, void* strea
 
 extern "C" int dh_plan_destroy(dh_plan* p) {
   if (!p) return DH_E_BADARG;
-  if (p->d_status) cudaFree(p->d_status);
+  if (p->d_status) {
+    if (range_flag_get() == p->d_status) range_flag_set(nullptr);  // never leave a dangling status pointer behind
+    cudaFree(p->d_status);
+  }
   for (auto& g : p->move_graphs) cudaGraphExecDestroy(g.exec);
   if (p->d_mcmc) cudaFree(p->d_mcmc);
   if (p->raw_params) cudaFree(p->raw_params);
@@ -445,6 +449,16 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       if (jets) rc = attention_jets(w.qkv, w.att, Bc, nd, (l == 0 && p->gemm_impl == 1) ? 1 : 0, p->tc_f16 ? 0 : 1, s);
       else rc = attention_value(w.qkv, w.att, Bc, nd, s);
       if (rc) return rc; }
+    // value-only passes on the fp16-piece tensor-core path: the residual + LayerNorm (+ tanh) that follows a 256-wide
+    // contraction runs as its epilogue (gemm_tc.cu, LNV) -- no separate LayerNorm launch, the contraction's output never
+    // goes to HBM.
+    const bool lnv = !jets && p->gemm_impl == 1 && p->tc_f16 && D == 256 && p->ln_value_fuse;
+    if (lnv) {
+      const LnArgs la0{P + o.ln0_s, P + o.ln0_b, 0}, la1{P + o.ln1_s, P + o.ln1_b, 1};
+      if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.h, rows, D, R, s, false, &la0))) return rc;  // h = LN0(h + att Wod + bod)
+      if ((rc = dense_tc(p, w.h, l * SL_PER_LAYER + SL_D2, w.h, rows, D, R, s, false, &la1))) return rc;    // h = LN1(h + tanh(h W2 + b2))
+      continue;
+    }
     if (p->gemm_impl == 1) {
       // MHA out-projection and the bias-free Dense that follows it are one linear map (Wo W1, bo W1)
       if ((rc = dense_tc(p, w.att, l * SL_PER_LAYER + SL_OD, w.t2, rows, D, R, s, pl))) return rc;
@@ -473,7 +487,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     g.bias = nullptr; g.inv_scale = nullptr;  // both are folded into the envelope table
     g.C = w.Mj; g.ldc = sl.Nout; g.M = rows; g.N = sl.Nout; g.K = p->D; g.rpg = R;
     g.f16 = 1; g.merged = 1; g.reduce_add = 0; g.a_scale = nullptr; g.A_lo = nullptr;
-    g.orb_env = w.cbuf; g.orb_Mj = w.Mj; g.orb_L = p->L;
+    g.orb_env = w.cbuf; g.orb_Mj = w.Mj; g.orb_L = p->L; g.ln_res = nullptr; g.ln_gamma = nullptr; g.ln_beta = nullptr; g.ln_tanh = 0;
     if ((rc = gemm_tc_ex(g, s))) return rc;
   } else {
     if ((rc = dense_orb(p, P, w.h, w.cbuf, rows, R, s, pl))) return rc;
@@ -893,6 +907,7 @@ extern "C" int dh_gemm(const float* A, const float* W, const float* bias, float*
                        void* stream) {
   if (!A || !W || !C) return DH_E_BADARG;
   cudaStream_t s = (cudaStream_t)stream;
+  range_flag_set(nullptr);  // plan-free entry point: no status word to report into
   if (impl == 0) return gemm_simt(A, W, bias, C, M, N, K, K, 1, N, 1, N, rows_per_group, accumulate, 1, s);
   if (!gemm_tc_supported(N, K) || accumulate) return DH_E_UNSUPPORTED;
   // test / bench / optimizer entry point: the split weights are made on the fly in the caller's workspace (the plan

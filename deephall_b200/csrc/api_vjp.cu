@@ -71,7 +71,7 @@ int dense_bwd_x_tc(const dh_plan* p, const float* G, int64_t ldg, int vs, int K,
   g.C = C; g.ldc = p->D; g.M = rows; g.N = p->D; g.K = K; g.rpg = 1;
   g.f16 = p->tc_f16; g.merged = p->tc_merged; g.reduce_add = accumulate;
   g.A_lo = nullptr;
-  g.orb_env = nullptr; g.orb_Mj = nullptr; g.orb_L = 0;
+  g.orb_env = nullptr; g.orb_Mj = nullptr; g.orb_L = 0; g.ln_res = nullptr; g.ln_gamma = nullptr; g.ln_beta = nullptr; g.ln_tanh = 0;
   g.a_scale = p->prep + p->cot_scale;  // gradients scale with the cotangents (O(1/B)): keep the fp16 pieces in range
   return gemm_tc_ex(g, s);
 }

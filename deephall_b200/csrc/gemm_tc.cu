@@ -298,18 +298,28 @@ struct OrbFuse {
   float* Mj;         // out: orbital-matrix jets [walkers][32 rows][12 electrons][12 orbitals] complex
   int L;             // orbitals 2Q + 1
 };
+// LNV (pair form, value-only passes: one row per electron, N = 256): the epilogue is the residual + (tanh) + LayerNorm that
+// follows the contraction in the network (psiformer.py:45-48) -- C = LN(res + acc + bias) or LN(res + tanh(acc + bias)),
+// in place over res.  Value rows only need their own statistics (no jet couplings), so the fused form is two sweeps over the
+// tile's accumulator columns: x = res + f(acc) back into tensor memory with the row sums, then normalise and store.
+struct LnFuse {
+  const float* res;    // residual = output tensor [M][ldc] (in place)
+  const float* gamma;  // LayerNorm scale [256]
+  const float* beta;   // LayerNorm bias  [256]
+  int tanh_mode;
+};
 constexpr int ORB_NK = 12;               // orbital columns per (part, m) group
 constexpr int ORB_GW = 2 * ORB_NK;       // accumulator columns per m: [re (12) | im (12)]
 constexpr int ORB_MPT = BLOCK_N / ORB_GW;  // m per column tile: 10 (the last 16 columns of a full tile are zero weights)
 
-template <bool F16, bool MERGED, bool PAIR, bool ORB>
+template <bool F16, bool MERGED, bool PAIR, bool ORB, bool LNV>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                const float* __restrict__ bias, const float* __restrict__ inv_scale_ptr, float* __restrict__ C, int64_t M,
                int N, int K, int64_t ldc, int rpg, int tma_store, int reduce_add, int cl, const float* __restrict__ a_scale_ptr,
-               int a_pre, int res, OrbFuse orb, unsigned long long* __restrict__ prof, unsigned* __restrict__ rflag) {
+               int a_pre, int res, OrbFuse orb, LnFuse ln, unsigned long long* __restrict__ prof, unsigned* __restrict__ rflag) {
   constexpr int merged = MERGED ? 1 : 0;
   constexpr int UMMA_K = F16 ? 16 : 8;    // K elements per MMA (32 bytes of operand row)
   // Stage layout.  tf32 pieces: [A hi 16 KB | A lo 16 KB | B hi 32 KB | B lo 32 KB], rows of 128 B (SWIZZLE_128B).
@@ -318,6 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   //                PAIR:        [A hi 8 KB | A lo 8 KB | B hi 8 KB | B lo 8 KB]: this CTA's 128 of the tile's 256 weight rows.
   static_assert(!PAIR || (F16 && MERGED), "the CTA-pair form exists for fp16 pieces with the merged accumulator");
   static_assert(!ORB || PAIR, "the fused orbital-contraction epilogue exists for the pair form");
+  static_assert(!LNV || (PAIR && !ORB), "the fused value LayerNorm epilogue exists for the pair form");
   constexpr int STAGES = PAIR ? 6 : (F16 ? 4 : 2);
   constexpr int ROW_BYTES = F16 ? 64 : 128;            // operand tile row = BLOCK_K pieces
   constexpr int AP_BYTES = BLOCK_M * ROW_BYTES;        // one A piece tile
@@ -815,6 +826,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < ORB_NK; j += 2)
                 *reinterpret_cast<float4*>(dst + 2 * j) = make_float4(oacc[j], oacc[ORB_NK + j], oacc[j + 1], oacc[ORB_NK + j + 1]);
             }
+          }
+        }
+        continue;
+      }
+      if constexpr (LNV) {
+        // ---------------------------------------------------------------- fused residual + (tanh) + LayerNorm, value rows
+        // lane = one row (one electron's value row); the two warps of a lane quarter take the even / odd 32-column chunks.
+        const bool mvalid = m < M;
+        const float* rrow = ln.res + (mvalid ? m : 0) * ldc;
+        float s_x = 0.f, s_xx = 0.f;
+#pragma unroll 1
+        for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a4 = mvalid ? __ldg(reinterpret_cast<const float4*>(rrow + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            x[4 * j] = a4.x; x[4 * j + 1] = a4.y; x[4 * j + 2] = a4.z; x[4 * j + 3] = a4.w;
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = bias != nullptr ? __ldg(reinterpret_cast<const float4*>(bias + c0 + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float f = fmaf(__uint_as_float(v[4 * j + u]), inv_scale, bb[u]);
+              if (ln.tanh_mode) {
+                // tanh = 1 - 2 / (1 + e^{2|x|}) with the fast exponential and division: absolute error ~1e-7, the level of the
+                // contraction's own rounding, at a quarter of tanhf's instructions (32 per lane and chunk: the epilogue's main cost)
+                const float e2 = __expf(2.f * fabsf(f));
+                f = copysignf(1.f - __fdividef(2.f, e2 + 1.f), f);
+              }
+              const float xv = x[4 * j + u] + f;
+              x[4 * j + u] = xv;
+              s_x += xv;
+              s_xx = fmaf(xv, xv, s_xx);
+            }
+          }
+          tmem_st32(tbase + (uint32_t)c0, x);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // the two warps of the quarter exchange their halves of the row sums through their staging buffers
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous tile's stores have read them
+        __syncwarp();
+        reinterpret_cast<float2*>(buf)[lane] = make_float2(s_x, s_xx);
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        {
+          const uint8_t* other = epi_smem + ((warp - EPI_WARP0) ^ 4) * EPI_BUF_BYTES;
+          const float2 o2 = reinterpret_cast<const float2*>(other)[lane];
+          s_x += o2.x;
+          s_xx += o2.y;
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // both have read before the buffers take the outputs
+        constexpr float invD = 1.f / 256.f;
+        const float mu = s_x * invD;
+        const float rho = rsqrtf(fmaxf(s_xx * invD - mu * mu, 0.f) + 1e-5f);  // flax LayerNorm: fast variance, eps 1e-5
+#pragma unroll 1
+        for (int c0 = chalf * EPI_CHUNK; c0 < BLOCK_N; c0 += 2 * EPI_CHUNK) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 2 * EPI_CHUNK >= BLOCK_N) {  // last read of this accumulator
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader(tmem_empty_bar(ab)));
+          }
+          float y[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln.gamma + c0 + 4 * j));
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(ln.beta + c0 + 4 * j));
+            y[4 * j] = fmaf((__uint_as_float(v[4 * j]) - mu) * rho, g4.x, e4.x);
+            y[4 * j + 1] = fmaf((__uint_as_float(v[4 * j + 1]) - mu) * rho, g4.y, e4.y);
+            y[4 * j + 2] = fmaf((__uint_as_float(v[4 * j + 2]) - mu) * rho, g4.z, e4.z);
+            y[4 * j + 3] = fmaf((__uint_as_float(v[4 * j + 3]) - mu) * rho, g4.w, e4.w);
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, smem_u32(buf), n0 + c0, (int)(m0 + q * 32));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
         continue;
@@ -1337,6 +1436,7 @@ int gemm_tc(const float* A, const void* Wt_hi, const void* Wt_lo, const float* b
   g.a_scale = nullptr;
   g.A_lo = nullptr;
   g.orb_env = nullptr; g.orb_Mj = nullptr; g.orb_L = 0;
+  g.ln_res = nullptr; g.ln_gamma = nullptr; g.ln_beta = nullptr; g.ln_tanh = 0;
   return gemm_tc_ex(g, stream);
 }
 
@@ -1367,12 +1467,13 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc::gemm_tc_kernel<true, true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -1381,7 +1482,9 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   const int sms = tc::num_sms();
   // CTA pairs (tcgen05.mma.cta_group::2): fp16 pieces with the merged accumulator, fp32 A; DH_GEMM_PAIR=0 disables
   static const bool pair_env = !(dbg_env("DH_GEMM_PAIR") && atoi(dbg_env("DH_GEMM_PAIR")) == 0);
-  const bool pair = pair_env && f16 && merged && !a_pre && bands >= 2;
+  // (the fused value LayerNorm exists for the pair form only: a single band runs as a pair whose second band is out of range --
+  // its loads are zero-filled and its stores clipped -- so that every value pass takes the same arithmetic path)
+  const bool pair = pair_env && f16 && merged && !a_pre && (bands >= 2 || gm.ln_res != nullptr);
   // cluster size: DH_GEMM_CLUSTER = 1 | 2 | 4; small problems run un-clustered.  Default 1: with the
   // 192 KB operand ring the kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic, and the
   // multicast measured no faster at 2 and slower at 4 (profiles/r1_gemm_tc_notes.md).
@@ -1417,6 +1520,14 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   if (orb_on && !(pair && res && rpg == 32 && !reduce_add && gm.a_scale == nullptr && M % 128 == 0 && gm.orb_L >= 1 && gm.orb_L <= 48 &&
                   N == (gm.orb_L - 1) / tc::ORB_MPT * tc::BLOCK_N + ((gm.orb_L - 1) % tc::ORB_MPT + 1) * tc::ORB_GW))
     return -2;
+  // fused value LayerNorm epilogue: pair form, one 256-wide column tile, every row a value row, TMA-stored output in place
+  tc::LnFuse lnf;
+  lnf.res = gm.ln_res; lnf.gamma = gm.ln_gamma; lnf.beta = gm.ln_beta; lnf.tanh_mode = gm.ln_tanh;
+  const bool ln_on = gm.ln_res != nullptr;
+  if (ln_on && !(pair && !orb_on && N == tc::BLOCK_N && rpg <= 1 && tma_store && !reduce_add && gm.a_scale == nullptr &&
+                 gm.ln_gamma && gm.ln_beta && ((reinterpret_cast<uintptr_t>(gm.ln_res) | reinterpret_cast<uintptr_t>(gm.ln_gamma) |
+                                                reinterpret_cast<uintptr_t>(gm.ln_beta) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0))
+    return -2;
   cudaLaunchConfig_t lc;
   memset(&lc, 0, sizeof(lc));
   lc.gridDim = grid;
@@ -1431,12 +1542,15 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   lc.attrs = lattr;
   lc.numAttrs = 1;
   cudaError_t le;
-#define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR, false>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
-                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, prof, \
+#define DH_LAUNCH_TC(F, MG, PR) le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<F, MG, PR, false, false>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, \
+                                                        C, M, N, K, ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, lnf, prof, \
                                                         g_range_flag)
   if (orb_on)
-    le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<true, true, true, true>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K,
-                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, prof, g_range_flag);
+    le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<true, true, true, true, false>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K,
+                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, lnf, prof, g_range_flag);
+  else if (ln_on)
+    le = cudaLaunchKernelEx(&lc, tc::gemm_tc_kernel<true, true, true, false, true>, tmA, tmAlo, tmBh, tmBl, tmC, bias, inv_scale, C, M, N, K,
+                            ldc, rpg, tma_store, reduce_add, cl, gm.a_scale, a_pre, res, orb, lnf, prof, g_range_flag);
   else if (pair) DH_LAUNCH_TC(true, true, true);
   else if (f16) { if (merged) DH_LAUNCH_TC(true, true, false); else DH_LAUNCH_TC(true, false, false); }
   else { if (merged) DH_LAUNCH_TC(false, true, false); else DH_LAUNCH_TC(false, false, false); }

@@ -34,6 +34,9 @@ struct TcGemm {
   // epilogue contracts the coefficients with the per-electron envelope table orb_env [electrons][10][orb_L] complex into the
   // orbital-matrix jets orb_Mj -- C is not written; null = off
   const float* orb_env; float* orb_Mj; int orb_L;
+  // fused value LayerNorm epilogue (value-only passes, pair form, N = 256, rpg = 1): C = LN(ln_res + acc + bias) or
+  // LN(ln_res + tanh(acc + bias)), written in place over ln_res (= C); null = off
+  const float* ln_res; const float* ln_gamma; const float* ln_beta; int ln_tanh;
   const void* A_lo;      // non-null (fp16 pieces only): A and A_lo are fp16 hi / lo planes [M][lda] written by the
                          // producing kernel; the in-kernel split is skipped
 };

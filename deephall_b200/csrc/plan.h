@@ -55,6 +55,7 @@ struct dh_plan {
   int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
   int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators
   int tc_f16;     // tcgen05 path: 1 = kind::f16 pieces (D % 64 == 0), 0 = kind::tf32 pieces
+  int ln_value_fuse = 0;  // value-only passes: residual + LayerNorm as the epilogue of the 256-wide contractions
   int orb_fuse = 0;    // jet passes at N = 12: the envelope contraction runs as the epilogue of the orbital projection
   size_t orb_perm = 0; // prep offset of the permuted fp32 orbital kernel + bias (staging for the split)
   int a_planes;   // jet passes keep the activations that feed a contraction as fp16 hi / lo planes (fp16 pieces, D = 256)
@@ -215,8 +216,9 @@ enum { VS_D2 = 0, VS_D1 = 1, VS_O = 2, VS_QKV = 3, VS_PER_LAYER = 4 };
 // tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows).
 // a_planes: A is the fp16 hi / lo plane view of a [rows][D] buffer (common.cuh), written by the producing kernel.
 
+struct LnArgs { const float* gamma; const float* beta; int tanh_mode; };  // fused value LayerNorm epilogue: C = LN(C + f(A W + b)) in place
 static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C, int64_t rows, int64_t ldc, int R,
-                           cudaStream_t s, bool a_planes = false) {
+                           cudaStream_t s, bool a_planes = false, const LnArgs* ln = nullptr) {
   const dh_plan::Slot& sl = p->slots[slot];
   ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * sl.Nout * p->D, s);
   TcGemm g;
@@ -227,6 +229,7 @@ static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C,
   g.f16 = p->tc_f16; g.merged = p->tc_merged; g.reduce_add = 0; g.a_scale = nullptr;
   g.A_lo = a_planes ? reinterpret_cast<const __half*>(A) + rows * p->D : nullptr;
   g.orb_env = nullptr; g.orb_Mj = nullptr; g.orb_L = 0;
+  g.ln_res = ln ? C : nullptr; g.ln_gamma = ln ? ln->gamma : nullptr; g.ln_beta = ln ? ln->beta : nullptr; g.ln_tanh = ln ? ln->tanh_mode : 0;
   return gemm_tc_ex(g, s);
 }
 
