@@ -70,6 +70,7 @@ SIGNATURES = OrderedDict(
     dh_local_energy=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
     dh_potential=(C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     dh_mcmc_sweep=(C.c_int, [_vp, _vp, _vp, _i64, _i32, _f, _u64, _u64, _u64, _vp, _vp, _vp, _vp, C.c_size_t, _vp]),
+    dh_mcmc_sweep_dev=(C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, _u64, _vp, _vp, _vp, C.c_size_t, _vp]),
     dh_mcmc_propose=(C.c_int, [_vp, _vp, _i64, _f, _u64, _u64, _u64, _vp, _vp, _vp]),
     dh_mcmc_accept=(C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _u64, _u64, _u64, _vp, _vp, _vp]),
     dh_init_walkers=(C.c_int, [_vp, _vp, _i64, _u64, _u64, _vp]),
@@ -312,6 +313,19 @@ class Plan:
                                    int(subsequence0), _ptr(randoms), _ptr(nacc), _ptr(lp), _ptr(ws), ws.numel(), _stream()),
             "dh_mcmc_sweep",
         )
+        return nacc, lp
+
+    def mcmc_sweep_dev(self, params, x, steps, width_dev, key_dev, subsequence0=0, want_lp=False):
+        """dh_mcmc_sweep_dev: width_dev (1,) f32 and key_dev (2,) int64 = (seed, offset) are DEVICE tensors read by the kernels."""
+        self._prepare(params)
+        _f32(x, "walkers"), _f32(width_dev, "width")
+        assert key_dev.dtype == torch.int64 and key_dev.numel() == 2
+        B = x.shape[0]
+        nacc = torch.zeros((1,), dtype=torch.int64, device=x.device)
+        lp = torch.empty((B,), dtype=torch.float32, device=x.device) if want_lp else None
+        ws = self.workspace(OP_MCMC, B)
+        _check(self.lib.dh_mcmc_sweep_dev(self.handle, _ptr(params), _ptr(x), B, int(steps), _ptr(width_dev), _ptr(key_dev),
+                                          int(subsequence0), _ptr(nacc), _ptr(lp), _ptr(ws), ws.numel(), _stream()), "dh_mcmc_sweep_dev")
         return nacc, lp
 
     def mcmc_propose(self, x1, width, seed=0, offset=0, subsequence0=0, randoms=None):

@@ -784,11 +784,11 @@ extern "C" int dh_init_walkers(dh_plan* p, float* x, int64_t B, uint64_t seed, u
   return init_walkers(x, B, p->N, seed, subsequence0, (cudaStream_t)stream);
 }
 
-extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t B, int32_t steps, float width,
-                             uint64_t seed, uint64_t offset, uint64_t subsequence0, const float* randoms,
-                             long long* out_naccept, float* out_lp, void* ws, size_t ws_bytes, void* stream) {
-  if (!p || (!params && p->nparams > 0) || !x || !out_naccept || steps < 0) return DH_E_BADARG;
-  cudaStream_t s = (cudaStream_t)stream;
+// The sweep proper.  dev_args: the move arguments (Philox key / offset, width, first subsequence) are already in the plan's
+// device block (dh_mcmc_sweep_dev); otherwise they are the host scalars given here.
+static int mcmc_sweep_impl(dh_plan* p, const float* params, float* x, int64_t B, int32_t steps, float width, uint64_t seed,
+                           uint64_t offset, uint64_t subsequence0, const float* randoms, bool dev_args, long long* out_naccept,
+                           float* out_lp, void* ws, size_t ws_bytes, cudaStream_t s) {
   if (B == 0) return (int)cudaMemsetAsync(out_naccept, 0, sizeof(long long), s);
   float* base = align_ws(ws);
   McmcWs mw = carve_mcmc(p, base, B);
@@ -806,16 +806,19 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
     return rc;
   if ((rc = lp_from_logpsi(mw.logpsi2, mw.lp1, B, s))) return rc;
   const int64_t rstride = B * (2 * (int64_t)p->N + 1);
-  // ---- production path: in-kernel Philox, the move replayed from a captured CUDA graph (a sweep is ~17 short launches
-  // per move; at 1024 walkers per GPU their launch gaps are a third of the sweep)
+  // ---- production path: in-kernel Philox, the move replayed from a captured CUDA graph with its arguments in a device block
   static const bool graphs_env = !(dbg_env("DH_MCMC_GRAPH") && atoi(dbg_env("DH_MCMC_GRAPH")) == 0);
-  if (!randoms && steps >= 2 && !p->prof_on && p->graphs_ok && graphs_env && p->d_mcmc && (p->laughlin || p->raw_params)) {
+  const bool dev_ok = !randoms && p->d_mcmc && (p->laughlin || p->raw_params);
+  if (dev_args && !dev_ok) return DH_E_UNSUPPORTED;
+  if (dev_ok && (dev_args || (steps >= 2 && !p->prof_on && p->graphs_ok && graphs_env))) {
     const float* Pg = p->laughlin ? params : p->raw_params;
     if (!p->laughlin) DH_CHECK(cudaMemcpyAsync(p->raw_params, params, p->nparams * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if ((rc = mcmc_dev_init(p->d_mcmc, seed, offset, subsequence0, width, s))) return rc;
+    if (!dev_args && (rc = mcmc_dev_init(p->d_mcmc, seed, offset, subsequence0, width, s))) return rc;
     dh_plan::MoveGraph* mg = nullptr;
-    for (auto& g : p->move_graphs) if (g.x == x && g.ws == ws && g.B == B) mg = &g;
-    if (!mg) {
+    const bool want_graph = steps >= 2 && !p->prof_on && p->graphs_ok && graphs_env;
+    if (want_graph)
+      for (auto& g : p->move_graphs) if (g.x == x && g.ws == ws && g.B == B) mg = &g;
+    if (want_graph && !mg) {
       cudaGraph_t graph = nullptr;
       const long long l0 = p->launches;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -843,11 +846,21 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
     if (mg) {
       for (int st = 0; st < steps; ++st) DH_CHECK(cudaGraphLaunch(mg->exec, s));
       p->launches += mg->launches * steps;
+    } else if (dev_args) {  // no graph (one move, profiling, or capture refused): the same kernels launched one by one
+      for (int st = 0; st < steps; ++st) {
+        { ProfScope ps(p, PC_MCMC, 0, s); if ((rc = mcmc_propose_dev(x, mw.x2, B, p->N, p->d_mcmc, s))) return rc; }
+        if ((rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
+        { ProfScope ps(p, PC_MCMC, 0, s);
+          if ((rc = mcmc_accept_dev(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, p->d_mcmc, s))) return rc;
+          if ((rc = mcmc_dev_advance(p->d_mcmc, s))) return rc; }
+      }
+    }
+    if (mg || dev_args) {
       DH_CHECK(cudaMemcpyAsync(out_naccept, &p->d_mcmc->naccept, sizeof(long long), cudaMemcpyDeviceToDevice, s));
       if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
       return 0;
     }
-    // capture refused: fall through to the launch-by-launch loop (the dev block is simply unused)
+    // capture refused: fall through to the launch-by-launch loop with host arguments
   }
   for (int st = 0; st < steps; ++st) {
     const float* rnd = randoms ? randoms + st * rstride : nullptr;
@@ -862,6 +875,25 @@ extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t 
   }
   if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
+}
+
+extern "C" int dh_mcmc_sweep(dh_plan* p, const float* params, float* x, int64_t B, int32_t steps, float width,
+                             uint64_t seed, uint64_t offset, uint64_t subsequence0, const float* randoms,
+                             long long* out_naccept, float* out_lp, void* ws, size_t ws_bytes, void* stream) {
+  if (!p || (!params && p->nparams > 0) || !x || !out_naccept || steps < 0) return DH_E_BADARG;
+  return mcmc_sweep_impl(p, params, x, B, steps, width, seed, offset, subsequence0, randoms, false, out_naccept, out_lp, ws, ws_bytes,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int dh_mcmc_sweep_dev(dh_plan* p, const float* params, float* x, int64_t B, int32_t steps, const float* width_dev,
+                                 const uint64_t* key_dev, uint64_t subsequence0, long long* out_naccept, float* out_lp, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  if (!p || (!params && p->nparams > 0) || !x || !out_naccept || steps < 0 || !width_dev || !key_dev) return DH_E_BADARG;
+  if (!p->d_mcmc) return DH_E_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = mcmc_dev_init_from(p->d_mcmc, reinterpret_cast<const unsigned long long*>(key_dev), width_dev, subsequence0, s);
+  if (rc) return rc;
+  return mcmc_sweep_impl(p, params, x, B, steps, 0.f, 0, 0, subsequence0, nullptr, true, out_naccept, out_lp, ws, ws_bytes, s);
 }
 
 // --------------------------------------------------------------------------------- energy statistics (loss.py:66-92)

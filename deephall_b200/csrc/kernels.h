@@ -157,6 +157,7 @@ int energy_diff(const float* el, const float* lz, const float* lz2, const float*
 // device-resident arguments of a Metropolis move: lets one captured CUDA graph of a move be replayed for every move
 struct McmcDev { unsigned long long seed, offset, subseq0, naccept; float width; };
 int mcmc_dev_init(McmcDev* dv, uint64_t seed, uint64_t offset, uint64_t subseq0, float width, cudaStream_t s);
+int mcmc_dev_init_from(McmcDev* dv, const unsigned long long* key, const float* width, uint64_t subseq0, cudaStream_t s);
 int mcmc_dev_advance(McmcDev* dv, cudaStream_t s);
 int mcmc_propose_dev(const float* x1, float* x2, int64_t B, int N, const McmcDev* dv, cudaStream_t s);
 int mcmc_accept_dev(float* x1, const float* x2, float* lp1, const float* lp2c, int lp2_stride, int64_t B, int N, McmcDev* dv,

@@ -23,6 +23,15 @@ int mcmc_dev_init(McmcDev* dv, uint64_t seed, uint64_t offset, uint64_t subseq0,
   mcmc_dev_init_kernel<<<1, 1, 0, s>>>(dv, seed, offset, subseq0, width);
   return (int)cudaGetLastError();
 }
+// the same block filled from DEVICE scalars (traced values of a jit-compiled caller: the Philox key and the proposal width)
+__global__ void mcmc_dev_init_from_kernel(McmcDev* dv, const unsigned long long* __restrict__ key, const float* __restrict__ width,
+                                          unsigned long long subseq0) {
+  dv->seed = key[0]; dv->offset = key[1]; dv->subseq0 = subseq0; dv->naccept = 0ull; dv->width = width[0];
+}
+int mcmc_dev_init_from(McmcDev* dv, const unsigned long long* key, const float* width, uint64_t subseq0, cudaStream_t s) {
+  mcmc_dev_init_from_kernel<<<1, 1, 0, s>>>(dv, key, width, subseq0);
+  return (int)cudaGetLastError();
+}
 int mcmc_dev_advance(McmcDev* dv, cudaStream_t s) {
   mcmc_dev_advance_kernel<<<1, 1, 0, s>>>(dv);
   return (int)cudaGetLastError();

@@ -149,6 +149,14 @@ int dh_mcmc_sweep(dh_plan* plan, const float* params, float* x_inout, int64_t B,
                   const float* randoms, long long* out_naccept, float* out_lp, void* ws,
                   size_t ws_bytes, void* stream);
 
+/* The same sweep with its traced arguments on the DEVICE: width_dev (1 float) and key_dev (2 x uint64: Philox seed, offset)
+ * are read by the kernels, not by the host -- the form a jit-compiled caller needs (the reference's `mcmc_width` lives in the
+ * CheckpointState and its key is split every step: both are traced values under `jax.jit` / `pmap`, train.py:126-131), and
+ * the form the XLA FFI shim binds (integration/jax_ffi/dh_xla_ffi.cc).  In-kernel Philox only (no injected randoms). */
+int dh_mcmc_sweep_dev(dh_plan* plan, const float* params, float* x_inout, int64_t B, int32_t steps, const float* width_dev,
+                      const uint64_t* key_dev, uint64_t subsequence0, long long* out_naccept, float* out_lp, void* ws,
+                      size_t ws_bytes, void* stream);
+
 /* One proposal (mcmc.py:67-102) and one accept/select (mcmc.py:56-62), exposed for parity
  * tests.  `randoms` as above with steps = 1 (NULL -> Philox). */
 int dh_mcmc_propose(dh_plan* plan, const float* x1, int64_t B, float width, uint64_t seed,

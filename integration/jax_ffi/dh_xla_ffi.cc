@@ -14,7 +14,15 @@
 // an int64 attribute (the dh_plan* created once per (device, configuration) by the Python side through ctypes), and the
 // workspace is the LAST result buffer (sized with dh_workspace_bytes on the Python side, so XLA owns the memory and
 // the library never allocates -- the ownership rule of SURVEY 8b).
+//
+// Traced values are OPERANDS, not attributes: the proposal width lives in the reference's CheckpointState and changes by
+// x1.1 (mcmc.py:181-185), the key is split every step (train.py:127) -- as attributes they would force a recompile per
+// value.  The sweep handler therefore takes `width` (1 x f32) and `key` (2 x u64: Philox seed, offset) as device buffers and
+// calls dh_mcmc_sweep_dev, whose kernels read them on the device.  Static attributes: plan handle, steps, subsequence0.
+// Plans used through this shim keep the library default auto_prepare = 1 (the split / folded weight copies are rebuilt
+// from `params` on every call): XLA recycles donated buffer addresses, so an address-keyed weight cache would go stale.
 #include <cstdint>
+#include <string>
 
 #include <cuda_runtime_api.h>
 
@@ -57,19 +65,19 @@ ffi::Error LocalEnergyImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ff
 // make_mcmc_step(...)(params, data, key, width): `data` is donated (input_output_aliases={1: 0} on the Python side, so
 // x_out aliases x_in, train.py:75); naccept is one int64 on the device (pmove = naccept / (steps * B), mcmc.py:146)
 ffi::Error McmcSweepImpl(cudaStream_t stream, ffi::Buffer<ffi::F32> params, ffi::Buffer<ffi::F32> x_in,
-                         ffi::ResultBuffer<ffi::F32> x_out, ffi::ResultBuffer<ffi::S64> naccept,
-                         ffi::ResultBuffer<ffi::U8> ws, int64_t plan, int32_t steps, float width, int64_t seed,
-                         int64_t offset, int64_t subsequence0) {
+                         ffi::Buffer<ffi::F32> width, ffi::Buffer<ffi::U64> key, ffi::ResultBuffer<ffi::F32> x_out,
+                         ffi::ResultBuffer<ffi::S64> naccept, ffi::ResultBuffer<ffi::U8> ws, int64_t plan, int32_t steps,
+                         int64_t subsequence0) {
   const int64_t B = x_in.dimensions()[0];
   if (x_out->typed_data() != x_in.typed_data()) {  // not aliased: keep functional semantics
     cudaError_t e = cudaMemcpyAsync(x_out->typed_data(), x_in.typed_data(), x_in.size_bytes(), cudaMemcpyDeviceToDevice, stream);
     if (e != cudaSuccess) return status(static_cast<int>(e), "cudaMemcpyAsync");
   }
-  return status(dh_mcmc_sweep(plan_of(plan), params.typed_data(), x_out->typed_data(), B, steps, width,
-                              static_cast<uint64_t>(seed), static_cast<uint64_t>(offset), static_cast<uint64_t>(subsequence0),
-                              nullptr, reinterpret_cast<long long*>(naccept->typed_data()), nullptr, ws->typed_data(),
-                              ws->element_count(), stream),
-                "dh_mcmc_sweep");
+  return status(dh_mcmc_sweep_dev(plan_of(plan), params.typed_data(), x_out->typed_data(), B, steps, width.typed_data(),
+                                  key.typed_data(), static_cast<uint64_t>(subsequence0),
+                                  reinterpret_cast<long long*>(naccept->typed_data()), nullptr, ws->typed_data(),
+                                  ws->element_count(), stream),
+                "dh_mcmc_sweep_dev");
 }
 
 // VJP of b -> (Re, Im) log psi_b with per-walker cotangents cot (B, 2): grad (P) f32             loss.py:53-64,96-106
@@ -110,16 +118,15 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(dh_local_energy_ffi, LocalEnergyImpl,
 XLA_FFI_DEFINE_HANDLER_SYMBOL(dh_mcmc_sweep_ffi, McmcSweepImpl,
                               ffi::Ffi::Bind()
                                   .Ctx<ffi::PlatformStream<cudaStream_t>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
-                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()   // params (P)
+                                  .Arg<ffi::Buffer<ffi::F32>>()   // walkers (B, N, 2), donated
+                                  .Arg<ffi::Buffer<ffi::F32>>()   // width (1): traced
+                                  .Arg<ffi::Buffer<ffi::U64>>()   // key (2) = (Philox seed, offset): traced
                                   .Ret<ffi::Buffer<ffi::F32>>()   // walkers (B, N, 2), aliased to the input
                                   .Ret<ffi::Buffer<ffi::S64>>()   // accepted moves (1)
-                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()    // workspace
                                   .Attr<int64_t>("plan")
                                   .Attr<int32_t>("steps")
-                                  .Attr<float>("width")
-                                  .Attr<int64_t>("seed")
-                                  .Attr<int64_t>("offset")
                                   .Attr<int64_t>("subsequence0"));
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(dh_logpsi_vjp_ffi, LogpsiVjpImpl,

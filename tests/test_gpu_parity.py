@@ -490,6 +490,19 @@ def test_graph_replayed_sweep_is_the_same_chain(nat):
             flat = (flat * 0.99).clone()  # new tensor
 
 
+def test_sweep_with_device_arguments(nat):
+    """dh_mcmc_sweep_dev (width and Philox key read from device memory: the form a jit-compiled / XLA-FFI caller needs) is
+    the same chain as dh_mcmc_sweep with the same values as host scalars, for one move and for many."""
+    cfg, p64, plan, flat, x0 = setup_case(nat, CONFIGS["c2"], 300, burn=0)
+    for steps in (1, 5):
+        xa, xb = x0.clone(), x0.clone()
+        na, lpa = plan.mcmc_sweep(flat, xa, steps, 0.2, seed=77, offset=1234, subsequence0=5000, want_lp=True)
+        width = torch.tensor([0.2], device=DEV)
+        key = torch.tensor([77, 1234], dtype=torch.int64, device=DEV)
+        nb, lpb = plan.mcmc_sweep_dev(flat, xb, steps, width, key, subsequence0=5000, want_lp=True)
+        assert torch.equal(xa, xb) and int(na) == int(nb) and torch.equal(lpa, lpb) and 0 < int(na) < steps * 300
+
+
 def test_mcmc_samples_psi_squared(nat):
     """Filled-LLL N=3 state: <KE> = 1.5 exactly for every walker, and the sampled Coulomb energy of
     the chain is stationary -- the chain equilibrates to a distribution with E = 1.5 + <V>."""
