@@ -474,13 +474,15 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     { ProfScope ps(p, PC_LAYERNORM, 0, s);
       if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
   }
-  if (jets && p->orb_fuse && rows % 128 == 0) {
+  if (p->orb_fuse && (!jets || rows % 128 == 0)) {
     // The envelope contraction (blocks.py:59-70) is the EPILOGUE of the orbital projection (blocks.py:28-35): the per-electron
-    // envelope jets go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the contraction reads
-    // its coefficients out of tensor memory and writes the orbital-matrix jets -- c[rows][2 L N] never exists in HBM
+    // envelope values (jet passes: jets) go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the
+    // contraction reads its coefficients out of tensor memory and writes the orbital matrices -- c[rows][2 L N] never exists in HBM
     const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
     { ProfScope pse(p, PC_TAIL, 0, s);
-      if ((rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s))) return rc; }
+      if (jets) rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
+      else rc = envelope_value_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
+      if (rc) return rc; }
     ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * p->orbN * p->D, s);
     TcGemm g;
     g.A = w.h; g.lda = p->D; g.Wt_hi = p->prep + sl.hi; g.Wt_lo = p->prep + sl.lo; g.ldw = p->D;

@@ -711,6 +711,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * BLOCK_N;
       if constexpr (ORB) {
+        if (rpg <= 1) {
+          // -------------------------------------------------------------- value-only passes: one row per electron
+          // lane = one electron; its envelope (L complex numbers, pre-multiplied by the weight un-scale factor) and its bias
+          // products (12 complex) come from the per-electron table; the two warps of a lane quarter take the even / odd m.
+          const int nt = ntile_of(tk);
+          const int L = orb.L;
+          const bool live = m < M;
+          const float* et = orb.env + (live ? m : 0) * (int64_t)(2 * (L + ORB_NK));
+          float* xsum = reinterpret_cast<float*>(epi_smem + q * (2 * EPI_BUF_BYTES));  // [24][32] partial sums of the odd warp
+          if (nt == 0) {
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");  // the previous band's partial sums have been read
+#pragma unroll
+            for (int j = 0; j < ORB_GW; ++j) oacc[j] = 0.f;
+          }
+          const int mt = min(ORB_MPT, L - ORB_MPT * nt);
+#pragma unroll 1
+          for (int ml = chalf; ml < mt; ml += 2) {
+            uint32_t v[24];
+            tmem_ld16(tbase + (uint32_t)(ORB_GW * ml), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld8(tbase + (uint32_t)(ORB_GW * ml + 16), *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
+            const float2 e0 = __ldg(reinterpret_cast<const float2*>(et + 2 * (ORB_MPT * nt + ml)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (ml + 2 >= mt) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(leader(tmem_empty_bar(ab)));
+            }
+#pragma unroll
+            for (int j = 0; j < ORB_NK; ++j) {
+              const float cr = __uint_as_float(v[j]), ci = __uint_as_float(v[ORB_NK + j]);
+              oacc[j] = fmaf(cr, e0.x, fmaf(-ci, e0.y, oacc[j]));
+              oacc[ORB_NK + j] = fmaf(cr, e0.y, fmaf(ci, e0.x, oacc[ORB_NK + j]));
+            }
+          }
+          if (mt <= chalf) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(leader(tmem_empty_bar(ab)));
+          }
+          if (nt == n_ntiles - 1) {
+            if (chalf == 1) {
+#pragma unroll
+              for (int j = 0; j < ORB_GW; ++j) xsum[j * 32 + lane] = oacc[j];
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+            if (chalf == 0 && live) {
+              float* dst = orb.Mj + m * (int64_t)(2 * ORB_NK);
+#pragma unroll
+              for (int j = 0; j < ORB_NK; j += 2) {
+                const float4 bp = __ldg(reinterpret_cast<const float4*>(et + 2 * L + 2 * j));  // bias products of columns j, j + 1
+                *reinterpret_cast<float4*>(dst + 2 * j) =
+                    make_float4(oacc[j] + xsum[j * 32 + lane] + bp.x, oacc[ORB_NK + j] + xsum[(ORB_NK + j) * 32 + lane] + bp.y,
+                                oacc[j + 1] + xsum[(j + 1) * 32 + lane] + bp.z, oacc[ORB_NK + j + 1] + xsum[(ORB_NK + j + 1) * 32 + lane] + bp.w);
+              }
+            }
+          }
+          continue;
+        }
         // ---------------------------------------------------------------- fused envelope contraction (orbital matrices)
         // Accumulator columns of tile nt: m = 10 nt + ml, ml < 10, at [24 ml, 24 ml + 24) = [re c(m, 0..11) | im c(m, 0..11)]
         // (the weights were laid out so by orb_permute_weights).  The 32 lanes of this warp are the 32 jet rows of ONE
@@ -1484,7 +1542,7 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   static const bool pair_env = !(dbg_env("DH_GEMM_PAIR") && atoi(dbg_env("DH_GEMM_PAIR")) == 0);
   // (the fused value LayerNorm exists for the pair form only: a single band runs as a pair whose second band is out of range --
   // its loads are zero-filled and its stores clipped -- so that every value pass takes the same arithmetic path)
-  const bool pair = pair_env && f16 && merged && !a_pre && (bands >= 2 || gm.ln_res != nullptr);
+  const bool pair = pair_env && f16 && merged && !a_pre && (bands >= 2 || gm.ln_res != nullptr || gm.orb_env != nullptr);
   // cluster size: DH_GEMM_CLUSTER = 1 | 2 | 4; small problems run un-clustered.  Default 1: with the
   // 192 KB operand ring the kernel is bound by shared-memory bandwidth, not by L2 -> SM traffic, and the
   // multicast measured no faster at 2 and slower at 4 (profiles/r1_gemm_tc_notes.md).
@@ -1517,7 +1575,7 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   tc::OrbFuse orb;
   orb.env = gm.orb_env; orb.Mj = gm.orb_Mj; orb.L = gm.orb_L;
   const bool orb_on = gm.orb_env != nullptr;
-  if (orb_on && !(pair && res && rpg == 32 && !reduce_add && gm.a_scale == nullptr && M % 128 == 0 && gm.orb_L >= 1 && gm.orb_L <= 48 &&
+  if (orb_on && !(pair && res && ((rpg == 32 && M % 128 == 0) || rpg <= 1) && !reduce_add && gm.a_scale == nullptr && gm.orb_L >= 1 && gm.orb_L <= 48 &&
                   N == (gm.orb_L - 1) / tc::ORB_MPT * tc::BLOCK_N + ((gm.orb_L - 1) % tc::ORB_MPT + 1) * tc::ORB_GW))
     return -2;
   // fused value LayerNorm epilogue: pair form, one 256-wide column tile, every row a value row, TMA-stored output in place

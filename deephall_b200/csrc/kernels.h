@@ -103,6 +103,9 @@ struct TailDims {
 // (sum_m bias(m, j) env_s[m]): the right operand of the fused envelope contraction (gemm_tc.cu, ORB)
 int envelope_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
                    int64_t B, TailDims d, cudaStream_t s);
+// value-only form: per electron [L] complex envelope (times *unscale) + [N K] complex bias products
+int envelope_value_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
+                         int64_t B, TailDims d, cudaStream_t s);
 // orbital-projection kernels / biases -> fp32 [D][ncol] + [ncol] with columns ordered [tile][m (10)][re | im][NK]
 int orb_permute_weights(const float* Wre, const float* Wim, const float* bre, const float* bim, float* Wp, float* bp, int D, int L,
                         int NK, int ncol, cudaStream_t s);

@@ -630,6 +630,51 @@ int envelope_table(const float* x, const double* normfac, const float* bre, cons
   return (int)cudaGetLastError();
 }
 
+// Value-only form of the table: per electron [L] complex envelope values (times *unscale) followed by [N K] complex bias
+// products.  One warp per electron (the envelope of orbital_value_kernel).
+__global__ void __launch_bounds__(256)
+envelope_value_table_kernel(const float* __restrict__ x, const double* __restrict__ normfac, const float* __restrict__ bre,
+                            const float* __restrict__ bim, const float* __restrict__ unscale, float* __restrict__ tab, int64_t rows,
+                            TailDims dm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int L = dm.L, NK = dm.N * dm.K, twoQ = dm.twoQ;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  cplx* env = reinterpret_cast<cplx*>(smraw) + warp * L;
+  const int64_t bi = (int64_t)blockIdx.x * 8 + warp;
+  if (bi >= rows) return;  // whole warps leave; only __syncwarp is used below
+  const double phi = (double)x[bi * 2 + 1];
+  double sh = 0.0, ch = 0.0;
+  if (lane == 0) sincos(0.5 * (double)x[bi * 2], &sh, &ch);
+  sh = __shfl_sync(0xffffffffu, sh, 0);
+  ch = __shfl_sync(0xffffffffu, ch, 0);
+  const float us = unscale ? __ldg(unscale) : 1.f;
+  float* dst = tab + bi * (int64_t)(2 * (L + NK));
+  for (int m = lane; m < L; m += 32) {
+    const double mag = normfac[m] * dpow_int(ch, m) * dpow_int(sh, twoQ - m);
+    double psi = (double)(2 * m - twoQ) * 0.5 * phi;
+    psi -= 6.283185307179586476925287 * rint(psi * 0.15915494309189533576888);
+    float sp, cp;
+    sincosf((float)psi, &sp, &cp);
+    const cplx e = make_float2((float)(mag * (double)cp), (float)(mag * (double)sp));
+    env[m] = e;
+    dst[2 * m] = e.x * us;
+    dst[2 * m + 1] = e.y * us;
+  }
+  __syncwarp();
+  for (int j = lane; j < NK; j += 32) {
+    cplx acc = cmake(0.f, 0.f);
+    for (int m = 0; m < L; ++m) acc = cfma(cmake(bre[m * NK + j], bim[m * NK + j]), env[m], acc);
+    dst[2 * L + 2 * j] = acc.x;
+    dst[2 * L + 2 * j + 1] = acc.y;
+  }
+}
+int envelope_value_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
+                         int64_t B, TailDims d, cudaStream_t s) {
+  const int64_t rows = B * d.N;
+  envelope_value_table_kernel<<<(unsigned)((rows + 7) / 8), 256, 8 * d.L * sizeof(cplx), s>>>(x, normfac, bre, bim, unscale, tab, rows, d);
+  return (int)cudaGetLastError();
+}
+
 // Orbital-projection kernels [D][L N] (real part, imaginary part) and biases -> ONE fp32 matrix [D][ncol] and bias [ncol]
 // whose columns are ordered for the fused envelope contraction: tile t (256 columns) holds the orbitals m = 10 t .. 10 t + 9,
 // each as 24 columns [re(m, 0..11) | im(m, 0..11)]; the remaining columns of a tile are zero.
