@@ -399,9 +399,29 @@ extern "C" int dh_workspace_bytes(const dh_plan* p, int op, int64_t B, size_t* b
 }
 
 // Runs the network body + tail for Bc walkers whose coordinates are x; fills w.ld / outputs.
+// mv (value-only passes): the pass evaluates a Metropolis move of these walkers -- x is then the OUTPUT buffer of the proposal
+// drawn from mv->x1 and the walkers' accept / select step runs at the end (both inside the pass's first / last kernel where
+// the fused forms apply, as launches of their own otherwise).
 int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, bool jets, const FwdWs& w,
-                  FinalizeArgs fa, cudaStream_t s) {
+                  FinalizeArgs fa, cudaStream_t s, const MoveChunk* mv) {
   const int N = p->N, D = p->D;
+  if (mv && jets) return DH_E_BADARG;
+  // value-only passes on the tensor-core path: proposal, features, both first-layer maps and the envelope table are ONE launch
+  const bool vprologue = !jets && !p->laughlin && p->gemm_impl == 1 && p->nl > 0;
+  const bool vtail = !jets && N <= 16 && w.Minv == nullptr;  // log-determinants (+ accept) inside the finalize launch
+  if (mv && !vprologue) {
+    ProfScope ps(p, PC_MCMC, 0, s);
+    int rcp = mcmc_propose_dev(mv->x1, const_cast<float*>(x), Bc, N, mv->dv, mv->walker0, s);
+    if (rcp) return rcp;
+  }
+  auto move_tail = [&](FinalizeArgs& f) {
+    if (mv && vtail) { f.mv_x1 = mv->x1; f.mv_lp1 = mv->lp1; f.mv_dv = mv->dv; f.mv_walker0 = mv->walker0; }
+  };
+  auto move_accept = [&]() -> int {  // separate accept launch when the fused tail does not apply
+    if (!mv || vtail) return 0;
+    ProfScope ps(p, PC_MCMC, 0, s);
+    return mcmc_accept_dev(mv->x1, x, mv->lp1, fa.out_logpsi, 2, Bc, N, mv->dv, mv->walker0, s);
+  };
   const int R = jets ? 2 * N + 8 : 1;
   const int64_t rows = Bc * N * R;
   NetDims nd{N, R, D, p->H, p->hd, p->cfg.n_up};
@@ -413,9 +433,11 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     tl.lskip = p->lskip;
     tl.qp = p->lqp;
     tl.qp_a = p->lqp_a;
-    ProfScope pst(p, PC_TAIL, 0, s, 3);
+    ProfScope pst(p, PC_TAIL, 0, s, vtail ? 2 : 3);
     if ((rc = laughlin_orbital_jets(x, p->d_normfac, w.Mj, Bc, tl, s))) return rc;
-    if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, tl, s))) return rc;
+    if (vtail) fa.Mj_value = w.Mj;
+    else if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, tl, s))) return rc;
+    move_tail(fa);
     fa.ld = w.ld;
     fa.x = x;
     fa.ee_par = nullptr;
@@ -425,20 +447,43 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     fa.interaction_strength = p->cfg.interaction_strength;
     fa.interaction_type = p->cfg.interaction_type;
     fa.lpjet = jets ? w.lpjet : nullptr;
-    return finalize(fa, Bc, tl, s);
+    if ((rc = finalize(fa, Bc, tl, s))) return rc;
+    return move_accept();
   }
   // jets on the tensor-core path: Dense_0's output has 10 non-zero jet rows per electron; it is written in that
   // compressed form (into t1, which is free until the second Dense of the layer) and expanded by the first LayerNorm
   const bool h0_comp = jets && p->gemm_impl == 1 && p->nl > 0;
-  { ProfScope ps(p, PC_OTHER, 0, s);
-    if ((rc = features_linear(x, P + p->off_W0, nullptr, h0_comp ? w.t1 : w.h, D, Bc, nd, h0_comp ? 1 : 0, s))) return rc; }
+  const bool orb_epi = p->orb_fuse && (!jets || rows % 128 == 0);  // envelope contraction as the orbital projection's epilogue
+  if (vprologue) {
+    ProfScope ps(p, PC_OTHER, 0, s);
+    const dh_plan::Slot& q = p->slots[SL_QKV];
+    ValuePrologue vp;
+    memset(&vp, 0, sizeof(vp));
+    vp.x = mv ? mv->x1 : x;
+    vp.x_new = mv ? const_cast<float*>(x) : nullptr;
+    vp.dv = mv ? mv->dv : nullptr;
+    vp.walker0 = mv ? mv->walker0 : 0;
+    vp.W0 = P + p->off_W0; vp.h = w.h; vp.n0 = D;
+    vp.W1 = p->prep + p->w0qkv; vp.b1 = p->prep + q.bias; vp.q = w.qkv; vp.n1 = 3 * D;
+    if (orb_epi) {
+      const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
+      vp.normfac = p->d_normfac; vp.bre = orbB(p, P, 0); vp.bim = orbB(p, P, 1); vp.unscale = p->prep + sl.scale + 1;
+      vp.tab = w.cbuf; vp.L = p->L; vp.NK = N * p->K; vp.twoQ = p->twoQ;
+    }
+    if ((rc = value_prologue(vp, Bc * N, N, p->cfg.n_up, s))) return rc;
+  } else {
+    ProfScope ps(p, PC_OTHER, 0, s);
+    if ((rc = features_linear(x, P + p->off_W0, nullptr, h0_comp ? w.t1 : w.h, D, Bc, nd, h0_comp ? 1 : 0, s))) return rc;
+  }
   // jet passes with fp16 pieces: every tensor that is the left operand of a contraction (att, h) lives as fp16
   // hi / lo planes in its buffer -- written so by the attention and LayerNorm kernels, read back as hi + lo by the
   // next LayerNorm's residual -- and the contraction takes its operand tiles straight from them by TMA
   const bool pl = jets && p->a_planes;
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
-    if (l == 0 && p->gemm_impl == 1) {
+    if (l == 0 && vprologue) {
+      // q|k|v of the first layer came with the prologue
+    } else if (l == 0 && p->gemm_impl == 1) {
       // h = feat @ W0 is linear in the features: q|k|v = feat @ (W0 Wqkv) + b, a 4-deep contraction
       ProfScope ps(p, PC_OTHER, 0, s);
       const dh_plan::Slot& q = p->slots[SL_QKV];
@@ -474,15 +519,15 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     { ProfScope ps(p, PC_LAYERNORM, 0, s);
       if ((rc = residual_layernorm_ex(w.h, w.t1, P + o.ln1_s, P + o.ln1_b, w.h, Bc, nd, 1, 0, pl ? 1 : 0, pl ? 1 : 0, s))) return rc; }
   }
-  if (p->orb_fuse && (!jets || rows % 128 == 0)) {
+  if (orb_epi) {
     // The envelope contraction (blocks.py:59-70) is the EPILOGUE of the orbital projection (blocks.py:28-35): the per-electron
     // envelope values (jet passes: jets) go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the
     // contraction reads its coefficients out of tensor memory and writes the orbital matrices -- c[rows][2 L N] never exists in HBM
     const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
-    { ProfScope pse(p, PC_TAIL, 0, s);
-      if (jets) rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
-      else rc = envelope_value_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
-      if (rc) return rc; }
+    if (jets) {  // (value-only passes: the table came with the prologue)
+      ProfScope pse(p, PC_TAIL, 0, s);
+      if ((rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s))) return rc;
+    }
     ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * p->orbN * p->D, s);
     TcGemm g;
     g.A = w.h; g.lda = p->D; g.Wt_hi = p->prep + sl.hi; g.Wt_lo = p->prep + sl.lo; g.ldw = p->D;
@@ -496,8 +541,10 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     ProfScope psc(p, PC_TAIL, 0, s);
     if ((rc = orbital_contract(w.cbuf, x, p->d_normfac, w.Mj, Bc, td, s))) return rc;
   }
-  ProfScope pst(p, PC_TAIL, 0, s, 2);
-  if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;
+  ProfScope pst(p, PC_TAIL, 0, s, vtail ? 1 : 2);
+  if (vtail) fa.Mj_value = w.Mj;
+  else if ((rc = logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s))) return rc;
+  move_tail(fa);
   fa.ld = w.ld;
   fa.x = x;
   fa.ee_par = p->ee_par >= 0 ? P + p->ee_par : nullptr;
@@ -507,7 +554,8 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   fa.interaction_strength = p->cfg.interaction_strength;
   fa.interaction_type = p->cfg.interaction_type;
   fa.lpjet = jets ? w.lpjet : nullptr;
-  return finalize(fa, Bc, td, s);
+  if ((rc = finalize(fa, Bc, td, s))) return rc;
+  return move_accept();
 }
 
 static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
@@ -687,9 +735,11 @@ extern "C" int dh_plan_set_auto_prepare(dh_plan* p, int32_t on) {
   return 0;
 }
 
+// mv: the (value-only) pass evaluates a Metropolis move -- x receives the proposal drawn from mv->x1, and mv->x1 / mv->lp1 are
+// updated by the accept step (forward_chunk); walker0 is ignored on input (set per chunk).
 static int run_forward(dh_plan* p, const float* params, const float* x, int64_t B, bool jets, float* out_el,
                        float* out_kin, float* out_pot, float* out_lz, float* out_lz2, float* out_l2,
-                       float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s) {
+                       float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s, const MoveChunk* mv = nullptr) {
   if (!p || B < 0) return DH_E_BADARG;
   if (B == 0) return 0;
   if ((!params && p->nparams > 0) || !x) return DH_E_BADARG;
@@ -729,7 +779,9 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
     fa.out_lz2 = out_lz2 ? out_lz2 + b0 : nullptr;
     fa.out_l2 = out_l2 ? out_l2 + b0 : nullptr;
     const bool odd = dual && (k & 1);
-    rc = forward_chunk(p, params, x + b0 * p->N * 2, Bc, jets, odd ? w2 : w, fa, odd ? p->side_stream : s);
+    MoveChunk mc;
+    if (mv) mc = MoveChunk{mv->x1 + b0 * p->N * 2, mv->lp1 + b0, mv->dv, b0};
+    rc = forward_chunk(p, params, x + b0 * p->N * 2, Bc, jets, odd ? w2 : w, fa, odd ? p->side_stream : s, mv ? &mc : nullptr);
   }
   if (dual) {  // join even after an error, so the side stream never outlives the call
     cudaError_t e = cudaEventRecord(p->ev_join, p->side_stream);
@@ -816,6 +868,7 @@ static int mcmc_sweep_impl(dh_plan* p, const float* params, float* x, int64_t B,
     const float* Pg = p->laughlin ? params : p->raw_params;
     if (!p->laughlin) DH_CHECK(cudaMemcpyAsync(p->raw_params, params, p->nparams * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (!dev_args && (rc = mcmc_dev_init(p->d_mcmc, seed, offset, subsequence0, width, s))) return rc;
+    const MoveChunk move{x, mw.lp1, p->d_mcmc, 0};  // proposal and accept / select run inside the pass (forward_chunk)
     dh_plan::MoveGraph* mg = nullptr;
     const bool want_graph = steps >= 2 && !p->prof_on && p->graphs_ok && graphs_env;
     if (want_graph)
@@ -824,15 +877,13 @@ static int mcmc_sweep_impl(dh_plan* p, const float* params, float* x, int64_t B,
       cudaGraph_t graph = nullptr;
       const long long l0 = p->launches;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        rc = mcmc_propose_dev(x, mw.x2, B, p->N, p->d_mcmc, s);
-        if (!rc) rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s);
-        if (!rc) rc = mcmc_accept_dev(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, p->d_mcmc, s);
+        rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s, &move);
         if (!rc) rc = mcmc_dev_advance(p->d_mcmc, s);
         const cudaError_t ce = cudaStreamEndCapture(s, &graph);
         cudaGraphExec_t exec = nullptr;
         if (!rc && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
           if (p->move_graphs.size() >= 4) { cudaGraphExecDestroy(p->move_graphs.front().exec); p->move_graphs.erase(p->move_graphs.begin()); }
-          p->move_graphs.push_back({x, ws, B, exec, p->launches - l0 + 2});
+          p->move_graphs.push_back({x, ws, B, exec, p->launches - l0 + 1});
           mg = &p->move_graphs.back();
         } else {
           p->graphs_ok = 0;
@@ -850,10 +901,8 @@ static int mcmc_sweep_impl(dh_plan* p, const float* params, float* x, int64_t B,
       p->launches += mg->launches * steps;
     } else if (dev_args) {  // no graph (one move, profiling, or capture refused): the same kernels launched one by one
       for (int st = 0; st < steps; ++st) {
-        { ProfScope ps(p, PC_MCMC, 0, s); if ((rc = mcmc_propose_dev(x, mw.x2, B, p->N, p->d_mcmc, s))) return rc; }
-        if ((rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s))) return rc;
+        if ((rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s, &move))) return rc;
         { ProfScope ps(p, PC_MCMC, 0, s);
-          if ((rc = mcmc_accept_dev(x, mw.x2, mw.lp1, mw.logpsi2, 2, B, p->N, p->d_mcmc, s))) return rc;
           if ((rc = mcmc_dev_advance(p->d_mcmc, s))) return rc; }
       }
     }

@@ -139,4 +139,55 @@ __host__ __device__ inline float u01(uint32_t r) { return (r >> 8) * (1.0f / 167
 // uniform in (0, 1] for Box-Muller
 __host__ __device__ inline float u01_open0(uint32_t r) { return ((r >> 8) + 1) * (1.0f / 16777216.0f); }
 
+constexpr float kTwoPi = 6.283185307179586f;
+
+// The proposal draws of electron i of (global) walker `subseq` in move `offset`: a standard normal and a uniform in [0, 1)
+// (Philox addressing: mcmc_kernels.cu).
+__device__ inline void propose_draws(uint64_t seed, uint64_t offset, uint64_t subseq, int i, float& nrm, float& uph) {
+  Philox ph(seed);
+  const uint4 r = ph(offset * 64 + (uint64_t)i, subseq);
+  const float u1 = u01_open0(r.x), u2 = u01(r.y);
+  float s_, c_;
+  sincosf(kTwoPi * u2, &s_, &c_);
+  nrm = sqrtf(-2.f * logf(u1)) * c_;
+  uph = u01(r.z);
+}
+// sph_sampling (mcmc.py:67-102): the point at polar angle atan(nrm width) / azimuth 2 pi uph around the north pole, carried
+// to the frame of (theta, phi) by R_z(phi) R_y(theta).
+__device__ inline void propose_point(float theta, float phi, float nrm, float uph, float width, float& th2, float& ph2) {
+  const float theta_p = atanf(nrm * width);
+  const float phi_p = uph * kTwoPi;
+  float stp, ctp, spp, cpp, st, ct, sp, cp;
+  sincosf(theta_p, &stp, &ctp);
+  sincosf(phi_p, &spp, &cpp);
+  sincosf(theta, &st, &ct);
+  sincosf(phi, &sp, &cp);
+  const float xp = stp * cpp, yp = stp * spp, zp = ctp;
+  const float X = ct * xp + st * zp;
+  const float Y = yp;
+  const float Z = -st * xp + ct * zp;
+  const float x2v = cp * X - sp * Y;
+  const float y2v = sp * X + cp * Y;
+  const float z2v = Z;
+  th2 = acosf(fminf(fmaxf(z2v, -1.f), 1.f));
+  const float sgn = (y2v > 0.f) ? 1.f : ((y2v < 0.f) ? -1.f : 0.f);
+  ph2 = sgn * acosf(fminf(fmaxf(x2v / sinf(th2), -1.f), 1.f));
+}
+// log of the accept draw of (global) walker `subseq` in move `offset` (one rounding: oracle.mcmc.log_uniform)
+__device__ inline float accept_log_uniform(uint64_t seed, uint64_t offset, uint64_t subseq) {
+  Philox ph(seed);
+  const float u = u01(ph(offset * 64 + 63, subseq).x);
+  return (float)log((double)u);
+}
+
+__device__ inline double dpow_int(double z, int e) {
+  double r = 1.0;
+  while (e) {
+    if (e & 1) r *= z;
+    z *= z;
+    e >>= 1;
+  }
+  return r;
+}
+
 }  // namespace dh

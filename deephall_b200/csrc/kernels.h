@@ -130,6 +130,16 @@ struct FinalizeArgs {
   float* out_kin;        // [B] complex
   float* out_pot, *out_lz, *out_lz2, *out_l2;  // [B]
   float* lpjet;          // optional [B][R] complex debug copy of the log psi jets
+  // value-only passes (R = 1, N <= 16): the orbital matrices [B][K][N][N] complex -- the warp takes the log-determinants
+  // itself (no separate launch, `ld` unused)
+  const float* Mj_value;
+  // Metropolis move evaluated by this pass (value-only): accept / select (mcmc.py:56-62) in the same warp -- the "accept ->
+  // forward epilogue" fusion.  x = the proposal; mv_x1 / mv_lp1 = current configuration / log-probability of the chunk's
+  // walkers, updated in place; mv_walker0 = the chunk's first walker in the rank's batch (Philox subsequence).
+  float* mv_x1;
+  float* mv_lp1;
+  struct McmcDev* mv_dv;
+  int64_t mv_walker0;
 };
 int finalize(FinalizeArgs a, int64_t B, TailDims d, cudaStream_t s);
 // sparse orbitals (blocks.py:52-62).  W8 [D][8][NK], b8 [8][NK], Wl [8][L], bl [L] (added when add_bl != 0: the real
@@ -162,9 +172,23 @@ struct McmcDev { unsigned long long seed, offset, subseq0, naccept; float width;
 int mcmc_dev_init(McmcDev* dv, uint64_t seed, uint64_t offset, uint64_t subseq0, float width, cudaStream_t s);
 int mcmc_dev_init_from(McmcDev* dv, const unsigned long long* key, const float* width, uint64_t subseq0, cudaStream_t s);
 int mcmc_dev_advance(McmcDev* dv, cudaStream_t s);
-int mcmc_propose_dev(const float* x1, float* x2, int64_t B, int N, const McmcDev* dv, cudaStream_t s);
+// walker0: index of x1's first walker in the rank's batch (its Philox subsequence is dv->subseq0 + walker0 + b)
+int mcmc_propose_dev(const float* x1, float* x2, int64_t B, int N, const McmcDev* dv, int64_t walker0, cudaStream_t s);
 int mcmc_accept_dev(float* x1, const float* x2, float* lp1, const float* lp2c, int lp2_stride, int64_t B, int N, McmcDev* dv,
-                    cudaStream_t s);
+                    int64_t walker0, cudaStream_t s);
+
+// ---- value_path.cu: the coordinate-only prologue of a value-only pass in one launch
+struct ValuePrologue {
+  const float* x;        // [rows][2] coordinates (a move: the CURRENT configuration)
+  float* x_new;          // a move: the proposal is written here and the pass evaluates it; else nullptr
+  const McmcDev* dv;     // move arguments (device block), needed with x_new
+  int64_t walker0;       // index of the first walker in the rank's batch (Philox subsequence)
+  const float* W0; float* h; int n0;                     // first map [4][n0] (no bias) -> h [rows][n0]
+  const float* W1; const float* b1; float* q; int n1;    // second map [4][n1] + bias -> q [rows][n1]; W1 = nullptr: none
+  // envelope table of the fused orbital epilogue [rows][2 (L + NK)]; tab = nullptr: none
+  const double* normfac; const float* bre; const float* bim; const float* unscale; float* tab; int L, NK, twoQ;
+};
+int value_prologue(const ValuePrologue& a, int64_t rows, int N, int n_up, cudaStream_t s);
 
 // ---- vjp_kernels.cu
 int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* x, const double* normfac,

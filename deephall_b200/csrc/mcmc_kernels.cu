@@ -9,7 +9,6 @@
 
 namespace dh {
 
-constexpr float kTwoPi = 6.283185307179586f;
 
 // Device-resident arguments of a Metropolis move (McmcDev, kernels.h): when a kernel is given this block it reads the
 // Philox key / offset / width from it instead of from its launch arguments, so ONE captured CUDA graph of a move
@@ -42,7 +41,7 @@ __global__ void mcmc_propose_kernel(const float* __restrict__ x1, float* __restr
                                     const float* __restrict__ randoms, const McmcDev* __restrict__ dv) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
-  if (dv != nullptr) { seed = dv->seed; offset = dv->offset; subseq0 = dv->subseq0; width = dv->width; }
+  if (dv != nullptr) { seed = dv->seed; offset = dv->offset; subseq0 += dv->subseq0; width = dv->width; }
   const int64_t b = t / N;
   const int i = (int)(t % N);
   float nrm, uph;
@@ -50,33 +49,10 @@ __global__ void mcmc_propose_kernel(const float* __restrict__ x1, float* __restr
     nrm = randoms[b * (2 * N + 1) + i];
     uph = randoms[b * (2 * N + 1) + N + i];
   } else {
-    Philox ph(seed);
-    uint4 r = ph(offset * 64 + (uint64_t)i, subseq0 + (uint64_t)b);
-    float u1 = u01_open0(r.x), u2 = u01(r.y);
-    float s_, c_;
-    sincosf(kTwoPi * u2, &s_, &c_);
-    nrm = sqrtf(-2.f * logf(u1)) * c_;
-    uph = u01(r.z);
+    propose_draws(seed, offset, subseq0 + (uint64_t)b, i, nrm, uph);
   }
-  const float theta = x1[t * 2], phi = x1[t * 2 + 1];
-  const float theta_p = atanf(nrm * width);
-  const float phi_p = uph * kTwoPi;
-  float stp, ctp, spp, cpp, st, ct, sp, cp;
-  sincosf(theta_p, &stp, &ctp);
-  sincosf(phi_p, &spp, &cpp);
-  sincosf(theta, &st, &ct);
-  sincosf(phi, &sp, &cp);
-  const float xp = stp * cpp, yp = stp * spp, zp = ctp;
-  // R_z(phi) R_y(theta) (xp, yp, zp)
-  const float X = ct * xp + st * zp;
-  const float Y = yp;
-  const float Z = -st * xp + ct * zp;
-  const float x2v = cp * X - sp * Y;
-  const float y2v = sp * X + cp * Y;
-  const float z2v = Z;
-  const float th2 = acosf(fminf(fmaxf(z2v, -1.f), 1.f));
-  const float sgn = (y2v > 0.f) ? 1.f : ((y2v < 0.f) ? -1.f : 0.f);
-  const float ph2 = sgn * acosf(fminf(fmaxf(x2v / sinf(th2), -1.f), 1.f));
+  float th2, ph2;
+  propose_point(x1[t * 2], x1[t * 2 + 1], nrm, uph, width, th2, ph2);
   x2[t * 2] = th2;
   x2[t * 2 + 1] = ph2;
 }
@@ -88,9 +64,9 @@ int mcmc_propose(const float* x1, float* x2, int64_t B, int N, float width, uint
                                                                       subseq0, randoms, nullptr);
   return (int)cudaGetLastError();
 }
-int mcmc_propose_dev(const float* x1, float* x2, int64_t B, int N, const McmcDev* dv, cudaStream_t s) {
+int mcmc_propose_dev(const float* x1, float* x2, int64_t B, int N, const McmcDev* dv, int64_t walker0, cudaStream_t s) {
   const int64_t total = B * N;
-  mcmc_propose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x1, x2, total, N, 0.f, 0, 0, 0, nullptr, dv);
+  mcmc_propose_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x1, x2, total, N, 0.f, 0, 0, (uint64_t)walker0, nullptr, dv);
   return (int)cudaGetLastError();
 }
 
@@ -102,15 +78,11 @@ __global__ void mcmc_accept_kernel(float* __restrict__ x1, const float* __restri
                                    unsigned long long* __restrict__ naccept, McmcDev* __restrict__ dv) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool acc = false;
-  if (dv != nullptr) { seed = dv->seed; offset = dv->offset; subseq0 = dv->subseq0; naccept = &dv->naccept; }
+  if (dv != nullptr) { seed = dv->seed; offset = dv->offset; subseq0 += dv->subseq0; naccept = &dv->naccept; }
   if (b < B) {
-    float u;
-    if (randoms != nullptr) u = randoms[b * (2 * N + 1) + 2 * N];
-    else {
-      Philox ph(seed);
-      u = u01(ph(offset * 64 + 63, subseq0 + (uint64_t)b).x);
-    }
-    const float logu = (float)log((double)u);  // one rounding, same convention as oracle.mcmc.log_uniform
+    float logu;
+    if (randoms != nullptr) logu = (float)log((double)randoms[b * (2 * N + 1) + 2 * N]);  // one rounding, as oracle.mcmc.log_uniform
+    else logu = accept_log_uniform(seed, offset, subseq0 + (uint64_t)b);
     const float l2 = lp2_stride == 2 ? 2.0f * lp2c[b * 2] : lp2c[b];
     const float l1 = lp1[b];
     acc = (l2 - l1) > logu;  // NaN -> false (mcmc.py:59)
@@ -131,8 +103,8 @@ int mcmc_accept(float* x1, const float* x2, float* lp1, const float* lp2c, int l
   return (int)cudaGetLastError();
 }
 int mcmc_accept_dev(float* x1, const float* x2, float* lp1, const float* lp2c, int lp2_stride, int64_t B, int N, McmcDev* dv,
-                    cudaStream_t s) {
-  mcmc_accept_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(x1, x2, lp1, lp2c, lp2_stride, B, N, 0, 0, 0, nullptr, nullptr, dv);
+                    int64_t walker0, cudaStream_t s) {
+  mcmc_accept_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(x1, x2, lp1, lp2c, lp2_stride, B, N, 0, 0, (uint64_t)walker0, nullptr, nullptr, dv);
   return (int)cudaGetLastError();
 }
 

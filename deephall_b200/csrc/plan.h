@@ -216,6 +216,9 @@ enum { VS_D2 = 0, VS_D1 = 1, VS_O = 2, VS_QKV = 3, VS_PER_LAYER = 4 };
 // tcgen05 path: C[rows, Nout] (ldc) = A[rows, D] @ W_slot (+ bias on value rows).
 // a_planes: A is the fp16 hi / lo plane view of a [rows][D] buffer (common.cuh), written by the producing kernel.
 
+// A Metropolis move evaluated by a value-only pass (forward_chunk): current configuration / log-probability of the chunk's
+// walkers (both updated by the accept step), the device block of move arguments, the chunk's first walker in the rank's batch.
+struct MoveChunk { float* x1; float* lp1; McmcDev* dv; int64_t walker0; };
 struct LnArgs { const float* gamma; const float* beta; int tanh_mode; };  // fused value LayerNorm epilogue: C = LN(C + f(A W + b)) in place
 static inline int dense_tc(const dh_plan* p, const float* A, int slot, float* C, int64_t rows, int64_t ldc, int R,
                            cudaStream_t s, bool a_planes = false, const LnArgs* ln = nullptr) {

@@ -413,15 +413,6 @@ int laughlin_orbital_jets(const float* x, const double* ones, float* Mj, int64_t
 //   env[m] = sqrt(C(2Q,m)) cos^m(theta/2) sin^(2Q-m)(theta/2) e^{i (m - Q) phi}: magnitudes by repeated squaring
 //   in double (exponents reach 2Q), phase angle reduced in double and evaluated in fp32;
 //   M[i][j,kd] = sum_m c[m][j,kd] env[m] with lanes = (m-group, column), coalesced 4-byte loads.
-__device__ inline double dpow_int(double z, int e) {
-  double r = 1.0;
-  while (e) {
-    if (e & 1) r *= z;
-    z *= z;
-    e >>= 1;
-  }
-  return r;
-}
 
 __global__ void __launch_bounds__(256)
 orbital_value_kernel(const float* __restrict__ c, const float* __restrict__ x, const double* __restrict__ normfac,
@@ -1027,9 +1018,24 @@ finalize_kernel(FinalizeArgs a, int64_t B, TailDims dm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
   if (b >= B) return;
-  cplx* lp = reinterpret_cast<cplx*>(smraw) + (size_t)warp * (R + K);  // [R] log psi jets
-  cplx* wk = lp + R;                                                  // [K] determinant weights
+  cplx* lp = reinterpret_cast<cplx*>(smraw) + (size_t)warp * (R + 2 * K);  // [R] log psi jets
+  cplx* wk = lp + R;                                                      // [K] determinant weights
   const cplx* ld = reinterpret_cast<const cplx*>(a.ld) + b * K * R;
+  if (a.Mj_value != nullptr) {  // value-only pass: log-determinants of the K orbital matrices taken here (logdet_value_kernel's arithmetic)
+    cplx* lds = wk + K;
+    for (int k = 0; k < K; ++k) {
+      const cplx* M0 = reinterpret_cast<const cplx*>(a.Mj_value) + (b * K + k) * N * N;
+      cplx m[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) m[c] = (lane < N && c < N) ? M0[lane * N + c] : cmake(0.f, 0.f);
+      float la;
+      cplx ph;
+      warp_lu_regs(m, N, la, ph);
+      if (lane == 0) lds[k] = cmake(la, (ph.x == 0.f && ph.y == 0.f) ? 0.f : atan2f(ph.y, ph.x));
+    }
+    __syncwarp();
+    ld = lds;
+  }
   // ---- value: log sum_k exp(ld_k)
   float mx = -INFINITY;
   for (int k = 0; k < K; ++k) mx = fmaxf(mx, ld[k * R].x);
@@ -1057,6 +1063,21 @@ finalize_kernel(FinalizeArgs a, int64_t B, TailDims dm) {
   if (lane == 0 && a.out_logpsi) { a.out_logpsi[b * 2] = lp0.x; a.out_logpsi[b * 2 + 1] = lp0.y; }
   if (R == 1) {
     if (lane == 0 && a.out_pot) a.out_pot[b] = pot_raw * a.interaction_strength;
+    if (a.mv_x1 != nullptr) {  // Metropolis accept / select of this walker's move (mcmc_accept_kernel's arithmetic)
+      int acc = 0;
+      if (lane == 0) {
+        const float logu = accept_log_uniform(a.mv_dv->seed, a.mv_dv->offset, a.mv_dv->subseq0 + (uint64_t)(a.mv_walker0 + b));
+        const float l2 = 2.0f * lp0.x, l1 = a.mv_lp1[b];
+        acc = (l2 - l1) > logu ? 1 : 0;  // NaN -> false (mcmc.py:59)
+        if (acc) {
+          a.mv_lp1[b] = l2;
+          atomicAdd(&a.mv_dv->naccept, 1ull);
+        }
+      }
+      acc = __shfl_sync(0xffffffffu, acc, 0);
+      if (acc)
+        for (int q = lane; q < 2 * N; q += 32) a.mv_x1[b * 2 * N + q] = a.x[b * 2 * N + q];
+    }
     return;
   }
   Rows rw(N, true);
@@ -1144,7 +1165,9 @@ finalize_kernel(FinalizeArgs a, int64_t B, TailDims dm) {
 int finalize(FinalizeArgs a, int64_t B, TailDims d, cudaStream_t s) {
   if (d.N > 32) return -2;
   const int wpb = 4;
-  size_t smem = (size_t)wpb * (d.R + d.K) * sizeof(cplx);
+  if (a.Mj_value != nullptr && (d.R != 1 || d.N > 16)) return -2;
+  if (a.mv_x1 != nullptr && (d.R != 1 || !a.mv_lp1 || !a.mv_dv)) return -2;
+  size_t smem = (size_t)wpb * (d.R + 2 * d.K) * sizeof(cplx);
   finalize_kernel<<<(unsigned)((B + wpb - 1) / wpb), wpb * 32, smem, s>>>(a, B, d);
   return (int)cudaGetLastError();
 }
