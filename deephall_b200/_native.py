@@ -85,6 +85,10 @@ SIGNATURES = OrderedDict(
     dh_launch_count=(C.c_longlong, [_vp]),
     dh_kfac_layout=(C.c_int, [_vp, C.POINTER(dh_kfac_entry), C.POINTER(_i32), C.POINTER(_i64)]),
     dh_kfac_factors=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
+    dh_kfac_update_shape=(C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
+                                    C.POINTER(_i64)]),
+    dh_kfac_damped_factors=(C.c_int, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    dh_kfac_update=(C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, C.c_size_t, _vp]),
     dh_profile_begin=(C.c_int, [_vp, _i32]),
     dh_profile_end=(C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i32), C.POINTER(C.c_double)]),
     dh_pair_correlation=(C.c_int, [_vp, _i64, _i32, _i32, _i64, _vp, _vp, _vp]),
@@ -372,6 +376,49 @@ def _kfac_methods():
             out.append(d)
         return out, int(nf.value)
 
+    def kfac_update_shape(self):
+        """(n_small, dim_small, n_large, dim_large, n_blocks, gather_floats) of the KFAC update (dh_kfac_update_shape), or None
+        when the plan's factors are outside the native update's range (a factor with more than 1024 rows)."""
+        if not hasattr(self, "_kfu_shape"):
+            v = [C.c_int32(0) for _ in range(5)]
+            g = C.c_int64(0)
+            rc = self.lib.dh_kfac_update_shape(self.handle, *[C.byref(a) for a in v], C.byref(g))
+            if rc == -2:  # DH_E_UNSUPPORTED
+                self._kfu_shape = None
+            else:
+                _check(rc, "dh_kfac_update_shape")
+                self._kfu_shape = tuple(int(a.value) for a in v) + (int(g.value),)
+        return self._kfu_shape
+
+    def kfac_damped_factors(self, stats, dense0_xtx, weight, damping):
+        """-> (coef [n_blocks, 8], mats_small [n_small, d, d], mats_large [n_large, D, D]): the damped, trace-normalised
+        Kronecker factors of every dense block (dh_kfac_damped_factors)."""
+        ns, ds, nl, dl, nb, _ = self.kfac_update_shape()
+        _f32(stats, "stats"); _f32(dense0_xtx, "dense0_xtx")
+        dev = stats.device
+        coef = torch.empty((nb, 8), dtype=torch.float32, device=dev)
+        ms = torch.empty((ns, ds, ds), dtype=torch.float32, device=dev)
+        ml = torch.empty((nl, dl, dl), dtype=torch.float32, device=dev)
+        _check(self.lib.dh_kfac_damped_factors(self.handle, _ptr(stats), _ptr(dense0_xtx), float(weight), float(damping), _ptr(coef),
+                                               _ptr(ms) if ns else None, _ptr(ml) if nl else None, _stream()),
+               "dh_kfac_damped_factors")
+        return coef, ms, ml
+
+    def kfac_update(self, inv_small, inv_large, coef, stats, weight, damping, grads):
+        """Preconditioned gradient from the inverted damped factors (dh_kfac_update): flat f32 tensor like `grads`."""
+        ns, ds, nl, dl, nb, gf = self.kfac_update_shape()
+        _f32(grads, "grads"); _f32(stats, "stats"); _f32(coef, "coef")
+        if ns:
+            _f32(inv_small, "inv_small")
+        if nl:
+            _f32(inv_large, "inv_large")
+        out = torch.empty_like(grads)
+        ws = torch.empty(3 * gf + 4, dtype=torch.float32, device=grads.device)
+        _check(self.lib.dh_kfac_update(self.handle, _ptr(inv_small) if ns else None, _ptr(inv_large) if nl else None, _ptr(coef),
+                                       _ptr(stats), float(weight), float(damping), _ptr(grads), _ptr(out), _ptr(ws), ws.numel() * 4,
+                                       _stream()), "dh_kfac_update")
+        return out
+
     def kfac_factors(self, params, x):
         """Factor sums of the KFAC curvature blocks for the walkers x (dh_kfac_factors): flat f32 tensor."""
         self._prepare(params)
@@ -386,6 +433,9 @@ def _kfac_methods():
 
     Plan.kfac_layout = kfac_layout
     Plan.kfac_factors = kfac_factors
+    Plan.kfac_update_shape = kfac_update_shape
+    Plan.kfac_damped_factors = kfac_damped_factors
+    Plan.kfac_update = kfac_update
 
 
 _kfac_methods()

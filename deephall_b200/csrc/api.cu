@@ -345,6 +345,9 @@ extern "C" int dh_plan_destroy(dh_plan* p) {
     cudaFree(p->d_status);
   }
   for (auto& g : p->move_graphs) cudaGraphExecDestroy(g.exec);
+  if (p->kfu.d_blk) cudaFree(p->kfu.d_blk);
+  if (p->kfu.d_mat) cudaFree(p->kfu.d_mat);
+  if (p->kfu.d_diag) cudaFree(p->kfu.d_diag);
   if (p->d_mcmc) cudaFree(p->d_mcmc);
   if (p->raw_params) cudaFree(p->raw_params);
   if (p->d_normfac) cudaFree(p->d_normfac);
@@ -524,9 +527,11 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     // envelope values (jet passes: jets) go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the
     // contraction reads its coefficients out of tensor memory and writes the orbital matrices -- c[rows][2 L N] never exists in HBM
     const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
-    if (jets) {  // (value-only passes: the table came with the prologue)
+    if (jets || !vprologue) {  // (value-only passes: the table normally comes with the prologue)
       ProfScope pse(p, PC_TAIL, 0, s);
-      if ((rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s))) return rc;
+      if (jets) rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
+      else rc = envelope_value_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
+      if (rc) return rc;
     }
     ProfScope ps(p, PC_GEMM, 2.0 * (double)rows * p->orbN * p->D, s);
     TcGemm g;

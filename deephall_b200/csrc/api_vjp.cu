@@ -338,3 +338,109 @@ extern "C" int dh_kfac_factors(dh_plan* p, const float* P, const float* x, int64
   if (!P || !factors || B < 0 || (B > 0 && !x)) return DH_E_BADARG;
   return vjp_core(p, P, x, B, nullptr, nullptr, factors, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
+
+// --------------------------------------------------------------------------------- KFAC update (optimizers/kfac.py:202-219)
+// Factors up to KFU_SMALL rows form the "small" batch (inverted by 4-CTA clusters), the others the "large" one.
+static constexpr int KFU_SMALL = 288;
+
+static int kfac_update_tables(dh_plan* p) {
+  auto& u = p->kfu;
+  if (u.ready) return u.ready > 0 ? 0 : DH_E_UNSUPPORTED;
+  if (p->laughlin || p->sparse || p->kfac.empty()) { u.ready = -1; return DH_E_UNSUPPORTED; }
+  for (const auto& e : p->kfac)
+    if (e.kind == 0 && (e.in_dim + e.has_bias > 1024 || e.out_dim > 1024)) { u.ready = -1; return DH_E_UNSUPPORTED; }
+  for (const auto& e : p->kfac) {
+    if (e.kind != 0) { u.diag.push_back(KfDiagDesc{e.kernel_offset, e.diag_offset, e.size}); continue; }
+    const int blk = (int)u.blk.size();
+    KfBlkDesc b{e.kernel_offset, e.has_bias ? e.bias_offset : -1, e.xtx_offset, e.gtg_offset, u.gather_floats,
+                e.in_dim, e.out_dim, e.has_bias, e.rows_per_walker};
+    u.gather_floats += (int64_t)(e.in_dim + e.has_bias) * e.out_dim;
+    u.gather_floats = (u.gather_floats + 3) & ~(int64_t)3;  // 16-byte aligned operands for the contractions
+    u.blk.push_back(b);
+    KfMatDesc a{e.xtx_offset, e.has_bias ? e.xsum_offset : -1, 0, e.in_dim, e.in_dim + e.has_bias, 0, 0, blk, 0};
+    KfMatDesc g{e.gtg_offset, -1, 0, e.out_dim, e.out_dim, 0, 0, blk, 1};
+    u.mat.push_back(a);  // mat[2 blk] = A, mat[2 blk + 1] = G
+    u.mat.push_back(g);
+  }
+  for (auto& m : u.mat) {
+    m.cls = m.n > KFU_SMALL ? 1 : 0;
+    int& dim = m.cls ? u.dim_large : u.dim_small;
+    dim = m.n > dim ? m.n : dim;
+  }
+  u.dim_small = (u.dim_small + 3) & ~3;  // row strides the 16-byte loads of the contractions can use
+  u.dim_large = (u.dim_large + 3) & ~3;
+  for (auto& m : u.mat) {
+    int& cnt = m.cls ? u.n_large : u.n_small;
+    m.dim = m.cls ? u.dim_large : u.dim_small;
+    m.dst = (long long)cnt * m.dim * m.dim;
+    ++cnt;
+  }
+  auto up = [](const void* src, size_t bytes, void** dst) -> bool {
+    if (bytes == 0) { *dst = nullptr; return true; }
+    if (cudaMalloc(dst, bytes) != cudaSuccess) return false;
+    return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  };
+  if (!up(u.blk.data(), u.blk.size() * sizeof(KfBlkDesc), (void**)&u.d_blk) ||
+      !up(u.mat.data(), u.mat.size() * sizeof(KfMatDesc), (void**)&u.d_mat) ||
+      !up(u.diag.data(), u.diag.size() * sizeof(KfDiagDesc), (void**)&u.d_diag)) {
+    u.ready = -1;
+    return (int)cudaGetLastError();
+  }
+  u.ready = 1;
+  return 0;
+}
+
+extern "C" int dh_kfac_update_shape(dh_plan* p, int32_t* n_small, int32_t* dim_small, int32_t* n_large, int32_t* dim_large,
+                                    int32_t* n_blocks, int64_t* gather_floats) {
+  if (!p) return DH_E_BADARG;
+  int rc = kfac_update_tables(p);
+  if (rc) return rc;
+  if (n_small) *n_small = p->kfu.n_small;
+  if (dim_small) *dim_small = p->kfu.dim_small;
+  if (n_large) *n_large = p->kfu.n_large;
+  if (dim_large) *dim_large = p->kfu.dim_large;
+  if (n_blocks) *n_blocks = (int32_t)p->kfu.blk.size();
+  if (gather_floats) *gather_floats = p->kfu.gather_floats;
+  return 0;
+}
+
+extern "C" int dh_kfac_damped_factors(dh_plan* p, const float* stats, const float* dense0_xtx, float weight, float damping,
+                                      float* coef, float* mats_small, float* mats_large, void* stream) {
+  if (!p || !stats || !dense0_xtx || !coef || !(weight > 0.f)) return DH_E_BADARG;
+  int rc = kfac_update_tables(p);
+  if (rc) return rc;
+  const auto& u = p->kfu;
+  if ((u.n_small && !mats_small) || (u.n_large && !mats_large)) return DH_E_BADARG;
+  p->launches += 2;
+  return kfac_damped_factors(u.d_blk, (int)u.blk.size(), u.d_mat, (int)u.mat.size(), stats, dense0_xtx, weight, damping, coef,
+                             mats_small, mats_large, (cudaStream_t)stream);
+}
+
+extern "C" int dh_kfac_update(dh_plan* p, const float* inv_small, const float* inv_large, const float* coef, const float* stats,
+                              float weight, float damping, const float* grads, float* out, void* ws, size_t ws_bytes,
+                              void* stream) {
+  if (!p || !coef || !stats || !grads || !out || !(weight > 0.f)) return DH_E_BADARG;
+  int rc = kfac_update_tables(p);
+  if (rc) return rc;
+  const auto& u = p->kfu;
+  if ((u.n_small && !inv_small) || (u.n_large && !inv_large)) return DH_E_BADARG;
+  if (!ws || (reinterpret_cast<uintptr_t>(ws) & 15) || ws_bytes < (size_t)(3 * u.gather_floats) * sizeof(float)) return DH_E_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  float* V = static_cast<float*>(ws);
+  float* T = V + u.gather_floats;
+  float* U = T + u.gather_floats;
+  DH_CHECK(cudaMemsetAsync(out, 0, (size_t)p->nparams * sizeof(float), s));
+  if ((rc = kfac_gather(u.d_blk, (int)u.blk.size(), grads, V, s))) return rc;
+  for (size_t b = 0; b < u.blk.size(); ++b) {
+    const KfBlkDesc& bd = u.blk[b];
+    const KfMatDesc &ma = u.mat[2 * b], &mg = u.mat[2 * b + 1];
+    const float* Ai = (ma.cls ? inv_large : inv_small) + ma.dst;
+    const float* Gi = (mg.cls ? inv_large : inv_small) + mg.dst;
+    const int na = bd.din + bd.hb;
+    // T = A~^-1 V~ ; U = T G~^-1  (fp32 FMA contraction of the library)
+    if ((rc = gemm_simt(Ai, V + bd.v_off, nullptr, T + bd.v_off, na, bd.dout, na, ma.dim, 1, bd.dout, 1, bd.dout, 1, 0, 1, s))) return rc;
+    if ((rc = gemm_simt(T + bd.v_off, Gi, nullptr, U + bd.v_off, na, bd.dout, bd.dout, bd.dout, 1, mg.dim, 1, bd.dout, 1, 0, 1, s))) return rc;
+  }
+  p->launches += 3 + 2 * (long long)u.blk.size();
+  return kfac_scatter(u.d_blk, (int)u.blk.size(), u.d_diag, (int)u.diag.size(), U, coef, stats, weight, damping, grads, out, s);
+}

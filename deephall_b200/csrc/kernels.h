@@ -196,6 +196,25 @@ int tail_bwd(const float* cot, const float* ld, const float* Minv, const float* 
 int jastrow_bwd(const float* cot, const float* x, const float* ee_par, const float* ee_anti, float* g_eepar,
                 float* g_eeanti, float* sq_eepar, float* sq_eeanti, int64_t B, int N, int n_up, cudaStream_t s);
 int spd_inverse_batched(float* mats, int n, int batch, cudaStream_t s);
+
+// ---- kfac_kernels.cu: the KFAC update from the moving-average statistics (descriptor tables: plan.h / api_vjp.cu)
+struct KfBlkDesc {   // one dense curvature block
+  long long ko, bo;        // kernel / bias offset in the parameter vector (bo < 0: no bias)
+  long long xtx, gtg;      // factor-vector offsets of sum x x^T (< 0: Dense_0, the caller's 4 x 4 matrix) and sum g g^T
+  long long v_off;         // float offset of the block's [din + hb][dout] gradient / update in the gather buffers
+  int din, dout, hb, npw;
+};
+struct KfMatDesc {   // one damped Kronecker factor
+  long long src, xsum;     // factor-vector offsets of the core matrix (< 0: Dense_0's) and of sum x (bias blocks)
+  long long dst;           // float offset inside its batch (slot * dim * dim)
+  int n_core, n, dim, cls, blk, is_g;   // core size, size with the bias row, padded size, batch (0 small / 1 large), block
+};
+struct KfDiagDesc { long long ko, o, n; };   // diagonal block: parameter offset, factor-vector offset, size
+int kfac_damped_factors(const KfBlkDesc* bd, int nblk, const KfMatDesc* md, int nmat, const float* stats, const float* xtx0,
+                        float weight, float damping, float* coef, float* batch_s, float* batch_l, cudaStream_t s);
+int kfac_gather(const KfBlkDesc* bd, int nblk, const float* grads, float* V, cudaStream_t s);
+int kfac_scatter(const KfBlkDesc* bd, int nblk, const KfDiagDesc* dd, int ndiag, const float* U, const float* coef,
+                 const float* stats, float weight, float damping, const float* grads, float* out, cudaStream_t s);
 // KFAC factor pass (dh_kfac_factors)
 int fill_unit_cot(float* cot, int64_t n, cudaStream_t s);
 int mask_rows_by_spin(const float* src, float* dst, int64_t rows, int D, int N, int n_up, int sb, cudaStream_t s);

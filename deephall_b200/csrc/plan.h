@@ -51,6 +51,18 @@ struct dh_plan {
   std::vector<KfLayer> kf_layer;
   int kf_dense0, kf_orb[4], kf_eepar, kf_eeanti;
   int64_t kfac_floats;
+  // KFAC update tables (dh_kfac_update_shape builds them on first use; device copies freed with the plan)
+  struct KfUpdate {
+    int ready = 0;  // 0 not built, 1 built, -1 unsupported (a factor with more than 1024 rows)
+    std::vector<KfBlkDesc> blk;
+    std::vector<KfMatDesc> mat;
+    std::vector<KfDiagDesc> diag;
+    KfBlkDesc* d_blk = nullptr;
+    KfMatDesc* d_mat = nullptr;
+    KfDiagDesc* d_diag = nullptr;
+    int n_small = 0, dim_small = 0, n_large = 0, dim_large = 0;
+    int64_t gather_floats = 0;
+  } kfu;
   double* d_normfac;
   int gemm_impl;  // 0 = SIMT fp32 FMA, 1 = tcgen05 (two-piece operand split)
   int tc_merged;  // tcgen05 path: 1 = one double-buffered accumulator per tile, 0 = main + correction accumulators

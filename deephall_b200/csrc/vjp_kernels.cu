@@ -238,20 +238,23 @@ spd_inverse_kernel(float* __restrict__ mats, int n) {
 //           barrier.cluster, then every CTA updates its own rows (it holds its own entries of the old column k).
 // One barrier per step is enough: the buffer of step k is rewritten at step k + 2, after barrier k + 1, which a CTA
 // only passes once every CTA has finished the update of step k.
-constexpr int SPD_CL = 8;
+constexpr int SPD_CL = 8;        // matrices of more than SPD_SMALL rows
+constexpr int SPD_CL_SMALL = 4;  // up to SPD_SMALL rows: four CTAs hold the matrix, twice as many matrices per wave
+constexpr int SPD_SMALL = 288;
 __device__ __forceinline__ uint32_t spd_mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
-__global__ void __cluster_dims__(SPD_CL, 1, 1) __launch_bounds__(1024, 1)
+template <int CL>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(1024, 1)
 spd_inverse_cluster_kernel(float* __restrict__ mats, int n, int rpc, int ldn) {
   extern __shared__ __align__(16) float spd_smem[];
   float* rows = spd_smem;                 // [rpc][ldn]  this CTA's rows
   float* rowbuf = spd_smem + rpc * ldn;   // [2][ldn]    pivot row of the current / next step
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  float* a = mats + (size_t)(blockIdx.x / SPD_CL) * n * n;
+  float* a = mats + (size_t)(blockIdx.x / CL) * n * n;
   const int r0 = (int)rank * rpc, nr = max(0, min(rpc, n - r0));
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   for (int i = warp; i < nr; i += nw)
@@ -266,7 +269,7 @@ spd_inverse_cluster_kernel(float* __restrict__ mats, int n, int rpc, int ldn) {
         const float v = src[j];
         const uint32_t dst = rowbuf_s + (uint32_t)(((k & 1) * ldn + j) * 4);
 #pragma unroll
-        for (int c = 0; c < SPD_CL; ++c) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(spd_mapa(dst, c)), "f"(v) : "memory");
+        for (int c = 0; c < CL; ++c) asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(spd_mapa(dst, c)), "f"(v) : "memory");
       }
     }
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -292,21 +295,28 @@ spd_inverse_cluster_kernel(float* __restrict__ mats, int n, int rpc, int ldn) {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+template <int CL>
+static int spd_inverse_cluster_launch(float* mats, int n, int batch, cudaStream_t s, bool* fits) {
+  const int rpc = (n + CL - 1) / CL, ldn = (n + 3) & ~3;
+  const size_t smem = (size_t)(rpc + 2) * ldn * sizeof(float);
+  *fits = smem <= 220 * 1024;
+  if (!*fits) return 0;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(spd_inverse_cluster_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr = smem;
+  }
+  spd_inverse_cluster_kernel<CL><<<batch * CL, 1024, smem, s>>>(mats, n, rpc, ldn);
+  return (int)cudaGetLastError();
+}
 int spd_inverse_batched(float* mats, int n, int batch, cudaStream_t s) {
   if (n < 1 || n > 1024 || batch < 0) return -2;
   if (batch == 0) return 0;
-  const int rpc = (n + SPD_CL - 1) / SPD_CL, ldn = (n + 3) & ~3;
-  const size_t smem = (size_t)(rpc + 2) * ldn * sizeof(float);
-  if (smem <= 220 * 1024) {
-    static size_t attr = 0;
-    if (smem > attr) {
-      cudaError_t e = cudaFuncSetAttribute(spd_inverse_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return (int)e;
-      attr = smem;
-    }
-    spd_inverse_cluster_kernel<<<batch * SPD_CL, 1024, smem, s>>>(mats, n, rpc, ldn);
-    return (int)cudaGetLastError();
-  }
+  bool fits = false;
+  int rc = n <= SPD_SMALL ? spd_inverse_cluster_launch<SPD_CL_SMALL>(mats, n, batch, s, &fits)
+                          : spd_inverse_cluster_launch<SPD_CL>(mats, n, batch, s, &fits);
+  if (fits) return rc;
   spd_inverse_kernel<<<batch, 1024, 0, s>>>(mats, n);
   return (int)cudaGetLastError();
 }

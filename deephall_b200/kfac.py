@@ -85,6 +85,26 @@ def _batched_inverses(groups: dict) -> dict:
     return out
 
 
+def _inverse_batch(batch: torch.Tensor) -> torch.Tensor:
+    """In-place inverses of a (count, n, n) batch of SPD matrices by dh_spd_inverse; with more than one rank the matrices are
+    dealt out round-robin -- every rank inverts 1/world of them -- and exchanged with one all-gather (the statistics
+    they come from are identical on all ranks)."""
+    world, rank = constants.world_size(), constants.rank()
+    count, n = batch.shape[0], batch.shape[1]
+    if count == 0:
+        return batch
+    if world == 1:
+        return _native.spd_inverse(batch, inplace=True)
+    per = (count + world - 1) // world
+    mine = torch.eye(n, dtype=torch.float32, device=batch.device).repeat(per, 1, 1)
+    own = batch[rank::world]
+    mine[: own.shape[0]] = own
+    _native.spd_inverse(mine, inplace=True)
+    gathered = torch.empty((world, per, n, n), dtype=torch.float32, device=batch.device)
+    torch.distributed.all_gather_into_tensor(gathered, mine)
+    return gathered.permute(1, 0, 2, 3).reshape(per * world, n, n)[:count].contiguous()
+
+
 def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_constraint=1e-3, curvature_ema=0.95,
                             damping=1e-3):
     """-> (init, step) like optimizers/kfac.py:198-241.  `network` is `model.apply` of a deephall_b200 Psiformer."""
@@ -128,6 +148,17 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
         return raw * sc, feat.T @ feat / feat.shape[0]
 
     def precondition(state: KfacState, grads: torch.Tensor) -> torch.Tensor:
+        """The update direction.  Library path (dh_kfac_damped_factors -> dh_spd_inverse -> dh_kfac_update): the damped
+        factors of all blocks are assembled by one kernel, inverted in two batches (<= 288 rows / larger) and applied by the
+        library's fp32 contraction; `precondition_tensor_ops` is the same rule as small tensor ops, for plans with a
+        factor beyond dh_spd_inverse's 1024 rows."""
+        pl = net.plan(system)
+        if pl.kfac_update_shape() is None:
+            return precondition_tensor_ops(state, grads)
+        coef, ms, ml = pl.kfac_damped_factors(state.stats, state.dense0_xtx, state.weight, damping)
+        return pl.kfac_update(_inverse_batch(ms), _inverse_batch(ml), coef, state.stats, state.weight, damping, grads.contiguous())
+
+    def precondition_tensor_ops(state: KfacState, grads: torch.Tensor) -> torch.Tensor:
         w = state.weight
         st = state.stats / w
         out = torch.zeros_like(grads)
@@ -214,4 +245,5 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
         params = params - (lr * coeff) * pg
         return CheckpointState(params, data, KfacState(opt.step + 1, opt.weight, opt.stats, opt.dense0_xtx), width), stats
 
+    step.precondition, step.precondition_tensor_ops = precondition, precondition_tensor_ops  # (tests compare the two routes)
     return init, step

@@ -217,6 +217,28 @@ int dh_kfac_layout(const dh_plan* plan, dh_kfac_entry* entries, int32_t* n, int6
 int dh_kfac_factors(dh_plan* plan, const float* params, const float* x, int64_t B, float* factors, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* The KFAC update from the moving-average statistics (optimizers/kfac.py:202-219 hands the loss to kfac_jax.Optimizer;
+ * its update rule is restated in oracle/kfac.py).  `stats` is the moving average of the factor vector of dh_kfac_factors
+ * (each entry already divided by its row count), `dense0_xtx` the same for Dense_0's 4 x 4 input factor, `weight` the
+ * moving-average weight both are divided by.
+ *   dh_kfac_update_shape    -> number and padded size of the damped Kronecker factors in the "small" (<= 288 rows) and the
+ *                              "large" batch, the number of dense blocks and the floats of one gather buffer.  First call
+ *                              builds the plan's descriptor tables (allocates; later calls and the two ops below do not).
+ *                              DH_E_UNSUPPORTED: a factor has more than 1024 rows, sparse orbitals, Laughlin.
+ *   dh_kfac_damped_factors  -> coef [8 n_blocks] = {tr_avg(A), tr_avg(G), d, c_k, ok, -, -, -} per block and every
+ *                              A / tr_avg(A) + d I, G / tr_avg(G) + d I (kfac_jax's pi-adjusted damping with average-trace
+ *                              norms, d = sqrt(damping / rows_per_walker / (tr_avg(A) tr_avg(G)))), each embedded as
+ *                              diag(M, I) in its batch: mats_small [n_small][dim_small^2], mats_large likewise.
+ *   (the caller inverts the batches with dh_spd_inverse -- sharded over ranks + all-gathered when there are several)
+ *   dh_kfac_update          -> out [num_params] = A~^-1 V G~^-1 / (c_k^2 rows_per_walker) for the dense blocks,
+ *                              g / (F + damping) for the diagonal ones.  ws: 3 * gather_floats floats, 16-byte aligned. */
+int dh_kfac_update_shape(dh_plan* plan, int32_t* n_small, int32_t* dim_small, int32_t* n_large, int32_t* dim_large,
+                         int32_t* n_blocks, int64_t* gather_floats);
+int dh_kfac_damped_factors(dh_plan* plan, const float* stats, const float* dense0_xtx, float weight, float damping,
+                           float* coef, float* mats_small, float* mats_large, void* stream);
+int dh_kfac_update(dh_plan* plan, const float* inv_small, const float* inv_large, const float* coef, const float* stats,
+                   float weight, float damping, const float* grads, float* out, void* ws, size_t ws_bytes, void* stream);
+
 /* In-place inverse of `batch` symmetric positive-definite n x n fp32 matrices (row-major, contiguous), n <= 1024: the
  * damped Kronecker factors of the KFAC update (Gauss-Jordan without pivoting, one block per matrix). */
 int dh_spd_inverse(float* mats, int32_t n, int32_t batch, void* stream);

@@ -490,10 +490,13 @@ def test_graph_replayed_sweep_is_the_same_chain(nat):
             flat = (flat * 0.99).clone()  # new tensor
 
 
-def test_sweep_with_device_arguments(nat):
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_sweep_with_device_arguments(nat, name):
     """dh_mcmc_sweep_dev (width and Philox key read from device memory: the form a jit-compiled / XLA-FFI caller needs) is
-    the same chain as dh_mcmc_sweep with the same values as host scalars, for one move and for many."""
-    cfg, p64, plan, flat, x0 = setup_case(nat, CONFIGS["c2"], 300, burn=0)
+    the same chain as dh_mcmc_sweep with the same values as host scalars, for one move and for many.  One move with host
+    scalars is propose -> log psi -> accept as three public steps' kernels; the device-argument form runs the proposal
+    inside the pass's prologue launch and accept / select inside its last one (c3: with the envelope table): same bits."""
+    cfg, p64, plan, flat, x0 = setup_case(nat, CONFIGS[name], 300, burn=0)
     for steps in (1, 5):
         xa, xb = x0.clone(), x0.clone()
         na, lpa = plan.mcmc_sweep(flat, xa, steps, 0.2, seed=77, offset=1234, subsequence0=5000, want_lp=True)
@@ -849,6 +852,34 @@ def test_kfac_training_step_matches_the_restated_update(nat):
         energies.append(float(st["energy"].real))
     assert all(math.isfinite(e) for e in energies)
     assert sum(energies[-5:]) / 5 < sum(energies[:5]) / 5 and abs(sum(energies[-5:]) / 5 - 1.5) < 0.15, energies
+
+
+def test_kfac_library_update_matches_tensor_ops(nat):
+    """dh_kfac_damped_factors -> dh_spd_inverse -> dh_kfac_update (the KFAC step's default route) against the same rule as
+    small tensor ops, at c3 (29 factors of 256-408 rows, bias rows, the 4 x 4 Dense_0 factor, diagonal blocks), after one
+    and after two moving-average updates, on the step's own gradient and on a random one."""
+    from deephall_b200 import kfac as K, loss, mcmc, networks
+    from deephall_b200.config import Network, Optim, System
+    from deephall_b200.optimizers import CheckpointState
+
+    system = System(flux=33, nspins=(12, 0))
+    model = networks.make_network(system, Network())
+    params = model.init(0)
+    data = mcmc.init_guess(1, 256, 12, model)
+    lg = loss.make_loss_fn(model.apply, system)
+    init, step = K.make_kfac_training_step(Optim().kfac, lg, model.apply, system)
+    assert model.plan(system).kfac_update_shape() is not None
+    st = CheckpointState(params, data, init(params, None, data), 0.1)
+    g = torch.Generator().manual_seed(5)
+    for it in range(2):
+        st, _ = step(st, None)
+        _, grads = lg(st.params, st.data)
+        for gr in (grads, torch.randn(grads.shape, generator=g).to(DEV) * grads.abs().mean()):
+            a = step.precondition(st.opt_state, gr).double()
+            b = step.precondition_tensor_ops(st.opt_state, gr).double()
+            assert torch.isfinite(a).all() and a.norm() > 0
+            assert (a - b).norm() / b.norm() < 2e-4, (it, ((a - b).norm() / b.norm()).item())
+            assert ((a - b).abs() / (b.abs() + 1e-3 * b.abs().max())).max() < 5e-2
 
 
 def test_spd_inverse(nat):
