@@ -869,7 +869,7 @@ static int mcmc_sweep_impl(dh_plan* p, const float* params, float* x, int64_t B,
   static const bool graphs_env = !(dbg_env("DH_MCMC_GRAPH") && atoi(dbg_env("DH_MCMC_GRAPH")) == 0);
   const bool dev_ok = !randoms && p->d_mcmc && (p->laughlin || p->raw_params);
   if (dev_args && !dev_ok) return DH_E_UNSUPPORTED;
-  if (dev_ok && (dev_args || (steps >= 2 && !p->prof_on && p->graphs_ok && graphs_env))) {
+  if (dev_ok) {
     const float* Pg = p->laughlin ? params : p->raw_params;
     if (!p->laughlin) DH_CHECK(cudaMemcpyAsync(p->raw_params, params, p->nparams * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (!dev_args && (rc = mcmc_dev_init(p->d_mcmc, seed, offset, subsequence0, width, s))) return rc;
@@ -904,20 +904,18 @@ static int mcmc_sweep_impl(dh_plan* p, const float* params, float* x, int64_t B,
     if (mg) {
       for (int st = 0; st < steps; ++st) DH_CHECK(cudaGraphLaunch(mg->exec, s));
       p->launches += mg->launches * steps;
-    } else if (dev_args) {  // no graph (one move, profiling, or capture refused): the same kernels launched one by one
+    } else {  // no graph (one move, profiling, or capture refused): the same kernels launched one by one
       for (int st = 0; st < steps; ++st) {
         if ((rc = run_forward(p, Pg, mw.x2, B, false, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mw.logpsi2, fbase, fwd_bytes, s, &move))) return rc;
         { ProfScope ps(p, PC_MCMC, 0, s);
           if ((rc = mcmc_dev_advance(p->d_mcmc, s))) return rc; }
       }
     }
-    if (mg || dev_args) {
-      DH_CHECK(cudaMemcpyAsync(out_naccept, &p->d_mcmc->naccept, sizeof(long long), cudaMemcpyDeviceToDevice, s));
-      if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
-      return 0;
-    }
-    // capture refused: fall through to the launch-by-launch loop with host arguments
+    DH_CHECK(cudaMemcpyAsync(out_naccept, &p->d_mcmc->naccept, sizeof(long long), cudaMemcpyDeviceToDevice, s));
+    if (out_lp) DH_CHECK(cudaMemcpyAsync(out_lp, mw.lp1, B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
   }
+  // injected randoms (bit-exact parity tests against the oracle's decisions): the three public steps' kernels, launch by launch
   for (int st = 0; st < steps; ++st) {
     const float* rnd = randoms ? randoms + st * rstride : nullptr;
     { ProfScope ps(p, PC_MCMC, 0, s); if ((rc = mcmc_propose(x, mw.x2, B, p->N, width, seed, offset + st, subsequence0, rnd, s))) return rc; }

@@ -473,7 +473,7 @@ def test_mcmc_philox_stream(nat):
 
 def test_graph_replayed_sweep_is_the_same_chain(nat):
     """dh_mcmc_sweep replays one captured CUDA graph of a move (device-resident Philox offset); the chain is bit-identical
-    to the same moves launched one by one (steps = 1 calls take the launch-by-launch path), also after the parameters
+    to the same moves launched one by one (steps = 1 calls launch the move's kernels directly), also after the parameters
     change at the same address or move to another tensor."""
     cfg, p64, plan, flat, x0 = setup_case(nat, CONFIGS["c2"], 512, burn=0)
     for trial in range(3):
@@ -488,6 +488,26 @@ def test_graph_replayed_sweep_is_the_same_chain(nat):
             flat.mul_(1.01)              # in-place update: same address, new values
         else:
             flat = (flat * 0.99).clone()  # new tensor
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "spin32"])
+def test_fused_move_equals_the_three_public_steps(nat, name):
+    """A sweep draws the proposal inside the pass's prologue launch (with the features, the first layer's q|k|v and, at c3,
+    the envelope table of the fused orbital epilogue) and takes the log-determinants and accept / select inside its last
+    launch.  Same bits as the three public steps dh_mcmc_propose -> dh_logpsi -> dh_mcmc_accept with the same Philox key,
+    move after move (mcmc.py:54-62)."""
+    cfg, p64, plan, flat, x0 = setup_case(nat, CONFIGS[name], 300, burn=0)
+    seed, off, sub0, width = 21, 77, 4000, 0.2
+    xa = x0.clone()
+    na, lpa = plan.mcmc_sweep(flat, xa, 3, width, seed=seed, offset=off, subsequence0=sub0, want_lp=True)
+    xb = x0.clone()
+    lpb = 2.0 * plan.logpsi(flat, xb).real.contiguous()
+    nb = 0
+    for st in range(3):
+        x2 = plan.mcmc_propose(xb, width, seed=seed, offset=off + st, subsequence0=sub0)
+        lp2 = 2.0 * plan.logpsi(flat, x2).real.contiguous()
+        nb += int(plan.mcmc_accept(xb, x2, lpb, lp2, seed=seed, offset=off + st, subsequence0=sub0))
+    assert torch.equal(xa, xb) and torch.equal(lpa, lpb) and int(na) == nb and 0 < nb < 3 * 300
 
 
 @pytest.mark.parametrize("name", ["c2", "c3"])
