@@ -457,6 +457,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   // compressed form (into t1, which is free until the second Dense of the layer) and expanded by the first LayerNorm
   const bool h0_comp = jets && p->gemm_impl == 1 && p->nl > 0;
   const bool orb_epi = p->orb_fuse && (!jets || rows % 128 == 0);  // envelope contraction as the orbital projection's epilogue
+  const bool jprologue = jets && h0_comp && orb_epi && (D & 3) == 0;
   if (vprologue) {
     ProfScope ps(p, PC_OTHER, 0, s);
     const dh_plan::Slot& q = p->slots[SL_QKV];
@@ -474,6 +475,14 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
       vp.tab = w.cbuf; vp.L = p->L; vp.NK = N * p->K; vp.twoQ = p->twoQ;
     }
     if ((rc = value_prologue(vp, Bc * N, N, p->cfg.n_up, s))) return rc;
+  } else if (jprologue) {
+    // jet passes: compressed Dense_0 output, compressed first-layer q|k|v and the envelope table in one launch
+    ProfScope ps(p, PC_OTHER, 0, s);
+    const dh_plan::Slot& q = p->slots[SL_QKV];
+    const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
+    if ((rc = jets_prologue(x, P + p->off_W0, w.t1, D, p->prep + p->w0qkv, p->prep + q.bias, w.qkv, 3 * D, p->d_normfac, orbB(p, P, 0),
+                            orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, p->cfg.n_up, td, s)))
+      return rc;
   } else {
     ProfScope ps(p, PC_OTHER, 0, s);
     if ((rc = features_linear(x, P + p->off_W0, nullptr, h0_comp ? w.t1 : w.h, D, Bc, nd, h0_comp ? 1 : 0, s))) return rc;
@@ -484,7 +493,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
   const bool pl = jets && p->a_planes;
   for (int l = 0; l < p->nl; ++l) {
     const LayerOff& o = p->layer[l];
-    if (l == 0 && vprologue) {
+    if (l == 0 && (vprologue || jprologue)) {
       // q|k|v of the first layer came with the prologue
     } else if (l == 0 && p->gemm_impl == 1) {
       // h = feat @ W0 is linear in the features: q|k|v = feat @ (W0 Wqkv) + b, a 4-deep contraction
@@ -527,7 +536,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
     // envelope values (jet passes: jets) go to a small table first (w.cbuf, which the coefficient tensor no longer needs), the
     // contraction reads its coefficients out of tensor memory and writes the orbital matrices -- c[rows][2 L N] never exists in HBM
     const dh_plan::Slot& sl = p->slots[p->nl * SL_PER_LAYER + 1];
-    if (jets || !vprologue) {  // (value-only passes: the table normally comes with the prologue)
+    if (!jprologue && (jets || !vprologue)) {  // (the table normally comes with the prologue)
       ProfScope pse(p, PC_TAIL, 0, s);
       if (jets) rc = envelope_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);
       else rc = envelope_value_table(x, p->d_normfac, orbB(p, P, 0), orbB(p, P, 1), p->prep + sl.scale + 1, w.cbuf, Bc, td, s);

@@ -103,6 +103,11 @@ struct TailDims {
 // (sum_m bias(m, j) env_s[m]): the right operand of the fused envelope contraction (gemm_tc.cu, ORB)
 int envelope_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
                    int64_t B, TailDims d, cudaStream_t s);
+// jet-pass prologue in one launch: compressed Dense_0 output h [B N][10][n0], compressed first-layer q|k|v [B N][10][n1]
+// (W1 [4][n1] + bias b1) and the envelope table
+int jets_prologue(const float* x, const float* W0, float* h, int n0, const float* W1, const float* b1, float* q, int n1,
+                  const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab, int64_t B, int n_up,
+                  TailDims d, cudaStream_t s);
 // value-only form: per electron [L] complex envelope (times *unscale) + [N K] complex bias products
 int envelope_value_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
                          int64_t B, TailDims d, cudaStream_t s);

@@ -621,6 +621,89 @@ int envelope_table(const float* x, const double* normfac, const float* bre, cons
   return (int)cudaGetLastError();
 }
 
+// Prologue of a jet pass in ONE launch, one block per electron: the compressed feature maps (features_dense0_kernel's
+// 10 non-zero jet rows: Dense_0 -> h and the first layer's q|k|v = feat (W0 Wqkv) + b) followed by the envelope table above.
+// The maps are store-bound (40 KB per electron); the fp64 envelope jets run while those stores drain.
+__global__ void __launch_bounds__(64)
+jets_prologue_kernel(const float* __restrict__ x, const float* __restrict__ W0, float* __restrict__ h, int n0,
+                     const float* __restrict__ W1, const float* __restrict__ b1, float* __restrict__ q, int n1,
+                     const double* __restrict__ normfac, const float* __restrict__ bre, const float* __restrict__ bim,
+                     const float* __restrict__ unscale, float* __restrict__ tab, int n_up, TailDims dm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  __shared__ __align__(16) float feat[ENV_SLOTS][4];  // value | own theta, phi flows | S | D_a | T_a
+  const int64_t bi = blockIdx.x;
+  const int i = (int)(bi % dm.N);
+  const float th = x[bi * 2], ph = x[bi * 2 + 1];
+  if (threadIdx.x == 0) {
+    float st, ct, sp, cp;
+    sincosf(th, &st, &ct);
+    sincosf(ph, &sp, &cp);
+    const float rx = st * cp, ry = st * sp, rz = ct;
+    const float f[ENV_SLOTS][4] = {{rz, rx, ry, i < n_up ? 1.f : -1.f},  // feature order: (z, x, y, spin)
+                                   {0.f, sp, -cp, 0.f},                   // theta_hat x r = -phi_hat
+                                   {-st, ct * cp, ct * sp, 0.f},          // phi_hat x r = theta_hat
+                                   {-2.f * rz, -2.f * rx, -2.f * ry, 0.f},
+                                   {ry, 0.f, -rz, 0.f}, {-rx, rz, 0.f, 0.f}, {0.f, -ry, rx, 0.f},   // e_a x r
+                                   {-rz, 0.f, -ry, 0.f}, {-rz, -rx, 0.f, 0.f}, {0.f, -rx, -ry, 0.f}};  // e_a r_a - r
+#pragma unroll
+    for (int r = 0; r < ENV_SLOTS; ++r)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) feat[r][k] = f[r][k];
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < (n0 + n1) / 4; g += blockDim.x) {
+    const bool second = g >= n0 / 4;
+    const int d = 4 * (second ? g - n0 / 4 : g), nout = second ? n1 : n0;
+    const float* W = second ? W1 : W0;
+    float* out = (second ? q : h) + bi * ENV_SLOTS * nout + d;
+    const float4 w0 = *reinterpret_cast<const float4*>(W + d), w1 = *reinterpret_cast<const float4*>(W + nout + d);
+    const float4 w2 = *reinterpret_cast<const float4*>(W + 2 * nout + d), w3 = *reinterpret_cast<const float4*>(W + 3 * nout + d);
+    const float4 bb = second && b1 != nullptr ? *reinterpret_cast<const float4*>(b1 + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < ENV_SLOTS; ++r) {
+      const float4 f = *reinterpret_cast<const float4*>(feat[r]);
+      float4 v;
+      v.x = fmaf(f.x, w0.x, fmaf(f.y, w1.x, fmaf(f.z, w2.x, f.w * w3.x)));
+      v.y = fmaf(f.x, w0.y, fmaf(f.y, w1.y, fmaf(f.z, w2.y, f.w * w3.y)));
+      v.z = fmaf(f.x, w0.z, fmaf(f.y, w1.z, fmaf(f.z, w2.z, f.w * w3.z)));
+      v.w = fmaf(f.x, w0.w, fmaf(f.y, w1.w, fmaf(f.z, w2.w, f.w * w3.w)));
+      if (r == 0) { v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
+      *reinterpret_cast<float4*>(out + (int64_t)r * nout) = v;
+    }
+  }
+  // ---- envelope table (envelope_table_kernel's arithmetic)
+  const int L = dm.L, NK = dm.N * dm.K;
+  dcplx* upow = reinterpret_cast<dcplx*>(smraw);
+  dcplx* vpow = upow + L;
+  cplx* env = reinterpret_cast<cplx*>(vpow + L);  // [ENV_SLOTS][L]
+  envelope_jets(th, ph, dm.twoQ, normfac, upow, vpow, env, ENV_SLOTS);  // ends with __syncthreads
+  float* dst = tab + bi * (int64_t)(ENV_SLOTS * 2 * L + ENV_SLOTS * 2 * NK);
+  const float us = unscale ? __ldg(unscale) : 1.f;
+  const float* src = reinterpret_cast<const float*>(env);
+  for (int t = threadIdx.x; t < ENV_SLOTS * 2 * L; t += blockDim.x) dst[t] = src[t] * us;
+  for (int t = threadIdx.x; t < ENV_SLOTS * NK; t += blockDim.x) {
+    const int sl = t / NK, j = t - sl * NK;
+    cplx acc = cmake(0.f, 0.f);
+    for (int m = 0; m < L; ++m) acc = cfma(cmake(bre[m * NK + j], bim[m * NK + j]), env[sl * L + m], acc);
+    dst[ENV_SLOTS * 2 * L + 2 * t] = acc.x;
+    dst[ENV_SLOTS * 2 * L + 2 * t + 1] = acc.y;
+  }
+}
+int jets_prologue(const float* x, const float* W0, float* h, int n0, const float* W1, const float* b1, float* q, int n1,
+                  const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab, int64_t B, int n_up,
+                  TailDims d, cudaStream_t s) {
+  if ((n0 | n1) & 3) return -2;
+  if ((reinterpret_cast<uintptr_t>(W0) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(h) |
+       reinterpret_cast<uintptr_t>(q)) & 15)
+    return -2;
+  const size_t smem = 2 * d.L * sizeof(dcplx) + (size_t)ENV_SLOTS * d.L * sizeof(cplx);
+  // 64 threads per electron: the envelope jets are a chain of short serial fp64 phases, so many small blocks per SM overlap
+  // better than few large ones (measured per 1024-walker chunk: 64 threads 123 us, 128: 146 us, 256: 207 us; the three
+  // separate launches this replaces: 148 us)
+  jets_prologue_kernel<<<(unsigned)(B * d.N), 64, smem, s>>>(x, W0, h, n0, W1, b1, q, n1, normfac, bre, bim, unscale, tab, n_up, d);
+  return (int)cudaGetLastError();
+}
+
 // Value-only form of the table: per electron [L] complex envelope values (times *unscale) followed by [N K] complex bias
 // products.  One warp per electron (the envelope of orbital_value_kernel).
 __global__ void __launch_bounds__(256)
