@@ -64,7 +64,7 @@ def gemm_traffic_per_launch():
     """dram bytes (read + write) per launch of the dominant kernel from the committed ncu --set full
     summary (profiles/r2_gemm_traffic.json), or None."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")) as f:
             return json.load(f)["avg_dram_bytes_per_launch"]
     except Exception:
         return None
