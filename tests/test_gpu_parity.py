@@ -508,6 +508,15 @@ def test_fused_move_equals_the_three_public_steps(nat, name):
         lp2 = 2.0 * plan.logpsi(flat, x2).real.contiguous()
         nb += int(plan.mcmc_accept(xb, x2, lpb, lp2, seed=seed, offset=off + st, subsequence0=sub0))
     assert torch.equal(xa, xb) and torch.equal(lpa, lpb) and int(na) == nb and 0 < nb < 3 * 300
+    # the same chain when the pass is cut into ragged chunks on two streams (each chunk draws its walkers' proposals with the
+    # walkers' own Philox subsequences) and when the walkers are a shard of a larger batch
+    p_small = make_plan(nat, cfg, chunk_walkers=77)
+    xc = x0.clone()
+    nc, lpc = p_small.mcmc_sweep(flat, xc, 3, width, seed=seed, offset=off, subsequence0=sub0, want_lp=True)
+    assert torch.equal(xa, xc) and torch.equal(lpa, lpc) and int(nc) == nb
+    xd = x0[100:].clone()
+    plan.mcmc_sweep(flat, xd, 3, width, seed=seed, offset=off, subsequence0=sub0 + 100)
+    assert torch.equal(xa[100:], xd)
 
 
 @pytest.mark.parametrize("name", ["c2", "c3"])
