@@ -85,6 +85,7 @@ SIGNATURES = OrderedDict(
     dh_launch_count=(C.c_longlong, [_vp]),
     dh_kfac_layout=(C.c_int, [_vp, C.POINTER(dh_kfac_entry), C.POINTER(_i32), C.POINTER(_i64)]),
     dh_kfac_factors=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
+    dh_kfac_factors_reuse_forward=(C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, C.c_size_t, _vp]),
     dh_kfac_update_shape=(C.c_int, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32),
                                     C.POINTER(_i64)]),
     dh_kfac_damped_factors=(C.c_int, [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
@@ -419,16 +420,18 @@ def _kfac_methods():
                                        _stream()), "dh_kfac_update")
         return out
 
-    def kfac_factors(self, params, x):
-        """Factor sums of the KFAC curvature blocks for the walkers x (dh_kfac_factors): flat f32 tensor."""
+    def kfac_factors(self, params, x, reuse_forward=False):
+        """Factor sums of the KFAC curvature blocks for the walkers x (dh_kfac_factors): flat f32 tensor.
+        reuse_forward: the caller's previous op on this plan was `logpsi_vjp` on the same params and x, untouched since --
+        its activations are reused (dh_kfac_factors_reuse_forward)."""
         self._prepare(params)
         _f32(x, "walkers")
         B = x.shape[0]
         _, nf = self.kfac_layout()
         out = torch.empty(nf, dtype=torch.float32, device=x.device)
         ws = self.workspace(OP_KFAC, B)
-        _check(self.lib.dh_kfac_factors(self.handle, _ptr(params), _ptr(x), B, _ptr(out), _ptr(ws), ws.numel(), _stream()),
-               "dh_kfac_factors")
+        fn = self.lib.dh_kfac_factors_reuse_forward if reuse_forward else self.lib.dh_kfac_factors
+        _check(fn(self.handle, _ptr(params), _ptr(x), B, _ptr(out), _ptr(ws), ws.numel(), _stream()), "dh_kfac_factors")
         return out
 
     Plan.kfac_layout = kfac_layout

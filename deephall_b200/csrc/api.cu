@@ -573,6 +573,7 @@ int forward_chunk(const dh_plan* p, const float* P, const float* x, int64_t Bc, 
 }
 
 static int prepare_weights_now(dh_plan* p, const float* P, cudaStream_t s) {
+  p->vjp_fwd.valid = false;  // the parameters may have changed
   const int D = p->D, LNK = p->LNK, f16 = p->tc_f16;
   int rc;
   if (p->sparse) {  // effective full projections of the sparse orbitals (both contraction implementations read them)
@@ -757,7 +758,7 @@ static int run_forward(dh_plan* p, const float* params, const float* x, int64_t 
   if (!p || B < 0) return DH_E_BADARG;
   if (B == 0) return 0;
   if ((!params && p->nparams > 0) || !x) return DH_E_BADARG;
-  if (B == 0) return 0;
+  p->vjp_fwd.valid = false;  // this pass takes the workspace
   int copies = 1;
   int64_t chunk = plan_chunks(p, jets, B, &copies);
   float* base = align_ws(ws);

@@ -122,7 +122,11 @@ size_t vjp_ws_floats(const dh_plan* p, int64_t Bc) { return carve_vjp(p, nullptr
 // kf != nullptr: cotangent (1, 0) for every walker and, instead of parameter gradients, the factor sums of the KFAC
 // curvature blocks (dh_kfac_factors); `cot` is ignored and the parameter-shaped by-products go to a scratch vector.
 static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const float* cot, float* grad, float* kf,
-                    float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s) {
+                    float* out_logpsi, void* ws, size_t ws_bytes, cudaStream_t s, bool reuse_forward = false) {
+  // the forward of the previous reverse pass may be reused when it ran on the same parameters, walkers and workspace, as one chunk
+  const bool skip_fwd = reuse_forward && p->vjp_fwd.valid && p->vjp_fwd.P == P && p->vjp_fwd.x == x && p->vjp_fwd.B == B &&
+                        p->vjp_fwd.ws == ws && !out_logpsi;
+  p->vjp_fwd.valid = false;
   if (kf) DH_CHECK(cudaMemsetAsync(kf, 0, (size_t)p->kfac_floats * sizeof(float), s));
   if (!kf) DH_CHECK(cudaMemsetAsync(grad, 0, p->nparams * sizeof(float), s));
   if (B == 0) return 0;
@@ -162,6 +166,8 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
     const float* xc = x + b0 * N * 2;
     const float* cotc = kf ? unit_cot : cot + b0 * 2;
     // ------------------------------------------------------------ forward, keeping activations
+    const float* hf = w.hs[nl];
+    if (!skip_fwd) {
     RUN(PC_OTHER, features_dense0(xc, P + p->off_W0, w.hs[0], Bc, nd, s));
     for (int l = 0; l < nl; ++l) {
       const LayerOff& o = p->layer[l];
@@ -173,10 +179,10 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
       if ((rc = dense_layer(p, P, l, SL_D2, w.hA[l], w.z[l], rows, 1, s))) return rc;
       RUN(PC_LAYERNORM, residual_layernorm(w.hA[l], w.z[l], P + o.ln1_s, P + o.ln1_b, w.hs[l + 1], Bc, nd, 1, s));
     }
-    const float* hf = w.hs[nl];
     if ((rc = dense_orb(p, P, hf, w.cbuf, rows, 1, s))) return rc;
     RUN(PC_TAIL, orbital_contract(w.cbuf, xc, p->d_normfac, w.Mj, Bc, td, s));
     RUN(PC_TAIL, logdet_jets_impl(w.Mj, w.ld, w.Minv, Bc, td, s));
+    }
     if (out_logpsi) {
       FinalizeArgs fa;
       memset(&fa, 0, sizeof(fa));
@@ -306,6 +312,7 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
     }
   }
 #undef RUN
+  if (B <= chunk) p->vjp_fwd = dh_plan::FwdKey{P, x, B, ws, true};  // one chunk: its activations stay in the workspace
   return 0;
 }
 
@@ -337,6 +344,14 @@ extern "C" int dh_kfac_factors(dh_plan* p, const float* P, const float* x, int64
   if (p->laughlin || p->sparse) return DH_E_UNSUPPORTED;
   if (!P || !factors || B < 0 || (B > 0 && !x)) return DH_E_BADARG;
   return vjp_core(p, P, x, B, nullptr, nullptr, factors, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dh_kfac_factors_reuse_forward(dh_plan* p, const float* P, const float* x, int64_t B, float* factors, void* ws,
+                                             size_t ws_bytes, void* stream) {
+  if (!p) return DH_E_BADARG;
+  if (p->laughlin || p->sparse) return DH_E_UNSUPPORTED;
+  if (!P || !factors || B < 0 || (B > 0 && !x)) return DH_E_BADARG;
+  return vjp_core(p, P, x, B, nullptr, nullptr, factors, nullptr, ws, ws_bytes, (cudaStream_t)stream, true);
 }
 
 // --------------------------------------------------------------------------------- KFAC update (optimizers/kfac.py:202-219)

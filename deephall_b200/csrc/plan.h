@@ -51,6 +51,9 @@ struct dh_plan {
   std::vector<KfLayer> kf_layer;
   int kf_dense0, kf_orb[4], kf_eepar, kf_eeanti;
   int64_t kfac_floats;
+  // The activations of the last reverse pass's forward (dh_logpsi_vjp / dh_kfac_factors, single chunk) are still in the
+  // caller's workspace: dh_kfac_factors_reuse_forward may skip its forward.  Cleared by every other op of the plan.
+  struct FwdKey { const float* P = nullptr; const float* x = nullptr; int64_t B = 0; void* ws = nullptr; bool valid = false; } vjp_fwd;
   // KFAC update tables (dh_kfac_update_shape builds them on first use; device copies freed with the plan)
   struct KfUpdate {
     int ready = 0;  // 0 not built, 1 built, -1 unsupported (a factor with more than 1024 rows)

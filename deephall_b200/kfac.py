@@ -140,7 +140,8 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
 
     def normalised_stats(params, data):
         """This step's statistics (local shard), each already divided by its batch size."""
-        raw = net.plan(system).kfac_factors(params, data.contiguous())
+        # (the step's previous plan op is the gradient's VJP on these params and walkers: its forward is reused)
+        raw = net.plan(system).kfac_factors(params, data.contiguous(), reuse_forward=True)
         sc, naive = stat_scales(data.shape[0], raw.device)
         for o, n in naive:
             raw[o : o + n] = raw[o : o + n] ** 2

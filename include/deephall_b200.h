@@ -216,6 +216,12 @@ int dh_plan_status_copy(dh_plan* plan, uint32_t* dst_device, void* stream);
 int dh_kfac_layout(const dh_plan* plan, dh_kfac_entry* entries, int32_t* n, int64_t* factor_floats);
 int dh_kfac_factors(dh_plan* plan, const float* params, const float* x, int64_t B, float* factors, void* ws,
                     size_t ws_bytes, void* stream);
+/* The same, allowed to skip its forward pass: when the plan's previous op was dh_logpsi_vjp (or dh_kfac_factors) on the
+ * same params, x, B and ws, the batch fitted one chunk, and the caller has not written to params, x or ws since, that
+ * op's activations are still in the workspace (the KFAC step calls it right after the gradient's VJP, optimizers/kfac.py
+ * estimates the curvature on the batch of the gradient).  In every other case it is dh_kfac_factors. */
+int dh_kfac_factors_reuse_forward(dh_plan* plan, const float* params, const float* x, int64_t B, float* factors, void* ws,
+                                  size_t ws_bytes, void* stream);
 
 /* The KFAC update from the moving-average statistics (optimizers/kfac.py:202-219 hands the loss to kfac_jax.Optimizer;
  * its update rule is restated in oracle/kfac.py).  `stats` is the moving average of the factor vector of dh_kfac_factors

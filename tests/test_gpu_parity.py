@@ -883,6 +883,25 @@ def test_kfac_training_step_matches_the_restated_update(nat):
     assert sum(energies[-5:]) / 5 < sum(energies[:5]) / 5 and abs(sum(energies[-5:]) / 5 - 1.5) < 0.15, energies
 
 
+def test_kfac_factor_pass_reuses_the_vjp_forward(nat):
+    """dh_kfac_factors_reuse_forward right after dh_logpsi_vjp on the same parameters and walkers skips its forward pass
+    (one launch sequence shorter) and delivers the same factor sums; after any other op it runs the full pass."""
+    cfg, p64, plan, flat, x = setup_case(nat, CONFIGS["c2"], 200, burn=1)
+    ref = plan.kfac_factors(flat, x)
+    cot = torch.randn(200, 2, device=DEV)
+    plan.logpsi_vjp(flat, x, cot)
+    l0 = plan.launch_count
+    a = plan.kfac_factors(flat, x, reuse_forward=True)
+    n_reuse = plan.launch_count - l0
+    plan.logpsi(flat, x)  # takes the workspace: nothing to reuse afterwards
+    l0 = plan.launch_count
+    b = plan.kfac_factors(flat, x, reuse_forward=True)
+    n_full = plan.launch_count - l0
+    assert n_reuse < n_full
+    scale = ref.abs().max()
+    assert (a - ref).abs().max() / scale < 1e-5 and (b - ref).abs().max() / scale < 1e-5
+
+
 def test_kfac_library_update_matches_tensor_ops(nat):
     """dh_kfac_damped_factors -> dh_spd_inverse -> dh_kfac_update (the KFAC step's default route) against the same rule as
     small tensor ops, at c3 (29 factors of 256-408 rows, bias rows, the 4 x 4 Dense_0 factor, diagonal blocks), after one
