@@ -278,8 +278,8 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
     };
     for (int l = 0; l < p->nl; ++l) { slot(3 * D, true); slot(D, true); slot(D, false); slot(D, true); slot(D, true); }
     slot(p->orbN, true);
-    if (p->orb_fuse) {  // the same projection with its output columns permuted to [tile][m][re | im][column], 10 m per tile
-      const int nperm = (L - 1) / 10 * 256 + ((L - 1) % 10 + 1) * 24;
+    if (p->orb_fuse) {  // the same projection with its output columns permuted to [tile][m][re | im][column], orb_per_tile(L) m per tile
+      const int nperm = orb_columns(L);
       slot(nperm, true);
       p->orb_perm = off; off += al((size_t)(D + 1) * nperm);  // fp32 staging of the permuted kernel [D][nperm] and bias [nperm]
     }

@@ -297,6 +297,7 @@ struct OrbFuse {
                      // [10][12] complex bias products sum_m bias(m, j) env_s[m]  (envelope_table, tail_kernels.cu)
   float* Mj;         // out: orbital-matrix jets [walkers][32 rows][12 electrons][12 orbitals] complex
   int L;             // orbitals 2Q + 1
+  int mpt;           // orbitals per 256-column weight tile (orb_per_tile(L), kernels.h)
 };
 // LNV (pair form, value-only passes: one row per electron, N = 256): the epilogue is the residual + (tanh) + LayerNorm that
 // follows the contraction in the network (psiformer.py:45-48) -- C = LN(res + acc + bias) or LN(res + tanh(acc + bias)),
@@ -310,7 +311,11 @@ struct LnFuse {
 };
 constexpr int ORB_NK = 12;               // orbital columns per (part, m) group
 constexpr int ORB_GW = 2 * ORB_NK;       // accumulator columns per m: [re (12) | im (12)]
-constexpr int ORB_MPT = BLOCK_N / ORB_GW;  // m per column tile: 10 (the last 16 columns of a full tile are zero weights)
+constexpr int ORB_MPT = BLOCK_N / ORB_GW;  // at most 10 m per column tile; OrbFuse::mpt = orb_per_tile(L) are used
+// tensor columns of column tile nt: its orbitals' 24 columns each, rounded up to the 16-column granule of the pair MMA
+__device__ __forceinline__ int orb_tile_cols(const OrbFuse& o, int nt) {
+  return (ORB_GW * min(o.mpt, o.L - o.mpt * nt) + 15) & ~15;
+}
 
 template <bool F16, bool MERGED, bool PAIR, bool ORB, bool LNV>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -468,7 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int64_t bi = 0; bi < my_bands; ++bi) {
         for (int nt = 0; nt < n_ntiles; ++nt) {
           const int n0 = nt * BLOCK_N;
-          const int n_tile = N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N;
+          const int n_tile = ORB ? orb_tile_cols(orb, nt) : (N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N);
           const int nb = n0 + (int)crank * (n_tile / 2);
           for (int kb = 0; kb < num_kb; ++kb, ++itb) {
             if (nt == 0) while (ja <= bi * num_kb + kb) issue_a(true);   // this step's A tile at the latest now
@@ -532,7 +537,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int64_t bi = 0; bi < my_bands; ++bi) {
         for (int nt = 0; nt < n_ntiles; ++nt, ++tl) {
           const int n0 = nt * BLOCK_N;
-          const int n_tile = N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N;
+          const int n_tile = ORB ? orb_tile_cols(orb, nt) : (N - n0 < BLOCK_N ? ((N - n0 + 15) & ~15) : BLOCK_N);
           const uint32_t idesc = make_idesc<F16>(2 * BLOCK_M, n_tile);
           const int ab = (int)(tl & 1);
           const uint32_t acc = tmem_base + (uint32_t)ab * BLOCK_N;
@@ -725,13 +730,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < ORB_GW; ++j) oacc[j] = 0.f;
           }
-          const int mt = min(ORB_MPT, L - ORB_MPT * nt);
+          const int mt = min(orb.mpt, L - orb.mpt * nt);
 #pragma unroll 1
           for (int ml = chalf; ml < mt; ml += 2) {
             uint32_t v[24];
             tmem_ld16(tbase + (uint32_t)(ORB_GW * ml), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
             tmem_ld8(tbase + (uint32_t)(ORB_GW * ml + 16), *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
-            const float2 e0 = __ldg(reinterpret_cast<const float2*>(et + 2 * (ORB_MPT * nt + ml)));
+            const float2 e0 = __ldg(reinterpret_cast<const float2*>(et + 2 * (orb.mpt * nt + ml)));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (ml + 2 >= mt) {
               asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -808,10 +813,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < ORB_GW; ++j) { oacc[j] = 0.f; oacc2[j] = 0.f; }
         }
-        const int mt = min(ORB_MPT, L - ORB_MPT * nt);  // m's in this tile
+        const int mt = min(orb.mpt, L - orb.mpt * nt);  // m's in this tile
 #pragma unroll 1
         for (int ml = chalf; ml < mt; ml += 2) {
-          const int mm = ORB_MPT * nt + ml;
+          const int mm = orb.mpt * nt + ml;
           uint32_t v[24];
           tmem_ld16(tbase + (uint32_t)(ORB_GW * ml), *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
           tmem_ld8(tbase + (uint32_t)(ORB_GW * ml + 16), *reinterpret_cast<uint32_t(*)[8]>(&v[16]));
@@ -1573,10 +1578,10 @@ int gemm_tc_ex(const TcGemm& gm, cudaStream_t stream) {
   // fused envelope contraction (orbital matrices): pair form with resident A, 32 jet rows per electron, whole electrons per
   // band, weights in the permuted [tile][m][re | im] layout (10 m per 256-column tile)
   tc::OrbFuse orb;
-  orb.env = gm.orb_env; orb.Mj = gm.orb_Mj; orb.L = gm.orb_L;
+  orb.env = gm.orb_env; orb.Mj = gm.orb_Mj; orb.L = gm.orb_L; orb.mpt = gm.orb_L > 0 ? orb_per_tile(gm.orb_L) : tc::ORB_MPT;
   const bool orb_on = gm.orb_env != nullptr;
   if (orb_on && !(pair && res && ((rpg == 32 && M % 128 == 0) || rpg <= 1) && !reduce_add && gm.a_scale == nullptr && gm.orb_L >= 1 && gm.orb_L <= 48 &&
-                  N == (gm.orb_L - 1) / tc::ORB_MPT * tc::BLOCK_N + ((gm.orb_L - 1) % tc::ORB_MPT + 1) * tc::ORB_GW))
+                  N == orb_columns(gm.orb_L)))
     return -2;
   // fused value LayerNorm epilogue: pair form, one 256-wide column tile, every row a value row, TMA-stored output in place
   tc::LnFuse lnf;

@@ -111,9 +111,15 @@ int jets_prologue(const float* x, const float* W0, float* h, int n0, const float
 // value-only form: per electron [L] complex envelope (times *unscale) + [N K] complex bias products
 int envelope_value_table(const float* x, const double* normfac, const float* bre, const float* bim, const float* unscale, float* tab,
                          int64_t B, TailDims d, cudaStream_t s);
+// Column tiles of the fused envelope contraction (gemm_tc.cu, ORB): the L orbitals are dealt out EVENLY over ceil(L / 10) tiles
+// of 256 weight columns (24 columns per orbital), so that no tile's tensor work is much shorter than its neighbour's epilogue
+// (L = 34: 9, 9, 9, 7 orbitals = 224, 224, 224, 176 tensor columns instead of 256, 256, 256, 96)
+inline int orb_tiles(int L) { return (L + 9) / 10; }
+inline int orb_per_tile(int L) { return (L + orb_tiles(L) - 1) / orb_tiles(L); }
+inline int orb_columns(int L) { return (orb_tiles(L) - 1) * 256 + (L - orb_per_tile(L) * (orb_tiles(L) - 1)) * 24; }
 // orbital-projection kernels / biases -> fp32 [D][ncol] + [ncol] with columns ordered [tile][m (10)][re | im][NK]
 int orb_permute_weights(const float* Wre, const float* Wim, const float* bre, const float* bim, float* Wp, float* bp, int D, int L,
-                        int NK, int ncol, cudaStream_t s);
+                        int NK, int ncol, cudaStream_t s);  // ncol = orb_columns(L); orb_per_tile(L) orbitals per 256-column tile
 int orbital_contract(const float* c, const float* x, const double* normfac, float* Mj, int64_t B, TailDims d,
                      cudaStream_t s);
 // Laughlin ground-state orbital matrix jets (networks/laughlin.py:59-71): Mj [B][1][R][N][N] complex; d.L == d.N,

@@ -750,17 +750,17 @@ int envelope_value_table(const float* x, const double* normfac, const float* bre
 }
 
 // Orbital-projection kernels [D][L N] (real part, imaginary part) and biases -> ONE fp32 matrix [D][ncol] and bias [ncol]
-// whose columns are ordered for the fused envelope contraction: tile t (256 columns) holds the orbitals m = 10 t .. 10 t + 9,
-// each as 24 columns [re(m, 0..11) | im(m, 0..11)]; the remaining columns of a tile are zero.
+// whose columns are ordered for the fused envelope contraction: tile t (256 columns) holds the orbitals m = g t .. g t + g - 1
+// (g = orb_per_tile(L)), each as 24 columns [re(m, 0..11) | im(m, 0..11)]; the remaining columns of a tile are zero.
 __global__ void orb_permute_weights_kernel(const float* __restrict__ Wre, const float* __restrict__ Wim, const float* __restrict__ bre,
                                            const float* __restrict__ bim, float* __restrict__ Wp, float* __restrict__ bp, int D,
-                                           int L, int NK, int ncol) {
+                                           int L, int NK, int ncol, int mpt) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)(D + 1) * ncol) return;
   const int k = (int)(t / ncol), n = (int)(t % ncol);
   const int tile = n >> 8, rem = n & 255, ml = rem / (2 * NK), w = rem - ml * 2 * NK;
-  const int m = 10 * tile + ml, part = w / NK, col = w - part * NK;
-  const bool valid = ml < 10 && m < L;
+  const int m = mpt * tile + ml, part = w / NK, col = w - part * NK;
+  const bool valid = ml < mpt && m < L;
   const int src = m * NK + col;
   if (k < D) Wp[(int64_t)k * ncol + n] = valid ? (part ? Wim : Wre)[(int64_t)k * L * NK + src] : 0.f;
   else bp[n] = valid ? (part ? bim : bre)[src] : 0.f;
@@ -768,7 +768,7 @@ __global__ void orb_permute_weights_kernel(const float* __restrict__ Wre, const 
 int orb_permute_weights(const float* Wre, const float* Wim, const float* bre, const float* bim, float* Wp, float* bp, int D, int L,
                         int NK, int ncol, cudaStream_t s) {
   const int64_t n = (int64_t)(D + 1) * ncol;
-  orb_permute_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Wre, Wim, bre, bim, Wp, bp, D, L, NK, ncol);
+  orb_permute_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Wre, Wim, bre, bim, Wp, bp, D, L, NK, ncol, orb_per_tile(L));
   return (int)cudaGetLastError();
 }
 
