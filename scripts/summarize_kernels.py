@@ -25,12 +25,13 @@ for i in ids:
                    ("issue", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                    ("tensor", "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"),
                    ("fp64", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+                   ("hmma", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
                    ("warps", "sm__warps_active.avg.pct_of_peak_sustained_active")):
         a[k] += L.get(key, 0.0) * t
-print(f"| kernel | launches | time us | dram GB/s (read+write) | % of {peak:.0f} GB/s | FP32-FMA pipe active % | issue active % | fp16 tensor ops % of peak | FP64 pipe % | warps active % |")
-print("|---|---|---|---|---|---|---|---|---|---|")
+print(f"| kernel | launches | time us | dram GB/s (read+write) | % of {peak:.0f} GB/s | FP32-FMA pipe active % | issue active % | fp16 tensor ops (tcgen05) % of peak | tensor pipe active % (incl. HMMA) | FP64 pipe % | warps active % |")
+print("|---|---|---|---|---|---|---|---|---|---|---|")
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["t"]):
     t = a["t"]
     gbs = a["bytes"] / t  # bytes per ns = GB/s
     print(f"| {name[:60]} | {int(a['n'])} | {t / 1e3:.1f} | {gbs:.0f} | {100 * gbs / peak:.0f} | {a['fma'] / t:.1f} | {a['issue'] / t:.1f} | "
-          f"{a['tensor'] / t:.1f} | {a['fp64'] / t:.1f} | {a['warps'] / t:.1f} |")
+          f"{a['tensor'] / t:.1f} | {a['hmma'] / t:.1f} | {a['fp64'] / t:.1f} | {a['warps'] / t:.1f} |")
