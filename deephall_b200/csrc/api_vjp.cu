@@ -446,16 +446,14 @@ extern "C" int dh_kfac_update(dh_plan* p, const float* inv_small, const float* i
   float* U = T + u.gather_floats;
   DH_CHECK(cudaMemsetAsync(out, 0, (size_t)p->nparams * sizeof(float), s));
   if ((rc = kfac_gather(u.d_blk, (int)u.blk.size(), grads, V, s))) return rc;
-  for (size_t b = 0; b < u.blk.size(); ++b) {
-    const KfBlkDesc& bd = u.blk[b];
-    const KfMatDesc &ma = u.mat[2 * b], &mg = u.mat[2 * b + 1];
-    const float* Ai = (ma.cls ? inv_large : inv_small) + ma.dst;
-    const float* Gi = (mg.cls ? inv_large : inv_small) + mg.dst;
-    const int na = bd.din + bd.hb;
-    // T = A~^-1 V~ ; U = T G~^-1  (fp32 FMA contraction of the library)
-    if ((rc = gemm_simt(Ai, V + bd.v_off, nullptr, T + bd.v_off, na, bd.dout, na, ma.dim, 1, bd.dout, 1, bd.dout, 1, 0, 1, s))) return rc;
-    if ((rc = gemm_simt(T + bd.v_off, Gi, nullptr, U + bd.v_off, na, bd.dout, bd.dout, bd.dout, 1, mg.dim, 1, bd.dout, 1, 0, 1, s))) return rc;
+  // T = A~^-1 V~ ; U = T G~^-1 for all blocks: two grouped launches of the fp32 FMA contraction
+  int max_rows = 0, max_cols = 0;
+  for (const KfBlkDesc& bd : u.blk) {
+    max_rows = bd.din + bd.hb > max_rows ? bd.din + bd.hb : max_rows;
+    max_cols = bd.dout > max_cols ? bd.dout : max_cols;
   }
-  p->launches += 3 + 2 * (long long)u.blk.size();
+  if ((rc = kfac_grouped_gemm(u.d_blk, u.d_mat, (int)u.blk.size(), max_rows, max_cols, inv_small, inv_large, V, T, 0, s))) return rc;
+  if ((rc = kfac_grouped_gemm(u.d_blk, u.d_mat, (int)u.blk.size(), max_rows, max_cols, inv_small, inv_large, T, U, 1, s))) return rc;
+  p->launches += 5;
   return kfac_scatter(u.d_blk, (int)u.blk.size(), u.d_diag, (int)u.diag.size(), U, coef, stats, weight, damping, grads, out, s);
 }

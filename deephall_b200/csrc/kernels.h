@@ -224,6 +224,8 @@ struct KfDiagDesc { long long ko, o, n; };   // diagonal block: parameter offset
 int kfac_damped_factors(const KfBlkDesc* bd, int nblk, const KfMatDesc* md, int nmat, const float* stats, const float* xtx0,
                         float weight, float damping, float* coef, float* batch_s, float* batch_l, cudaStream_t s);
 int kfac_gather(const KfBlkDesc* bd, int nblk, const float* grads, float* V, cudaStream_t s);
+int kfac_grouped_gemm(const KfBlkDesc* bd, const KfMatDesc* md, int nblk, int max_rows, int max_cols, const float* inv_s,
+                      const float* inv_l, const float* X, float* Y, int stage, cudaStream_t s);
 int kfac_scatter(const KfBlkDesc* bd, int nblk, const KfDiagDesc* dd, int ndiag, const float* U, const float* coef,
                  const float* stats, float weight, float damping, const float* grads, float* out, cudaStream_t s);
 // KFAC factor pass (dh_kfac_factors)

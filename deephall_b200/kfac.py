@@ -85,6 +85,16 @@ def _batched_inverses(groups: dict) -> dict:
     return out
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
 def _inverse_batch(batch: torch.Tensor) -> torch.Tensor:
     """In-place inverses of a (count, n, n) batch of SPD matrices by dh_spd_inverse; with more than one rank the matrices are
     dealt out round-robin -- every rank inverts 1/world of them -- and exchanged with one all-gather (the statistics
@@ -157,7 +167,17 @@ def make_kfac_training_step(optim_cfg, loss_grad_fn, network, system=None, norm_
         if pl.kfac_update_shape() is None:
             return precondition_tensor_ops(state, grads)
         coef, ms, ml = pl.kfac_damped_factors(state.stats, state.dense0_xtx, state.weight, damping)
-        return pl.kfac_update(_inverse_batch(ms), _inverse_batch(ml), coef, state.stats, state.weight, damping, grads.contiguous())
+        # the two batches are inverted side by side (27 x 4 + 2 x 8 CTAs at c3: both fit the machine at once)
+        cur = torch.cuda.current_stream()
+        side = _side_stream(grads.device)
+        side.wait_stream(cur)
+        ml.record_stream(side)
+        with torch.cuda.stream(side):
+            inv_l = _inverse_batch(ml)
+        inv_s = _inverse_batch(ms)
+        cur.wait_stream(side)
+        inv_l.record_stream(cur)
+        return pl.kfac_update(inv_s, inv_l, coef, state.stats, state.weight, damping, grads.contiguous())
 
     def precondition_tensor_ops(state: KfacState, grads: torch.Tensor) -> torch.Tensor:
         w = state.weight
