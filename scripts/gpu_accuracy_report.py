@@ -11,13 +11,12 @@ from deephall_b200 import _native as nat  # noqa: E402
 from oracle import jets as OJ  # noqa: E402
 from oracle import psiformer as OP  # noqa: E402
 
-CASES = [("c1", dict(nspins=(3, 0), flux=2), 96, 0.0), ("c2", dict(nspins=(6, 0), flux=15), 64, 1.0),
-         ("c3", dict(nspins=(12, 0), flux=33), 48, 1.0)]
-MODES = [("fp32 FMA (simt)", dict(DH_GEMM_IMPL="simt")),
-         ("fp16 pieces, main+correction accumulators", dict(DH_GEMM_ACC="split")),
-         ("fp16 pieces, one accumulator (default)", dict()),
-         ("fp16 pieces, one accumulator, activations as fp16 hi/lo planes (DH_A_PLANES=1)", dict(DH_A_PLANES="1")),
-         ("tf32 pieces, main+correction accumulators", dict(DH_GEMM_IMPL="tf32"))]
+CASES = [("c1", dict(nspins=(3, 0), flux=2), 256, 0.0), ("c2", dict(nspins=(6, 0), flux=15), 256, 1.0),
+         ("c3", dict(nspins=(12, 0), flux=33), 256, 1.0), ("c4", dict(nspins=(10, 0), flux=21), 128, 1.0),
+         ("c5k4", dict(nspins=(16, 0), flux=45, ndets=4), 48, 1.0)]
+# dh_config.contraction (round 2: no environment switches in the library)
+MODES = [("fp32 FMA", "fp32"), ("fp16 pieces (default: tcgen05 contractions, tensor-core attention, fused epilogues)", "f16"),
+         ("tf32 pieces (range-guard fallback)", "tf32")]
 
 
 def q(v):
@@ -33,11 +32,8 @@ for name, kw, B, kappa in CASES:
     flat32 = OP.flatten_params(p64).float()
     p64 = OP.unflatten_params(flat32.double(), cfg)
     ref = None
-    for label, env in MODES:
-        for k in ("DH_GEMM_IMPL", "DH_GEMM_ACC", "DH_A_PLANES"):
-            os.environ.pop(k, None)
-        os.environ.update(env)
-        plan = nat.Plan(nspins=cfg.nspins, flux=cfg.flux, interaction_strength=kappa)
+    for label, mode in MODES:
+        plan = nat.Plan(nspins=cfg.nspins, flux=cfg.flux, ndets=cfg.ndets, interaction_strength=kappa, contraction=mode)
         flat = flat32.cuda()
         x = plan.init_walkers(B, seed=11)
         plan.mcmc_sweep(flat, x, 30, 0.2, seed=3)
