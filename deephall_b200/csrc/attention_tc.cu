@@ -33,6 +33,20 @@ constexpr int AT_NP = 16;   // padded electron count (one m16 / two n8 tiles)
 constexpr int AT_HD = 64;   // head size this kernel is built for
 constexpr int AT_RC = 10;   // compressed first-layer rows per electron
 
+#ifdef DH_DEBUG_SWITCHES
+// developer builds (make DEBUG=1): per-phase clock sums of thread 0 of every block of the full form, read by dh_debug_at_prof
+// [0] blocks [1] whole kernel [2] score steps: wait + barrier + conversion [3] score steps: multiply [4] score write-out
+// [5] softmax [6] P fragments [7] P.V steps: wait + barrier + conversion [8] P.V steps: multiply + stores
+__device__ unsigned long long g_at_prof[16];
+#define AT_PROF_DECL long long tp_ = clock64(), tp0_ = tp_; (void)tp0_;
+#define AT_LAP(slot) if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(g_at_prof + (slot), (unsigned long long)(t_ - tp_)); tp_ = t_; }
+#define AT_PROF_END if (threadIdx.x == 0) { atomicAdd(g_at_prof + 1, (unsigned long long)(clock64() - tp0_)); atomicAdd(g_at_prof, 1ull); }
+#else
+#define AT_PROF_DECL
+#define AT_LAP(slot)
+#define AT_PROF_END
+#endif
+
 __device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -72,7 +86,11 @@ struct AtGeom {
   static constexpr int SCRATCH = 4 * (5 * N * AT_NP + 11 * 256);  // qq, dd, xw, dw (softmax scratch, in the idle planes)
   static constexpr int PLANES = 4 * PL > SCRATCH ? 4 * PL : SCRATCH;  // q hi | q lo | k hi | k lo  (P.V: v hi | v lo)
   static constexpr int RAW = NR * 64;                       // bytes of 16 fp32 columns of one tensor, as they arrive
-  static constexpr int SJ_J = R * AT_NP + 4;                // floats per key electron in sj (the pad spreads banks)
+  // sj[j][r][i]: jet-row stride 17 and floats per key electron = 4 (mod 16).  The score accumulators leave the fragments as
+  // (row g, column pair t4) per lane: with these strides the 32 lanes of a store hit 32 different banks (strides 16 / 516
+  // put them into 4 banks: 8-way conflicts on every store of the write-out)
+  static constexpr int SJ_R = AT_NP + 1;
+  static constexpr int SJ_J = R * SJ_R + ((4 - R * SJ_R) % 16 + 16) % 16;
   static constexpr int SJ_FLOATS = (N * SJ_J + 3) & ~3;
   // shared memory: planes | raw | sj | p0 [N][16] | red [warp][lane][8]
   //   scores: the raw area of q AND k (2 RAW bytes) runs over sj, which is not live before the last stage is converted
@@ -103,8 +121,8 @@ struct AtStager {
   bool active;
   float amax;                 // largest |x| converted by this thread (fp16 pieces saturate beyond 65504)
   uint32_t raw_off, pl_off;   // of electron egrp
-  int64_t g_off;              // global float offset of electron egrp (full form), column 0
-  __device__ __forceinline__ void init() {
+  int64_t g_own;              // global float offset of this thread's piece of electron egrp (full form with a constant stride)
+  __device__ __forceinline__ void init(int64_t ld) {
     const int slot = threadIdx.x % G::SLOTS;
     egrp = threadIdx.x / G::SLOTS;
     active = egrp < G::EPP;
@@ -113,16 +131,30 @@ struct AtStager {
     q4 = slot & 3;
     raw_off = (uint32_t)(((egrp * G::R + r) * 4 + q4) * 16);
     pl_off = (uint32_t)(egrp * (G::R * 32 + 16) + r * 32 + (((q4 >> 1) ^ ((r >> 2) & 1)) << 4) + ((q4 & 1) << 3));
+    g_own = (int64_t)(egrp * G::R + r) * ld + 4 * q4;
   }
-  // global -> raw (asynchronous); src points at column col0 of row 0 of this walker's tensor
+  // global -> raw (asynchronous); src points at column col0 of row 0 of this walker's tensor.  LDT = the row stride as a
+  // compile-time constant (0: use ld): the copies of a thread then differ by immediates from ONE address (g_own)
+  template <int LDT>
   __device__ __forceinline__ void issue(uint32_t raw_s, const float* __restrict__ src, int64_t ld) const {
     if (active) {
+      if constexpr (!L0 && LDT > 0) {
+        const float* gp0 = src + g_own;
+        const uint32_t dst0 = raw_s + raw_off;
 #pragma unroll
-      for (int e = egrp, k = 0; e < G::N; e += G::EPP, ++k) {
-        const int rc = L0 ? l0_row<NT>(e, r) : r;
-        if (rc >= 0) {
-          const float* gp = src + (int64_t)(e * (L0 ? AT_RC : G::R) + rc) * ld + 4 * q4;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + raw_off + (uint32_t)(k * G::EPP * G::R * 64)), "l"(gp) : "memory");
+        for (int k = 0; k * G::EPP < G::N; ++k) {
+          if (egrp + k * G::EPP < G::N)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(k * G::EPP * G::R * 64)),
+                         "l"(gp0 + (int64_t)k * (G::EPP * G::R) * LDT) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int e = egrp, k = 0; e < G::N; e += G::EPP, ++k) {
+          const int rc = L0 ? l0_row<NT>(e, r) : r;
+          if (rc >= 0) {
+            const float* gp = src + (int64_t)(e * (L0 ? AT_RC : G::R) + rc) * ld + 4 * q4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + raw_off + (uint32_t)(k * G::EPP * G::R * 64)), "l"(gp) : "memory");
+          }
         }
       }
     }
@@ -155,7 +187,7 @@ __device__ __forceinline__ void softmax_jets(float* sj, float* p0, float* qq, fl
   constexpr int N = G::N, NP = AT_NP;
   const int tid = threadIdx.x;
   Rows rw(N, true);
-#define SJ(i, j, r) ((j) * G::SJ_J + (r) * NP + (i))
+#define SJ(i, j, r) ((j) * G::SJ_J + (r) * G::SJ_R + (i))
   for (int i = tid; i < N; i += AT_THREADS) {
     float mx = -INFINITY;
     for (int j = 0; j < N; ++j) mx = fmaxf(mx, sj[SJ(i, j, 0)]);
@@ -204,7 +236,7 @@ __device__ __forceinline__ void softmax_jets(float* sj, float* p0, float* qq, fl
 #undef SJ
 }
 
-template <int NT, bool L0>
+template <int NT, bool L0, int DT>
 __global__ void __launch_bounds__(AT_THREADS, NT <= 12 ? 2 : 1)
 attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, unsigned* __restrict__ rflag) {
   using G = AtGeom<NT>;
@@ -219,8 +251,11 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
   float* dd = qq + N * NP;                                       // [3][j][NP]
   float* xw = dd + 3 * N * NP;                                   // [warp][16 x 16]
   float* dw = xw + AT_WARPS * 256;                               // [3][16 x 16]
-#define SJ(i, j, r) ((j) * G::SJ_J + (r) * NP + (i))
-  const int D = dm.D;
+#define SJ(i, j, r) ((j) * G::SJ_J + (r) * G::SJ_R + (i))
+  // DT = model width as a compile-time constant (0 = read it from dm): with constant row strides the staging copies and the
+  // output stores of a thread differ by immediates, one address register pair serves them all -- the copies of a step used
+  // to wait for one another's address registers (long-scoreboard stalls on the address arithmetic, 10 % of the samples)
+  const int D = DT ? DT : dm.D;
   const int hh = blockIdx.x;
   const int64_t b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -233,8 +268,9 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
   const float scl = rsqrtf((float)AT_HD);
   Rows rw(N, true);
   AtStager<NT, L0> stg;
-  stg.init();
+  stg.init(ld);
   const uint32_t raw_s = sm_u32(raw), pl_s = sm_u32(planes);
+  AT_PROF_DECL
 
   // ------------------------------------------------------------------ phase 1: score jets on the tensor cores
   {
@@ -263,8 +299,8 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
       t_off[ts] = plane_off<R, 32>(arow, a_c);
     }
     const uint32_t xa_off = (uint32_t)(a_e * (R * 32 + 16)), xb_off = (uint32_t)(b_e * (R * 32 + 16));  // + row term of the flow
-    stg.issue(raw_s, qbase, ld);
-    stg.issue(raw_s + G::RAW, kbase, ld);
+    stg.template issue<3 * DT>(raw_s, qbase, ld);
+    stg.template issue<3 * DT>(raw_s + G::RAW, kbase, ld);
 #pragma unroll 1
     for (int st = 0; st < AT_HD / 16; ++st) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -272,9 +308,10 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
       stg.convert(raw, planes, planes + G::PL);
       stg.convert(raw + G::RAW, planes + 2 * G::PL, planes + 3 * G::PL);
       __syncthreads();
+      AT_LAP(2)
       if (st + 1 < AT_HD / 16) {  // the next 16 columns arrive while this stage is multiplied
-        stg.issue(raw_s, qbase + (st + 1) * 16, ld);
-        stg.issue(raw_s + G::RAW, kbase + (st + 1) * 16, ld);
+        stg.template issue<3 * DT>(raw_s, qbase + (st + 1) * 16, ld);
+        stg.template issue<3 * DT>(raw_s + G::RAW, kbase + (st + 1) * 16, ld);
       } else {
         for (int t = tid; t < G::SJ_FLOATS; t += AT_THREADS) sj[t] = 0.f;  // (the raw area of k ran over sj until now)
       }
@@ -315,6 +352,7 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
           mma16816(da[0], ah, bh[0], bh[1]); mma16816(da[1], ah, bh[2], bh[3]);
         }
       }
+      AT_LAP(3)
     }
     __syncthreads();  // every warp is done with the planes (xw, dw live there) and sj is zeroed
     // accumulators -> sj: every entry has exactly one G1 term (stored first) and, for r > 0, one G2 term (added after a
@@ -348,7 +386,7 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
         xw[warp * 256 + idx] = xa[nt][c];
         if (fd < 3) dw[fd * 256 + idx] = da[nt][c];
       }
-    stg.issue(raw_s, vbase, ld);  // the first 16 columns of v arrive during the softmax
+    stg.template issue<3 * DT>(raw_s, vbase, ld);  // the first 16 columns of v arrive during the softmax
     __syncthreads();
 #pragma unroll
     for (int ts = 0; ts < G::TPW; ++ts) {
@@ -390,7 +428,9 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
   }
   __syncthreads();
   // ------------------------------------------------------------------ phase 2: softmax jets (as attention_jets.cu)
+  AT_LAP(4)
   softmax_jets<NT>(sj, p0, qq, dd);
+  AT_LAP(5)
   // ------------------------------------------------------------------ phase 3: o = P V jets on the tensor cores
   {
     const uint32_t vh_s = pl_s, vl_s = pl_s + G::PL;
@@ -462,12 +502,18 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
     };
 #pragma unroll 1
     for (int qt = 0; qt < AT_HD / 16; ++qt) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (qt == 0) { AT_LAP(6) } else { AT_LAP(8) }
+      // v steps arrive two deep: step qt lies in raw half qt & 1 (the second half runs over sj, which is dead once the P
+      // fragments are in registers), steps qt + 1 and, from here on, qt + 2 are in flight while step qt is multiplied
+      if (qt == 0 || qt + 1 == AT_HD / 16) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();  // the planes are free (softmax scratch / previous step's fragments) and `red` is complete
       if (qt > 0) finish_s(qt - 1);
-      stg.convert(raw, planes, planes + G::PL);
+      stg.convert(raw + (qt & 1) * G::RAW, planes, planes + G::PL);
       __syncthreads();  // (also: `red` has been read before this step's partials overwrite it)
-      if (qt + 1 < AT_HD / 16) stg.issue(raw_s, vbase + (qt + 1) * 16, ld);
+      AT_LAP(7)
+      if (qt == 0 && AT_HD / 16 > 1) stg.template issue<3 * DT>(raw_s + G::RAW, vbase + 16, ld);
+      if (qt + 2 < AT_HD / 16) stg.template issue<3 * DT>(raw_s + (qt & 1) * G::RAW, vbase + (qt + 2) * 16, ld);
       uint32_t v0h[4], v0l[4];
       vfrag(0, v0h, v0l);
       float sx[2][4];
@@ -540,6 +586,8 @@ attention_jets_tc_kernel(const float* __restrict__ qkv, float* __restrict__ o, N
   }
   // the fp16 pieces have a narrower range than the reference's fp32: a saturated operand is reported (dh_plan_status)
   if (rflag != nullptr && !(stg.amax <= 65504.f)) atomicOr(rflag, 1u);
+  AT_LAP(8)
+  AT_PROF_END
 #undef SJ
 }
 
@@ -582,7 +630,8 @@ struct AtStagerC {
   bool active;
   float amax;
   uint32_t raw_off, pl_off;
-  __device__ __forceinline__ void init() {
+  int64_t g_own;
+  __device__ __forceinline__ void init(int64_t ld) {
     const int slot = threadIdx.x % G::SLOTS;
     egrp = threadIdx.x / G::SLOTS;
     active = egrp < G::EPP;
@@ -591,13 +640,26 @@ struct AtStagerC {
     q4 = slot & 3;
     raw_off = (uint32_t)(((egrp * G::RC + c) * 4 + q4) * 16);
     pl_off = plane_off_c<NT>(egrp, c, q4 >> 1) + (uint32_t)((q4 & 1) << 3);
+    g_own = (int64_t)(egrp * G::RC + c) * ld + 4 * q4;
   }
+  template <int LDT>
   __device__ __forceinline__ void issue(uint32_t raw_s, const float* __restrict__ src, int64_t ld) const {
     if (active) {
+      if constexpr (LDT > 0) {  // constant row stride: one address, immediates (see AtStager)
+        const float* gp0 = src + g_own;
+        const uint32_t dst0 = raw_s + raw_off;
 #pragma unroll
-      for (int e = egrp, k = 0; e < G::N; e += G::EPP, ++k) {
-        const float* gp = src + (int64_t)(e * G::RC + c) * ld + 4 * q4;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + raw_off + (uint32_t)(k * G::EPP * G::RC * 64)), "l"(gp) : "memory");
+        for (int k = 0; k * G::EPP < G::N; ++k) {
+          if (egrp + k * G::EPP < G::N)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(k * G::EPP * G::RC * 64)),
+                         "l"(gp0 + (int64_t)k * (G::EPP * G::RC) * LDT) : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int e = egrp, k = 0; e < G::N; e += G::EPP, ++k) {
+          const float* gp = src + (int64_t)(e * G::RC + c) * ld + 4 * q4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_s + raw_off + (uint32_t)(k * G::EPP * G::RC * 64)), "l"(gp) : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -619,7 +681,7 @@ struct AtStagerC {
   }
 };
 
-template <int NT>
+template <int NT, int DT>
 __global__ void __launch_bounds__(AT_THREADS, NT <= 12 ? 2 : 1)
 attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o, NetDims dm, unsigned* __restrict__ rflag) {
   using G = AtGeomC<NT>;
@@ -635,8 +697,8 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
   float* dd = qq + N * NP;
   float* xw = dd + 3 * N * NP;      // [warp][16 x 16]: own-flow cross products (warps 0, 1)
   float* dw = xw + AT_WARPS * 256;  // [3][16 x 16]
-#define SJ(i, j, r) ((j) * GF::SJ_J + (r) * NP + (i))
-  const int D = dm.D;
+#define SJ(i, j, r) ((j) * GF::SJ_J + (r) * GF::SJ_R + (i))
+  const int D = DT ? DT : dm.D;  // (compile-time row strides: see attention_jets_tc_kernel)
   const int hh = blockIdx.x;
   const int64_t b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -651,7 +713,7 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
   // full jet row of compressed row c of electron e
   auto full_row = [&](int e, int c) { return c == 0 ? 0 : (c <= 2 ? 2 * e + c : (c == 3 ? rS : (c <= 6 ? rD0 + (c - 4) : rT0 + (c - 7)))); };
   AtStagerC<NT> stg;
-  stg.init();
+  stg.init(ld);
   const uint32_t raw_s = sm_u32(raw), pl_s = sm_u32(planes);
   for (int t = tid; t < GF::SJ_FLOATS; t += AT_THREADS) sj[t] = 0.f;
 
@@ -684,8 +746,8 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
     //              warp 2 + a -> D_a (compressed row 4 + a)
     const int xc = warp < 2 ? 1 + warp : 4 + (warp - 2);
     const uint32_t xa_off = plane_off_c<NT>(a_e, xc, a_c), xb_off = plane_off_c<NT>(b_e, xc, b_c);
-    stg.issue(raw_s, qbase, ld);
-    stg.issue(raw_s + G::RAW, kbase, ld);
+    stg.template issue<3 * DT>(raw_s, qbase, ld);
+    stg.template issue<3 * DT>(raw_s + G::RAW, kbase, ld);
 #pragma unroll 1
     for (int st = 0; st < AT_HD / 16; ++st) {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -694,8 +756,8 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
       stg.convert(raw + G::RAW, planes + 2 * G::PL, planes + 3 * G::PL);
       __syncthreads();
       if (st + 1 < AT_HD / 16) {
-        stg.issue(raw_s, qbase + (st + 1) * 16, ld);
-        stg.issue(raw_s + G::RAW, kbase + (st + 1) * 16, ld);
+        stg.template issue<3 * DT>(raw_s, qbase + (st + 1) * 16, ld);
+        stg.template issue<3 * DT>(raw_s + G::RAW, kbase + (st + 1) * 16, ld);
       }
       uint32_t k0h[4], k0l[4], q0h[4], q0l[4];
       ldsm_x4(kh_s + b0_off, k0h); ldsm_x4(kl_s + b0_off, k0l);
@@ -759,7 +821,7 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
         xw[warp * 256 + idx] = xa[nt][c];
         if (warp >= 2 && warp < 5) dw[(warp - 2) * 256 + idx] = da[nt][c];
       }
-    stg.issue(raw_s, vbase, ld);
+    stg.template issue<3 * DT>(raw_s, vbase, ld);
     __syncthreads();
     // G2: k_e^(c) . q_x -> s^(r)_{x e}   (r > 0; the entry (e, e, r) already holds its G1 term)
 #pragma unroll
@@ -867,12 +929,15 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
     };
 #pragma unroll 1
     for (int qt = 0; qt < AT_HD / 16; ++qt) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      // v steps arrive two deep, step qt in raw half qt & 1 (see the full form)
+      if (qt == 0 || qt + 1 == AT_HD / 16) asm volatile("cp.async.wait_group 0;" ::: "memory");
+      else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
       if (qt > 0) finish_s(qt - 1);
-      stg.convert(raw, planes, planes + G::PL);
+      stg.convert(raw + (qt & 1) * G::RAW, planes, planes + G::PL);
       __syncthreads();
-      if (qt + 1 < AT_HD / 16) stg.issue(raw_s, vbase + (qt + 1) * 16, ld);
+      if (qt == 0 && AT_HD / 16 > 1) stg.template issue<3 * DT>(raw_s + G::RAW, vbase + 16, ld);
+      if (qt + 2 < AT_HD / 16) stg.template issue<3 * DT>(raw_s + (qt & 1) * G::RAW, vbase + (qt + 2) * 16, ld);
       uint32_t v0h[4], v0l[4];
       vfrag(0, v0h, v0l);
       float sx[2][4];
@@ -967,35 +1032,45 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
 #undef SJ
 }
 
-template <int NT>
+template <int NT, int DT>
 int launch_at_l0(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
   using G = AtGeomC<NT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_jets_tc_l0_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_jets_tc_l0_kernel<NT, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
   dim3 grid((unsigned)d.H, (unsigned)B);
-  attention_jets_tc_l0_kernel<NT><<<grid, AT_THREADS, G::SMEM, s>>>(qkv, o, d, range_flag_get());
+  attention_jets_tc_l0_kernel<NT, DT><<<grid, AT_THREADS, G::SMEM, s>>>(qkv, o, d, range_flag_get());
   return (int)cudaGetLastError();
 }
 
-template <int NT, bool L0>
+template <int NT, int DT>
 int launch_at(const float* qkv, float* o, int64_t B, NetDims d, cudaStream_t s) {
   using G = AtGeom<NT>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(attention_jets_tc_kernel<NT, L0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_jets_tc_kernel<NT, false, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_done = true;
   }
   dim3 grid((unsigned)d.H, (unsigned)B);
-  attention_jets_tc_kernel<NT, L0><<<grid, AT_THREADS, G::SMEM, s>>>(qkv, o, d, range_flag_get());
+  attention_jets_tc_kernel<NT, false, DT><<<grid, AT_THREADS, G::SMEM, s>>>(qkv, o, d, range_flag_get());
   return (int)cudaGetLastError();
 }
 
+
 }  // namespace
+
+#ifdef DH_DEBUG_SWITCHES
+extern "C" int dh_debug_at_prof(unsigned long long* host16, int reset) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && host16) e = cudaMemcpyFromSymbol(host16, g_at_prof, 16 * sizeof(unsigned long long));
+  if (e == cudaSuccess && reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_at_prof, z, sizeof(z)); }
+  return (int)e;
+}
+#endif
 
 // The tensor-core form exists for head size 64 and the electron counts of the BASELINE configurations.
 bool attention_jets_tc_ok(NetDims d) {
@@ -1004,7 +1079,9 @@ bool attention_jets_tc_ok(NetDims d) {
 
 int attention_jets_tc(const float* qkv, float* o, int64_t B, NetDims d, int layer0, cudaStream_t s) {
   if (!attention_jets_tc_ok(d)) return -2;
-#define DH_AT(NT) (layer0 ? launch_at_l0<NT>(qkv, o, B, d, s) : launch_at<NT, false>(qkv, o, B, d, s))
+  // the default width (D = 256) has its own instantiation with compile-time row strides
+#define DH_AT(NT) (d.D == 256 ? (layer0 ? launch_at_l0<NT, 256>(qkv, o, B, d, s) : launch_at<NT, 256>(qkv, o, B, d, s)) \
+                              : (layer0 ? launch_at_l0<NT, 0>(qkv, o, B, d, s) : launch_at<NT, 0>(qkv, o, B, d, s)))
   switch (d.N) {
     case 3: return DH_AT(3);
     case 6: return DH_AT(6);
