@@ -34,7 +34,7 @@ constexpr int AT_HD = 64;   // head size this kernel is built for
 constexpr int AT_RC = 10;   // compressed first-layer rows per electron
 
 #ifdef DH_DEBUG_SWITCHES
-// developer builds (make DEBUG=1): per-phase clock sums of thread 0 of every block of the full form, read by dh_debug_at_prof
+// developer builds (make DEBUG=1): per-phase clock sums of thread 0 of every block (both kernels add into the same slots), read by dh_debug_at_prof
 // [0] blocks [1] whole kernel [2] score steps: wait + barrier + conversion [3] score steps: multiply [4] score write-out
 // [5] softmax [6] P fragments [7] P.V steps: wait + barrier + conversion [8] P.V steps: multiply + stores
 __device__ unsigned long long g_at_prof[16];
@@ -714,6 +714,7 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
   auto full_row = [&](int e, int c) { return c == 0 ? 0 : (c <= 2 ? 2 * e + c : (c == 3 ? rS : (c <= 6 ? rD0 + (c - 4) : rT0 + (c - 7)))); };
   AtStagerC<NT> stg;
   stg.init(ld);
+  AT_PROF_DECL
   const uint32_t raw_s = sm_u32(raw), pl_s = sm_u32(planes);
   for (int t = tid; t < GF::SJ_FLOATS; t += AT_THREADS) sj[t] = 0.f;
 
@@ -755,6 +756,7 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
       stg.convert(raw, planes, planes + G::PL);
       stg.convert(raw + G::RAW, planes + 2 * G::PL, planes + 3 * G::PL);
       __syncthreads();
+      AT_LAP(2)
       if (st + 1 < AT_HD / 16) {
         stg.template issue<3 * DT>(raw_s, qbase + (st + 1) * 16, ld);
         stg.template issue<3 * DT>(raw_s + G::RAW, kbase + (st + 1) * 16, ld);
@@ -790,6 +792,7 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
           mma16816(da[0], ah, bh[0], bh[1]); mma16816(da[1], ah, bh[2], bh[3]);
         }
       }
+      AT_LAP(3)
     }
     __syncthreads();  // every warp is done with the planes (xw, dw live there); sj was zeroed at the start
     // G1: q_e^(c) . k_x -> s^(r)_{e x}
@@ -861,7 +864,9 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
   }
   __syncthreads();
   // ------------------------------------------------------------------ phase 2: softmax jets
+  AT_LAP(4)
   softmax_jets<NT>(sj, p0, qq, dd);
+  AT_LAP(5)
   // ------------------------------------------------------------------ phase 3: o = P V jets
   {
     const uint32_t vh_s = pl_s, vl_s = pl_s + G::PL;
@@ -930,12 +935,14 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
 #pragma unroll 1
     for (int qt = 0; qt < AT_HD / 16; ++qt) {
       // v steps arrive two deep, step qt in raw half qt & 1 (see the full form)
+      if (qt == 0) { AT_LAP(6) } else { AT_LAP(8) }
       if (qt == 0 || qt + 1 == AT_HD / 16) asm volatile("cp.async.wait_group 0;" ::: "memory");
       else asm volatile("cp.async.wait_group 1;" ::: "memory");
       __syncthreads();
       if (qt > 0) finish_s(qt - 1);
       stg.convert(raw + (qt & 1) * G::RAW, planes, planes + G::PL);
       __syncthreads();
+      AT_LAP(7)
       if (qt == 0 && AT_HD / 16 > 1) stg.template issue<3 * DT>(raw_s + G::RAW, vbase + 16, ld);
       if (qt + 2 < AT_HD / 16) stg.template issue<3 * DT>(raw_s + (qt & 1) * G::RAW, vbase + (qt + 2) * 16, ld);
       uint32_t v0h[4], v0l[4];
@@ -1029,6 +1036,8 @@ attention_jets_tc_l0_kernel(const float* __restrict__ qkv, float* __restrict__ o
     finish_s(AT_HD / 16 - 1);
   }
   if (rflag != nullptr && !(stg.amax <= 65504.f)) atomicOr(rflag, 1u);
+  AT_LAP(8)
+  AT_PROF_END
 #undef SJ
 }
 

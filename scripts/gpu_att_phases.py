@@ -7,7 +7,9 @@ sys.path.insert(0, ".")
 from deephall_b200 import _native as nat
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-plan = nat.Plan(nspins=(12, 0), flux=33)
+# "l0" as second argument: a one-layer network, so that only the first-layer kernel runs (both kernels add into the same slots)
+L0_ONLY = len(sys.argv) > 2 and sys.argv[2] == "l0"
+plan = nat.Plan(nspins=(12, 0), flux=33, **({"num_layers": 1} if L0_ONLY else {}))
 lib = nat.load()
 torch.manual_seed(0)
 params = torch.randn(plan.num_params, device="cuda") * 0.05
