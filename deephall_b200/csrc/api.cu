@@ -236,8 +236,20 @@ extern "C" int dh_plan_create(const dh_config* cfg, dh_plan** out) {
       const int n_alpha = p->nsb == 1 ? N : (sbk == 0 ? cfg->n_up : cfg->n_dn);
       for (int part = 0; part < 2; ++part) {
         const int t = 2 * sbk + part;
-        p->kf_orb[t] = dense(ob + "DenseGeneral_" + std::to_string(t) + "/kernel", p->orb_k[t], p->orb_b[t], D, p->LNK, n_alpha, xb, sbs);
+        // (sparse orbitals, blocks.py:52-56: the projection's own output is the 8-feature tensor [8][N][K])
+        p->kf_orb[t] = dense(ob + "DenseGeneral_" + std::to_string(t) + "/kernel", p->orb_k[t], p->orb_b[t], D,
+                             p->sparse ? 8 * N * K : p->LNK, n_alpha, xb, sbs);
       }
+    }
+    // sparse orbitals: `lll_weight` is a DenseGeneral over axis 1 of a complex tensor (blocks.py:57): its dot_general
+    // has the dimension numbers of none of optimizers/kfac.py:148-195's patterns, so kernel and bias fall to kfac_jax's
+    // generic tag like the Jastrow parameters -- naive diagonal, the factor vector carries the batch-summed gradient
+    p->kf_lllk = p->kf_lllb = -1;
+    if (p->sparse) {
+      p->kf_lllk = diag("Orbitals_0/lll_weight/kernel", p->lll_k, 8 * L);
+      p->kf_lllb = diag("Orbitals_0/lll_weight/bias", p->lll_b, L);
+      p->kfac[p->kf_lllk].kind = 2;
+      p->kfac[p->kf_lllb].kind = 2;
     }
     // no layer pattern matches the Jastrow parameters: kfac_jax's generic tag, whose diagonal is "naive" -- the square of
     // the batch-summed gradient; the factor vector carries that sum (kind 2)

@@ -220,7 +220,18 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
         RUN(PC_OTHER, colsum_add(xin, kf + e.xsum_offset, rows, D, D, s));
         for (int part = 0; part < 2; ++part) {
           const int t = 2 * sbk + part;
-          if ((rc = gram(p, w.gCb + (size_t)t * LNK, ldg, LNK, kf + K(p->kf_orb[t]).gtg_offset, rows, s, true))) return rc;
+          if (!p->sparse) {
+            if ((rc = gram(p, w.gCb + (size_t)t * LNK, ldg, LNK, kf + K(p->kf_orb[t]).gtg_offset, rows, s, true))) return rc;
+          } else {
+            // sparse orbitals: the block's output is the 8-feature tensor; its gradient is the effective coefficients'
+            // gradient contracted with lll_weight (gQKV is free until the layer loop)
+            const int F8 = 8 * N * p->K;
+            RUN(PC_OTHER, sparse_g8(w.gCb + (size_t)t * LNK, ldg, P + p->lll_k, w.gQKV, rows, p->L, N * p->K, s));
+            if ((rc = gram(p, w.gQKV, F8, F8, kf + K(p->kf_orb[t]).gtg_offset, rows, s, true))) return rc;
+            // the batch-summed gradient of lll_weight (naive-diagonal blocks) comes out of the effective kernels' gradients
+            if ((rc = dense_bwd_w(p, hf, D, w.gCb + (size_t)t * LNK, ldg, LNK, orbGW(p, grad, t), rows, s))) return rc;
+            RUN(PC_OTHER, colsum_add(w.gCb + (size_t)t * LNK, orbGB(p, grad, t), rows, LNK, ldg, s));
+          }
         }
       }
     }
@@ -303,13 +314,17 @@ static int vjp_core(dh_plan* p, const float* P, const float* x, int64_t B, const
       if (idx[t] >= 0)
         DH_CHECK(cudaMemcpyAsync(kf + K(idx[t]).diag_offset, grad + src[t], sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
-  if (p->sparse && !kf) {
+  if (p->sparse) {  // (factor pass: only the lll_weight part of the result is used, below)
     for (int t = 0; t < 2 * p->nsb; ++t) {
       ProfScope ps(p, PC_OTHER, 0, s, 2);
       if ((rc = sparse_fold_bwd(orbGW(p, grad, t), P + p->orb_k[t], P + p->orb_b[t], P + p->lll_k, (t & 1) == 0 ? 1 : 0,
                                 grad + p->orb_k[t], grad + p->orb_b[t], grad + p->lll_k, grad + p->lll_b, D, p->L, N * p->K, s)))
         return rc;
     }
+  }
+  if (kf && p->sparse) {
+    DH_CHECK(cudaMemcpyAsync(kf + K(p->kf_lllk).diag_offset, grad + p->lll_k, (size_t)8 * p->L * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    DH_CHECK(cudaMemcpyAsync(kf + K(p->kf_lllb).diag_offset, grad + p->lll_b, (size_t)p->L * sizeof(float), cudaMemcpyDeviceToDevice, s));
   }
 #undef RUN
   if (B <= chunk) p->vjp_fwd = dh_plan::FwdKey{P, x, B, ws, true};  // one chunk: its activations stay in the workspace
@@ -341,7 +356,7 @@ extern "C" int dh_kfac_layout(const dh_plan* p, dh_kfac_entry* entries, int32_t*
 extern "C" int dh_kfac_factors(dh_plan* p, const float* P, const float* x, int64_t B, float* factors, void* ws,
                                size_t ws_bytes, void* stream) {
   if (!p) return DH_E_BADARG;
-  if (p->laughlin || p->sparse) return DH_E_UNSUPPORTED;
+  if (p->laughlin || (p->sparse && 8 * p->N * p->K > 3 * p->D)) return DH_E_UNSUPPORTED;
   if (!P || !factors || B < 0 || (B > 0 && !x)) return DH_E_BADARG;
   return vjp_core(p, P, x, B, nullptr, nullptr, factors, nullptr, ws, ws_bytes, (cudaStream_t)stream);
 }
@@ -349,7 +364,7 @@ extern "C" int dh_kfac_factors(dh_plan* p, const float* P, const float* x, int64
 extern "C" int dh_kfac_factors_reuse_forward(dh_plan* p, const float* P, const float* x, int64_t B, float* factors, void* ws,
                                              size_t ws_bytes, void* stream) {
   if (!p) return DH_E_BADARG;
-  if (p->laughlin || p->sparse) return DH_E_UNSUPPORTED;
+  if (p->laughlin || (p->sparse && 8 * p->N * p->K > 3 * p->D)) return DH_E_UNSUPPORTED;
   if (!P || !factors || B < 0 || (B > 0 && !x)) return DH_E_BADARG;
   return vjp_core(p, P, x, B, nullptr, nullptr, factors, nullptr, ws, ws_bytes, (cudaStream_t)stream, true);
 }
@@ -361,7 +376,7 @@ static constexpr int KFU_SMALL = 288;
 static int kfac_update_tables(dh_plan* p) {
   auto& u = p->kfu;
   if (u.ready) return u.ready > 0 ? 0 : DH_E_UNSUPPORTED;
-  if (p->laughlin || p->sparse || p->kfac.empty()) { u.ready = -1; return DH_E_UNSUPPORTED; }
+  if (p->laughlin || p->kfac.empty()) { u.ready = -1; return DH_E_UNSUPPORTED; }
   for (const auto& e : p->kfac)
     if (e.kind == 0 && (e.in_dim + e.has_bias > 1024 || e.out_dim > 1024)) { u.ready = -1; return DH_E_UNSUPPORTED; }
   for (const auto& e : p->kfac) {

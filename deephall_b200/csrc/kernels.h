@@ -160,6 +160,9 @@ int sparse_fold(const float* W8, const float* b8, const float* Wl, const float* 
                 int NK, cudaStream_t s);
 int sparse_fold_bwd(const float* g_Weff, const float* W8, const float* b8, const float* Wl, int add_bl, float* g_W8,
                     float* g_b8, float* g_Wl, float* g_bl, int D, int L, int NK, cudaStream_t s);
+// g8[row][s][jk] = sum_m g[row][m][jk] Wl[s][m]: the gradient with respect to the 8-feature projection's own output
+// (the KFAC output factor of the sparse orbitals); g rows have stride ldg, g8 rows 8 NK
+int sparse_g8(const float* g, int64_t ldg, const float* Wl, float* g8, int64_t rows, int L, int NK, cudaStream_t s);
 int potential(const float* x, float* out, int64_t B, int N, float Q, float radius, int interaction_type,
               cudaStream_t s);
 int slogdet_batched(const float* mats, int64_t B, int K, int n, float* out_sign, float* out_logabs,

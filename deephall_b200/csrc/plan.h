@@ -49,7 +49,7 @@ struct dh_plan {
   // KFAC curvature blocks (dh_kfac_layout / dh_kfac_factors)
   std::vector<dh_kfac_entry> kfac;
   std::vector<KfLayer> kf_layer;
-  int kf_dense0, kf_orb[4], kf_eepar, kf_eeanti;
+  int kf_dense0, kf_orb[4], kf_eepar, kf_eeanti, kf_lllk, kf_lllb;
   int64_t kfac_floats;
   // The activations of the last reverse pass's forward (dh_logpsi_vjp / dh_kfac_factors, single chunk) are still in the
   // caller's workspace: dh_kfac_factors_reuse_forward may skip its forward.  Cleared by every other op of the plan.

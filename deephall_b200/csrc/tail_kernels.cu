@@ -200,6 +200,30 @@ __global__ void sparse_fold_bwd_wl_kernel(const float* __restrict__ g, const flo
     }
   }
 }
+__global__ void __launch_bounds__(256)
+sparse_g8_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ Wl, float* __restrict__ g8, int64_t rows,
+                 int L, int NK) {
+  extern __shared__ float wl_s[];  // [8][L]
+  for (int t = threadIdx.x; t < 8 * L; t += blockDim.x) wl_s[t] = Wl[t];
+  __syncthreads();
+  const int64_t total = rows * 8 * NK;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = t / (8 * NK);
+    const int r = (int)(t - row * 8 * NK), sft = r / NK, jk = r - sft * NK;
+    const float* gr = g + row * ldg + jk;
+    float acc = 0.f;
+    for (int m = 0; m < L; ++m) acc = fmaf(gr[(size_t)m * NK], wl_s[sft * L + m], acc);
+    g8[t] = acc;
+  }
+}
+int sparse_g8(const float* g, int64_t ldg, const float* Wl, float* g8, int64_t rows, int L, int NK, cudaStream_t s) {
+  const int64_t total = rows * 8 * NK;
+  if (total <= 0) return 0;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  sparse_g8_kernel<<<(unsigned)blocks, 256, 8 * L * sizeof(float), s>>>(g, ldg, Wl, g8, rows, L, NK);
+  return (int)cudaGetLastError();
+}
 int sparse_fold(const float* W8, const float* b8, const float* Wl, const float* bl, int add_bl, float* Weff, int D, int L,
                 int NK, cudaStream_t s) {
   sparse_fold_kernel<<<D + 1, 256, 0, s>>>(W8, b8, Wl, bl, add_bl, Weff, D, L, NK);

@@ -93,8 +93,10 @@ enum dh_op { DH_OP_LOGPSI = 0, DH_OP_LOCAL_ENERGY = 1, DH_OP_MCMC = 2, DH_OP_VJP
  *         inputs are the four features of psiformer.py:51-60).  Layers that share their input share xtx / xsum.
  * kind 1: LayerNorm scale / bias (kfac_jax's scale-and-shift blocks): diagonal Fisher from per-walker gradients,
  *         sum_b (d Re log psi_b / d theta)^2 at diag_offset, `size` entries.
- * kind 2: a parameter no layer pattern matches (Jastrow ee_par / ee_anti; kfac_jax's generic tag with its "naive"
- *         diagonal = square of the batch-summed gradient): sum_b d Re log psi_b / d theta at diag_offset. */
+ * kind 2: a parameter no layer pattern matches (Jastrow ee_par / ee_anti, and lll_weight kernel / bias of the sparse
+ *         orbitals, blocks.py:57: a DenseGeneral over axis 1; kfac_jax's generic tag with its "naive" diagonal = square
+ *         of the batch-summed gradient): sum_b d Re log psi_b / d theta at diag_offset, `size` entries.
+ * Sparse orbitals: the kind-0 blocks of the orbital projections have out_dim = 8 N K (their own 8-feature output). */
 typedef struct dh_kfac_entry {
   char name[96];             /* parameter path of the kernel (kind 0) or of the parameter (kind 1)      */
   int32_t kind, in_dim, out_dim, has_bias, rows_per_walker;

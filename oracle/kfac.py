@@ -12,6 +12,10 @@ optimizer step, so this is a restatement of the PUBLISHED algorithm -- PARITY UN
   curvature is fixed_scale * A (x) G with fixed_scale = number of electrons that pass through the layer;
 * LayerNorm scale / bias: scale-and-shift diagonal blocks, mean_b[(per-walker gradient)^2];
 * Jastrow ee_par / ee_anti: no pattern -> generic tag -> naive diagonal (batch-summed gradient)^2 / batch;
+* sparse orbitals (`blocks.py:52-62`): the 8-feature projections are repeated-dense blocks like the full ones (output
+  [8][N][K]); `lll_weight` = `nn.DenseGeneral(2Q+1, axis=1)` on a COMPLEX tensor contracts axis 1 of a 4-d operand, the
+  dimension numbers of none of `optimizers/kfac.py:148-195`'s example graphs (they contract the last axis; its
+  `repeated_dense_complex_no_bias` is 3-d, last axis) -> generic tag for kernel and bias, like the Jastrow parameters;
 * factors are exponential moving averages with weight de-biasing, the damped inverse of a Kronecker pair is the
   pi-adjusted factored Tikhonov form with average-trace norms, and the update is
   -lr * min(1, sqrt(norm_constraint / (lr^2 <P g, g>))) * P g.
@@ -90,16 +94,20 @@ def layer_io(params, x, cfg: OP.NetCfg):
         h = lnorm(f"{p}LayerNorm_{2 * l + 1}/", h + torch.tanh(z))
     o = "Orbitals_0/featured_orbitals/"
     N, L, K = cfg.nelec, cfg.norb, cfg.ndets
+    F = L if cfg.orbital_type == "full" else 8  # blocks.py:47-56: sparse orbitals project to 8 features first
     cs, idx, start = [], 0, 0
     for n_alpha in cfg.nspins:
         if n_alpha:
             ha = h[..., start : start + n_alpha, :]
-            re = dense(f"{o}DenseGeneral_{idx}/kernel", ha, f"{o}DenseGeneral_{idx}/bias", (D, L * N * K))
-            im = dense(f"{o}DenseGeneral_{idx + 1}/kernel", ha, f"{o}DenseGeneral_{idx + 1}/bias", (D, L * N * K))
-            cs.append(torch.complex(re, im).reshape(*ha.shape[:-1], L, N, K))
+            re = dense(f"{o}DenseGeneral_{idx}/kernel", ha, f"{o}DenseGeneral_{idx}/bias", (D, F * N * K))
+            im = dense(f"{o}DenseGeneral_{idx + 1}/kernel", ha, f"{o}DenseGeneral_{idx + 1}/bias", (D, F * N * K))
+            cs.append(torch.complex(re, im).reshape(*ha.shape[:-1], F, N, K))
             idx += 2
         start += n_alpha
     c = torch.cat(cs, dim=-4)
+    if cfg.orbital_type == "sparse":  # blocks.py:57,61-62: real (8, L) kernel and bias on the complex 8-feature tensor
+        wl, bl = params["Orbitals_0/lll_weight/kernel"], params["Orbitals_0/lll_weight/bias"]
+        c = torch.einsum("...nsjk,sl->...nljk", c, wl.to(c.dtype)) + bl.to(c.dtype)[:, None, None]
     env = OP.envelope(x, cfg)
     orb = torch.movedim((c * env[..., None, None]).sum(-3), -1, -3)
     jas = OP.jastrow(params, x, cfg)
@@ -134,7 +142,7 @@ def curvature_stats(params_flat, x, cfg: OP.NetCfg):
     off = 0
     for name, shape in OP.param_shapes(cfg).items():
         n = int(torch.tensor(shape).prod())
-        if name.startswith("Jastrow_0/"):
+        if name.startswith("Jastrow_0/") or name.startswith("Orbitals_0/lll_weight/"):
             diag[name] = t2 * pf.grad[off : off + n] ** 2 / B  # naive diagonal: (batch-summed gradient)^2 / batch
         off += n
     return dense, diag

@@ -787,6 +787,9 @@ def test_facade_spin_unpolarised_sparse_orbitals(nat):
 KFAC_CASES = {
     "pol": dict(nspins=(3, 0), flux=2, ndets=2, num_heads=2, heads_dim=16, num_layers=1),
     "spin": dict(nspins=(2, 1), flux=4, num_heads=2, heads_dim=16, num_layers=2),
+    # sparse orbitals (blocks.py:52-62): 8-feature projections as dense blocks, lll_weight as naive-diagonal blocks
+    "sparse": dict(nspins=(4, 0), flux=9, num_heads=2, heads_dim=16, num_layers=1, orbital_type="sparse"),
+    "sparse_spin": dict(nspins=(2, 2), flux=5, ndets=2, num_heads=2, heads_dim=16, num_layers=1, orbital_type="sparse"),
 }
 
 
@@ -881,6 +884,38 @@ def test_kfac_training_step_matches_the_restated_update(nat):
         energies.append(float(st["energy"].real))
     assert all(math.isfinite(e) for e in energies)
     assert sum(energies[-5:]) / 5 < sum(energies[:5]) / 5 and abs(sum(energies[-5:]) / 5 - 1.5) < 0.15, energies
+
+
+def test_kfac_training_step_with_sparse_orbitals(nat):
+    """optimizer=kfac (the reference default) with orbital=sparse (blocks.py:52-62): two steps against oracle/kfac.py -- the
+    8-feature projections as repeated-dense blocks, lll_weight kernel / bias as naive-diagonal blocks -- through the
+    library update route (dh_kfac_damped_factors -> dh_spd_inverse -> dh_kfac_update)."""
+    from deephall_b200 import loss, mcmc, networks, optimizers
+    from deephall_b200.config import Config, Network, Optim, PsiformerNetwork, System
+    from oracle import kfac as OK
+
+    system = System(flux=5, nspins=(2, 2))
+    net = Network(orbital="sparse", psiformer=PsiformerNetwork(num_heads=2, heads_dim=16, num_layers=1, determinants=2))
+    cfgt = Config(batch_size=128, seed=3, system=system, network=net, optim=Optim(iterations=4, optimizer="kfac"))
+    model = networks.make_network(system, net)
+    params = model.init(2)
+    B = 128
+    data = mcmc.init_guess(0, B, 4, model)
+    data, _ = mcmc.make_mcmc_step(model.apply, B, steps=10)(params, data, mcmc.PhiloxKey(2), 0.3)
+    assert model.plan(system).kfac_update_shape() is not None
+    init, step = optimizers.make_optimizer_step(cfgt, model.apply)
+    state = optimizers.CheckpointState(params, data, init(params, None, data), 0.1)
+    cfg = OP.NetCfg(nspins=(2, 2), flux=5, ndets=2, num_heads=2, heads_dim=16, num_layers=1, orbital_type="sparse")
+    ok = OK.Kfac(cfg, cfgt.optim.kfac.lr.schedule)
+    loss_fn = loss.make_loss_fn(model.apply, system)
+    for it in range(2):
+        _, g = loss_fn(state.params, state.data)
+        p_ref_next = ok.step(state.params.double().cpu(), g.double().cpu(), state.data.double().cpu())
+        prev = state.params
+        state, stats = step(state, None)
+        upd, upd_ref = (state.params - prev).double().cpu(), p_ref_next - prev.double().cpu()
+        assert torch.isfinite(upd).all() and upd.norm() > 0
+        assert (upd - upd_ref).norm() / upd_ref.norm() < 5e-3, (it, ((upd - upd_ref).norm() / upd_ref.norm()).item())
 
 
 def test_kfac_factor_pass_reuses_the_vjp_forward(nat):
