@@ -61,6 +61,8 @@ CONFIGS = {
     "c4": dict(nspins=(10, 0), flux=21),
     "c5k4": dict(nspins=(16, 0), flux=45, ndets=4),
     "odd": dict(nspins=(5, 0), flux=11, ndets=3, num_heads=2, heads_dim=48, num_layers=1),
+    # head size 64 with a model width other than 256: the tensor-core attention's run-time-stride instantiation
+    "d128": dict(nspins=(6, 0), flux=15, num_heads=2, heads_dim=64, num_layers=2),
     # spin-unpolarised systems: one (re, im) pair of orbital projections per spin block
     # (blocks.py:29-34), spin feature -1 for the down electrons (psiformer.py:81), ee_anti Jastrow (blocks.py:99-105)
     "spin32": dict(nspins=(3, 2), flux=8, ndets=2),
@@ -71,7 +73,7 @@ CONFIGS = {
 }
 # walkers per parity case: >= 256 for the BASELINE configs c1-c4, 64 for c5 K=4 (the fp64 oracle's forward-Laplacian pass takes
 # ~25 s for 256 walkers at c3 on 8 cores)
-SIZES = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5k4": 64, "odd": 33, "spin32": 40, "spin11": 64, "sparse": 40,
+SIZES = {"c1": 256, "c2": 256, "c3": 256, "c4": 256, "c5k4": 64, "odd": 33, "d128": 48, "spin32": 40, "spin11": 64, "sparse": 40,
          "sparse_spin": 40}
 BASELINE_CONFIGS = ("c1", "c2", "c3", "c4", "c5k4")
 # Tail bounds of the per-walker error distributions for the BASELINE configs, from the measured distributions in
