@@ -49,7 +49,7 @@ constexpr int EPI_CHUNK = 32;                            // accumulator columns 
 constexpr int EPI_BUF_BYTES = 32 * EPI_CHUNK * 4;        // 32 rows x 32 floats = 4 KB (one warp, one step)
 constexpr int EPI_WARPS = 8;                             // two per TMEM lane quarter, alternating 32-column chunks
 constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES;     // one staging buffer per warp = 32 KB
-constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr int SMEM_BYTES = RING_BYTES + EPI_BYTES + 512 /*barriers*/;  // (the window is 1024-byte aligned: no slack)
 constexpr int SPLIT_WARPS = 8;
 constexpr int EPI_WARP0 = 2 + SPLIT_WARPS;  // first epilogue warp
 constexpr int THREADS = 32 * (EPI_WARP0 + EPI_WARPS);  // 576
@@ -341,8 +341,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int STAGE_BYTES = 2 * AP_BYTES + 2 * B_BYTES;
   static_assert(STAGES * STAGE_BYTES == RING_BYTES && 2 * AP_BYTES >= A_BYTES, "operand ring geometry");
   constexpr int A_TX_BYTES = A_BYTES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // The dynamic shared-memory window is declared 1024-byte aligned (the operand tiles' swizzle atoms need it), so no slack
+  // is allocated for rounding the base up: with 230,912 bytes + the 1 KB the system reserves per block, one 128-thread
+  // block without shared memory of ANOTHER launch still fits the SM's 228 KB next to this CTA -- the LayerNorm kernels of the
+  // other chunk stream run in the contraction's shadow on the registers and threads it leaves free.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* smem = smem_raw;
   uint8_t* epi_smem = smem + RING_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_BYTES);
   // bars: [0..S) full, [S..2S) split, [2S..3S) empty, [3S] tmem_full, [3S+1] tmem_empty ; then tmem ptr
@@ -1097,7 +1102,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 gemm_tn_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmC, int64_t rows, int nblk_n, int ksplit,
                   const float* __restrict__ a_scale_ptr, const float* __restrict__ b_scale_ptr) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // [landing: 2 stages x (A 32 KB | B 32 KB)] [operands: A hi | A lo | B hi | B lo, 16 KB each] [epilogue staging] [barriers]
   uint8_t* land = smem;

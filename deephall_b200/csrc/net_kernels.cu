@@ -184,8 +184,10 @@ __device__ __forceinline__ float tanh_fast(float x) {
 
 // VEC4 (D = 256, 16-byte aligned tensors): lane l owns columns 4l..4l+3 and 128+4l..128+4l+3, moved as two
 // float4 per row (512-byte requests); otherwise lane l owns columns l, l+32, ...
+// (at most 80 registers: a block of this kernel fits next to a persistent contraction CTA of the other chunk stream,
+// 576 threads x 96 registers, see gemm_tc.cu)
 template <bool TANH, bool VEC4>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 residual_layernorm_kernel(const float* __restrict__ a, const float* __restrict__ b,
                           const float* __restrict__ scale, const float* __restrict__ bias,
                           float* __restrict__ out, int64_t groups, NetDims dm, int a_comp, int a_pl, int o_pl) {
