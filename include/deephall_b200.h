@@ -213,7 +213,8 @@ int dh_plan_status_copy(dh_plan* plan, uint32_t* dst_device, void* stream);
 /* Curvature statistics for KFAC with the reference's registration (loss.py:98: a unit-variance normal predictive
  * distribution on Re log psi, `fisher_exact`): one forward + one reverse pass with cotangent (1, 0) per walker.
  * dh_kfac_layout: entries == NULL -> *n = number of blocks; *factor_floats = length of the factor vector.
- * dh_kfac_factors overwrites `factors` (factor_floats floats) with the sums described at dh_kfac_entry.
+ * dh_kfac_factors overwrites `factors` (factor_floats floats) with the sums described at dh_kfac_entry (full and sparse
+ * orbitals; DH_E_UNSUPPORTED for the parameter-free Laughlin network and for sparse orbitals with 8 N K > 3 D).
  * Workspace: DH_OP_KFAC.  Not available for the Laughlin network (no parameters) and sparse orbitals. */
 int dh_kfac_layout(const dh_plan* plan, dh_kfac_entry* entries, int32_t* n, int64_t* factor_floats);
 int dh_kfac_factors(dh_plan* plan, const float* params, const float* x, int64_t B, float* factors, void* ws,
@@ -232,7 +233,7 @@ int dh_kfac_factors_reuse_forward(dh_plan* plan, const float* params, const floa
  *   dh_kfac_update_shape    -> number and padded size of the damped Kronecker factors in the "small" (<= 288 rows) and the
  *                              "large" batch, the number of dense blocks and the floats of one gather buffer.  First call
  *                              builds the plan's descriptor tables (allocates; later calls and the two ops below do not).
- *                              DH_E_UNSUPPORTED: a factor has more than 1024 rows, sparse orbitals, Laughlin.
+ *                              DH_E_UNSUPPORTED: a factor has more than 1024 rows, Laughlin.
  *   dh_kfac_damped_factors  -> coef [8 n_blocks] = {tr_avg(A), tr_avg(G), d, c_k, ok, -, -, -} per block and every
  *                              A / tr_avg(A) + d I, G / tr_avg(G) + d I (kfac_jax's pi-adjusted damping with average-trace
  *                              norms, d = sqrt(damping / rows_per_walker / (tr_avg(A) tr_avg(G)))), each embedded as
